@@ -1,0 +1,134 @@
+/*
+ * varnet_b200.h — C ABI of the B200-native weak-form residual + gradient engine.
+ *
+ * This is the drop-in boundary for the reference's compute backend, the `TFNN`
+ * object (`/root/reference/TFModel.py:54-437`) that `VarNet` holds as `tfData`
+ * (`VarNet.py:201-203`) and drives through `sess.run(nodes, feed_dict)`
+ * (`VarNetUtility.py:1044,1080,1086,1142`).  The reference has no FFI; the entry
+ * points below are what a ctypes binding of that object needs (see INTEGRATION.md
+ * and varnet_b200/_capi.py).  One handle = one GPU = one reference "tower"
+ * (`TFModel.py:253-289`).
+ *
+ * Conventions: every function returns 0 on success or a negative VN_E_* code and
+ * never throws; `vn_last_error` gives the message.  Host pointers are caller-owned
+ * and only read/written during the call.  All work is enqueued on the handle's
+ * stream (`vn_set_stream`); calls that return host data synchronise that stream.
+ * Arithmetic is FP32 (the reference's placeholders are tf.float32,
+ * TFModel.py:531,602-620); `*_f64` uploads round to FP32 exactly like the feed cast.
+ */
+#ifndef VARNET_B200_H
+#define VARNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VN_MAX_LAYERS 8      /* hidden layers */
+#define VN_MAX_INPDIM 8      /* dim + time + MOR parameters (VarNet.py:174-180) */
+
+#define VN_ACT_SIGMOID 0     /* VarNet.py:162-164 default */
+#define VN_ACT_TANH 1
+
+#define VN_OPT_ADAM 0        /* tf.train.AdamOptimizer, TFModel.py:184 */
+#define VN_OPT_RMSPROP 1     /* tf.train.RMSPropOptimizer, TFModel.py:186 */
+
+#define VN_OK 0
+#define VN_E_INVALID -1      /* bad argument (mirrors the reference's ValueError sites) */
+#define VN_E_CUDA -2         /* CUDA runtime error */
+#define VN_E_STATE -3        /* call order violated, e.g. loss before upload (VarNetUtility.py:1031) */
+#define VN_E_UNSUPPORTED -4  /* network shape outside the compiled kernel families */
+
+typedef struct vn_engine vn_engine;
+
+/* Mirrors the TFNN constructor arguments that shape the graph (TFModel.py:85-86). */
+typedef struct vn_config {
+    int32_t dim;                       /* spatial dimension (1 or 2) */
+    int32_t inpDim;                    /* MLP inputs: x, [t], MOR params (TFModel.py:517-518) */
+    int32_t nLayers;                   /* number of hidden Dense layers */
+    int32_t widths[VN_MAX_LAYERS];     /* layerWidth */
+    int32_t act;                       /* VN_ACT_* (same for all hidden layers) */
+    int32_t timeDependent;             /* TFModel.py:537,646,655 */
+    int32_t isSource;                  /* lossOpt['isSource']   (TFModel.py:656) */
+    int32_t integWflag;                /* lossOpt['integWflag'] (TFModel.py:660) */
+    int32_t optimizer;                 /* VN_OPT_* */
+    int32_t device;                    /* CUDA device ordinal */
+} vn_config;
+
+/* ---- lifetime ------------------------------------------------------------- */
+int vn_create(const vn_config* cfg, vn_engine** out);
+int vn_destroy(vn_engine* e);
+const char* vn_last_error(void);
+int vn_set_stream(vn_engine* e, void* cuda_stream);          /* cudaStream_t; NULL = default */
+int vn_synchronize(vn_engine* e);
+
+/* ---- parameters: flat Keras order, per layer kernel[in,out] row-major then bias;
+ *      last is Dense(1) 'output' (TFModel.py:208-242).  Replaces tf.train.Saver /
+ *      sess.run(tf.trainable_variables()) (VarNet.py:1362,2197-2239). */
+int vn_param_count(const vn_engine* e, int64_t* n);
+int vn_set_params(vn_engine* e, const float* theta, int64_t n);   /* also resets optimizer state */
+int vn_get_params(vn_engine* e, float* theta, int64_t n);
+int vn_get_optimizer_state(vn_engine* e, float* m, float* v, int64_t n, int64_t* step);
+int vn_set_optimizer_state(vn_engine* e, const float* m, const float* v, int64_t n, int64_t step);
+
+/* ---- per-tower feed (VarNetUtility.py:840-854).  Row-major host arrays exactly as
+ *      the reference feeds them: Input[P,inpDim], gcoef[P,dim], source[P,1] or NULL,
+ *      N[P,1] or NULL, dNt[P,1] or NULL; P = nb*integNum rows grouped test-function
+ *      major.  integW[integNum] or NULL.  detJ: 1 value, or nb values when
+ *      detJ_is_vector (the `detJvec` branch, TFModel.py:662-664).
+ *      Data become device-resident; re-upload only when the caller changes them. */
+int vn_upload_points_f32(vn_engine* e, const float* Input, const float* gcoef, const float* source,
+                         const float* N, const float* dNt, int64_t nb, int32_t integNum,
+                         const float* integW, const float* detJ, int32_t detJ_is_vector);
+int vn_upload_points_f64(vn_engine* e, const double* Input, const double* gcoef, const double* source,
+                         const double* N, const double* dNt, int64_t nb, int32_t integNum,
+                         const double* integW, const double* detJ, int32_t detJ_is_vector);
+/* biInput[nbi,inpDim], biLabel[nbi,1]; rows [0,bDof) are boundary rows, the rest
+ * initial-condition rows (TFModel.py:643-650). */
+int vn_upload_bic_f32(vn_engine* e, const float* biInput, const float* biLabel, int64_t nbi,
+                      int64_t bDof, float biDimVal);
+int vn_upload_bic_f64(vn_engine* e, const double* biInput, const double* biLabel, int64_t nbi,
+                      int64_t bDof, double biDimVal);
+/* loss weights w[3] = [BC, IC, variational] (TFModel.py:666); device-resident so a
+ * captured step graph sees updates. */
+int vn_set_weights(vn_engine* e, const float w[3]);
+
+/* ---- the hot path ----------------------------------------------------------
+ * vn_loss:       forward only.  out[4] = {loss, BCloss, ICloss, varLoss}
+ *                (TFModel.py:666,686-688); lossVec (nb floats, TFModel.py:668) may be NULL.
+ * vn_loss_grad:  loss + d loss / d theta (NNModel.computeGrad, TFModel.py:695-714).
+ *                Results stay on the device in the gradient buffer
+ *                [grad(nparam) | loss, BCloss, ICloss, varLoss]; this is the buffer a
+ *                multi-GPU caller all-reduces (SUM), mirroring TFNN.sum_grads
+ *                (TFModel.py:342-377).  out may be NULL (no host sync).
+ * vn_optimizer_step: TF-1.x Adam / RMSProp update from the gradient buffer
+ *                (optimizer.apply_gradients, TFModel.py:313).
+ * vn_train_step: loss_grad + optimizer_step in one call = one
+ *                sess.run([optMinimize, loss]) (VarNetUtility.py:1044); single-GPU. */
+int vn_loss(vn_engine* e, float out[4], float* lossVec);
+int vn_loss_grad(vn_engine* e, float out[4]);
+int vn_grad_buffer(vn_engine* e, void** device_ptr, int64_t* n_floats);
+int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]);
+int vn_optimizer_step(vn_engine* e, float lr);
+int vn_train_step(vn_engine* e, float lr, float* loss_out);
+
+/* ---- evaluation (VarNetUtility.runSession, VarNetUtility.py:1098-1142)
+ * vn_eval:     u = model(X), X[n,inpDim] host row-major, u[n].
+ * vn_residual: strong-form residual  res = -u_t + kappa*Lap u - (vel - grad kappa).grad u + s
+ *              (NNModel.Residual, TFModel.py:718-772).  diff[n], vel[n,dim],
+ *              diff_dx[n,dim], source[n]; u and res are [n] (u may be NULL). */
+int vn_eval_f32(vn_engine* e, const float* X, int64_t n, float* u);
+int vn_eval_f64(vn_engine* e, const double* X, int64_t n, float* u);
+int vn_residual_f64(vn_engine* e, const double* X, const double* diff, const double* vel,
+                    const double* diff_dx, const double* source, int64_t n, float* u, float* res);
+
+/* ---- introspection for tests / bench --------------------------------------- */
+int vn_kernel_info(const vn_engine* e, char* buf, size_t buflen);   /* kernel family, tile, smem */
+int64_t vn_launch_count(const vn_engine* e);                         /* kernels launched so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VARNET_B200_H */

@@ -1,0 +1,100 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the FP64 oracle on identical seeded feeds.
+
+Tolerance (BASELINE.json north_star): 1e-5 relative in FP32 for the loss, each loss component, the
+lossVec field (max-norm relative) and each gradient tensor (||d||inf / ||g||inf)."""
+import numpy as np
+import pytest
+
+from oracle import graph_oracle as go
+from tests.util import synth_feed, make_engine, rel_inf, layer_slices
+
+TOL = 1e-5
+
+CASES = [
+    # dim inpDim layers          act       td     src    iw     dvec   nb   integNum nbi bDof
+    (1, 2, [20], "sigmoid", True, False, False, False, 300, 16, 62, 40),            # Operator_1Dt shape
+    (2, 3, [10, 20], "sigmoid", True, False, False, False, 150, 64, 212, 180),      # Operator_2Dt shape
+    (1, 3, [10, 20, 30], "sigmoid", True, False, False, False, 250, 16, 175, 160),  # Operator_1DtMOR shape
+    (2, 3, [64, 64, 64, 64], "tanh", True, False, False, False, 100, 64, 300, 200), # synthetic 2D+t scale-up net
+    (2, 3, [16, 16, 16, 16], "tanh", True, True, False, False, 37, 64, 100, 77),    # width sweep 16 + source
+    (1, 2, [20], "tanh", True, True, True, False, 41, 36, 50, 33),                  # integPnum=3 (integNum=36, weights)
+    (2, 2, [12, 7], "sigmoid", False, True, False, False, 53, 16, 60, 60),          # steady 2D, no IC rows
+    (2, 3, [24, 24], "tanh", True, False, True, True, 19, 216, 90, 50),             # integPnum=3 2D+t, vector detJ
+    (1, 1, [9], "sigmoid", False, False, False, False, 77, 4, 2, 2),                # steady 1D, tiny
+    (2, 5, [33, 40, 64], "sigmoid", True, True, False, True, 29, 64, 129, 100),     # MOR-like extra inputs, ragged widths
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[str(c[2]) + c[3] + ("_d%d" % c[0]) for c in CASES])
+def test_loss_and_grad_match_oracle(case):
+    dim, inpDim, lw, act, td, src, iw, dvec, nb, integNum, nbi, bDof = case
+    rng = np.random.RandomState(1234 + nb)
+    feed = synth_feed(rng, dim, inpDim, nb, integNum, nbi, bDof, td, src, iw, dvec)
+    theta = go.glorot_init(inpDim, lw, seed=7) + 0.05 * rng.randn(go.param_count(inpDim, lw)).astype(np.float32)
+    lossOpt = dict(isSource=src, integWflag=iw)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation=act, timeDependent=td, lossOpt=lossOpt)
+    ref = go.loss_and_grad(theta, feed, **kw)
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        fwd = eng.loss(lossVec=True)
+        for k in ("loss", "BCloss", "ICloss", "varLoss"):
+            assert abs(float(fwd[k]) - ref[k]) <= TOL * abs(ref[k]) + 1e-30, (k, fwd[k], ref[k])
+        assert rel_inf(fwd["lossVec"], ref["lossVec"]) <= TOL
+        out = eng.loss_grad()
+        for k in ("loss", "BCloss", "ICloss", "varLoss"):
+            assert abs(float(out[k]) - ref[k]) <= TOL * abs(ref[k]) + 1e-30, (k, out[k], ref[k])
+        for name, sl in layer_slices(inpDim, lw):
+            assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
+        assert eng.launch_count() > 0
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_eval_matches_oracle():
+    rng = np.random.RandomState(5)
+    inpDim, lw = 3, [64, 64, 64, 64]
+    theta = go.glorot_init(inpDim, lw, seed=1)
+    from varnet_b200._capi import Engine
+    eng = Engine(2, inpDim, lw, "tanh", True)
+    eng.set_params(theta)
+    X = rng.uniform(-1, 1, (1000, inpDim))
+    u = eng.eval(X)
+    ref = go.mlp_value(theta.astype(np.float64), X.astype(np.float32).astype(np.float64), inpDim, lw, go.ACT_TANH)
+    assert rel_inf(u, ref) <= TOL
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_f32_and_f64_uploads_agree_bitwise():
+    rng = np.random.RandomState(11)
+    feed = synth_feed(rng, 1, 2, 64, 16, 40, 30)
+    lw = [20]
+    theta = go.glorot_init(2, lw, seed=2)
+    kw = dict(dim=1, inpDim=2, layerWidth=lw, activation="sigmoid", timeDependent=True,
+              lossOpt=dict(isSource=False, integWflag=False))
+    e64 = make_engine(feed, theta=theta, dtype=np.float64, **kw)
+    e32 = make_engine(feed, theta=theta, dtype=np.float32, **kw)
+    a, b = e64.loss_grad(), e32.loss_grad()
+    assert np.array_equal(a["grad"], b["grad"]) and a["loss"] == b["loss"]
+    e64.close(); e32.close()
+
+
+@pytest.mark.gpu
+def test_adam_matches_tf_formula():
+    rng = np.random.RandomState(3)
+    feed = synth_feed(rng, 1, 2, 128, 16, 40, 30)
+    lw = [20]
+    theta = go.glorot_init(2, lw, seed=4)
+    kw = dict(dim=1, inpDim=2, layerWidth=lw, activation="sigmoid", timeDependent=True,
+              lossOpt=dict(isSource=False, integWflag=False))
+    eng = make_engine(feed, theta=theta, **kw)
+    th = theta.astype(np.float64); m = np.zeros_like(th); v = np.zeros_like(th)
+    for t in range(1, 6):
+        ref = go.loss_and_grad(th.astype(np.float32), feed, **kw)
+        loss = eng.train_step(1e-3)
+        assert abs(float(loss) - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+        th, m, v = go.adam_step(th, ref["grad"], m, v, t, lr=1e-3)
+        assert rel_inf(eng.get_params(), th) <= 2e-5
+    eng.close()

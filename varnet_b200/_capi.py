@@ -1,0 +1,283 @@
+"""ctypes binding of include/varnet_b200.h (the C-ABI drop-in boundary).
+
+There is no CPU implementation behind this module: if the shared library is
+missing or no CUDA device is visible the calls raise — they never fall back.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvarnet_b200.so")
+
+VN_MAX_LAYERS = 8
+VN_MAX_INPDIM = 8
+ACT_IDS = {"sigmoid": 0, "tanh": 1}
+OPT_IDS = {"adam": 0, "rmsprop": 1, "rms": 1}
+
+# name -> (restype, argtypes); mirrors include/varnet_b200.h one to one
+_f32p, _f64p, _vp = C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p
+_i64, _i32 = C.c_int64, C.c_int32
+
+
+class vn_config(C.Structure):
+    _fields_ = [("dim", _i32), ("inpDim", _i32), ("nLayers", _i32), ("widths", _i32 * VN_MAX_LAYERS),
+                ("act", _i32), ("timeDependent", _i32), ("isSource", _i32), ("integWflag", _i32),
+                ("optimizer", _i32), ("device", _i32)]
+
+
+SIGNATURES = {
+    "vn_create": (C.c_int, [C.POINTER(vn_config), C.POINTER(_vp)]),
+    "vn_destroy": (C.c_int, [_vp]),
+    "vn_last_error": (C.c_char_p, []),
+    "vn_set_stream": (C.c_int, [_vp, _vp]),
+    "vn_synchronize": (C.c_int, [_vp]),
+    "vn_param_count": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "vn_set_params": (C.c_int, [_vp, _f32p, _i64]),
+    "vn_get_params": (C.c_int, [_vp, _f32p, _i64]),
+    "vn_get_optimizer_state": (C.c_int, [_vp, _f32p, _f32p, _i64, C.POINTER(_i64)]),
+    "vn_set_optimizer_state": (C.c_int, [_vp, _f32p, _f32p, _i64, _i64]),
+    "vn_upload_points_f32": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _i32]),
+    "vn_upload_points_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32]),
+    "vn_upload_bic_f32": (C.c_int, [_vp, _f32p, _f32p, _i64, _i64, C.c_float]),
+    "vn_upload_bic_f64": (C.c_int, [_vp, _f64p, _f64p, _i64, _i64, C.c_double]),
+    "vn_set_weights": (C.c_int, [_vp, _f32p]),
+    "vn_loss": (C.c_int, [_vp, _f32p, _f32p]),
+    "vn_loss_grad": (C.c_int, [_vp, _f32p]),
+    "vn_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "vn_get_grad": (C.c_int, [_vp, _f32p, _i64, _f32p]),
+    "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
+    "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
+    "vn_eval_f32": (C.c_int, [_vp, _f32p, _i64, _f32p]),
+    "vn_eval_f64": (C.c_int, [_vp, _f64p, _i64, _f32p]),
+    "vn_residual_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _f32p, _f32p]),
+    "vn_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "vn_launch_count": (_i64, [_vp]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("varnet_b200 engine error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen the engine and bind every symbol of the header.  Raises if absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError("%s not found: build it with `python -m varnet_b200.build` "
+                          "(the CUDA engine has no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _prep(a, dtype, shape=None):
+    """Feed values as the reference passes them (arrays, scalars, None, [[None]])."""
+    if a is None:
+        return None
+    arr = np.asarray(a)
+    if arr.dtype == object or arr.size == 0:
+        return None
+    arr = np.ascontiguousarray(arr, dtype=dtype)
+    if shape is not None:
+        arr = arr.reshape(shape)
+    return arr
+
+
+class Engine:
+    """One GPU-resident tower: owns weights, optimizer state and the uploaded tables."""
+
+    def __init__(self, dim, inpDim, layerWidth, activation="sigmoid", timeDependent=True, isSource=False,
+                 integWflag=False, optimizer="adam", device=0):
+        self.lib = load_library()
+        if isinstance(activation, (list, tuple)):
+            if len(set(a.lower() for a in activation)) != 1:
+                raise ValueError("a single activation function for all hidden layers is supported")
+            activation = activation[0]
+        if activation.lower() not in ACT_IDS:
+            raise ValueError("unknown activation function '%s'" % activation)
+        if optimizer.lower() not in OPT_IDS:
+            raise ValueError("unknown optimizer requested!")
+        if len(layerWidth) > VN_MAX_LAYERS:
+            raise ValueError("at most %d hidden layers are supported" % VN_MAX_LAYERS)
+        cfg = vn_config()
+        cfg.dim, cfg.inpDim, cfg.nLayers = int(dim), int(inpDim), len(layerWidth)
+        for i, w in enumerate(layerWidth):
+            cfg.widths[i] = int(w)
+        cfg.act = ACT_IDS[activation.lower()]
+        cfg.timeDependent, cfg.isSource, cfg.integWflag = int(bool(timeDependent)), int(bool(isSource)), int(bool(integWflag))
+        cfg.optimizer, cfg.device = OPT_IDS[optimizer.lower()], int(device)
+        self.cfg = cfg
+        self.dim, self.inpDim, self.layerWidth = int(dim), int(inpDim), [int(w) for w in layerWidth]
+        self.timeDependent = bool(timeDependent)
+        self._h = _vp()
+        self._check(self.lib.vn_create(C.byref(cfg), C.byref(self._h)))
+        n = _i64()
+        self._check(self.lib.vn_param_count(self._h, C.byref(n)))
+        self.nparam = int(n.value)
+        self.nb = 0
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(rc, self.lib.vn_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.vn_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.vn_set_stream(self._h, _vp(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.vn_synchronize(self._h))
+
+    # -- parameters
+    def set_params(self, theta):
+        th = np.ascontiguousarray(theta, dtype=np.float32).ravel()
+        self._check(self.lib.vn_set_params(self._h, _ptr(th, C.c_float), th.size))
+
+    def get_params(self):
+        th = np.empty(self.nparam, dtype=np.float32)
+        self._check(self.lib.vn_get_params(self._h, _ptr(th, C.c_float), th.size))
+        return th
+
+    def get_optimizer_state(self):
+        m = np.empty(self.nparam, dtype=np.float32); v = np.empty_like(m); st = _i64()
+        self._check(self.lib.vn_get_optimizer_state(self._h, _ptr(m, C.c_float), _ptr(v, C.c_float), m.size, C.byref(st)))
+        return m, v, int(st.value)
+
+    def set_optimizer_state(self, m, v, step):
+        m = np.ascontiguousarray(m, dtype=np.float32); v = np.ascontiguousarray(v, dtype=np.float32)
+        self._check(self.lib.vn_set_optimizer_state(self._h, _ptr(m, C.c_float), _ptr(v, C.c_float), m.size, int(step)))
+
+    # -- feeds
+    def upload_points(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None):
+        nb, integNum = int(intShape[0]), int(intShape[1])
+        P = nb * integNum
+        if dtype is None:
+            dtype = np.float32 if np.asarray(Input).dtype == np.float32 else np.float64
+        X = _prep(Input, dtype, (P, self.inpDim))
+        G = _prep(gcoef, dtype, (P, self.dim))
+        S = _prep(source, dtype, (P,)) if self.cfg.isSource else None
+        Nn = _prep(N, dtype, (P,)) if self.cfg.isSource else None
+        T = _prep(dNt, dtype, (P,)) if self.cfg.timeDependent else None
+        W = _prep(integW, dtype) if self.cfg.integWflag else None
+        if W is not None:
+            W = W.reshape(-1)
+            if W.size != integNum:
+                raise ValueError("integW must hold integNum=%d weights" % integNum)
+        D = _prep(detJ, dtype)
+        D = D.reshape(-1)
+        if detJvec and D.size != nb:
+            raise ValueError("vector detJ must hold one value per test function")
+        ct = C.c_float if dtype == np.float32 else C.c_double
+        fn = self.lib.vn_upload_points_f32 if dtype == np.float32 else self.lib.vn_upload_points_f64
+        self._check(fn(self._h, _ptr(X, ct), _ptr(G, ct), _ptr(S, ct), _ptr(Nn, ct), _ptr(T, ct), nb, integNum,
+                       _ptr(W, ct), _ptr(D, ct), int(bool(detJvec))))
+        self.nb = nb
+
+    def upload_bic(self, biInput, biLabel, bDof, biDimVal, dtype=None):
+        if dtype is None:
+            dtype = np.float32 if np.asarray(biInput).dtype == np.float32 else np.float64
+        bX = _prep(biInput, dtype)
+        bX = bX.reshape(-1, self.inpDim)
+        bL = _prep(biLabel, dtype, (bX.shape[0],))
+        ct = C.c_float if dtype == np.float32 else C.c_double
+        if dtype == np.float32:
+            self._check(self.lib.vn_upload_bic_f32(self._h, _ptr(bX, ct), _ptr(bL, ct), bX.shape[0], int(bDof), float(np.float32(biDimVal))))
+        else:
+            self._check(self.lib.vn_upload_bic_f64(self._h, _ptr(bX, ct), _ptr(bL, ct), bX.shape[0], int(bDof), float(biDimVal)))
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).astype(np.float32).reshape(3))
+        self._check(self.lib.vn_set_weights(self._h, _ptr(w, C.c_float)))
+
+    # -- hot path
+    def loss(self, lossVec=False):
+        out = np.empty(4, dtype=np.float32)
+        lv = np.empty(self.nb, dtype=np.float32) if lossVec else None
+        self._check(self.lib.vn_loss(self._h, _ptr(out, C.c_float), _ptr(lv, C.c_float)))
+        res = dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3])
+        if lossVec:
+            res["lossVec"] = lv
+        return res
+
+    def loss_grad(self, fetch=True):
+        if not fetch:
+            self._check(self.lib.vn_loss_grad(self._h, None))
+            return None
+        self._check(self.lib.vn_loss_grad(self._h, None))
+        g = np.empty(self.nparam, dtype=np.float32); out = np.empty(4, dtype=np.float32)
+        self._check(self.lib.vn_get_grad(self._h, _ptr(g, C.c_float), g.size, _ptr(out, C.c_float)))
+        return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3], grad=g)
+
+    def grad_buffer(self):
+        p = _vp(); n = _i64()
+        self._check(self.lib.vn_grad_buffer(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def optimizer_step(self, lr):
+        self._check(self.lib.vn_optimizer_step(self._h, float(lr)))
+
+    def train_step(self, lr, fetch_loss=True):
+        if fetch_loss:
+            out = C.c_float()
+            self._check(self.lib.vn_train_step(self._h, float(lr), C.byref(out)))
+            return np.float32(out.value)
+        self._check(self.lib.vn_train_step(self._h, float(lr), None))
+        return None
+
+    # -- evaluation
+    def eval(self, X):
+        X = np.asarray(X)
+        dtype = np.float32 if X.dtype == np.float32 else np.float64
+        X = np.ascontiguousarray(X, dtype=dtype).reshape(-1, self.inpDim)
+        u = np.empty(X.shape[0], dtype=np.float32)
+        if dtype == np.float32:
+            self._check(self.lib.vn_eval_f32(self._h, _ptr(X, C.c_float), X.shape[0], _ptr(u, C.c_float)))
+        else:
+            self._check(self.lib.vn_eval_f64(self._h, _ptr(X, C.c_double), X.shape[0], _ptr(u, C.c_float)))
+        return u
+
+    def residual(self, X, diff, vel, diff_dx, source):
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.inpDim)
+        n = X.shape[0]
+        d = np.ascontiguousarray(np.broadcast_to(np.asarray(diff, dtype=np.float64).reshape(-1, 1), (n, 1)))
+        v = np.ascontiguousarray(np.asarray(vel, dtype=np.float64).reshape(n, self.dim))
+        dd = np.ascontiguousarray(np.asarray(diff_dx, dtype=np.float64).reshape(n, self.dim))
+        s = np.ascontiguousarray(np.broadcast_to(np.asarray(source, dtype=np.float64).reshape(-1, 1), (n, 1)))
+        u = np.empty(n, dtype=np.float32); r = np.empty(n, dtype=np.float32)
+        self._check(self.lib.vn_residual_f64(self._h, _ptr(X, C.c_double), _ptr(d, C.c_double), _ptr(v, C.c_double),
+                                             _ptr(dd, C.c_double), _ptr(s, C.c_double), n, _ptr(u, C.c_float), _ptr(r, C.c_float)))
+        return u, r
+
+    def kernel_info(self):
+        buf = C.create_string_buffer(1024)
+        self._check(self.lib.vn_kernel_info(self._h, buf, 1024))
+        return buf.value.decode()
+
+    def launch_count(self):
+        return int(self.lib.vn_launch_count(self._h))

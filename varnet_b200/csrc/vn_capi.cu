@@ -1,0 +1,747 @@
+// vn_capi.cu — C ABI (include/varnet_b200.h) + the small reduction / optimizer / packing kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/varnet_b200.h"
+#include "vn_dispatch.h"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(VN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* vn_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------ dispatch over width classes
+bool vn_tile_geometry(int S, int wclass, int act, int mode, int L, TileGeom* g) {
+    if (wclass == 32) return vn_geom_w32(S, act, mode, L, g);
+    if (wclass == 64) return vn_geom_w64(S, act, mode, L, g);
+    return false;
+}
+cudaError_t vn_tile_launch(int S, int wclass, int act, int mode, const TileArgs& a, int grid, size_t smem,
+                           cudaStream_t st) {
+    if (wclass == 32) return vn_launch_w32(S, act, mode, a, grid, smem, st);
+    if (wclass == 64) return vn_launch_w64(S, act, mode, a, grid, smem, st);
+    return cudaErrorInvalidValue;
+}
+cudaError_t vn_tile_prepare(int S, int wclass, int act, int mode, size_t smem) {
+    if (wclass == 32) return vn_prepare_w32(S, act, mode, smem);
+    if (wclass == 64) return vn_prepare_w64(S, act, mode, smem);
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ small kernels
+// One thread per test function: R_i = sum_q Iw[i,q] (TFModel.py:659-661), lossVec_i = detJ_i R_i^2
+// (:668); FP64 block partials of sum_i detJ_i R_i^2 (detJvec) or sum_i R_i^2 (scalar detJ, :662-664).
+__global__ void vn_segreduce_kernel(SegArgs A) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double term = 0.0;
+    if (i < A.nb) {
+        const float* row = A.Iw + (size_t)i * A.integNum;
+        float r = 0.f;
+        if ((A.integNum & 3) == 0) {
+            for (unsigned int q = 0; q < A.integNum; q += 4) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(row + q));
+                r += v.x; r += v.y; r += v.z; r += v.w;
+            }
+        } else {
+            for (unsigned int q = 0; q < A.integNum; ++q) r += __ldg(row + q);
+        }
+        const float r2 = r * r;
+        const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+        A.R[i] = r;
+        A.lossVec[i] = dj * r2;
+        term = A.detJvec ? (double)dj * (double)r2 : (double)r2;
+    }
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = term;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) A.blockSum[blockIdx.x] = v;
+    }
+}
+
+__device__ static double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;   // valid in thread 0
+}
+
+// Blocks [0, gridDim.x-1): one thread per flat parameter sums the per-CTA FP64 slabs in a fixed
+// order (deterministic replacement for TF's gradient accumulation).  Last block: the loss scalars
+// loss = w0*bCs + w1*iCs + w2*varLoss (TFModel.py:643-666).
+__global__ void vn_finalize_kernel(FinalArgs A) {
+    const NetDesc& net = A.net;
+    const PartLayout& pl = A.pl;
+    if (blockIdx.x + 1 < gridDim.x) {
+        if (!A.needGrad) return;
+        const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= net.nparam) return;
+        // locate (layer, kind, i, j)
+        int l = 0, isBias = 0, i = 0, j = 0;
+        for (l = 0; l <= net.L; ++l) {
+            const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+            const int wo = l == net.L ? 1 : net.width[l];
+            if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { i = (idx - net.woff[l]) / wo; j = (idx - net.woff[l]) - i * wo; break; }
+            if (idx >= net.boff[l] && idx < net.boff[l] + wo) { isBias = 1; j = idx - net.boff[l]; break; }
+        }
+        int slot[8], nslot = 1;
+        if (l == net.L) {
+            if (isBias) slot[0] = pl.off_bout;
+            else { nslot = pl.NT / pl.WP; for (int p = 0; p < nslot; ++p) slot[p] = pl.off_wout + i + pl.WP * p; }
+        } else if (isBias) {
+            slot[0] = pl.off_gb[l] + (j % pl.NJG) * pl.TJ + j / pl.NJG;
+        } else {
+            const int ig = i & 7, t = i >> 3, jg = j % pl.NJG, u = j / pl.NJG;
+            const int tid = (jg >> 2) * 32 + ig + 8 * (jg & 3);
+            slot[0] = pl.off_gw[l] + (l == 0 ? tid * pl.TJ + u : tid * (pl.TI * pl.TJ) + t * pl.TJ + u);
+        }
+        double s = 0.0;
+        for (int p = 0; p < nslot; ++p) {
+            for (int c = 0; c < A.nVar; ++c) s += A.partVar[(size_t)c * pl.psz + slot[p]];
+            for (int c = 0; c < A.nBic; ++c) s += A.partBic[(size_t)c * pl.psz + slot[p]];
+        }
+        A.gbuf[idx] = (float)s;
+        return;
+    }
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int k = threadIdx.x; k < A.nSeg; k += blockDim.x) v += A.segSum[k];
+    const double segTot = block_sum(v, sh);
+    double vb = 0.0, vi = 0.0;
+    for (unsigned int k = threadIdx.x; k < A.nbi; k += blockDim.x) {
+        const double c = (double)A.cj[k];
+        if (k < A.bDof) vb += c; else vi += c;
+    }
+    const double sb = block_sum(vb, sh);
+    const double si = block_sum(vi, sh);
+    if (threadIdx.x == 0) {
+        const float varLoss = A.detJvec ? (float)segTot : A.detJ[0] * (float)segTot;   // detJ moved outside the sum (:664)
+        const float bCs = (float)(sb / (double)A.bDof);                                  // 0/0 -> nan like tf.reduce_mean
+        const float iCs = A.timeDependent ? (float)(si / (double)(A.nbi - A.bDof)) : 0.f;
+        const float loss = A.wts[0] * bCs + A.wts[1] * iCs + A.wts[2] * varLoss;
+        float* o = A.gbuf + net.nparam;
+        o[0] = loss; o[1] = bCs; o[2] = iCs; o[3] = varLoss;
+    }
+}
+
+// TF-1.x Adam (adam.py _apply_dense): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).
+// `corr` = sqrt(1-b2^t)/(1-b1^t) for the step being applied, maintained by vn_advance_kernel.
+__global__ void vn_adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                               const float* __restrict__ g, int n, float lr, const double* __restrict__ corr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float lr_t = lr * (float)corr[0];
+    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+// TF-1.x RMSProp (decay .9, momentum 0, eps 1e-10, ms initialised to ones): ms = .9 ms + .1 g^2;
+// mom = lr*g/sqrt(ms+eps); theta -= mom.
+__global__ void vn_rmsprop_kernel(float* __restrict__ theta, float* __restrict__ ms, const float* __restrict__ g,
+                                  int n, float lr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float s = 0.9f * ms[i] + 0.1f * gi * gi;
+    ms[i] = s;
+    theta[i] -= lr * gi / sqrtf(s + 1e-10f);
+}
+__global__ void vn_advance_kernel(long long* step, double* corr) {
+    const long long t = step[0] + 1;       // step just applied
+    step[0] = t;
+    const double tn = (double)(t + 1);     // bias correction of the NEXT step
+    corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
+}
+__global__ void vn_fill_kernel(float* p, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Row-major feed arrays -> SoA column table (float32, zero-padded to `pstride`).  Casting a float64
+// feed with __double2float_rn reproduces the float32 placeholder rounding bit-for-bit.
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<double>(double v) { return __double2float_rn(v); }
+
+template <typename T>
+__global__ void vn_pack_kernel(const T* __restrict__ X, int inpDim, const T* __restrict__ G, int dim,
+                               const T* __restrict__ dNt, const T* __restrict__ src, const T* __restrict__ N,
+                               float* __restrict__ cols, long long pstride, long long off, long long n,
+                               int colX, int colG, int colT, int colS) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const long long gp = off + r;
+    for (int c = 0; c < inpDim; ++c) cols[(size_t)(colX + c) * pstride + gp] = to_f32<T>(X[r * inpDim + c]);
+    if (G) for (int c = 0; c < dim; ++c) cols[(size_t)(colG + c) * pstride + gp] = to_f32<T>(G[r * dim + c]);
+    if (dNt && colT >= 0) cols[(size_t)colT * pstride + gp] = to_f32<T>(dNt[r]);
+    if (src && N && colS >= 0) cols[(size_t)colS * pstride + gp] = to_f32<T>(src[r]) * to_f32<T>(N[r]);   // float32 product, as tf.multiply(source, N) (:657)
+}
+template <typename T>
+__global__ void vn_cast_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = to_f32<T>(in[r]);
+}
+
+// ------------------------------------------------------------------ engine
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct vn_engine {
+    vn_config cfg;
+    NetDesc net;
+    int S = 0, wclass = 0, numSMs = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // parameters + optimizer
+    DevBuf theta, m, v, gbuf, wts, stepbuf, corrbuf;
+    // interior points
+    DevBuf cols, integW, detJ, Iw, R, lossVec, segSum;
+    long long pstride = 0; unsigned int P = 0, nb = 0, integNum = 0; int detJvec = 0, hasIntegW = 0;
+    int colX = 0, colG = 0, colT = -1, colS = -1, ncols = 0;
+    // boundary / initial rows
+    DevBuf bcols, blabel, cj;
+    long long bstride = 0; unsigned int nbi = 0, bDof = 0; float biDimVal = 0.f;
+    // adjoint partial slabs
+    DevBuf partVar, partBic; int gridVar = 0, gridBic = 0;
+    // scratch
+    DevBuf stage, evalCols, evalOut;
+    // geometry
+    TileGeom gVarFwd, gVarAdj, gBicFwd, gBicAdj, gEval;
+    bool weightsSet = false;
+};
+
+static const int kPad = 128;    // point-table padding: multiple of every tile size
+
+static int build_net(const vn_config& c, NetDesc* n) {
+    memset(n, 0, sizeof(*n));
+    n->L = c.nLayers; n->inpDim = c.inpDim;
+    int off = 0;
+    for (int l = 0; l <= c.nLayers; ++l) {
+        const int wi = l == 0 ? c.inpDim : c.widths[l - 1];
+        const int wo = l == c.nLayers ? 1 : c.widths[l];
+        n->woff[l] = off; off += wi * wo;
+        n->boff[l] = off; off += wo;
+        if (l < c.nLayers) { n->width[l] = c.widths[l]; n->wpad[l] = (c.widths[l] + 3) & ~3; }
+    }
+    n->nparam = off;
+    return 0;
+}
+
+extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
+    if (!cfg || !out) return fail(VN_E_INVALID, "null argument");
+    if (cfg->dim < 1 || cfg->dim > 2) return fail(VN_E_INVALID, "dim must be 1 or 2 (got %d)", cfg->dim);
+    if (cfg->nLayers < 1 || cfg->nLayers > VN_MAX_LAYERS) return fail(VN_E_INVALID, "nLayers must be in [1,%d]", VN_MAX_LAYERS);
+    const int minInp = cfg->dim + (cfg->timeDependent ? 1 : 0);
+    if (cfg->inpDim < minInp || cfg->inpDim > VN_MAX_INPDIM) return fail(VN_E_INVALID, "inpDim must be in [%d,%d]", minInp, VN_MAX_INPDIM);
+    if (cfg->act != VN_ACT_SIGMOID && cfg->act != VN_ACT_TANH) return fail(VN_E_INVALID, "unknown activation id %d", cfg->act);
+    if (cfg->optimizer != VN_OPT_ADAM && cfg->optimizer != VN_OPT_RMSPROP) return fail(VN_E_INVALID, "unknown optimizer requested!");
+    int wmax = 0;
+    for (int l = 0; l < cfg->nLayers; ++l) {
+        if (cfg->widths[l] < 1) return fail(VN_E_INVALID, "layer width must be positive");
+        wmax = std::max(wmax, (int)cfg->widths[l]);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(VN_E_CUDA, "no CUDA device visible: the varnet_b200 engine has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(VN_E_INVALID, "requested processor %d is unavailable!", cfg->device);
+    CK(cudaSetDevice(cfg->device));
+
+    vn_engine* e = new (std::nothrow) vn_engine();
+    if (!e) return fail(VN_E_INVALID, "out of host memory");
+    e->cfg = *cfg;
+    build_net(*cfg, &e->net);
+    e->S = 1 + cfg->dim;
+    e->wclass = wmax <= 32 ? 32 : (wmax <= 64 ? 64 : 0);
+    if (!e->wclass) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    e->numSMs = prop.multiProcessorCount;
+    const int L = cfg->nLayers, act = cfg->act;
+    bool ok = vn_tile_geometry(e->S, e->wclass, act, MODE_VAR_FWD, L, &e->gVarFwd) &&
+              vn_tile_geometry(e->S, e->wclass, act, MODE_VAR_ADJ, L, &e->gVarAdj) &&
+              vn_tile_geometry(1, e->wclass, act, MODE_BIC_FWD, L, &e->gBicFwd) &&
+              vn_tile_geometry(1, e->wclass, act, MODE_BIC_ADJ, L, &e->gBicAdj) &&
+              vn_tile_geometry(1, e->wclass, act, MODE_EVAL, L, &e->gEval);
+    if (!ok) { delete e; return fail(VN_E_UNSUPPORTED, "no compiled kernel for this configuration"); }
+    const size_t smemMax = prop.sharedMemPerBlockOptin;
+    const TileGeom* gs[5] = {&e->gVarFwd, &e->gVarAdj, &e->gBicFwd, &e->gBicAdj, &e->gEval};
+    const int modes[5] = {MODE_VAR_FWD, MODE_VAR_ADJ, MODE_BIC_FWD, MODE_BIC_ADJ, MODE_EVAL};
+    for (int k = 0; k < 5; ++k) {
+        if (gs[k]->smemBytes > smemMax) {
+            const size_t need = gs[k]->smemBytes;
+            delete e;
+            return fail(VN_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA (limit %zu): depth/width outside the resident-tile kernel family", need, smemMax);
+        }
+        const int S = (k < 2) ? e->S : 1;
+        cudaError_t ce = vn_tile_prepare(S, e->wclass, act, modes[k], gs[k]->smemBytes);
+        if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
+    }
+    const int np = e->net.nparam;
+    CK(e->theta.ensure(np * sizeof(float)));
+    CK(e->m.ensure(np * sizeof(float)));
+    CK(e->v.ensure(np * sizeof(float)));
+    CK(e->gbuf.ensure((np + 4) * sizeof(float)));
+    CK(e->wts.ensure(4 * sizeof(float)));
+    CK(e->stepbuf.ensure(sizeof(long long)));
+    CK(e->corrbuf.ensure(sizeof(double)));
+    CK(cudaMemset(e->theta.p, 0, np * sizeof(float)));
+    CK(cudaMemset(e->gbuf.p, 0, (np + 4) * sizeof(float)));
+    const float w1[4] = {1.f, 1.f, 1.f, 0.f};
+    CK(cudaMemcpy(e->wts.p, w1, sizeof(w1), cudaMemcpyHostToDevice));
+    *out = e;
+    const float* nullf = nullptr;
+    return vn_set_optimizer_state(e, nullf, nullf, np, 0);
+}
+
+extern "C" int vn_destroy(vn_engine* e) {
+    if (!e) return VN_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->cols, &e->integW,
+                      &e->detJ, &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
+                      &e->partBic, &e->stage, &e->evalCols, &e->evalOut};
+    for (DevBuf* b : bufs) b->release();
+    delete e;
+    return VN_OK;
+}
+
+extern "C" int vn_set_stream(vn_engine* e, void* s) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    e->stream = reinterpret_cast<cudaStream_t>(s);
+    return VN_OK;
+}
+extern "C" int vn_synchronize(vn_engine* e) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_param_count(const vn_engine* e, int64_t* n) {
+    if (!e || !n) return fail(VN_E_INVALID, "null argument");
+    *n = e->net.nparam;
+    return VN_OK;
+}
+
+extern "C" int vn_set_optimizer_state(vn_engine* e, const float* m, const float* v, int64_t n, int64_t step) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (n != e->net.nparam) return fail(VN_E_INVALID, "parameter count mismatch: got %lld, expected %d", (long long)n, e->net.nparam);
+    CK(cudaSetDevice(e->cfg.device));
+    const int np = e->net.nparam;
+    if (m) CK(cudaMemcpyAsync(e->m.p, m, np * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    else CK(cudaMemsetAsync(e->m.p, 0, np * sizeof(float), e->stream));
+    if (v) CK(cudaMemcpyAsync(e->v.p, v, np * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    else if (e->cfg.optimizer == VN_OPT_RMSPROP) {      // TF initialises the rms slot to ones
+        vn_fill_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->v.as<float>(), 1.0f, np);
+        CK(cudaGetLastError());
+    } else CK(cudaMemsetAsync(e->v.p, 0, np * sizeof(float), e->stream));
+    const long long st = step;
+    const double tn = (double)(step + 1);
+    const double corr = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
+    CK(cudaMemcpyAsync(e->stepbuf.p, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->corrbuf.p, &corr, sizeof(corr), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_get_optimizer_state(vn_engine* e, float* m, float* v, int64_t n, int64_t* step) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (n != e->net.nparam) return fail(VN_E_INVALID, "parameter count mismatch");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (m) CK(cudaMemcpy(m, e->m.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (v) CK(cudaMemcpy(v, e->v.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (step) { long long st = 0; CK(cudaMemcpy(&st, e->stepbuf.p, sizeof(st), cudaMemcpyDeviceToHost)); *step = st; }
+    return VN_OK;
+}
+extern "C" int vn_set_params(vn_engine* e, const float* theta, int64_t n) {
+    if (!e || !theta) return fail(VN_E_INVALID, "null argument");
+    if (n != e->net.nparam) return fail(VN_E_INVALID, "parameter count mismatch: got %lld, expected %d", (long long)n, e->net.nparam);
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(e->theta.p, theta, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return vn_set_optimizer_state(e, nullptr, nullptr, n, 0);
+}
+extern "C" int vn_get_params(vn_engine* e, float* theta, int64_t n) {
+    if (!e || !theta) return fail(VN_E_INVALID, "null argument");
+    if (n != e->net.nparam) return fail(VN_E_INVALID, "parameter count mismatch");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(theta, e->theta.p, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_set_weights(vn_engine* e, const float w[3]) {
+    if (!e || !w) return fail(VN_E_INVALID, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(e->wts.p, w, 3 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->weightsSet = true;
+    return VN_OK;
+}
+
+// ------------------------------------------------------------------ uploads
+static const long long kChunk = 1 << 22;    // rows per staging chunk
+
+template <typename T>
+static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, const T* N, const T* dNt, int64_t nb,
+                         int32_t integNum, const T* integW, const T* detJ, int32_t detJvec) {
+    if (!e || !X || !G || !detJ) return fail(VN_E_INVALID, "Input, gcoef and detJ are required");
+    if (nb < 1 || integNum < 1) return fail(VN_E_INVALID, "intShape must be positive");
+    const long long P = (long long)nb * integNum;
+    if (P >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "more than 2^31 quadrature points per engine; shard the test functions");
+    const vn_config& c = e->cfg;
+    if (c.timeDependent && !dNt) return fail(VN_E_INVALID, "dNt is required for time-dependent problems");
+    if (c.isSource && (!src || !N)) return fail(VN_E_INVALID, "source and N are required when lossOpt['isSource'] is set");
+    if (c.integWflag && !integW) return fail(VN_E_INVALID, "integW is required when lossOpt['integWflag'] is set");
+    CK(cudaSetDevice(c.device));
+    int col = 0;
+    e->colX = col; col += c.inpDim;
+    e->colG = col; col += c.dim;
+    e->colT = c.timeDependent ? col++ : -1;
+    e->colS = c.isSource ? col++ : -1;
+    e->ncols = col;
+    e->pstride = (P + kPad - 1) / kPad * kPad;
+    e->P = (unsigned int)P; e->nb = (unsigned int)nb; e->integNum = (unsigned int)integNum; e->detJvec = detJvec ? 1 : 0;
+    CK(e->cols.ensure((size_t)e->ncols * e->pstride * sizeof(float)));
+    CK(cudaMemsetAsync(e->cols.p, 0, (size_t)e->ncols * e->pstride * sizeof(float), e->stream));
+    const int rowVals = c.inpDim + c.dim + 3;
+    const long long chunk = std::min<long long>(kChunk, P);
+    CK(e->stage.ensure((size_t)chunk * rowVals * sizeof(T)));
+    for (long long off = 0; off < P; off += chunk) {
+        const long long n = std::min(chunk, P - off);
+        T* sX = e->stage.as<T>();
+        T* sG = sX + n * c.inpDim;
+        T* sT = sG + n * c.dim;
+        T* sS = sT + n;
+        T* sN = sS + n;
+        CK(cudaMemcpyAsync(sX, X + off * c.inpDim, n * c.inpDim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        if (e->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        if (e->colS >= 0) {
+            CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        }
+        vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            sX, c.inpDim, sG, c.dim, e->colT >= 0 ? sT : nullptr, e->colS >= 0 ? sS : nullptr,
+            e->colS >= 0 ? sN : nullptr, e->cols.as<float>(), e->pstride, off, n, e->colX, e->colG, e->colT, e->colS);
+        CK(cudaGetLastError());
+        e->launches++;
+        CK(cudaStreamSynchronize(e->stream));      // staging buffer is reused by the next chunk
+    }
+    // small tables
+    e->hasIntegW = (c.integWflag && integW) ? 1 : 0;
+    const long long nd = detJvec ? nb : 1;
+    CK(e->detJ.ensure(nd * sizeof(float)));
+    CK(e->stage.ensure((size_t)std::max<long long>(nd, integNum) * sizeof(T)));
+    CK(cudaMemcpyAsync(e->stage.p, detJ, nd * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    vn_cast_kernel<T><<<(unsigned)((nd + 255) / 256), 256, 0, e->stream>>>(e->stage.as<T>(), e->detJ.as<float>(), nd);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->hasIntegW) {
+        CK(e->integW.ensure(integNum * sizeof(float)));
+        CK(cudaMemcpyAsync(e->stage.p, integW, integNum * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        vn_cast_kernel<T><<<(integNum + 255) / 256, 256, 0, e->stream>>>(e->stage.as<T>(), e->integW.as<float>(), integNum);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    e->launches += 1 + e->hasIntegW;
+    // work buffers
+    CK(e->Iw.ensure((size_t)P * sizeof(float)));
+    CK(e->R.ensure((size_t)nb * sizeof(float)));
+    CK(e->lossVec.ensure((size_t)nb * sizeof(float)));
+    const int nSeg = (int)((nb + 255) / 256);
+    CK(e->segSum.ensure((size_t)nSeg * sizeof(double)));
+    const long long tilesAdj = e->pstride / e->gVarAdj.TP;
+    e->gridVar = (int)std::min<long long>(tilesAdj, e->numSMs);
+    CK(e->partVar.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(double)));
+    return VN_OK;
+}
+
+template <typename T>
+static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64_t bDof, double biDimVal) {
+    if (!e || !bX || !bL) return fail(VN_E_INVALID, "biInput and biLabel are required");
+    if (nbi < 1 || bDof < 0 || bDof > nbi) return fail(VN_E_INVALID, "need 0 <= bDof <= nbi and nbi >= 1");
+    const vn_config& c = e->cfg;
+    CK(cudaSetDevice(c.device));
+    e->bstride = (nbi + kPad - 1) / kPad * kPad;
+    e->nbi = (unsigned int)nbi; e->bDof = (unsigned int)bDof; e->biDimVal = (float)biDimVal;
+    CK(e->bcols.ensure((size_t)c.inpDim * e->bstride * sizeof(float)));
+    CK(cudaMemsetAsync(e->bcols.p, 0, (size_t)c.inpDim * e->bstride * sizeof(float), e->stream));
+    CK(e->blabel.ensure((size_t)e->bstride * sizeof(float)));
+    CK(e->cj.ensure((size_t)e->bstride * sizeof(float)));
+    CK(e->stage.ensure((size_t)nbi * (c.inpDim + 1) * sizeof(T)));
+    T* sX = e->stage.as<T>();
+    T* sL = sX + nbi * c.inpDim;
+    CK(cudaMemcpyAsync(sX, bX, nbi * c.inpDim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sL, bL, nbi * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    vn_pack_kernel<T><<<(unsigned)((nbi + 255) / 256), 256, 0, e->stream>>>(
+        sX, c.inpDim, nullptr, 0, nullptr, nullptr, nullptr, e->bcols.as<float>(), e->bstride, 0, nbi, 0, 0, -1, -1);
+    CK(cudaGetLastError());
+    vn_cast_kernel<T><<<(unsigned)((nbi + 255) / 256), 256, 0, e->stream>>>(sL, e->blabel.as<float>(), nbi);
+    CK(cudaGetLastError());
+    e->launches += 2;
+    CK(cudaStreamSynchronize(e->stream));
+    const long long tiles = e->bstride / e->gBicAdj.TP;
+    e->gridBic = (int)std::min<long long>(tiles, e->numSMs);
+    CK(e->partBic.ensure((size_t)e->gridBic * e->gBicAdj.pl.psz * sizeof(double)));
+    return VN_OK;
+}
+
+extern "C" int vn_upload_points_f32(vn_engine* e, const float* X, const float* G, const float* s, const float* N,
+                                    const float* dNt, int64_t nb, int32_t integNum, const float* iw, const float* dj,
+                                    int32_t djv) {
+    return upload_points<float>(e, X, G, s, N, dNt, nb, integNum, iw, dj, djv);
+}
+extern "C" int vn_upload_points_f64(vn_engine* e, const double* X, const double* G, const double* s, const double* N,
+                                    const double* dNt, int64_t nb, int32_t integNum, const double* iw, const double* dj,
+                                    int32_t djv) {
+    return upload_points<double>(e, X, G, s, N, dNt, nb, integNum, iw, dj, djv);
+}
+extern "C" int vn_upload_bic_f32(vn_engine* e, const float* bX, const float* bL, int64_t nbi, int64_t bDof, float bdv) {
+    return upload_bic<float>(e, bX, bL, nbi, bDof, (double)bdv);
+}
+extern "C" int vn_upload_bic_f64(vn_engine* e, const double* bX, const double* bL, int64_t nbi, int64_t bDof, double bdv) {
+    return upload_bic<double>(e, bX, bL, nbi, bDof, bdv);
+}
+
+// ------------------------------------------------------------------ hot path
+static void base_args(const vn_engine* e, TileArgs* a) {
+    memset(a, 0, sizeof(*a));
+    a->net = e->net;
+    a->theta = e->theta.as<float>();
+    a->timeDependent = e->cfg.timeDependent;
+    a->isSource = e->cfg.isSource;
+    a->wts = e->wts.as<float>();
+}
+static void var_args(const vn_engine* e, TileArgs* a) {
+    base_args(e, a);
+    a->cols = e->cols.as<float>(); a->pstride = e->pstride;
+    a->colX = e->colX; a->colG = e->colG; a->colT = e->colT; a->colS = e->colS;
+    a->P = e->P;
+    a->integNum = e->integNum;
+    a->integW = e->hasIntegW ? e->integW.as<float>() : nullptr;
+    a->detJ = e->detJ.as<float>(); a->detJvec = e->detJvec;
+    a->R = e->R.as<float>(); a->Iw = e->Iw.as<float>();
+}
+static void bic_args(const vn_engine* e, TileArgs* a) {
+    base_args(e, a);
+    a->cols = e->bcols.as<float>(); a->pstride = e->bstride;
+    a->colX = 0; a->colG = 0; a->colT = -1; a->colS = -1;
+    a->P = e->nbi; a->label = e->blabel.as<float>(); a->bDof = e->bDof; a->biDimVal = e->biDimVal;
+    a->cj = e->cj.as<float>();
+}
+
+static int run_loss(vn_engine* e, bool needGrad) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (!e->P) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+    if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
+    const vn_config& c = e->cfg;
+    CK(cudaSetDevice(c.device));
+    cudaStream_t st = e->stream;
+    TileArgs a;
+    // 1. forward over all quadrature points -> weighted integrand
+    var_args(e, &a);
+    {
+        const TileGeom& g = e->gVarFwd;
+        a.ntiles = (int)(e->pstride / g.TP);
+        const int grid = std::min(a.ntiles, 2 * e->numSMs);
+        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
+    }
+    // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
+    const int nSeg = (int)((e->nb + 255) / 256);
+    {
+        SegArgs s;
+        s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->integNum; s.detJ = e->detJ.as<float>();
+        s.detJvec = e->detJvec; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
+        s.blockSum = e->segSum.as<double>();
+        vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
+        CK(cudaGetLastError());
+    }
+    e->launches += 2;
+    if (needGrad) {
+        // 3. adjoint over quadrature points (forward recomputed per tile, seeds from R_i)
+        const TileGeom& g = e->gVarAdj;
+        a.ntiles = (int)(e->pstride / g.TP);
+        a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_ADJ, a, e->gridVar, g.smemBytes, st));
+        e->launches++;
+    }
+    // 4. boundary / initial rows
+    bic_args(e, &a);
+    {
+        const int mode = needGrad ? MODE_BIC_ADJ : MODE_BIC_FWD;
+        const TileGeom& g = needGrad ? e->gBicAdj : e->gBicFwd;
+        a.ntiles = (int)(e->bstride / g.TP);
+        a.part = e->partBic.as<double>(); a.psz = g.pl.psz;
+        const int grid = needGrad ? e->gridBic : std::min(a.ntiles, 2 * e->numSMs);
+        CK(vn_tile_launch(1, e->wclass, c.act, mode, a, grid, g.smemBytes, st));
+        e->launches++;
+    }
+    // 5. deterministic cross-CTA reduction + loss scalars
+    {
+        FinalArgs f;
+        memset(&f, 0, sizeof(f));
+        f.net = e->net; f.pl = e->gVarAdj.pl;
+        f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
+        f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
+        f.segSum = e->segSum.as<double>(); f.nSeg = nSeg;
+        f.detJ = e->detJ.as<float>(); f.detJvec = e->detJvec;
+        f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
+        f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
+        const int nb = needGrad ? (e->net.nparam + 127) / 128 : 0;
+        vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    return VN_OK;
+}
+
+static int read_scalars(vn_engine* e, float out[4]) {
+    CK(cudaMemcpyAsync(out, e->gbuf.as<float>() + e->net.nparam, 4 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+
+extern "C" int vn_loss(vn_engine* e, float out[4], float* lossVec) {
+    int rc = run_loss(e, false);
+    if (rc) return rc;
+    if (lossVec) CK(cudaMemcpyAsync(lossVec, e->lossVec.p, (size_t)e->nb * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (out) return read_scalars(e, out);
+    if (lossVec) CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_loss_grad(vn_engine* e, float out[4]) {
+    int rc = run_loss(e, true);
+    if (rc) return rc;
+    if (out) return read_scalars(e, out);
+    return VN_OK;
+}
+extern "C" int vn_grad_buffer(vn_engine* e, void** p, int64_t* n) {
+    if (!e || !p || !n) return fail(VN_E_INVALID, "null argument");
+    *p = e->gbuf.p; *n = e->net.nparam + 4;
+    return VN_OK;
+}
+extern "C" int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]) {
+    if (!e || !grad) return fail(VN_E_INVALID, "null argument");
+    if (n != e->net.nparam) return fail(VN_E_INVALID, "parameter count mismatch");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(grad, e->gbuf.p, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (out) return read_scalars(e, out);
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
+    CK(cudaSetDevice(e->cfg.device));
+    const int np = e->net.nparam;
+    if (e->cfg.optimizer == VN_OPT_ADAM)
+        vn_adam_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->m.as<float>(), e->v.as<float>(),
+                                                                e->gbuf.as<float>(), np, lr, e->corrbuf.as<double>());
+    else
+        vn_rmsprop_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->v.as<float>(),
+                                                                   e->gbuf.as<float>(), np, lr);
+    CK(cudaGetLastError());
+    vn_advance_kernel<<<1, 1, 0, e->stream>>>(e->stepbuf.as<long long>(), e->corrbuf.as<double>());
+    CK(cudaGetLastError());
+    e->launches += 2;
+    return VN_OK;
+}
+extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
+    int rc = run_loss(e, true);
+    if (rc) return rc;
+    rc = vn_optimizer_step(e, lr);
+    if (rc) return rc;
+    if (loss_out) {
+        CK(cudaMemcpyAsync(loss_out, e->gbuf.as<float>() + e->net.nparam, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return VN_OK;
+}
+
+// ------------------------------------------------------------------ evaluation
+template <typename T>
+static int eval_impl(vn_engine* e, const T* X, int64_t n, float* u) {
+    if (!e || !X || !u) return fail(VN_E_INVALID, "null argument");
+    if (n < 1) return fail(VN_E_INVALID, "need at least one evaluation point");
+    if (n >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "too many evaluation points in one call");
+    const vn_config& c = e->cfg;
+    CK(cudaSetDevice(c.device));
+    const long long stride = (n + kPad - 1) / kPad * kPad;
+    CK(e->evalCols.ensure((size_t)c.inpDim * stride * sizeof(float)));
+    CK(e->evalOut.ensure((size_t)stride * sizeof(float)));
+    CK(cudaMemsetAsync(e->evalCols.p, 0, (size_t)c.inpDim * stride * sizeof(float), e->stream));
+    CK(e->stage.ensure((size_t)n * c.inpDim * sizeof(T)));
+    CK(cudaMemcpyAsync(e->stage.p, X, (size_t)n * c.inpDim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+        e->stage.as<T>(), c.inpDim, nullptr, 0, nullptr, nullptr, nullptr, e->evalCols.as<float>(), stride, 0, n, 0, 0, -1, -1);
+    CK(cudaGetLastError());
+    TileArgs a;
+    base_args(e, &a);
+    a.cols = e->evalCols.as<float>(); a.pstride = stride; a.colX = 0; a.colT = -1; a.colS = -1;
+    a.P = (unsigned int)n; a.uout = e->evalOut.as<float>();
+    const TileGeom& g = e->gEval;
+    a.ntiles = (int)(stride / g.TP);
+    CK(vn_tile_launch(1, e->wclass, c.act, MODE_EVAL, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, e->stream));
+    e->launches += 2;
+    CK(cudaMemcpyAsync(u, e->evalOut.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_eval_f32(vn_engine* e, const float* X, int64_t n, float* u) { return eval_impl<float>(e, X, n, u); }
+extern "C" int vn_eval_f64(vn_engine* e, const double* X, int64_t n, float* u) { return eval_impl<double>(e, X, n, u); }
+
+extern "C" int vn_residual_f64(vn_engine* e, const double*, const double*, const double*, const double*, const double*,
+                               int64_t, float*, float*) {
+    (void)e;
+    return fail(VN_E_UNSUPPORTED, "strong-form residual kernel not built yet");
+}
+
+extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
+    if (!e || !buf) return fail(VN_E_INVALID, "null argument");
+    snprintf(buf, n,
+             "family=fp32-fma-resident-tile wclass=%d S=%d L=%d var_fwd(TP=%d,NT=%d,smem=%zu) var_adj(TP=%d,NT=%d,smem=%zu,grid=%d) "
+             "bic_adj(TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+             e->wclass, e->S, e->net.L, e->gVarFwd.TP, e->gVarFwd.NT, e->gVarFwd.smemBytes, e->gVarAdj.TP, e->gVarAdj.NT,
+             e->gVarAdj.smemBytes, e->gridVar, e->gBicAdj.TP, e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
+    return VN_OK;
+}
+extern "C" int64_t vn_launch_count(const vn_engine* e) { return e ? e->launches : 0; }

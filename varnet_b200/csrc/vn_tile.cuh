@@ -1,0 +1,577 @@
+// vn_tile.cuh — fused FP32 tile kernels for the weak-form residual and its adjoint.
+//
+// One CTA owns a tile of TP quadrature points and walks the whole MLP for them with
+// every layer's activations resident in shared memory:
+//   stream 0      : a_l        = act(a_{l-1} W_l + b_l)                (model(Input),   TFModel.py:625)
+//   stream 1..DIM : da_l/dx_k  = act'(z_l) * (da_{l-1}/dx_k W_l)       (tf.gradients(model(Input), Input)[:, :dim], TFModel.py:536-541,
+//                                                                        evaluated forward-mode: same numbers, no second sweep)
+// Each layer is a [S*TP x Kin] x [Kin x W] register-tiled FP32-FMA GEMM whose A operand
+// (activations, point-contiguous) and B operand (weights) are read from shared memory
+// with 128-bit loads; the epilogue applies the activation and writes the next layer's
+// operand.  The adjoint walks the layers backwards with two more
+// GEMMs per layer: abar_{l-1} = zbar_l W_l^T and gW_l += [a_{l-1}; da_{l-1}]^T [zbar_l; dzbar_l].
+// Weight-gradient tiles are accumulated per CTA in FP64 partial buffers (thread-private
+// slots, no atomics => deterministic) and summed across CTAs by vn_finalize_kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VN_MAX_LAYERS 8
+#define VN_KIN 8          // padded MLP input rows (== VN_MAX_INPDIM)
+
+enum { VN_SIGMOID = 0, VN_TANH = 1 };
+
+enum {
+    MODE_VAR_FWD = 0,   // I_p per point                       (TFModel.py:653-660)
+    MODE_EVAL = 1,      // u = model(X)                        (VarNetUtility.py:1127)
+    MODE_BIC_FWD = 2,   // biDimVal*(model(biInput)-biLabel)^2 (TFModel.py:643)
+    MODE_VAR_ADJ = 3,   // d(w2*varLoss)/d theta               (TFModel.py:709)
+    MODE_BIC_ADJ = 4    // d(w0*bCs+w1*iCs)/d theta
+};
+
+struct NetDesc {
+    int L;                          // hidden layers
+    int inpDim;
+    int width[VN_MAX_LAYERS];       // hidden widths
+    int wpad[VN_MAX_LAYERS];        // rounded up to a multiple of 4
+    int woff[VN_MAX_LAYERS + 1];    // flat offset of kernel l (l == L: output layer)
+    int boff[VN_MAX_LAYERS + 1];    // flat offset of bias l
+    int nparam;
+};
+
+struct TileArgs {
+    NetDesc net;
+    const float* theta;             // flat parameters (device)
+    const float* cols;              // SoA point table: column c at cols + c*pstride
+    long long pstride;              // multiple of the tile size, zero padded
+    int colX, colG, colT, colS;     // first column of X, gcoef, dNt, source*N (-1 = absent)
+    unsigned int P;                 // valid points (rows)
+    int ntiles;
+    int timeDependent, isSource;
+    // variational term
+    unsigned int integNum;
+    const float* integW;            // [integNum] or nullptr
+    const float* detJ;              // [1] or [nb]
+    int detJvec;
+    const float* R;                 // [nb] per-test-function residuals (ADJ)
+    const float* wts;               // [3] loss weights (device)
+    float* Iw;                      // [P] weighted integrand out (VAR_FWD)
+    // boundary / initial rows
+    const float* label;             // [nbi]
+    unsigned int bDof;
+    float biDimVal;
+    float* cj;                      // [nbi] biDimVal*(u-label)^2 out
+    // evaluation
+    float* uout;                    // [P]
+    // adjoint partial sums
+    double* part;                   // [gridDim.x][psz]
+    int psz;
+};
+
+template <int S_, int WP_, int TP_, int TN_, int ACT_>
+struct TileCfg {
+    static constexpr int S = S_;            // streams: value + DIM input tangents
+    static constexpr int WP = WP_;          // padded hidden width class
+    static constexpr int TP = TP_;          // points per tile
+    static constexpr int TN = TN_;          // neurons per thread in the layer GEMMs
+    static constexpr int ACT = ACT_;
+    static constexpr int TPS = TP + 4;      // padded point stride  (bank-conflict-free row walks)
+    static constexpr int WS = WP + 4;       // padded weight row stride
+    static constexpr int NPG = TP / 4;      // point groups (4 points per thread)
+    static constexpr int NNG = WP / TN;     // neuron groups
+    static constexpr int NT = NPG * NNG;    // threads per CTA
+    static constexpr int NPGW = NPG / 8;    // warps along the point axis
+    static constexpr int KIN = VN_KIN;
+    static constexpr int NJG = NT / 8;      // weight-gradient GEMM: column groups
+    static constexpr int TJ = WP / NJG;     //   columns per thread
+    static constexpr int TI = WP / 8;       //   rows per thread
+    static constexpr int BUF = S * WP * TPS;
+    static constexpr int BUF0 = S * KIN * TPS;
+    static_assert(NPG % 8 == 0 && NNG % 4 == 0, "warp mapping needs 8 point groups x 4 neuron groups per warp");
+    static_assert(WP % NJG == 0 && TJ >= 1, "bad weight-gradient tiling");
+    static_assert(NT % WP == 0, "output-layer gradient mapping");
+};
+
+// layout of one CTA's FP64 partial-gradient slab (shared by kernels and finalize)
+struct PartLayout {
+    int NT, NJG, TI, TJ, WP;
+    int off_gw[VN_MAX_LAYERS];
+    int off_gb[VN_MAX_LAYERS];
+    int off_wout, off_bout, psz;
+};
+
+template <class C>
+__host__ __device__ inline PartLayout make_part_layout(int L) {
+    PartLayout p;
+    p.NT = C::NT; p.NJG = C::NJG; p.TI = C::TI; p.TJ = C::TJ; p.WP = C::WP;
+    int o = 0;
+    for (int l = 0; l < L; ++l) {
+        p.off_gw[l] = o; o += C::NT * (l == 0 ? C::TJ : C::TI * C::TJ);
+        p.off_gb[l] = o; o += C::WP;
+    }
+    p.off_wout = o; o += C::NT;
+    p.off_bout = o; o += 1;
+    p.psz = (o + 1) & ~1;
+    return p;
+}
+
+template <class C>
+__host__ __device__ inline size_t tile_smem_floats(int L, bool adj) {
+    size_t n = 0;
+    n += C::KIN * C::WS;                    // W0
+    n += (size_t)(L - 1) * C::WP * C::WS;   // W1..W_{L-1}
+    n += (size_t)L * C::WP;                 // biases
+    n += C::WP + 4;                         // wout | bout
+    n += C::BUF0;                           // layer "-1": inputs + unit tangent rows
+    n += (size_t)(adj ? L : 2) * C::BUF;    // activations (all layers kept for the adjoint)
+    n += adj ? 2 * (size_t)C::BUF : 0;      // zbar ping-pong
+    n += 4 * C::TP;                         // per-point coefficients
+    n += (size_t)C::S * C::TP;              // u / seeds
+    return n;
+}
+
+// ------------------------------------------------------------------ activations
+template <int ACT> __device__ __forceinline__ float act_f(float z) {
+    if (ACT == VN_SIGMOID) return __fdividef(1.0f, 1.0f + expf(-z));
+    return tanhf(z);
+}
+template <int ACT> __device__ __forceinline__ float act_d1(float a) {      // act'(z) in terms of a
+    return ACT == VN_SIGMOID ? a * (1.0f - a) : fmaf(-a, a, 1.0f);
+}
+template <int ACT> __device__ __forceinline__ float act_d2r(float a) {     // act''(z)/act'(z)
+    return ACT == VN_SIGMOID ? fmaf(-2.0f, a, 1.0f) : -2.0f * a;
+}
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// out[s][j][p] = sum_i in[s][i][p] * W[i][j]; thread tile: 4 points x S streams x TN neurons
+template <class C, int KD>
+__device__ __forceinline__ void fwd_gemm(const float* __restrict__ Bin, const float* __restrict__ Wm,
+                                         int Kin, int p0, int j0, float (&acc)[C::S][4][C::TN]) {
+#pragma unroll
+    for (int s = 0; s < C::S; ++s)
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int t = 0; t < C::TN; ++t) acc[s][p][t] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < Kin; ++i) {
+        float w[C::TN];
+        if (C::TN % 4 == 0) {
+#pragma unroll
+            for (int t4 = 0; t4 < C::TN / 4; ++t4) {
+                float4 v = lds4(Wm + i * C::WS + j0 + 4 * t4);
+                w[4 * t4 + 0] = v.x; w[4 * t4 + 1] = v.y; w[4 * t4 + 2] = v.z; w[4 * t4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < C::TN; ++t) w[t] = Wm[i * C::WS + j0 + t];
+        }
+#pragma unroll
+        for (int s = 0; s < C::S; ++s) {
+            float4 a = lds4(Bin + (s * KD + i) * C::TPS + p0);
+#pragma unroll
+            for (int t = 0; t < C::TN; ++t) {
+                acc[s][0][t] = fmaf(a.x, w[t], acc[s][0][t]);
+                acc[s][1][t] = fmaf(a.y, w[t], acc[s][1][t]);
+                acc[s][2][t] = fmaf(a.z, w[t], acc[s][2][t]);
+                acc[s][3][t] = fmaf(a.w, w[t], acc[s][3][t]);
+            }
+        }
+    }
+}
+
+// out[s][i_t][p] = sum_j D[s][j][p] * W[i_t][j];  thread owns interleaved rows i_t = ng + NNG*t
+template <class C>
+__device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const float* __restrict__ Wm,
+                                         int Kout, int p0, int ng, float (&acc)[C::S][4][C::TN]) {
+#pragma unroll
+    for (int s = 0; s < C::S; ++s)
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int t = 0; t < C::TN; ++t) acc[s][p][t] = 0.f;
+    for (int j0 = 0; j0 < Kout; j0 += 4) {
+        float4 w[C::TN];
+#pragma unroll
+        for (int t = 0; t < C::TN; ++t) w[t] = lds4(Wm + (ng + C::NNG * t) * C::WS + j0);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+            for (int s = 0; s < C::S; ++s) {
+                float4 d = lds4(Dm + (s * C::WP + j0 + jj) * C::TPS + p0);
+#pragma unroll
+                for (int t = 0; t < C::TN; ++t) {
+                    const float wv = f4get(w[t], jj);
+                    acc[s][0][t] = fmaf(d.x, wv, acc[s][0][t]);
+                    acc[s][1][t] = fmaf(d.y, wv, acc[s][1][t]);
+                    acc[s][2][t] = fmaf(d.z, wv, acc[s][2][t]);
+                    acc[s][3][t] = fmaf(d.w, wv, acc[s][3][t]);
+                }
+            }
+        }
+    }
+}
+
+// gW[i][j] += sum_{s,p} Bprev[s][i][p] * D[s][j][p];  i = ig + 8t, j = jg + NJG*t'
+// (ig == 0 threads also produce gb[j] = sum_p D[0][j][p]).  Accumulates into the CTA's
+// FP64 partial slab; `first` overwrites instead of accumulating.
+template <class C, int KD, int TIK>
+__device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const float* __restrict__ Dm,
+                                        int ig, int jg, double* __restrict__ pgw, double* __restrict__ pgb,
+                                        bool first) {
+    float acc[TIK][C::TJ];
+    float bacc[C::TJ];
+#pragma unroll
+    for (int t = 0; t < TIK; ++t)
+#pragma unroll
+        for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
+#pragma unroll
+    for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
+#pragma unroll
+    for (int s = 0; s < C::S; ++s) {
+#pragma unroll 2
+        for (int p = 0; p < C::TP; p += 4) {
+            float4 a[TIK], d[C::TJ];
+#pragma unroll
+            for (int t = 0; t < TIK; ++t) a[t] = lds4(Bprev + (s * KD + ig + 8 * t) * C::TPS + p);
+#pragma unroll
+            for (int u = 0; u < C::TJ; ++u) d[u] = lds4(Dm + (s * C::WP + jg + C::NJG * u) * C::TPS + p);
+#pragma unroll
+            for (int t = 0; t < TIK; ++t)
+#pragma unroll
+                for (int u = 0; u < C::TJ; ++u) {
+                    float v = acc[t][u];
+                    v = fmaf(a[t].x, d[u].x, v); v = fmaf(a[t].y, d[u].y, v);
+                    v = fmaf(a[t].z, d[u].z, v); v = fmaf(a[t].w, d[u].w, v);
+                    acc[t][u] = v;
+                }
+            if (s == 0 && ig == 0) {
+#pragma unroll
+                for (int u = 0; u < C::TJ; ++u) bacc[u] += (d[u].x + d[u].y) + (d[u].z + d[u].w);
+            }
+        }
+    }
+    if (first) {
+#pragma unroll
+        for (int t = 0; t < TIK; ++t)
+#pragma unroll
+            for (int u = 0; u < C::TJ; ++u) __stcg(pgw + t * C::TJ + u, (double)acc[t][u]);
+        if (ig == 0) {
+#pragma unroll
+            for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, (double)bacc[u]);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < TIK; ++t)
+#pragma unroll
+            for (int u = 0; u < C::TJ; ++u) __stcg(pgw + t * C::TJ + u, __ldcg(pgw + t * C::TJ + u) + (double)acc[t][u]);
+        if (ig == 0) {
+#pragma unroll
+            for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, __ldcg(pgb + u) + (double)bacc[u]);
+        }
+    }
+}
+
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT, 1) vn_tile_kernel(const __grid_constant__ TileArgs A) {
+    constexpr bool ADJ = (MODE == MODE_VAR_ADJ || MODE == MODE_BIC_ADJ);
+    constexpr bool BIC = (MODE == MODE_BIC_FWD || MODE == MODE_BIC_ADJ);
+    constexpr bool NEED_OUT = (MODE != MODE_VAR_ADJ);      // output layer forward needed?
+    constexpr int S = C::S, WP = C::WP, TP = C::TP, TN = C::TN, TPS = C::TPS, WS = C::WS, NT = C::NT;
+    constexpr int KIN = C::KIN, BUF = C::BUF;
+    extern __shared__ __align__(16) float smem[];
+    const NetDesc& net = A.net;
+    const int L = net.L;
+
+    float* W0 = smem;
+    float* Wl = W0 + KIN * WS;
+    float* bias = Wl + (L - 1) * WP * WS;
+    float* wout = bias + L * WP;
+    float* Bm1 = wout + WP + 4;
+    float* B = Bm1 + C::BUF0;
+    float* D = B + (ADJ ? L : 2) * BUF;
+    float* coef = D + (ADJ ? 2 * BUF : 0);
+    float* us = coef + 4 * TP;                              // u_s[p] (forward) / seeds (adjoint)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = (lane & 7) + 8 * (warp % C::NPGW);
+    const int ng = (lane >> 3) + 4 * (warp / C::NPGW);
+    const int p0 = 4 * pg;
+    const int ig = lane & 7, jg = (lane >> 3) + 4 * warp;   // weight-gradient GEMM mapping
+
+    // ---- one-time: zero shared memory, stage the weights
+    {
+        const int total = (int)tile_smem_floats<C>(L, ADJ);
+        for (int i = tid; i < total; i += NT) smem[i] = 0.f;
+        __syncthreads();
+        const float* __restrict__ th = A.theta;
+        for (int idx = tid; idx < net.inpDim * net.width[0]; idx += NT) {
+            int i = idx / net.width[0], j = idx - i * net.width[0];
+            W0[i * WS + j] = th[net.woff[0] + idx];
+        }
+        for (int l = 1; l < L; ++l) {
+            const int wi = net.width[l - 1], wo = net.width[l];
+            float* Wm = Wl + (l - 1) * WP * WS;
+            for (int idx = tid; idx < wi * wo; idx += NT) {
+                int i = idx / wo, j = idx - i * wo;
+                Wm[i * WS + j] = th[net.woff[l] + idx];
+            }
+        }
+        for (int l = 0; l < L; ++l)
+            for (int j = tid; j < net.width[l]; j += NT) bias[l * WP + j] = th[net.boff[l] + j];
+        for (int j = tid; j < net.width[L - 1]; j += NT) wout[j] = th[net.woff[L] + j];
+        if (tid == 0) wout[WP] = th[net.boff[L]];
+        // unit tangent rows: d x_c / d x_k = delta_ck  (stream 1+k seeds input column k)
+        for (int idx = tid; idx < (S - 1) * TP; idx += NT) {
+            int k = idx / TP, p = idx - k * TP;
+            Bm1[((1 + k) * KIN + k) * TPS + p] = 1.f;
+        }
+        __syncthreads();
+    }
+
+    const PartLayout pl = make_part_layout<C>(L);
+    double* part = ADJ ? A.part + (size_t)blockIdx.x * pl.psz : nullptr;
+    const int kin0 = (net.inpDim + 3) & ~3;
+    bool first = true;
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const unsigned int base = (unsigned int)tile * TP;
+        // ---- phase 1: stage the tile's inputs (coalesced 128-bit loads from the SoA table)
+        for (int idx = tid; idx < net.inpDim * C::NPG; idx += NT) {
+            int c = idx / C::NPG, q = idx - c * C::NPG;
+            float4 v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + base) + q);
+            sts4(Bm1 + c * TPS + 4 * q, v);
+        }
+        if (MODE == MODE_VAR_ADJ) {
+            // adjoint seeds: lambda = 2 w2 detJ_i w_q R_i ; ubar = -lambda dNt ; ubar_k = lambda gcoef_k
+            for (int p = tid; p < TP; p += NT) {
+                const unsigned int gp = base + p;
+                float lam = 0.f;
+                if (gp < A.P) {
+                    const unsigned int i = gp / A.integNum, q = gp - i * A.integNum;
+                    const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                    const float wq = A.integW ? __ldg(A.integW + q) : 1.f;
+                    lam = 2.f * __ldg(A.wts + 2) * dj * wq * __ldg(A.R + i);
+                }
+                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + gp) : 0.f;
+#pragma unroll
+                for (int k = 0; k < S - 1; ++k)
+                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp);
+            }
+        }
+        __syncthreads();
+
+        // ---- forward sweep
+        for (int l = 0; l < L; ++l) {
+            const int j0 = TN * ng;
+            float* Bout = B + (ADJ ? l : (l & 1)) * BUF;
+            if (j0 < net.wpad[l]) {
+                float acc[S][4][TN];
+                if (l == 0) {
+                    fwd_gemm<C, KIN>(Bm1, W0, kin0, p0, j0, acc);
+                } else {
+                    const float* Bin = B + (ADJ ? (l - 1) : ((l - 1) & 1)) * BUF;
+                    fwd_gemm<C, WP>(Bin, Wl + (l - 1) * WP * WS, net.wpad[l - 1], p0, j0, acc);
+                }
+#pragma unroll
+                for (int t = 0; t < TN; ++t) {
+                    const float b = bias[l * WP + j0 + t];
+                    float a[4], d1[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        a[p] = act_f<C::ACT>(acc[0][p][t] + b);
+                        d1[p] = act_d1<C::ACT>(a[p]);
+                    }
+                    sts4(Bout + (j0 + t) * TPS + p0, make_float4(a[0], a[1], a[2], a[3]));
+#pragma unroll
+                    for (int s = 1; s < S; ++s)
+                        sts4(Bout + (s * WP + j0 + t) * TPS + p0,
+                             make_float4(d1[0] * acc[s][0][t], d1[1] * acc[s][1][t],
+                                         d1[2] * acc[s][2][t], d1[3] * acc[s][3][t]));
+                }
+            }
+            __syncthreads();
+        }
+        const float* Blast = B + (ADJ ? (L - 1) : ((L - 1) & 1)) * BUF;
+        const int wlast = net.wpad[L - 1];
+
+        // ---- output layer (Dense(1), linear): u and du/dx_k
+        if (NEED_OUT) {
+            for (int idx = tid; idx < S * TP; idx += NT) {
+                const int s = idx / TP, p = idx - s * TP;
+                float acc = 0.f;
+                for (int i = 0; i < wlast; ++i) acc = fmaf(Blast[(s * WP + i) * TPS + p], wout[i], acc);
+                if (s == 0) acc += wout[WP];
+                us[idx] = acc;
+            }
+            __syncthreads();
+        }
+        if (MODE == MODE_VAR_FWD) {
+            // integrand  I = sum_k u_k gcoef_k - u dNt - source N   (TFModel.py:653-657), weighted (:660)
+            for (int p = tid; p < TP; p += NT) {
+                const unsigned int gp = base + p;
+                if (gp < A.P) {
+                    float I = 0.f;
+#pragma unroll
+                    for (int k = 0; k < S - 1; ++k)
+                        I = fmaf(us[(1 + k) * TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp), I);
+                    if (A.timeDependent) I -= us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + gp);
+                    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
+                    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+                    A.Iw[gp] = I;
+                }
+            }
+        } else if (MODE == MODE_EVAL) {
+            for (int p = tid; p < TP; p += NT)
+                if (base + p < A.P) A.uout[base + p] = us[p];
+        } else if (BIC) {
+            for (int p = tid; p < TP; p += NT) {
+                const unsigned int gp = base + p;
+                float seed = 0.f;
+                if (gp < A.P) {
+                    const float r = us[p] - __ldg(A.label + gp);
+                    if (MODE == MODE_BIC_FWD || A.cj) A.cj[gp] = A.biDimVal * r * r;
+                    // mean over boundary rows / initial rows (TFModel.py:644-648)
+                    float sc;
+                    if (gp < A.bDof) sc = __ldg(A.wts + 0) / (float)A.bDof;
+                    else sc = A.timeDependent ? __ldg(A.wts + 1) / (float)(A.P - A.bDof) : 0.f;
+                    seed = 2.f * A.biDimVal * r * sc;
+                }
+                if (ADJ) us[p] = seed;
+            }
+        }
+
+        if (ADJ) {
+            if (BIC) __syncthreads();       // seeds were just written to `us`
+            // ---- top of the adjoint: zbar_{L-1} from ubar (outer product with w_out), g(w_out), g(b_out)
+            float* Dcur = D;
+#pragma unroll
+            for (int t = 0; t < TN; ++t) {
+                const int i = ng + C::NNG * t;
+                if (i < wlast) {
+                    const float wv = wout[i];
+                    const float4 a4 = lds4(Blast + i * TPS + p0);
+                    const float4 u0 = lds4(us + p0);
+                    float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float ub[4] = {u0.x * wv, u0.y * wv, u0.z * wv, u0.w * wv};
+                    float zb[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, d1[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
+#pragma unroll
+                    for (int s = 1; s < S; ++s) {
+                        const float4 us4 = lds4(us + s * TP + p0);
+                        const float4 da4 = lds4(Blast + (s * WP + i) * TPS + p0);
+                        const float dab[4] = {us4.x * wv, us4.y * wv, us4.z * wv, us4.w * wv};
+                        const float da[4] = {da4.x, da4.y, da4.z, da4.w};
+                        float o[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) { cross[p] = fmaf(dab[p], da[p], cross[p]); o[p] = dab[p] * d1[p]; }
+                        sts4(Dcur + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) zb[p] = fmaf(ub[p], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
+                    sts4(Dcur + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
+                }
+            }
+            {
+                // g(w_out)[i] = sum_{s,p} B_last[s][i][p] * ubar_s[p]   (thread: neuron i, point slice)
+                constexpr int NPART = NT / WP, PSL = TP / NPART;
+                const int i = tid % WP, prt = tid / WP;
+                float acc = 0.f;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    for (int p = prt * PSL; p < (prt + 1) * PSL; p += 4) {
+                        const float4 b4 = lds4(Blast + (s * WP + i) * TPS + p);
+                        const float4 u4 = lds4(us + s * TP + p);
+                        acc = fmaf(b4.x, u4.x, acc); acc = fmaf(b4.y, u4.y, acc);
+                        acc = fmaf(b4.z, u4.z, acc); acc = fmaf(b4.w, u4.w, acc);
+                    }
+                double* pw = part + pl.off_wout + tid;
+                __stcg(pw, first ? (double)acc : __ldcg(pw) + (double)acc);
+                if (tid == 0) {
+                    float sb = 0.f;
+                    for (int p = 0; p < TP; ++p) sb += us[p];
+                    double* pb = part + pl.off_bout;
+                    __stcg(pb, first ? (double)sb : __ldcg(pb) + (double)sb);
+                }
+            }
+            __syncthreads();
+
+            // ---- backward sweep
+            int cur = 0;
+            for (int l = L - 1; l >= 0; --l) {
+                float* Dc = D + cur * BUF;
+                float* Dn = D + (cur ^ 1) * BUF;
+                if (l == 0) {
+                    gw_gemm<C, KIN, 1>(Bm1, Dc, ig, jg, part + pl.off_gw[0] + tid * C::TJ,
+                                       part + pl.off_gb[0] + jg * C::TJ, first);
+                } else {
+                    const float* Bprev = B + (l - 1) * BUF;
+                    gw_gemm<C, WP, C::TI>(Bprev, Dc, ig, jg, part + pl.off_gw[l] + tid * (C::TI * C::TJ),
+                                          part + pl.off_gb[l] + jg * C::TJ, first);
+                    // abar_{l-1} = zbar_l W_l^T, then through act' / act'' of layer l-1
+                    if (ng < net.wpad[l - 1]) {
+                        float acc[S][4][TN];
+                        adj_gemm<C>(Dc, Wl + (l - 1) * WP * WS, net.wpad[l], p0, ng, acc);
+#pragma unroll
+                        for (int t = 0; t < TN; ++t) {
+                            const int i = ng + C::NNG * t;
+                            if (i < net.wpad[l - 1]) {
+                                const float4 a4 = lds4(Bprev + i * TPS + p0);
+                                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                                float d1[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, zb[4];
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
+#pragma unroll
+                                for (int s = 1; s < S; ++s) {
+                                    const float4 da4 = lds4(Bprev + (s * WP + i) * TPS + p0);
+                                    const float da[4] = {da4.x, da4.y, da4.z, da4.w};
+                                    float o[4];
+#pragma unroll
+                                    for (int p = 0; p < 4; ++p) {
+                                        cross[p] = fmaf(acc[s][p][t], da[p], cross[p]);
+                                        o[p] = acc[s][p][t] * d1[p];
+                                    }
+                                    sts4(Dn + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
+                                }
+#pragma unroll
+                                for (int p = 0; p < 4; ++p)
+                                    zb[p] = fmaf(acc[0][p][t], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
+                                sts4(Dn + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                cur ^= 1;
+            }
+            first = false;
+        } else {
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ small kernels
+// R_i = sum_q Iw[i*integNum+q]; lossVec_i = detJ_i R_i^2; block partial of sum_i (detJ_i) R_i^2 in FP64.
+struct SegArgs {
+    const float* Iw; unsigned int nb, integNum; const float* detJ; int detJvec;
+    float* R; float* lossVec; double* blockSum;
+};
+__global__ void vn_segreduce_kernel(SegArgs A);
+
+struct FinalArgs {
+    NetDesc net; PartLayout pl;
+    const double* partVar; int nVar;        // per-CTA slabs of the variational adjoint kernel
+    const double* partBic; int nBic;        // ... of the boundary/initial adjoint kernel
+    const double* segSum; int nSeg;         // block partials from vn_segreduce_kernel
+    const float* detJ; int detJvec;
+    const float* cj; unsigned int nbi, bDof; int timeDependent;
+    const float* wts;
+    float* gbuf;                            // [nparam | loss, BCloss, ICloss, varLoss]
+    int needGrad;
+};
+__global__ void vn_finalize_kernel(FinalArgs A);
