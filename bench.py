@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — weak-form residual + gradient throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one reference training step `sess.run([optMinimize, loss], feed)`
+(VarNetUtility.py:1044): residual loss + all weight gradients (+ NCCL all-reduce at N>1) + TF-Adam
+on one batch of synthetic input.  The workload at N=1 is BASELINE.json configs[3], the config the
+metric is quoted on: 10^6 space-time test functions x 4^3 Gauss points (P = 6.4e7 quadrature
+points), 4x64 tanh MLP, built with the reference API's discretisation (varnet_b200/workloads.py).
+At N>1 the same 10^6 test functions are sharded contiguously over the ranks like the reference's
+towers (VarNetUtility.py:830-838) => "strong" scaling; the only collective is the all-reduce of
+the [grad | 4 loss scalars] buffer (51 KB).
+
+Timing: W>=3 warm-up steps, then exactly K steps between barrier+synchronize, CUDA events on the
+launching stream, max over ranks.  Inputs (1.5 GB/GPU at N=1) are far larger than L2 (126 MB), so no
+explicit flush is needed.  `value` = resident-table throughput; `e2e` = the same step with the host
+feed (pinned float32) re-uploaded inside the timed region every step and the loss read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, ntime, layerWidth, activation)
+    "synthetic_2dt_1e6x64_mlp4x64_tanh": (100, 100, 100, (64, 64, 64, 64), "tanh"),
+    "synthetic_2dt_1e6x64_mlp4x16_tanh": (100, 100, 100, (16, 16, 16, 16), "tanh"),
+    "synthetic_2dt_small_mlp4x64_tanh": (40, 40, 25, (64, 64, 64, 64), "tanh"),
+}
+DEFAULT = "synthetic_2dt_1e6x64_mlp4x64_tanh"
+METRIC = "weak-form residual+grad quad-pts/sec"
+UNIT = "quad-pts/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    power_w_max=max(pw) if pw else None, samples=len(sm))
+
+
+def cpu_feed(nx, ny, ntime, sample_tf):
+    """Bounded sample of the same workload for the CPU legs: the first `sample_tf` test functions."""
+    from varnet_b200 import workloads
+    feed, meta = workloads.shard_feed(nx, ny, ntime, 0, sample_tf, dtype=np.float32)
+    return feed, meta
+
+
+def run_cpu(args, nx, ny, ntime, lw, act, steps, warmup, budget_s=None):
+    """The reference's CPU path for this step: torch CPU FP32 double back-prop mirroring the TF graph
+    (oracle/torch_oracle.py; TF 1.10 is not installable), all host threads."""
+    import torch
+    from oracle import torch_oracle, graph_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_tf = 4096 if len(lw) and max(lw) >= 64 else 16384          # 2.6e5 / 1.0e6 points per CPU step
+    feed, meta = cpu_feed(nx, ny, ntime, sample_tf)
+    theta = graph_oracle.glorot_init(meta["inpDim"], list(lw), seed=0)
+    st = torch_oracle.CpuStepper(theta, feed, meta["dim"], meta["inpDim"], list(lw), act, True, meta["lossOpt"],
+                                 threads=cores)
+    P = sample_tf * meta["integNum"]
+    for _ in range(warmup):
+        st.step()
+    times = []
+    t_all = time.perf_counter()
+    for k in range(steps):
+        t0 = time.perf_counter()
+        st.step()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_all > budget_s and k >= 1:
+            break
+    dt = float(np.mean(times))
+    # the float64->float32 feed cast the reference pays on every sess.run (VarNetUtility.py:1044)
+    f64 = [np.asarray(feed[k], dtype=np.float64) for k in ("Input", "gcoef", "N", "dNt", "source")]
+    t0 = time.perf_counter()
+    for a in f64:
+        a.astype(np.float32)
+    cast = time.perf_counter() - t0
+    return dict(value=P / dt, ms_per_step=dt * 1e3, cores=cores, steps=len(times), P=P, sample_tf=sample_tf,
+                feed_cast_ms=cast * 1e3,
+                sample="first %d of %d test functions (%d quad points) of the same workload, torch-CPU FP32 "
+                       "double back-prop + TF-Adam, %d threads" % (sample_tf, nx * ny * ntime, P, cores))
+
+
+def main():
+    args = parse()
+    nx, ny, ntime, lw, act = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = dict(workload=args.workload, test_functions=nx * ny * ntime, integNum=64, quad_points=nx * ny * ntime * 64,
+                  mlp="%dx%d %s" % (len(lw), lw[0], act), inpDim=3, dim=2, sharding="contiguous test-function ranges per rank",
+                  l2_policy="per-GPU tables larger than L2, no flush")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_cpu(args, nx, ny, ntime, lw, act, args.steps, args.warmup)
+        line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps"], warmup=args.warmup,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32", data="synthetic", impl="reference", config=config,
+                    cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                      feed_cast_ms_per_step=r["feed_cast_ms"]),
+                    e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the varnet_b200 engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from varnet_b200 import workloads
+    from varnet_b200.backend import TFNN
+    from varnet_b200._capi import fp32_peak_tflops
+
+    # ---- this rank's tower: contiguous range of test functions
+    nt = nx * ny * ntime
+    n0, n1 = workloads.tower_range(nt, world, rank)
+    t_build = time.perf_counter()
+    feed, meta = workloads.shard_feed(nx, ny, ntime, n0, n1, dtype=np.float32)
+    # BC/IC rows are replicated on every tower and down-weighted by 1/puNum (VarNetUtility.py:900-901)
+    feed["w"] = np.array([1.0 / world, 1.0 / world, 1.0])
+    pinned = {}
+    for k in ("Input", "gcoef", "dNt", "biInput", "biLabel"):
+        t = torch.from_numpy(np.ascontiguousarray(feed[k])).pin_memory()
+        pinned[k] = t
+        feed[k] = t.numpy()
+    t_build = time.perf_counter() - t_build
+    procs = ["GPU:%d" % i for i in range(world)]
+    tf = TFNN(meta["dim"], meta["inpDim"], list(lw), "MLP", act, True, None, procs, None, meta["lossOpt"], "adam", 1e-3, seed=0)
+    tw = tf.compTowers[rank]
+    eng = tw.engine
+    fd = {getattr(tw, k): feed[k] for k in ("Input", "gcoef", "source", "N", "dNt", "biInput", "biLabel", "bDof",
+                                             "intShape", "integW", "biDimVal", "detJvec", "detJ", "w")}
+    P_local = (n1 - n0) * meta["integNum"]
+    P_total = nt * meta["integNum"]
+    h2d = sum(feed[k].nbytes for k in ("Input", "gcoef", "dNt", "biInput", "biLabel"))
+
+    def step():
+        return tf.sess.run([tf.optMinimize, tf.loss], feed_dict=fd)[1]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step()
+    eng.profile_enable(True)
+    eng.profile_read()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_step = ms / args.steps
+
+    # ---- e2e: host feed re-uploaded inside the timed region every step (pinned float32 -> H2D), loss read back
+    tf.feed_cache = False
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        te = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te[0])
+    ms_e2e /= args.e2e_steps
+    tf.feed_cache = True
+
+    if rank == 0:
+        flop_pt = workloads.algorithmic_flops_per_point(meta["inpDim"], meta["dim"], lw)
+        adj_ms, adj_n = prof["var_adj"]
+        fwd_ms, fwd_n = prof["var_fwd"]
+        kernel_ms = adj_ms / max(adj_n, 1)
+        # the adjoint kernel recomputes the forward sweep and does both adjoint GEMMs per layer: its
+        # algorithmic work is the whole residual+gradient count F_alg minus nothing (the separate
+        # forward pass that produces R_i is extra, non-algorithmic work and is NOT credited)
+        peak_tf = fp32_peak_tflops(local_rank)
+        achieved = flop_pt * P_local / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+        pk = peaks()
+        bytes_pt = 4 * (meta["inpDim"] + meta["dim"] + 1)
+        roofline = dict(bound="fp32", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf if peak_tf else None,
+                        traffic=None, kernel="vn_tile_kernel<MODE_VAR_ADJ>", kernel_ms=kernel_ms,
+                        kernel_share_of_step=kernel_ms / ms_step if ms_step else None,
+                        flop_per_point=flop_pt, points_per_launch=P_local,
+                        peak_source="FFMA microbenchmark (vn_fp32_peak_tflops) measured in this run",
+                        hbm=dict(bound="hbm", achieved=bytes_pt * P_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
+                                 peak=pk["hbm_gbs"], unit="GB/s", bytes_per_point=bytes_pt, peak_source=pk["source"]),
+                        other_kernels_ms=dict(var_fwd=fwd_ms / max(fwd_n, 1), segreduce=prof["segreduce"][0] / max(prof["segreduce"][1], 1),
+                                              bic=prof["bic"][0] / max(prof["bic"][1], 1), finalize=prof["finalize"][0] / max(prof["finalize"][1], 1),
+                                              optimizer=prof["optimizer"][0] / max(prof["optimizer"][1], 1)))
+        roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / pk["hbm_gbs"]
+        line = dict(metric=METRIC, value=P_total / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                    train_steps_per_sec=1e3 / ms_step, loss=float(loss), table_build_s=t_build,
+                    roofline=roofline,
+                    e2e=dict(value=P_total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                             ms_per_step=ms_e2e, api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False"),
+                    gpu_launches=int(launches), clocks=clocks, kernel_info=eng.kernel_info())
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                        ms_per_step=r["ms_per_step"], feed_cast_ms_per_step=r["feed_cast_ms"])
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    tf.sess.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,6 +35,8 @@ extern "C" {
 #define VN_OPT_ADAM 0        /* tf.train.AdamOptimizer, TFModel.py:184 */
 #define VN_OPT_RMSPROP 1     /* tf.train.RMSPropOptimizer, TFModel.py:186 */
 
+#define VN_PROF_SLOTS 8
+
 #define VN_OK 0
 #define VN_E_INVALID -1      /* bad argument (mirrors the reference's ValueError sites) */
 #define VN_E_CUDA -2         /* CUDA runtime error */
@@ -123,6 +125,16 @@ int vn_eval_f32(vn_engine* e, const float* X, int64_t n, float* u);
 int vn_eval_f64(vn_engine* e, const double* X, int64_t n, float* u);
 int vn_residual_f64(vn_engine* e, const double* X, const double* diff, const double* vel,
                     const double* diff_dx, const double* source, int64_t n, float* u, float* res);
+
+/* ---- measurement -----------------------------------------------------------
+ * Per-kernel device time from CUDA events recorded on the engine's stream around each launch
+ * (slots: 0 variational forward, 1 segmented reduce, 2 variational adjoint, 3 boundary/initial,
+ * 4 finalize, 5 optimizer).  vn_profile_read synchronises, returns the totals since the last
+ * read and resets them.  vn_fp32_peak_tflops runs an FFMA-only microbenchmark: the FP32
+ * roofline denominator measured on the same GPU in the same run. */
+int vn_profile_enable(vn_engine* e, int on);
+int vn_profile_read(vn_engine* e, double ms[VN_PROF_SLOTS], int64_t counts[VN_PROF_SLOTS]);
+int vn_fp32_peak_tflops(int device, int reps, double* tflops);
 
 /* ---- introspection for tests / bench --------------------------------------- */
 int vn_kernel_info(const vn_engine* e, char* buf, size_t buflen);   /* kernel family, tile, smem */

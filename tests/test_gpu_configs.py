@@ -1,0 +1,164 @@
+"""GPU: the reference's operator configurations end to end.
+
+(1) golden feed dicts produced by the reference's own table code -> CUDA engine vs the FP64 oracle's
+    stored loss / gradient / lossVec (1e-5 relative, BASELINE.json north_star);
+(2) the VarNet / TFNN API path (sess.run protocol) on the same configs;
+(3) size-independent properties at larger sizes: partition additivity of the loss and gradient over
+    test functions, tower-sum equivalence, determinism, descent of the training loss."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import configs
+from oracle import graph_oracle as go
+from tests.util import rel_inf, layer_slices, synth_feed, make_engine
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-5
+pytestmark = pytest.mark.gpu
+
+
+def golden_feed(z, b):
+    fd = {k: z["b%d_%s" % (b, k)] for k in ("Input", "biInput", "biLabel", "gcoef", "source", "N", "dNt", "bDof",
+                                             "intShape", "biDimVal", "detJvec", "detJ")}
+    fd["integW"] = None
+    fd["w"] = z["w"]
+    return fd
+
+
+@pytest.mark.parametrize("name", ["Operator_1Dt", "Operator_2Dt", "Operator_1DtMOR"])
+def test_engine_on_reference_feeds_matches_oracle(name):
+    z = np.load(os.path.join(GOLD, "feed_%s.npz" % name))
+    lw = [int(v) for v in z["layerWidth"]]
+    kw = dict(dim=int(z["dim"]), inpDim=int(z["inpDim"]), layerWidth=lw, activation="sigmoid",
+              timeDependent=bool(z["timeDependent"]),
+              lossOpt=dict(isSource=bool(z["isSource"]), integWflag=bool(z["integWflag"])))
+    for b in range(int(z["nbatch"])):
+        eng = make_engine(golden_feed(z, b), theta=z["theta"], **kw)
+        out = eng.loss_grad()
+        ref = z["b%d_oracle_scalars" % b]
+        for i, k in enumerate(("loss", "BCloss", "ICloss", "varLoss")):
+            assert abs(float(out[k]) - ref[i]) <= TOL * abs(ref[i]) + 1e-30, (k, out[k], ref[i])
+        g = z["b%d_oracle_grad" % b]
+        for nm, sl in layer_slices(kw["inpDim"], lw):
+            assert rel_inf(out["grad"][sl], g[sl]) <= TOL, nm
+        lv = eng.loss(lossVec=True)["lossVec"]
+        assert rel_inf(lv, z["b%d_oracle_lossVec" % b]) <= TOL
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["Operator_1Dt", "Operator_2Dt", "Operator_1DtMOR"])
+def test_varnet_api_path(name):
+    """VarNet(...) -> splitLoss / optimIter through TFNN.sess.run, checked against the oracle fed with
+    the very feed dict the host mirror produced."""
+    import varnet_b200
+    z = np.load(os.path.join(GOLD, "feed_%s.npz" % name))
+    bn = int(z["batchNum"])
+    vn = configs.BUILDERS[name](varnet_b200, float(z["scale"]), seed=11)
+    tf = vn.tfData
+    theta = tf.get_parameters()
+    fd = vn.fixData
+    fd.setFEdata()
+    Input, _, biInput, _ = vn.trainingPoints()
+    disc = None if vn.PDE.MORvar is None else vn.PDE.MORvar.discretizeArg(vn.MORdiscScheme)
+    tData = varnet_b200.ManageTrainData(Input, biInput, None if bn < 0 else bn, None, False, fd.MORbatchNum)
+    tData = vn.trainData(0, disc, tData)
+    w = np.array([10.0, 10.0, 1.0])
+    tData.updateDictFields('trainW', w.copy(), normalizeW=False)
+    kw = dict(dim=tf.dim, inpDim=tf.inpDim, layerWidth=tf.layerWidth, activation="sigmoid",
+              timeDependent=tf.timeDependent, lossOpt=tf.lossOpt)
+    tw = tf.compTowers[0]
+    # oracle on every mini-batch feed
+    refs = []
+    for fdict in tData.optimFeedicts:
+        plain = {k.name: v for k, v in fdict.items()}
+        refs.append(go.loss_and_grad(theta, plain, **kw))
+    bc, ic, var, lv = tData.splitLoss(tf, True)
+    assert abs(bc - refs[0]["BCloss"]) <= TOL * abs(refs[0]["BCloss"])
+    assert abs(ic - refs[0]["ICloss"]) <= TOL * abs(refs[0]["ICloss"])
+    assert abs(var - sum(r["varLoss"] for r in refs)) <= TOL * abs(sum(r["varLoss"] for r in refs))
+    assert rel_inf(lv.ravel(), np.concatenate([r["lossVec"] for r in refs])) <= TOL
+    # one optimizer step on the first mini-batch = TF-Adam on the oracle gradient
+    _, loss = tf.sess.run([tf.optMinimize, tf.loss], feed_dict=tData.optimFeedicts[0])
+    assert abs(loss - refs[0]["loss"]) <= TOL * abs(refs[0]["loss"])
+    th1, _, _ = go.adam_step(theta.astype(np.float64), refs[0]["grad"], 0, 0, 1, lr=tf.learning_rate)
+    assert rel_inf(tf.get_parameters(), th1) <= 2e-6
+    # evaluation node
+    u = vn.evaluate() if vn.PDE.MORvar is None else vn.evaluate(batch=0)
+    Xe = fd.uniform_input if vn.PDE.MORvar is None else np.hstack([fd.uniform_input, np.tile(disc[0][0:1], [len(fd.uniform_input), 1])])
+    ue = go.mlp_value(tf.get_parameters().astype(np.float64), Xe.astype(np.float32).astype(np.float64), tf.inpDim,
+                      tf.layerWidth, go.ACT_SIGMOID)
+    assert rel_inf(u.ravel(), ue) <= TOL
+    tf.sess.close()
+
+
+def test_train_loop_descends_and_checkpoints():
+    import varnet_b200
+    vn = configs.operator_1dt(varnet_b200, 0.3, seed=5)
+    with tempfile.TemporaryDirectory() as d:
+        res = vn.train(d, weight=[10., 10., 1.], epochNum=60, saveFreq=20, verbose=False)
+        assert len(res.loss) == 60
+        assert abs(res.loss[0] - 1e6) <= 1e6 * 1e-3          # initial weighted loss normalised to 1e6 (VarNet.py:1094-1131)
+        assert res.loss[-1] < res.loss[0]
+        before = vn.tfData.get_parameters().copy()
+        fname = vn.loadModel()
+        assert os.path.exists(fname)
+        assert vn.tfData.get_parameters().shape == before.shape
+    vn.tfData.sess.close()
+
+
+def test_partition_additivity_and_determinism_at_scale():
+    """Size-independent properties on a large batch (no oracle at this size): (a) loss and gradient of
+    the whole batch equal the sums over any partition of the test functions (with the BC/IC term
+    counted once) — this is what the multi-GPU all-reduce relies on; (b) bitwise run-to-run determinism."""
+    rng = np.random.RandomState(0)
+    dim, inpDim, lw, nb, q = 2, 3, [64, 64, 64, 64], 20000, 64
+    feed = synth_feed(rng, dim, inpDim, nb, q, 3000, 2500)
+    for k in ("Input", "gcoef", "dNt"):
+        feed[k] = feed[k].astype(np.float32)
+    theta = go.glorot_init(inpDim, lw, seed=3)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True,
+              lossOpt=dict(isSource=False, integWflag=False))
+    whole = make_engine(feed, theta=theta, dtype=np.float32, **kw)
+    a = whole.loss_grad(); b = whole.loss_grad()
+    assert np.array_equal(a["grad"], b["grad"]) and a["loss"] == b["loss"]
+    cut = 7777
+    gsum = np.zeros_like(a["grad"], dtype=np.float64); lsum = 0.0
+    for lo, hi, wfac in ((0, cut, 1.0), (cut, nb, 0.0)):
+        f = dict(feed)
+        for k in ("Input", "gcoef", "dNt"):
+            f[k] = feed[k][lo * q:hi * q]
+        f["intShape"] = [hi - lo, q]
+        f["w"] = feed["w"] * np.array([wfac, wfac, 1.0])
+        e = make_engine(f, theta=theta, dtype=np.float32, **kw)
+        r = e.loss_grad()
+        gsum += r["grad"]; lsum += float(r["loss"])
+        e.close()
+    assert abs(lsum - float(a["loss"])) <= 2e-6 * abs(float(a["loss"]))
+    for nm, sl in layer_slices(inpDim, lw):
+        assert rel_inf(gsum[sl], a["grad"][sl]) <= 5e-6, nm
+    whole.close()
+
+
+def test_feed_identity_cache_and_reupload():
+    """The shim uploads a feed array only when it is replaced (reference re-feeds every step,
+    VarNetUtility.py:1044) and must notice replaced arrays (updateDictFields/shuffleTrainData)."""
+    import varnet_b200
+    vn = configs.operator_1dt(varnet_b200, 0.2, seed=1)
+    tf = vn.tfData
+    fd = vn.fixData; fd.setFEdata()
+    Input, _, biInput, _ = vn.trainingPoints()
+    tData = varnet_b200.ManageTrainData(Input, biInput, 2, None, False, 1)
+    tData = vn.trainData(0, None, tData)
+    tData.updateDictFields('trainW', np.array([1., 1., 1.]))
+    n0 = tf.uploads
+    tData.optimIter(tf); first = tf.uploads - n0
+    tData.optimIter(tf); second = tf.uploads - n0 - first
+    assert first >= 2 and second == first - 1 or second <= first   # points re-uploaded per mini-batch, BC/IC rows cached
+    np.random.seed(0)
+    tData.shuffleTrainData(fd)
+    l1 = tData.optimIter(tf)
+    assert np.isfinite(l1)
+    tf.sess.close()

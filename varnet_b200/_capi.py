@@ -52,6 +52,9 @@ SIGNATURES = {
     "vn_eval_f32": (C.c_int, [_vp, _f32p, _i64, _f32p]),
     "vn_eval_f64": (C.c_int, [_vp, _f64p, _i64, _f32p]),
     "vn_residual_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _f32p, _f32p]),
+    "vn_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "vn_profile_read": (C.c_int, [_vp, _f64p, C.POINTER(_i64)]),
+    "vn_fp32_peak_tflops": (C.c_int, [C.c_int, C.c_int, _f64p]),
     "vn_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "vn_launch_count": (_i64, [_vp]),
 }
@@ -97,6 +100,16 @@ def _prep(a, dtype, shape=None):
     if shape is not None:
         arr = arr.reshape(shape)
     return arr
+
+
+def fp32_peak_tflops(device=0, reps=5):
+    """Measured FP32 FMA peak of `device` (FFMA-only microbenchmark in the engine library)."""
+    lib = load_library()
+    out = C.c_double()
+    rc = lib.vn_fp32_peak_tflops(int(device), int(reps), C.byref(out))
+    if rc != 0:
+        raise EngineError(rc, "vn_fp32_peak_tflops failed")
+    return float(out.value)
 
 
 class Engine:
@@ -273,6 +286,16 @@ class Engine:
         self._check(self.lib.vn_residual_f64(self._h, _ptr(X, C.c_double), _ptr(d, C.c_double), _ptr(v, C.c_double),
                                              _ptr(dd, C.c_double), _ptr(s, C.c_double), n, _ptr(u, C.c_float), _ptr(r, C.c_float)))
         return u, r
+
+    PROF_SLOTS = ("var_fwd", "segreduce", "var_adj", "bic", "finalize", "optimizer")
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.vn_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        ms = (C.c_double * 8)(); cnt = (_i64 * 8)()
+        self._check(self.lib.vn_profile_read(self._h, ms, cnt))
+        return {name: (ms[i], int(cnt[i])) for i, name in enumerate(self.PROF_SLOTS)}
 
     def kernel_info(self):
         buf = C.create_string_buffer(1024)

@@ -1,0 +1,454 @@
+"""`TFNN`: the drop-in replacement of the reference's TensorFlow backend object.
+
+The reference's compute backend is the `TFNN` object (`/root/reference/TFModel.py:54-437`)
+held as `VarNet.tfData` and driven through `sess.run(nodes, feed_dict)`
+(`VarNetUtility.py:1044,1080,1086,1142`).  This module provides an object with the same
+constructor signature (`TFModel.py:85-86`), the same attributes the callers touch
+ and the same call protocol, backed by the CUDA engine
+(include/varnet_b200.h) instead of a TensorFlow graph:
+
+    sess.run([optMinimize, loss], feed_dict)      -> vn_loss_grad (+ all-reduce) + vn_optimizer_step
+    sess.run([BCloss, ICloss], feed_dict)         -> vn_loss
+    sess.run([varLoss, lossVec], feed_dict)       -> vn_loss
+    sess.run([model(Input), residual], feed_dict) -> vn_eval / vn_residual
+
+One reference "tower" (`TFModel.py:253-289`) = one engine = one GPU.  Towers of this process are
+`tower.local`; under `torchrun` every rank owns the tower whose index equals its rank and the
+per-tower gradients/losses are summed with one NCCL all-reduce of the engine's gradient buffer
+(the reference sums them with `tf.reduce_sum` on the controller, `TFModel.py:342-377,315-318`).
+
+There is no CPU path: without the compiled library or a CUDA device construction raises.
+"""
+import os
+
+import numpy as np
+
+from ._capi import Engine, EngineError  # noqa: F401
+
+
+# ------------------------------------------------------------------ graph stand-ins
+class Node:
+    """A placeholder or fetchable node of one tower (or of the summed graph: tower=None)."""
+    __slots__ = ("name", "tower", "arg")
+
+    def __init__(self, name, tower=None, arg=None):
+        self.name, self.tower, self.arg = name, tower, arg
+
+    def __repr__(self):
+        return "<Node %s tower=%s>" % (self.name, self.tower)
+
+
+_PLACEHOLDERS = ("Input", "biInput", "biLabel", "bDof", "w", "intShape", "detJ", "integW", "biDimVal", "source",
+                 "gcoef", "N", "dNt", "detJvec", "diff", "vel", "diff_dx")
+_FETCHES = ("loss", "BCloss", "ICloss", "varLoss", "lossVec", "residual", "grad")
+
+
+class Tower:
+    """Feed keys and fetch nodes of one computational tower (`NNModel`, TFModel.py:442-772)."""
+
+    def __init__(self, index, local, engine):
+        self.index, self.local, self.engine = index, local, engine
+        for k in _PLACEHOLDERS + _FETCHES:
+            setattr(self, k, Node(k, index))
+        self._tokens = {}
+
+
+class Model:
+    """Stand-in for the shared Keras `Sequential` (TFModel.py:195-249)."""
+
+    def __init__(self, inpDim, layerWidth):
+        self.inpDim, self.layerWidth = inpDim, list(layerWidth)
+
+    def __call__(self, node):
+        if not isinstance(node, Node):
+            raise TypeError("model(...) expects a tower's Input placeholder")
+        return Node("model", node.tower, node)
+
+    def count_params(self):
+        dims = [self.inpDim] + self.layerWidth + [1]
+        return int(sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1)))
+
+    def summary(self):
+        dims = [self.inpDim] + self.layerWidth + [1]
+        for i in range(len(dims) - 1):
+            name = "dense_%d" % i if i < len(dims) - 2 else "output"
+            print("%-10s (None, %d)  params %d" % (name, dims[i + 1], dims[i] * dims[i + 1] + dims[i + 1]))
+        print("Total params: %d" % self.count_params())
+
+
+class _Graph:
+    """`with graph.as_default():` is a no-op here (VarNet.py:1290,1411)."""
+
+    def as_default(self):
+        return self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class GlobalInit(Node):
+    """What `tf.global_variables_initializer()` becomes: sess.run(GlobalInit()) re-draws weights."""
+
+    def __init__(self):
+        super().__init__("global_variables_initializer")
+
+
+def glorot_uniform(inpDim, layerWidth, rng):
+    """Keras default init of every Dense layer: glorot_uniform kernel, zero bias (TFModel.py:210-242)."""
+    dims = [inpDim] + list(layerWidth) + [1]
+    parts = []
+    for i in range(len(dims) - 1):
+        lim = np.sqrt(6.0 / (dims[i] + dims[i + 1]))
+        parts.append(rng.uniform(-lim, lim, size=dims[i] * dims[i + 1]))
+        parts.append(np.zeros(dims[i + 1]))
+    return np.concatenate(parts).astype(np.float32)
+
+
+# ------------------------------------------------------------------ helpers
+def _token(v):
+    """Cheap identity token of a feed value: re-upload only when it changes."""
+    if isinstance(v, np.ndarray):
+        flat = v.reshape(-1) if v.flags.c_contiguous else None
+        probe = ()
+        if flat is not None and flat.size and v.dtype != object:
+            n = flat.size
+            probe = (float(flat[0]), float(flat[n // 2]), float(flat[-1]))
+        return ("a", id(v), v.shape, str(v.dtype), v.__array_interface__["data"][0], probe)
+    if isinstance(v, (list, tuple)):
+        return ("l", tuple(_token(x) for x in v))
+    return ("s", v)
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+class _DevView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _parse_device(spec):
+    """'GPU:i' -> i ('CPU:*' is rejected: the engine has no CPU path)."""
+    s = str(spec).upper().replace("/DEVICE:", "")
+    if s.startswith("GPU:"):
+        return int(s[4:])
+    raise ValueError("requested processor %s is unavailable! (the B200 engine runs on GPUs only)" % spec)
+
+
+# ------------------------------------------------------------------ session
+class Session:
+    def __init__(self, owner):
+        self._o = owner
+
+    def close(self):
+        for tw in self._o.compTowers:
+            if tw.engine is not None:
+                tw.engine.close()
+
+    # -- feed handling
+    def _sync_feeds(self, feed, need_points=True, need_bic=True):
+        by_tower = {}
+        for key, val in (feed or {}).items():
+            if isinstance(key, Node) and key.tower is not None:
+                by_tower.setdefault(key.tower, {})[key.name] = val
+        for tw in self._o.compTowers:
+            if not tw.local or tw.index not in by_tower:
+                continue
+            fd, eng, tok = by_tower[tw.index], tw.engine, tw._tokens
+            if need_points and "Input" in fd and "intShape" in fd:
+                names = ("Input", "gcoef", "source", "N", "dNt", "intShape", "integW", "detJ", "detJvec")
+                t = tuple(_token(fd.get(k)) for k in names)
+                if tok.get("points") != t or not self._o.feed_cache:
+                    eng.upload_points(fd["Input"], fd["gcoef"], fd.get("source"), fd.get("N"), fd.get("dNt"),
+                                      fd["intShape"], fd.get("integW"), fd["detJ"], bool(fd.get("detJvec", False)))
+                    tok["points"] = t
+                    self._o.uploads += 1
+            if need_bic and "biInput" in fd:
+                names = ("biInput", "biLabel", "bDof", "biDimVal")
+                t = tuple(_token(fd.get(k)) for k in names)
+                if tok.get("bic") != t or not self._o.feed_cache:
+                    eng.upload_bic(fd["biInput"], fd["biLabel"], int(fd["bDof"]), float(fd["biDimVal"]))
+                    tok["bic"] = t
+                    self._o.uploads += 1
+            if "w" in fd:
+                w = np.asarray(fd["w"], dtype=np.float64).reshape(3)
+                t = tuple(w.tolist())
+                if tok.get("w") != t:
+                    eng.set_weights(w)
+                    tok["w"] = t
+        return by_tower
+
+    def _local_towers(self):
+        return [tw for tw in self._o.compTowers if tw.local]
+
+    def _reduce_scalars(self, vals):
+        """Sum [loss, BCloss, ICloss, varLoss] over the towers of other ranks."""
+        dist = _dist()
+        if dist is None:
+            return vals
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda:%d" % self._local_towers()[0].engine.cfg.device)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def _forward(self, want_lossvec):
+        tot = np.zeros(4)
+        first = None
+        lvs = {}
+        for tw in self._local_towers():
+            r = tw.engine.loss(lossVec=want_lossvec)
+            vals = np.array([r["loss"], r["BCloss"], r["ICloss"], r["varLoss"]], dtype=np.float64)
+            if tw.index == 0:
+                first = vals
+            tot += vals
+            if want_lossvec:
+                lvs[tw.index] = r["lossVec"].reshape(-1, 1)
+        tot = self._reduce_scalars(tot)
+        lossVec = None
+        if want_lossvec:
+            dist = _dist()
+            if dist is not None:
+                gathered = [None] * dist.get_world_size()
+                dist.all_gather_object(gathered, lvs)
+                lvs = {k: v for d in gathered for k, v in d.items()}
+            lossVec = np.vstack([lvs[k] for k in sorted(lvs)])
+        return tot, first, lossVec
+
+    def _train_step(self):
+        o = self._o
+        towers = self._local_towers()
+        dist = _dist()
+        if dist is None and len(towers) == 1:
+            loss = towers[0].engine.train_step(o.learning_rate, fetch_loss=True)
+            return float(loss)
+        import torch
+        views = []
+        for tw in towers:
+            tw.engine.loss_grad(fetch=False)
+            ptr, n = tw.engine.grad_buffer()
+            dev = "cuda:%d" % tw.engine.cfg.device
+            with torch.cuda.device(dev):
+                views.append(torch.as_tensor(_DevView(ptr, n), device=dev))
+        if len(towers) > 1:                       # single process, several GPUs: sum on the controller
+            ctrl = views[0]
+            torch.cuda.synchronize()
+            total = ctrl.clone()
+            for v in views[1:]:
+                total += v.to(ctrl.device)
+            for v in views:
+                v.copy_(total.to(v.device))
+            torch.cuda.synchronize()
+        if dist is not None:
+            dist.all_reduce(views[0])             # NCCL SUM over NVLink: [grad | loss, BCloss, ICloss, varLoss]
+        for tw in towers:
+            tw.engine.optimizer_step(o.learning_rate)
+        n = towers[0].engine.nparam
+        return float(views[0][n].item())
+
+    # -- the protocol
+    def run(self, fetches, feed_dict=None):
+        o = self._o
+        single = not isinstance(fetches, (list, tuple))
+        flist = [fetches] if single else list(fetches)
+        names = [f.name if isinstance(f, Node) else None for f in flist]
+        out = [None] * len(flist)
+
+        if any(isinstance(f, GlobalInit) for f in flist):
+            o.initialize_variables()
+            return None if single else out
+
+        if "model" in names or "residual" in names:
+            tw0 = o.compTowers[0]
+            if not tw0.local:
+                raise RuntimeError("evaluation nodes live on tower 0; call from the rank that owns it")
+            fd = {k.name: v for k, v in (feed_dict or {}).items() if isinstance(k, Node)}
+            X = fd["Input"]
+            u = res = None
+            if "residual" in names:
+                u, res = tw0.engine.residual(X, fd["diff"], fd["vel"], fd["diff_dx"], fd["source"])
+            else:
+                u = tw0.engine.eval(X)
+            for i, nm in enumerate(names):
+                if nm == "model":
+                    out[i] = u.reshape(-1, 1)
+                elif nm == "residual":
+                    out[i] = res.reshape(-1, 1)
+            return out[0] if single else out
+
+        train = "optMinimize" in names
+        self._sync_feeds(feed_dict)
+        if train:
+            loss = self._train_step()
+            o.step_count += 1
+            for i, nm in enumerate(names):
+                if nm == "loss":
+                    out[i] = np.float32(loss)
+            return out[0] if single else out
+        wanted = [nm for nm in names if nm is not None]
+        if wanted:
+            tot, first, lossVec = self._forward("lossVec" in wanted)
+            for i, (f, nm) in enumerate(zip(flist, names)):
+                if nm is None:
+                    out[i] = []                    # e.g. the empty placeholder fetch in splitLoss (VU:1076)
+                    continue
+                idx = {"loss": 0, "BCloss": 1, "ICloss": 2, "varLoss": 3}.get(nm)
+                if idx is not None:
+                    # tower-level BC/IC nodes (compTowers[0].BCloss) are per-tower values; graph-level ones are sums
+                    src = first if (f.tower is not None and first is not None) else tot
+                    out[i] = np.float32(src[idx])
+                elif nm == "lossVec":
+                    out[i] = lossVec
+                else:
+                    raise ValueError("cannot fetch node %r" % (f,))
+        else:
+            out = [[] for _ in flist]
+        return out[0] if single else out
+
+
+class Saver:
+    """Flat-vector checkpoint replacing tf.train.Saver(max_to_keep=2) (TFModel.py:307)."""
+
+    def __init__(self, owner, max_to_keep=2):
+        self._o, self._keep, self._files = owner, max_to_keep, []
+
+    def save(self, sess, path, global_step=None):
+        fname = "%s-%s.npz" % (path, global_step) if global_step is not None else path + ".npz"
+        eng = next(tw.engine for tw in self._o.compTowers if tw.local)
+        m, v, step = eng.get_optimizer_state()
+        np.savez(fname, theta=eng.get_params(), m=m, v=v, step=step, layerWidth=np.array(self._o.layerWidth),
+                 inpDim=self._o.inpDim)
+        self._files.append(fname)
+        while len(self._files) > self._keep:
+            old = self._files.pop(0)
+            if os.path.exists(old):
+                os.remove(old)
+        return fname
+
+    def restore(self, sess, fname):
+        if not fname.endswith(".npz"):
+            fname += ".npz"
+        z = np.load(fname)
+        for tw in self._o.compTowers:
+            if tw.local:
+                tw.engine.set_params(z["theta"])
+                tw.engine.set_optimizer_state(z["m"], z["v"], int(z["step"]))
+
+
+# ------------------------------------------------------------------ TFNN
+class TFNN:
+    """Same constructor as the reference (`TFModel.py:85-86`).
+
+    processors: None (first GPU), 'GPU:i' or a list of them — one tower per entry.  Under torchrun
+    with world_size == len(processors), rank r owns tower r on its LOCAL_RANK GPU.
+    """
+
+    def __init__(self, dim, inpDim, layerWidth, modelId, activationFun, timeDependent, RNNdata, processors,
+                 controller, lossOpt, optimizer_name, learning_rate, seed=None):
+        depth = len(layerWidth)
+        if type(activationFun) == str:
+            activationFun = [activationFun] * depth
+        elif type(activationFun) == list and len(activationFun) == 1:
+            activationFun = activationFun * depth
+        elif not len(activationFun) == depth:
+            raise ValueError('activation function list is incompatible with number of layers!')
+        if modelId != 'MLP':
+            raise ValueError('only the MLP model is supported (the reference RNN path is incomplete, TFModel.py:225)')
+        if learning_rate < 0.0:
+            raise ValueError('learning rate must be positive!')
+        if optimizer_name.lower() == 'rms':
+            optimizer_name = 'rmsprop'
+        if optimizer_name.lower() not in ('adam', 'rmsprop'):
+            raise ValueError('unknown optimizer requested!')
+        if processors is None:
+            processors = ['GPU:0']
+        elif not isinstance(processors, list):
+            processors = [processors]
+        devices = [_parse_device(p) for p in processors]
+        puNum = len(devices)
+
+        self.dim, self.inpDim, self.depth = dim, inpDim, depth
+        self.layerWidth, self.modelId, self.activationFun = layerWidth, modelId, activationFun
+        self.timeDependent, self.RNNdata = timeDependent, RNNdata
+        self.processorNum = puNum
+        self.processors = ['/device:GPU:%d' % d for d in devices]
+        self.controller = self.processors[0] if controller is None else controller
+        self.lossOpt, self.optimizer_name, self.learning_rate = lossOpt, optimizer_name, learning_rate
+        self.uploads, self.step_count = 0, 0
+        # True: a feed array is uploaded only when it is replaced by a new object; False: every
+        # sess.run re-uploads its feeds, like the reference's per-step feed (VarNetUtility.py:1044)
+        self.feed_cache = True
+        self._rng = np.random.RandomState(seed)
+
+        dist = _dist()
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world_size = dist.get_world_size() if dist is not None else 1
+        if dist is not None and self.world_size != puNum:
+            raise ValueError('torchrun world size (%d) must equal the number of processors (%d)' % (self.world_size, puNum))
+        local_dev = int(os.environ.get("LOCAL_RANK", "0")) if dist is not None else None
+
+        self.model = Model(inpDim, layerWidth)
+        self.compTowers = []
+        for i, d in enumerate(devices):
+            local = (dist is None) or (i == self.rank)
+            eng = None
+            if local:
+                eng = Engine(dim, inpDim, layerWidth, activationFun[0], timeDependent, lossOpt['isSource'],
+                             lossOpt['integWflag'], optimizer=optimizer_name,
+                             device=local_dev if local_dev is not None else d)
+            self.compTowers.append(Tower(i, local, eng))
+        if len({a.lower() for a in activationFun}) != 1:
+            raise ValueError('a single activation function for all hidden layers is supported')
+
+        self.graph = _Graph()
+        self.loss, self.BCloss, self.ICloss = Node("loss"), Node("BCloss"), Node("ICloss")
+        self.varLoss, self.lossVec = Node("varLoss"), Node("lossVec")
+        self.optMinimize, self.step = Node("optMinimize"), Node("step")
+        self.saver = Saver(self)
+        self.sess = Session(self)
+        self.initialize_variables()
+
+    # weights are shared by all towers (TFModel.py:180): every engine holds the same copy
+    def initialize_variables(self):
+        theta = glorot_uniform(self.inpDim, self.layerWidth, self._rng)
+        dist = _dist()
+        if dist is not None:
+            box = [theta]
+            dist.broadcast_object_list(box, src=0)
+            theta = box[0]
+        self.set_parameters(theta)
+
+    def set_parameters(self, theta):
+        for tw in self.compTowers:
+            if tw.local:
+                tw.engine.set_params(theta)
+
+    def get_parameters(self):
+        return next(tw.engine for tw in self.compTowers if tw.local).get_params()
+
+    def trainable_variables(self):
+        """[(name, array)] in Keras order, for saveNNparam-style exports (VarNet.py:2197-2239)."""
+        theta = self.get_parameters()
+        dims = [self.inpDim] + list(self.layerWidth) + [1]
+        out, off = [], 0
+        for i in range(len(dims) - 1):
+            name = "dense_%d" % i if i < len(dims) - 2 else "output"
+            n = dims[i] * dims[i + 1]
+            out.append((name + "/kernel", theta[off:off + n].reshape(dims[i], dims[i + 1]))); off += n
+            out.append((name + "/bias", theta[off:off + dims[i + 1]])); off += dims[i + 1]
+        return out
+
+    def get_available_gpus(self):
+        import torch
+        return ['/device:GPU:%d' % i for i in range(torch.cuda.device_count())]

@@ -12,6 +12,7 @@
 
 #include "../../include/varnet_b200.h"
 #include "vn_dispatch.h"
+#include <utility>
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -212,6 +213,7 @@ __global__ void vn_cast_kernel(const T* __restrict__ in, float* __restrict__ out
 }
 
 // ------------------------------------------------------------------ engine
+enum { PK_VAR_FWD = 0, PK_SEG = 1, PK_VAR_ADJ = 2, PK_BIC = 3, PK_FINAL = 4, PK_OPT = 5 };
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
     cudaError_t ensure(size_t need) {
@@ -248,6 +250,26 @@ struct vn_engine {
     // geometry
     TileGeom gVarFwd, gVarAdj, gBicFwd, gBicAdj, gEval;
     bool weightsSet = false;
+    // optional per-kernel CUDA-event timing (vn_profile_enable / vn_profile_read)
+    bool profOn = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profPending[VN_PROF_SLOTS];
+    double profMs[VN_PROF_SLOTS] = {0};
+    int64_t profCnt[VN_PROF_SLOTS] = {0};
+};
+
+// RAII bracket: records an event pair around a kernel launch on the engine's stream when profiling is on
+struct ProfScope {
+    vn_engine* e; int slot; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(vn_engine* e_, int slot_) : e(e_), slot(slot_) {
+        if (!e->profOn) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, e->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, e->stream);
+        e->profPending[slot].push_back({a, b});
+    }
 };
 
 static const int kPad = 128;    // point-table padding: multiple of every tile size
@@ -583,6 +605,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         const TileGeom& g = e->gVarFwd;
         a.ntiles = (int)(e->pstride / g.TP);
         const int grid = std::min(a.ntiles, 2 * e->numSMs);
+        ProfScope ps(e, PK_VAR_FWD);
         CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
     }
     // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
@@ -592,6 +615,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->integNum; s.detJ = e->detJ.as<float>();
         s.detJvec = e->detJvec; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
         s.blockSum = e->segSum.as<double>();
+        ProfScope ps(e, PK_SEG);
         vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
         CK(cudaGetLastError());
     }
@@ -601,6 +625,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         const TileGeom& g = e->gVarAdj;
         a.ntiles = (int)(e->pstride / g.TP);
         a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+        ProfScope ps(e, PK_VAR_ADJ);
         CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_ADJ, a, e->gridVar, g.smemBytes, st));
         e->launches++;
     }
@@ -612,6 +637,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         a.ntiles = (int)(e->bstride / g.TP);
         a.part = e->partBic.as<double>(); a.psz = g.pl.psz;
         const int grid = needGrad ? e->gridBic : std::min(a.ntiles, 2 * e->numSMs);
+        ProfScope ps(e, PK_BIC);
         CK(vn_tile_launch(1, e->wclass, c.act, mode, a, grid, g.smemBytes, st));
         e->launches++;
     }
@@ -627,6 +653,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
         const int nb = needGrad ? (e->net.nparam + 127) / 128 : 0;
+        ProfScope ps(e, PK_FINAL);
         vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
         CK(cudaGetLastError());
         e->launches++;
@@ -673,6 +700,7 @@ extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
     if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
     CK(cudaSetDevice(e->cfg.device));
     const int np = e->net.nparam;
+    ProfScope ps(e, PK_OPT);
     if (e->cfg.optimizer == VN_OPT_ADAM)
         vn_adam_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->m.as<float>(), e->v.as<float>(),
                                                                 e->gbuf.as<float>(), np, lr, e->corrbuf.as<double>());
@@ -733,6 +761,30 @@ extern "C" int vn_residual_f64(vn_engine* e, const double*, const double*, const
                                int64_t, float*, float*) {
     (void)e;
     return fail(VN_E_UNSUPPORTED, "strong-form residual kernel not built yet");
+}
+
+extern "C" int vn_profile_enable(vn_engine* e, int on) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    e->profOn = on != 0;
+    return VN_OK;
+}
+// Accumulated device time (ms) and launch counts per kernel slot since the last read:
+// 0 var forward, 1 segmented reduce, 2 var adjoint, 3 boundary/initial, 4 finalize, 5 optimizer.
+extern "C" int vn_profile_read(vn_engine* e, double ms[VN_PROF_SLOTS], int64_t counts[VN_PROF_SLOTS]) {
+    if (!e || !ms || !counts) return fail(VN_E_INVALID, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < VN_PROF_SLOTS; ++k) {
+        for (auto& pr : e->profPending[k]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { e->profMs[k] += t; e->profCnt[k]++; }
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        e->profPending[k].clear();
+        ms[k] = e->profMs[k]; counts[k] = e->profCnt[k];
+        e->profMs[k] = 0.0; e->profCnt[k] = 0;
+    }
+    return VN_OK;
 }
 
 extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
