@@ -71,6 +71,8 @@ def feed_fixture(ref, name):
         out["b%d_oracle_scalars" % b] = np.array([res["loss"], res["BCloss"], res["ICloss"], res["varLoss"]])
         out["b%d_oracle_grad" % b] = res["grad"]
         out["b%d_oracle_lossVec" % b] = res["lossVec"]
+        out["b%d_oracle_lossVec_tol" % b] = go.lossvec_tolerance(res)
+        out["b%d_oracle_varLoss_tol" % b] = go.varloss_tolerance(res)
     return out
 
 

@@ -39,13 +39,20 @@ def test_engine_on_reference_feeds_matches_oracle(name):
         eng = make_engine(golden_feed(z, b), theta=z["theta"], **kw)
         out = eng.loss_grad()
         ref = z["b%d_oracle_scalars" % b]
+        # varLoss sums squares of cancelling sums R_i (terms ~1e3 x |R_i| on these tables): 1e-5 relative
+        # plus the accumulated FP32 conditioning bound (oracle.graph_oracle.varloss_tolerance)
+        vtol = float(z["b%d_oracle_varLoss_tol" % b])
+        tols = dict(loss=TOL * abs(ref[0]) + float(z["w"][2]) * vtol, BCloss=TOL * abs(ref[1]), ICloss=TOL * abs(ref[2]),
+                    varLoss=vtol)
         for i, k in enumerate(("loss", "BCloss", "ICloss", "varLoss")):
-            assert abs(float(out[k]) - ref[i]) <= TOL * abs(ref[i]) + 1e-30, (k, out[k], ref[i])
+            assert abs(float(out[k]) - ref[i]) <= tols[k] + 1e-30, (k, out[k], ref[i], tols[k])
         g = z["b%d_oracle_grad" % b]
         for nm, sl in layer_slices(kw["inpDim"], lw):
             assert rel_inf(out["grad"][sl], g[sl]) <= TOL, nm
+        # per-test-function field: R_i is a cancelling sum, so the bound is conditioning-aware
+        # (oracle.graph_oracle.lossvec_tolerance); the summed varLoss above holds the 1e-5 bar
         lv = eng.loss(lossVec=True)["lossVec"]
-        assert rel_inf(lv, z["b%d_oracle_lossVec" % b]) <= TOL
+        assert np.all(np.abs(lv - z["b%d_oracle_lossVec" % b]) <= z["b%d_oracle_lossVec_tol" % b])
         eng.close()
 
 
@@ -78,11 +85,13 @@ def test_varnet_api_path(name):
     bc, ic, var, lv = tData.splitLoss(tf, True)
     assert abs(bc - refs[0]["BCloss"]) <= TOL * abs(refs[0]["BCloss"])
     assert abs(ic - refs[0]["ICloss"]) <= TOL * abs(refs[0]["ICloss"])
-    assert abs(var - sum(r["varLoss"] for r in refs)) <= TOL * abs(sum(r["varLoss"] for r in refs))
-    assert rel_inf(lv.ravel(), np.concatenate([r["lossVec"] for r in refs])) <= TOL
+    assert abs(var - sum(r["varLoss"] for r in refs)) <= sum(go.varloss_tolerance(r) for r in refs)
+    lv_ref = np.concatenate([r["lossVec"] for r in refs])
+    lv_tol = np.concatenate([go.lossvec_tolerance(r) for r in refs])
+    assert np.all(np.abs(lv.ravel() - lv_ref) <= lv_tol)
     # one optimizer step on the first mini-batch = TF-Adam on the oracle gradient
     _, loss = tf.sess.run([tf.optMinimize, tf.loss], feed_dict=tData.optimFeedicts[0])
-    assert abs(loss - refs[0]["loss"]) <= TOL * abs(refs[0]["loss"])
+    assert abs(loss - refs[0]["loss"]) <= TOL * abs(refs[0]["loss"]) + w[2] * go.varloss_tolerance(refs[0])
     th1, _, _ = go.adam_step(theta.astype(np.float64), refs[0]["grad"], 0, 0, 1, lr=tf.learning_rate)
     assert rel_inf(tf.get_parameters(), th1) <= 2e-6
     # evaluation node
@@ -156,7 +165,7 @@ def test_feed_identity_cache_and_reupload():
     n0 = tf.uploads
     tData.optimIter(tf); first = tf.uploads - n0
     tData.optimIter(tf); second = tf.uploads - n0 - first
-    assert first >= 2 and second == first - 1 or second <= first   # points re-uploaded per mini-batch, BC/IC rows cached
+    assert (first, second) == (3, 2)   # 2 mini-batch point tables per epoch; BC/IC rows uploaded once, then cached
     np.random.seed(0)
     tData.shuffleTrainData(fd)
     l1 = tData.optimIter(tf)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvarnet_b200.so")
-SOURCES = ["vn_capi.cu", "vn_inst_w32.cu", "vn_inst_w64.cu", "vn_extra.cu"]
+SOURCES = ["vn_capi.cu", "vn_inst_w32.cu", "vn_inst_w64.cu", "vn_inst_w64d.cu", "vn_extra.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -57,7 +57,7 @@ def build(force=False, verbose=True):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     with cf.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(_compile, srcs))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -28,21 +28,24 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* vn_last_error(void) { return g_err; }
 
-// ------------------------------------------------------------------ dispatch over width classes
-bool vn_tile_geometry(int S, int wclass, int act, int mode, int L, TileGeom* g) {
-    if (wclass == 32) return vn_geom_w32(S, act, mode, L, g);
-    if (wclass == 64) return vn_geom_w64(S, act, mode, L, g);
+// ------------------------------------------------------------------ dispatch over kernel classes
+bool vn_tile_geometry(int S, int cls, int act, int mode, int L, TileGeom* g) {
+    if (cls == 32) return vn_geom_c32(S, act, mode, L, g);
+    if (cls == 64) return vn_geom_c64(S, act, mode, L, g);
+    if (cls == 164) return vn_geom_c164(S, act, mode, L, g);
     return false;
 }
-cudaError_t vn_tile_launch(int S, int wclass, int act, int mode, const TileArgs& a, int grid, size_t smem,
+cudaError_t vn_tile_launch(int S, int cls, int act, int mode, const TileArgs& a, int grid, size_t smem,
                            cudaStream_t st) {
-    if (wclass == 32) return vn_launch_w32(S, act, mode, a, grid, smem, st);
-    if (wclass == 64) return vn_launch_w64(S, act, mode, a, grid, smem, st);
+    if (cls == 32) return vn_launch_c32(S, act, mode, a, grid, smem, st);
+    if (cls == 64) return vn_launch_c64(S, act, mode, a, grid, smem, st);
+    if (cls == 164) return vn_launch_c164(S, act, mode, a, grid, smem, st);
     return cudaErrorInvalidValue;
 }
-cudaError_t vn_tile_prepare(int S, int wclass, int act, int mode, size_t smem) {
-    if (wclass == 32) return vn_prepare_w32(S, act, mode, smem);
-    if (wclass == 64) return vn_prepare_w64(S, act, mode, smem);
+cudaError_t vn_tile_prepare(int S, int cls, int act, int mode, size_t smem) {
+    if (cls == 32) return vn_prepare_c32(S, act, mode, smem);
+    if (cls == 64) return vn_prepare_c64(S, act, mode, smem);
+    if (cls == 164) return vn_prepare_c164(S, act, mode, smem);
     return cudaErrorInvalidValue;
 }
 
@@ -111,16 +114,22 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { i = (idx - net.woff[l]) / wo; j = (idx - net.woff[l]) - i * wo; break; }
             if (idx >= net.boff[l] && idx < net.boff[l] + wo) { isBias = 1; j = idx - net.boff[l]; break; }
         }
-        int slot[8], nslot = 1;
+        int slot[16], nslot = 1;
         if (l == net.L) {
             if (isBias) slot[0] = pl.off_bout;
             else { nslot = pl.NT / pl.WP; for (int p = 0; p < nslot; ++p) slot[p] = pl.off_wout + i + pl.WP * p; }
         } else if (isBias) {
-            slot[0] = pl.off_gb[l] + (j % pl.NJG) * pl.TJ + j / pl.NJG;
+            nslot = pl.KS;
+            for (int h = 0; h < pl.KS; ++h) slot[h] = pl.off_gb[l] + h * pl.WP + (j & 15) * pl.TJ + (j >> 4);
         } else {
-            const int ig = i & 7, t = i >> 3, jg = j % pl.NJG, u = j / pl.NJG;
-            const int tid = (jg >> 2) * 32 + ig + 8 * (jg & 3);
-            slot[0] = pl.off_gw[l] + (l == 0 ? tid * pl.TJ + u : tid * (pl.TI * pl.TJ) + t * pl.TJ + u);
+            // owner thread of gW[i][j]: i = ig + 8t, j = jg + 16u (vn_tile.cuh gw_gemm); one slot per point slice
+            const int ig = i & 7, t = i >> 3, jg = j & 15, u = j >> 4;
+            const int own = (jg >> 2) * 32 + ig + 8 * (jg & 3);
+            nslot = pl.KS;
+            for (int h = 0; h < pl.KS; ++h) {
+                const int tid = h * 128 + own;
+                slot[h] = pl.off_gw[l] + (l == 0 ? tid * pl.TJ + u : tid * (pl.TI * pl.TJ) + t * pl.TJ + u);
+            }
         }
         double s = 0.0;
         for (int p = 0; p < nslot; ++p) {
@@ -232,6 +241,7 @@ struct vn_engine {
     vn_config cfg;
     NetDesc net;
     int S = 0, wclass = 0, numSMs = 0;
+    bool fused = false;          // per-test-function residual reduced inside the adjoint kernel (integNum | TP)
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     // parameters + optimizer
@@ -244,7 +254,7 @@ struct vn_engine {
     DevBuf bcols, blabel, cj;
     long long bstride = 0; unsigned int nbi = 0, bDof = 0; float biDimVal = 0.f;
     // adjoint partial slabs
-    DevBuf partVar, partBic; int gridVar = 0, gridBic = 0;
+    DevBuf partVar, partBic, stashVar, stashBic, lossPart; int gridVar = 0, gridBic = 0;
     // scratch
     DevBuf stage, evalCols, evalOut;
     // geometry
@@ -313,12 +323,17 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     e->cfg = *cfg;
     build_net(*cfg, &e->net);
     e->S = 1 + cfg->dim;
-    e->wclass = wmax <= 32 ? 32 : (wmax <= 64 ? 64 : 0);
-    if (!e->wclass) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
+    if (wmax > 64) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     e->numSMs = prop.multiProcessorCount;
     const int L = cfg->nLayers, act = cfg->act;
+    e->wclass = wmax <= 32 ? 32 : 64;
+    if (e->wclass == 64) {       // deep 64-wide networks: the weights of all layers no longer fit next to 64-point tiles
+        TileGeom probe;
+        if (vn_tile_geometry(e->S, 64, act, MODE_VAR_ADJ, L, &probe) && probe.smemBytes > prop.sharedMemPerBlockOptin)
+            e->wclass = 164;
+    }
     bool ok = vn_tile_geometry(e->S, e->wclass, act, MODE_VAR_FWD, L, &e->gVarFwd) &&
               vn_tile_geometry(e->S, e->wclass, act, MODE_VAR_ADJ, L, &e->gVarAdj) &&
               vn_tile_geometry(1, e->wclass, act, MODE_BIC_FWD, L, &e->gBicFwd) &&
@@ -326,15 +341,15 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
               vn_tile_geometry(1, e->wclass, act, MODE_EVAL, L, &e->gEval);
     if (!ok) { delete e; return fail(VN_E_UNSUPPORTED, "no compiled kernel for this configuration"); }
     const size_t smemMax = prop.sharedMemPerBlockOptin;
-    const TileGeom* gs[5] = {&e->gVarFwd, &e->gVarAdj, &e->gBicFwd, &e->gBicAdj, &e->gEval};
-    const int modes[5] = {MODE_VAR_FWD, MODE_VAR_ADJ, MODE_BIC_FWD, MODE_BIC_ADJ, MODE_EVAL};
-    for (int k = 0; k < 5; ++k) {
+    const TileGeom* gs[6] = {&e->gVarFwd, &e->gVarAdj, &e->gBicFwd, &e->gBicAdj, &e->gEval, &e->gVarAdj};
+    const int modes[6] = {MODE_VAR_FWD, MODE_VAR_ADJ, MODE_BIC_FWD, MODE_BIC_ADJ, MODE_EVAL, MODE_VAR_FUSED};
+    for (int k = 0; k < 6; ++k) {
         if (gs[k]->smemBytes > smemMax) {
             const size_t need = gs[k]->smemBytes;
             delete e;
             return fail(VN_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA (limit %zu): depth/width outside the resident-tile kernel family", need, smemMax);
         }
-        const int S = (k < 2) ? e->S : 1;
+        const int S = (k < 2 || k == 5) ? e->S : 1;
         cudaError_t ce = vn_tile_prepare(S, e->wclass, act, modes[k], gs[k]->smemBytes);
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
     }
@@ -361,7 +376,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->cols, &e->integW,
                       &e->detJ, &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
-                      &e->partBic, &e->stage, &e->evalCols, &e->evalOut};
+                      &e->partBic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -514,6 +529,9 @@ static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, con
     const long long tilesAdj = e->pstride / e->gVarAdj.TP;
     e->gridVar = (int)std::min<long long>(tilesAdj, e->numSMs);
     CK(e->partVar.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(double)));
+    CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->gridVar * e->gVarAdj.stashFloats * sizeof(float))));
+    CK(e->lossPart.ensure((size_t)e->gridVar * (e->gVarAdj.NT / 32) * sizeof(double)));
+    e->fused = (e->gVarAdj.TP % integNum) == 0;
     return VN_OK;
 }
 
@@ -544,6 +562,7 @@ static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64
     const long long tiles = e->bstride / e->gBicAdj.TP;
     e->gridBic = (int)std::min<long long>(tiles, e->numSMs);
     CK(e->partBic.ensure((size_t)e->gridBic * e->gBicAdj.pl.psz * sizeof(double)));
+    CK(e->stashBic.ensure(std::max<size_t>(16, (size_t)e->gridBic * e->gBicAdj.stashFloats * sizeof(float))));
     return VN_OK;
 }
 
@@ -581,7 +600,7 @@ static void var_args(const vn_engine* e, TileArgs* a) {
     a->integNum = e->integNum;
     a->integW = e->hasIntegW ? e->integW.as<float>() : nullptr;
     a->detJ = e->detJ.as<float>(); a->detJvec = e->detJvec;
-    a->R = e->R.as<float>(); a->Iw = e->Iw.as<float>();
+    a->R = e->R.as<float>(); a->Iw = e->Iw.as<float>(); a->lossVec = e->lossVec.as<float>();
 }
 static void bic_args(const vn_engine* e, TileArgs* a) {
     base_args(e, a);
@@ -599,35 +618,51 @@ static int run_loss(vn_engine* e, bool needGrad) {
     CK(cudaSetDevice(c.device));
     cudaStream_t st = e->stream;
     TileArgs a;
-    // 1. forward over all quadrature points -> weighted integrand
     var_args(e, &a);
-    {
-        const TileGeom& g = e->gVarFwd;
-        a.ntiles = (int)(e->pstride / g.TP);
-        const int grid = std::min(a.ntiles, 2 * e->numSMs);
-        ProfScope ps(e, PK_VAR_FWD);
-        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
-    }
-    // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
-    const int nSeg = (int)((e->nb + 255) / 256);
-    {
-        SegArgs s;
-        s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->integNum; s.detJ = e->detJ.as<float>();
-        s.detJvec = e->detJvec; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
-        s.blockSum = e->segSum.as<double>();
-        ProfScope ps(e, PK_SEG);
-        vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
-        CK(cudaGetLastError());
-    }
-    e->launches += 2;
-    if (needGrad) {
-        // 3. adjoint over quadrature points (forward recomputed per tile, seeds from R_i)
+    int nSeg = (int)((e->nb + 255) / 256);
+    const double* segPtr = e->segSum.as<double>();
+    if (needGrad && e->fused) {
+        // single pass: forward, in-tile residual reduction, adjoint (MODE_VAR_FUSED)
         const TileGeom& g = e->gVarAdj;
         a.ntiles = (int)(e->pstride / g.TP);
         a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+        a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
+        a.lossPart = e->lossPart.as<double>();
         ProfScope ps(e, PK_VAR_ADJ);
-        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_ADJ, a, e->gridVar, g.smemBytes, st));
+        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
         e->launches++;
+        nSeg = e->gridVar * (g.NT / 32);
+        segPtr = e->lossPart.as<double>();
+    } else {
+        // 1. forward over all quadrature points -> weighted integrand
+        {
+            const TileGeom& g = e->gVarFwd;
+            a.ntiles = (int)(e->pstride / g.TP);
+            const int grid = std::min(a.ntiles, 2 * e->numSMs);
+            ProfScope ps(e, PK_VAR_FWD);
+            CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
+        }
+        // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
+        {
+            SegArgs s;
+            s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->integNum; s.detJ = e->detJ.as<float>();
+            s.detJvec = e->detJvec; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
+            s.blockSum = e->segSum.as<double>();
+            ProfScope ps(e, PK_SEG);
+            vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
+            CK(cudaGetLastError());
+        }
+        e->launches += 2;
+        if (needGrad) {
+            // 3. adjoint over quadrature points (forward recomputed per tile, seeds from R_i)
+            const TileGeom& g = e->gVarAdj;
+            a.ntiles = (int)(e->pstride / g.TP);
+            a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+            a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
+            ProfScope ps(e, PK_VAR_ADJ);
+            CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_ADJ, a, e->gridVar, g.smemBytes, st));
+            e->launches++;
+        }
     }
     // 4. boundary / initial rows
     bic_args(e, &a);
@@ -636,6 +671,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         const TileGeom& g = needGrad ? e->gBicAdj : e->gBicFwd;
         a.ntiles = (int)(e->bstride / g.TP);
         a.part = e->partBic.as<double>(); a.psz = g.pl.psz;
+        a.stash = e->stashBic.as<float>(); a.stashFloats = g.stashFloats;
         const int grid = needGrad ? e->gridBic : std::min(a.ntiles, 2 * e->numSMs);
         ProfScope ps(e, PK_BIC);
         CK(vn_tile_launch(1, e->wclass, c.act, mode, a, grid, g.smemBytes, st));
@@ -648,7 +684,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         f.net = e->net; f.pl = e->gVarAdj.pl;
         f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
-        f.segSum = e->segSum.as<double>(); f.nSeg = nSeg;
+        f.segSum = segPtr; f.nSeg = nSeg;
         f.detJ = e->detJ.as<float>(); f.detJvec = e->detJvec;
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
@@ -790,10 +826,11 @@ extern "C" int vn_profile_read(vn_engine* e, double ms[VN_PROF_SLOTS], int64_t c
 extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
     if (!e || !buf) return fail(VN_E_INVALID, "null argument");
     snprintf(buf, n,
-             "family=fp32-fma-resident-tile wclass=%d S=%d L=%d var_fwd(TP=%d,NT=%d,smem=%zu) var_adj(TP=%d,NT=%d,smem=%zu,grid=%d) "
-             "bic_adj(TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+             "family=fp32-fma-tile class=%d S=%d L=%d var_fwd(TP=%d,NT=%d,smem=%zu) var_adj(TP=%d,NT=%d,smem=%zu,grid=%d,%s,"
+             "stash=%lldB/CTA) bic_adj(TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
              e->wclass, e->S, e->net.L, e->gVarFwd.TP, e->gVarFwd.NT, e->gVarFwd.smemBytes, e->gVarAdj.TP, e->gVarAdj.NT,
-             e->gVarAdj.smemBytes, e->gridVar, e->gBicAdj.TP, e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
+             e->gVarAdj.smemBytes, e->gridVar, e->fused ? "fused-R single pass" : "two-pass",
+             (long long)(e->gVarAdj.stashFloats * 4), e->gBicAdj.TP, e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
     return VN_OK;
 }
 extern "C" int64_t vn_launch_count(const vn_engine* e) { return e ? e->launches : 0; }

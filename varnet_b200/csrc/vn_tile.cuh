@@ -1,17 +1,23 @@
 // vn_tile.cuh — fused FP32 tile kernels for the weak-form residual and its adjoint.
 //
-// One CTA owns a tile of TP quadrature points and walks the whole MLP for them with
-// every layer's activations resident in shared memory:
+// One CTA owns a tile of TP quadrature points and walks the whole MLP for them:
 //   stream 0      : a_l        = act(a_{l-1} W_l + b_l)                (model(Input),   TFModel.py:625)
 //   stream 1..DIM : da_l/dx_k  = act'(z_l) * (da_{l-1}/dx_k W_l)       (tf.gradients(model(Input), Input)[:, :dim], TFModel.py:536-541,
 //                                                                        evaluated forward-mode: same numbers, no second sweep)
 // Each layer is a [S*TP x Kin] x [Kin x W] register-tiled FP32-FMA GEMM whose A operand
-// (activations, point-contiguous) and B operand (weights) are read from shared memory
-// with 128-bit loads; the epilogue applies the activation and writes the next layer's
-// operand.  The adjoint walks the layers backwards with two more
-// GEMMs per layer: abar_{l-1} = zbar_l W_l^T and gW_l += [a_{l-1}; da_{l-1}]^T [zbar_l; dzbar_l].
-// Weight-gradient tiles are accumulated per CTA in FP64 partial buffers (thread-private
-// slots, no atomics => deterministic) and summed across CTAs by vn_finalize_kernel.
+// (activations, point-contiguous) and B operand (weights) are read from shared memory with
+// 128-bit loads; the epilogue applies the activation and writes the next layer's operand.
+//
+// vn_fwd_kernel : forward only (loss / evaluation), two ping-pong operand buffers.
+// vn_adj_kernel : forward + adjoint in one pass over the tile.  Shared memory holds
+//   three operand buffers; the activations of layers 0..L-3 are stashed in a per-CTA global slab that
+//   stays L2-resident (148 CTAs x <=2 x 52 KB) and are brought back with cp.async while the
+//   abar = zbar W^T GEMM of the layer above runs.  Per layer the adjoint does two GEMMs:
+//   abar_{l-1} = zbar_l W_l^T and gW_l += [a_{l-1}; da_{l-1}]^T [zbar_l; dzbar_l].
+//   When integNum divides TP the per-test-function residual R_i = sum_q w_q I_iq (TFModel.py:659-661)
+//   is reduced inside the tile (MODE_VAR_FUSED) so the step needs no separate forward pass.
+// Weight-gradient tiles are accumulated per CTA in FP64 partial slabs (thread-private slots, no
+// atomics => bitwise deterministic) and summed across CTAs by vn_finalize_kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,8 +31,9 @@ enum {
     MODE_VAR_FWD = 0,   // I_p per point                       (TFModel.py:653-660)
     MODE_EVAL = 1,      // u = model(X)                        (VarNetUtility.py:1127)
     MODE_BIC_FWD = 2,   // biDimVal*(model(biInput)-biLabel)^2 (TFModel.py:643)
-    MODE_VAR_ADJ = 3,   // d(w2*varLoss)/d theta               (TFModel.py:709)
-    MODE_BIC_ADJ = 4    // d(w0*bCs+w1*iCs)/d theta
+    MODE_VAR_ADJ = 3,   // d(w2*varLoss)/d theta, R_i read from global (any integNum)
+    MODE_BIC_ADJ = 4,   // d(w0*bCs+w1*iCs)/d theta
+    MODE_VAR_FUSED = 5  // loss + d(w2*varLoss)/d theta, R_i reduced in the tile (integNum | TP)
 };
 
 struct NetDesc {
@@ -53,7 +60,8 @@ struct TileArgs {
     const float* integW;            // [integNum] or nullptr
     const float* detJ;              // [1] or [nb]
     int detJvec;
-    const float* R;                 // [nb] per-test-function residuals (ADJ)
+    float* R;                       // [nb] per-test-function residuals (read: VAR_ADJ, written: VAR_FUSED)
+    float* lossVec;                 // [nb] detJ_i R_i^2 (written by VAR_FUSED)
     const float* wts;               // [3] loss weights (device)
     float* Iw;                      // [P] weighted integrand out (VAR_FWD)
     // boundary / initial rows
@@ -63,9 +71,12 @@ struct TileArgs {
     float* cj;                      // [nbi] biDimVal*(u-label)^2 out
     // evaluation
     float* uout;                    // [P]
-    // adjoint partial sums
-    double* part;                   // [gridDim.x][psz]
+    // adjoint
+    double* part;                   // [gridDim.x][psz] FP64 partial gradients
     int psz;
+    float* stash;                   // [gridDim.x][stashFloats] activations of layers 0..L-3
+    long long stashFloats;
+    double* lossPart;               // [gridDim.x][NT/32] partial sums of (detJ_i) R_i^2 (VAR_FUSED)
 };
 
 template <int S_, int WP_, int TP_, int TN_, int ACT_>
@@ -80,21 +91,23 @@ struct TileCfg {
     static constexpr int NPG = TP / 4;      // point groups (4 points per thread)
     static constexpr int NNG = WP / TN;     // neuron groups
     static constexpr int NT = NPG * NNG;    // threads per CTA
+    static constexpr int NW = NT / 32;
     static constexpr int NPGW = NPG / 8;    // warps along the point axis
     static constexpr int KIN = VN_KIN;
-    static constexpr int NJG = NT / 8;      // weight-gradient GEMM: column groups
-    static constexpr int TJ = WP / NJG;     //   columns per thread
-    static constexpr int TI = WP / 8;       //   rows per thread
+    // weight-gradient GEMM: 128 tile owners (8 row groups x 16 column groups) x KS point slices
+    static constexpr int KS = NT / 128;
+    static constexpr int TI = WP / 8;       //   rows per thread    (i = ig + 8 t)
+    static constexpr int TJ = WP / 16;      //   columns per thread (j = jg + 16 u)
     static constexpr int BUF = S * WP * TPS;
     static constexpr int BUF0 = S * KIN * TPS;
     static_assert(NPG % 8 == 0 && NNG % 4 == 0, "warp mapping needs 8 point groups x 4 neuron groups per warp");
-    static_assert(WP % NJG == 0 && TJ >= 1, "bad weight-gradient tiling");
-    static_assert(NT % WP == 0, "output-layer gradient mapping");
+    static_assert(NT % 128 == 0 && TP % (4 * KS) == 0, "weight-gradient tiling");
+    static_assert(NT % WP == 0 && (TP / (NT / WP)) % 4 == 0, "output-layer gradient mapping");
 };
 
-// layout of one CTA's FP64 partial-gradient slab (shared by kernels and finalize)
+// layout of one CTA's FP64 partial-gradient slab (shared by the adjoint kernel and finalize)
 struct PartLayout {
-    int NT, NJG, TI, TJ, WP;
+    int NT, KS, TI, TJ, WP;
     int off_gw[VN_MAX_LAYERS];
     int off_gb[VN_MAX_LAYERS];
     int off_wout, off_bout, psz;
@@ -103,11 +116,12 @@ struct PartLayout {
 template <class C>
 __host__ __device__ inline PartLayout make_part_layout(int L) {
     PartLayout p;
-    p.NT = C::NT; p.NJG = C::NJG; p.TI = C::TI; p.TJ = C::TJ; p.WP = C::WP;
+    p.NT = C::NT; p.KS = C::KS; p.TI = C::TI; p.TJ = C::TJ; p.WP = C::WP;
     int o = 0;
+    for (int l = 0; l < VN_MAX_LAYERS; ++l) { p.off_gw[l] = 0; p.off_gb[l] = 0; }
     for (int l = 0; l < L; ++l) {
         p.off_gw[l] = o; o += C::NT * (l == 0 ? C::TJ : C::TI * C::TJ);
-        p.off_gb[l] = o; o += C::WP;
+        p.off_gb[l] = o; o += C::KS * C::WP;
     }
     p.off_wout = o; o += C::NT;
     p.off_bout = o; o += 1;
@@ -123,12 +137,13 @@ __host__ __device__ inline size_t tile_smem_floats(int L, bool adj) {
     n += (size_t)L * C::WP;                 // biases
     n += C::WP + 4;                         // wout | bout
     n += C::BUF0;                           // layer "-1": inputs + unit tangent rows
-    n += (size_t)(adj ? L : 2) * C::BUF;    // activations (all layers kept for the adjoint)
-    n += adj ? 2 * (size_t)C::BUF : 0;      // zbar ping-pong
-    n += 4 * C::TP;                         // per-point coefficients
+    n += (size_t)(adj ? 3 : 2) * C::BUF;    // operand buffers
+    n += 4 * C::TP;                         // integrand / per-tile scratch
     n += (size_t)C::S * C::TP;              // u / seeds
     return n;
 }
+template <class C>
+__host__ __device__ inline long long tile_stash_floats(int L) { return L > 2 ? (long long)(L - 2) * C::BUF : 0; }
 
 // ------------------------------------------------------------------ activations
 template <int ACT> __device__ __forceinline__ float act_f(float z) {
@@ -145,6 +160,12 @@ template <int ACT> __device__ __forceinline__ float act_d2r(float a) {     // ac
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // out[s][j][p] = sum_i in[s][i][p] * W[i][j]; thread tile: 4 points x S streams x TN neurons
 template <class C, int KD>
@@ -215,13 +236,13 @@ __device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const flo
     }
 }
 
-// gW[i][j] += sum_{s,p} Bprev[s][i][p] * D[s][j][p];  i = ig + 8t, j = jg + NJG*t'
-// (ig == 0 threads also produce gb[j] = sum_p D[0][j][p]).  Accumulates into the CTA's
-// FP64 partial slab; `first` overwrites instead of accumulating.
+// gW[i][j] += sum_{s,p} Bprev[s][i][p] * D[s][j][p];  i = ig + 8t, j = jg + 16u; the CTA's KS point
+// slices accumulate into separate partial slots (no cross-thread reduction).  ig == 0 threads also
+// produce gb[j] = sum_p D[0][j][p].  `first` overwrites instead of accumulating.
 template <class C, int KD, int TIK>
 __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const float* __restrict__ Dm,
-                                        int ig, int jg, double* __restrict__ pgw, double* __restrict__ pgb,
-                                        bool first) {
+                                        int ig, int jg, int kslice, double* __restrict__ pgw,
+                                        double* __restrict__ pgb, bool first) {
     float acc[TIK][C::TJ];
     float bacc[C::TJ];
 #pragma unroll
@@ -230,15 +251,17 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
         for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
 #pragma unroll
     for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
+    constexpr int PSL = C::TP / C::KS;
+    const int pbeg = kslice * PSL;
 #pragma unroll
     for (int s = 0; s < C::S; ++s) {
 #pragma unroll 2
-        for (int p = 0; p < C::TP; p += 4) {
+        for (int p = pbeg; p < pbeg + PSL; p += 4) {
             float4 a[TIK], d[C::TJ];
 #pragma unroll
             for (int t = 0; t < TIK; ++t) a[t] = lds4(Bprev + (s * KD + ig + 8 * t) * C::TPS + p);
 #pragma unroll
-            for (int u = 0; u < C::TJ; ++u) d[u] = lds4(Dm + (s * C::WP + jg + C::NJG * u) * C::TPS + p);
+            for (int u = 0; u < C::TJ; ++u) d[u] = lds4(Dm + (s * C::WP + jg + 16 * u) * C::TPS + p);
 #pragma unroll
             for (int t = 0; t < TIK; ++t)
 #pragma unroll
@@ -275,78 +298,204 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     }
 }
 
+// ---- pieces shared by the two kernels -------------------------------------------------------------
+template <class C>
+struct SmemMap {
+    float *W0, *Wl, *bias, *wout, *Bm1, *A, *coef, *us;
+    __device__ SmemMap(float* smem, int L, int nbuf) {
+        W0 = smem;
+        Wl = W0 + C::KIN * C::WS;
+        bias = Wl + (L - 1) * C::WP * C::WS;
+        wout = bias + L * C::WP;
+        Bm1 = wout + C::WP + 4;
+        A = Bm1 + C::BUF0;
+        coef = A + nbuf * C::BUF;
+        us = coef + 4 * C::TP;
+    }
+};
+
+// zero shared memory, stage the weights (zero padded), write the unit tangent rows of layer "-1"
+template <class C>
+__device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C>& m, float* smem, int total) {
+    const NetDesc& net = A.net;
+    const int tid = threadIdx.x, L = net.L;
+    constexpr int NT = C::NT, WS = C::WS, WP = C::WP;
+    for (int i = tid; i < total; i += NT) smem[i] = 0.f;
+    __syncthreads();
+    const float* __restrict__ th = A.theta;
+    for (int idx = tid; idx < net.inpDim * net.width[0]; idx += NT) {
+        int i = idx / net.width[0], j = idx - i * net.width[0];
+        m.W0[i * WS + j] = th[net.woff[0] + idx];
+    }
+    for (int l = 1; l < L; ++l) {
+        const int wi = net.width[l - 1], wo = net.width[l];
+        float* Wm = m.Wl + (l - 1) * WP * WS;
+        for (int idx = tid; idx < wi * wo; idx += NT) {
+            int i = idx / wo, j = idx - i * wo;
+            Wm[i * WS + j] = th[net.woff[l] + idx];
+        }
+    }
+    for (int l = 0; l < L; ++l)
+        for (int j = tid; j < net.width[l]; j += NT) m.bias[l * WP + j] = th[net.boff[l] + j];
+    for (int j = tid; j < net.width[L - 1]; j += NT) m.wout[j] = th[net.woff[L] + j];
+    if (tid == 0) m.wout[WP] = th[net.boff[L]];
+    // d x_c / d x_k = delta_ck  (stream 1+k seeds input column k)
+    for (int idx = tid; idx < (C::S - 1) * C::TP; idx += NT) {
+        int k = idx / C::TP, p = idx - k * C::TP;
+        m.Bm1[((1 + k) * C::KIN + k) * C::TPS + p] = 1.f;
+    }
+    __syncthreads();
+}
+
+// one forward layer: GEMM + bias + activation -> Bout (and optionally the global stash)
+template <class C>
+__device__ __forceinline__ void forward_layer(const NetDesc& net, const SmemMap<C>& m, int l, const float* Bin,
+                                              float* Bout, float* stash, int p0, int ng) {
+    constexpr int S = C::S, WP = C::WP, TN = C::TN, TPS = C::TPS;
+    const int j0 = TN * ng;
+    if (j0 >= net.wpad[l]) return;
+    float acc[S][4][TN];
+    if (l == 0) fwd_gemm<C, C::KIN>(m.Bm1, m.W0, (net.inpDim + 3) & ~3, p0, j0, acc);
+    else fwd_gemm<C, WP>(Bin, m.Wl + (l - 1) * WP * C::WS, net.wpad[l - 1], p0, j0, acc);
+#pragma unroll
+    for (int t = 0; t < TN; ++t) {
+        const float b = m.bias[l * WP + j0 + t];
+        float a[4], d1[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            a[p] = act_f<C::ACT>(acc[0][p][t] + b);
+            d1[p] = act_d1<C::ACT>(a[p]);
+        }
+        const int off0 = (j0 + t) * TPS + p0;
+        const float4 v0 = make_float4(a[0], a[1], a[2], a[3]);
+        sts4(Bout + off0, v0);
+        if (stash) __stcg(reinterpret_cast<float4*>(stash + off0), v0);
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            const int off = (s * WP + j0 + t) * TPS + p0;
+            const float4 v = make_float4(d1[0] * acc[s][0][t], d1[1] * acc[s][1][t], d1[2] * acc[s][2][t],
+                                         d1[3] * acc[s][3][t]);
+            sts4(Bout + off, v);
+            if (stash) __stcg(reinterpret_cast<float4*>(stash + off), v);
+        }
+    }
+}
+
+// stage the tile's input columns into layer "-1" (coalesced 128-bit loads from the SoA table)
+template <class C>
+__device__ __forceinline__ void load_inputs(const TileArgs& A, const SmemMap<C>& m, unsigned int base) {
+    for (int idx = threadIdx.x; idx < A.net.inpDim * C::NPG; idx += C::NT) {
+        int c = idx / C::NPG, q = idx - c * C::NPG;
+        float4 v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + base) + q);
+        sts4(m.Bm1 + c * C::TPS + 4 * q, v);
+    }
+}
+
+// output layer (Dense(1), linear): us[s][p] = u (s=0) and du/dx_k (s=1+k)
+template <class C>
+__device__ __forceinline__ void output_layer(const SmemMap<C>& m, const float* Blast, int wlast) {
+    for (int idx = threadIdx.x; idx < C::S * C::TP; idx += C::NT) {
+        const int s = idx / C::TP, p = idx - s * C::TP;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = 0; i < wlast; i += 2) {
+            acc0 = fmaf(Blast[(s * C::WP + i) * C::TPS + p], m.wout[i], acc0);
+            acc1 = fmaf(Blast[(s * C::WP + i + 1) * C::TPS + p], m.wout[i + 1], acc1);
+        }
+        float acc = acc0 + acc1;
+        if (s == 0) acc += m.wout[C::WP];
+        m.us[idx] = acc;
+    }
+}
+
+// integrand I = sum_k u_k gcoef_k - u dNt - source N  (TFModel.py:653-657), times integW_q (:660)
+template <class C>
+__device__ __forceinline__ float integrand(const TileArgs& A, const SmemMap<C>& m, int p, unsigned int gp) {
+    float I = 0.f;
+#pragma unroll
+    for (int k = 0; k < C::S - 1; ++k)
+        I = fmaf(m.us[(1 + k) * C::TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp), I);
+    if (A.timeDependent) I -= m.us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + gp);
+    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
+    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+    return I;
+}
+
+// ------------------------------------------------------------------ forward-only kernel
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT, 1) vn_tile_kernel(const __grid_constant__ TileArgs A) {
-    constexpr bool ADJ = (MODE == MODE_VAR_ADJ || MODE == MODE_BIC_ADJ);
-    constexpr bool BIC = (MODE == MODE_BIC_FWD || MODE == MODE_BIC_ADJ);
-    constexpr bool NEED_OUT = (MODE != MODE_VAR_ADJ);      // output layer forward needed?
+__global__ void __launch_bounds__(C::NT, 1) vn_fwd_kernel(const __grid_constant__ TileArgs A) {
+    constexpr int TP = C::TP, NT = C::NT, BUF = C::BUF;
+    extern __shared__ __align__(16) float smem[];
+    const NetDesc& net = A.net;
+    const int L = net.L;
+    const SmemMap<C> m(smem, L, 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = (lane & 7) + 8 * (warp % C::NPGW);
+    const int ng = (lane >> 3) + 4 * (warp / C::NPGW);
+    const int p0 = 4 * pg;
+    stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, false));
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const unsigned int base = (unsigned int)tile * TP;
+        load_inputs<C>(A, m, base);
+        __syncthreads();
+        for (int l = 0; l < L; ++l) {
+            forward_layer<C>(net, m, l, m.A + ((l - 1) & 1) * BUF, m.A + (l & 1) * BUF, nullptr, p0, ng);
+            __syncthreads();
+        }
+        output_layer<C>(m, m.A + ((L - 1) & 1) * BUF, net.wpad[L - 1]);
+        __syncthreads();
+        for (int p = tid; p < TP; p += NT) {
+            const unsigned int gp = base + p;
+            if (gp >= A.P) continue;
+            if (MODE == MODE_VAR_FWD) {
+                A.Iw[gp] = integrand<C>(A, m, p, gp);
+            } else if (MODE == MODE_EVAL) {
+                A.uout[gp] = m.us[p];
+            } else {
+                const float r = m.us[p] - __ldg(A.label + gp);
+                A.cj[gp] = A.biDimVal * r * r;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ forward + adjoint kernel
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant__ TileArgs A) {
+    constexpr bool BIC = (MODE == MODE_BIC_ADJ);
+    constexpr bool FUSED = (MODE == MODE_VAR_FUSED);
     constexpr int S = C::S, WP = C::WP, TP = C::TP, TN = C::TN, TPS = C::TPS, WS = C::WS, NT = C::NT;
     constexpr int KIN = C::KIN, BUF = C::BUF;
     extern __shared__ __align__(16) float smem[];
     const NetDesc& net = A.net;
     const int L = net.L;
-
-    float* W0 = smem;
-    float* Wl = W0 + KIN * WS;
-    float* bias = Wl + (L - 1) * WP * WS;
-    float* wout = bias + L * WP;
-    float* Bm1 = wout + WP + 4;
-    float* B = Bm1 + C::BUF0;
-    float* D = B + (ADJ ? L : 2) * BUF;
-    float* coef = D + (ADJ ? 2 * BUF : 0);
-    float* us = coef + 4 * TP;                              // u_s[p] (forward) / seeds (adjoint)
+    const SmemMap<C> m(smem, L, 3);
+    float* us = m.us;                                        // u_s[p] (forward) then the adjoint seeds
+    float* Ish = m.coef;                                     // integrand per point (FUSED)
+    float* Rsh = m.coef + TP;                                // R per test function of the tile (FUSED)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pg = (lane & 7) + 8 * (warp % C::NPGW);
     const int ng = (lane >> 3) + 4 * (warp / C::NPGW);
     const int p0 = 4 * pg;
-    const int ig = lane & 7, jg = (lane >> 3) + 4 * warp;   // weight-gradient GEMM mapping
+    // weight-gradient GEMM mapping: 128 owners x KS point slices
+    const int own = tid & 127, kslice = tid >> 7;
+    const int ig = own & 7, jg = ((own & 31) >> 3) + 4 * (own >> 5);
 
-    // ---- one-time: zero shared memory, stage the weights
-    {
-        const int total = (int)tile_smem_floats<C>(L, ADJ);
-        for (int i = tid; i < total; i += NT) smem[i] = 0.f;
-        __syncthreads();
-        const float* __restrict__ th = A.theta;
-        for (int idx = tid; idx < net.inpDim * net.width[0]; idx += NT) {
-            int i = idx / net.width[0], j = idx - i * net.width[0];
-            W0[i * WS + j] = th[net.woff[0] + idx];
-        }
-        for (int l = 1; l < L; ++l) {
-            const int wi = net.width[l - 1], wo = net.width[l];
-            float* Wm = Wl + (l - 1) * WP * WS;
-            for (int idx = tid; idx < wi * wo; idx += NT) {
-                int i = idx / wo, j = idx - i * wo;
-                Wm[i * WS + j] = th[net.woff[l] + idx];
-            }
-        }
-        for (int l = 0; l < L; ++l)
-            for (int j = tid; j < net.width[l]; j += NT) bias[l * WP + j] = th[net.boff[l] + j];
-        for (int j = tid; j < net.width[L - 1]; j += NT) wout[j] = th[net.woff[L] + j];
-        if (tid == 0) wout[WP] = th[net.boff[L]];
-        // unit tangent rows: d x_c / d x_k = delta_ck  (stream 1+k seeds input column k)
-        for (int idx = tid; idx < (S - 1) * TP; idx += NT) {
-            int k = idx / TP, p = idx - k * TP;
-            Bm1[((1 + k) * KIN + k) * TPS + p] = 1.f;
-        }
-        __syncthreads();
-    }
+    stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, true));
 
     const PartLayout pl = make_part_layout<C>(L);
-    double* part = ADJ ? A.part + (size_t)blockIdx.x * pl.psz : nullptr;
-    const int kin0 = (net.inpDim + 3) & ~3;
+    double* part = A.part + (size_t)blockIdx.x * pl.psz;
+    float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
+    double lossAcc = 0.0;                                    // lane 0 of each warp (FUSED)
     bool first = true;
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const unsigned int base = (unsigned int)tile * TP;
-        // ---- phase 1: stage the tile's inputs (coalesced 128-bit loads from the SoA table)
-        for (int idx = tid; idx < net.inpDim * C::NPG; idx += NT) {
-            int c = idx / C::NPG, q = idx - c * C::NPG;
-            float4 v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + base) + q);
-            sts4(Bm1 + c * TPS + 4 * q, v);
-        }
+        load_inputs<C>(A, m, base);
         if (MODE == MODE_VAR_ADJ) {
-            // adjoint seeds: lambda = 2 w2 detJ_i w_q R_i ; ubar = -lambda dNt ; ubar_k = lambda gcoef_k
+            // seeds from the globally reduced R_i: lambda = 2 w2 detJ_i w_q R_i ; ubar = -lambda dNt ; ubar_k = lambda gcoef_k
             for (int p = tid; p < TP; p += NT) {
                 const unsigned int gp = base + p;
                 float lam = 0.f;
@@ -364,195 +513,197 @@ __global__ void __launch_bounds__(C::NT, 1) vn_tile_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // ---- forward sweep
+        // ---- forward sweep: B_l -> operand buffer (l & 1); layers 0..L-3 also go to the L2 stash
         for (int l = 0; l < L; ++l) {
-            const int j0 = TN * ng;
-            float* Bout = B + (ADJ ? l : (l & 1)) * BUF;
-            if (j0 < net.wpad[l]) {
-                float acc[S][4][TN];
-                if (l == 0) {
-                    fwd_gemm<C, KIN>(Bm1, W0, kin0, p0, j0, acc);
-                } else {
-                    const float* Bin = B + (ADJ ? (l - 1) : ((l - 1) & 1)) * BUF;
-                    fwd_gemm<C, WP>(Bin, Wl + (l - 1) * WP * WS, net.wpad[l - 1], p0, j0, acc);
-                }
-#pragma unroll
-                for (int t = 0; t < TN; ++t) {
-                    const float b = bias[l * WP + j0 + t];
-                    float a[4], d1[4];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        a[p] = act_f<C::ACT>(acc[0][p][t] + b);
-                        d1[p] = act_d1<C::ACT>(a[p]);
-                    }
-                    sts4(Bout + (j0 + t) * TPS + p0, make_float4(a[0], a[1], a[2], a[3]));
-#pragma unroll
-                    for (int s = 1; s < S; ++s)
-                        sts4(Bout + (s * WP + j0 + t) * TPS + p0,
-                             make_float4(d1[0] * acc[s][0][t], d1[1] * acc[s][1][t],
-                                         d1[2] * acc[s][2][t], d1[3] * acc[s][3][t]));
-                }
-            }
+            forward_layer<C>(net, m, l, m.A + ((l - 1) & 1) * BUF, m.A + (l & 1) * BUF,
+                             (l < L - 2) ? stash + (size_t)l * BUF : nullptr, p0, ng);
             __syncthreads();
         }
-        const float* Blast = B + (ADJ ? (L - 1) : ((L - 1) & 1)) * BUF;
+        const int cur = (L - 1) & 1;
+        const float* Blast = m.A + cur * BUF;
         const int wlast = net.wpad[L - 1];
 
-        // ---- output layer (Dense(1), linear): u and du/dx_k
-        if (NEED_OUT) {
-            for (int idx = tid; idx < S * TP; idx += NT) {
-                const int s = idx / TP, p = idx - s * TP;
-                float acc = 0.f;
-                for (int i = 0; i < wlast; ++i) acc = fmaf(Blast[(s * WP + i) * TPS + p], wout[i], acc);
-                if (s == 0) acc += wout[WP];
-                us[idx] = acc;
+        if (FUSED || BIC) {
+            output_layer<C>(m, Blast, wlast);
+            __syncthreads();
+        }
+        if (FUSED) {
+            // R_i = sum_q w_q I_iq over the test functions of this tile, lossVec_i = detJ_i R_i^2
+            for (int p = tid; p < TP; p += NT) {
+                const unsigned int gp = base + p;
+                Ish[p] = gp < A.P ? integrand<C>(A, m, p, gp) : 0.f;
+            }
+            __syncthreads();
+            const int nf = TP / (int)A.integNum;
+            for (int f = warp; f < nf; f += C::NW) {
+                float r = 0.f;
+                for (int q = lane; q < (int)A.integNum; q += 32) r += Ish[f * A.integNum + q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == 0) {
+                    const unsigned int i = base / A.integNum + f;
+                    Rsh[f] = r;
+                    if (i * A.integNum < A.P) {
+                        const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                        const float r2 = r * r;
+                        A.R[i] = r;
+                        A.lossVec[i] = dj * r2;
+                        lossAcc += A.detJvec ? (double)dj * (double)r2 : (double)r2;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int p = tid; p < TP; p += NT) {
+                const unsigned int gp = base + p;
+                float lam = 0.f;
+                if (gp < A.P) {
+                    const unsigned int i = gp / A.integNum, q = gp - i * A.integNum;
+                    const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                    const float wq = A.integW ? __ldg(A.integW + q) : 1.f;
+                    lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
+                }
+                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + gp) : 0.f;
+#pragma unroll
+                for (int k = 0; k < S - 1; ++k)
+                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp);
             }
             __syncthreads();
         }
-        if (MODE == MODE_VAR_FWD) {
-            // integrand  I = sum_k u_k gcoef_k - u dNt - source N   (TFModel.py:653-657), weighted (:660)
-            for (int p = tid; p < TP; p += NT) {
-                const unsigned int gp = base + p;
-                if (gp < A.P) {
-                    float I = 0.f;
-#pragma unroll
-                    for (int k = 0; k < S - 1; ++k)
-                        I = fmaf(us[(1 + k) * TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp), I);
-                    if (A.timeDependent) I -= us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + gp);
-                    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
-                    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
-                    A.Iw[gp] = I;
-                }
-            }
-        } else if (MODE == MODE_EVAL) {
-            for (int p = tid; p < TP; p += NT)
-                if (base + p < A.P) A.uout[base + p] = us[p];
-        } else if (BIC) {
+        if (BIC) {
             for (int p = tid; p < TP; p += NT) {
                 const unsigned int gp = base + p;
                 float seed = 0.f;
                 if (gp < A.P) {
                     const float r = us[p] - __ldg(A.label + gp);
-                    if (MODE == MODE_BIC_FWD || A.cj) A.cj[gp] = A.biDimVal * r * r;
+                    A.cj[gp] = A.biDimVal * r * r;
                     // mean over boundary rows / initial rows (TFModel.py:644-648)
                     float sc;
                     if (gp < A.bDof) sc = __ldg(A.wts + 0) / (float)A.bDof;
                     else sc = A.timeDependent ? __ldg(A.wts + 1) / (float)(A.P - A.bDof) : 0.f;
                     seed = 2.f * A.biDimVal * r * sc;
                 }
-                if (ADJ) us[p] = seed;
+                us[p] = seed;
             }
+            __syncthreads();
         }
 
-        if (ADJ) {
-            if (BIC) __syncthreads();       // seeds were just written to `us`
-            // ---- top of the adjoint: zbar_{L-1} from ubar (outer product with w_out), g(w_out), g(b_out)
-            float* Dcur = D;
+        // ---- top of the adjoint: zbar_{L-1} from ubar (outer product with w_out) -> buffer 2
+        float* X = m.A + 2 * BUF;                            // D_l
+        float* Y = m.A + (cur ^ 1) * BUF;                    // B_{l-1}: B_{L-2} is still resident from the forward sweep
+        float* Z = m.A + cur * BUF;                          // D_{l-1} (overwrites B_{L-1} once it is consumed)
 #pragma unroll
-            for (int t = 0; t < TN; ++t) {
-                const int i = ng + C::NNG * t;
-                if (i < wlast) {
-                    const float wv = wout[i];
-                    const float4 a4 = lds4(Blast + i * TPS + p0);
-                    const float4 u0 = lds4(us + p0);
-                    float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                    float ub[4] = {u0.x * wv, u0.y * wv, u0.z * wv, u0.w * wv};
-                    float zb[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, d1[4];
+        for (int t = 0; t < TN; ++t) {
+            const int i = ng + C::NNG * t;
+            if (i < wlast) {
+                const float wv = m.wout[i];
+                const float4 a4 = lds4(Blast + i * TPS + p0);
+                const float4 u0 = lds4(us + p0);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float ub[4] = {u0.x * wv, u0.y * wv, u0.z * wv, u0.w * wv};
+                float zb[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, d1[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
+                for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
 #pragma unroll
-                    for (int s = 1; s < S; ++s) {
-                        const float4 us4 = lds4(us + s * TP + p0);
-                        const float4 da4 = lds4(Blast + (s * WP + i) * TPS + p0);
-                        const float dab[4] = {us4.x * wv, us4.y * wv, us4.z * wv, us4.w * wv};
-                        const float da[4] = {da4.x, da4.y, da4.z, da4.w};
-                        float o[4];
+                for (int s = 1; s < S; ++s) {
+                    const float4 us4 = lds4(us + s * TP + p0);
+                    const float4 da4 = lds4(Blast + (s * WP + i) * TPS + p0);
+                    const float dab[4] = {us4.x * wv, us4.y * wv, us4.z * wv, us4.w * wv};
+                    const float da[4] = {da4.x, da4.y, da4.z, da4.w};
+                    float o[4];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) { cross[p] = fmaf(dab[p], da[p], cross[p]); o[p] = dab[p] * d1[p]; }
-                        sts4(Dcur + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
-                    }
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) zb[p] = fmaf(ub[p], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
-                    sts4(Dcur + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
+                    for (int p = 0; p < 4; ++p) { cross[p] = fmaf(dab[p], da[p], cross[p]); o[p] = dab[p] * d1[p]; }
+                    sts4(X + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
                 }
-            }
-            {
-                // g(w_out)[i] = sum_{s,p} B_last[s][i][p] * ubar_s[p]   (thread: neuron i, point slice)
-                constexpr int NPART = NT / WP, PSL = TP / NPART;
-                const int i = tid % WP, prt = tid / WP;
-                float acc = 0.f;
 #pragma unroll
+                for (int p = 0; p < 4; ++p) zb[p] = fmaf(ub[p], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
+                sts4(X + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
+            }
+        }
+        {
+            // g(w_out)[i] = sum_{s,p} B_last[s][i][p] * ubar_s[p]   (thread: neuron i, point slice)
+            constexpr int NPART = NT / WP, PSL = TP / NPART;
+            const int i = tid % WP, prt = tid / WP;
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                for (int p = prt * PSL; p < (prt + 1) * PSL; p += 4) {
+                    const float4 b4 = lds4(Blast + (s * WP + i) * TPS + p);
+                    const float4 u4 = lds4(us + s * TP + p);
+                    acc = fmaf(b4.x, u4.x, acc); acc = fmaf(b4.y, u4.y, acc);
+                    acc = fmaf(b4.z, u4.z, acc); acc = fmaf(b4.w, u4.w, acc);
+                }
+            double* pw = part + pl.off_wout + tid;
+            __stcg(pw, first ? (double)acc : __ldcg(pw) + (double)acc);
+            if (tid == 0) {
+                float sb = 0.f;
+                for (int p = 0; p < TP; ++p) sb += us[p];
+                double* pb = part + pl.off_bout;
+                __stcg(pb, first ? (double)sb : __ldcg(pb) + (double)sb);
+            }
+        }
+        __syncthreads();
+
+        // ---- backward sweep.  Roles: X = zbar_l, Y = activations of layer l-1, Z = zbar_{l-1}.
+        for (int l = L - 1; l >= 1; --l) {
+            if (l < L - 1) {
+                // bring B_{l-1} back from the L2 stash while the abar GEMM below runs
+                const float* src = stash + (size_t)(l - 1) * BUF;
+                const int rows = net.wpad[l - 1], chunks = rows * (TPS / 4);
                 for (int s = 0; s < S; ++s)
-                    for (int p = prt * PSL; p < (prt + 1) * PSL; p += 4) {
-                        const float4 b4 = lds4(Blast + (s * WP + i) * TPS + p);
-                        const float4 u4 = lds4(us + s * TP + p);
-                        acc = fmaf(b4.x, u4.x, acc); acc = fmaf(b4.y, u4.y, acc);
-                        acc = fmaf(b4.z, u4.z, acc); acc = fmaf(b4.w, u4.w, acc);
-                    }
-                double* pw = part + pl.off_wout + tid;
-                __stcg(pw, first ? (double)acc : __ldcg(pw) + (double)acc);
-                if (tid == 0) {
-                    float sb = 0.f;
-                    for (int p = 0; p < TP; ++p) sb += us[p];
-                    double* pb = part + pl.off_bout;
-                    __stcg(pb, first ? (double)sb : __ldcg(pb) + (double)sb);
-                }
+                    for (int c = tid; c < chunks; c += NT)
+                        cp_async16(Y + s * WP * TPS + 4 * c, src + s * WP * TPS + 4 * c);
+                cp_async_commit();
             }
-            __syncthreads();
-
-            // ---- backward sweep
-            int cur = 0;
-            for (int l = L - 1; l >= 0; --l) {
-                float* Dc = D + cur * BUF;
-                float* Dn = D + (cur ^ 1) * BUF;
-                if (l == 0) {
-                    gw_gemm<C, KIN, 1>(Bm1, Dc, ig, jg, part + pl.off_gw[0] + tid * C::TJ,
-                                       part + pl.off_gb[0] + jg * C::TJ, first);
-                } else {
-                    const float* Bprev = B + (l - 1) * BUF;
-                    gw_gemm<C, WP, C::TI>(Bprev, Dc, ig, jg, part + pl.off_gw[l] + tid * (C::TI * C::TJ),
-                                          part + pl.off_gb[l] + jg * C::TJ, first);
-                    // abar_{l-1} = zbar_l W_l^T, then through act' / act'' of layer l-1
-                    if (ng < net.wpad[l - 1]) {
-                        float acc[S][4][TN];
-                        adj_gemm<C>(Dc, Wl + (l - 1) * WP * WS, net.wpad[l], p0, ng, acc);
-#pragma unroll
-                        for (int t = 0; t < TN; ++t) {
-                            const int i = ng + C::NNG * t;
-                            if (i < net.wpad[l - 1]) {
-                                const float4 a4 = lds4(Bprev + i * TPS + p0);
-                                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                                float d1[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, zb[4];
-#pragma unroll
-                                for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
-#pragma unroll
-                                for (int s = 1; s < S; ++s) {
-                                    const float4 da4 = lds4(Bprev + (s * WP + i) * TPS + p0);
-                                    const float da[4] = {da4.x, da4.y, da4.z, da4.w};
-                                    float o[4];
-#pragma unroll
-                                    for (int p = 0; p < 4; ++p) {
-                                        cross[p] = fmaf(acc[s][p][t], da[p], cross[p]);
-                                        o[p] = acc[s][p][t] * d1[p];
-                                    }
-                                    sts4(Dn + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
-                                }
-#pragma unroll
-                                for (int p = 0; p < 4; ++p)
-                                    zb[p] = fmaf(acc[0][p][t], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
-                                sts4(Dn + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
-                            }
-                        }
-                    }
-                }
+            float acc[S][4][TN];
+            const bool active = ng < net.wpad[l - 1];
+            if (active) adj_gemm<C>(X, m.Wl + (l - 1) * WP * WS, net.wpad[l], p0, ng, acc);
+            if (l < L - 1) {
+                cp_async_wait_all();
                 __syncthreads();
-                cur ^= 1;
             }
-            first = false;
-        } else {
+            // through act' / act'' of layer l-1: zbar_{l-1}, dzbar_{l-1} -> Z
+            if (active) {
+#pragma unroll
+                for (int t = 0; t < TN; ++t) {
+                    const int i = ng + C::NNG * t;
+                    if (i < net.wpad[l - 1]) {
+                        const float4 a4 = lds4(Y + i * TPS + p0);
+                        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                        float d1[4], cross[4] = {0.f, 0.f, 0.f, 0.f}, zb[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) d1[p] = act_d1<C::ACT>(a[p]);
+#pragma unroll
+                        for (int s = 1; s < S; ++s) {
+                            const float4 da4 = lds4(Y + (s * WP + i) * TPS + p0);
+                            const float da[4] = {da4.x, da4.y, da4.z, da4.w};
+                            float o[4];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                cross[p] = fmaf(acc[s][p][t], da[p], cross[p]);
+                                o[p] = acc[s][p][t] * d1[p];
+                            }
+                            sts4(Z + (s * WP + i) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+                            zb[p] = fmaf(acc[0][p][t], d1[p], act_d2r<C::ACT>(a[p]) * cross[p]);
+                        sts4(Z + i * TPS + p0, make_float4(zb[0], zb[1], zb[2], zb[3]));
+                    }
+                }
+            }
+            // gW_l, gb_l from (B_{l-1}, zbar_l)
+            gw_gemm<C, WP, C::TI>(Y, X, ig, jg, kslice, part + pl.off_gw[l] + tid * (C::TI * C::TJ),
+                                  part + pl.off_gb[l] + kslice * WP + jg * C::TJ, first);
             __syncthreads();
+            float* t = X; X = Z; Z = Y; Y = t;               // zbar_{l-1} becomes the operand; the other two are free
         }
+        // layer 0: gW_0, gb_0 from the inputs (layer "-1": X rows + unit tangent rows)
+        gw_gemm<C, KIN, 1>(m.Bm1, X, ig, jg, kslice, part + pl.off_gw[0] + tid * C::TJ,
+                           part + pl.off_gb[0] + kslice * WP + jg * C::TJ, first);
+        __syncthreads();
+        first = false;
     }
+    if (FUSED && lane == 0) A.lossPart[blockIdx.x * C::NW + warp] = lossAcc;
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -567,7 +718,7 @@ struct FinalArgs {
     NetDesc net; PartLayout pl;
     const double* partVar; int nVar;        // per-CTA slabs of the variational adjoint kernel
     const double* partBic; int nBic;        // ... of the boundary/initial adjoint kernel
-    const double* segSum; int nSeg;         // block partials from vn_segreduce_kernel
+    const double* segSum; int nSeg;         // partial sums of (detJ_i) R_i^2
     const float* detJ; int detJvec;
     const float* cj; unsigned int nbi, bDof; int timeDependent;
     const float* wts;
