@@ -23,11 +23,14 @@ def run(nb, lw, act, dim=2, inpDim=3, integNum=64, reps=5):
         dt = (time.perf_counter() - t0) / reps
         M = sum(i * o for i, o in go.layer_sizes(inpDim, lw))
         print("%-10s lw=%s P=%d  %.3f ms  %.3e pts/s  alg %.2f TFLOP/s" % (name, lw, P, dt * 1e3, P / dt, 6 * (1 + dim) * M * P / dt / 1e12 if name != "loss" else 2 * (1 + dim) * M * P / dt / 1e12))
+    eng.profile_enable(True); eng.profile_read()
+    for _ in range(reps): eng.lib.vn_train_step(eng._h, 1e-3, None)
+    pr = eng.profile_read()
+    print("   per-kernel us:", {k: round(v[0] * 1e3 / max(v[1], 1), 1) for k, v in pr.items()})
     eng.close()
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    run(1 << 14, [64] * 4, "tanh")
     run(1 << 16, [64] * 4, "tanh")
     run(1 << 16, [10, 20], "sigmoid")
     run(1 << 16, [16] * 4, "tanh")

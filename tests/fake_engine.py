@@ -1,0 +1,111 @@
+"""TEST-ONLY stand-in for varnet_b200._capi.Engine backed by the FP64 oracle.
+
+Lets the CPU suite exercise the `TFNN` shim's protocol logic (feed caching, fetch semantics, tower
+sums, checkpointing) — including under the reference's own unmodified `VarNet.train` — in a container
+without a GPU.  It is injected by monkeypatching inside tests only; the product never imports it
+(the real Engine raises when no CUDA device is present)."""
+import numpy as np
+
+from oracle import graph_oracle as go
+
+
+class FakeCfg:
+    device = 0
+
+
+class FakeEngine:
+    instances = []
+
+    def __init__(self, dim, inpDim, layerWidth, activation="sigmoid", timeDependent=True, isSource=False,
+                 integWflag=False, optimizer="adam", device=0):
+        self.dim, self.inpDim, self.layerWidth = dim, inpDim, list(layerWidth)
+        self.kw = dict(dim=dim, inpDim=inpDim, layerWidth=self.layerWidth, activation=activation,
+                       timeDependent=timeDependent, lossOpt=dict(isSource=isSource, integWflag=integWflag))
+        self.optimizer = optimizer
+        self.cfg = FakeCfg(); self.cfg.device = device
+        self.nparam = go.param_count(inpDim, self.layerWidth)
+        self.theta = np.zeros(self.nparam); self.m = np.zeros(self.nparam); self.v = np.zeros(self.nparam)
+        self.step = 0
+        self.feed = {"w": np.ones(3)}          # the real engine also starts with unit loss weights
+        self.calls = dict(upload_points=0, upload_bic=0, loss=0, loss_grad=0, step=0, eval=0)
+        self.gbuf = np.zeros(self.nparam + 4)
+        FakeEngine.instances.append(self)
+
+    def close(self):
+        pass
+
+    def set_params(self, theta):
+        self.theta = np.asarray(theta, dtype=np.float32).astype(np.float64).copy()
+        self.m[:] = 0; self.v[:] = 1.0 if self.optimizer.startswith("rms") else 0.0; self.step = 0
+
+    def get_params(self):
+        return self.theta.astype(np.float32)
+
+    def get_optimizer_state(self):
+        return self.m.astype(np.float32), self.v.astype(np.float32), self.step
+
+    def set_optimizer_state(self, m, v, step):
+        self.m, self.v, self.step = np.array(m, dtype=np.float64), np.array(v, dtype=np.float64), int(step)
+
+    def upload_points(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None):
+        self.feed.update(Input=np.array(Input), gcoef=np.array(gcoef), source=source, N=N, dNt=dNt,
+                         intShape=list(intShape), integW=integW, detJ=detJ, detJvec=detJvec)
+        self.nb = int(intShape[0])
+        self.calls["upload_points"] += 1
+
+    def upload_bic(self, biInput, biLabel, bDof, biDimVal, dtype=None):
+        self.feed.update(biInput=np.array(biInput), biLabel=np.array(biLabel), bDof=bDof, biDimVal=biDimVal)
+        self.calls["upload_bic"] += 1
+
+    def set_weights(self, w):
+        self.feed["w"] = np.asarray(w, dtype=np.float64).reshape(3).copy()
+
+    def _run(self, need_grad):
+        return go.loss_and_grad(self.theta.astype(np.float32), self.feed, need_grad=need_grad, **self.kw)
+
+    def loss(self, lossVec=False):
+        self.calls["loss"] += 1
+        r = self._run(False)
+        out = dict(loss=np.float32(r["loss"]), BCloss=np.float32(r["BCloss"]), ICloss=np.float32(r["ICloss"]),
+                   varLoss=np.float32(r["varLoss"]))
+        if lossVec:
+            out["lossVec"] = r["lossVec"].astype(np.float32)
+        return out
+
+    def loss_grad(self, fetch=True):
+        self.calls["loss_grad"] += 1
+        r = self._run(True)
+        self.gbuf[:self.nparam] = r["grad"]
+        self.gbuf[self.nparam:] = [r["loss"], r["BCloss"], r["ICloss"], r["varLoss"]]
+        if fetch:
+            return dict(loss=np.float32(r["loss"]), BCloss=np.float32(r["BCloss"]), ICloss=np.float32(r["ICloss"]),
+                        varLoss=np.float32(r["varLoss"]), grad=r["grad"].astype(np.float32))
+
+    def optimizer_step(self, lr):
+        self.calls["step"] += 1
+        g = self.gbuf[:self.nparam]
+        self.step += 1
+        if self.optimizer.startswith("rms"):
+            self.theta, self.v, self.m = go.rmsprop_step(self.theta, g, self.v, self.m, lr=lr)
+        else:
+            self.theta, self.m, self.v = go.adam_step(self.theta, g, self.m, self.v, self.step, lr=lr)
+
+    def train_step(self, lr, fetch_loss=True):
+        self.loss_grad(fetch=False)
+        loss = self.gbuf[self.nparam]
+        self.optimizer_step(lr)
+        return np.float32(loss) if fetch_loss else None
+
+    def eval(self, X):
+        self.calls["eval"] += 1
+        X = np.asarray(X, dtype=np.float32).astype(np.float64).reshape(-1, self.inpDim)
+        return go.mlp_value(self.theta.astype(np.float32).astype(np.float64), X, self.inpDim, self.layerWidth,
+                            go.act_id(self.kw["activation"])).astype(np.float32)
+
+    def residual(self, X, diff, vel, diff_dx, source):
+        n = np.asarray(X).reshape(-1, self.inpDim).shape[0]
+        bc = lambda a, c: np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1, c) if np.size(a) > 1 else np.full((1, c), float(np.asarray(a).reshape(-1)[0])), (n, c))
+        u, r = go.strong_residual(self.theta.astype(np.float32), X, bc(diff, 1), bc(vel, self.dim), bc(diff_dx, self.dim),
+                                  bc(source, 1), self.dim, self.inpDim, self.layerWidth, self.kw["activation"],
+                                  self.kw["timeDependent"])
+        return u.astype(np.float32), r.astype(np.float32)

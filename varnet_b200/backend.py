@@ -346,6 +346,26 @@ class Saver:
                 tw.engine.set_optimizer_state(z["m"], z["v"], int(z["step"]))
 
 
+class _TFCompat:
+    """The handful of TensorFlow calls `VarNet.py` makes outside `TFNN`:
+    `tf.global_variables_initializer()` (VarNet.py:1412) and `tf.trainable_variables()`
+    (VarNet.py:2197).  Bound to the most recently constructed TFNN."""
+    current = None
+
+    @staticmethod
+    def global_variables_initializer():
+        return GlobalInit()
+
+    @classmethod
+    def trainable_variables(cls):
+        if cls.current is None:
+            raise RuntimeError("no TFNN has been constructed")
+        return [arr for _, arr in cls.current.trainable_variables()]
+
+
+tf_compat = _TFCompat
+
+
 # ------------------------------------------------------------------ TFNN
 class TFNN:
     """Same constructor as the reference (`TFModel.py:85-86`).
@@ -417,6 +437,7 @@ class TFNN:
         self.optMinimize, self.step = Node("optMinimize"), Node("step")
         self.saver = Saver(self)
         self.sess = Session(self)
+        _TFCompat.current = self
         self.initialize_variables()
 
     # weights are shared by all towers (TFModel.py:180): every engine holds the same copy

@@ -96,15 +96,17 @@ __device__ static double block_sum(double v, double* sh) {
     return r;   // valid in thread 0
 }
 
-// Blocks [0, gridDim.x-1): one thread per flat parameter sums the per-CTA FP64 slabs in a fixed
-// order (deterministic replacement for TF's gradient accumulation).  Last block: the loss scalars
-// loss = w0*bCs + w1*iCs + w2*varLoss (TFModel.py:643-666).
+// Blocks [0, gridDim.x-1): one WARP per flat parameter sums the per-CTA FP64 slabs: lane c takes slabs
+// c, c+32, ... in order and the lanes are combined by a fixed xor tree (deterministic replacement for
+// TF's gradient accumulation; a serial per-thread walk over ~300 slabs was latency-bound).
+// Last block: the loss scalars loss = w0*bCs + w1*iCs + w2*varLoss (TFModel.py:643-666).
 __global__ void vn_finalize_kernel(FinalArgs A) {
     const NetDesc& net = A.net;
     const PartLayout& pl = A.pl;
     if (blockIdx.x + 1 < gridDim.x) {
         if (!A.needGrad) return;
-        const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (idx >= net.nparam) return;
         // locate (layer, kind, i, j)
         int l = 0, isBias = 0, i = 0, j = 0;
@@ -127,16 +129,17 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             const int own = (jg >> 2) * 32 + ig + 8 * (jg & 3);
             nslot = pl.KS;
             for (int h = 0; h < pl.KS; ++h) {
-                const int tid = h * 128 + own;
-                slot[h] = pl.off_gw[l] + (l == 0 ? tid * pl.TJ + u : tid * (pl.TI * pl.TJ) + t * pl.TJ + u);
+                const int tid = h * 128 + own, r = (l == 0 ? 0 : t * pl.TJ) + u;
+                slot[h] = pl.off_gw[l] + (r >> 1) * (2 * pl.NT) + 2 * tid + (r & 1);   // pair-interleaved slab
             }
         }
         double s = 0.0;
-        for (int p = 0; p < nslot; ++p) {
-            for (int c = 0; c < A.nVar; ++c) s += A.partVar[(size_t)c * pl.psz + slot[p]];
-            for (int c = 0; c < A.nBic; ++c) s += A.partBic[(size_t)c * pl.psz + slot[p]];
-        }
-        A.gbuf[idx] = (float)s;
+        for (int c = lane; c < A.nVar; c += 32)
+            for (int p = 0; p < nslot; ++p) s += __ldcg(A.partVar + (size_t)c * pl.psz + slot[p]);
+        for (int c = lane; c < A.nBic; c += 32)
+            for (int p = 0; p < nslot; ++p) s += __ldcg(A.partBic + (size_t)c * pl.psz + slot[p]);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) A.gbuf[idx] = (float)s;
         return;
     }
     __shared__ double sh[32];
@@ -688,7 +691,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         f.detJ = e->detJ.as<float>(); f.detJvec = e->detJvec;
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
-        const int nb = needGrad ? (e->net.nparam + 127) / 128 : 0;
+        const int nb = needGrad ? (e->net.nparam + 3) / 4 : 0;          // one warp per parameter, 4 warps per block
         ProfScope ps(e, PK_FINAL);
         vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
         CK(cudaGetLastError());

@@ -214,6 +214,7 @@ __device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const flo
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int t = 0; t < C::TN; ++t) acc[s][p][t] = 0.f;
+#pragma unroll 2
     for (int j0 = 0; j0 < Kout; j0 += 4) {
         float4 w[C::TN];
 #pragma unroll
@@ -251,6 +252,15 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
         for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
 #pragma unroll
     for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
+    // FP64 partial slab, pair-interleaved so that a warp's 128-bit accesses are contiguous:
+    // element r = t*TJ+u of thread `tid` lives at pgw[(r>>1)*2*NT + (r&1)]  (pgw already includes 2*tid).
+    // The previous partial sums are fetched from L2 BEFORE the K loop so their latency hides under it.
+    static_assert(C::TJ % 2 == 0, "pair layout");
+    double2 old[TIK * C::TJ / 2];
+    if (!first) {
+#pragma unroll
+        for (int r = 0; r < TIK * C::TJ / 2; ++r) old[r] = __ldcg(reinterpret_cast<const double2*>(pgw + r * (2 * C::NT)));
+    }
     constexpr int PSL = C::TP / C::KS;
     const int pbeg = kslice * PSL;
 #pragma unroll
@@ -277,24 +287,18 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
             }
         }
     }
-    if (first) {
 #pragma unroll
-        for (int t = 0; t < TIK; ++t)
+    for (int t = 0; t < TIK; ++t)
 #pragma unroll
-            for (int u = 0; u < C::TJ; ++u) __stcg(pgw + t * C::TJ + u, (double)acc[t][u]);
-        if (ig == 0) {
-#pragma unroll
-            for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, (double)bacc[u]);
+        for (int u = 0; u < C::TJ; u += 2) {
+            const int r = (t * C::TJ + u) >> 1;
+            double2 v = make_double2((double)acc[t][u], (double)acc[t][u + 1]);
+            if (!first) { v.x += old[r].x; v.y += old[r].y; }
+            __stcg(reinterpret_cast<double2*>(pgw + r * (2 * C::NT)), v);
         }
-    } else {
+    if (ig == 0) {
 #pragma unroll
-        for (int t = 0; t < TIK; ++t)
-#pragma unroll
-            for (int u = 0; u < C::TJ; ++u) __stcg(pgw + t * C::TJ + u, __ldcg(pgw + t * C::TJ + u) + (double)acc[t][u]);
-        if (ig == 0) {
-#pragma unroll
-            for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, __ldcg(pgb + u) + (double)bacc[u]);
-        }
+        for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, first ? (double)bacc[u] : __ldcg(pgb + u) + (double)bacc[u]);
     }
 }
 
@@ -692,13 +696,13 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
                 }
             }
             // gW_l, gb_l from (B_{l-1}, zbar_l)
-            gw_gemm<C, WP, C::TI>(Y, X, ig, jg, kslice, part + pl.off_gw[l] + tid * (C::TI * C::TJ),
+            gw_gemm<C, WP, C::TI>(Y, X, ig, jg, kslice, part + pl.off_gw[l] + 2 * tid,
                                   part + pl.off_gb[l] + kslice * WP + jg * C::TJ, first);
             __syncthreads();
             float* t = X; X = Z; Z = Y; Y = t;               // zbar_{l-1} becomes the operand; the other two are free
         }
         // layer 0: gW_0, gb_0 from the inputs (layer "-1": X rows + unit tangent rows)
-        gw_gemm<C, KIN, 1>(m.Bm1, X, ig, jg, kslice, part + pl.off_gw[0] + tid * C::TJ,
+        gw_gemm<C, KIN, 1>(m.Bm1, X, ig, jg, kslice, part + pl.off_gw[0] + 2 * tid,
                            part + pl.off_gb[0] + kslice * WP + jg * C::TJ, first);
         __syncthreads();
         first = false;
