@@ -277,7 +277,7 @@ def main():
         pk = peaks()
         bytes_pt = 4 * (meta["inpDim"] + meta["dim"] + 1)
         roofline = dict(bound="fp32", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf if peak_tf else None,
-                        traffic=None, kernel="vn_tile_kernel<MODE_VAR_ADJ>", kernel_ms=kernel_ms,
+                        traffic=None, kernel="vn_adj_kernel<MODE_VAR_FUSED>", kernel_ms=kernel_ms,
                         kernel_share_of_step=kernel_ms / ms_step if ms_step else None,
                         flop_per_point=flop_pt, points_per_launch=P_local,
                         peak_source="FFMA microbenchmark (vn_fp32_peak_tflops) measured in this run",
