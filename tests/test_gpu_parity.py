@@ -98,3 +98,29 @@ def test_adam_matches_tf_formula():
         th, m, v = go.adam_step(th, ref["grad"], m, v, t, lr=1e-3)
         assert rel_inf(eng.get_params(), th) <= 2e-5
     eng.close()
+
+
+RES_CASES = [(1, 2, [20], "sigmoid", True), (2, 3, [10, 20], "sigmoid", True), (2, 3, [64, 64, 64, 64], "tanh", True),
+             (2, 2, [16, 24], "tanh", False), (1, 3, [10, 20, 30], "sigmoid", True), (1, 1, [12], "tanh", False)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RES_CASES, ids=[str(c[2]) + c[3] + ("_d%d" % c[0]) for c in RES_CASES])
+def test_strong_residual_matches_oracle(case):
+    """vn_residual_f64 vs NNModel.Residual restated (TFModel.py:718-772): u_t, Laplacian by
+    forward-over-forward second derivatives."""
+    dim, inpDim, lw, act, td = case
+    rng = np.random.RandomState(77)
+    n = 777
+    theta = go.glorot_init(inpDim, lw, seed=9) + 0.05 * rng.randn(go.param_count(inpDim, lw)).astype(np.float32)
+    X = rng.uniform(-1, 1, (n, inpDim)); diff = rng.rand(n, 1) * 0.1; vel = rng.randn(n, dim)
+    ddx = rng.randn(n, dim) * 0.01; src = rng.randn(n, 1)
+    from varnet_b200._capi import Engine
+    eng = Engine(dim, inpDim, lw, act, td)
+    eng.set_params(theta)
+    u, res = eng.residual(X, diff, vel, ddx, src)
+    uo, ro = go.strong_residual(theta, X, diff, vel, ddx, src, dim, inpDim, lw, act, td)
+    assert rel_inf(u, uo) <= TOL
+    # the residual mixes terms of different size: bound relative to the sum of their magnitudes
+    assert np.abs(res - ro).max() <= TOL * np.abs(ro).max() + 1e-6
+    eng.close()

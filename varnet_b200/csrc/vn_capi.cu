@@ -218,6 +218,20 @@ __global__ void vn_pack_kernel(const T* __restrict__ X, int inpDim, const T* __r
     if (dNt && colT >= 0) cols[(size_t)colT * pstride + gp] = to_f32<T>(dNt[r]);
     if (src && N && colS >= 0) cols[(size_t)colS * pstride + gp] = to_f32<T>(src[r]) * to_f32<T>(N[r]);   // float32 product, as tf.multiply(source, N) (:657)
 }
+// residual inputs: X | diff | vel[dim] | diff_dx[dim] | source  ->  SoA columns
+template <typename T>
+__global__ void vn_pack_res_kernel(const T* __restrict__ X, int inpDim, const T* __restrict__ diff,
+                                   const T* __restrict__ vel, const T* __restrict__ ddx, const T* __restrict__ src,
+                                   int dim, float* __restrict__ cols, long long pstride, long long n) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int c = 0;
+    for (int k = 0; k < inpDim; ++k) cols[(size_t)(c++) * pstride + r] = to_f32<T>(X[r * inpDim + k]);
+    cols[(size_t)(c++) * pstride + r] = to_f32<T>(diff[r]);
+    for (int k = 0; k < dim; ++k) cols[(size_t)(c++) * pstride + r] = to_f32<T>(vel[r * dim + k]);
+    for (int k = 0; k < dim; ++k) cols[(size_t)(c++) * pstride + r] = to_f32<T>(ddx[r * dim + k]);
+    cols[(size_t)(c++) * pstride + r] = to_f32<T>(src[r]);
+}
 template <typename T>
 __global__ void vn_cast_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,8 +275,9 @@ struct vn_engine {
     // scratch
     DevBuf stage, evalCols, evalOut;
     // geometry
-    TileGeom gVarFwd, gVarAdj, gBicFwd, gBicAdj, gEval;
+    TileGeom gVarFwd, gVarAdj, gBicFwd, gBicAdj, gEval, gRes;
     bool weightsSet = false;
+    bool resOK = true;           // strong-form residual kernel available for this depth/width
     // optional per-kernel CUDA-event timing (vn_profile_enable / vn_profile_read)
     bool profOn = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profPending[VN_PROF_SLOTS];
@@ -341,18 +356,20 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
               vn_tile_geometry(e->S, e->wclass, act, MODE_VAR_ADJ, L, &e->gVarAdj) &&
               vn_tile_geometry(1, e->wclass, act, MODE_BIC_FWD, L, &e->gBicFwd) &&
               vn_tile_geometry(1, e->wclass, act, MODE_BIC_ADJ, L, &e->gBicAdj) &&
-              vn_tile_geometry(1, e->wclass, act, MODE_EVAL, L, &e->gEval);
+              vn_tile_geometry(1, e->wclass, act, MODE_EVAL, L, &e->gEval) &&
+              vn_tile_geometry(VN_S_RES, e->wclass, act, MODE_RESIDUAL, L, &e->gRes);
     if (!ok) { delete e; return fail(VN_E_UNSUPPORTED, "no compiled kernel for this configuration"); }
     const size_t smemMax = prop.sharedMemPerBlockOptin;
-    const TileGeom* gs[6] = {&e->gVarFwd, &e->gVarAdj, &e->gBicFwd, &e->gBicAdj, &e->gEval, &e->gVarAdj};
-    const int modes[6] = {MODE_VAR_FWD, MODE_VAR_ADJ, MODE_BIC_FWD, MODE_BIC_ADJ, MODE_EVAL, MODE_VAR_FUSED};
-    for (int k = 0; k < 6; ++k) {
+    const TileGeom* gs[7] = {&e->gVarFwd, &e->gVarAdj, &e->gBicFwd, &e->gBicAdj, &e->gEval, &e->gVarAdj, &e->gRes};
+    const int modes[7] = {MODE_VAR_FWD, MODE_VAR_ADJ, MODE_BIC_FWD, MODE_BIC_ADJ, MODE_EVAL, MODE_VAR_FUSED, MODE_RESIDUAL};
+    for (int k = 0; k < 7; ++k) {
+        if (gs[k]->smemBytes > smemMax && k == 6) { e->resOK = false; continue; }   // evaluation-only kernel: not fatal
         if (gs[k]->smemBytes > smemMax) {
             const size_t need = gs[k]->smemBytes;
             delete e;
             return fail(VN_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA (limit %zu): depth/width outside the resident-tile kernel family", need, smemMax);
         }
-        const int S = (k < 2 || k == 5) ? e->S : 1;
+        const int S = (k < 2 || k == 5) ? e->S : (k == 6 ? VN_S_RES : 1);
         cudaError_t ce = vn_tile_prepare(S, e->wclass, act, modes[k], gs[k]->smemBytes);
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
     }
@@ -593,6 +610,7 @@ static void base_args(const vn_engine* e, TileArgs* a) {
     a->theta = e->theta.as<float>();
     a->timeDependent = e->cfg.timeDependent;
     a->isSource = e->cfg.isSource;
+    a->dim = e->cfg.dim;
     a->wts = e->wts.as<float>();
 }
 static void var_args(const vn_engine* e, TileArgs* a) {
@@ -796,10 +814,49 @@ static int eval_impl(vn_engine* e, const T* X, int64_t n, float* u) {
 extern "C" int vn_eval_f32(vn_engine* e, const float* X, int64_t n, float* u) { return eval_impl<float>(e, X, n, u); }
 extern "C" int vn_eval_f64(vn_engine* e, const double* X, int64_t n, float* u) { return eval_impl<double>(e, X, n, u); }
 
-extern "C" int vn_residual_f64(vn_engine* e, const double*, const double*, const double*, const double*, const double*,
-                               int64_t, float*, float*) {
-    (void)e;
-    return fail(VN_E_UNSUPPORTED, "strong-form residual kernel not built yet");
+extern "C" int vn_residual_f64(vn_engine* e, const double* X, const double* diff, const double* vel,
+                               const double* diff_dx, const double* source, int64_t n, float* u, float* res) {
+    if (!e || !X || !diff || !vel || !diff_dx || !source || !res) return fail(VN_E_INVALID, "null argument");
+    if (n < 1) return fail(VN_E_INVALID, "need at least one evaluation point");
+    if (n >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "too many evaluation points in one call");
+    if (!e->resOK) return fail(VN_E_UNSUPPORTED, "strong-form residual kernel does not fit shared memory for this network depth");
+    const vn_config& c = e->cfg;
+    CK(cudaSetDevice(c.device));
+    const int ncol = c.inpDim + 2 + 2 * c.dim;
+    const long long stride = (n + kPad - 1) / kPad * kPad;
+    CK(e->evalCols.ensure((size_t)ncol * stride * sizeof(float)));
+    CK(e->evalOut.ensure((size_t)2 * stride * sizeof(float)));
+    CK(cudaMemsetAsync(e->evalCols.p, 0, (size_t)ncol * stride * sizeof(float), e->stream));
+    const size_t rowVals = (size_t)c.inpDim + 2 + 2 * c.dim;
+    CK(e->stage.ensure((size_t)n * rowVals * sizeof(double)));
+    double* sX = e->stage.as<double>();
+    double* sD = sX + n * c.inpDim;
+    double* sV = sD + n;
+    double* sG = sV + n * c.dim;
+    double* sS = sG + n * c.dim;
+    CK(cudaMemcpyAsync(sX, X, (size_t)n * c.inpDim * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sD, diff, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sV, vel, (size_t)n * c.dim * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sG, diff_dx, (size_t)n * c.dim * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sS, source, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    vn_pack_res_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(sX, c.inpDim, sD, sV, sG, sS, c.dim,
+                                                                                  e->evalCols.as<float>(), stride, n);
+    CK(cudaGetLastError());
+    TileArgs a;
+    base_args(e, &a);
+    a.cols = e->evalCols.as<float>(); a.pstride = stride;
+    a.colX = 0; a.colD = c.inpDim; a.colG = c.inpDim + 1; a.colDD = c.inpDim + 1 + c.dim; a.colS = c.inpDim + 1 + 2 * c.dim;
+    a.colT = -1; a.dim = c.dim;
+    a.P = (unsigned int)n;
+    a.uout = e->evalOut.as<float>(); a.Iw = e->evalOut.as<float>() + stride;
+    const TileGeom& g = e->gRes;
+    a.ntiles = (int)(stride / g.TP);
+    CK(vn_tile_launch(VN_S_RES, e->wclass, c.act, MODE_RESIDUAL, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, e->stream));
+    e->launches += 2;
+    if (u) CK(cudaMemcpyAsync(u, e->evalOut.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(res, e->evalOut.as<float>() + stride, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
 }
 
 extern "C" int vn_profile_enable(vn_engine* e, int on) {

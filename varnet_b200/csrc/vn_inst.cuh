@@ -4,6 +4,7 @@
 //   VN_W        hidden-width class
 //   VN_TP_ADJ   points per tile of the forward+adjoint kernels
 //   VN_TP_FWD   points per tile of the forward-only kernels
+//   VN_TP_RES   points per tile of the strong-form residual kernel (6 streams)
 //   VN_TN       neurons per thread
 #include "vn_dispatch.h"
 
@@ -12,7 +13,7 @@ namespace {
 constexpr bool is_adj(int mode) { return mode == MODE_VAR_ADJ || mode == MODE_BIC_ADJ || mode == MODE_VAR_FUSED; }
 
 template <int S, int ACT, int MODE> struct CfgOf {
-    using type = TileCfg<S, VN_W, is_adj(MODE) ? VN_TP_ADJ : VN_TP_FWD, VN_TN, ACT>;
+    using type = TileCfg<S, VN_W, is_adj(MODE) ? VN_TP_ADJ : (MODE == MODE_RESIDUAL ? VN_TP_RES : VN_TP_FWD), VN_TN, ACT>;
 };
 
 template <int S, int ACT, int MODE> bool geom(int L, TileGeom* g) {
@@ -52,7 +53,8 @@ template <int S, int ACT, int MODE> cudaError_t prepare(size_t smem) {
     VN_CASE(2, MODE_VAR_FUSED, OP, __VA_ARGS__)                                                           \
     VN_CASE(3, MODE_VAR_FWD, OP, __VA_ARGS__)                                                             \
     VN_CASE(3, MODE_VAR_ADJ, OP, __VA_ARGS__)                                                             \
-    VN_CASE(3, MODE_VAR_FUSED, OP, __VA_ARGS__)
+    VN_CASE(3, MODE_VAR_FUSED, OP, __VA_ARGS__)                                                           \
+    VN_CASE(VN_S_RES, MODE_RESIDUAL, OP, __VA_ARGS__)
 
 }  // namespace
 

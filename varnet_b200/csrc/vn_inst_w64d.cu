@@ -4,5 +4,6 @@
 #define VN_W 64
 #define VN_TP_ADJ 32
 #define VN_TP_FWD 32
+#define VN_TP_RES 32
 #define VN_TN 4
 #include "vn_inst.cuh"

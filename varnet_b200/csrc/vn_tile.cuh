@@ -33,8 +33,10 @@ enum {
     MODE_BIC_FWD = 2,   // biDimVal*(model(biInput)-biLabel)^2 (TFModel.py:643)
     MODE_VAR_ADJ = 3,   // d(w2*varLoss)/d theta, R_i read from global (any integNum)
     MODE_BIC_ADJ = 4,   // d(w0*bCs+w1*iCs)/d theta
-    MODE_VAR_FUSED = 5  // loss + d(w2*varLoss)/d theta, R_i reduced in the tile (integNum | TP)
+    MODE_VAR_FUSED = 5, // loss + d(w2*varLoss)/d theta, R_i reduced in the tile (integNum | TP)
+    MODE_RESIDUAL = 6   // strong-form residual -u_t + kappa Lap u - (vel - grad kappa).grad u + s (TFModel.py:718-772)
 };
+#define VN_S_RES 6      // residual streams: value | 3 input tangents (x.., t) | 2 second derivatives (x_0, x_1)
 
 struct NetDesc {
     int L;                          // hidden layers
@@ -51,7 +53,9 @@ struct TileArgs {
     const float* theta;             // flat parameters (device)
     const float* cols;              // SoA point table: column c at cols + c*pstride
     long long pstride;              // multiple of the tile size, zero padded
-    int colX, colG, colT, colS;     // first column of X, gcoef, dNt, source*N (-1 = absent)
+    int colX, colG, colT, colS;     // first column of X, gcoef (residual: vel), dNt, source*N (residual: source); -1 = absent
+    int colD, colDD;                // residual: diffusivity column, first grad(kappa) column
+    int dim;                        // spatial dimension (residual kernel: runtime stream roles)
     unsigned int P;                 // valid points (rows)
     int ntiles;
     int timeDependent, isSource;
@@ -320,7 +324,8 @@ struct SmemMap {
 
 // zero shared memory, stage the weights (zero padded), write the unit tangent rows of layer "-1"
 template <class C>
-__device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C>& m, float* smem, int total) {
+__device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C>& m, float* smem, int total,
+                                              int nunit = C::S - 1) {
     const NetDesc& net = A.net;
     const int tid = threadIdx.x, L = net.L;
     constexpr int NT = C::NT, WS = C::WS, WP = C::WP;
@@ -344,7 +349,7 @@ __device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C
     for (int j = tid; j < net.width[L - 1]; j += NT) m.wout[j] = th[net.woff[L] + j];
     if (tid == 0) m.wout[WP] = th[net.boff[L]];
     // d x_c / d x_k = delta_ck  (stream 1+k seeds input column k)
-    for (int idx = tid; idx < (C::S - 1) * C::TP; idx += NT) {
+    for (int idx = tid; idx < nunit * C::TP; idx += NT) {
         int k = idx / C::TP, p = idx - k * C::TP;
         m.Bm1[((1 + k) * C::KIN + k) * C::TPS + p] = 1.f;
     }
@@ -352,7 +357,7 @@ __device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C
 }
 
 // one forward layer: GEMM + bias + activation -> Bout (and optionally the global stash)
-template <class C>
+template <class C, bool RES = false>
 __device__ __forceinline__ void forward_layer(const NetDesc& net, const SmemMap<C>& m, int l, const float* Bin,
                                               float* Bout, float* stash, int p0, int ng) {
     constexpr int S = C::S, WP = C::WP, TN = C::TN, TPS = C::TPS;
@@ -374,13 +379,31 @@ __device__ __forceinline__ void forward_layer(const NetDesc& net, const SmemMap<
         const float4 v0 = make_float4(a[0], a[1], a[2], a[3]);
         sts4(Bout + off0, v0);
         if (stash) __stcg(reinterpret_cast<float4*>(stash + off0), v0);
+        if constexpr (RES) {
+            // streams 1..3: first derivatives d1*zdot_k; streams 4,5: second derivatives
+            // d2a/dx_k^2 = act''(z) zdot_k^2 + act'(z) zddot_k   (act'' = act' * act''/act')
 #pragma unroll
-        for (int s = 1; s < S; ++s) {
-            const int off = (s * WP + j0 + t) * TPS + p0;
-            const float4 v = make_float4(d1[0] * acc[s][0][t], d1[1] * acc[s][1][t], d1[2] * acc[s][2][t],
-                                         d1[3] * acc[s][3][t]);
-            sts4(Bout + off, v);
-            if (stash) __stcg(reinterpret_cast<float4*>(stash + off), v);
+            for (int s = 1; s < S; ++s) {
+                float o[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (s <= 3) o[p] = d1[p] * acc[s][p][t];
+                    else {
+                        const float zd = acc[s - 3][p][t];
+                        o[p] = d1[p] * fmaf(act_d2r<C::ACT>(a[p]) * zd, zd, acc[s][p][t]);
+                    }
+                }
+                sts4(Bout + (s * WP + j0 + t) * TPS + p0, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        } else {
+#pragma unroll
+            for (int s = 1; s < S; ++s) {
+                const int off = (s * WP + j0 + t) * TPS + p0;
+                const float4 v = make_float4(d1[0] * acc[s][0][t], d1[1] * acc[s][1][t], d1[2] * acc[s][2][t],
+                                             d1[3] * acc[s][3][t]);
+                sts4(Bout + off, v);
+                if (stash) __stcg(reinterpret_cast<float4*>(stash + off), v);
+            }
         }
     }
 }
@@ -436,14 +459,16 @@ __global__ void __launch_bounds__(C::NT, 1) vn_fwd_kernel(const __grid_constant_
     const int pg = (lane & 7) + 8 * (warp % C::NPGW);
     const int ng = (lane >> 3) + 4 * (warp / C::NPGW);
     const int p0 = 4 * pg;
-    stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, false));
+    constexpr bool RES = (MODE == MODE_RESIDUAL);
+    // residual: unit tangent rows for the dim spatial inputs and, if time dependent, the time input (column dim)
+    stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, false), RES ? A.dim + (A.timeDependent ? 1 : 0) : C::S - 1);
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const unsigned int base = (unsigned int)tile * TP;
         load_inputs<C>(A, m, base);
         __syncthreads();
         for (int l = 0; l < L; ++l) {
-            forward_layer<C>(net, m, l, m.A + ((l - 1) & 1) * BUF, m.A + (l & 1) * BUF, nullptr, p0, ng);
+            forward_layer<C, RES>(net, m, l, m.A + ((l - 1) & 1) * BUF, m.A + (l & 1) * BUF, nullptr, p0, ng);
             __syncthreads();
         }
         output_layer<C>(m, m.A + ((L - 1) & 1) * BUF, net.wpad[L - 1]);
@@ -453,6 +478,20 @@ __global__ void __launch_bounds__(C::NT, 1) vn_fwd_kernel(const __grid_constant_
             if (gp >= A.P) continue;
             if (MODE == MODE_VAR_FWD) {
                 A.Iw[gp] = integrand<C>(A, m, p, gp);
+            } else if (MODE == MODE_RESIDUAL) {
+                // res = -u_t + kappa * sum_k d2u/dx_k^2 - sum_k (vel_k - dkappa/dx_k) du/dx_k + s   (TFModel.py:750-754)
+                float res = A.timeDependent ? -m.us[(1 + A.dim) * TP + p] : 0.f;
+                float lap = 0.f, adv = 0.f;
+                for (int k = 0; k < A.dim; ++k) {
+                    lap += m.us[(4 + k) * TP + p];
+                    const float vd = __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp) -
+                                     __ldg(A.cols + (size_t)(A.colDD + k) * A.pstride + gp);
+                    adv = fmaf(vd, m.us[(1 + k) * TP + p], adv);
+                }
+                res = fmaf(__ldg(A.cols + (size_t)A.colD * A.pstride + gp), lap, res) - adv;
+                res += __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
+                A.Iw[gp] = res;
+                A.uout[gp] = m.us[p];
             } else if (MODE == MODE_EVAL) {
                 A.uout[gp] = m.us[p];
             } else {
