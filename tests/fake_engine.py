@@ -81,6 +81,16 @@ class FakeEngine:
             return dict(loss=np.float32(r["loss"]), BCloss=np.float32(r["BCloss"]), ICloss=np.float32(r["ICloss"]),
                         varLoss=np.float32(r["varLoss"]), grad=r["grad"].astype(np.float32))
 
+    def torch_device(self):
+        return "cpu"
+
+    def synchronize(self):
+        pass
+
+    def grad_tensor(self):
+        import torch
+        return torch.from_numpy(self.gbuf)          # shares memory: an all-reduce lands in self.gbuf
+
     def optimizer_step(self, lr):
         self.calls["step"] += 1
         g = self.gbuf[:self.nparam]

@@ -252,6 +252,23 @@ class Engine:
         self._check(self.lib.vn_grad_buffer(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def torch_device(self):
+        return "cuda:%d" % self.cfg.device
+
+    def grad_tensor(self):
+        """The engine's [grad | loss, BCloss, ICloss, varLoss] device buffer as a torch tensor (no copy):
+        the unit that multi-GPU callers all-reduce."""
+        import torch
+
+        class _View:
+            pass
+        ptr, n = self.grad_buffer()
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        dev = self.torch_device()
+        with torch.cuda.device(dev):
+            return torch.as_tensor(v, device=dev)
+
     def optimizer_step(self, lr):
         self._check(self.lib.vn_optimizer_step(self._h, float(lr)))
 

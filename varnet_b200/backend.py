@@ -132,13 +132,6 @@ def _dist():
     return None
 
 
-class _DevView:
-    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def _parse_device(spec):
     """'GPU:i' -> i ('CPU:*' is rejected: the engine has no CPU path)."""
     s = str(spec).upper().replace("/DEVICE:", "")
@@ -199,7 +192,7 @@ class Session:
         if dist is None:
             return vals
         import torch
-        t = torch.tensor(vals, dtype=torch.float64, device="cuda:%d" % self._local_towers()[0].engine.cfg.device)
+        t = torch.tensor(vals, dtype=torch.float64, device=self._local_towers()[0].engine.torch_device())
         dist.all_reduce(t)
         return t.cpu().numpy()
 
@@ -216,6 +209,15 @@ class Session:
             if want_lossvec:
                 lvs[tw.index] = r["lossVec"].reshape(-1, 1)
         tot = self._reduce_scalars(tot)
+        dist = _dist()
+        if dist is not None:
+            # tower-level nodes (compTowers[0].BCloss/ICloss, VarNetUtility.py:1072-1073) are tower 0's own values:
+            # every rank gets them from the rank that owns tower 0
+            import torch
+            t0 = torch.tensor(first if first is not None else np.zeros(4), dtype=torch.float64,
+                              device=self._local_towers()[0].engine.torch_device())
+            dist.broadcast(t0, src=0)
+            first = t0.cpu().numpy()
         lossVec = None
         if want_lossvec:
             dist = _dist()
@@ -237,19 +239,18 @@ class Session:
         views = []
         for tw in towers:
             tw.engine.loss_grad(fetch=False)
-            ptr, n = tw.engine.grad_buffer()
-            dev = "cuda:%d" % tw.engine.cfg.device
-            with torch.cuda.device(dev):
-                views.append(torch.as_tensor(_DevView(ptr, n), device=dev))
+            views.append(tw.engine.grad_tensor())
         if len(towers) > 1:                       # single process, several GPUs: sum on the controller
             ctrl = views[0]
-            torch.cuda.synchronize()
+            for tw in towers:
+                tw.engine.synchronize()
             total = ctrl.clone()
             for v in views[1:]:
                 total += v.to(ctrl.device)
             for v in views:
                 v.copy_(total.to(v.device))
-            torch.cuda.synchronize()
+            if ctrl.is_cuda:
+                torch.cuda.synchronize()
         if dist is not None:
             dist.all_reduce(views[0])             # NCCL SUM over NVLink: [grad | loss, BCloss, ICloss, varLoss]
         for tw in towers:
