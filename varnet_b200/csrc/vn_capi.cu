@@ -259,8 +259,14 @@ struct vn_engine {
     NetDesc net;
     int S = 0, wclass = 0, numSMs = 0;
     bool fused = false;          // per-test-function residual reduced inside the adjoint kernel (integNum | TP)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
+    cudaStream_t ownStream = nullptr;
     int64_t launches = 0;
+    // captured training step (vn_train_step): kernels of loss_grad + optimizer as one CUDA graph
+    cudaGraphExec_t stepGraph = nullptr;
+    float graphLr = -1.f;
+    int graphLaunches = 0;
+    bool graphOK = true;
     // parameters + optimizer
     DevBuf theta, m, v, gbuf, wts, stepbuf, corrbuf;
     // interior points
@@ -300,7 +306,12 @@ struct ProfScope {
     }
 };
 
-static const int kPad = 128;    // point-table padding: multiple of every tile size
+static const int kPad = 128;
+
+static void drop_graph(vn_engine* e) {
+    if (e->stepGraph) { cudaGraphExecDestroy(e->stepGraph); e->stepGraph = nullptr; }
+    e->graphLr = -1.f;
+}    // point-table padding: multiple of every tile size
 
 static int build_net(const vn_config& c, NetDesc* n) {
     memset(n, 0, sizeof(*n));
@@ -339,6 +350,7 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     vn_engine* e = new (std::nothrow) vn_engine();
     if (!e) return fail(VN_E_INVALID, "out of host memory");
     e->cfg = *cfg;
+    if (cudaStreamCreate(&e->ownStream) == cudaSuccess) e->stream = e->ownStream;
     build_net(*cfg, &e->net);
     e->S = 1 + cfg->dim;
     if (wmax > 64) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
@@ -394,6 +406,8 @@ extern "C" int vn_destroy(vn_engine* e) {
     if (!e) return VN_OK;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
+    drop_graph(e);
+    if (e->ownStream) cudaStreamDestroy(e->ownStream);
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->cols, &e->integW,
                       &e->detJ, &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
@@ -404,7 +418,8 @@ extern "C" int vn_destroy(vn_engine* e) {
 
 extern "C" int vn_set_stream(vn_engine* e, void* s) {
     if (!e) return fail(VN_E_INVALID, "null engine");
-    e->stream = reinterpret_cast<cudaStream_t>(s);
+    drop_graph(e);
+    e->stream = s ? reinterpret_cast<cudaStream_t>(s) : e->ownStream;
     return VN_OK;
 }
 extern "C" int vn_synchronize(vn_engine* e) {
@@ -484,6 +499,7 @@ static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, con
     if (nb < 1 || integNum < 1) return fail(VN_E_INVALID, "intShape must be positive");
     const long long P = (long long)nb * integNum;
     if (P >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "more than 2^31 quadrature points per engine; shard the test functions");
+    drop_graph(e);
     const vn_config& c = e->cfg;
     if (c.timeDependent && !dNt) return fail(VN_E_INVALID, "dNt is required for time-dependent problems");
     if (c.isSource && (!src || !N)) return fail(VN_E_INVALID, "source and N are required when lossOpt['isSource'] is set");
@@ -559,6 +575,7 @@ template <typename T>
 static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64_t bDof, double biDimVal) {
     if (!e || !bX || !bL) return fail(VN_E_INVALID, "biInput and biLabel are required");
     if (nbi < 1 || bDof < 0 || bDof > nbi) return fail(VN_E_INVALID, "need 0 <= bDof <= nbi and nbi >= 1");
+    drop_graph(e);
     const vn_config& c = e->cfg;
     CK(cudaSetDevice(c.device));
     e->bstride = (nbi + kPad - 1) / kPad * kPad;
@@ -771,10 +788,48 @@ extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
     return VN_OK;
 }
 extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
-    int rc = run_loss(e, true);
-    if (rc) return rc;
-    rc = vn_optimizer_step(e, lr);
-    if (rc) return rc;
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
+    CK(cudaSetDevice(e->cfg.device));
+    const bool useGraph = e->graphOK && !e->profOn && e->stream != nullptr;
+    if (useGraph && e->stepGraph && e->graphLr == lr) {
+        CK(cudaGraphLaunch(e->stepGraph, e->stream));
+        e->launches += e->graphLaunches;
+    } else if (useGraph) {
+        // capture the step once per (tables, lr): replay removes the per-kernel launch gaps that dominate
+        // the small operator configurations (5 kernels of a few tens of microseconds)
+        drop_graph(e);
+        if (!e->P) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+        if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
+        const int64_t l0 = e->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = VN_OK;
+        if (ce == cudaSuccess) {
+            rc = run_loss(e, true);
+            if (!rc) rc = vn_optimizer_step(e, lr);
+            ce = cudaStreamEndCapture(e->stream, &g);
+        }
+        if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&e->stepGraph, g, 0) != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            e->stepGraph = nullptr; e->graphOK = false;         // fall back to plain launches for this engine
+            e->launches = l0;
+            rc = run_loss(e, true);
+            if (rc) return rc;
+            rc = vn_optimizer_step(e, lr);
+            if (rc) return rc;
+        } else {
+            cudaGraphDestroy(g);
+            e->graphLr = lr; e->graphLaunches = (int)(e->launches - l0);
+            CK(cudaGraphLaunch(e->stepGraph, e->stream));
+        }
+    } else {
+        int rc = run_loss(e, true);
+        if (rc) return rc;
+        rc = vn_optimizer_step(e, lr);
+        if (rc) return rc;
+    }
     if (loss_out) {
         CK(cudaMemcpyAsync(loss_out, e->gbuf.as<float>() + e->net.nparam, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
