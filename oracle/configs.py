@@ -15,11 +15,11 @@ def _n(v, scale, lo=2):
     return max(lo, int(round(v * scale)))
 
 
-def operator_1dt(api, scale=1.0, **kw):
+def operator_1dt(api, scale=1.0, bDiscNum=None, **kw):
     domain = api.Domain1D()
     pde = api.ADPDE(domain, diff=0.1 / pi, vel=1.0, timeDependent=True, tInterval=[0, 2.0],
                     IC=lambda x: -np.sin(pi * x))
-    return api.VarNet(pde, layerWidth=[20], discNum=_n(20, scale), bDiscNum=None, tDiscNum=_n(300, scale),
+    return api.VarNet(pde, layerWidth=[20], discNum=_n(20, scale), bDiscNum=bDiscNum, tDiscNum=_n(300, scale),
                       processors='GPU:0', **kw)
 
 

@@ -171,3 +171,47 @@ def test_feed_identity_cache_and_reupload():
     l1 = tData.optimIter(tf)
     assert np.isfinite(l1)
     tf.sess.close()
+
+
+def test_optimal_sampling_with_scaled_supports_on_gpu():
+    """smpScheme='optimal' with suppFactor != 1: new test functions get smaller supports, detJ becomes a
+    per-test-function vector (the `detJvec` branch, TFModel.py:662-664; FIXData.updateOptimData)."""
+    import varnet_b200
+    np.random.seed(5)
+    vn = configs.operator_1dt(varnet_b200, 0.2, seed=2)
+    with tempfile.TemporaryDirectory() as d:
+        res = vn.train(d, weight=[10., 10., 1.], smpScheme='optimal', epochNum=12, saveFreq=4, verbose=False,
+                       trainUpdelay=4, tolUpd=1e9, addTrainPts=True, frac=0.5, suppFactor=0.5, reinitrain=False)
+    assert len(res.inpIter) == 1 and vn.fixData.detJvec and vn.fixData.nt > vn.fixData.nt0
+    assert np.all(np.isfinite(res.loss)) and res.loss[-1] < res.loss[0]
+    vn.tfData.sess.close()
+
+
+def test_rmsprop_matches_tf_formula():
+    rng = np.random.RandomState(8)
+    feed = synth_feed(rng, 1, 2, 96, 16, 40, 30)
+    lw = [12]
+    theta = go.glorot_init(2, lw, seed=4)
+    kw = dict(dim=1, inpDim=2, layerWidth=lw, activation="tanh", timeDependent=True,
+              lossOpt=dict(isSource=False, integWflag=False))
+    eng = make_engine(feed, theta=theta, optimizer="rmsprop", **kw)
+    th = theta.astype(np.float64); ms = np.ones_like(th); mom = np.zeros_like(th)
+    for _ in range(4):
+        ref = go.loss_and_grad(th.astype(np.float32), feed, **kw)
+        loss = eng.train_step(1e-3)
+        assert abs(float(loss) - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+        th, ms, mom = go.rmsprop_step(th, ref["grad"], ms, mom, lr=1e-3)
+        assert rel_inf(eng.get_params(), th) <= 2e-5
+    eng.close()
+
+
+def test_no_initial_rows_gives_nan_like_tf_mean_of_empty():
+    """Time-dependent problem fed without IC rows: tf.reduce_mean of an empty slice is nan (TFModel.py:648)."""
+    rng = np.random.RandomState(9)
+    feed = synth_feed(rng, 1, 2, 32, 16, 20, 20)
+    kw = dict(dim=1, inpDim=2, layerWidth=[8], activation="sigmoid", timeDependent=True,
+              lossOpt=dict(isSource=False, integWflag=False))
+    eng = make_engine(feed, theta=go.glorot_init(2, [8], seed=1), **kw)
+    out = eng.loss()
+    assert np.isnan(out["ICloss"]) and np.isfinite(out["BCloss"]) and np.isfinite(out["varLoss"])
+    eng.close()

@@ -102,3 +102,36 @@ def test_unmodified_reference_varnet_drives_the_shim(shim, monkeypatch):
     assert cApp.shape == (vn.fixData.nt, 1) and np.all(np.isfinite(cApp))
     res, resVec, err, _ = vn.residual()
     assert np.isfinite(res) and resVec.shape == (vn.fixData.nt, 1)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("addTrainPts", [True, False])
+def test_optimal_sampling_matches_reference_trajectory(shim, monkeypatch, addTrainPts):
+    """smpScheme='optimal' (Operator_1Dt.py:170): residual-driven rejection sampling of new test functions
+    (VarNet.py:1696-1966, UtilityFunc.py:342-404).  Same seed + same (oracle-backed) engine => the mirror must
+    select the same points, hence reproduce the reference's loss history and final weights."""
+    import varnet_b200
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    refVarNet = ref.modules["VarNet"]
+    monkeypatch.setattr(refVarNet, "TFNN", lambda *a, **k: shim.TFNN(*a, seed=7, **k))
+    monkeypatch.setattr(refVarNet, "tf", shim.tf_compat)
+    monkeypatch.setattr(time, "clock", time.perf_counter, raising=False)
+    kw = dict(weight=[10., 10., 1.], smpScheme='optimal', epochNum=8, saveFreq=2, verbose=False, trainUpdelay=3,
+              tolUpd=1e9, addTrainPts=addTrainPts, frac=0.3)
+    out = []
+    for api, extra in ((ref, {}), (varnet_b200, dict(seed=7))):
+        np.random.seed(1234)
+        # bDiscNum must be numeric here: the reference's optBiTrainPoints computes ceil(frac2*bDiscNum)
+        # (VarNet.py:1914) and crashes on the None that Operator_1Dt.py:157 passes; the mirror accepts None
+        vn = configs.operator_1dt(api, 0.12, bDiscNum=50, **extra)
+        with tempfile.TemporaryDirectory() as d:
+            vn.train(d, **kw)
+        out.append((np.array(vn.trainRes.loss, dtype=float), vn.tfData.get_parameters(), vn.fixData.nt,
+                    list(vn.trainRes.inpIter)))
+    (la, tha, nta, ia), (lb, thb, ntb, ib) = out
+    assert ia == ib and len(ia) == 1                       # one re-sampling event, at the same epoch
+    assert nta == ntb
+    # the reference logs the loss every saveFreq epochs, the mirror every epoch
+    assert np.allclose(la, lb[1::2][:len(la)], rtol=1e-9)
+    assert np.allclose(tha, thb, rtol=1e-6, atol=1e-8)

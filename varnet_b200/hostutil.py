@@ -56,3 +56,45 @@ def l2_err(x_true, x_app):
     if x_true.size != x_app.size:
         raise ValueError('\'xTrue\' and \'xApp\' must have the same shape!')
     return np.linalg.norm(x_true - x_app) / np.linalg.norm(x_true)
+
+
+def split_rows(vec, counts):
+    """Consecutive row blocks of the given sizes; a trailing remainder becomes one more block
+    (what UtilityFunc.listSegment does without a callback, UtilityFunc.py:407-455)."""
+    if counts is None:
+        return [vec]
+    counts = [counts] if isinstance(counts, numbers.Number) else list(counts)
+    out, start = [], 0
+    for c in counts:
+        out.append(vec[start:start + c])
+        start += c
+    if start < len(vec):
+        out.append(vec[start:])
+    return out
+
+
+def rejection_sampling(func, smpfun, dof, dofT=None):
+    """Draw `dof[i]` samples per segment with acceptance probability func(x)/max(func) (segment-wise max
+    over the default grid `func()`), the scheme of UtilityFunc.rejectionSampling (UtilityFunc.py:342-404).
+    The order of random draws (candidate batch, then one uniform vector per segment) is kept so that a
+    seeded run selects the same points as the reference."""
+    if isinstance(dof, numbers.Number):
+        if dofT is not None:
+            raise ValueError('\'dofT\' must be None for scalar \'dof\'')
+        dof = [dof]
+    m = len(dof)
+    if m > 1 and dofT is None:
+        raise ValueError('\'dofT\' must be provided when \'dof\' is a list!')
+    fmax = [np.max(seg) for seg in split_rows(func(), dofT)]
+    kept = [[] for _ in range(m)]
+    count = [0] * m
+    while any(count[i] < dof[i] for i in range(m)):
+        samples = smpfun()
+        cand = split_rows(samples, dofT)
+        vals = split_rows(func(samples), dofT)
+        for i in range(m):
+            v = vals[i]
+            accept = (np.random.uniform(size=[len(v), 1]) < (v / fmax[i])).reshape(len(v))
+            kept[i] = stack_rows([kept[i], cand[i][accept]])
+            count[i] += int(np.sum(accept))
+    return np.vstack([kept[i][:dof[i], :] for i in range(m)])

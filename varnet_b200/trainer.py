@@ -5,10 +5,11 @@ Mirror of the reference's `VarNet` class for the MLP / weak-form path
 `trainingPoints` (`:504-600`), `biTrainPoints`/`biTrainData` (`:604-722`), `PDEinpData`
 (`:726-774`), `trainData` (`:778-897`), `MORargExtract` (`:901-1049`), `splitLoss` (`:1053-1090`),
 `trainWeight` (`:1094-1146`), `train` (`:1197-1421`), `evaluate` (`:1510-1595`), `residual`
-(`:1599-1692`), `loadModel` (checkpoint = flat vector, `:1426-1506`).
+(`:1599-1692`), residual-driven resampling `optTrainPoints`/`optBiTrainPoints` (`:1696-1966`),
+`loadModel` (checkpoint = flat vector, `:1426-1506`).
 
-Out of scope here: the RNN/GRU variant, matplotlib plotting (`simRes`), the
-periodic `weightUpdate` heuristic, residual-driven resampling (`smpScheme='optimal'`).
+Out of scope here: the RNN/GRU variant, matplotlib plotting (`simRes`, the residual
+contour plots inside `optTrainPoints`), the periodic `weightUpdate` heuristic.
 """
 import glob
 import math
@@ -19,7 +20,8 @@ import warnings
 import numpy as np
 
 from .backend import TFNN, GlobalInit
-from .hostutil import is_empty, is_none, is_number, l2_err, pair_rows, stack_rows
+from .hostutil import (is_empty, is_none, is_number, l2_err, pair_rows, rejection_sampling, split_rows,
+                       stack_rows)
 from .tables import FIXData, ManageTrainData
 
 
@@ -117,7 +119,7 @@ class VarNet:
         """Quadrature-point coordinates Input[nT, feDim]: centre + h*delta, space index slow, time
         index fast, Gauss index fastest (VarNet.py:576-586)."""
         if smpScheme == 'optimal':
-            raise NotImplementedError('residual-driven resampling is not built yet (SURVEY.md §8f-3)')
+            return self.optTrainPoints(frac, addTrainPts, suppFactor)
         rfrac = frac if smpScheme == 'random' else 0.
         fd, PDE, dim = self.fixData, self.PDE, self.dim
         td, domain = PDE.timeDependent, PDE.domain
@@ -144,6 +146,94 @@ class VarNet:
         Input = np.stack(cols, axis=1)
         biInput, biDof = self.biTrainPoints(mesh, t_coord)
         return Input, [], biInput, biDof
+
+    # ------------------------------------------------------------------ residual-driven sampling
+    def optTrainPoints(self, frac=0.25, addTrainPts=True, suppFactor=1.0):
+        """Test-function centres drawn by rejection sampling on |strong-form residual| (VarNet.py:1696-1860),
+        stacked before the (possibly thinned) uniform ones; with suppFactor != 1 the new supports are
+        scaled and detJ becomes a per-test-function vector (FIXData.updateOptimData).  Plots are skipped."""
+        fd, PDE, dim = self.fixData, self.PDE, self.dim
+        td, domain = PDE.timeDependent, PDE.domain
+        nt, nT, hVec, delta, integNum = fd.nt0, fd.nT, fd.hVec, fd.delta, fd.integNum
+        keep = 1 if addTrainPts else (1 - frac) ** (1 / fd.feDim)
+        if td:
+            tDisc2 = math.ceil(keep * self.tDiscNum)
+            _, t_coord = self.timeDisc(tDisc2)
+        else:
+            tDisc2, t_coord = 1, []
+        mesh = domain.getMesh([math.ceil(keep * d) for d in self.discNum], self.bDiscNum)
+        uniform_part = pair_rows(mesh.coordinates, t_coord)
+        nt1 = math.ceil(frac * nt) if addTrainPts else nt - mesh.dof * tDisc2
+        scaled = np.abs(suppFactor - 1.0) >= 1.e-15
+        tole = suppFactor * hVec[:dim] if scaled else None
+        tolt = suppFactor * hVec[-1] if (scaled and td) else None
+
+        def resfun(pts=None):
+            return np.abs(self.residual(pts)[1])
+
+        def smpfun():
+            tc = self.timeDisc(rfrac=1, sortflg=False, discTol=tolt)[1] if td else []
+            m = domain.getMesh(self.discNum, self.bDiscNum, rfrac=1, sortflg=False, discTol=tole)
+            return pair_rows(m.coordinates, tc)
+
+        optimal_part = rejection_sampling(resfun, smpfun, nt1)
+        if addTrainPts:
+            nt = nt1 + nt
+            nT = nt * integNum
+        pts = np.vstack([optimal_part, uniform_part])
+        coord = pts[:, :dim]
+        if td:
+            t_coord = pts[:, dim:dim + 1]
+            if not scaled:                                      # identical supports: order by time
+                order = np.argsort(t_coord, axis=0).reshape(nt)
+                coord, t_coord = coord[order], t_coord[order]
+        biInput, biDof, _, _ = self.optBiTrainPoints(frac, addTrainPts)
+        if scaled:
+            supp = np.ones([nt, 1]); supp[:nt1, :] = suppFactor
+        else:
+            supp = 1.0
+        cols = [(coord[:, d].reshape(nt, 1) + hVec[d] * delta[d, :] * supp).reshape(nT) for d in range(dim)]
+        if td:
+            cols.append((t_coord + hVec[-1] * delta[-1, :] * supp).reshape(nT))
+        Input = np.stack(cols, axis=1)
+        if addTrainPts:
+            self.fixData.updateOptimData(frac, suppFactor)
+        return Input, [], biInput, biDof
+
+    def optBiTrainPoints(self, frac=0.25, addTrainPts=True):
+        """Boundary/initial rows by rejection sampling on (model - label)^2 per boundary segment
+        (VarNet.py:1864-1966)."""
+        fd, PDE, dim = self.fixData, self.PDE, self.dim
+        td, domain, tf = PDE.timeDependent, PDE.domain, self.tfData
+        biDof = fd.biDof0
+        keep = 1 if addTrainPts else (1 - frac) ** (1 / (fd.feDim - 1))
+        t_coord = self.timeDisc(math.ceil(keep * self.tDiscNum))[1] if td else []
+        bDisc2 = math.ceil(keep * self.bDiscNum) if self.bDiscNum is not None else None
+        mesh = domain.getMesh([math.ceil(keep * d) for d in self.discNum], bDisc2)
+        uniform_part, biDof2 = self.biTrainPoints(mesh, t_coord)
+        biDof1 = [math.ceil(frac * b) for b in biDof] if addTrainPts else list(np.array(biDof) - np.array(biDof2))
+        tw = tf.compTowers[0]
+
+        def resfun(rows=None):
+            rows = fd.uniform_biInput if rows is None else rows
+            val = tf.sess.run(tf.model(tw.Input), {tw.Input: rows})
+            return (val - self.biTrainData(rows, biDof)) ** 2
+
+        def smpfun():
+            tc = self.timeDisc(rfrac=1, sortflg=False)[1] if td else []
+            m = domain.getMesh(self.discNum, self.bDiscNum, rfrac=1, sortflg=False)
+            return self.biTrainPoints(m, tc)[0]
+
+        optimal_part = rejection_sampling(resfun, smpfun, biDof1, biDof)
+        biDofNew = list(np.array(biDof1) + np.array(biDof2)) if addTrainPts else biDof
+        blocks = []
+        for o, u, n in zip(split_rows(optimal_part, biDof1), split_rows(uniform_part, biDof2), biDofNew):
+            rows = stack_rows([o, u])
+            if td:
+                order = np.argsort(rows[:, dim:dim + 1], axis=0).reshape(n)
+                rows = np.hstack([rows[:, :dim][order], rows[:, dim:dim + 1][order]])
+            blocks.append(rows)
+        return np.vstack(blocks), biDofNew, optimal_part, uniform_part
 
     def biTrainPoints(self, mesh, t_coord):
         """Dirichlet boundary rows (space x time) per boundary, then initial-condition rows [x, 0]."""
@@ -346,14 +436,17 @@ class VarNet:
             raise ValueError('weight dimension does not match!')
         if smpScheme not in ('uniform', 'random', 'optimal'):
             raise ValueError('sampling scheme is not valid!')
-        if smpScheme == 'optimal':
-            raise NotImplementedError('residual-driven resampling is not built yet (SURVEY.md §8f-3)')
         if updateWeights:
             raise NotImplementedError('periodic weight re-balancing is out of scope (latent bug in the reference, App. C.7)')
         if batchNum is None and batchLen is None and shuffleData:
             warnings.warn('shuffling data is possible for batch-optimization, setting \'shuffleData\' to False!')
             shuffleData = False
         self.smpScheme = smpScheme
+        if frac is None:
+            frac = 0.50 if addTrainPts else 0.25
+        if not addTrainPts and np.abs(suppFactor - 1.0) > 1.e-15:
+            warnings.warn('\'suppFactor\' is set to 1.0 since the number of training points does not change!')
+            suppFactor = 1.0
         argDict = dict(locals())
         self.fixData.setFEdata()
         fixData, tf = self.fixData, self.tfData
@@ -371,7 +464,13 @@ class VarNet:
         tData.updateDictFields('trainW', trainW)
         self.trainRes.lossComp.append(lossVal)
         tData0 = tData
+        fixData0 = None
+        if smpScheme == 'optimal' and addTrainPts:                      # frozen uniform tables for a comparable loss (VarNet.py:1330-1334)
+            fixData0 = FIXData(self, fixData.integPnum)
+            fixData0.setFEdata()
+            fixData0.removeInputData()
         min_loss, epoch_time = float('inf'), 0.0
+        tp_epoch, tp_updates = 1, 0
         resVal = err = lossComp = lossVec = None
         best = os.path.join(folderpath, 'best_model')
         for epoch in range(1, epochNum + 1):
@@ -393,28 +492,32 @@ class VarNet:
                 except Exception as ex:                                 # monitoring only
                     resVal, err = None, None
                     self.trainRes.writeCase('residual monitoring unavailable: %s' % ex)
-                lossComp, _, lossVec = self.splitLoss(tData0, None)
+                lossComp, _, lossVec = self.splitLoss(tData0, fixData0)
             self.trainRes.iterOutput(epoch, current_loss, min_loss, epoch_time, resVal, err, lossComp, lossVec)
             if current_loss < tol:
                 self.trainRes.writeCase('Training completed!')
                 if verbose:
                     print('Training completed!')
                 break
-            if smpScheme == 'random' and (multiTrainUpd or not self.trainRes.inpIter) and epoch >= trainUpdelay:
+            if smpScheme != 'uniform' and (multiTrainUpd or tp_updates == 0) and (epoch - tp_epoch) >= (trainUpdelay - 1):
                 recent = np.array(self.trainRes.loss[-5:])
                 drop = recent[:-1] - recent[1:]
-                if len(recent) == 5 and np.sum(drop[drop > 0]) / recent[-1] < tolUpd:
+                if np.sum(drop[drop > 0]) / recent[-1] < tolUpd:          # plateau: re-sample (VarNet.py:1385-1421)
                     min_loss = float('inf')
+                    tp_epoch, tp_updates = epoch, tp_updates + 1
                     self.trainRes.inpIter.append(epoch)
-                    Input, _, biInput, _ = self.trainingPoints(smpScheme, frac if frac is not None else 0.5)
+                    Input, _, biInput, _ = self.trainingPoints(smpScheme, frac, addTrainPts, suppFactor)
+                    if addTrainPts:
+                        fixData = self.fixData
                     tData = ManageTrainData(Input, biInput, batchNum, batchLen, saveMORdata, fixData.MORbatchNum)
+                    self.trainRes.writeCase('Training points updated at epoch %d.' % epoch)
                     if reinitrain:
                         tf.sess.run(GlobalInit())
+                        self.trainRes.writeCase('trainable variables reinitialized.')
                     if adjustWeight:
                         weight = [5 * w for w in weight[:-1]] + [weight[-1]]
                     trainW, tData, _ = self.trainWeight(weight, tData, MORdiscArg, normalizeW, useOriginalW)
                     tData.updateDictFields('trainW', trainW)
-                    tData0 = tData
         return self.trainRes
 
     # ------------------------------------------------------------------ evaluation
