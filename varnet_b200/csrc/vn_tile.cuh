@@ -256,15 +256,11 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
         for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
 #pragma unroll
     for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
-    // FP64 partial slab, pair-interleaved so that a warp's 128-bit accesses are contiguous:
-    // element r = t*TJ+u of thread `tid` lives at pgw[(r>>1)*2*NT + (r&1)]  (pgw already includes 2*tid).
-    // The previous partial sums are fetched from L2 BEFORE the K loop so their latency hides under it.
+    // FP64 partial slab, pair-interleaved so that a warp's accesses are contiguous: element r = t*TJ+u of
+    // thread `tid` lives at pgw[(r>>1)*2*NT + (r&1)] (pgw already includes 2*tid).  Every slot has exactly one
+    // writer, so accumulating with fire-and-forget reductions (RED.ADD.F64, no load, no scoreboard wait) is
+    // still bitwise deterministic; the first tile of a CTA overwrites instead.
     static_assert(C::TJ % 2 == 0, "pair layout");
-    double2 old[TIK * C::TJ / 2];
-    if (!first) {
-#pragma unroll
-        for (int r = 0; r < TIK * C::TJ / 2; ++r) old[r] = __ldcg(reinterpret_cast<const double2*>(pgw + r * (2 * C::NT)));
-    }
     constexpr int PSL = C::TP / C::KS;
     const int pbeg = kslice * PSL;
 #pragma unroll
@@ -295,14 +291,16 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     for (int t = 0; t < TIK; ++t)
 #pragma unroll
         for (int u = 0; u < C::TJ; u += 2) {
-            const int r = (t * C::TJ + u) >> 1;
-            double2 v = make_double2((double)acc[t][u], (double)acc[t][u + 1]);
-            if (!first) { v.x += old[r].x; v.y += old[r].y; }
-            __stcg(reinterpret_cast<double2*>(pgw + r * (2 * C::NT)), v);
+            double* q = pgw + ((t * C::TJ + u) >> 1) * (2 * C::NT);
+            if (first) __stcg(reinterpret_cast<double2*>(q), make_double2((double)acc[t][u], (double)acc[t][u + 1]));
+            else { atomicAdd(q, (double)acc[t][u]); atomicAdd(q + 1, (double)acc[t][u + 1]); }
         }
     if (ig == 0) {
 #pragma unroll
-        for (int u = 0; u < C::TJ; ++u) __stcg(pgb + u, first ? (double)bacc[u] : __ldcg(pgb + u) + (double)bacc[u]);
+        for (int u = 0; u < C::TJ; ++u) {
+            if (first) __stcg(pgb + u, (double)bacc[u]);
+            else atomicAdd(pgb + u, (double)bacc[u]);
+        }
     }
 }
 
