@@ -277,7 +277,7 @@ struct vn_engine {
     DevBuf bcols, blabel, cj;
     long long bstride = 0; unsigned int nbi = 0, bDof = 0; float biDimVal = 0.f;
     // adjoint partial slabs
-    DevBuf partVar, partBic, stashVar, stashBic, lossPart; int gridVar = 0, gridBic = 0;
+    DevBuf partVar, partBic, part32Var, part32Bic, stashVar, stashBic, lossPart; int gridVar = 0, gridBic = 0;
     // scratch
     DevBuf stage, evalCols, evalOut;
     // geometry
@@ -410,7 +410,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     if (e->ownStream) cudaStreamDestroy(e->ownStream);
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->cols, &e->integW,
                       &e->detJ, &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
-                      &e->partBic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
+                      &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -565,6 +565,7 @@ static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, con
     const long long tilesAdj = e->pstride / e->gVarAdj.TP;
     e->gridVar = (int)std::min<long long>(tilesAdj, e->numSMs);
     CK(e->partVar.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(double)));
+    CK(e->part32Var.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(float)));
     CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->gridVar * e->gVarAdj.stashFloats * sizeof(float))));
     CK(e->lossPart.ensure((size_t)e->gridVar * (e->gVarAdj.NT / 32) * sizeof(double)));
     e->fused = (e->gVarAdj.TP % integNum) == 0;
@@ -599,6 +600,7 @@ static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64
     const long long tiles = e->bstride / e->gBicAdj.TP;
     e->gridBic = (int)std::min<long long>(tiles, e->numSMs);
     CK(e->partBic.ensure((size_t)e->gridBic * e->gBicAdj.pl.psz * sizeof(double)));
+    CK(e->part32Bic.ensure((size_t)e->gridBic * e->gBicAdj.pl.psz * sizeof(float)));
     CK(e->stashBic.ensure(std::max<size_t>(16, (size_t)e->gridBic * e->gBicAdj.stashFloats * sizeof(float))));
     return VN_OK;
 }
@@ -663,7 +665,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         // single pass: forward, in-tile residual reduction, adjoint (MODE_VAR_FUSED)
         const TileGeom& g = e->gVarAdj;
         a.ntiles = (int)(e->pstride / g.TP);
-        a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+        a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
         ProfScope ps(e, PK_VAR_ADJ);
@@ -695,7 +697,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
             // 3. adjoint over quadrature points (forward recomputed per tile, seeds from R_i)
             const TileGeom& g = e->gVarAdj;
             a.ntiles = (int)(e->pstride / g.TP);
-            a.part = e->partVar.as<double>(); a.psz = g.pl.psz;
+            a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
             a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
             ProfScope ps(e, PK_VAR_ADJ);
             CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_ADJ, a, e->gridVar, g.smemBytes, st));
@@ -708,7 +710,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         const int mode = needGrad ? MODE_BIC_ADJ : MODE_BIC_FWD;
         const TileGeom& g = needGrad ? e->gBicAdj : e->gBicFwd;
         a.ntiles = (int)(e->bstride / g.TP);
-        a.part = e->partBic.as<double>(); a.psz = g.pl.psz;
+        a.part = e->partBic.as<double>(); a.part32 = e->part32Bic.as<float>(); a.psz = g.pl.psz;
         a.stash = e->stashBic.as<float>(); a.stashFloats = g.stashFloats;
         const int grid = needGrad ? e->gridBic : std::min(a.ntiles, 2 * e->numSMs);
         ProfScope ps(e, PK_BIC);

@@ -76,7 +76,8 @@ struct TileArgs {
     // evaluation
     float* uout;                    // [P]
     // adjoint
-    double* part;                   // [gridDim.x][psz] FP64 partial gradients
+    double* part;                   // [gridDim.x][psz] FP64 partial gradients (folded from part32 every VN_FOLD tiles)
+    float* part32;                  // [gridDim.x][psz] FP32 window accumulators (same slot layout)
     int psz;
     float* stash;                   // [gridDim.x][stashFloats] activations of layers 0..L-3
     long long stashFloats;
@@ -171,6 +172,8 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+#define VN_FOLD 32   // tiles accumulated in the FP32 window slab before it is folded into the FP64 slab
+
 // out[s][j][p] = sum_i in[s][i][p] * W[i][j]; thread tile: 4 points x S streams x TN neurons
 template <class C, int KD>
 __device__ __forceinline__ void fwd_gemm(const float* __restrict__ Bin, const float* __restrict__ Wm,
@@ -246,8 +249,8 @@ __device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const flo
 // produce gb[j] = sum_p D[0][j][p].  `first` overwrites instead of accumulating.
 template <class C, int KD, int TIK>
 __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const float* __restrict__ Dm,
-                                        int ig, int jg, int kslice, double* __restrict__ pgw,
-                                        double* __restrict__ pgb, bool first) {
+                                        int ig, int jg, int kslice, float* __restrict__ pgw,
+                                        float* __restrict__ pgb, bool first) {
     float acc[TIK][C::TJ];
     float bacc[C::TJ];
 #pragma unroll
@@ -256,10 +259,10 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
         for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
 #pragma unroll
     for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
-    // FP64 partial slab, pair-interleaved so that a warp's accesses are contiguous: element r = t*TJ+u of
+    // FP32 window slab, pair-interleaved so that a warp's accesses are contiguous: element r = t*TJ+u of
     // thread `tid` lives at pgw[(r>>1)*2*NT + (r&1)] (pgw already includes 2*tid).  Every slot has exactly one
-    // writer, so accumulating with fire-and-forget reductions (RED.ADD.F64, no load, no scoreboard wait) is
-    // still bitwise deterministic; the first tile of a CTA overwrites instead.
+    // writer, so accumulating with fire-and-forget reductions (RED.ADD.F32: no load, no conversion, no
+    // scoreboard wait) stays bitwise deterministic; the first tile of a window overwrites instead.
     static_assert(C::TJ % 2 == 0, "pair layout");
     constexpr int PSL = C::TP / C::KS;
     const int pbeg = kslice * PSL;
@@ -291,17 +294,35 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     for (int t = 0; t < TIK; ++t)
 #pragma unroll
         for (int u = 0; u < C::TJ; u += 2) {
-            double* q = pgw + ((t * C::TJ + u) >> 1) * (2 * C::NT);
-            if (first) __stcg(reinterpret_cast<double2*>(q), make_double2((double)acc[t][u], (double)acc[t][u + 1]));
-            else { atomicAdd(q, (double)acc[t][u]); atomicAdd(q + 1, (double)acc[t][u + 1]); }
+            float* q = pgw + ((t * C::TJ + u) >> 1) * (2 * C::NT);
+            if (first) __stcg(reinterpret_cast<float2*>(q), make_float2(acc[t][u], acc[t][u + 1]));
+            else { atomicAdd(q, acc[t][u]); atomicAdd(q + 1, acc[t][u + 1]); }
         }
     if (ig == 0) {
 #pragma unroll
         for (int u = 0; u < C::TJ; ++u) {
-            if (first) __stcg(pgb + u, (double)bacc[u]);
-            else atomicAdd(pgb + u, (double)bacc[u]);
+            if (first) __stcg(pgb + u, bacc[u]);
+            else atomicAdd(pgb + u, bacc[u]);
         }
     }
+}
+
+// Fold this thread's slots of the FP32 window slab into the FP64 slab (first fold overwrites).
+template <class C>
+__device__ __forceinline__ void fold_slab(const PartLayout& pl, int L, const float* __restrict__ p32,
+                                          double* __restrict__ p64, int tid, int ig, int jg, int kslice, bool firstFold) {
+    auto put = [&](int idx) {
+        const double v = (double)__ldcg(p32 + idx);
+        if (firstFold) __stcg(p64 + idx, v); else atomicAdd(p64 + idx, v);
+    };
+    for (int l = 0; l < L; ++l) {
+        const int n = l == 0 ? C::TJ : C::TI * C::TJ;
+        for (int r = 0; r < n; ++r) put(pl.off_gw[l] + (r >> 1) * (2 * C::NT) + 2 * tid + (r & 1));
+        if (ig == 0)
+            for (int u = 0; u < C::TJ; ++u) put(pl.off_gb[l] + kslice * C::WP + jg * C::TJ + u);
+    }
+    put(pl.off_wout + tid);
+    if (tid == 0) put(pl.off_bout);
 }
 
 // ---- pieces shared by the two kernels -------------------------------------------------------------
@@ -527,10 +548,13 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
     stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, true));
 
     const PartLayout pl = make_part_layout<C>(L);
-    double* part = A.part + (size_t)blockIdx.x * pl.psz;
+    double* part64 = A.part + (size_t)blockIdx.x * pl.psz;
+    float* part = A.part32 + (size_t)blockIdx.x * pl.psz;   // FP32 window accumulators
     float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
     double lossAcc = 0.0;                                    // lane 0 of each warp (FUSED)
-    bool first = true;
+    bool first = true;                                       // first tile of the current FP32 window
+    bool firstFold = true;
+    int win = 0;
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const unsigned int base = (unsigned int)tile * TP;
@@ -673,13 +697,13 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
                     acc = fmaf(b4.x, u4.x, acc); acc = fmaf(b4.y, u4.y, acc);
                     acc = fmaf(b4.z, u4.z, acc); acc = fmaf(b4.w, u4.w, acc);
                 }
-            double* pw = part + pl.off_wout + tid;
-            __stcg(pw, first ? (double)acc : __ldcg(pw) + (double)acc);
+            float* pw = part + pl.off_wout + tid;
+            if (first) __stcg(pw, acc); else atomicAdd(pw, acc);
             if (tid == 0) {
                 float sb = 0.f;
                 for (int p = 0; p < TP; ++p) sb += us[p];
-                double* pb = part + pl.off_bout;
-                __stcg(pb, first ? (double)sb : __ldcg(pb) + (double)sb);
+                float* pb = part + pl.off_bout;
+                if (first) __stcg(pb, sb); else atomicAdd(pb, sb);
             }
         }
         __syncthreads();
@@ -743,6 +767,10 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
                            part + pl.off_gb[0] + kslice * WP + jg * C::TJ, first);
         __syncthreads();
         first = false;
+        if (++win == VN_FOLD || tile + (int)gridDim.x >= A.ntiles) {
+            fold_slab<C>(pl, L, part, part64, tid, ig, jg, kslice, firstFold);
+            firstFold = false; first = true; win = 0;
+        }
     }
     if (FUSED && lane == 0) A.lossPart[blockIdx.x * C::NW + warp] = lossAcc;
 }
