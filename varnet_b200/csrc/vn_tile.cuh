@@ -174,53 +174,76 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 #define VN_FOLD 32   // tiles accumulated in the FP32 window slab before it is folded into the FP64 slab
 
+// ---- packed FP32 FMA (Blackwell fma.rn.f32x2 -> SASS FFMA2): two IEEE-rn FMAs per issued instruction.
+// The GEMM cores keep their accumulators as point pairs so that the activation fragment (a float4 of four
+// consecutive points) is used directly as two packed operands; only the weight is duplicated into a pair.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ ulonglong2 lds2x64(const float* p) { return *reinterpret_cast<const ulonglong2*>(p); }
+
 // out[s][j][p] = sum_i in[s][i][p] * W[i][j]; thread tile: 4 points x S streams x TN neurons
 template <class C, int KD>
 __device__ __forceinline__ void fwd_gemm(const float* __restrict__ Bin, const float* __restrict__ Wm,
                                          int Kin, int p0, int j0, float (&acc)[C::S][4][C::TN]) {
+    u64 acc2[C::S][2][C::TN];
 #pragma unroll
     for (int s = 0; s < C::S; ++s)
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int t = 0; t < C::TN; ++t) acc[s][p][t] = 0.f;
-#pragma unroll 4
+            for (int t = 0; t < C::TN; ++t) acc2[s][h][t] = 0ull;
+#pragma unroll 8
     for (int i = 0; i < Kin; ++i) {
-        float w[C::TN];
+        u64 w2[C::TN];
         if (C::TN % 4 == 0) {
 #pragma unroll
             for (int t4 = 0; t4 < C::TN / 4; ++t4) {
                 float4 v = lds4(Wm + i * C::WS + j0 + 4 * t4);
-                w[4 * t4 + 0] = v.x; w[4 * t4 + 1] = v.y; w[4 * t4 + 2] = v.z; w[4 * t4 + 3] = v.w;
+                w2[4 * t4 + 0] = pack2(v.x, v.x); w2[4 * t4 + 1] = pack2(v.y, v.y);
+                w2[4 * t4 + 2] = pack2(v.z, v.z); w2[4 * t4 + 3] = pack2(v.w, v.w);
             }
         } else {
 #pragma unroll
-            for (int t = 0; t < C::TN; ++t) w[t] = Wm[i * C::WS + j0 + t];
+            for (int t = 0; t < C::TN; ++t) { const float v = Wm[i * C::WS + j0 + t]; w2[t] = pack2(v, v); }
         }
 #pragma unroll
         for (int s = 0; s < C::S; ++s) {
-            float4 a = lds4(Bin + (s * KD + i) * C::TPS + p0);
+            const ulonglong2 a = lds2x64(Bin + (s * KD + i) * C::TPS + p0);
 #pragma unroll
             for (int t = 0; t < C::TN; ++t) {
-                acc[s][0][t] = fmaf(a.x, w[t], acc[s][0][t]);
-                acc[s][1][t] = fmaf(a.y, w[t], acc[s][1][t]);
-                acc[s][2][t] = fmaf(a.z, w[t], acc[s][2][t]);
-                acc[s][3][t] = fmaf(a.w, w[t], acc[s][3][t]);
+                ffma2(acc2[s][0][t], a.x, w2[t]);
+                ffma2(acc2[s][1][t], a.y, w2[t]);
             }
         }
     }
+#pragma unroll
+    for (int s = 0; s < C::S; ++s)
+#pragma unroll
+        for (int t = 0; t < C::TN; ++t) {
+            unpack2(acc2[s][0][t], acc[s][0][t], acc[s][1][t]);
+            unpack2(acc2[s][1][t], acc[s][2][t], acc[s][3][t]);
+        }
 }
 
 // out[s][i_t][p] = sum_j D[s][j][p] * W[i_t][j];  thread owns interleaved rows i_t = ng + NNG*t
 template <class C>
 __device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const float* __restrict__ Wm,
                                          int Kout, int p0, int ng, float (&acc)[C::S][4][C::TN]) {
+    u64 acc2[C::S][2][C::TN];
 #pragma unroll
     for (int s = 0; s < C::S; ++s)
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int t = 0; t < C::TN; ++t) acc[s][p][t] = 0.f;
+            for (int t = 0; t < C::TN; ++t) acc2[s][h][t] = 0ull;
 #pragma unroll 2
     for (int j0 = 0; j0 < Kout; j0 += 4) {
         float4 w[C::TN];
@@ -228,20 +251,27 @@ __device__ __forceinline__ void adj_gemm(const float* __restrict__ Dm, const flo
         for (int t = 0; t < C::TN; ++t) w[t] = lds4(Wm + (ng + C::NNG * t) * C::WS + j0);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
+            u64 w2[C::TN];
+#pragma unroll
+            for (int t = 0; t < C::TN; ++t) { const float wv = f4get(w[t], jj); w2[t] = pack2(wv, wv); }
 #pragma unroll
             for (int s = 0; s < C::S; ++s) {
-                float4 d = lds4(Dm + (s * C::WP + j0 + jj) * C::TPS + p0);
+                const ulonglong2 d = lds2x64(Dm + (s * C::WP + j0 + jj) * C::TPS + p0);
 #pragma unroll
                 for (int t = 0; t < C::TN; ++t) {
-                    const float wv = f4get(w[t], jj);
-                    acc[s][0][t] = fmaf(d.x, wv, acc[s][0][t]);
-                    acc[s][1][t] = fmaf(d.y, wv, acc[s][1][t]);
-                    acc[s][2][t] = fmaf(d.z, wv, acc[s][2][t]);
-                    acc[s][3][t] = fmaf(d.w, wv, acc[s][3][t]);
+                    ffma2(acc2[s][0][t], d.x, w2[t]);
+                    ffma2(acc2[s][1][t], d.y, w2[t]);
                 }
             }
         }
     }
+#pragma unroll
+    for (int s = 0; s < C::S; ++s)
+#pragma unroll
+        for (int t = 0; t < C::TN; ++t) {
+            unpack2(acc2[s][0][t], acc[s][0][t], acc[s][1][t]);
+            unpack2(acc2[s][1][t], acc[s][2][t], acc[s][3][t]);
+        }
 }
 
 // gW[i][j] += sum_{s,p} Bprev[s][i][p] * D[s][j][p];  i = ig + 8t, j = jg + 16u; the CTA's KS point
@@ -251,12 +281,13 @@ template <class C, int KD, int TIK>
 __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const float* __restrict__ Dm,
                                         int ig, int jg, int kslice, float* __restrict__ pgw,
                                         float* __restrict__ pgb, bool first) {
-    float acc[TIK][C::TJ];
+    // packed accumulators: (sum over even points, sum over odd points) per (i, j); added at the end
+    u64 acc2[TIK][C::TJ];
     float bacc[C::TJ];
 #pragma unroll
     for (int t = 0; t < TIK; ++t)
 #pragma unroll
-        for (int u = 0; u < C::TJ; ++u) acc[t][u] = 0.f;
+        for (int u = 0; u < C::TJ; ++u) acc2[t][u] = 0ull;
 #pragma unroll
     for (int u = 0; u < C::TJ; ++u) bacc[u] = 0.f;
     // FP32 window slab, pair-interleaved so that a warp's accesses are contiguous: element r = t*TJ+u of
@@ -270,26 +301,35 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     for (int s = 0; s < C::S; ++s) {
 #pragma unroll 2
         for (int p = pbeg; p < pbeg + PSL; p += 4) {
-            float4 a[TIK], d[C::TJ];
+            ulonglong2 a[TIK], d[C::TJ];
 #pragma unroll
-            for (int t = 0; t < TIK; ++t) a[t] = lds4(Bprev + (s * KD + ig + 8 * t) * C::TPS + p);
+            for (int t = 0; t < TIK; ++t) a[t] = lds2x64(Bprev + (s * KD + ig + 8 * t) * C::TPS + p);
 #pragma unroll
-            for (int u = 0; u < C::TJ; ++u) d[u] = lds4(Dm + (s * C::WP + jg + 16 * u) * C::TPS + p);
+            for (int u = 0; u < C::TJ; ++u) d[u] = lds2x64(Dm + (s * C::WP + jg + 16 * u) * C::TPS + p);
+            // two passes so that consecutive FFMA2s never hit the same accumulator back to back
 #pragma unroll
             for (int t = 0; t < TIK; ++t)
 #pragma unroll
-                for (int u = 0; u < C::TJ; ++u) {
-                    float v = acc[t][u];
-                    v = fmaf(a[t].x, d[u].x, v); v = fmaf(a[t].y, d[u].y, v);
-                    v = fmaf(a[t].z, d[u].z, v); v = fmaf(a[t].w, d[u].w, v);
-                    acc[t][u] = v;
-                }
+                for (int u = 0; u < C::TJ; ++u) ffma2(acc2[t][u], a[t].x, d[u].x);
+#pragma unroll
+            for (int t = 0; t < TIK; ++t)
+#pragma unroll
+                for (int u = 0; u < C::TJ; ++u) ffma2(acc2[t][u], a[t].y, d[u].y);
             if (s == 0 && ig == 0) {
 #pragma unroll
-                for (int u = 0; u < C::TJ; ++u) bacc[u] += (d[u].x + d[u].y) + (d[u].z + d[u].w);
+                for (int u = 0; u < C::TJ; ++u) {
+                    float d0, d1, d2, d3;
+                    unpack2(d[u].x, d0, d1); unpack2(d[u].y, d2, d3);
+                    bacc[u] += (d0 + d1) + (d2 + d3);
+                }
             }
         }
     }
+    float acc[TIK][C::TJ];
+#pragma unroll
+    for (int t = 0; t < TIK; ++t)
+#pragma unroll
+        for (int u = 0; u < C::TJ; ++u) { float lo, hi; unpack2(acc2[t][u], lo, hi); acc[t][u] = lo + hi; }
 #pragma unroll
     for (int t = 0; t < TIK; ++t)
 #pragma unroll
