@@ -54,6 +54,18 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel on this workload, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json; regenerate with scripts/make_traffic_json.py)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("workload") == workload:
+            return t.get("dram_bytes_per_launch")
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -277,7 +289,7 @@ def main():
         pk = peaks()
         bytes_pt = 4 * (meta["inpDim"] + meta["dim"] + 1)
         roofline = dict(bound="fp32", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf if peak_tf else None,
-                        traffic=None, kernel="vn_adj_kernel<MODE_VAR_FUSED>", kernel_ms=kernel_ms,
+                        traffic=measured_traffic(args.workload) if world == 1 else None, kernel="vn_adj_kernel<MODE_VAR_FUSED>", kernel_ms=kernel_ms,
                         kernel_share_of_step=kernel_ms / ms_step if ms_step else None,
                         flop_per_point=flop_pt, points_per_launch=P_local,
                         peak_source="FFMA microbenchmark (vn_fp32_peak_tflops) measured in this run",
