@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-operator-configs", action="store_true", help="skip the steps/sec legs of configs 1-3")
     return ap.parse_args()
 
 
@@ -164,6 +165,70 @@ def run_cpu(args, nx, ny, ntime, lw, act, steps, warmup, budget_s=None):
                 feed_cast_ms=cast * 1e3,
                 sample="first %d of %d test functions (%d quad points) of the same workload, torch-CPU FP32 "
                        "double back-prop + TF-Adam, %d threads" % (sample_tf, nx * ny * ntime, P, cores))
+
+
+def operator_config_steps(budget_s=4.0):
+    """train steps/sec of BASELINE.json configs 1-3 (the reference's operator scripts) on one GPU: each is
+    built with the reference API of the host mirror and driven through ManageTrainData.optimIter ->
+    TFNN.sess.run([optMinimize, loss]) exactly like VarNet.train's hot loop (VarNet.py:1350-1352)."""
+    import varnet_b200
+    from varnet_b200 import ManageTrainData
+    pi = np.pi
+    out = {}
+
+    def cfg1():
+        pde = varnet_b200.ADPDE(varnet_b200.Domain1D(), diff=0.1 / pi, vel=1.0, timeDependent=True, tInterval=[0, 2.0],
+                                IC=lambda x: -np.sin(pi * x))
+        return varnet_b200.VarNet(pde, layerWidth=[20], discNum=20, bDiscNum=None, tDiscNum=300, processors='GPU:0', seed=0), None, False
+
+    def cfg2():
+        v = np.array([[0.0, -0.5], [0.0, -0.2], [0.0, 0.2], [0.0, 0.5], [2.0, 0.5], [2.0, -0.5]])
+        pde = varnet_b200.ADPDE(varnet_b200.PolygonDomain2D(v), diff=1.e-3, vel=[1., 0.], tInterval=[0, 1.5],
+                                BCs=[[], [0.0, 1.0, 1.0], [], [], [], []], IC=0.0)
+        return varnet_b200.VarNet(pde, layerWidth=[10, 20], discNum=[80, 40], bDiscNum=40, tDiscNum=75, processors='GPU:0', seed=0), None, False
+
+    def diffFun(x, t=0, D=0.1 / pi):
+        return D * np.ones([np.shape(x)[0], 1])
+
+    def cfg3():
+        mor = varnet_b200.MOR(diffFun, ['D'], [[0.003, 0.033]])
+        pde = varnet_b200.ADPDE(varnet_b200.Domain1D(), diff=diffFun, vel=1.0, timeDependent=True, tInterval=[0, 2.0],
+                                IC=lambda x: -np.sin(pi * x), MORvar=mor)
+        disc = lambda n=6: np.array([0.003 * (11 ** (k / (n - 1))) for k in range(n)])[np.newaxis].T
+        return varnet_b200.VarNet(pde, layerWidth=[10, 20, 30], discNum=150, bDiscNum=75, tDiscNum=800, MORdiscScheme=disc,
+                                  processors='GPU:0', seed=0), 20, True
+
+    for name, build in (("Operator_1Dt", cfg1), ("Operator_2Dt", cfg2), ("Operator_1DtMOR", cfg3)):
+        t_build = time.perf_counter()
+        vn, batchNum, saveMOR = build()
+        fd = vn.fixData
+        fd.setFEdata()
+        Input, _, biInput, _ = vn.trainingPoints()
+        disc = None if vn.PDE.MORvar is None else vn.PDE.MORvar.discretizeArg(vn.MORdiscScheme)
+        tData = ManageTrainData(Input, biInput, batchNum, None, saveMOR, fd.MORbatchNum)
+        tData = vn.trainData(0, disc, tData)
+        tData.updateDictFields('trainW', np.array([10., 10., 1.]))
+        t_build = time.perf_counter() - t_build
+        tf = vn.tfData
+
+        def epoch():
+            nonlocal tData
+            n = 0
+            for b in range(fd.MORbatchNum):
+                tData = vn.trainData(b, disc, tData)
+                tData.optimIter(tf)
+                n += tData.batchNum
+            return n
+        epoch()                                        # warm-up (also caches the MOR batches on the host)
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s:
+            steps += epoch()
+        dt = time.perf_counter() - t0
+        P = int(np.prod(tData.optimFeedicts[0][tf.compTowers[0].intShape]))
+        out[name] = dict(steps_per_sec=steps / dt, quad_points_per_step=P, quad_pts_per_sec=steps * P / dt,
+                         steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build)
+        tf.sess.close()
+    return out
 
 
 def main():
@@ -311,6 +376,11 @@ def main():
             r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                                         ms_per_step=r["ms_per_step"], feed_cast_ms_per_step=r["feed_cast_ms"])
+        if world == 1 and not args.no_operator_configs and not args.no_cpu_baseline:
+            try:
+                line["operator_configs"] = operator_config_steps()
+            except Exception as ex:                      # never lose the headline line to an auxiliary leg
+                line["operator_configs"] = dict(error=repr(ex))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

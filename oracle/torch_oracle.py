@@ -141,4 +141,4 @@ class CpuStepper:
         self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
         lr_t = self.lr * (1 - b2 ** self.t) ** 0.5 / (1 - b1 ** self.t)
         self.theta.addcdiv_(self.m, self.v.sqrt() + eps, value=-lr_t)
-        return float(loss)
+        return float(loss.detach())
