@@ -36,6 +36,7 @@ extern "C" {
 #define VN_OPT_RMSPROP 1     /* tf.train.RMSPropOptimizer, TFModel.py:186 */
 
 #define VN_PROF_SLOTS 8
+#define VN_MAX_TABLES 4096   /* resident point tables per engine (vn_select_table) */
 
 #define VN_OK 0
 #define VN_E_INVALID -1      /* bad argument (mirrors the reference's ValueError sites) */
@@ -93,6 +94,25 @@ int vn_upload_bic_f32(vn_engine* e, const float* biInput, const float* biLabel, 
                       int64_t bDof, float biDimVal);
 int vn_upload_bic_f64(vn_engine* e, const double* biInput, const double* biLabel, int64_t nbi,
                       int64_t bDof, double biDimVal);
+/* ---- device-resident mini-batches.  The reference re-gathers `integInd[batchInd[n0:n1]]`
+ *      on the host for every mini-batch / shuffle / MOR batch and re-feeds the copies
+ *      (VarNetUtility.py:833-844,918-950,988-1013; VarNet.py:843-851).  Here several tables can stay
+ *      resident (slots), a mini-batch is a list of test-function indices into the current table
+ *      (on-device permutation; needs integNum % 4 == 0), and trailing MLP inputs that are constant over
+ *      a batch (MOR parameters) are passed as scalars instead of re-tiled columns.
+ *      vn_upload_table_*: like vn_upload_points_* but Input has only the first `nx` MLP input columns. */
+int vn_select_table(vn_engine* e, int32_t slot);
+int vn_table_loaded(const vn_engine* e, int32_t slot);                 /* 1 if the slot holds a table */
+int vn_free_table(vn_engine* e, int32_t slot);
+int vn_upload_table_f32(vn_engine* e, const float* Input, int32_t nx, const float* gcoef, const float* source,
+                        const float* N, const float* dNt, int64_t nb, int32_t integNum,
+                        const float* integW, const float* detJ, int32_t detJ_is_vector);
+int vn_upload_table_f64(vn_engine* e, const double* Input, int32_t nx, const double* gcoef, const double* source,
+                        const double* N, const double* dNt, int64_t nb, int32_t integNum,
+                        const double* integW, const double* detJ, int32_t detJ_is_vector);
+int vn_set_batch(vn_engine* e, const int32_t* tf_index, int64_t nb);   /* NULL: whole table, in order */
+int vn_set_extra_inputs(vn_engine* e, const float* vals, int32_t n);
+
 /* loss weights w[3] = [BC, IC, variational] (TFModel.py:666); device-resident so a
  * captured step graph sees updates. */
 int vn_set_weights(vn_engine* e, const float w[3]);

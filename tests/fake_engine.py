@@ -47,11 +47,58 @@ class FakeEngine:
     def set_optimizer_state(self, m, v, step):
         self.m, self.v, self.step = np.array(m, dtype=np.float64), np.array(v, dtype=np.float64), int(step)
 
+    supports_table_views = True
+
     def upload_points(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None):
-        self.feed.update(Input=np.array(Input), gcoef=np.array(gcoef), source=source, N=N, dNt=dNt,
-                         intShape=list(intShape), integW=integW, detJ=detJ, detJvec=detJvec)
-        self.nb = int(intShape[0])
+        self.upload_table(Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec, nx=self.inpDim)
+        self.set_extra_inputs(None)
+
+    # device-resident tables / mini-batches: same call protocol as the real engine, materialised for the oracle
+    def select_table(self, slot):
+        self.slot = slot
+        self.tables = getattr(self, "tables", {})
+        if slot in self.tables:
+            self.batch = None
+            self._refresh()
+
+    def upload_table(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None, nx=None):
+        self.tables = getattr(self, "tables", {})
+        self.slot = getattr(self, "slot", 0)
+        arr = lambda a: None if a is None or np.asarray(a).dtype == object else np.array(a, dtype=np.float64)
+        self.tables[self.slot] = dict(Input=arr(Input), gcoef=arr(gcoef), source=arr(source), N=arr(N), dNt=arr(dNt),
+                                      nbTab=int(intShape[0]), integNum=int(intShape[1]), integW=integW, detJ=detJ,
+                                      detJvec=detJvec)
+        self.batch = None
         self.calls["upload_points"] += 1
+        self._refresh()
+
+    def set_batch(self, tf_index):
+        self.batch = None if tf_index is None else np.array(tf_index, dtype=np.int64).ravel()
+        self.calls["set_batch"] = self.calls.get("set_batch", 0) + 1
+        self._refresh()
+
+    def set_extra_inputs(self, vals):
+        self.extra = None if vals is None or np.size(vals) == 0 else np.asarray(vals, dtype=np.float32).astype(np.float64).reshape(1, -1)
+        if getattr(self, "tables", None) and getattr(self, "slot", 0) in self.tables:
+            self._refresh()
+
+    def _refresh(self):
+        t = self.tables[self.slot]
+        q = t["integNum"]
+        tf = np.arange(t["nbTab"]) if getattr(self, "batch", None) is None else self.batch
+        rows = (tf.reshape(-1, 1) * q + np.arange(q)).ravel()
+        take = lambda a: None if a is None else a.reshape(t["nbTab"] * q, -1)[rows]
+        X = take(t["Input"])
+        extra = getattr(self, "extra", None)
+        if extra is not None:
+            X = np.hstack([X, np.tile(extra, [len(X), 1])])
+        detJ = t["detJ"]
+        if t["detJvec"]:
+            detJ = np.asarray(detJ, dtype=np.float64).reshape(-1, 1)[tf]
+        self.feed.update(Input=X, gcoef=take(t["gcoef"]), source=take(t["source"]), N=take(t["N"]),
+                         dNt=take(t["dNt"]) if t["dNt"] is not None else [[None]], intShape=[len(tf), q],
+                         integW=t["integW"], detJ=detJ, detJvec=t["detJvec"])
+        self.nb = len(tf)
 
     def upload_bic(self, biInput, biLabel, bDof, biDimVal, dtype=None):
         self.feed.update(biInput=np.array(biInput), biLabel=np.array(biLabel), bDof=bDof, biDimVal=biDimVal)

@@ -124,3 +124,46 @@ def test_strong_residual_matches_oracle(case):
     # the residual mixes terms of different size: bound relative to the sum of their magnitudes
     assert np.abs(res - ro).max() <= TOL * np.abs(ro).max() + 1e-6
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dvec", [False, True])
+def test_indexed_batch_and_extra_inputs_equal_materialised_upload(dvec):
+    """Device-resident mini-batch (table + test-function index list + constant MOR input) must be bitwise
+    identical to uploading the gathered rows the way the reference feeds them (VarNetUtility.py:833-844)."""
+    from varnet_b200._capi import Engine
+    rng = np.random.RandomState(21)
+    dim, inpDim, lw, nbTab, q = 1, 3, [10, 20, 30], 50, 16
+    full = synth_feed(rng, dim, 2, nbTab, q, 40, 30, True, False, False, dvec)
+    mor = 0.0123
+    theta = go.glorot_init(inpDim, lw, seed=3)
+    perm = rng.permutation(nbTab)[:23]
+    rows = (perm.reshape(-1, 1) * q + np.arange(q)).ravel()
+    bX = np.hstack([full["biInput"], np.full((40, 1), mor)])
+
+    a = Engine(dim, inpDim, lw, "sigmoid", True)
+    a.set_params(theta)
+    a.select_table(3)
+    a.upload_table(full["Input"], full["gcoef"], None, None, full["dNt"], [nbTab, q], None, full["detJ"], dvec, nx=2)
+    a.set_extra_inputs([mor])
+    a.set_batch(perm)
+    a.upload_bic(bX, full["biLabel"], 30, 2.0)
+    a.set_weights(full["w"])
+
+    b = Engine(dim, inpDim, lw, "sigmoid", True)
+    b.set_params(theta)
+    Xm = np.hstack([full["Input"][rows], np.full((len(rows), 1), mor)])
+    detJ = full["detJ"][perm] if dvec else full["detJ"]
+    b.upload_points(Xm, full["gcoef"][rows], None, None, full["dNt"][rows], [len(perm), q], None, detJ, dvec)
+    b.upload_bic(bX, full["biLabel"], 30, 2.0)
+    b.set_weights(full["w"])
+
+    ra, rb = a.loss_grad(), b.loss_grad()
+    assert ra["loss"] == rb["loss"] and np.array_equal(ra["grad"], rb["grad"])
+    la, lb = a.loss(lossVec=True), b.loss(lossVec=True)
+    assert np.array_equal(la["lossVec"], lb["lossVec"]) and la["varLoss"] == lb["varLoss"]
+    # the same table serves another batch without any re-upload; training steps replay a captured graph
+    a.set_batch(np.arange(nbTab))
+    l1 = a.train_step(1e-3); l2 = a.train_step(1e-3)
+    assert np.isfinite(l1) and np.isfinite(l2)
+    a.close(); b.close()

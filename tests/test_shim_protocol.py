@@ -135,3 +135,27 @@ def test_optimal_sampling_matches_reference_trajectory(shim, monkeypatch, addTra
     # the reference logs the loss every saveFreq epochs, the mirror every epoch
     assert np.allclose(la, lb[1::2][:len(la)], rtol=1e-9)
     assert np.allclose(tha, thb, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("name,kw", [("Operator_1Dt", dict(batchNum=3, shuffleData=True)),
+                                     ("Operator_1DtMOR", dict(batchNum=2, shuffleData=True, saveMORdata=True)),
+                                     ("Operator_1DtMOR", dict(batchNum=2, saveMORdata=False))])
+def test_device_resident_batches_equal_host_gathers(shim, monkeypatch, name, kw):
+    """Lazy TableView feeds (resident table + index list + constant MOR columns) must reproduce the training
+    trajectory of the reference-style host gathers exactly."""
+    import varnet_b200
+    results = []
+    for views in (True, False):
+        monkeypatch.setattr(FakeEngine, "supports_table_views", views)
+        np.random.seed(99)
+        scale = 0.15 if name == "Operator_1Dt" else 0.05
+        vn = configs.BUILDERS[name](varnet_b200, scale, seed=4)
+        assert vn.tfData.supports_table_views == views
+        with tempfile.TemporaryDirectory() as d:
+            res = vn.train(d, weight=[10., 10., 1.], epochNum=4, saveFreq=2, verbose=False, **kw)
+        eng = FakeEngine.instances[-1]
+        results.append((np.array(res.loss, dtype=float), vn.tfData.get_parameters(), eng.calls["upload_points"],
+                        eng.calls.get("set_batch", 0)))
+    (lv, tv, upv, sbv), (lm, tm, upm, sbm) = results
+    assert np.allclose(lv, lm, rtol=1e-12) and np.allclose(tv, tm, rtol=1e-7, atol=1e-9)
+    assert upv < upm and sbv > 0            # tables stay resident; batches are index lists

@@ -42,6 +42,13 @@ SIGNATURES = {
     "vn_upload_points_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32]),
     "vn_upload_bic_f32": (C.c_int, [_vp, _f32p, _f32p, _i64, _i64, C.c_float]),
     "vn_upload_bic_f64": (C.c_int, [_vp, _f64p, _f64p, _i64, _i64, C.c_double]),
+    "vn_select_table": (C.c_int, [_vp, _i32]),
+    "vn_table_loaded": (C.c_int, [_vp, _i32]),
+    "vn_free_table": (C.c_int, [_vp, _i32]),
+    "vn_upload_table_f32": (C.c_int, [_vp, _f32p, _i32, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _i32]),
+    "vn_upload_table_f64": (C.c_int, [_vp, _f64p, _i32, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32]),
+    "vn_set_batch": (C.c_int, [_vp, C.POINTER(_i32), _i64]),
+    "vn_set_extra_inputs": (C.c_int, [_vp, _f32p, _i32]),
     "vn_set_weights": (C.c_int, [_vp, _f32p]),
     "vn_loss": (C.c_int, [_vp, _f32p, _f32p]),
     "vn_loss_grad": (C.c_int, [_vp, _f32p]),
@@ -187,12 +194,45 @@ class Engine:
         self._check(self.lib.vn_set_optimizer_state(self._h, _ptr(m, C.c_float), _ptr(v, C.c_float), m.size, int(step)))
 
     # -- feeds
+    supports_table_views = True
+
     def upload_points(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None):
+        """One tower's feed as the reference passes it (all inpDim input columns, batch = whole table)."""
+        self.upload_table(Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec, dtype=dtype, nx=self.inpDim)
+        self.set_extra_inputs(None)
+
+    # device-resident tables / mini-batches (include/varnet_b200.h, "device-resident mini-batches")
+    def select_table(self, slot):
+        self._check(self.lib.vn_select_table(self._h, int(slot)))
+
+    def table_loaded(self, slot):
+        return bool(self.lib.vn_table_loaded(self._h, int(slot)))
+
+    def free_table(self, slot):
+        self._check(self.lib.vn_free_table(self._h, int(slot)))
+
+    def set_batch(self, tf_index):
+        if tf_index is None:
+            self._check(self.lib.vn_set_batch(self._h, None, 0))
+            return
+        idx = np.ascontiguousarray(tf_index, dtype=np.int32).ravel()
+        self._check(self.lib.vn_set_batch(self._h, idx.ctypes.data_as(C.POINTER(_i32)), idx.size))
+        self.nb = int(idx.size)
+
+    def set_extra_inputs(self, vals):
+        if vals is None or np.size(vals) == 0:
+            self._check(self.lib.vn_set_extra_inputs(self._h, None, 0))
+            return
+        v = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).astype(np.float32).ravel())
+        self._check(self.lib.vn_set_extra_inputs(self._h, _ptr(v, C.c_float), v.size))
+
+    def upload_table(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None, nx=None):
         nb, integNum = int(intShape[0]), int(intShape[1])
         P = nb * integNum
+        nx = self.inpDim if nx is None else int(nx)
         if dtype is None:
             dtype = np.float32 if np.asarray(Input).dtype == np.float32 else np.float64
-        X = _prep(Input, dtype, (P, self.inpDim))
+        X = _prep(Input, dtype, (P, nx))
         G = _prep(gcoef, dtype, (P, self.dim))
         S = _prep(source, dtype, (P,)) if self.cfg.isSource else None
         Nn = _prep(N, dtype, (P,)) if self.cfg.isSource else None
@@ -207,8 +247,8 @@ class Engine:
         if detJvec and D.size != nb:
             raise ValueError("vector detJ must hold one value per test function")
         ct = C.c_float if dtype == np.float32 else C.c_double
-        fn = self.lib.vn_upload_points_f32 if dtype == np.float32 else self.lib.vn_upload_points_f64
-        self._check(fn(self._h, _ptr(X, ct), _ptr(G, ct), _ptr(S, ct), _ptr(Nn, ct), _ptr(T, ct), nb, integNum,
+        fn = self.lib.vn_upload_table_f32 if dtype == np.float32 else self.lib.vn_upload_table_f64
+        self._check(fn(self._h, _ptr(X, ct), nx, _ptr(G, ct), _ptr(S, ct), _ptr(Nn, ct), _ptr(T, ct), nb, integNum,
                        _ptr(W, ct), _ptr(D, ct), int(bool(detJvec))))
         self.nb = nb
 

@@ -24,6 +24,7 @@ import os
 import numpy as np
 
 from ._capi import Engine, EngineError  # noqa: F401
+from .tables import TableView
 
 
 # ------------------------------------------------------------------ graph stand-ins
@@ -161,13 +162,20 @@ class Session:
                 continue
             fd, eng, tok = by_tower[tw.index], tw.engine, tw._tokens
             if need_points and "Input" in fd and "intShape" in fd:
-                names = ("Input", "gcoef", "source", "N", "dNt", "intShape", "integW", "detJ", "detJvec")
-                t = tuple(_token(fd.get(k)) for k in names)
-                if tok.get("points") != t or not self._o.feed_cache:
-                    eng.upload_points(fd["Input"], fd["gcoef"], fd.get("source"), fd.get("N"), fd.get("dNt"),
-                                      fd["intShape"], fd.get("integW"), fd["detJ"], bool(fd.get("detJvec", False)))
-                    tok["points"] = t
-                    self._o.uploads += 1
+                if self._is_view_feed(fd):
+                    self._sync_view_feed(tw, fd)
+                else:
+                    names = ("Input", "gcoef", "source", "N", "dNt", "intShape", "integW", "detJ", "detJvec")
+                    t = tuple(_token(fd.get(k)) for k in names)
+                    if tok.get("points") != t or not self._o.feed_cache:
+                        mat = {k: (np.asarray(fd[k]) if isinstance(fd.get(k), TableView) else fd.get(k)) for k in names}
+                        if getattr(eng, "supports_table_views", False):
+                            eng.select_table(0)                     # slot 0 = plain (reference-style) feeds
+                        eng.upload_points(mat["Input"], mat["gcoef"], mat["source"], mat["N"], mat["dNt"],
+                                          fd["intShape"], mat["integW"], mat["detJ"], bool(fd.get("detJvec", False)))
+                        tok["points"] = t
+                        tok.pop("view", None)
+                        self._o.uploads += 1
             if need_bic and "biInput" in fd:
                 names = ("biInput", "biLabel", "bDof", "biDimVal")
                 t = tuple(_token(fd.get(k)) for k in names)
@@ -182,6 +190,58 @@ class Session:
                     eng.set_weights(w)
                     tok["w"] = t
         return by_tower
+
+    # -- device-resident tables: the feed carries TableViews (lazy gathers) instead of gathered copies
+    @staticmethod
+    def _is_view_feed(fd):
+        X = fd.get("Input")
+        if not (isinstance(X, TableView) and X.tf is not None):
+            return False
+        for k in ("gcoef", "source", "N", "dNt"):
+            v = fd.get(k)
+            if isinstance(v, TableView) and (v.integNum != X.integNum or
+                                             not (v.tf is X.tf or np.array_equal(v.tf, X.tf))):
+                return False
+        return isinstance(fd.get("gcoef"), TableView)
+
+    def _sync_view_feed(self, tw, fd):
+        o, eng, tok = self._o, tw.engine, tw._tokens
+        X = fd["Input"]
+        base = lambda k: (fd[k].base if isinstance(fd.get(k), TableView) else fd.get(k))
+        detJ = fd["detJ"]
+        detJvec = bool(fd.get("detJvec", False))
+        key = tuple(_token(base(k)) for k in ("Input", "gcoef", "source", "N", "dNt")) + (
+            _token(detJ.base if isinstance(detJ, TableView) else detJ), _token(fd.get("integW")), X.integNum, detJvec)
+        slots = tw.__dict__.setdefault("_slots", {})                   # table key -> slot (LRU order)
+        slot = slots.pop(key, None)
+        fresh = slot is None or not o.feed_cache
+        if slot is None:
+            if len(slots) >= o.max_resident_tables:
+                _, slot = next(iter(slots.items()))                     # evict the least recently used table
+                del slots[next(iter(slots))]
+            else:
+                slot = 1 + len(slots)                                   # slot 0 is reserved for plain feeds
+        slots[key] = slot
+        if tok.get("view_slot") != slot or fresh:
+            eng.select_table(slot)
+            tok["view_slot"] = slot
+            tok.pop("view_batch", None)
+        if fresh:
+            nbTab = len(X.base) // X.integNum
+            eng.upload_table(X.base, base("gcoef"), base("source"), base("N"), base("dNt"), [nbTab, X.integNum],
+                             fd.get("integW"), detJ.base if isinstance(detJ, TableView) else detJ, detJvec,
+                             nx=X.base.shape[1])
+            o.uploads += 1
+        extra = None if X.extra is None else tuple(np.asarray(X.extra, dtype=np.float32).ravel().tolist())
+        if tok.get("view_extra") != extra or fresh:
+            eng.set_extra_inputs(extra)
+            tok["view_extra"] = extra
+        bt = _token(X.tf)
+        if tok.get("view_batch") != bt:
+            eng.set_batch(X.tf)
+            tok["view_batch"] = bt
+        tok["view"] = True
+        tok.pop("points", None)
 
     def _local_towers(self):
         return [tw for tw in self._o.compTowers if tw.local]
@@ -410,6 +470,7 @@ class TFNN:
         # True: a feed array is uploaded only when it is replaced by a new object; False: every
         # sess.run re-uploads its feeds, like the reference's per-step feed (VarNetUtility.py:1044)
         self.feed_cache = True
+        self.max_resident_tables = 64       # LRU bound on device-resident point tables per tower
         self._rng = np.random.RandomState(seed)
 
         dist = _dist()
@@ -432,6 +493,9 @@ class TFNN:
         if len({a.lower() for a in activationFun}) != 1:
             raise ValueError('a single activation function for all hidden layers is supported')
 
+        # lazy-gather feeds (tables.TableView) are understood when every local engine keeps tables resident
+        self.supports_table_views = all(getattr(tw.engine, "supports_table_views", False)
+                                        for tw in self.compTowers if tw.local)
         self.graph = _Graph()
         self.loss, self.BCloss, self.ICloss = Node("loss"), Node("BCloss"), Node("ICloss")
         self.varLoss, self.lossVec = Node("varLoss"), Node("lossVec")

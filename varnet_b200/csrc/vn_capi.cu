@@ -67,7 +67,7 @@ __global__ void vn_segreduce_kernel(SegArgs A) {
             for (unsigned int q = 0; q < A.integNum; ++q) r += __ldg(row + q);
         }
         const float r2 = r * r;
-        const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+        const float dj = A.detJvec ? __ldg(A.detJ + (A.tfIndex ? (unsigned int)__ldg(A.tfIndex + i) : i)) : __ldg(A.detJ);
         A.R[i] = r;
         A.lossVec[i] = dj * r2;
         term = A.detJvec ? (double)dj * (double)r2 : (double)r2;
@@ -254,6 +254,15 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// one uploaded point table (SoA columns + per-test-function detJ + Gauss weights) and its captured step graph
+struct PointSet {
+    DevBuf cols, integW, detJ;
+    long long pstride = 0; unsigned int rows = 0, nbTab = 0, integNum = 0; int detJvec = 0, hasIntegW = 0;
+    int colX = 0, colG = 0, colT = -1, colS = -1, ncols = 0, nx = 0;
+    bool loaded = false;
+    cudaGraphExec_t graph = nullptr; float graphLr = -1.f; int graphLaunches = 0; unsigned int graphNb = 0; bool graphIndexed = false;
+};
+
 struct vn_engine {
     vn_config cfg;
     NetDesc net;
@@ -262,17 +271,19 @@ struct vn_engine {
     cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
     cudaStream_t ownStream = nullptr;
     int64_t launches = 0;
-    // captured training step (vn_train_step): kernels of loss_grad + optimizer as one CUDA graph
-    cudaGraphExec_t stepGraph = nullptr;
-    float graphLr = -1.f;
-    int graphLaunches = 0;
-    bool graphOK = true;
+    bool graphOK = true;         // CUDA-graph capture of vn_train_step available (one graph per table slot)
+    // table slots: several uploaded point tables can be resident; mini-batches select test functions of the
+    // current table through a device index list (vn_select_table / vn_set_batch)
+    std::vector<PointSet*> slots;
+    PointSet* t = nullptr;
+    DevBuf batchIdx, extraX;
+    bool indexed = false;        // batch = index list into the table (else: the whole table in order)
+    int nExtra = 0;              // trailing MLP inputs supplied as per-call constants (MOR parameters)
     // parameters + optimizer
     DevBuf theta, m, v, gbuf, wts, stepbuf, corrbuf;
-    // interior points
-    DevBuf cols, integW, detJ, Iw, R, lossVec, segSum;
-    long long pstride = 0; unsigned int P = 0, nb = 0, integNum = 0; int detJvec = 0, hasIntegW = 0;
-    int colX = 0, colG = 0, colT = -1, colS = -1, ncols = 0;
+    // interior points of the current batch (P = nb * integNum)
+    DevBuf Iw, R, lossVec, segSum;
+    unsigned int P = 0, nb = 0;
     // boundary / initial rows
     DevBuf bcols, blabel, cj;
     long long bstride = 0; unsigned int nbi = 0, bDof = 0; float biDimVal = 0.f;
@@ -308,9 +319,12 @@ struct ProfScope {
 
 static const int kPad = 128;
 
-static void drop_graph(vn_engine* e) {
-    if (e->stepGraph) { cudaGraphExecDestroy(e->stepGraph); e->stepGraph = nullptr; }
-    e->graphLr = -1.f;
+static void drop_graph(PointSet* t) {
+    if (t && t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
+    if (t) t->graphLr = -1.f;
+}
+static void drop_graph(vn_engine* e) {            // everything captured so far is stale (stream / BC-IC table changed)
+    for (PointSet* t : e->slots) drop_graph(t);
 }    // point-table padding: multiple of every tile size
 
 static int build_net(const vn_config& c, NetDesc* n) {
@@ -351,6 +365,8 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     if (!e) return fail(VN_E_INVALID, "out of host memory");
     e->cfg = *cfg;
     if (cudaStreamCreate(&e->ownStream) == cudaSuccess) e->stream = e->ownStream;
+    e->slots.push_back(new PointSet());
+    e->t = e->slots[0];
     build_net(*cfg, &e->net);
     e->S = 1 + cfg->dim;
     if (wmax > 64) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
@@ -408,8 +424,9 @@ extern "C" int vn_destroy(vn_engine* e) {
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
     if (e->ownStream) cudaStreamDestroy(e->ownStream);
-    DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->cols, &e->integW,
-                      &e->detJ, &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
+    for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
+    DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
+                      &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
     for (DevBuf* b : bufs) b->release();
     delete e;
@@ -492,84 +509,179 @@ extern "C" int vn_set_weights(vn_engine* e, const float w[3]) {
 // ------------------------------------------------------------------ uploads
 static const long long kChunk = 1 << 22;    // rows per staging chunk
 
+// size the per-batch work buffers and pick the single-pass (fused residual) path when integNum | TP
+static int ensure_work(vn_engine* e) {
+    PointSet* t = e->t;
+    const long long P = (long long)e->nb * t->integNum;
+    e->P = (unsigned int)P;
+    CK(e->Iw.ensure((size_t)std::max<long long>(P, 1) * sizeof(float)));
+    CK(e->R.ensure((size_t)std::max<unsigned>(e->nb, 1) * sizeof(float)));
+    CK(e->lossVec.ensure((size_t)std::max<unsigned>(e->nb, 1) * sizeof(float)));
+    const int nSeg = (int)((e->nb + 255) / 256);
+    CK(e->segSum.ensure((size_t)std::max(nSeg, 1) * sizeof(double)));
+    const long long tilesAdj = (P + e->gVarAdj.TP - 1) / e->gVarAdj.TP;
+    e->gridVar = (int)std::max<long long>(1, std::min<long long>(tilesAdj, e->numSMs));
+    CK(e->partVar.ensure((size_t)e->numSMs * e->gVarAdj.pl.psz * sizeof(double)));
+    CK(e->part32Var.ensure((size_t)e->numSMs * e->gVarAdj.pl.psz * sizeof(float)));
+    CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->numSMs * e->gVarAdj.stashFloats * sizeof(float))));
+    CK(e->lossPart.ensure((size_t)e->numSMs * (e->gVarAdj.NT / 32) * sizeof(double)));
+    e->fused = (e->gVarAdj.TP % t->integNum) == 0;
+    return VN_OK;
+}
+
+// Upload one point table into the current slot.  X has `nx` columns; the remaining inpDim-nx MLP inputs are
+// per-call constants (vn_set_extra_inputs).  The batch is reset to "whole table, in order".
 template <typename T>
-static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, const T* N, const T* dNt, int64_t nb,
-                         int32_t integNum, const T* integW, const T* detJ, int32_t detJvec) {
+static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* src, const T* N, const T* dNt,
+                        int64_t nb, int32_t integNum, const T* integW, const T* detJ, int32_t detJvec) {
     if (!e || !X || !G || !detJ) return fail(VN_E_INVALID, "Input, gcoef and detJ are required");
     if (nb < 1 || integNum < 1) return fail(VN_E_INVALID, "intShape must be positive");
+    const vn_config& c = e->cfg;
+    if (nx < c.dim + (c.timeDependent ? 1 : 0) || nx > c.inpDim)
+        return fail(VN_E_INVALID, "the table must hold between %d and %d input columns", c.dim + (c.timeDependent ? 1 : 0), c.inpDim);
     const long long P = (long long)nb * integNum;
     if (P >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "more than 2^31 quadrature points per engine; shard the test functions");
-    drop_graph(e);
-    const vn_config& c = e->cfg;
     if (c.timeDependent && !dNt) return fail(VN_E_INVALID, "dNt is required for time-dependent problems");
     if (c.isSource && (!src || !N)) return fail(VN_E_INVALID, "source and N are required when lossOpt['isSource'] is set");
     if (c.integWflag && !integW) return fail(VN_E_INVALID, "integW is required when lossOpt['integWflag'] is set");
     CK(cudaSetDevice(c.device));
+    PointSet* t = e->t;
+    drop_graph(t);
     int col = 0;
-    e->colX = col; col += c.inpDim;
-    e->colG = col; col += c.dim;
-    e->colT = c.timeDependent ? col++ : -1;
-    e->colS = c.isSource ? col++ : -1;
-    e->ncols = col;
-    e->pstride = (P + kPad - 1) / kPad * kPad;
-    e->P = (unsigned int)P; e->nb = (unsigned int)nb; e->integNum = (unsigned int)integNum; e->detJvec = detJvec ? 1 : 0;
-    CK(e->cols.ensure((size_t)e->ncols * e->pstride * sizeof(float)));
-    CK(cudaMemsetAsync(e->cols.p, 0, (size_t)e->ncols * e->pstride * sizeof(float), e->stream));
-    const int rowVals = c.inpDim + c.dim + 3;
+    t->nx = nx;
+    t->colX = col; col += nx;
+    t->colG = col; col += c.dim;
+    t->colT = c.timeDependent ? col++ : -1;
+    t->colS = c.isSource ? col++ : -1;
+    t->ncols = col;
+    t->pstride = (P + kPad - 1) / kPad * kPad;
+    t->rows = (unsigned int)P; t->nbTab = (unsigned int)nb; t->integNum = (unsigned int)integNum; t->detJvec = detJvec ? 1 : 0;
+    CK(t->cols.ensure((size_t)t->ncols * t->pstride * sizeof(float)));
+    CK(cudaMemsetAsync(t->cols.p, 0, (size_t)t->ncols * t->pstride * sizeof(float), e->stream));
+    const int rowVals = nx + c.dim + 3;
     const long long chunk = std::min<long long>(kChunk, P);
     CK(e->stage.ensure((size_t)chunk * rowVals * sizeof(T)));
     for (long long off = 0; off < P; off += chunk) {
         const long long n = std::min(chunk, P - off);
         T* sX = e->stage.as<T>();
-        T* sG = sX + n * c.inpDim;
+        T* sG = sX + n * nx;
         T* sT = sG + n * c.dim;
         T* sS = sT + n;
         T* sN = sS + n;
-        CK(cudaMemcpyAsync(sX, X + off * c.inpDim, n * c.inpDim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(sX, X + off * nx, n * nx * sizeof(T), cudaMemcpyHostToDevice, e->stream));
         CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
-        if (e->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
-        if (e->colS >= 0) {
+        if (t->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        if (t->colS >= 0) {
             CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
             CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
         }
         vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            sX, c.inpDim, sG, c.dim, e->colT >= 0 ? sT : nullptr, e->colS >= 0 ? sS : nullptr,
-            e->colS >= 0 ? sN : nullptr, e->cols.as<float>(), e->pstride, off, n, e->colX, e->colG, e->colT, e->colS);
+            sX, nx, sG, c.dim, t->colT >= 0 ? sT : nullptr, t->colS >= 0 ? sS : nullptr,
+            t->colS >= 0 ? sN : nullptr, t->cols.as<float>(), t->pstride, off, n, t->colX, t->colG, t->colT, t->colS);
         CK(cudaGetLastError());
         e->launches++;
         CK(cudaStreamSynchronize(e->stream));      // staging buffer is reused by the next chunk
     }
     // small tables
-    e->hasIntegW = (c.integWflag && integW) ? 1 : 0;
+    t->hasIntegW = (c.integWflag && integW) ? 1 : 0;
     const long long nd = detJvec ? nb : 1;
-    CK(e->detJ.ensure(nd * sizeof(float)));
+    CK(t->detJ.ensure(nd * sizeof(float)));
     CK(e->stage.ensure((size_t)std::max<long long>(nd, integNum) * sizeof(T)));
     CK(cudaMemcpyAsync(e->stage.p, detJ, nd * sizeof(T), cudaMemcpyHostToDevice, e->stream));
-    vn_cast_kernel<T><<<(unsigned)((nd + 255) / 256), 256, 0, e->stream>>>(e->stage.as<T>(), e->detJ.as<float>(), nd);
+    vn_cast_kernel<T><<<(unsigned)((nd + 255) / 256), 256, 0, e->stream>>>(e->stage.as<T>(), t->detJ.as<float>(), nd);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
-    if (e->hasIntegW) {
-        CK(e->integW.ensure(integNum * sizeof(float)));
+    if (t->hasIntegW) {
+        CK(t->integW.ensure(integNum * sizeof(float)));
         CK(cudaMemcpyAsync(e->stage.p, integW, integNum * sizeof(T), cudaMemcpyHostToDevice, e->stream));
-        vn_cast_kernel<T><<<(integNum + 255) / 256, 256, 0, e->stream>>>(e->stage.as<T>(), e->integW.as<float>(), integNum);
+        vn_cast_kernel<T><<<(integNum + 255) / 256, 256, 0, e->stream>>>(e->stage.as<T>(), t->integW.as<float>(), integNum);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
     }
-    e->launches += 1 + e->hasIntegW;
-    // work buffers
-    CK(e->Iw.ensure((size_t)P * sizeof(float)));
-    CK(e->R.ensure((size_t)nb * sizeof(float)));
-    CK(e->lossVec.ensure((size_t)nb * sizeof(float)));
-    const int nSeg = (int)((nb + 255) / 256);
-    CK(e->segSum.ensure((size_t)nSeg * sizeof(double)));
-    const long long tilesAdj = e->pstride / e->gVarAdj.TP;
-    e->gridVar = (int)std::min<long long>(tilesAdj, e->numSMs);
-    CK(e->partVar.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(double)));
-    CK(e->part32Var.ensure((size_t)e->gridVar * e->gVarAdj.pl.psz * sizeof(float)));
-    CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->gridVar * e->gVarAdj.stashFloats * sizeof(float))));
-    CK(e->lossPart.ensure((size_t)e->gridVar * (e->gVarAdj.NT / 32) * sizeof(double)));
-    e->fused = (e->gVarAdj.TP % integNum) == 0;
+    e->launches += 1 + t->hasIntegW;
+    t->loaded = true;
+    e->indexed = false;
+    e->nb = t->nbTab;
+    return ensure_work(e);
+}
+
+template <typename T>
+static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, const T* N, const T* dNt, int64_t nb,
+                         int32_t integNum, const T* integW, const T* detJ, int32_t detJvec) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    e->nExtra = 0;
+    return upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec);
+}
+
+extern "C" int vn_select_table(vn_engine* e, int32_t slot) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (slot < 0 || slot >= VN_MAX_TABLES) return fail(VN_E_INVALID, "table slot must be in [0,%d)", VN_MAX_TABLES);
+    while ((int)e->slots.size() <= slot) e->slots.push_back(new PointSet());
+    e->t = e->slots[slot];
+    if (e->t->loaded) {                     // default batch of a resident table: all of it, in order
+        e->indexed = false;
+        e->nb = e->t->nbTab;
+        return ensure_work(e);
+    }
+    e->nb = 0; e->P = 0;
     return VN_OK;
+}
+extern "C" int vn_table_loaded(const vn_engine* e, int32_t slot) {
+    return (e && slot >= 0 && slot < (int)e->slots.size() && e->slots[slot]->loaded) ? 1 : 0;
+}
+extern "C" int vn_free_table(vn_engine* e, int32_t slot) {
+    if (!e || slot < 0 || slot >= (int)e->slots.size()) return fail(VN_E_INVALID, "bad table slot");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    PointSet* t = e->slots[slot];
+    drop_graph(t);
+    t->cols.release(); t->integW.release(); t->detJ.release();
+    t->loaded = false; t->rows = t->nbTab = 0;
+    if (t == e->t) { e->nb = 0; e->P = 0; }
+    return VN_OK;
+}
+// Mini-batch = the listed test functions of the current table, in that order (the reference gathers
+// `integInd[batchInd[n0:n1]]` on the host for every batch, VarNetUtility.py:833-844); NULL = whole table.
+extern "C" int vn_set_batch(vn_engine* e, const int32_t* tf_index, int64_t nb) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (!e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+    CK(cudaSetDevice(e->cfg.device));
+    if (!tf_index) {
+        e->indexed = false; e->nb = e->t->nbTab;
+        return ensure_work(e);
+    }
+    if (nb < 1) return fail(VN_E_INVALID, "a batch needs at least one test function");
+    if (e->t->integNum % 4 != 0) return fail(VN_E_UNSUPPORTED, "indexed batches need integNum to be a multiple of 4");
+    CK(e->batchIdx.ensure((size_t)nb * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(e->batchIdx.p, tf_index, (size_t)nb * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->indexed = true; e->nb = (unsigned int)nb;
+    return ensure_work(e);
+}
+// Constant values of the trailing MLP inputs (MOR parameters): the table then only stores the space-time
+// columns, instead of a re-tiled copy per parameter batch (VarNet.py:843-851, VarNetUtility.py:725-729).
+extern "C" int vn_set_extra_inputs(vn_engine* e, const float* vals, int32_t n) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (n < 0 || n > e->cfg.inpDim) return fail(VN_E_INVALID, "bad number of extra inputs");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(e->extraX.ensure(VN_MAX_INPDIM * sizeof(float)));
+    if (n > 0) {
+        if (!vals) return fail(VN_E_INVALID, "null argument");
+        CK(cudaMemcpyAsync(e->extraX.p, vals, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    e->nExtra = n;
+    return VN_OK;
+}
+extern "C" int vn_upload_table_f64(vn_engine* e, const double* X, int32_t nx, const double* G, const double* s,
+                                   const double* N, const double* dNt, int64_t nb, int32_t integNum, const double* iw,
+                                   const double* dj, int32_t djv) {
+    return upload_table<double>(e, X, nx, G, s, N, dNt, nb, integNum, iw, dj, djv);
+}
+extern "C" int vn_upload_table_f32(vn_engine* e, const float* X, int32_t nx, const float* G, const float* s,
+                                   const float* N, const float* dNt, int64_t nb, int32_t integNum, const float* iw,
+                                   const float* dj, int32_t djv) {
+    return upload_table<float>(e, X, nx, G, s, N, dNt, nb, integNum, iw, dj, djv);
 }
 
 template <typename T>
@@ -630,30 +742,37 @@ static void base_args(const vn_engine* e, TileArgs* a) {
     a->timeDependent = e->cfg.timeDependent;
     a->isSource = e->cfg.isSource;
     a->dim = e->cfg.dim;
+    a->nxTable = e->cfg.inpDim; a->tfIndex = nullptr; a->extraX = nullptr;
     a->wts = e->wts.as<float>();
 }
 static void var_args(const vn_engine* e, TileArgs* a) {
     base_args(e, a);
-    a->cols = e->cols.as<float>(); a->pstride = e->pstride;
-    a->colX = e->colX; a->colG = e->colG; a->colT = e->colT; a->colS = e->colS;
+    const PointSet* t = e->t;
+    a->cols = t->cols.as<float>(); a->pstride = t->pstride;
+    a->colX = t->colX; a->colG = t->colG; a->colT = t->colT; a->colS = t->colS;
+    a->nxTable = t->nx; a->extraX = e->extraX.as<float>();
+    a->tfIndex = e->indexed ? e->batchIdx.as<int>() : nullptr;
     a->P = e->P;
-    a->integNum = e->integNum;
-    a->integW = e->hasIntegW ? e->integW.as<float>() : nullptr;
-    a->detJ = e->detJ.as<float>(); a->detJvec = e->detJvec;
+    a->integNum = t->integNum;
+    a->integW = t->hasIntegW ? t->integW.as<float>() : nullptr;
+    a->detJ = t->detJ.as<float>(); a->detJvec = t->detJvec;
     a->R = e->R.as<float>(); a->Iw = e->Iw.as<float>(); a->lossVec = e->lossVec.as<float>();
 }
 static void bic_args(const vn_engine* e, TileArgs* a) {
     base_args(e, a);
     a->cols = e->bcols.as<float>(); a->pstride = e->bstride;
     a->colX = 0; a->colG = 0; a->colT = -1; a->colS = -1;
+    a->nxTable = e->cfg.inpDim; a->tfIndex = nullptr;
     a->P = e->nbi; a->label = e->blabel.as<float>(); a->bDof = e->bDof; a->biDimVal = e->biDimVal;
     a->cj = e->cj.as<float>();
 }
 
 static int run_loss(vn_engine* e, bool needGrad) {
     if (!e) return fail(VN_E_INVALID, "null engine");
-    if (!e->P) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+    if (!e->P || !e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
     if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
+    if (e->t->nx + e->nExtra != e->cfg.inpDim)
+        return fail(VN_E_STATE, "table holds %d input columns and %d extra inputs are set, the MLP needs %d", e->t->nx, e->nExtra, e->cfg.inpDim);
     const vn_config& c = e->cfg;
     CK(cudaSetDevice(c.device));
     cudaStream_t st = e->stream;
@@ -664,7 +783,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
     if (needGrad && e->fused) {
         // single pass: forward, in-tile residual reduction, adjoint (MODE_VAR_FUSED)
         const TileGeom& g = e->gVarAdj;
-        a.ntiles = (int)(e->pstride / g.TP);
+        a.ntiles = (int)(((long long)e->P + g.TP - 1) / g.TP);
         a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
@@ -677,7 +796,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         // 1. forward over all quadrature points -> weighted integrand
         {
             const TileGeom& g = e->gVarFwd;
-            a.ntiles = (int)(e->pstride / g.TP);
+            a.ntiles = (int)(((long long)e->P + g.TP - 1) / g.TP);
             const int grid = std::min(a.ntiles, 2 * e->numSMs);
             ProfScope ps(e, PK_VAR_FWD);
             CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
@@ -685,8 +804,8 @@ static int run_loss(vn_engine* e, bool needGrad) {
         // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
         {
             SegArgs s;
-            s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->integNum; s.detJ = e->detJ.as<float>();
-            s.detJvec = e->detJvec; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
+            s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->t->integNum; s.detJ = e->t->detJ.as<float>();
+            s.detJvec = e->t->detJvec; s.tfIndex = e->indexed ? e->batchIdx.as<int>() : nullptr; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
             s.blockSum = e->segSum.as<double>();
             ProfScope ps(e, PK_SEG);
             vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
@@ -696,7 +815,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         if (needGrad) {
             // 3. adjoint over quadrature points (forward recomputed per tile, seeds from R_i)
             const TileGeom& g = e->gVarAdj;
-            a.ntiles = (int)(e->pstride / g.TP);
+            a.ntiles = (int)(((long long)e->P + g.TP - 1) / g.TP);
             a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
             a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
             ProfScope ps(e, PK_VAR_ADJ);
@@ -725,7 +844,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
         f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
         f.segSum = segPtr; f.nSeg = nSeg;
-        f.detJ = e->detJ.as<float>(); f.detJvec = e->detJvec;
+        f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
         const int nb = needGrad ? (e->net.nparam + 3) / 4 : 0;          // one warp per parameter, 4 warps per block
@@ -794,15 +913,19 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
     if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
     CK(cudaSetDevice(e->cfg.device));
     const bool useGraph = e->graphOK && !e->profOn && e->stream != nullptr;
-    if (useGraph && e->stepGraph && e->graphLr == lr) {
-        CK(cudaGraphLaunch(e->stepGraph, e->stream));
-        e->launches += e->graphLaunches;
+    PointSet* t = e->t;
+    // a captured step stays valid while the table, the batch size / kind and lr are unchanged (the index list,
+    // the extra inputs and the loss weights are read from device memory at replay time)
+    if (useGraph && t->graph && t->graphLr == lr && t->graphNb == e->nb && t->graphIndexed == e->indexed) {
+        CK(cudaGraphLaunch(t->graph, e->stream));
+        e->launches += t->graphLaunches;
     } else if (useGraph) {
         // capture the step once per (tables, lr): replay removes the per-kernel launch gaps that dominate
         // the small operator configurations (5 kernels of a few tens of microseconds)
-        drop_graph(e);
-        if (!e->P) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+        drop_graph(t);
+        if (!e->P || !t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
         if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
+        if (t->nx + e->nExtra != e->cfg.inpDim) return fail(VN_E_STATE, "table input columns + extra inputs do not match the MLP input size");
         const int64_t l0 = e->launches;
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
@@ -812,10 +935,10 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
             if (!rc) rc = vn_optimizer_step(e, lr);
             ce = cudaStreamEndCapture(e->stream, &g);
         }
-        if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&e->stepGraph, g, 0) != cudaSuccess) {
+        if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&t->graph, g, 0) != cudaSuccess) {
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
-            e->stepGraph = nullptr; e->graphOK = false;         // fall back to plain launches for this engine
+            t->graph = nullptr; e->graphOK = false;             // fall back to plain launches for this engine
             e->launches = l0;
             rc = run_loss(e, true);
             if (rc) return rc;
@@ -823,8 +946,9 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
             if (rc) return rc;
         } else {
             cudaGraphDestroy(g);
-            e->graphLr = lr; e->graphLaunches = (int)(e->launches - l0);
-            CK(cudaGraphLaunch(e->stepGraph, e->stream));
+            t->graphLr = lr; t->graphLaunches = (int)(e->launches - l0);
+            t->graphNb = e->nb; t->graphIndexed = e->indexed;
+            CK(cudaGraphLaunch(t->graph, e->stream));
         }
     } else {
         int rc = run_loss(e, true);

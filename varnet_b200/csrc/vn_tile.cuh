@@ -55,6 +55,9 @@ struct TileArgs {
     long long pstride;              // multiple of the tile size, zero padded
     int colX, colG, colT, colS;     // first column of X, gcoef (residual: vel), dNt, source*N (residual: source); -1 = absent
     int colD, colDD;                // residual: diffusivity column, first grad(kappa) column
+    int nxTable;                    // MLP input columns stored in the table; inputs [nxTable, inpDim) are constants
+    const float* extraX;            // [inpDim - nxTable] constant trailing inputs (MOR parameters), device
+    const int* tfIndex;             // mini-batch: table test-function index of batch slot b, or nullptr (identity)
     int dim;                        // spatial dimension (residual kernel: runtime stream roles)
     unsigned int P;                 // valid points (rows)
     int ntiles;
@@ -467,12 +470,32 @@ __device__ __forceinline__ void forward_layer(const NetDesc& net, const SmemMap<
     }
 }
 
-// stage the tile's input columns into layer "-1" (coalesced 128-bit loads from the SoA table)
+// batch point -> table row: mini-batches address the resident table through a test-function index list
+__device__ __forceinline__ size_t table_row(const TileArgs& A, unsigned int gp) {
+    if (!A.tfIndex) return gp;
+    const unsigned int b = gp / A.integNum;
+    return (size_t)__ldg(A.tfIndex + b) * A.integNum + (gp - b * A.integNum);
+}
+__device__ __forceinline__ unsigned int table_tf(const TileArgs& A, unsigned int b) {
+    return A.tfIndex ? (unsigned int)__ldg(A.tfIndex + b) : b;
+}
+
+// stage the tile's input columns into layer "-1" (coalesced 128-bit loads from the SoA table; groups of 4
+// points never straddle a test function in indexed mode because integNum % 4 == 0 there)
 template <class C>
 __device__ __forceinline__ void load_inputs(const TileArgs& A, const SmemMap<C>& m, unsigned int base) {
     for (int idx = threadIdx.x; idx < A.net.inpDim * C::NPG; idx += C::NT) {
-        int c = idx / C::NPG, q = idx - c * C::NPG;
-        float4 v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + base) + q);
+        const int c = idx / C::NPG, q = idx - c * C::NPG;
+        const unsigned int gp = base + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= A.nxTable) {
+            const float x = __ldg(A.extraX + (c - A.nxTable));
+            v = make_float4(x, x, x, x);
+        } else if (!A.tfIndex) {
+            v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + gp));   // padded table
+        } else if (gp < A.P) {
+            v = __ldg(reinterpret_cast<const float4*>(A.cols + (size_t)(A.colX + c) * A.pstride + table_row(A, gp)));
+        }
         sts4(m.Bm1 + c * C::TPS + 4 * q, v);
     }
 }
@@ -497,11 +520,12 @@ __device__ __forceinline__ void output_layer(const SmemMap<C>& m, const float* B
 template <class C>
 __device__ __forceinline__ float integrand(const TileArgs& A, const SmemMap<C>& m, int p, unsigned int gp) {
     float I = 0.f;
+    const size_t row = table_row(A, gp);
 #pragma unroll
     for (int k = 0; k < C::S - 1; ++k)
-        I = fmaf(m.us[(1 + k) * C::TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp), I);
-    if (A.timeDependent) I -= m.us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + gp);
-    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
+        I = fmaf(m.us[(1 + k) * C::TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
+    if (A.timeDependent) I -= m.us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
+    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
     if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
     return I;
 }
@@ -604,16 +628,18 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
             for (int p = tid; p < TP; p += NT) {
                 const unsigned int gp = base + p;
                 float lam = 0.f;
+                size_t row = 0;
                 if (gp < A.P) {
                     const unsigned int i = gp / A.integNum, q = gp - i * A.integNum;
-                    const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                    const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
                     const float wq = A.integW ? __ldg(A.integW + q) : 1.f;
                     lam = 2.f * __ldg(A.wts + 2) * dj * wq * __ldg(A.R + i);
+                    row = table_row(A, gp);
                 }
-                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + gp) : 0.f;
+                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + row) : 0.f;
 #pragma unroll
                 for (int k = 0; k < S - 1; ++k)
-                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp);
+                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
             }
         }
         __syncthreads();
@@ -649,7 +675,7 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
                     const unsigned int i = base / A.integNum + f;
                     Rsh[f] = r;
                     if (i * A.integNum < A.P) {
-                        const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                        const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
                         const float r2 = r * r;
                         A.R[i] = r;
                         A.lossVec[i] = dj * r2;
@@ -661,16 +687,18 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
             for (int p = tid; p < TP; p += NT) {
                 const unsigned int gp = base + p;
                 float lam = 0.f;
+                size_t row = 0;
                 if (gp < A.P) {
                     const unsigned int i = gp / A.integNum, q = gp - i * A.integNum;
-                    const float dj = A.detJvec ? __ldg(A.detJ + i) : __ldg(A.detJ);
+                    const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
                     const float wq = A.integW ? __ldg(A.integW + q) : 1.f;
                     lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
+                    row = table_row(A, gp);
                 }
-                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + gp) : 0.f;
+                us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + row) : 0.f;
 #pragma unroll
                 for (int k = 0; k < S - 1; ++k)
-                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp);
+                    us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
             }
             __syncthreads();
         }
@@ -819,6 +847,7 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
 // R_i = sum_q Iw[i*integNum+q]; lossVec_i = detJ_i R_i^2; block partial of sum_i (detJ_i) R_i^2 in FP64.
 struct SegArgs {
     const float* Iw; unsigned int nb, integNum; const float* detJ; int detJvec;
+    const int* tfIndex;             // batch slot -> table test function (per-test-function detJ), or nullptr
     float* R; float* lossVec; double* blockSum;
 };
 __global__ void vn_segreduce_kernel(SegArgs A);

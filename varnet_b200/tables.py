@@ -20,6 +20,52 @@ from .fe import FE
 from .hostutil import is_empty, is_none, pair_rows, stack_rows
 
 
+class TableView:
+    """Lazy gather: the rows of `base` that belong to the test functions `tf` (each owns `integNum`
+    consecutive rows; tf=None means every row), optionally followed by constant columns `extra`.
+
+    The reference materialises these gathers on the host for every mini-batch, shuffle and MOR batch
+    (`InpuTot[intgInd,:]`, VarNetUtility.py:840-844; `hstack(Input, tile(MORinp))`, VarNet.py:843-851).
+    A backend that advertises `supports_table_views` keeps `base` resident on the device and receives
+    only the index list / the constants; any other consumer gets the materialised array via
+    `np.asarray(view)`, bit-identical to the reference's copy."""
+
+    def __init__(self, base, tf=None, integNum=1, extra=None):
+        self.base, self.tf, self.integNum = base, tf, int(integNum)
+        self.extra = None if extra is None or np.size(extra) == 0 else np.asarray(extra, dtype=float).reshape(1, -1)
+        n = len(base) if tf is None else len(tf) * self.integNum
+        self.shape = (n, base.shape[1] + (0 if self.extra is None else self.extra.shape[1]))
+        self.dtype = base.dtype
+        self.ndim = 2
+
+    def __len__(self):
+        return self.shape[0]
+
+    def rows(self):
+        if self.tf is None:
+            return slice(None)
+        return (np.asarray(self.tf).reshape(-1, 1) * self.integNum + np.arange(self.integNum)).reshape(-1)
+
+    def materialize(self):
+        out = self.base[self.rows(), :]
+        if self.extra is not None:
+            out = np.hstack([out, np.tile(self.extra, reps=[len(out), 1])])
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.materialize()
+        return out if dtype is None else out.astype(dtype)
+
+    def __getitem__(self, key):
+        return self.materialize()[key]
+
+    def take(self, tf, integNum):
+        """Restrict an all-rows view to the test functions `tf`."""
+        if self.tf is not None:
+            raise ValueError('view is already restricted')
+        return TableView(self.base, tf, integNum, self.extra)
+
+
 class FIXData:
     """Fixed tables of one VarNet instance (mesh sizes, FE tables, monitoring grid)."""
 
@@ -188,7 +234,10 @@ class ManageTrainData:
         if batch < 0 or batch > self.MORbatchNum:
             raise ValueError('batch number out of range!')
         inpMOR, names, data = self.MORinp[batch], self.fieldNames[batch], list(self.MORdata[batch])
-        self.InpuTot = np.hstack([self.Input, np.tile(inpMOR, reps=[len(self.Input), 1])])
+        if getattr(self, "_views", False):
+            self.InpuTot = TableView(self.Input, None, 1, inpMOR)           # the MOR columns stay constants
+        else:
+            self.InpuTot = np.hstack([self.Input, np.tile(inpMOR, reps=[len(self.Input), 1])])
         self.biInpuTot = np.hstack([self.biInput, np.tile(inpMOR, reps=[len(self.biInput), 1])])
         for key, attr in (('biLabel', 'biLabel'), ('gcoef', 'gcoef'), ('source', 'sourceVal'), ('diff', 'diff'),
                           ('vel', 'vel')):
@@ -208,16 +257,43 @@ class ManageTrainData:
         """Yield (batch, tower, bInd, point indices) in the reference's order: batches outer,
         towers inner, contiguous runs of `batchLen` test functions (VarNetUtility.py:829-838)."""
         n1 = 0
+        views = getattr(self, "_views", False)
+        cache = self.__dict__.setdefault("_tf_cache", {})
         for bi in range(self.batchNum):
             for tower in self.compTowers:
                 n0, n1 = n1, min(n1 + self.batchLen, self.nt)
                 bInd = self.batchInd[n0:n1]
-                pts = self.integInd[bInd, :].reshape(-1)
+                if views:
+                    # one index-list object per slice and shuffle epoch, shared by every field's TableView
+                    key = (n0, n1, getattr(self, "_tf_version", 0))
+                    if key not in cache:
+                        for old in [k for k in cache if k[:2] == (n0, n1)]:
+                            del cache[old]
+                        cache[key] = bInd.copy()
+                    bInd = cache[key]
+                pts = self.integInd[bInd, :].reshape(-1) if not (views and self.integNum % 4 == 0) else None
                 yield bi, tower, bInd, pts
 
     @staticmethod
     def _local(tower):
         return getattr(tower, "local", True)
+
+    def _take_tf(self, table, bInd):
+        """Per-test-function table (vector detJ) restricted to bInd."""
+        if getattr(self, "_views", False) and self.integNum % 4 == 0:
+            return TableView(table, bInd, 1)
+        return table[bInd, :]
+
+    def _take(self, table, bInd, pts):
+        """Rows of a per-point table for the test functions bInd: a lazy TableView when the backend keeps
+        tables resident, else the reference's host gather `table[pts, :]`."""
+        if getattr(self, "_views", False) and self.integNum % 4 == 0:
+            if isinstance(table, TableView):
+                return table.take(bInd, self.integNum)
+            return TableView(table, bInd, self.integNum)
+        if isinstance(table, TableView):
+            table = table.materialize()
+        return table[pts, :]
 
     def trainDicts(self, fixData, tfData):
         if hasattr(self, 'optimFeedicts'):
@@ -238,24 +314,25 @@ class ManageTrainData:
         self.nt, self.integNum, self.puNum = nt, integNum, puNum
         self.batchNum, self.batchLen = batchNum, batchLen
         self.compTowers = tfData.compTowers
+        self._views = bool(getattr(tfData, "supports_table_views", False))
         feeds = [dict() for _ in range(batchNum)]
         for bi, tw, bInd, pts in self._slices():
             if not self._local(tw):
                 continue            # another rank owns this tower: do not materialise its slice
             fd = feeds[bi]
-            fd[tw.Input] = InpuTot[pts, :]
+            fd[tw.Input] = self._take(InpuTot, bInd, pts)
             fd[tw.biInput] = biInpuTot
             fd[tw.biLabel] = biLabel
-            fd[tw.gcoef] = gcoef[pts, :]
-            fd[tw.source] = sourceVal[pts, :]
-            fd[tw.N] = fixData.N[pts, :]
+            fd[tw.gcoef] = self._take(gcoef, bInd, pts)
+            fd[tw.source] = self._take(sourceVal, bInd, pts)
+            fd[tw.N] = self._take(fixData.N, bInd, pts)
             fd[tw.bDof] = fixData.bDofsum
             fd[tw.intShape] = [len(bInd), integNum]
             fd[tw.integW] = fixData.integW
             fd[tw.biDimVal] = fixData.biDimVal
             fd[tw.detJvec] = fixData.detJvec
-            fd[tw.dNt] = fixData.dNt[pts, :] if fixData.timeDependent else fixData.dNt
-            fd[tw.detJ] = fixData.detJ[bInd, :] if fixData.detJvec else fixData.detJ
+            fd[tw.dNt] = self._take(fixData.dNt, bInd, pts) if fixData.timeDependent else fixData.dNt
+            fd[tw.detJ] = self._take_tf(fixData.detJ, bInd) if fixData.detJvec else fixData.detJ
         self.optimFeedicts = feeds
 
     def updateDictFields(self, fieldnames, trainW=None, normalizeW=True):
@@ -281,11 +358,11 @@ class ManageTrainData:
             fd = feeds[bi]
             self._update_shared(fd, tw, fieldnames, trainW)
             if 'InpuTot' in fieldnames:
-                fd[tw.Input] = self.InpuTot[pts, :]
+                fd[tw.Input] = self._take(self.InpuTot, bInd, pts)
             if 'gcoef' in fieldnames:
-                fd[tw.gcoef] = self.gcoef[pts, :]
+                fd[tw.gcoef] = self._take(self.gcoef, bInd, pts)
             if 'source' in fieldnames:
-                fd[tw.source] = self.sourceVal[pts, :]
+                fd[tw.source] = self._take(self.sourceVal, bInd, pts)
 
     def _update_shared(self, fd, tw, fieldnames, trainW):
         if 'trainW' in fieldnames:
@@ -301,6 +378,7 @@ class ManageTrainData:
             raise ValueError('first call trainDicts() to create the training dictionaries!')
         InpuTot, biInpuTot, biLabel, gcoef, sourceVal = self.getTrainData()
         np.random.shuffle(self.batchInd)
+        self._tf_version = getattr(self, "_tf_version", 0) + 1
         biInd = np.arange(len(biLabel))
         feeds = self.optimFeedicts
         for bi, tw, bInd, pts in self._slices():
@@ -310,14 +388,15 @@ class ManageTrainData:
             fd = feeds[bi]
             fd[tw.biInput] = biInpuTot[biInd, :]
             fd[tw.biLabel] = biLabel[biInd, :]
-            fd[tw.Input] = InpuTot[pts, :]
-            fd[tw.gcoef] = gcoef[pts, :]
-            fd[tw.source] = sourceVal[pts, :]
-            if fixData.detJvec:
-                fd[tw.N] = fixData.N[pts, :]
+            fd[tw.Input] = self._take(InpuTot, bInd, pts)
+            fd[tw.gcoef] = self._take(gcoef, bInd, pts)
+            fd[tw.source] = self._take(sourceVal, bInd, pts)
+            if fixData.detJvec or self._views:
+                fd[tw.N] = self._take(fixData.N, bInd, pts)
                 if fixData.timeDependent:
-                    fd[tw.dNt] = fixData.dNt[pts, :]
-                fd[tw.detJ] = fixData.detJ[bInd, :]
+                    fd[tw.dNt] = self._take(fixData.dNt, bInd, pts)
+            if fixData.detJvec:
+                fd[tw.detJ] = self._take_tf(fixData.detJ, bInd)
 
     # ---- session drivers ------------------------------------------------------------------
     def optimIter(self, tfData):

@@ -22,7 +22,7 @@ import numpy as np
 from .backend import TFNN, GlobalInit
 from .hostutil import (is_empty, is_none, is_number, l2_err, pair_rows, rejection_sampling, split_rows,
                        stack_rows)
-from .tables import FIXData, ManageTrainData
+from .tables import FIXData, ManageTrainData, TableView
 
 
 class TrainLog:
@@ -369,7 +369,11 @@ class VarNet:
                     gcoef = (diff0 if diff is None else diff) * fd.dNx + (vel0 if vel is None else vel) * fd.N
             else:
                 gcoef = src = diff = vel = None
-        if MORinpNN is not None:
+        if MORinpNN is not None and not resCalc and getattr(self.tfData, 'supports_table_views', False):
+            tData._views = True
+            InpuTot = TableView(Input, None, 1, MORinpNN)                   # MOR columns stay per-batch constants
+            biInpuTot = np.hstack([biInput, np.tile(MORinpNN, reps=[int(np.sum(fd.biDof)), 1])])
+        elif MORinpNN is not None:
             InpuTot = np.hstack([Input, np.tile(MORinpNN, reps=[nT, 1])])
             biInpuTot = [] if resCalc else np.hstack([biInput, np.tile(MORinpNN, reps=[int(np.sum(fd.biDof)), 1])])
         else:
