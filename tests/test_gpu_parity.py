@@ -167,3 +167,56 @@ def test_indexed_batch_and_extra_inputs_equal_materialised_upload(dvec):
     l1 = a.train_step(1e-3); l2 = a.train_step(1e-3)
     assert np.isfinite(l1) and np.isfinite(l2)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_c_abi_error_behaviour():
+    """Error conventions of the boundary: int status + message, mirroring the reference's ValueError /
+    'trainDicts must be called first' sites (TFModel.py:117-134, VarNetUtility.py:1031-1032)."""
+    from varnet_b200._capi import Engine, EngineError
+    eng = Engine(1, 2, [8], "sigmoid", True)
+    with pytest.raises(EngineError, match="must be called first"):
+        eng.loss_grad()
+    with pytest.raises(EngineError, match="must be called first"):
+        eng.train_step(1e-3)
+    with pytest.raises(EngineError, match="parameter count mismatch"):
+        eng.set_params(np.zeros(3, dtype=np.float32))
+    rng = np.random.RandomState(0)
+    feed = synth_feed(rng, 1, 2, 8, 6, 10, 6)                        # integNum = 6: not a multiple of 4
+    eng.set_params(go.glorot_init(2, [8], seed=0))
+    eng.upload_points(feed["Input"], feed["gcoef"], None, None, feed["dNt"], feed["intShape"], None, feed["detJ"])
+    with pytest.raises(EngineError, match="must be called first"):   # BC/IC rows still missing
+        eng.loss()
+    eng.upload_bic(feed["biInput"], feed["biLabel"], 6, 2.0)
+    with pytest.raises(EngineError, match="multiple of 4"):
+        eng.set_batch(np.arange(4))
+    with pytest.raises(EngineError, match="learning rate must be positive"):
+        eng.train_step(-1.0)
+    with pytest.raises(EngineError, match="dNt is required"):
+        eng.upload_points(feed["Input"], feed["gcoef"], None, None, None, feed["intShape"], None, feed["detJ"])
+    out = eng.loss_grad()                                             # engine still usable after the errors
+    ref = go.loss_and_grad(go.glorot_init(2, [8], seed=0), dict(feed, w=np.ones(3)), dim=1, inpDim=2, layerWidth=[8],
+                           activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    assert abs(float(out["loss"]) - ref["loss"]) <= TOL * abs(ref["loss"])
+    with pytest.raises(EngineError, match="exceeds the compiled kernel families"):
+        Engine(2, 3, [256, 256], "tanh", True)
+    deep = Engine(2, 3, [64] * 7, "tanh", True)                       # deep 64-wide nets use the 32-point-tile class
+    assert "class=164" in deep.kernel_info()
+    deep.close(); eng.close()
+
+
+@pytest.mark.gpu
+def test_deep_and_ragged_networks_match_oracle():
+    rng = np.random.RandomState(31)
+    for dim, inpDim, lw, act in ((2, 3, [64] * 6, "tanh"), (1, 2, [5, 64, 3, 17, 40], "sigmoid")):
+        feed = synth_feed(rng, dim, inpDim, 45, 16, 33, 20)
+        theta = go.glorot_init(inpDim, lw, seed=5)
+        kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation=act, timeDependent=True,
+                  lossOpt=dict(isSource=False, integWflag=False))
+        ref = go.loss_and_grad(theta, feed, **kw)
+        eng = make_engine(feed, theta=theta, **kw)
+        out = eng.loss_grad()
+        assert abs(float(out["loss"]) - ref["loss"]) <= TOL * abs(ref["loss"])
+        for name, sl in layer_slices(inpDim, lw):
+            assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
+        eng.close()
