@@ -342,6 +342,23 @@ def lossvec_tolerance(res, rel=2e-6):
     return res["detJ"] * (2.0 * np.abs(res["R"]) * dR + dR * dR)
 
 
+def bout_tolerance(res, feed, timeDependent, rel=2e-6, base=1e-5):
+    """Conditioning-aware bound for the gradient of the output bias.  g(b_out) contains
+    sum_p ubar_p = -sum_i lambda_i sum_q w_q dNt_iq, a cancelling sum (on the reference's tables
+    sum_q dNt_iq = 0 exactly), so an FP32 evaluation can only deliver it to eps32-level relative to
+    sum_p |ubar_p|.  Allowed: base * |g| + rel * sum_p |ubar_p|  (ubar = -lambda dNt,
+    lambda = 2 w2 detJ_i w_q R_i, App. A.3)."""
+    if not timeDependent:
+        return base * abs(float(res["grad"][-1]))
+    nb, integNum = [int(v) for v in feed["intShape"]]
+    dNt = np.abs(np.asarray(feed["dNt"], dtype=np.float64).reshape(nb, integNum))
+    wq = np.ones((1, integNum)) if feed.get("integW") is None else np.abs(np.asarray(feed["integW"], dtype=np.float64).reshape(1, integNum))
+    w2 = float(np.asarray(feed["w"], dtype=np.float64).reshape(3)[2])
+    detJ = np.asarray(res["detJ"], dtype=np.float64).reshape(-1, 1) * np.ones((nb, 1))
+    lam = 2.0 * w2 * detJ * np.abs(np.asarray(res["R"], dtype=np.float64).reshape(nb, 1))
+    return base * abs(float(res["grad"][-1])) + rel * float(np.sum(lam * wq * dNt))
+
+
 def varloss_tolerance(res, rel=2e-6, base=1e-5):
     """Bound for the summed variational loss on ill-conditioned (real) tables: the 1e-5 relative
     bar plus the worst-case accumulation of the per-test-function FP32 conditioning bound."""

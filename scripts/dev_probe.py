@@ -31,6 +31,10 @@ def run(nb, lw, act, dim=2, inpDim=3, integNum=64, reps=5):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    if len(sys.argv) > 1 and sys.argv[1] == "tc":
+        run(1 << 14, [256] * 4, "tanh", reps=3)
+        run(1 << 14, [128] * 4, "tanh", reps=3)
+        sys.exit(0)
     run(1 << 16, [64] * 4, "tanh")
     run(1 << 16, [10, 20], "sigmoid")
     run(1 << 16, [16] * 4, "tanh")

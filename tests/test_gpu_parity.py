@@ -203,7 +203,7 @@ def test_c_abi_error_behaviour():
                            activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
     assert abs(float(out["loss"]) - ref["loss"]) <= TOL * abs(ref["loss"])
     with pytest.raises(EngineError, match="exceeds the compiled kernel families"):
-        Engine(2, 3, [256, 256], "tanh", True)
+        Engine(2, 3, [300, 300], "tanh", True)
     deep = Engine(2, 3, [64] * 7, "tanh", True)                       # deep 64-wide nets use the 32-point-tile class
     assert "class=164" in deep.kernel_info()
     deep.close(); eng.close()

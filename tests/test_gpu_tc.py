@@ -1,0 +1,145 @@
+"""GPU parity of the tensor-core kernel class (hidden width 65..256: tcgen05 3xTF32 layer GEMMs, vn_tc.cu)
+against the FP64 oracle, through the C ABI.  Same bar as the FMA classes: 1e-5 relative for the loss, its
+components, lossVec and every gradient tensor; the output-bias gradient (a single cancelling sum) uses the
+conditioning-aware bound of oracle.graph_oracle.bout_tolerance."""
+import numpy as np
+import pytest
+
+from oracle import graph_oracle as go
+from tests.util import synth_feed, make_engine, rel_inf, layer_slices
+
+TOL = 1e-5
+
+CASES = [
+    # dim inpDim layers               act       td     src    iw     dvec   nb   integNum nbi  bDof
+    (2, 3, [128, 128], "tanh", True, False, False, False, 40, 64, 300, 200),
+    (1, 2, [100, 256, 130], "sigmoid", True, True, False, False, 70, 16, 150, 100),     # ragged widths, 1D+t
+    (2, 3, [256, 256, 256, 256], "tanh", True, False, False, False, 700, 64, 3000, 2000),  # width-sweep 256 net
+    (2, 5, [80], "tanh", True, False, True, True, 33, 36, 70, 40),                       # one layer, MOR-like inputs, detJ vector
+    (2, 2, [96, 72], "sigmoid", False, True, False, False, 53, 16, 60, 60),              # steady 2D, no IC rows
+    (1, 3, [65, 200], "tanh", True, True, True, False, 29, 216, 129, 100),               # integNum 216 (chunk = lcm with 128)
+]
+
+
+def check_against_oracle(eng, ref, feed, inpDim, lw, td):
+    fwd = eng.loss(lossVec=True)
+    for k in ("loss", "BCloss", "ICloss", "varLoss"):
+        assert abs(float(fwd[k]) - ref[k]) <= TOL * abs(ref[k]) + 1e-30, (k, fwd[k], ref[k])
+    assert rel_inf(fwd["lossVec"], ref["lossVec"]) <= TOL
+    out = eng.loss_grad()
+    for k in ("loss", "BCloss", "ICloss", "varLoss"):
+        assert abs(float(out[k]) - ref[k]) <= TOL * abs(ref[k]) + 1e-30, (k, out[k], ref[k])
+    slices = layer_slices(inpDim, lw)
+    for name, sl in slices[:-1]:
+        assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
+    assert abs(float(out["grad"][-1]) - float(ref["grad"][-1])) <= go.bout_tolerance(ref, feed, td), "output bias"
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[str(c[2]) + c[3] + ("_d%d" % c[0]) for c in CASES])
+def test_tensor_core_class_matches_oracle(case):
+    dim, inpDim, lw, act, td, src, iw, dvec, nb, integNum, nbi, bDof = case
+    rng = np.random.RandomState(4321 + nb)
+    feed = synth_feed(rng, dim, inpDim, nb, integNum, nbi, bDof, td, src, iw, dvec)
+    theta = go.glorot_init(inpDim, lw, seed=7) + 0.05 * rng.randn(go.param_count(inpDim, lw)).astype(np.float32)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation=act, timeDependent=td, lossOpt=dict(isSource=src, integWflag=iw))
+    ref = go.loss_and_grad(theta, feed, **kw)
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        assert "family=tcgen05-3xtf32" in eng.kernel_info()
+        check_against_oracle(eng, ref, feed, inpDim, lw, td)
+        assert eng.launch_count() > 0
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_many_chunks_and_eval(monkeypatch):
+    """One 128-point tile per SM and chunk: the step runs over several chunks (last one ragged) and the FP64
+    accumulation across chunks reproduces the single-pass oracle; vn_eval goes through the same pipeline."""
+    monkeypatch.setenv("VARNET_B200_TC_WAVES", "1")
+    rng = np.random.RandomState(77)
+    dim, inpDim, lw = 2, 3, [128, 96, 128]
+    feed = synth_feed(rng, dim, inpDim, 700, 64, 2500, 1700)            # 44800 points > 2 x 18944
+    theta = go.glorot_init(inpDim, lw, seed=3)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    ref = go.loss_and_grad(theta, feed, **kw)
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        assert "chunk=18944" in eng.kernel_info()
+        check_against_oracle(eng, ref, feed, inpDim, lw, True)
+        X = rng.uniform(-1, 1, (20011, inpDim))
+        u = eng.eval(X)
+        refu = go.mlp_value(theta.astype(np.float64), X.astype(np.float32).astype(np.float64), inpDim, lw, go.ACT_TANH)
+        assert rel_inf(u, refu) <= TOL
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_forced_tensor_core_class_agrees_with_fma_class(monkeypatch):
+    """Width 64 through both kernel families (VARNET_B200_CLASS=tc pads 64 -> 128): the crossover measurement
+    of the width sweep compares like with like."""
+    rng = np.random.RandomState(5)
+    dim, inpDim, lw = 2, 3, [64, 64, 64, 64]
+    feed = synth_feed(rng, dim, inpDim, 300, 64, 333, 200)
+    theta = go.glorot_init(inpDim, lw, seed=3)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    outs = {}
+    for kind in ("fma", "tc"):
+        monkeypatch.setenv("VARNET_B200_CLASS", kind)
+        eng = make_engine(feed, theta=theta, **kw)
+        try:
+            assert ("tcgen05" in eng.kernel_info()) == (kind == "tc")
+            outs[kind] = eng.loss_grad()
+        finally:
+            eng.close()
+    for k in ("loss", "BCloss", "ICloss", "varLoss"):
+        assert abs(float(outs["tc"][k]) - float(outs["fma"][k])) <= TOL * abs(float(outs["fma"][k]))
+    for name, sl in layer_slices(inpDim, lw)[:-1]:
+        assert rel_inf(outs["tc"]["grad"][sl], outs["fma"]["grad"][sl]) <= TOL, name
+
+
+@pytest.mark.gpu
+def test_training_trajectory_and_minibatch_index_list():
+    """Adam steps on the tensor-core class follow the oracle's TF-Adam trajectory; a device-resident index list
+    (vn_set_batch) selects test functions of the resident table like a host-side gather."""
+    rng = np.random.RandomState(9)
+    dim, inpDim, lw = 1, 2, [160, 160]
+    nb, integNum = 96, 16
+    feed = synth_feed(rng, dim, inpDim, nb, integNum, 120, 80)
+    theta = go.glorot_init(inpDim, lw, seed=11)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        th = theta.astype(np.float64); m = np.zeros_like(th); v = np.zeros_like(th)
+        for t in range(1, 4):
+            ref = go.loss_and_grad(th.astype(np.float32), feed, **kw)
+            loss = eng.train_step(1e-3)
+            assert abs(float(loss) - ref["loss"]) <= 5e-5 * abs(ref["loss"])
+            th, m, v = go.adam_step(th, ref["grad"], m, v, t)
+        assert rel_inf(eng.get_params(), th) <= 1e-4
+        # mini-batch: 40 of the 96 test functions through the on-device index list
+        idx = rng.permutation(nb)[:40]
+        eng.set_params(theta)
+        eng.set_batch(idx)
+        rows = (idx[:, None] * integNum + np.arange(integNum)[None, :]).ravel()
+        sub = dict(feed, Input=feed["Input"][rows], gcoef=feed["gcoef"][rows], dNt=feed["dNt"][rows], source=feed["source"][rows],
+                   N=feed["N"][rows], intShape=[40, integNum])
+        ref = go.loss_and_grad(theta, sub, **kw)
+        check_against_oracle(eng, ref, sub, inpDim, lw, True)
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_tensor_core_class_limits():
+    from varnet_b200._capi import Engine, EngineError
+    with pytest.raises(EngineError, match="exceeds the compiled kernel families"):
+        Engine(2, 3, [300, 300], "tanh", True)
+    eng = Engine(2, 3, [256, 256], "tanh", True)
+    eng.set_params(go.glorot_init(3, [256, 256], seed=0))
+    with pytest.raises(EngineError, match="strong-form residual"):
+        eng.residual(np.zeros((4, 3)), 1e-3, np.zeros((4, 2)), np.zeros((4, 2)), 0.0)
+    eng.close()

@@ -12,6 +12,7 @@
 
 #include "../../include/varnet_b200.h"
 #include "vn_dispatch.h"
+#include "vn_tc.h"
 #include <utility>
 
 // ------------------------------------------------------------------ errors
@@ -267,6 +268,9 @@ struct vn_engine {
     vn_config cfg;
     NetDesc net;
     int S = 0, wclass = 0, numSMs = 0;
+    // tensor-core class (wclass == 256): chunk workspace, FP64 gradient accumulator [nparam | loss sum], barrier-timeout flag
+    TcGeom tcGeom{};
+    DevBuf tcWork, tcAcc, tcErr;
     bool fused = false;          // per-test-function residual reduced inside the adjoint kernel (integNum | TP)
     cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
     cudaStream_t ownStream = nullptr;
@@ -369,11 +373,28 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     e->t = e->slots[0];
     build_net(*cfg, &e->net);
     e->S = 1 + cfg->dim;
-    if (wmax > 64) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=64)", wmax); }
+    if (wmax > 256) { delete e; return fail(VN_E_UNSUPPORTED, "hidden width %d exceeds the compiled kernel families (<=256)", wmax); }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     e->numSMs = prop.multiProcessorCount;
     const int L = cfg->nLayers, act = cfg->act;
+    const char* forceCls = getenv("VARNET_B200_CLASS");            // "tc": tensor-core class for any width (crossover measurements)
+    if (wmax > 64 || (forceCls && !strcmp(forceCls, "tc"))) {
+        // tensor-core class: tcgen05 3xTF32 layer GEMMs, activations of a chunk streamed through global memory (vn_tc.h)
+        e->wclass = 256;
+        if (!vn_tc_geometry(e->net, e->S, e->numSMs, &e->tcGeom)) { delete e; return fail(VN_E_UNSUPPORTED, "no compiled kernel for this configuration"); }
+        if (e->tcGeom.smemGemm > prop.sharedMemPerBlockOptin || e->tcGeom.smemGw > prop.sharedMemPerBlockOptin) {
+            delete e; return fail(VN_E_UNSUPPORTED, "tensor-core class needs %zu B of shared memory per CTA", e->tcGeom.smemGemm);
+        }
+        cudaError_t ce = vn_tc_prepare(e->S, act);
+        if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
+        e->resOK = false;            // strong-form residual (second derivatives) is only built for the resident-tile classes
+        e->graphOK = false;          // thousands of launches per step: plain stream launches
+        CK(e->tcWork.ensure(e->tcGeom.workBytes));
+        CK(e->tcAcc.ensure((size_t)(e->net.nparam + 2) * sizeof(double)));
+        CK(e->tcErr.ensure(sizeof(int)));
+        CK(cudaMemset(e->tcErr.p, 0, sizeof(int)));
+    } else {
     e->wclass = wmax <= 32 ? 32 : 64;
     if (e->wclass == 64) {       // deep 64-wide networks: the weights of all layers no longer fit next to 64-point tiles
         TileGeom probe;
@@ -401,6 +422,7 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         cudaError_t ce = vn_tile_prepare(S, e->wclass, act, modes[k], gs[k]->smemBytes);
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
     }
+    }
     const int np = e->net.nparam;
     CK(e->theta.ensure(np * sizeof(float)));
     CK(e->m.ensure(np * sizeof(float)));
@@ -427,7 +449,8 @@ extern "C" int vn_destroy(vn_engine* e) {
     for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
-                      &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut};
+                      &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
+                      &e->tcWork, &e->tcAcc, &e->tcErr};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -519,6 +542,7 @@ static int ensure_work(vn_engine* e) {
     CK(e->lossVec.ensure((size_t)std::max<unsigned>(e->nb, 1) * sizeof(float)));
     const int nSeg = (int)((e->nb + 255) / 256);
     CK(e->segSum.ensure((size_t)std::max(nSeg, 1) * sizeof(double)));
+    if (e->wclass == 256) { e->fused = false; e->gridVar = 0; return VN_OK; }     // tensor-core class: chunk workspace is fixed at creation
     const long long tilesAdj = (P + e->gVarAdj.TP - 1) / e->gVarAdj.TP;
     e->gridVar = (int)std::max<long long>(1, std::min<long long>(tilesAdj, e->numSMs));
     CK(e->partVar.ensure((size_t)e->numSMs * e->gVarAdj.pl.psz * sizeof(double)));
@@ -709,6 +733,7 @@ static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64
     CK(cudaGetLastError());
     e->launches += 2;
     CK(cudaStreamSynchronize(e->stream));
+    if (e->wclass == 256) { e->gridBic = 0; return VN_OK; }
     const long long tiles = e->bstride / e->gBicAdj.TP;
     e->gridBic = (int)std::min<long long>(tiles, e->numSMs);
     CK(e->partBic.ensure((size_t)e->gridBic * e->gBicAdj.pl.psz * sizeof(double)));
@@ -767,6 +792,49 @@ static void bic_args(const vn_engine* e, TileArgs* a) {
     a->cj = e->cj.as<float>();
 }
 
+// tensor-core class: chunked layer pipeline (vn_tc.cu), FP64 accumulation of the gradient across chunks
+static int run_loss_tc(vn_engine* e, bool needGrad) {
+    const vn_config& c = e->cfg;
+    cudaStream_t st = e->stream;
+    const int np = e->net.nparam;
+    double* acc = e->tcAcc.as<double>();
+    CK(cudaMemsetAsync(acc, 0, (size_t)(np + 2) * sizeof(double), st));
+    CK(vn_tc_stage_weights(e->net, e->tcGeom, e->theta.as<float>(), e->tcWork.p, st));
+    e->launches++;
+    TcJob j;
+    j.act = c.act; j.geom = e->tcGeom; j.needGrad = needGrad; j.work = e->tcWork.p; j.g64 = acc; j.lossAcc = acc + np;
+    j.err = e->tcErr.as<int>(); j.st = st; j.numSMs = e->numSMs;
+    {
+        j.S = e->S; j.mode = TC_VAR;
+        var_args(e, &j.in);
+        ProfScope ps(e, PK_VAR_ADJ);
+        cudaError_t ce = vn_tc_run(j);
+        if (ce != cudaSuccess) return fail(VN_E_CUDA, "tensor-core pipeline (variational term): %s", cudaGetErrorString(ce));
+        e->launches += j.launches;
+    }
+    {
+        j.S = 1; j.mode = TC_BIC;
+        bic_args(e, &j.in);
+        ProfScope ps(e, PK_BIC);
+        cudaError_t ce = vn_tc_run(j);
+        if (ce != cudaSuccess) return fail(VN_E_CUDA, "tensor-core pipeline (boundary/initial rows): %s", cudaGetErrorString(ce));
+        e->launches += j.launches;
+    }
+    ProfScope ps(e, PK_FINAL);
+    if (needGrad) { CK(vn_tc_grad_out(acc, e->gbuf.as<float>(), np, st)); e->launches++; }
+    FinalArgs f;
+    memset(&f, 0, sizeof(f));
+    f.net = e->net;
+    f.segSum = acc + np; f.nSeg = 1;
+    f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
+    f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
+    f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = 0;
+    vn_finalize_kernel<<<1, 128, 0, st>>>(f);         // loss scalars only
+    CK(cudaGetLastError());
+    e->launches++;
+    return VN_OK;
+}
+
 static int run_loss(vn_engine* e, bool needGrad) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (!e->P || !e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
@@ -776,6 +844,7 @@ static int run_loss(vn_engine* e, bool needGrad) {
     const vn_config& c = e->cfg;
     CK(cudaSetDevice(c.device));
     cudaStream_t st = e->stream;
+    if (e->wclass == 256) return run_loss_tc(e, needGrad);
     TileArgs a;
     var_args(e, &a);
     int nSeg = (int)((e->nb + 255) / 256);
@@ -858,7 +927,10 @@ static int run_loss(vn_engine* e, bool needGrad) {
 
 static int read_scalars(vn_engine* e, float out[4]) {
     CK(cudaMemcpyAsync(out, e->gbuf.as<float>() + e->net.nparam, 4 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    int tcErr = 0;
+    if (e->wclass == 256) CK(cudaMemcpyAsync(&tcErr, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (tcErr) return fail(VN_E_CUDA, "tensor-core pipeline: an mbarrier wait expired (results invalid)");
     return VN_OK;
 }
 
@@ -984,10 +1056,20 @@ static int eval_impl(vn_engine* e, const T* X, int64_t n, float* u) {
     base_args(e, &a);
     a.cols = e->evalCols.as<float>(); a.pstride = stride; a.colX = 0; a.colT = -1; a.colS = -1;
     a.P = (unsigned int)n; a.uout = e->evalOut.as<float>();
+    if (e->wclass == 256) {
+        CK(vn_tc_stage_weights(e->net, e->tcGeom, e->theta.as<float>(), e->tcWork.p, e->stream));
+        TcJob j;
+        j.S = 1; j.act = c.act; j.mode = TC_EVAL; j.geom = e->tcGeom; j.in = a; j.needGrad = false; j.work = e->tcWork.p;
+        j.g64 = e->tcAcc.as<double>(); j.lossAcc = j.g64 + e->net.nparam; j.err = e->tcErr.as<int>(); j.st = e->stream; j.numSMs = e->numSMs;
+        cudaError_t ce = vn_tc_run(j);
+        if (ce != cudaSuccess) return fail(VN_E_CUDA, "tensor-core pipeline (evaluation): %s", cudaGetErrorString(ce));
+        e->launches += j.launches + 2;
+    } else {
     const TileGeom& g = e->gEval;
     a.ntiles = (int)(stride / g.TP);
     CK(vn_tile_launch(1, e->wclass, c.act, MODE_EVAL, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, e->stream));
     e->launches += 2;
+    }
     CK(cudaMemcpyAsync(u, e->evalOut.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return VN_OK;
@@ -1066,6 +1148,12 @@ extern "C" int vn_profile_read(vn_engine* e, double ms[VN_PROF_SLOTS], int64_t c
 
 extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
     if (!e || !buf) return fail(VN_E_INVALID, "null argument");
+    if (e->wclass == 256) {
+        snprintf(buf, n, "family=tcgen05-3xtf32 class=256 S=%d L=%d WP=%d chunk=%u points gemm(tile=128x128,smem=%zu) gw(smem=%zu) "
+                 "workspace=%zuB nparam=%d SMs=%d", e->S, e->net.L, e->tcGeom.WP, e->tcGeom.capPts, e->tcGeom.smemGemm,
+                 e->tcGeom.smemGw, e->tcGeom.workBytes, e->net.nparam, e->numSMs);
+        return VN_OK;
+    }
     snprintf(buf, n,
              "family=fp32-fma-tile class=%d S=%d L=%d var_fwd(TP=%d,NT=%d,smem=%zu) var_adj(TP=%d,NT=%d,smem=%zu,grid=%d,%s,"
              "stash=%lldB/CTA) bic_adj(TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",

@@ -1,0 +1,979 @@
+// vn_tc.cu — tensor-core kernel class (see vn_tc.h): tcgen05.mma kind::tf32 with the 3xTF32 split,
+// accumulators in TMEM, operands staged in shared memory in the no-swizzle K-major canonical layout
+// (8 rows x 16 bytes core matrices; validated by scripts/micro/tc_probe.cu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <algorithm>
+#include "vn_tc.h"
+
+namespace {
+
+constexpr int TM = 128;         // rows (points, or input neurons in tc_gw) per CTA tile == TMEM lanes
+constexpr int TN = 128;         // columns (neurons) per CTA tile
+constexpr int NTHR = 256;        // loader / epilogue threads (8 warps)
+constexpr int NTHR_ALL = NTHR + 32;   // + one MMA-issuing warp
+constexpr int KC = 32;           // K floats per pipeline stage (one 128-byte row segment per operand row)
+constexpr uint32_t TILE_SBO = 128;                  // bytes between 8-row groups
+// bytes between 16-byte K units: 128 rows x 16 B, plus one 16-byte pad so that the eight K units of one row
+// fall into eight different bank groups (the loader writes a row's 128-byte segment with one quarter-warp)
+constexpr uint32_t TILE_LBO = (TM / 8) * 128 + 16;
+constexpr int TILE_BYTES = (KC / 4) * TILE_LBO;
+constexpr int NST = 3;                               // pipeline stages
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A hi, A lo, B hi, B lo
+constexpr int BAR_OFF = NST * STAGE_BYTES;         // mbarriers: full[NST] (256 loader arrivals), empty[NST] and done (tcgen05.commit)
+constexpr int SMEM_BYTES = BAR_OFF + 128;
+constexpr uint32_t TMEM_COLS = 512;                  // four 128-column accumulator sets: three rotating main sets + the small terms
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                  // start address        [0,14)
+    d |= (uint64_t)((TILE_LBO >> 4) & 0x3FFF) << 16;         // leading byte offset  [16,30)
+    d |= (uint64_t)((TILE_SBO >> 4) & 0x3FFF) << 32;         // stride byte offset   [32,46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
+    return d;                                                // no swizzle, base offset 0
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t dTmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dTmem), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// bounded wait (a lost commit must not hang the GPU): false on timeout
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 18) && !done; ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <uint32_t NCOL>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOL) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOL>
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOL) : "memory");
+}
+
+// ------------------------------------------------------------------ operand tiles
+// One tile = 128 rows x KC floats of a row-major, K-contiguous FP32 matrix, loaded by 256 threads: a quarter
+// warp reads one whole 128-byte row segment (4 full lines per warp request) and, after the split, writes its
+// eight 16-byte K units of that row conflict free (padded TILE_LBO).
+struct TileRegs { float4 v[TM * (KC / 4) / NTHR]; };
+
+__device__ __forceinline__ void tile_load(const float* __restrict__ src, size_t ld, TileRegs& r, int tid) {
+    constexpr int K4 = KC / 4, U = TM * K4 / NTHR;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const int u = i * NTHR + tid;
+        const int k4 = u % K4, row = u / K4;
+        r.v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + k4 * 4));
+    }
+}
+// round to the 10-bit TF32 mantissa (the tensor core itself truncates: a truncated split leaves a one-sided
+// 2^-21 bias per product that grows with K; rounding both halves makes the residual 2^-22 and sign-symmetric)
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned char* hiTile, unsigned char* loTile, int tid) {
+    constexpr int K4 = KC / 4, U = TM * K4 / NTHR;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const int u = i * NTHR + tid;
+        const int k4 = u % K4, row = u / K4;
+        const uint32_t off = k4 * TILE_LBO + row * 16;
+        const float4 v = r.v[i];
+        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+        *reinterpret_cast<float4*>(hiTile + off) = h;
+        *reinterpret_cast<float4*>(loTile + off) = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+    }
+}
+
+// MMAs of one K chunk.  The tensor core accumulates with truncation, a one-sided error of ~0.25 ulp of the
+// accumulator per MMA (measured: error grows linearly with the chain length), so the chains are kept short:
+// the two small products lo*hi, hi*lo go to their own column set (magnitude 2^-11: their truncation is
+// harmless) and hi*hi of K block kb goes to the main set chosen by `mainSet(kb, fresh)`; the sets are summed
+// in FP32 (round to nearest) by the epilogue.
+template <class F>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t stageAddr, bool firstChunk, F&& mainSet) {
+    const uint32_t aHi = stageAddr, aLo = stageAddr + TILE_BYTES, bHi = stageAddr + 2 * TILE_BYTES, bLo = stageAddr + 3 * TILE_BYTES;
+#pragma unroll
+    for (int kb = 0; kb < KC / 8; ++kb) {
+        const uint64_t dAh = make_desc(aHi + kb * 2 * TILE_LBO), dAl = make_desc(aLo + kb * 2 * TILE_LBO);
+        const uint64_t dBh = make_desc(bHi + kb * 2 * TILE_LBO), dBl = make_desc(bLo + kb * 2 * TILE_LBO);
+        mma_tf32(tmem + 3 * TN, dAl, dBh, (firstChunk && kb == 0) ? 0u : 1u);
+        mma_tf32(tmem + 3 * TN, dAh, dBl, 1u);
+        bool fresh = false;
+        const int set = mainSet(kb, fresh);
+        mma_tf32(tmem + set * TN, dAh, dBh, fresh ? 0u : 1u);
+    }
+}
+
+// barriers: full[b] = all 256 loader threads stored (and proxy-fenced) their part of stage b; empty[b] = the MMAs
+// that read stage b completed (tcgen05.commit); done = every MMA of the tile completed
+struct Bars {
+    uint32_t full, empty, done;         // shared-space addresses; full + 8*b, empty + 8*b
+};
+__device__ __forceinline__ uint32_t pipe_setup(unsigned char* smem, int tid, int warp, Bars& bars) {
+    uint64_t* bp = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 8 * (2 * NST + 1));
+    bars.full = smem_u32(bp); bars.empty = smem_u32(bp + NST); bars.done = smem_u32(bp + 2 * NST);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) { mbar_init(bars.full + 8 * i, NTHR); mbar_init(bars.empty + 8 * i, 1); }
+        mbar_init(bars.done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<TMEM_COLS>(tslot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *tslot;
+}
+
+// Loader side of one K chunk (256 threads): wait until the MMAs that read this stage three chunks ago are done,
+// write the split tiles, put the chunk after next in flight, publish the stage to the MMA warp.
+template <class FA, class FB>
+__device__ __forceinline__ void loader_step(unsigned char* smem, const Bars& bars, int it, int nIt, TileRegs& ra, TileRegs& rb,
+                                            FA&& srcA, FB&& srcB, size_t ldA, size_t ldB, int tid, bool& ok) {
+    const int b = it % NST;
+    unsigned char* stage = smem + b * STAGE_BYTES;
+    if (it >= NST && ok) ok = mbar_wait(bars.empty + 8 * b, (uint32_t)((it / NST) - 1) & 1u);
+    tile_store_split(ra, stage, stage + TILE_BYTES, tid);
+    tile_store_split(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
+    if (it + 2 < nIt) {
+        tile_load(srcA(it + 2), ldA, ra, tid);
+        tile_load(srcB(it + 2), ldB, rb, tid);
+    }
+    fence_async_smem();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+    mbar_arrive(bars.full + 8 * b);
+}
+// MMA warp (one elected lane): consume the stages in order
+template <class F>
+__device__ __forceinline__ bool mma_warp_loop(unsigned char* smem, const Bars& bars, uint32_t tmem, int nIt, F&& mainSetOf) {
+    bool ok = true;
+    for (int it = 0; it < nIt; ++it) {
+        const int b = it % NST;
+        if (ok) ok = mbar_wait(bars.full + 8 * b, (uint32_t)(it / NST) & 1u);
+        tc_fence_after();
+        issue_chunk(tmem, smem_u32(smem + b * STAGE_BYTES), it == 0, [&](int kb, bool& fresh) { return mainSetOf(it, kb, fresh); });
+        mma_commit(bars.empty + 8 * b);
+    }
+    mma_commit(bars.done);
+    return ok;
+}
+
+// ------------------------------------------------------------------ layer GEMM (forward / adjoint), one stream per launch
+enum { EPI_FWD_VALUE = 0, EPI_FWD_TANGENT = 1, EPI_ADJ_TANGENT = 2, EPI_ADJ_VALUE = 3 };
+
+struct GemmArgs {
+    const float* A; int ldA;                // this stream's operand [rows][ldA], K contiguous
+    const float* B; int ldB;                // [N][K] row-major (K contiguous), zero padded
+    int K;                                  // multiple of KC
+    int nTilesN;
+    const float* bias; int widthOut;        // FWD_VALUE
+    const float* val; int ldVal;            // FWD_TANGENT: a of this layer; ADJ_*: a of the layer below   (point-major)
+    const float* tan;                       // ADJ_TANGENT: tangent activation of the layer below, this stream (ldVal)
+    float* cross; int crossMode;            // ADJ_TANGENT: 0 = write, 1 = accumulate; ADJ_VALUE: 1 = read, 0 = no tangent streams
+    float* outPm; int ldOut;                // [p][ldOut]
+    float* outNm; unsigned int ldNm;        // [n][ldNm]
+    int* err;
+};
+
+__device__ __forceinline__ void ld16(const float* __restrict__ src, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+
+template <int EPI, int ACT>
+__global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (*reinterpret_cast<volatile int*>(a.err)) return;                      // an earlier launch lost a barrier: do not spin again
+    const int mt = blockIdx.x / a.nTilesN, nt = blockIdx.x - mt * a.nTilesN;
+    const size_t m0 = (size_t)mt * TM;
+    const int n0 = nt * TN;
+    Bars bars;
+    const uint32_t tmem = pipe_setup(smem, tid, warp, bars);
+    const int nIt = a.K / KC;
+
+    if (warp == NTHR / 32) {
+        // ---- MMA warp: the main chain rotates over three column sets (chains of <= K/24 MMAs)
+        if (lane == 0) {
+            const bool ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
+                const int kbg = it * (KC / 8) + kb;
+                fresh = kbg < 3;
+                return kbg % 3;
+            });
+            if (!ok) *a.err = 1;
+        }
+    } else {
+        // ---- loaders, then epilogue: thread = one point (TMEM lane), warps 0-3 / 4-7 take the two column halves
+        const float* Ag = a.A + m0 * a.ldA;
+        const float* Bg = a.B + (size_t)n0 * a.ldB;
+        auto srcA = [&](int it) { return Ag + (size_t)it * KC; };
+        auto srcB = [&](int it) { return Bg + (size_t)it * KC; };
+        TileRegs ra[2], rb[2];                                                // two K chunks in flight
+        tile_load(srcA(0), a.ldA, ra[0], tid); tile_load(srcB(0), a.ldB, rb[0], tid);
+        if (nIt > 1) { tile_load(srcA(1), a.ldA, ra[1], tid); tile_load(srcB(1), a.ldB, rb[1], tid); }
+        bool ok = true;
+#pragma unroll 1
+        for (int it0 = 0; it0 < nIt; it0 += 2) {
+            loader_step(smem, bars, it0, nIt, ra[0], rb[0], srcA, srcB, a.ldA, a.ldB, tid, ok);
+            if (it0 + 1 < nIt) loader_step(smem, bars, it0 + 1, nIt, ra[1], rb[1], srcA, srcB, a.ldA, a.ldB, tid, ok);
+        }
+
+        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+        const size_t prow = m0 + row;
+        const int nb = n0 + half * 64;                                        // first of this thread's 64 columns
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
+        // epilogue operands of all 64 columns are requested before the accumulators are complete
+        float av[EPI == EPI_FWD_VALUE ? 1 : 64], xv[(EPI == EPI_ADJ_TANGENT || EPI == EPI_ADJ_VALUE) ? 64 : 1];
+        if (EPI != EPI_FWD_VALUE) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) ld16(a.val + prow * a.ldVal + nb + cb * 16, reinterpret_cast<float(&)[16]>(av[cb * 16 % (EPI == EPI_FWD_VALUE ? 1 : 64)]));
+        }
+        if (EPI == EPI_ADJ_TANGENT) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) ld16(a.tan + prow * a.ldVal + nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]));
+        }
+        if (EPI == EPI_ADJ_VALUE && a.crossMode) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) ld16(a.cross + prow * a.ldOut + nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_VALUE ? 64 : 1)]));
+        }
+        if (ok) ok = mbar_wait(bars.done, 0u);
+        if (!ok) *a.err = 1;
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const int n = nb + cb * 16;
+            float z[16], t1[16], t2[16], t3[16];
+            tmem_ld16(tlane + cb * 16, z);
+            tmem_ld16(tlane + TN + cb * 16, t1);
+            tmem_ld16(tlane + 2 * TN + cb * 16, t2);
+            tmem_ld16(tlane + 3 * TN + cb * 16, t3);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) z[c] = (z[c] + t1[c]) + (t2[c] + t3[c]);     // FP32, round to nearest
+            if (EPI == EPI_FWD_VALUE) {
+                // a = act(z + b)   (App. A.2)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float bv = (n + c < a.widthOut) ? __ldg(a.bias + n + c) : 0.f;
+                    z[c] = act_f<ACT>(z[c] + bv);
+                }
+            } else if (EPI == EPI_FWD_TANGENT) {
+                // tangent stream: act'(z) * zdot, act' from the value a of this layer
+#pragma unroll
+                for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
+            } else if (EPI == EPI_ADJ_TANGENT) {
+                // dabar_k -> dzbar_k = dabar_k act'; its share of the second-order term: cross += dabar_k * adot_k   (App. A.3)
+                float* cp = a.cross + prow * a.ldOut + n;
+                if (a.crossMode) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) red_add_f32(cp + c, z[c] * xv[(cb * 16 + c) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        reinterpret_cast<float4*>(cp)[q] = make_float4(z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                                                       z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                                                       z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                                                       z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
+            } else {
+                // abar -> zbar = abar act' + act''/act' * cross
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float aa = av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)], d1 = act_d1<ACT>(aa);
+                    z[c] = a.crossMode ? fmaf(z[c], d1, act_d2r<ACT>(aa) * xv[(cb * 16 + c) % (EPI == EPI_ADJ_VALUE ? 64 : 1)]) : z[c] * d1;
+                }
+            }
+            float4* pm = reinterpret_cast<float4*>(a.outPm + prow * a.ldOut + n);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pm[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+            float* nm = a.outNm + (size_t)n * a.ldNm + prow;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);      // read once, much later (tc_gw): keep it out of the way in L2
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------ weight-gradient GEMM (split-K over points)
+struct GwArgs {
+    const float* A; size_t aStream;     // neuron-major activations of layer l-1: [s][i][ld]
+    const float* B; size_t bStream;     // neuron-major zbar of layer l:          [s][j][ld]
+    unsigned int ld;
+    int S;
+    unsigned int nPts, kPts;            // valid (padded to 128) points of the chunk; points per split (multiple of KC)
+    int tilesJ, nsplit;
+    double* g; int wi, wo;              // g[i*wo + j] += ...   for i < wi, j < wo
+    int* err;
+};
+
+// K runs over thousands of points: the main accumulator rotates over three column sets in epochs of GW_EPOCH
+// chunks and each set is drained into FP32 registers (round to nearest) two epochs later, when its MMAs have
+// long completed, so no truncating chain is longer than GW_EPOCH * KC / 8 MMAs and the pipeline never stalls.
+constexpr int GW_EPOCH = 4;
+
+__global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (*reinterpret_cast<volatile int*>(a.err)) return;
+    const int split = blockIdx.x % a.nsplit, tile = blockIdx.x / a.nsplit;
+    const int it_ = tile / a.tilesJ, jt = tile - it_ * a.tilesJ;
+    const unsigned int pBeg = (unsigned int)split * a.kPts;
+    if (pBeg >= a.nPts) return;
+    const unsigned int pEnd = min(pBeg + a.kPts, a.nPts);
+    const int chunks = (int)((pEnd - pBeg) / KC);
+    const int nIt = a.S * chunks;
+    Bars bars;
+    const uint32_t tmem = pipe_setup(smem, tid, warp, bars);
+
+    if (warp == NTHR / 32) {
+        if (lane == 0) {
+            const bool ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
+                fresh = (it % GW_EPOCH == 0) && kb == 0;
+                return (it / GW_EPOCH) % 3;
+            });
+            if (!ok) *a.err = 1;
+        }
+    } else {
+        const float* Ag = a.A + (size_t)(it_ * TM) * a.ld + pBeg;
+        const float* Bg = a.B + (size_t)(jt * TN) * a.ld + pBeg;
+        auto srcA = [&](int it) { const int s = it / chunks, pc = it - s * chunks; return Ag + s * a.aStream + (size_t)pc * KC; };
+        auto srcB = [&](int it) { const int s = it / chunks, pc = it - s * chunks; return Bg + s * a.bStream + (size_t)pc * KC; };
+        const int half = warp >> 2;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
+        float acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+        auto drain = [&](int set) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                float z[16];
+                tmem_ld16(tlane + set * TN + cb * 16, z);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[cb * 16 + c] += z[c];
+            }
+        };
+        TileRegs ra[2], rb[2];
+        tile_load(srcA(0), a.ld, ra[0], tid); tile_load(srcB(0), a.ld, rb[0], tid);
+        if (nIt > 1) { tile_load(srcA(1), a.ld, ra[1], tid); tile_load(srcB(1), a.ld, rb[1], tid); }
+        bool ok = true;
+#pragma unroll 1
+        for (int it0 = 0; it0 < nIt; it0 += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int it = it0 + h;
+                if (it < nIt) {
+                    if (it % GW_EPOCH == 0 && it >= 2 * GW_EPOCH) {
+                        // epoch e-2 is complete once the commit of chunk it-3 has been observed (GW_EPOCH + 1 >= NST)
+                        if (ok) ok = mbar_wait(bars.empty + 8 * (it % NST), (uint32_t)((it / NST) - 1) & 1u);
+                        tc_fence_after();
+                        drain(((it / GW_EPOCH) - 2) % 3);
+                        tc_fence_before();          // the set is overwritten by epoch e+1, whose first stage this thread publishes later
+                    }
+                    loader_step(smem, bars, it, nIt, ra[h], rb[h], srcA, srcB, a.ld, a.ld, tid, ok);
+                }
+            }
+        }
+        if (ok) ok = mbar_wait(bars.done, 0u);
+        if (!ok) *a.err = 1;
+        tc_fence_after();
+        const int nEp = (nIt + GW_EPOCH - 1) / GW_EPOCH;
+        for (int e = max(0, nEp - 2); e < nEp; ++e) drain(e % 3);           // the last two epochs were not drained in the loop
+        drain(3);                                                            // small terms
+
+        const int i = it_ * TM + (warp & 3) * 32 + lane;
+        if (ok && i < a.wi) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                const int j = jt * TN + half * 64 + c;
+                if (j < a.wo) atomicAdd(a.g + (size_t)i * a.wo + j, (double)acc[c]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------ FP32 kernels around the GEMMs
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;       // valid in thread 0
+}
+
+// zero-padded [WP][WP] copies of the hidden kernels: Wn[l-1][i][j] = W_l[i][j], Wt[l-1][j][i] = W_l[i][j]
+__global__ void tc_stage_weights_kernel(NetDesc net, int WP, const float* __restrict__ theta, float* __restrict__ Wn, float* __restrict__ Wt) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)WP * WP;
+    if (idx >= per * (net.L - 1)) return;
+    const int l = (int)(idx / per) + 1, r = (int)((idx % per) / WP), c = (int)(idx % WP);
+    const int wi = net.width[l - 1], wo = net.width[l];
+    Wn[idx] = (r < wi && c < wo) ? theta[net.woff[l] + r * wo + c] : 0.f;           // [in][out]
+    Wt[idx] = (c < wi && r < wo) ? theta[net.woff[l] + c * wo + r] : 0.f;           // [out][in]
+}
+
+struct L0Args {
+    TileArgs in; unsigned int base; int WP;
+    float* X; float* Apm; float* Anm; size_t sPm, sNm; unsigned int cap;
+};
+// layer 0 (K = inpDim): a = act(X W0 + b0), tangent k: act'(z) W0[k,:]; also keeps X of the chunk for g(W0)
+template <int S, int ACT>
+__global__ void __launch_bounds__(256) tc_layer0_kernel(const L0Args a) {
+    __shared__ float xs[VN_KIN][32];
+    __shared__ float tile[S][32][33];
+    const TileArgs& A = a.in;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned int p0 = blockIdx.x * 32; const int n0 = blockIdx.y * 32;
+    const int inpDim = A.net.inpDim;
+    if ((int)threadIdx.x < inpDim * 32) {
+        const int k = threadIdx.x >> 5, p = threadIdx.x & 31;
+        const unsigned int gp = a.base + p0 + p;
+        float x = 0.f;
+        if (gp < A.P) x = (k >= A.nxTable) ? __ldg(A.extraX + (k - A.nxTable)) : __ldg(A.cols + (size_t)(A.colX + k) * A.pstride + table_row(A, gp));
+        xs[k][p] = x;
+        if (blockIdx.y == 0) a.X[(size_t)k * a.cap + p0 + p] = x;
+    }
+    __syncthreads();
+    const int n = n0 + tx, w0 = A.net.width[0];
+    float w[VN_KIN], bv = 0.f;
+#pragma unroll
+    for (int k = 0; k < VN_KIN; ++k) w[k] = (k < inpDim && n < w0) ? __ldg(A.theta + A.net.woff[0] + k * w0 + n) : 0.f;
+    if (n < w0) bv = __ldg(A.theta + A.net.boff[0] + n);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int p = ty * 4 + r;
+        float z = bv;
+#pragma unroll
+        for (int k = 0; k < VN_KIN; ++k) z = fmaf(xs[k][p], w[k], z);
+        const float av = act_f<ACT>(z), d1 = act_d1<ACT>(av);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float o = s == 0 ? av : d1 * w[s - 1 < 0 ? 0 : s - 1];
+            a.Apm[s * a.sPm + (size_t)(p0 + p) * a.WP + n] = o;
+            tile[s][p][tx] = o;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int nn = ty * 4 + r;
+#pragma unroll
+        for (int s = 0; s < S; ++s) a.Anm[s * a.sNm + (size_t)(n0 + nn) * a.cap + p0 + tx] = tile[s][tx][nn];
+    }
+}
+
+struct OutArgs {
+    TileArgs in; unsigned int base, nPts; int WP; bool needGrad;
+    const float* Alast; size_t sPm;
+    float* U; float* seeds; unsigned int cap; double* g64;
+};
+// output layer (Dense(1), linear): u_s = A_{L-1,s} . w_out (+ b_out); then per mode the integrand
+// (TFModel.py:653-660), the BC/IC residual and its seed (TFModel.py:643-650), or the model value
+template <int S, int MODE>
+__global__ void __launch_bounds__(256) tc_out_kernel(const OutArgs a) {
+    __shared__ double sh[8];
+    const TileArgs& A = a.in;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int p = blockIdx.x * 8 + warp;
+    const int L = A.net.L, wlast = A.net.width[L - 1];
+    const float* wout = A.theta + A.net.woff[L];
+    float seedv = 0.f;
+    if (p < a.nPts) {
+        float u[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float* row = a.Alast + s * a.sPm + (size_t)p * a.WP;
+            float acc = 0.f;
+            for (int n = lane * 4; n < wlast; n += 128) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row + n));
+                acc = fmaf(v.x, __ldg(wout + n), acc);
+                if (n + 1 < wlast) acc = fmaf(v.y, __ldg(wout + n + 1), acc);
+                if (n + 2 < wlast) acc = fmaf(v.z, __ldg(wout + n + 2), acc);
+                if (n + 3 < wlast) acc = fmaf(v.w, __ldg(wout + n + 3), acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            u[s] = acc;
+        }
+        u[0] += __ldg(A.theta + A.net.boff[L]);
+        const unsigned int gp = a.base + p;
+        if (lane == 0) {
+            if (MODE == TC_VAR) {
+                float I = 0.f;
+                if (gp < A.P) {
+                    const size_t row = table_row(A, gp);
+#pragma unroll
+                    for (int k = 0; k < S - 1; ++k) I = fmaf(u[1 + k], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
+                    if (A.timeDependent) I -= u[0] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
+                    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+                    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+                    A.Iw[gp] = I;
+                }
+            } else if (MODE == TC_BIC) {
+                if (gp < A.P) {
+                    const float r = u[0] - __ldg(A.label + gp);
+                    A.cj[gp] = A.biDimVal * r * r;
+                    float sc;                                   // mean over boundary rows / initial rows (TFModel.py:644-648)
+                    if (gp < A.bDof) sc = __ldg(A.wts + 0) / (float)A.bDof;
+                    else sc = A.timeDependent ? __ldg(A.wts + 1) / (float)(A.P - A.bDof) : 0.f;
+                    seedv = 2.f * A.biDimVal * r * sc;
+                }
+                a.seeds[p] = seedv;
+            } else {
+                if (gp < A.P) A.uout[gp] = u[0];
+            }
+        }
+    }
+    if (MODE == TC_BIC && a.needGrad) {
+        const double t = block_sum_d(lane == 0 ? (double)seedv : 0.0, sh);
+        if (threadIdx.x == 0 && t != 0.0) atomicAdd(a.g64 + A.net.boff[L], t);       // g(b_out) = sum of seeds
+    }
+}
+
+struct SeedArgs {
+    TileArgs in; unsigned int tf0, nTf, base; bool needGrad;
+    float* seeds; unsigned int cap; double* lossAcc; double* g64;
+};
+// per test function: R_i = sum_q I_iq, lossVec_i = detJ_i R_i^2 (TFModel.py:659-668); adjoint seeds
+// lambda = 2 w2 detJ_i w_q R_i, ubar = -lambda dNt, ubar_k = lambda gcoef_k (App. A.3)
+template <int S>
+__global__ void __launch_bounds__(256) tc_seed_kernel(const SeedArgs a) {
+    __shared__ double sh[8];
+    const TileArgs& A = a.in;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int b = blockIdx.x * 8 + warp;
+    double lossv = 0.0, sb = 0.0;
+    if (b < a.nTf) {
+        const unsigned int i = a.tf0 + b;
+        float r = 0.f;
+        for (unsigned int q = lane; q < A.integNum; q += 32) r += A.Iw[(size_t)i * A.integNum + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
+        if (lane == 0) {
+            const float r2 = r * r;
+            A.R[i] = r;
+            A.lossVec[i] = dj * r2;
+            lossv = A.detJvec ? (double)dj * (double)r2 : (double)r2;
+        }
+        if (a.needGrad) {
+            const float w2 = __ldg(A.wts + 2);
+            for (unsigned int q = lane; q < A.integNum; q += 32) {
+                const unsigned int gp = i * A.integNum + q, p = gp - a.base;
+                const size_t row = table_row(A, gp);
+                const float wq = A.integW ? __ldg(A.integW + q) : 1.f;
+                const float lam = 2.f * w2 * dj * wq * r;
+                const float s0 = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + row) : 0.f;
+                a.seeds[p] = s0;
+                sb += (double)s0;
+#pragma unroll
+                for (int k = 0; k < S - 1; ++k)
+                    a.seeds[(size_t)(1 + k) * a.cap + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
+            }
+        }
+    }
+    const double tl = block_sum_d(lossv, sh);
+    if (threadIdx.x == 0) atomicAdd(a.lossAcc, tl);
+    if (a.needGrad) {
+        const double tb = block_sum_d(sb, sh);
+        if (threadIdx.x == 0) atomicAdd(a.g64 + A.net.boff[A.net.L], tb);
+    }
+}
+
+struct TopArgs {
+    int WP, wlast; const float* wout;
+    const float* Apm; size_t sPm; const float* seeds; unsigned int cap;
+    float* Dpm; float* Dnm; size_t sNm; double* gwout;
+};
+// top of the adjoint: zbar_{L-1} from the seeds (outer product with w_out), g(w_out)
+template <int S, int ACT>
+__global__ void __launch_bounds__(256) tc_top_kernel(const TopArgs a) {
+    __shared__ float tile[S][32][33];
+    __shared__ float red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned int p0 = blockIdx.x * 32; const int n0 = blockIdx.y * 32;
+    const int n = n0 + tx;
+    const float wv = n < a.wlast ? __ldg(a.wout + n) : 0.f;
+    float gacc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int pl = ty * 4 + r;
+        const size_t p = p0 + pl;
+        const float av = a.Apm[p * a.WP + n], d1 = act_d1<ACT>(av);
+        const float s0 = a.seeds[p];
+        float cross = 0.f;
+        gacc = fmaf(av, s0, gacc);
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            const float da = a.Apm[s * a.sPm + p * a.WP + n], sd = a.seeds[(size_t)s * a.cap + p];
+            const float ab = sd * wv;
+            gacc = fmaf(da, sd, gacc);
+            cross = fmaf(ab, da, cross);
+            const float o = ab * d1;
+            a.Dpm[s * a.sPm + p * a.WP + n] = o;
+            tile[s][pl][tx] = o;
+        }
+        const float zb = fmaf(s0 * wv, d1, act_d2r<ACT>(av) * cross);
+        a.Dpm[p * a.WP + n] = zb;
+        tile[0][pl][tx] = zb;
+    }
+    red[ty][tx] = gacc;
+    __syncthreads();
+    if (ty == 0 && n < a.wlast) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][tx];
+        atomicAdd(a.gwout + n, (double)t);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int nn = ty * 4 + r;
+#pragma unroll
+        for (int s = 0; s < S; ++s) a.Dnm[s * a.sNm + (size_t)(n0 + nn) * a.cap + p0 + tx] = tile[s][tx][nn];
+    }
+}
+
+struct RowArgs {
+    const float* Dnm; size_t sNm; unsigned int cap, nPts, len;   // len: points per split (multiple of 128)
+    int rows, width, splits, first; const float* X; int inpDim;
+    double* gb; double* gw0;        // gb[j]; gw0[k*width + j] (layer 0 only)
+};
+// bias gradients g(b_l)[j] = sum_p zbar_l[p][j]; for layer 0 also g(W_0)[k][j] = sum_p X[p][k] zbar_0[p][j]
+// plus, for the tangent streams, sum_p dzbar_0^k[p][j] added to row k   (App. A.3, l = 0)
+__global__ void __launch_bounds__(256) tc_rowsum_kernel(const RowArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= a.rows * a.splits) return;
+    const int rowi = w / a.splits, split = w - rowi * a.splits;
+    const int s = rowi / a.width, j = rowi - s * a.width;
+    const unsigned int pBeg = (unsigned int)split * a.len, pEnd = min(pBeg + a.len, a.nPts);
+    if (pBeg >= pEnd) return;
+    const float* d = a.Dnm + s * a.sNm + (size_t)j * a.cap;
+    const bool dots = a.first && s == 0;
+    float sum = 0.f, dot[VN_KIN];
+#pragma unroll
+    for (int k = 0; k < VN_KIN; ++k) dot[k] = 0.f;
+    for (unsigned int p = pBeg + lane * 4; p < pEnd; p += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(d + p);
+        sum += (v.x + v.y) + (v.z + v.w);
+        if (dots) {
+#pragma unroll
+            for (int k = 0; k < VN_KIN; ++k)
+                if (k < a.inpDim) {
+                    const float4 x = *reinterpret_cast<const float4*>(a.X + (size_t)k * a.cap + p);
+                    dot[k] = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, dot[k]))));
+                }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (dots) {
+#pragma unroll
+        for (int k = 0; k < VN_KIN; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+    }
+    if (lane == 0) {
+        if (s == 0) atomicAdd(a.gb + j, (double)sum);
+        else atomicAdd(a.gw0 + (size_t)(s - 1) * a.width + j, (double)sum);
+        if (dots)
+            for (int k = 0; k < a.inpDim; ++k) atomicAdd(a.gw0 + (size_t)k * a.width + j, (double)dot[k]);
+    }
+}
+
+__global__ void tc_grad_out_kernel(const double* __restrict__ g, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)g[i];
+}
+
+// ------------------------------------------------------------------ host side
+struct Work {
+    float *Wn, *Wt, *X, *Apm, *Anm, *Dpm, *Dnm, *U, *seeds, *cross;
+    size_t sPm, sNm, layerStride, bytes;
+};
+Work carve(void* base, int L, int S, int WP, unsigned int cap) {
+    Work w;
+    size_t off = 0;
+    auto take = [&](size_t nfloats) { float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; };
+    w.sPm = (size_t)cap * WP; w.sNm = (size_t)WP * cap; w.layerStride = (size_t)S * w.sPm;
+    w.Wn = take((size_t)std::max(L - 1, 1) * WP * WP);
+    w.Wt = take((size_t)std::max(L - 1, 1) * WP * WP);
+    w.X = take((size_t)VN_KIN * cap);
+    w.Apm = take((size_t)L * w.layerStride);
+    w.Anm = take((size_t)L * w.layerStride);
+    w.Dpm = take(2 * w.layerStride);
+    w.Dnm = take(2 * w.layerStride);
+    w.U = take((size_t)S * cap);
+    w.seeds = take((size_t)S * cap);
+    w.cross = take(w.sPm);
+    w.bytes = off;
+    return w;
+}
+
+template <int EPI> cudaError_t launch_gemm(int act, const GemmArgs& g, int grid, cudaStream_t st) {
+    if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
+    else tc_gemm_kernel<EPI, VN_TANH><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
+    return cudaGetLastError();
+}
+template <int EPI> cudaError_t prep_gemm() {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+template <int S> cudaError_t launch_layer0(int act, const L0Args& a, dim3 grid, cudaStream_t st) {
+    if (act == VN_SIGMOID) tc_layer0_kernel<S, VN_SIGMOID><<<grid, 256, 0, st>>>(a);
+    else tc_layer0_kernel<S, VN_TANH><<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+template <int S> cudaError_t launch_top(int act, const TopArgs& a, dim3 grid, cudaStream_t st) {
+    if (act == VN_SIGMOID) tc_top_kernel<S, VN_SIGMOID><<<grid, 256, 0, st>>>(a);
+    else tc_top_kernel<S, VN_TANH><<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define TC_S_SWITCH(S, CALL)                \
+    ((S) == 1 ? CALL(1) : ((S) == 2 ? CALL(2) : CALL(3)))
+
+unsigned int gcd_u(unsigned int a, unsigned int b) { while (b) { const unsigned int t = a % b; a = b; b = t; } return a; }
+
+}  // namespace
+
+bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
+    int wmax = 0;
+    for (int l = 0; l < net.L; ++l) wmax = std::max(wmax, net.width[l]);
+    if (wmax > 256 || S < 1 || S > 3) return false;
+    g->WP = wmax <= 128 ? 128 : 256;
+    int waves = 4;                                                   // 128-point tiles per SM and chunk
+    if (const char* w = getenv("VARNET_B200_TC_WAVES")) waves = std::max(1, std::min(16, atoi(w)));
+    g->capPts = (unsigned int)numSMs * TM * waves;
+    g->workBytes = carve(nullptr, net.L, S, g->WP, g->capPts).bytes;
+    g->smemGemm = SMEM_BYTES;
+    g->smemGw = SMEM_BYTES;
+    return true;
+}
+
+cudaError_t vn_tc_prepare(int S, int act) {
+    (void)S; (void)act;
+    cudaError_t e = cudaFuncSetAttribute(tc_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    if ((e = prep_gemm<EPI_FWD_VALUE>()) != cudaSuccess) return e;
+    if ((e = prep_gemm<EPI_FWD_TANGENT>()) != cudaSuccess) return e;
+    if ((e = prep_gemm<EPI_ADJ_TANGENT>()) != cudaSuccess) return e;
+    return prep_gemm<EPI_ADJ_VALUE>();
+}
+
+cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float* theta, void* work, cudaStream_t st) {
+    if (net.L < 2) return cudaSuccess;
+    const Work w = carve(work, net.L, 1, g.WP, g.capPts);             // Wn / Wt come first: independent of S
+    const long long n = (long long)(net.L - 1) * g.WP * g.WP;
+    tc_stage_weights_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(net, g.WP, theta, w.Wn, w.Wt);
+    return cudaGetLastError();
+}
+
+cudaError_t vn_tc_grad_out(const double* g64, float* gbuf, int n, cudaStream_t st) {
+    tc_grad_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(g64, gbuf, n);
+    return cudaGetLastError();
+}
+
+#define TCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t vn_tc_run(TcJob& j) {
+    const TileArgs& A = j.in;
+    const NetDesc& net = A.net;
+    const int L = net.L, S = j.S, WP = j.geom.WP, act = j.act;
+    const unsigned int cap = j.geom.capPts;
+    const Work w = carve(j.work, L, S, WP, cap);
+    // the staged weights are carved with S = 1 by vn_tc_stage_weights: same offsets (they precede every S-dependent block)
+    cudaStream_t st = j.st;
+    j.launches = 0;
+
+    // chunk size: whole test functions, whole 128-point tiles
+    unsigned int chunk = cap;
+    if (j.mode == TC_VAR) {
+        const unsigned int base = A.integNum / gcd_u(A.integNum, TM) * TM;       // lcm(integNum, 128)
+        if (base > cap) return cudaErrorInvalidValue;
+        chunk = cap / base * base;
+    }
+    const int tilesW[2] = {1, 1};
+    (void)tilesW;
+    for (unsigned long long c0 = 0; c0 < A.P; c0 += chunk) {
+        const unsigned int base = (unsigned int)c0;
+        const unsigned int valid = (unsigned int)std::min<unsigned long long>(chunk, A.P - c0);
+        const unsigned int nPts = (valid + TM - 1) / TM * TM;
+        const int mTiles = (int)(nPts / TM);
+
+        // ---- layer 0
+        {
+            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Apm = w.Apm; a.Anm = w.Anm; a.sPm = w.sPm; a.sNm = w.sNm; a.cap = cap;
+            const dim3 grid(nPts / 32, WP / 32);
+#define CALL(SS) launch_layer0<SS>(act, a, grid, st)
+            TCK(TC_S_SWITCH(S, CALL));
+#undef CALL
+            j.launches++;
+        }
+        // ---- hidden layers 1..L-1 (forward): value stream first, the tangent streams need act' of its output
+        for (int l = 1; l < L; ++l) {
+            for (int sidx = 0; sidx < S; ++sidx) {
+                GemmArgs g{};
+                g.A = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm; g.ldA = WP;
+                g.B = w.Wt + (size_t)(l - 1) * WP * WP; g.ldB = WP;
+                g.K = (net.width[l - 1] + KC - 1) / KC * KC;
+                g.nTilesN = (net.width[l] + TN - 1) / TN;
+                g.bias = A.theta + net.boff[l]; g.widthOut = net.width[l];
+                g.val = w.Apm + (size_t)l * w.layerStride; g.ldVal = WP;
+                g.outPm = w.Apm + (size_t)l * w.layerStride + sidx * w.sPm; g.ldOut = WP;
+                g.outNm = w.Anm + (size_t)l * w.layerStride + sidx * w.sNm; g.ldNm = cap;
+                g.err = j.err;
+                if (sidx == 0) TCK(launch_gemm<EPI_FWD_VALUE>(act, g, mTiles * g.nTilesN, st));
+                else TCK(launch_gemm<EPI_FWD_TANGENT>(act, g, mTiles * g.nTilesN, st));
+                j.launches++;
+            }
+        }
+        // ---- output layer + integrand / BC-IC residual / value
+        {
+            OutArgs a; a.in = A; a.base = base; a.nPts = nPts; a.WP = WP; a.needGrad = j.needGrad;
+            a.Alast = w.Apm + (size_t)(L - 1) * w.layerStride; a.sPm = w.sPm; a.U = w.U; a.seeds = w.seeds; a.cap = cap; a.g64 = j.g64;
+            const unsigned int grid = (nPts + 7) / 8;
+            if (j.mode == TC_VAR) {
+#define CALL(SS) (tc_out_kernel<SS, TC_VAR><<<grid, 256, 0, st>>>(a), cudaGetLastError())
+                TCK(TC_S_SWITCH(S, CALL));
+#undef CALL
+            } else if (j.mode == TC_BIC) {
+                tc_out_kernel<1, TC_BIC><<<grid, 256, 0, st>>>(a);
+                TCK(cudaGetLastError());
+            } else {
+                tc_out_kernel<1, TC_EVAL><<<grid, 256, 0, st>>>(a);
+                TCK(cudaGetLastError());
+            }
+            j.launches++;
+        }
+        if (j.mode == TC_EVAL) continue;
+        if (j.mode == TC_VAR) {
+            if (j.needGrad) TCK(cudaMemsetAsync(w.seeds, 0, (size_t)S * cap * sizeof(float), st));
+            SeedArgs a; a.in = A; a.tf0 = base / A.integNum; a.nTf = valid / A.integNum; a.base = base; a.needGrad = j.needGrad;
+            a.seeds = w.seeds; a.cap = cap; a.lossAcc = j.lossAcc; a.g64 = j.g64;
+            const unsigned int grid = (a.nTf + 7) / 8;
+#define CALL(SS) (tc_seed_kernel<SS><<<grid, 256, 0, st>>>(a), cudaGetLastError())
+            TCK(TC_S_SWITCH(S, CALL));
+#undef CALL
+            j.launches++;
+        }
+        if (!j.needGrad) continue;
+
+        // ---- top of the adjoint: D_{L-1}
+        int cur = 0;
+        {
+            TopArgs a; a.WP = WP; a.wlast = net.width[L - 1]; a.wout = A.theta + net.woff[L];
+            a.Apm = w.Apm + (size_t)(L - 1) * w.layerStride; a.sPm = w.sPm; a.seeds = w.seeds; a.cap = cap;
+            a.Dpm = w.Dpm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
+            const dim3 grid(nPts / 32, WP / 32);
+#define CALL(SS) launch_top<SS>(act, a, grid, st)
+            TCK(TC_S_SWITCH(S, CALL));
+#undef CALL
+            j.launches++;
+        }
+        auto rowsum = [&](int l, int curBuf) -> cudaError_t {
+            RowArgs r;
+            r.Dnm = w.Dnm + (size_t)curBuf * w.layerStride; r.sNm = w.sNm; r.cap = cap; r.nPts = nPts;
+            r.first = (l == 0); r.rows = (l == 0 ? S : 1) * net.width[l]; r.width = net.width[l];
+            r.splits = std::max(1, std::min<int>((int)(nPts / 1024), (8 * j.numSMs * 8) / std::max(r.rows, 1)));
+            r.len = ((nPts + r.splits - 1) / r.splits + TM - 1) / TM * TM;
+            r.X = w.X; r.inpDim = net.inpDim;
+            r.gb = j.g64 + net.boff[l]; r.gw0 = j.g64 + net.woff[0];
+            const int warps = r.rows * r.splits;
+            tc_rowsum_kernel<<<(warps + 7) / 8, 256, 0, st>>>(r);
+            j.launches++;
+            return cudaGetLastError();
+        };
+        for (int l = L - 1; l >= 1; --l) {
+            TCK(rowsum(l, cur));
+            // gW_l from (A_{l-1}, D_l)
+            {
+                GwArgs g{};
+                g.A = w.Anm + (size_t)(l - 1) * w.layerStride; g.aStream = w.sNm;
+                g.B = w.Dnm + (size_t)cur * w.layerStride; g.bStream = w.sNm;
+                g.ld = cap; g.S = S; g.nPts = nPts;
+                const int tilesI = (net.width[l - 1] + TM - 1) / TM;
+                g.tilesJ = (net.width[l] + TN - 1) / TN;
+                const int tiles = tilesI * g.tilesJ;
+                g.nsplit = std::max(1, std::min<int>(j.numSMs / tiles, (int)(nPts / 256)));
+                g.kPts = ((nPts + g.nsplit - 1) / g.nsplit + KC - 1) / KC * KC;
+                g.g = j.g64 + net.woff[l]; g.wi = net.width[l - 1]; g.wo = net.width[l];
+                g.err = j.err;
+                tc_gw_kernel<<<tiles * g.nsplit, NTHR_ALL, SMEM_BYTES, st>>>(g);
+                TCK(cudaGetLastError());
+                j.launches++;
+            }
+            // D_{l-1} = through act'/act'' of layer l-1 of (D_l W_l^T): tangent streams first (they build the
+            // second-order term `cross`), then the value stream
+            for (int sidx = S - 1; sidx >= 0; --sidx) {
+                GemmArgs g{};
+                g.A = w.Dpm + (size_t)cur * w.layerStride + sidx * w.sPm; g.ldA = WP;
+                g.B = w.Wn + (size_t)(l - 1) * WP * WP; g.ldB = WP;
+                g.K = (net.width[l] + KC - 1) / KC * KC;
+                g.nTilesN = (net.width[l - 1] + TN - 1) / TN;
+                g.val = w.Apm + (size_t)(l - 1) * w.layerStride; g.ldVal = WP;
+                g.tan = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm;
+                g.cross = w.cross;
+                g.outPm = w.Dpm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sPm; g.ldOut = WP;
+                g.outNm = w.Dnm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sNm; g.ldNm = cap;
+                g.err = j.err;
+                if (sidx > 0) { g.crossMode = (sidx == S - 1) ? 0 : 1; TCK(launch_gemm<EPI_ADJ_TANGENT>(act, g, mTiles * g.nTilesN, st)); }
+                else { g.crossMode = S > 1 ? 1 : 0; TCK(launch_gemm<EPI_ADJ_VALUE>(act, g, mTiles * g.nTilesN, st)); }
+                j.launches++;
+            }
+            cur ^= 1;
+        }
+        TCK(rowsum(0, cur));
+    }
+    return cudaSuccess;
+}

@@ -1,0 +1,48 @@
+// vn_tc.h — tensor-core kernel class (hidden width 65..256): tcgen05 3xTF32 layer GEMMs.
+//
+// The resident-tile FMA classes (vn_tile.cuh) keep the weights and three operand buffers of a point tile in
+// shared memory; at width 128/256 neither fits (one 256x256 layer is 256 KB).  At those widths the hidden
+// layers are real dense contractions (TFModel.py:208-242 Dense layers; 3.5 MFLOP per quadrature point for
+// 4x256), so this class runs them on the 5th-generation tensor cores and streams the activations of a chunk
+// of points through global memory (L2/HBM: ~150 flop/B, far above the ridge).  One chunk = ~2 waves of
+// 128-point tiles; per chunk and layer the step is
+//   forward   Z_s = A_{l-1,s} W_l             tc_gemm<EPI_FWD>   (epilogue: bias, act, act' * tangent)
+//   adjoint   abar_s = D_{l,s} W_l^T          tc_gemm<EPI_ADJ>   (epilogue: through act'/act'' of layer l-1)
+//   gradient  gW_l = sum_{s,p} A_{l-1,s}^T D_{l,s}   tc_gw       (split-K over points, FP64 atomics)
+// with FP32 accuracy from the 3xTF32 split x = hi + lo (hi*hi + lo*hi + hi*lo, FP32 accumulation in TMEM).
+// Layer 0 (K = inpDim <= 8), the output layer, the integrand / per-test-function residual and the bias
+// gradients are plain FP32 kernels.  Math: SURVEY.md App. A (TFModel.py:515-714).
+#pragma once
+#include "vn_tile.cuh"
+
+enum { TC_VAR = 0, TC_BIC = 1, TC_EVAL = 2 };
+
+struct TcGeom {
+    int WP;                 // padded hidden width (128 or 256)
+    unsigned int capPts;    // chunk capacity in points (multiple of 128)
+    size_t workBytes;       // workspace for one chunk (activations in both layouts, adjoint ping-pong, staged weights)
+    size_t smemGemm, smemGw;
+};
+
+// false when the network is outside this class (width > 256)
+bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g);
+cudaError_t vn_tc_prepare(int S, int act);          // opt-in shared memory attributes of the kernels used
+
+struct TcJob {
+    int S, act, mode;
+    TcGeom geom;
+    TileArgs in;            // rows to process: table columns, P, integNum, tfIndex, extraX, labels, outputs (R, lossVec, Iw, cj, uout)
+    bool needGrad;
+    void* work;             // geom.workBytes
+    double* g64;            // [nparam] FP64 gradient accumulator, reference variable order (caller zeroes it once per step)
+    double* lossAcc;        // sum_i (detJ_i) R_i^2 (TC_VAR; caller zeroes it)
+    int* err;               // device flag: set to 1 when a bounded mbarrier wait expired
+    cudaStream_t st;
+    int numSMs;
+    long long launches;     // out: kernels launched
+};
+
+// theta -> zero-padded [WP][WP] copies of the hidden kernels (natural and transposed) inside the workspace
+cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float* theta, void* work, cudaStream_t st);
+cudaError_t vn_tc_run(TcJob& j);
+cudaError_t vn_tc_grad_out(const double* g64, float* gbuf, int n, cudaStream_t st);
