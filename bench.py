@@ -35,6 +35,9 @@ WORKLOADS = {
     "synthetic_2dt_1e6x64_mlp4x64_tanh": (100, 100, 100, (64, 64, 64, 64), "tanh"),
     "synthetic_2dt_1e6x64_mlp4x16_tanh": (100, 100, 100, (16, 16, 16, 16), "tanh"),
     "synthetic_2dt_small_mlp4x64_tanh": (40, 40, 25, (64, 64, 64, 64), "tanh"),
+    # width sweep (BASELINE.json configs[4]): widths above 64 run on the tensor-core class (tcgen05 3xTF32)
+    "synthetic_2dt_1e6x64_mlp4x128_tanh": (100, 100, 100, (128, 128, 128, 128), "tanh"),
+    "synthetic_2dt_1e6x64_mlp4x256_tanh": (100, 100, 100, (256, 256, 256, 256), "tanh"),
 }
 DEFAULT = "synthetic_2dt_1e6x64_mlp4x64_tanh"
 METRIC = "weak-form residual+grad quad-pts/sec"
@@ -72,8 +75,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(hbm_gbs=p.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=p.get("hbm_gbs", 6650.0), bf16_tflops=p.get("bf16_tflops_sustained", p.get("bf16_tflops", 2250.0)),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=2250.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -138,7 +142,7 @@ def run_cpu(args, nx, ny, ntime, lw, act, steps, warmup, budget_s=None):
     from oracle import torch_oracle, graph_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_tf = 4096 if len(lw) and max(lw) >= 64 else 16384          # 2.6e5 / 1.0e6 points per CPU step
+    sample_tf = (1024 if max(lw) > 64 else 4096) if len(lw) and max(lw) >= 64 else 16384   # 6.6e4 / 2.6e5 / 1.0e6 points per CPU step
     feed, meta = cpu_feed(nx, ny, ntime, sample_tf)
     theta = graph_oracle.glorot_init(meta["inpDim"], list(lw), seed=0)
     st = torch_oracle.CpuStepper(theta, feed, meta["dim"], meta["inpDim"], list(lw), act, True, meta["lossOpt"],
@@ -364,6 +368,14 @@ def main():
                                               bic=prof["bic"][0] / max(prof["bic"][1], 1), finalize=prof["finalize"][0] / max(prof["finalize"][1], 1),
                                               optimizer=prof["optimizer"][0] / max(prof["optimizer"][1], 1)))
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / pk["hbm_gbs"]
+        if "tcgen05" in eng.kernel_info():
+            # tensor-core class: the layer GEMMs run as 3xTF32 (three tcgen05.mma kind::tf32 per algorithmic product);
+            # the bound is the TF32 tensor peak = half the measured dense bf16 figure (sustained: kernel timed inside a long step)
+            tf32_peak = 0.5 * pk["bf16_tflops"]
+            roofline.update(bound="tensor", peak=tf32_peak, frac=achieved / tf32_peak, kernel="tc_gemm_kernel / tc_gw_kernel pipeline (vn_tc.cu)",
+                            peak_source="0.5 x dense bf16 (%s): TF32 runs at half the bf16 rate" % pk["source"],
+                            executed_mma_tflops=3.0 * achieved, executed_frac=3.0 * achieved / tf32_peak,
+                            fp32_fma_peak=peak_tf, frac_of_fp32_fma_peak=achieved / peak_tf if peak_tf else None)
         line = dict(metric=METRIC, value=P_total / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic", config=config,

@@ -53,7 +53,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {      // 16-byte vector reduction (sm_90+)
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // bounded wait (a lost commit must not hang the GPU): false on timeout
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -303,7 +305,11 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
                 float* cp = a.cross + prow * a.ldOut + n;
                 if (a.crossMode) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) red_add_f32(cp + c, z[c] * xv[(cb * 16 + c) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
+                    for (int q = 0; q < 4; ++q)
+                        red_add_v4(cp + 4 * q, z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                   z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                   z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
+                                   z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -326,8 +332,13 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
 #pragma unroll
             for (int q = 0; q < 4; ++q) pm[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
             float* nm = a.outNm + (size_t)n * a.ldNm + prow;
+            if (EPI == EPI_FWD_VALUE || EPI == EPI_FWD_TANGENT) {           // read once, much later (tc_gw): keep it out of the way in L2
 #pragma unroll
-            for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);      // read once, much later (tc_gw): keep it out of the way in L2
+                for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);
+            } else {                                                         // zbar: tc_gw consumes it right after this launch
+#pragma unroll
+                for (int c = 0; c < 16; ++c) nm[(size_t)c * a.ldNm] = z[c];
+            }
         }
     }
     tc_fence_before();
