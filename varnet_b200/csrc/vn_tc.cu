@@ -89,29 +89,41 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tmem) {
 }
 
 // ------------------------------------------------------------------ operand tiles
-// One tile = 128 rows x KC floats of a row-major, K-contiguous FP32 matrix, loaded by 256 threads: a quarter
-// warp reads one whole 128-byte row segment (4 full lines per warp request) and, after the split, writes its
-// eight 16-byte K units of that row conflict free (padded TILE_LBO).
+// One tile = 128 rows x KC floats, loaded by 256 threads from one of two global layouts:
+//   quad-major  (QM): [K/4][rows][4]  — 16-byte units of four consecutive K of one row, rows contiguous.  This is the
+//                     order of the shared-memory canonical layout itself, so a warp reads 512 contiguous bytes and
+//                     writes four whole core matrices; the GEMM epilogues (thread = row) store it fully coalesced.
+//   row-major   (RM): [rows][ld]      — K contiguous per row (neuron-major activations, K = points, in tc_gw): a
+//                     quarter warp reads one 128-byte row segment and writes its eight K units conflict free thanks
+//                     to the padded TILE_LBO.
+struct Opnd { const float* p; size_t ld; };     // QM: p = base + row0*4, ld = rows of the array; RM: p = base + row0*ld, ld = row stride
 struct TileRegs { float4 v[TM * (KC / 4) / NTHR]; };
 
-__device__ __forceinline__ void tile_load(const float* __restrict__ src, size_t ld, TileRegs& r, int tid) {
-    constexpr int K4 = KC / 4, U = TM * K4 / NTHR;
+template <bool QM>
+__device__ __forceinline__ void tile_map(int u, int& k4, int& row) {
+    if (QM) { row = u % TM; k4 = u / TM; } else { k4 = u % (KC / 4); row = u / (KC / 4); }
+}
+template <bool QM>
+__device__ __forceinline__ void tile_load(const Opnd& o, int k0, TileRegs& r, int tid) {
+    constexpr int U = TM * (KC / 4) / NTHR;
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-        const int u = i * NTHR + tid;
-        const int k4 = u % K4, row = u / K4;
-        r.v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + k4 * 4));
+        int k4, row;
+        tile_map<QM>(i * NTHR + tid, k4, row);
+        const float* src = QM ? o.p + ((size_t)(k0 / 4 + k4) * o.ld + row) * 4 : o.p + (size_t)row * o.ld + k0 + k4 * 4;
+        r.v[i] = __ldg(reinterpret_cast<const float4*>(src));
     }
 }
 // round to the 10-bit TF32 mantissa (the tensor core itself truncates: a truncated split leaves a one-sided
 // 2^-21 bias per product that grows with K; rounding both halves makes the residual 2^-22 and sign-symmetric)
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+template <bool QM>
 __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned char* hiTile, unsigned char* loTile, int tid) {
-    constexpr int K4 = KC / 4, U = TM * K4 / NTHR;
+    constexpr int U = TM * (KC / 4) / NTHR;
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-        const int u = i * NTHR + tid;
-        const int k4 = u % K4, row = u / K4;
+        int k4, row;
+        tile_map<QM>(i * NTHR + tid, k4, row);
         const uint32_t off = k4 * TILE_LBO + row * 16;
         const float4 v = r.v[i];
         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
@@ -164,17 +176,19 @@ __device__ __forceinline__ uint32_t pipe_setup(unsigned char* smem, int tid, int
 
 // Loader side of one K chunk (256 threads): wait until the MMAs that read this stage three chunks ago are done,
 // write the split tiles, put the chunk after next in flight, publish the stage to the MMA warp.
-template <class FA, class FB>
+struct ChunkSrc { Opnd a, b; int k0; };
+template <bool QM, class F>
 __device__ __forceinline__ void loader_step(unsigned char* smem, const Bars& bars, int it, int nIt, TileRegs& ra, TileRegs& rb,
-                                            FA&& srcA, FB&& srcB, size_t ldA, size_t ldB, int tid, bool& ok) {
+                                            F&& src, int tid, bool& ok) {
     const int b = it % NST;
     unsigned char* stage = smem + b * STAGE_BYTES;
     if (it >= NST && ok) ok = mbar_wait(bars.empty + 8 * b, (uint32_t)((it / NST) - 1) & 1u);
-    tile_store_split(ra, stage, stage + TILE_BYTES, tid);
-    tile_store_split(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
+    tile_store_split<QM>(ra, stage, stage + TILE_BYTES, tid);
+    tile_store_split<QM>(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
     if (it + 2 < nIt) {
-        tile_load(srcA(it + 2), ldA, ra, tid);
-        tile_load(srcB(it + 2), ldB, rb, tid);
+        const ChunkSrc c = src(it + 2);
+        tile_load<QM>(c.a, c.k0, ra, tid);
+        tile_load<QM>(c.b, c.k0, rb, tid);
     }
     fence_async_smem();                 // generic-proxy stores -> visible to the tensor core (async proxy)
     mbar_arrive(bars.full + 8 * b);
@@ -198,25 +212,30 @@ __device__ __forceinline__ bool mma_warp_loop(unsigned char* smem, const Bars& b
 enum { EPI_FWD_VALUE = 0, EPI_FWD_TANGENT = 1, EPI_ADJ_TANGENT = 2, EPI_ADJ_VALUE = 3 };
 
 struct GemmArgs {
-    const float* A; int ldA;                // this stream's operand [rows][ldA], K contiguous
-    const float* B; int ldB;                // [N][K] row-major (K contiguous), zero padded
+    const float* A;                         // this stream's operand, quad-major [K/4][rows][4]
+    const float* B; int rowsB;              // weights, quad-major [K/4][rowsB][4], zero padded
+    unsigned int rows;                      // rows (points) of every quad-major activation array of the chunk
     int K;                                  // multiple of KC
     int nTilesN;
     const float* bias; int widthOut;        // FWD_VALUE
-    const float* val; int ldVal;            // FWD_TANGENT: a of this layer; ADJ_*: a of the layer below   (point-major)
-    const float* tan;                       // ADJ_TANGENT: tangent activation of the layer below, this stream (ldVal)
+    const float* val;                       // FWD_TANGENT: a of this layer; ADJ_*: a of the layer below   (quad-major)
+    const float* tan;                       // ADJ_TANGENT: tangent activation of the layer below, this stream
     float* cross; int crossMode;            // ADJ_TANGENT: 0 = write, 1 = accumulate; ADJ_VALUE: 1 = read, 0 = no tangent streams
-    float* outPm; int ldOut;                // [p][ldOut]
-    float* outNm; unsigned int ldNm;        // [n][ldNm]
+    float* outQm;                           // quad-major [N/4][rows][4]
+    float* outNm; unsigned int ldNm;        // neuron-major [n][ldNm]
     int* err;
 };
 
-__device__ __forceinline__ void ld16(const float* __restrict__ src, float (&v)[16]) {
+// 16 consecutive columns n..n+15 of row `prow` of a quad-major array: four 16-byte units, coalesced across the warp
+__device__ __forceinline__ void ld16(const float* __restrict__ base, unsigned int rows, size_t prow, int n, float (&v)[16]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + ((size_t)(n / 4 + q) * rows + prow) * 4));
         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
+}
+__device__ __forceinline__ float4* qm_ptr(float* base, unsigned int rows, size_t prow, int n) {
+    return reinterpret_cast<float4*>(base + ((size_t)(n / 4) * rows + prow) * 4);
 }
 
 template <int EPI, int ACT>
@@ -243,18 +262,16 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
         }
     } else {
         // ---- loaders, then epilogue: thread = one point (TMEM lane), warps 0-3 / 4-7 take the two column halves
-        const float* Ag = a.A + m0 * a.ldA;
-        const float* Bg = a.B + (size_t)n0 * a.ldB;
-        auto srcA = [&](int it) { return Ag + (size_t)it * KC; };
-        auto srcB = [&](int it) { return Bg + (size_t)it * KC; };
+        const Opnd oa{a.A + m0 * 4, a.rows}, ob{a.B + (size_t)n0 * 4, (size_t)a.rowsB};
+        auto src = [&](int it) { return ChunkSrc{oa, ob, it * KC}; };
         TileRegs ra[2], rb[2];                                                // two K chunks in flight
-        tile_load(srcA(0), a.ldA, ra[0], tid); tile_load(srcB(0), a.ldB, rb[0], tid);
-        if (nIt > 1) { tile_load(srcA(1), a.ldA, ra[1], tid); tile_load(srcB(1), a.ldB, rb[1], tid); }
+        tile_load<true>(oa, 0, ra[0], tid); tile_load<true>(ob, 0, rb[0], tid);
+        if (nIt > 1) { tile_load<true>(oa, KC, ra[1], tid); tile_load<true>(ob, KC, rb[1], tid); }
         bool ok = true;
 #pragma unroll 1
         for (int it0 = 0; it0 < nIt; it0 += 2) {
-            loader_step(smem, bars, it0, nIt, ra[0], rb[0], srcA, srcB, a.ldA, a.ldB, tid, ok);
-            if (it0 + 1 < nIt) loader_step(smem, bars, it0 + 1, nIt, ra[1], rb[1], srcA, srcB, a.ldA, a.ldB, tid, ok);
+            loader_step<true>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
+            if (it0 + 1 < nIt) loader_step<true>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
         }
 
         const int row = (warp & 3) * 32 + lane, half = warp >> 2;
@@ -265,15 +282,15 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
         float av[EPI == EPI_FWD_VALUE ? 1 : 64], xv[(EPI == EPI_ADJ_TANGENT || EPI == EPI_ADJ_VALUE) ? 64 : 1];
         if (EPI != EPI_FWD_VALUE) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.val + prow * a.ldVal + nb + cb * 16, reinterpret_cast<float(&)[16]>(av[cb * 16 % (EPI == EPI_FWD_VALUE ? 1 : 64)]));
+            for (int cb = 0; cb < 4; ++cb) ld16(a.val, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(av[cb * 16 % (EPI == EPI_FWD_VALUE ? 1 : 64)]));
         }
         if (EPI == EPI_ADJ_TANGENT) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.tan + prow * a.ldVal + nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]));
+            for (int cb = 0; cb < 4; ++cb) ld16(a.tan, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]));
         }
         if (EPI == EPI_ADJ_VALUE && a.crossMode) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.cross + prow * a.ldOut + nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_VALUE ? 64 : 1)]));
+            for (int cb = 0; cb < 4; ++cb) ld16(a.cross, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_VALUE ? 64 : 1)]));
         }
         if (ok) ok = mbar_wait(bars.done, 0u);
         if (!ok) *a.err = 1;
@@ -302,21 +319,15 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
                 for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
             } else if (EPI == EPI_ADJ_TANGENT) {
                 // dabar_k -> dzbar_k = dabar_k act'; its share of the second-order term: cross += dabar_k * adot_k   (App. A.3)
-                float* cp = a.cross + prow * a.ldOut + n;
-                if (a.crossMode) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        red_add_v4(cp + 4 * q, z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                   z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                   z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                   z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        reinterpret_cast<float4*>(cp)[q] = make_float4(z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                                                       z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                                                       z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)],
-                                                                       z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]);
+                for (int q = 0; q < 4; ++q) {
+                    float* cp = reinterpret_cast<float*>(qm_ptr(a.cross, a.rows, prow, n + 4 * q));
+                    const float c0 = z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
+                    const float c1 = z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
+                    const float c2 = z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
+                    const float c3 = z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
+                    if (a.crossMode) red_add_v4(cp, c0, c1, c2, c3);
+                    else *reinterpret_cast<float4*>(cp) = make_float4(c0, c1, c2, c3);
                 }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
@@ -328,9 +339,8 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
                     z[c] = a.crossMode ? fmaf(z[c], d1, act_d2r<ACT>(aa) * xv[(cb * 16 + c) % (EPI == EPI_ADJ_VALUE ? 64 : 1)]) : z[c] * d1;
                 }
             }
-            float4* pm = reinterpret_cast<float4*>(a.outPm + prow * a.ldOut + n);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pm[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) *qm_ptr(a.outQm, a.rows, prow, n + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
             float* nm = a.outNm + (size_t)n * a.ldNm + prow;
             if (EPI == EPI_FWD_VALUE || EPI == EPI_FWD_TANGENT) {           // read once, much later (tc_gw): keep it out of the way in L2
 #pragma unroll
@@ -386,10 +396,12 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
             if (!ok) *a.err = 1;
         }
     } else {
-        const float* Ag = a.A + (size_t)(it_ * TM) * a.ld + pBeg;
-        const float* Bg = a.B + (size_t)(jt * TN) * a.ld + pBeg;
-        auto srcA = [&](int it) { const int s = it / chunks, pc = it - s * chunks; return Ag + s * a.aStream + (size_t)pc * KC; };
-        auto srcB = [&](int it) { const int s = it / chunks, pc = it - s * chunks; return Bg + s * a.bStream + (size_t)pc * KC; };
+        const float* Ag = a.A + (size_t)(it_ * TM) * a.ld;
+        const float* Bg = a.B + (size_t)(jt * TN) * a.ld;
+        auto src = [&](int it) {
+            const int s = it / chunks, pc = it - s * chunks;
+            return ChunkSrc{Opnd{Ag + s * a.aStream, a.ld}, Opnd{Bg + s * a.bStream, a.ld}, (int)pBeg + pc * KC};
+        };
         const int half = warp >> 2;
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
         float acc[64];
@@ -406,8 +418,8 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
             }
         };
         TileRegs ra[2], rb[2];
-        tile_load(srcA(0), a.ld, ra[0], tid); tile_load(srcB(0), a.ld, rb[0], tid);
-        if (nIt > 1) { tile_load(srcA(1), a.ld, ra[1], tid); tile_load(srcB(1), a.ld, rb[1], tid); }
+        { const ChunkSrc c = src(0); tile_load<false>(c.a, c.k0, ra[0], tid); tile_load<false>(c.b, c.k0, rb[0], tid); }
+        if (nIt > 1) { const ChunkSrc c = src(1); tile_load<false>(c.a, c.k0, ra[1], tid); tile_load<false>(c.b, c.k0, rb[1], tid); }
         bool ok = true;
 #pragma unroll 1
         for (int it0 = 0; it0 < nIt; it0 += 2) {
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
                         drain(((it / GW_EPOCH) - 2) % 3);
                         tc_fence_before();          // the set is overwritten by epoch e+1, whose first stage this thread publishes later
                     }
-                    loader_step(smem, bars, it, nIt, ra[h], rb[h], srcA, srcB, a.ld, a.ld, tid, ok);
+                    loader_step<false>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
                 }
             }
         }
@@ -460,131 +472,124 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
     return t;       // valid in thread 0
 }
 
-// zero-padded [WP][WP] copies of the hidden kernels: Wn[l-1][i][j] = W_l[i][j], Wt[l-1][j][i] = W_l[i][j]
+// zero-padded quad-major copies [K/4][WP][4] of the hidden kernels as B operands (B[n][k]):
+//   forward  Wt: n = output neuron, k = input neuron  -> W_l[k][n]
+//   adjoint  Wn: n = input neuron,  k = output neuron -> W_l[n][k]
 __global__ void tc_stage_weights_kernel(NetDesc net, int WP, const float* __restrict__ theta, float* __restrict__ Wn, float* __restrict__ Wt) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per = (long long)WP * WP;
     if (idx >= per * (net.L - 1)) return;
-    const int l = (int)(idx / per) + 1, r = (int)((idx % per) / WP), c = (int)(idx % WP);
+    const int l = (int)(idx / per) + 1;
+    const int r = (int)(idx % per);
+    const int k = (r / (4 * WP)) * 4 + (r & 3), n = (r >> 2) % WP;
     const int wi = net.width[l - 1], wo = net.width[l];
-    Wn[idx] = (r < wi && c < wo) ? theta[net.woff[l] + r * wo + c] : 0.f;           // [in][out]
-    Wt[idx] = (c < wi && r < wo) ? theta[net.woff[l] + c * wo + r] : 0.f;           // [out][in]
+    Wt[idx] = (k < wi && n < wo) ? theta[net.woff[l] + k * wo + n] : 0.f;
+    Wn[idx] = (n < wi && k < wo) ? theta[net.woff[l] + n * wo + k] : 0.f;
 }
 
 struct L0Args {
     TileArgs in; unsigned int base; int WP;
-    float* X; float* Apm; float* Anm; size_t sPm, sNm; unsigned int cap;
+    float* X; float* Aqm; float* Anm; size_t sQm, sNm; unsigned int cap;
 };
-// layer 0 (K = inpDim): a = act(X W0 + b0), tangent k: act'(z) W0[k,:]; also keeps X of the chunk for g(W0)
+// layer 0 (K = inpDim): a = act(X W0 + b0), tangent k: act'(z) W0[k,:]; also keeps X of the chunk for g(W0).
+// thread = one point x four neurons: coalesced 16-byte quad-major stores, coalesced scalar neuron-major stores
 template <int S, int ACT>
 __global__ void __launch_bounds__(256) tc_layer0_kernel(const L0Args a) {
-    __shared__ float xs[VN_KIN][32];
-    __shared__ float tile[S][32][33];
     const TileArgs& A = a.in;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const unsigned int p0 = blockIdx.x * 32; const int n0 = blockIdx.y * 32;
-    const int inpDim = A.net.inpDim;
-    if ((int)threadIdx.x < inpDim * 32) {
-        const int k = threadIdx.x >> 5, p = threadIdx.x & 31;
-        const unsigned int gp = a.base + p0 + p;
-        float x = 0.f;
-        if (gp < A.P) x = (k >= A.nxTable) ? __ldg(A.extraX + (k - A.nxTable)) : __ldg(A.cols + (size_t)(A.colX + k) * A.pstride + table_row(A, gp));
-        xs[k][p] = x;
-        if (blockIdx.y == 0) a.X[(size_t)k * a.cap + p0 + p] = x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int p = blockIdx.x * 32 + lane;
+    const int n4 = blockIdx.y * 8 + warp, n0 = 4 * n4;
+    const int inpDim = A.net.inpDim, w0 = A.net.width[0];
+    const unsigned int gp = a.base + p;
+    float x[VN_KIN];
+#pragma unroll
+    for (int k = 0; k < VN_KIN; ++k) {
+        x[k] = 0.f;
+        if (k < inpDim && gp < A.P)
+            x[k] = (k >= A.nxTable) ? __ldg(A.extraX + (k - A.nxTable)) : __ldg(A.cols + (size_t)(A.colX + k) * A.pstride + table_row(A, gp));
+        if (k < inpDim && n4 == 0) a.X[(size_t)k * a.cap + p] = x[k];
     }
-    __syncthreads();
-    const int n = n0 + tx, w0 = A.net.width[0];
-    float w[VN_KIN], bv = 0.f;
+    float o[S][4];
 #pragma unroll
-    for (int k = 0; k < VN_KIN; ++k) w[k] = (k < inpDim && n < w0) ? __ldg(A.theta + A.net.woff[0] + k * w0 + n) : 0.f;
-    if (n < w0) bv = __ldg(A.theta + A.net.boff[0] + n);
+    for (int e = 0; e < 4; ++e) {
+        const int n = n0 + e;
+        float w[VN_KIN], z = (n < w0) ? __ldg(A.theta + A.net.boff[0] + n) : 0.f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int p = ty * 4 + r;
-        float z = bv;
-#pragma unroll
-        for (int k = 0; k < VN_KIN; ++k) z = fmaf(xs[k][p], w[k], z);
-        const float av = act_f<ACT>(z), d1 = act_d1<ACT>(av);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const float o = s == 0 ? av : d1 * w[s - 1 < 0 ? 0 : s - 1];
-            a.Apm[s * a.sPm + (size_t)(p0 + p) * a.WP + n] = o;
-            tile[s][p][tx] = o;
+        for (int k = 0; k < VN_KIN; ++k) {
+            w[k] = (k < inpDim && n < w0) ? __ldg(A.theta + A.net.woff[0] + k * w0 + n) : 0.f;
+            z = fmaf(x[k], w[k], z);
         }
+        const float av = act_f<ACT>(z), d1 = act_d1<ACT>(av);
+        o[0][e] = av;
+#pragma unroll
+        for (int s = 1; s < S; ++s) o[s][e] = d1 * w[s - 1];
     }
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int nn = ty * 4 + r;
+    for (int s = 0; s < S; ++s) {
+        *reinterpret_cast<float4*>(a.Aqm + s * a.sQm + ((size_t)n4 * a.cap + p) * 4) = make_float4(o[s][0], o[s][1], o[s][2], o[s][3]);
 #pragma unroll
-        for (int s = 0; s < S; ++s) a.Anm[s * a.sNm + (size_t)(n0 + nn) * a.cap + p0 + tx] = tile[s][tx][nn];
+        for (int e = 0; e < 4; ++e) __stcs(a.Anm + s * a.sNm + (size_t)(n0 + e) * a.cap + p, o[s][e]);
     }
 }
 
 struct OutArgs {
     TileArgs in; unsigned int base, nPts; int WP; bool needGrad;
-    const float* Alast; size_t sPm;
+    const float* Alast; size_t sQm;
     float* U; float* seeds; unsigned int cap; double* g64;
 };
 // output layer (Dense(1), linear): u_s = A_{L-1,s} . w_out (+ b_out); then per mode the integrand
-// (TFModel.py:653-660), the BC/IC residual and its seed (TFModel.py:643-650), or the model value
+// (TFModel.py:653-660), the BC/IC residual and its seed (TFModel.py:643-650), or the model value.
+// thread = one point (quad-major rows: coalesced 16-byte loads, w_out broadcast)
 template <int S, int MODE>
 __global__ void __launch_bounds__(256) tc_out_kernel(const OutArgs a) {
     __shared__ double sh[8];
     const TileArgs& A = a.in;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int p = blockIdx.x * 8 + warp;
+    const unsigned int p = blockIdx.x * 256 + threadIdx.x;
     const int L = A.net.L, wlast = A.net.width[L - 1];
     const float* wout = A.theta + A.net.woff[L];
     float seedv = 0.f;
     if (p < a.nPts) {
         float u[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const float* row = a.Alast + s * a.sPm + (size_t)p * a.WP;
-            float acc = 0.f;
-            for (int n = lane * 4; n < wlast; n += 128) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(row + n));
-                acc = fmaf(v.x, __ldg(wout + n), acc);
-                if (n + 1 < wlast) acc = fmaf(v.y, __ldg(wout + n + 1), acc);
-                if (n + 2 < wlast) acc = fmaf(v.z, __ldg(wout + n + 2), acc);
-                if (n + 3 < wlast) acc = fmaf(v.w, __ldg(wout + n + 3), acc);
-            }
+        for (int s = 0; s < S; ++s) u[s] = 0.f;
+        for (int n = 0; n < wlast; n += 4) {
+            const float w0 = __ldg(wout + n), w1 = n + 1 < wlast ? __ldg(wout + n + 1) : 0.f;
+            const float w2 = n + 2 < wlast ? __ldg(wout + n + 2) : 0.f, w3 = n + 3 < wlast ? __ldg(wout + n + 3) : 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            u[s] = acc;
+            for (int s = 0; s < S; ++s) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.Alast + s * a.sQm + ((size_t)(n >> 2) * a.cap + p) * 4));
+                u[s] = fmaf(v.x, w0, fmaf(v.y, w1, fmaf(v.z, w2, fmaf(v.w, w3, u[s]))));
+            }
         }
         u[0] += __ldg(A.theta + A.net.boff[L]);
         const unsigned int gp = a.base + p;
-        if (lane == 0) {
-            if (MODE == TC_VAR) {
+        if (MODE == TC_VAR) {
+            if (gp < A.P) {
                 float I = 0.f;
-                if (gp < A.P) {
-                    const size_t row = table_row(A, gp);
+                const size_t row = table_row(A, gp);
 #pragma unroll
-                    for (int k = 0; k < S - 1; ++k) I = fmaf(u[1 + k], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
-                    if (A.timeDependent) I -= u[0] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
-                    if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
-                    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
-                    A.Iw[gp] = I;
-                }
-            } else if (MODE == TC_BIC) {
-                if (gp < A.P) {
-                    const float r = u[0] - __ldg(A.label + gp);
-                    A.cj[gp] = A.biDimVal * r * r;
-                    float sc;                                   // mean over boundary rows / initial rows (TFModel.py:644-648)
-                    if (gp < A.bDof) sc = __ldg(A.wts + 0) / (float)A.bDof;
-                    else sc = A.timeDependent ? __ldg(A.wts + 1) / (float)(A.P - A.bDof) : 0.f;
-                    seedv = 2.f * A.biDimVal * r * sc;
-                }
-                a.seeds[p] = seedv;
-            } else {
-                if (gp < A.P) A.uout[gp] = u[0];
+                for (int k = 0; k < S - 1; ++k) I = fmaf(u[1 + k], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
+                if (A.timeDependent) I -= u[0] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
+                if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+                if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+                A.Iw[gp] = I;
             }
+        } else if (MODE == TC_BIC) {
+            if (gp < A.P) {
+                const float r = u[0] - __ldg(A.label + gp);
+                A.cj[gp] = A.biDimVal * r * r;
+                float sc;                                   // mean over boundary rows / initial rows (TFModel.py:644-648)
+                if (gp < A.bDof) sc = __ldg(A.wts + 0) / (float)A.bDof;
+                else sc = A.timeDependent ? __ldg(A.wts + 1) / (float)(A.P - A.bDof) : 0.f;
+                seedv = 2.f * A.biDimVal * r * sc;
+            }
+            a.seeds[p] = seedv;
+        } else {
+            if (gp < A.P) A.uout[gp] = u[0];
         }
     }
     if (MODE == TC_BIC && a.needGrad) {
-        const double t = block_sum_d(lane == 0 ? (double)seedv : 0.0, sh);
+        const double t = block_sum_d((double)seedv, sh);
         if (threadIdx.x == 0 && t != 0.0) atomicAdd(a.g64 + A.net.boff[L], t);       // g(b_out) = sum of seeds
     }
 }
@@ -640,55 +645,59 @@ __global__ void __launch_bounds__(256) tc_seed_kernel(const SeedArgs a) {
 }
 
 struct TopArgs {
-    int WP, wlast; const float* wout;
-    const float* Apm; size_t sPm; const float* seeds; unsigned int cap;
-    float* Dpm; float* Dnm; size_t sNm; double* gwout;
+    int WP, wlast; const float* wout; unsigned int nPts;
+    const float* Aqm; size_t sQm; const float* seeds; unsigned int cap;
+    float* Dqm; float* Dnm; size_t sNm; double* gwout;
 };
-// top of the adjoint: zbar_{L-1} from the seeds (outer product with w_out), g(w_out)
+// top of the adjoint: zbar_{L-1} from the seeds (outer product with w_out), g(w_out).
+// thread = one point x four neurons; a warp walks four 32-point groups and reduces its g(w_out) share once
 template <int S, int ACT>
 __global__ void __launch_bounds__(256) tc_top_kernel(const TopArgs a) {
-    __shared__ float tile[S][32][33];
-    __shared__ float red[8][32];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const unsigned int p0 = blockIdx.x * 32; const int n0 = blockIdx.y * 32;
-    const int n = n0 + tx;
-    const float wv = n < a.wlast ? __ldg(a.wout + n) : 0.f;
-    float gacc = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n4 = blockIdx.y * 8 + warp, n0 = 4 * n4;
+    float wv[4], gacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int pl = ty * 4 + r;
-        const size_t p = p0 + pl;
-        const float av = a.Apm[p * a.WP + n], d1 = act_d1<ACT>(av);
+    for (int e = 0; e < 4; ++e) wv[e] = n0 + e < a.wlast ? __ldg(a.wout + n0 + e) : 0.f;
+    for (int g = 0; g < 4; ++g) {
+        const unsigned int p = (blockIdx.x * 4 + g) * 32 + lane;
+        if (p >= a.nPts) break;
+        const size_t q = ((size_t)n4 * a.cap + p) * 4;
+        const float4 a4 = *reinterpret_cast<const float4*>(a.Aqm + q);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
         const float s0 = a.seeds[p];
-        float cross = 0.f;
-        gacc = fmaf(av, s0, gacc);
+        float d1[4], cross[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { d1[e] = act_d1<ACT>(av[e]); gacc[e] = fmaf(av[e], s0, gacc[e]); }
 #pragma unroll
         for (int s = 1; s < S; ++s) {
-            const float da = a.Apm[s * a.sPm + p * a.WP + n], sd = a.seeds[(size_t)s * a.cap + p];
-            const float ab = sd * wv;
-            gacc = fmaf(da, sd, gacc);
-            cross = fmaf(ab, da, cross);
-            const float o = ab * d1;
-            a.Dpm[s * a.sPm + p * a.WP + n] = o;
-            tile[s][pl][tx] = o;
+            const float4 d4 = *reinterpret_cast<const float4*>(a.Aqm + s * a.sQm + q);
+            const float da[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float sd = a.seeds[(size_t)s * a.cap + p];
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float ab = sd * wv[e];
+                gacc[e] = fmaf(da[e], sd, gacc[e]);
+                cross[e] = fmaf(ab, da[e], cross[e]);
+                o[e] = ab * d1[e];
+                a.Dnm[s * a.sNm + (size_t)(n0 + e) * a.cap + p] = o[e];
+            }
+            *reinterpret_cast<float4*>(a.Dqm + s * a.sQm + q) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        const float zb = fmaf(s0 * wv, d1, act_d2r<ACT>(av) * cross);
-        a.Dpm[p * a.WP + n] = zb;
-        tile[0][pl][tx] = zb;
-    }
-    red[ty][tx] = gacc;
-    __syncthreads();
-    if (ty == 0 && n < a.wlast) {
-        float t = 0.f;
+        float zb[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][tx];
-        atomicAdd(a.gwout + n, (double)t);
+        for (int e = 0; e < 4; ++e) {
+            zb[e] = fmaf(s0 * wv[e], d1[e], act_d2r<ACT>(av[e]) * cross[e]);
+            a.Dnm[(size_t)(n0 + e) * a.cap + p] = zb[e];
+        }
+        *reinterpret_cast<float4*>(a.Dqm + q) = make_float4(zb[0], zb[1], zb[2], zb[3]);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int nn = ty * 4 + r;
+    for (int e = 0; e < 4; ++e) {
+        float t = gacc[e];
 #pragma unroll
-        for (int s = 0; s < S; ++s) a.Dnm[s * a.sNm + (size_t)(n0 + nn) * a.cap + p0 + tx] = tile[s][tx][nn];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && n0 + e < a.wlast) atomicAdd(a.gwout + n0 + e, (double)t);
     }
 }
 
@@ -864,7 +873,7 @@ cudaError_t vn_tc_run(TcJob& j) {
 
         // ---- layer 0
         {
-            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Apm = w.Apm; a.Anm = w.Anm; a.sPm = w.sPm; a.sNm = w.sNm; a.cap = cap;
+            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Aqm = w.Apm; a.Anm = w.Anm; a.sQm = w.sPm; a.sNm = w.sNm; a.cap = cap;
             const dim3 grid(nPts / 32, WP / 32);
 #define CALL(SS) launch_layer0<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
@@ -875,13 +884,13 @@ cudaError_t vn_tc_run(TcJob& j) {
         for (int l = 1; l < L; ++l) {
             for (int sidx = 0; sidx < S; ++sidx) {
                 GemmArgs g{};
-                g.A = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm; g.ldA = WP;
-                g.B = w.Wt + (size_t)(l - 1) * WP * WP; g.ldB = WP;
+                g.A = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm; g.rows = cap;
+                g.B = w.Wt + (size_t)(l - 1) * WP * WP; g.rowsB = WP;
                 g.K = (net.width[l - 1] + KC - 1) / KC * KC;
                 g.nTilesN = (net.width[l] + TN - 1) / TN;
                 g.bias = A.theta + net.boff[l]; g.widthOut = net.width[l];
-                g.val = w.Apm + (size_t)l * w.layerStride; g.ldVal = WP;
-                g.outPm = w.Apm + (size_t)l * w.layerStride + sidx * w.sPm; g.ldOut = WP;
+                g.val = w.Apm + (size_t)l * w.layerStride;
+                g.outQm = w.Apm + (size_t)l * w.layerStride + sidx * w.sPm;
                 g.outNm = w.Anm + (size_t)l * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx == 0) TCK(launch_gemm<EPI_FWD_VALUE>(act, g, mTiles * g.nTilesN, st));
@@ -892,8 +901,8 @@ cudaError_t vn_tc_run(TcJob& j) {
         // ---- output layer + integrand / BC-IC residual / value
         {
             OutArgs a; a.in = A; a.base = base; a.nPts = nPts; a.WP = WP; a.needGrad = j.needGrad;
-            a.Alast = w.Apm + (size_t)(L - 1) * w.layerStride; a.sPm = w.sPm; a.U = w.U; a.seeds = w.seeds; a.cap = cap; a.g64 = j.g64;
-            const unsigned int grid = (nPts + 7) / 8;
+            a.Alast = w.Apm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sPm; a.U = w.U; a.seeds = w.seeds; a.cap = cap; a.g64 = j.g64;
+            const unsigned int grid = (nPts + 255) / 256;
             if (j.mode == TC_VAR) {
 #define CALL(SS) (tc_out_kernel<SS, TC_VAR><<<grid, 256, 0, st>>>(a), cudaGetLastError())
                 TCK(TC_S_SWITCH(S, CALL));
@@ -924,9 +933,9 @@ cudaError_t vn_tc_run(TcJob& j) {
         int cur = 0;
         {
             TopArgs a; a.WP = WP; a.wlast = net.width[L - 1]; a.wout = A.theta + net.woff[L];
-            a.Apm = w.Apm + (size_t)(L - 1) * w.layerStride; a.sPm = w.sPm; a.seeds = w.seeds; a.cap = cap;
-            a.Dpm = w.Dpm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
-            const dim3 grid(nPts / 32, WP / 32);
+            a.Aqm = w.Apm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sPm; a.seeds = w.seeds; a.cap = cap; a.nPts = nPts;
+            a.Dqm = w.Dpm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
+            const dim3 grid((nPts / 32 + 3) / 4, WP / 32);
 #define CALL(SS) launch_top<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
 #undef CALL
@@ -968,14 +977,14 @@ cudaError_t vn_tc_run(TcJob& j) {
             // second-order term `cross`), then the value stream
             for (int sidx = S - 1; sidx >= 0; --sidx) {
                 GemmArgs g{};
-                g.A = w.Dpm + (size_t)cur * w.layerStride + sidx * w.sPm; g.ldA = WP;
-                g.B = w.Wn + (size_t)(l - 1) * WP * WP; g.ldB = WP;
+                g.A = w.Dpm + (size_t)cur * w.layerStride + sidx * w.sPm; g.rows = cap;
+                g.B = w.Wn + (size_t)(l - 1) * WP * WP; g.rowsB = WP;
                 g.K = (net.width[l] + KC - 1) / KC * KC;
                 g.nTilesN = (net.width[l - 1] + TN - 1) / TN;
-                g.val = w.Apm + (size_t)(l - 1) * w.layerStride; g.ldVal = WP;
+                g.val = w.Apm + (size_t)(l - 1) * w.layerStride;
                 g.tan = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm;
                 g.cross = w.cross;
-                g.outPm = w.Dpm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sPm; g.ldOut = WP;
+                g.outQm = w.Dpm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sPm;
                 g.outNm = w.Dnm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx > 0) { g.crossMode = (sidx == S - 1) ? 0 : 1; TCK(launch_gemm<EPI_ADJ_TANGENT>(act, g, mTiles * g.nTilesN, st)); }
