@@ -105,7 +105,9 @@ def test_adam_matches_tf_formula():
 
 
 RES_CASES = [(1, 2, [20], "sigmoid", True), (2, 3, [10, 20], "sigmoid", True), (2, 3, [64, 64, 64, 64], "tanh", True),
-             (2, 2, [16, 24], "tanh", False), (1, 3, [10, 20, 30], "sigmoid", True), (1, 1, [12], "tanh", False)]
+             (2, 2, [16, 24], "tanh", False), (1, 3, [10, 20, 30], "sigmoid", True), (1, 1, [12], "tanh", False),
+             # wide networks (tensor-core class): plain FP32 residual kernel of vn_tc.cu
+             (2, 3, [256, 256], "tanh", True), (1, 4, [100, 130, 72], "tanh", True), (2, 2, [128], "tanh", False)]
 
 
 @pytest.mark.gpu

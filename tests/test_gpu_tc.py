@@ -139,7 +139,7 @@ def test_tensor_core_class_limits():
     with pytest.raises(EngineError, match="exceeds the compiled kernel families"):
         Engine(2, 3, [300, 300], "tanh", True)
     eng = Engine(2, 3, [256, 256], "tanh", True)
-    eng.set_params(go.glorot_init(3, [256, 256], seed=0))
-    with pytest.raises(EngineError, match="strong-form residual"):
-        eng.residual(np.zeros((4, 3)), 1e-3, np.zeros((4, 2)), np.zeros((4, 2)), 0.0)
+    assert "family=tcgen05-3xtf32" in eng.kernel_info() and "WP=256" in eng.kernel_info()
+    with pytest.raises(EngineError, match="must be called first"):
+        eng.loss()
     eng.close()

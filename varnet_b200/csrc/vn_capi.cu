@@ -388,7 +388,6 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         }
         cudaError_t ce = vn_tc_prepare(e->S, act);
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
-        e->resOK = false;            // strong-form residual (second derivatives) is only built for the resident-tile classes
         e->graphOK = false;          // thousands of launches per step: plain stream launches
         CK(e->tcWork.ensure(e->tcGeom.workBytes));
         CK(e->tcAcc.ensure((size_t)(e->net.nparam + 2) * sizeof(double)));
@@ -1112,10 +1111,17 @@ extern "C" int vn_residual_f64(vn_engine* e, const double* X, const double* diff
     a.colT = -1; a.dim = c.dim;
     a.P = (unsigned int)n;
     a.uout = e->evalOut.as<float>(); a.Iw = e->evalOut.as<float>() + stride;
+    if (e->wclass == 256) {
+        long long n_l = 0;
+        cudaError_t ce = vn_tc_residual(a, c.act, e->tcGeom, e->tcWork.p, e->stream, &n_l);
+        if (ce != cudaSuccess) return fail(VN_E_CUDA, "strong-form residual (wide networks): %s", cudaGetErrorString(ce));
+        e->launches += n_l + 1;
+    } else {
     const TileGeom& g = e->gRes;
     a.ntiles = (int)(stride / g.TP);
     CK(vn_tile_launch(VN_S_RES, e->wclass, c.act, MODE_RESIDUAL, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, e->stream));
     e->launches += 2;
+    }
     if (u) CK(cudaMemcpyAsync(u, e->evalOut.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(res, e->evalOut.as<float>() + stride, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

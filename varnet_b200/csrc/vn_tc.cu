@@ -128,7 +128,7 @@ __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned cha
         const float4 v = r.v[i];
         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
         *reinterpret_cast<float4*>(hiTile + off) = h;
-        *reinterpret_cast<float4*>(loTile + off) = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+        *reinterpret_cast<float4*>(loTile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);   // sign-symmetric: truncation by the tensor core is unbiased here
     }
 }
 
@@ -749,6 +749,101 @@ __global__ void __launch_bounds__(256) tc_rowsum_kernel(const RowArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ strong-form residual (monitoring path)
+// res = -u_t + kappa sum_k d2u/dx_k^2 - sum_k (vel_k - dkappa/dx_k) du/dx_k + s   (TFModel.py:718-772) for wide networks.
+// Called every few epochs on a test grid, so this is a plain FP32 kernel: thread = one point x four output neurons,
+// six streams (value | tangents of the dim+1 inputs | second derivatives in x_k) kept neuron-major in global scratch.
+struct ResLayerArgs {
+    TileArgs in; unsigned int base, n, ld;      // chunk: first point, points, scratch row stride
+    int l, nT, dim;                             // layer; tangent streams (dim + time); second-derivative streams
+    const float* src; float* dst;               // [6][WP][ld] neuron-major, stream stride = WPs*ld
+    size_t streamStride;
+};
+template <int ACT>
+__global__ void __launch_bounds__(128) tc_res_layer_kernel(const ResLayerArgs a) {
+    const TileArgs& A = a.in;
+    const NetDesc& net = A.net;
+    const unsigned int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= a.n) return;
+    const int j0 = blockIdx.y * 4, l = a.l, wo = net.width[l];
+    const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+    const float* W = A.theta + net.woff[l];
+    float acc[VN_S_RES][4];
+#pragma unroll
+    for (int s = 0; s < VN_S_RES; ++s)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[s][e] = 0.f;
+    if (l == 0) {
+        const unsigned int gp = a.base + p;
+        for (int k = 0; k < wi; ++k) {
+            const float x = __ldg(A.cols + (size_t)(A.colX + k) * A.pstride + gp);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float w = j0 + e < wo ? __ldg(W + k * wo + j0 + e) : 0.f;
+                acc[0][e] = fmaf(x, w, acc[0][e]);
+                if (k < a.nT) acc[1 + k][e] = w;          // zdot_k = W0[k][j]; zddot = 0 at the input layer
+            }
+        }
+    } else {
+        for (int i = 0; i < wi; ++i) {
+            float w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = j0 + e < wo ? __ldg(W + i * wo + j0 + e) : 0.f;
+#pragma unroll
+            for (int s = 0; s < VN_S_RES; ++s) {
+                if (s == 0 || (s <= 3 && s - 1 < a.nT) || (s >= 4 && s - 4 < a.dim)) {
+                    const float v = a.src[s * a.streamStride + (size_t)i * a.ld + p];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[s][e] = fmaf(v, w[e], acc[s][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        if (j >= wo) break;
+        const float av = act_f<ACT>(acc[0][e] + __ldg(A.theta + net.boff[l] + j)), d1 = act_d1<ACT>(av);
+        a.dst[(size_t)j * a.ld + p] = av;
+#pragma unroll
+        for (int s = 1; s < VN_S_RES; ++s) {
+            float o = 0.f;
+            if (s <= 3) { if (s - 1 < a.nT) o = d1 * acc[s][e]; }
+            else if (s - 4 < a.dim) { const float zd = acc[s - 3][e]; o = d1 * fmaf(act_d2r<ACT>(av) * zd, zd, acc[s][e]); }
+            a.dst[s * a.streamStride + (size_t)j * a.ld + p] = o;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) tc_res_out_kernel(const ResLayerArgs a) {
+    const TileArgs& A = a.in;
+    const NetDesc& net = A.net;
+    const unsigned int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= a.n) return;
+    const int L = net.L, wl = net.width[L - 1];
+    const float* wout = A.theta + net.woff[L];
+    float u[VN_S_RES];
+#pragma unroll
+    for (int s = 0; s < VN_S_RES; ++s) u[s] = 0.f;
+    for (int i = 0; i < wl; ++i) {
+        const float w = __ldg(wout + i);
+#pragma unroll
+        for (int s = 0; s < VN_S_RES; ++s)
+            if (s == 0 || (s <= 3 && s - 1 < a.nT) || (s >= 4 && s - 4 < a.dim)) u[s] = fmaf(a.src[s * a.streamStride + (size_t)i * a.ld + p], w, u[s]);
+    }
+    u[0] += __ldg(A.theta + net.boff[L]);
+    const unsigned int gp = a.base + p;
+    float res = A.timeDependent ? -u[1 + A.dim] : 0.f, lap = 0.f, adv = 0.f;
+    for (int k = 0; k < A.dim; ++k) {
+        lap += u[4 + k];
+        const float vd = __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + gp) - __ldg(A.cols + (size_t)(A.colDD + k) * A.pstride + gp);
+        adv = fmaf(vd, u[1 + k], adv);
+    }
+    res = fmaf(__ldg(A.cols + (size_t)A.colD * A.pstride + gp), lap, res) - adv;
+    res += __ldg(A.cols + (size_t)A.colS * A.pstride + gp);
+    A.Iw[gp] = res;
+    A.uout[gp] = u[0];
+}
+
 __global__ void tc_grad_out_kernel(const double* __restrict__ g, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)g[i];
@@ -807,6 +902,8 @@ unsigned int gcd_u(unsigned int a, unsigned int b) { while (b) { const unsigned 
 
 }  // namespace
 
+#define TCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+
 bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
     int wmax = 0;
     for (int l = 0; l < net.L; ++l) wmax = std::max(wmax, net.width[l]);
@@ -839,12 +936,43 @@ cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float
     return cudaGetLastError();
 }
 
+cudaError_t vn_tc_residual(const TileArgs& A, int act, const TcGeom& g, void* work, cudaStream_t st, long long* launches) {
+    const NetDesc& net = A.net;
+    const int L = net.L, nT = A.dim + (A.timeDependent ? 1 : 0);
+    int wmax = 0;
+    for (int l = 0; l < L; ++l) wmax = std::max(wmax, net.width[l]);
+    // two ping-pong buffers of six streams inside the chunk workspace
+    const size_t avail = g.workBytes / sizeof(float);
+    unsigned int chunk = (unsigned int)std::min<size_t>(g.capPts, avail / ((size_t)2 * VN_S_RES * wmax));
+    chunk = chunk / 128 * 128;
+    if (chunk == 0) return cudaErrorInvalidValue;
+    float* buf0 = reinterpret_cast<float*>(work);
+    float* buf1 = buf0 + (size_t)VN_S_RES * wmax * chunk;
+    for (unsigned long long c0 = 0; c0 < A.P; c0 += chunk) {
+        ResLayerArgs a; a.in = A; a.base = (unsigned int)c0; a.n = (unsigned int)std::min<unsigned long long>(chunk, A.P - c0); a.ld = chunk;
+        a.nT = nT; a.dim = A.dim; a.streamStride = (size_t)wmax * chunk;
+        float* src = buf1; float* dst = buf0;
+        for (int l = 0; l < L; ++l) {
+            a.l = l; a.src = src; a.dst = dst;
+            const dim3 grid((a.n + 127) / 128, (net.width[l] + 3) / 4);
+            if (act == VN_SIGMOID) tc_res_layer_kernel<VN_SIGMOID><<<grid, 128, 0, st>>>(a);
+            else tc_res_layer_kernel<VN_TANH><<<grid, 128, 0, st>>>(a);
+            TCK(cudaGetLastError());
+            std::swap(src, dst);
+            ++*launches;
+        }
+        a.src = src;
+        tc_res_out_kernel<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+        TCK(cudaGetLastError());
+        ++*launches;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t vn_tc_grad_out(const double* g64, float* gbuf, int n, cudaStream_t st) {
     tc_grad_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(g64, gbuf, n);
     return cudaGetLastError();
 }
-
-#define TCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
 cudaError_t vn_tc_run(TcJob& j) {
     const TileArgs& A = j.in;

@@ -45,4 +45,6 @@ struct TcJob {
 // theta -> zero-padded [WP][WP] copies of the hidden kernels (natural and transposed) inside the workspace
 cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float* theta, void* work, cudaStream_t st);
 cudaError_t vn_tc_run(TcJob& j);
+// strong-form residual of the evaluation rows described by A (cols: X | kappa | vel | grad kappa | source; outputs A.uout, A.Iw)
+cudaError_t vn_tc_residual(const TileArgs& A, int act, const TcGeom& g, void* work, cudaStream_t st, long long* launches);
 cudaError_t vn_tc_grad_out(const double* g64, float* gbuf, int n, cudaStream_t st);
