@@ -143,3 +143,19 @@ def test_tensor_core_class_limits():
     with pytest.raises(EngineError, match="must be called first"):
         eng.loss()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_varnet_api_with_wide_network():
+    """The reference-facing path (VarNet.train -> TFNN.sess.run, residual monitoring, evaluate) with a 128-wide
+    MLP: same host code, the engine picks the tensor-core class by width."""
+    import tempfile
+    import varnet_b200
+    from oracle import configs
+    vn = configs.synthetic_2dt(varnet_b200, nx=12, ny=10, ntime=8, layerWidth=(128, 128), activation='tanh', seed=2)
+    assert "tcgen05" in vn.tfData.compTowers[0].engine.kernel_info()
+    with tempfile.TemporaryDirectory() as d:
+        res = vn.train(d, weight=[10., 10., 1.], epochNum=30, saveFreq=10, verbose=False)
+        assert len(res.loss) == 30 and np.all(np.isfinite(res.loss))
+        assert res.loss[-1] < res.loss[0]
+    vn.tfData.sess.close()
