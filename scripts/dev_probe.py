@@ -38,4 +38,5 @@ if __name__ == "__main__":
     run(1 << 16, [64] * 4, "tanh")
     run(1 << 16, [10, 20], "sigmoid")
     run(1 << 16, [16] * 4, "tanh")
+    run(1 << 16, [10, 16], "sigmoid")
     run(6000, [20], "sigmoid", dim=1, inpDim=2, integNum=16, reps=50)

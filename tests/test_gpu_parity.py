@@ -22,6 +22,9 @@ CASES = [
     (2, 3, [24, 24], "tanh", True, False, True, True, 19, 216, 90, 50),             # integPnum=3 2D+t, vector detJ
     (1, 1, [9], "sigmoid", False, False, False, False, 77, 4, 2, 2),                # steady 1D, tiny
     (2, 5, [33, 40, 64], "sigmoid", True, True, False, True, 29, 64, 129, 100),     # MOR-like extra inputs, ragged widths
+    # narrow class (width <= 16, 256-point tiles)
+    (2, 3, [16, 9, 16], "sigmoid", True, False, True, True, 61, 36, 70, 30),            # two-pass (36), vector detJ
+    (1, 2, [8], "tanh", True, True, False, False, 700, 16, 300, 200),                   # several 256-point tiles
     # every hidden layer exactly 64 wide
     (1, 2, [64, 64], "sigmoid", True, True, True, False, 83, 16, 70, 41),           # 1D+t, fused single pass
     (2, 3, [64, 64, 64], "tanh", True, True, True, True, 23, 36, 45, 30),           # two-pass (36 does not divide the tile)

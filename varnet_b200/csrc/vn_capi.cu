@@ -31,6 +31,7 @@ extern "C" const char* vn_last_error(void) { return g_err; }
 
 // ------------------------------------------------------------------ dispatch over kernel classes
 bool vn_tile_geometry(int S, int cls, int act, int mode, int L, TileGeom* g) {
+    if (cls == 16) return vn_geom_c16(S, act, mode, L, g);
     if (cls == 32) return vn_geom_c32(S, act, mode, L, g);
     if (cls == 64) return vn_geom_c64(S, act, mode, L, g);
     if (cls == 164) return vn_geom_c164(S, act, mode, L, g);
@@ -38,12 +39,14 @@ bool vn_tile_geometry(int S, int cls, int act, int mode, int L, TileGeom* g) {
 }
 cudaError_t vn_tile_launch(int S, int cls, int act, int mode, const TileArgs& a, int grid, size_t smem,
                            cudaStream_t st) {
+    if (cls == 16) return vn_launch_c16(S, act, mode, a, grid, smem, st);
     if (cls == 32) return vn_launch_c32(S, act, mode, a, grid, smem, st);
     if (cls == 64) return vn_launch_c64(S, act, mode, a, grid, smem, st);
     if (cls == 164) return vn_launch_c164(S, act, mode, a, grid, smem, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t vn_tile_prepare(int S, int cls, int act, int mode, size_t smem) {
+    if (cls == 16) return vn_prepare_c16(S, act, mode, smem);
     if (cls == 32) return vn_prepare_c32(S, act, mode, smem);
     if (cls == 64) return vn_prepare_c64(S, act, mode, smem);
     if (cls == 164) return vn_prepare_c164(S, act, mode, smem);
@@ -321,7 +324,7 @@ struct ProfScope {
     }
 };
 
-static const int kPad = 128;
+static const int kPad = 256;
 
 static void drop_graph(PointSet* t) {
     if (t && t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
@@ -394,7 +397,7 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         CK(e->tcErr.ensure(sizeof(int)));
         CK(cudaMemset(e->tcErr.p, 0, sizeof(int)));
     } else {
-    e->wclass = wmax <= 32 ? 32 : 64;
+    e->wclass = wmax <= 16 ? 16 : (wmax <= 32 ? 32 : 64);
     if (e->wclass == 64) {       // deep 64-wide networks: the weights of all layers no longer fit next to 64-point tiles
         TileGeom probe;
         if (vn_tile_geometry(e->S, 64, act, MODE_VAR_ADJ, L, &probe) && probe.smemBytes > prop.sharedMemPerBlockOptin)

@@ -128,7 +128,7 @@ __host__ __device__ inline PartLayout make_part_layout(int L) {
     int o = 0;
     for (int l = 0; l < VN_MAX_LAYERS; ++l) { p.off_gw[l] = 0; p.off_gb[l] = 0; }
     for (int l = 0; l < L; ++l) {
-        p.off_gw[l] = o; o += C::NT * (l == 0 ? C::TJ : C::TI * C::TJ);
+        p.off_gw[l] = o; o += C::NT * (((l == 0 ? C::TJ : C::TI * C::TJ) + 1) & ~1);     // pair-interleaved: even slot count
         p.off_gb[l] = o; o += C::KS * C::WP;
     }
     p.off_wout = o; o += C::NT;
@@ -297,7 +297,6 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     // thread `tid` lives at pgw[(r>>1)*2*NT + (r&1)] (pgw already includes 2*tid).  Every slot has exactly one
     // writer, so accumulating with fire-and-forget reductions (RED.ADD.F32: no load, no conversion, no
     // scoreboard wait) stays bitwise deterministic; the first tile of a window overwrites instead.
-    static_assert(C::TJ % 2 == 0, "pair layout");
     constexpr int PSL = C::TP / C::KS;
     const int pbeg = kslice * PSL;
 #pragma unroll
@@ -333,14 +332,15 @@ __device__ __forceinline__ void gw_gemm(const float* __restrict__ Bprev, const f
     for (int t = 0; t < TIK; ++t)
 #pragma unroll
         for (int u = 0; u < C::TJ; ++u) { float lo, hi; unpack2(acc2[t][u], lo, hi); acc[t][u] = lo + hi; }
+    constexpr int NE = TIK * C::TJ;
 #pragma unroll
-    for (int t = 0; t < TIK; ++t)
-#pragma unroll
-        for (int u = 0; u < C::TJ; u += 2) {
-            float* q = pgw + ((t * C::TJ + u) >> 1) * (2 * C::NT);
-            if (first) __stcg(reinterpret_cast<float2*>(q), make_float2(acc[t][u], acc[t][u + 1]));
-            else { atomicAdd(q, acc[t][u]); atomicAdd(q + 1, acc[t][u + 1]); }
-        }
+    for (int r = 0; r < NE; r += 2) {
+        float* q = pgw + (r >> 1) * (2 * C::NT);
+        const float v0 = acc[r / C::TJ][r % C::TJ];
+        const float v1 = (r + 1 < NE) ? acc[(r + 1 < NE ? r + 1 : r) / C::TJ][(r + 1 < NE ? r + 1 : r) % C::TJ] : 0.f;
+        if (first) __stcg(reinterpret_cast<float2*>(q), make_float2(v0, v1));
+        else { atomicAdd(q, v0); if (r + 1 < NE) atomicAdd(q + 1, v1); }
+    }
     if (ig == 0) {
 #pragma unroll
         for (int u = 0; u < C::TJ; ++u) {
