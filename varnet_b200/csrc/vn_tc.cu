@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) tc_layer0_kernel(const L0Args a) {
 struct OutArgs {
     TileArgs in; unsigned int base, nPts; int WP; bool needGrad;
     const float* Alast; size_t sQm;
-    float* U; float* seeds; unsigned int cap; double* g64;
+    float* seeds; unsigned int cap; double* g64;
 };
 // output layer (Dense(1), linear): u_s = A_{L-1,s} . w_out (+ b_out); then per mode the integrand
 // (TFModel.py:653-660), the BC/IC residual and its seed (TFModel.py:643-650), or the model value.
@@ -851,24 +851,23 @@ __global__ void tc_grad_out_kernel(const double* __restrict__ g, float* __restri
 
 // ------------------------------------------------------------------ host side
 struct Work {
-    float *Wn, *Wt, *X, *Apm, *Anm, *Dpm, *Dnm, *U, *seeds, *cross;
-    size_t sPm, sNm, layerStride, bytes;
+    float *Wn, *Wt, *X, *Aqm, *Anm, *Dqm, *Dnm, *seeds, *cross;
+    size_t sQm, sNm, layerStride, bytes;     // stream strides of the quad-major / neuron-major arrays, layer stride
 };
 Work carve(void* base, int L, int S, int WP, unsigned int cap) {
     Work w;
     size_t off = 0;
     auto take = [&](size_t nfloats) { float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; };
-    w.sPm = (size_t)cap * WP; w.sNm = (size_t)WP * cap; w.layerStride = (size_t)S * w.sPm;
+    w.sQm = (size_t)cap * WP; w.sNm = (size_t)WP * cap; w.layerStride = (size_t)S * w.sQm;
     w.Wn = take((size_t)std::max(L - 1, 1) * WP * WP);
     w.Wt = take((size_t)std::max(L - 1, 1) * WP * WP);
     w.X = take((size_t)VN_KIN * cap);
-    w.Apm = take((size_t)L * w.layerStride);
+    w.Aqm = take((size_t)L * w.layerStride);
     w.Anm = take((size_t)L * w.layerStride);
-    w.Dpm = take(2 * w.layerStride);
+    w.Dqm = take(2 * w.layerStride);
     w.Dnm = take(2 * w.layerStride);
-    w.U = take((size_t)S * cap);
     w.seeds = take((size_t)S * cap);
-    w.cross = take(w.sPm);
+    w.cross = take(w.sQm);
     w.bytes = off;
     return w;
 }
@@ -991,8 +990,6 @@ cudaError_t vn_tc_run(TcJob& j) {
         if (base > cap) return cudaErrorInvalidValue;
         chunk = cap / base * base;
     }
-    const int tilesW[2] = {1, 1};
-    (void)tilesW;
     for (unsigned long long c0 = 0; c0 < A.P; c0 += chunk) {
         const unsigned int base = (unsigned int)c0;
         const unsigned int valid = (unsigned int)std::min<unsigned long long>(chunk, A.P - c0);
@@ -1001,7 +998,7 @@ cudaError_t vn_tc_run(TcJob& j) {
 
         // ---- layer 0
         {
-            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Aqm = w.Apm; a.Anm = w.Anm; a.sQm = w.sPm; a.sNm = w.sNm; a.cap = cap;
+            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Aqm = w.Aqm; a.Anm = w.Anm; a.sQm = w.sQm; a.sNm = w.sNm; a.cap = cap;
             const dim3 grid(nPts / 32, WP / 32);
 #define CALL(SS) launch_layer0<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
@@ -1012,13 +1009,13 @@ cudaError_t vn_tc_run(TcJob& j) {
         for (int l = 1; l < L; ++l) {
             for (int sidx = 0; sidx < S; ++sidx) {
                 GemmArgs g{};
-                g.A = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm; g.rows = cap;
+                g.A = w.Aqm + (size_t)(l - 1) * w.layerStride + sidx * w.sQm; g.rows = cap;
                 g.B = w.Wt + (size_t)(l - 1) * WP * WP; g.rowsB = WP;
                 g.K = (net.width[l - 1] + KC - 1) / KC * KC;
                 g.nTilesN = (net.width[l] + TN - 1) / TN;
                 g.bias = A.theta + net.boff[l]; g.widthOut = net.width[l];
-                g.val = w.Apm + (size_t)l * w.layerStride;
-                g.outQm = w.Apm + (size_t)l * w.layerStride + sidx * w.sPm;
+                g.val = w.Aqm + (size_t)l * w.layerStride;
+                g.outQm = w.Aqm + (size_t)l * w.layerStride + sidx * w.sQm;
                 g.outNm = w.Anm + (size_t)l * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx == 0) TCK(launch_gemm<EPI_FWD_VALUE>(act, g, mTiles * g.nTilesN, st));
@@ -1029,7 +1026,7 @@ cudaError_t vn_tc_run(TcJob& j) {
         // ---- output layer + integrand / BC-IC residual / value
         {
             OutArgs a; a.in = A; a.base = base; a.nPts = nPts; a.WP = WP; a.needGrad = j.needGrad;
-            a.Alast = w.Apm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sPm; a.U = w.U; a.seeds = w.seeds; a.cap = cap; a.g64 = j.g64;
+            a.Alast = w.Aqm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sQm; a.seeds = w.seeds; a.cap = cap; a.g64 = j.g64;
             const unsigned int grid = (nPts + 255) / 256;
             if (j.mode == TC_VAR) {
 #define CALL(SS) (tc_out_kernel<SS, TC_VAR><<<grid, 256, 0, st>>>(a), cudaGetLastError())
@@ -1061,8 +1058,8 @@ cudaError_t vn_tc_run(TcJob& j) {
         int cur = 0;
         {
             TopArgs a; a.WP = WP; a.wlast = net.width[L - 1]; a.wout = A.theta + net.woff[L];
-            a.Aqm = w.Apm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sPm; a.seeds = w.seeds; a.cap = cap; a.nPts = nPts;
-            a.Dqm = w.Dpm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
+            a.Aqm = w.Aqm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sQm; a.seeds = w.seeds; a.cap = cap; a.nPts = nPts;
+            a.Dqm = w.Dqm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
             const dim3 grid((nPts / 32 + 3) / 4, WP / 32);
 #define CALL(SS) launch_top<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
@@ -1105,14 +1102,14 @@ cudaError_t vn_tc_run(TcJob& j) {
             // second-order term `cross`), then the value stream
             for (int sidx = S - 1; sidx >= 0; --sidx) {
                 GemmArgs g{};
-                g.A = w.Dpm + (size_t)cur * w.layerStride + sidx * w.sPm; g.rows = cap;
+                g.A = w.Dqm + (size_t)cur * w.layerStride + sidx * w.sQm; g.rows = cap;
                 g.B = w.Wn + (size_t)(l - 1) * WP * WP; g.rowsB = WP;
                 g.K = (net.width[l] + KC - 1) / KC * KC;
                 g.nTilesN = (net.width[l - 1] + TN - 1) / TN;
-                g.val = w.Apm + (size_t)(l - 1) * w.layerStride;
-                g.tan = w.Apm + (size_t)(l - 1) * w.layerStride + sidx * w.sPm;
+                g.val = w.Aqm + (size_t)(l - 1) * w.layerStride;
+                g.tan = w.Aqm + (size_t)(l - 1) * w.layerStride + sidx * w.sQm;
                 g.cross = w.cross;
-                g.outQm = w.Dpm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sPm;
+                g.outQm = w.Dqm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sQm;
                 g.outNm = w.Dnm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx > 0) { g.crossMode = (sidx == S - 1) ? 0 : 1; TCK(launch_gemm<EPI_ADJ_TANGENT>(act, g, mTiles * g.nTilesN, st)); }
