@@ -932,7 +932,10 @@ static int read_scalars(vn_engine* e, float out[4]) {
     int tcErr = 0;
     if (e->wclass == 256) CK(cudaMemcpyAsync(&tcErr, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    if (tcErr) return fail(VN_E_CUDA, "tensor-core pipeline: an mbarrier wait expired (results invalid)");
+    if (tcErr) {
+        cudaMemsetAsync(e->tcErr.p, 0, sizeof(int), e->stream);       // report once; the next call starts clean
+        return fail(VN_E_CUDA, "tensor-core pipeline: an mbarrier wait expired (results of this call are invalid)");
+    }
     return VN_OK;
 }
 

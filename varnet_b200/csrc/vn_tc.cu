@@ -908,7 +908,7 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
     for (int l = 0; l < net.L; ++l) wmax = std::max(wmax, net.width[l]);
     if (wmax > 256 || S < 1 || S > 3) return false;
     g->WP = wmax <= 128 ? 128 : 256;
-    int waves = 4;                                                   // 128-point tiles per SM and chunk
+    int waves = 8;                                                   // 128-point tiles per SM and chunk
     if (const char* w = getenv("VARNET_B200_TC_WAVES")) waves = std::max(1, std::min(16, atoi(w)));
     g->capPts = (unsigned int)numSMs * TM * waves;
     g->workBytes = carve(nullptr, net.L, S, g->WP, g->capPts).bytes;
