@@ -23,6 +23,16 @@ constexpr int NST = 3;                               // pipeline stages
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A hi, A lo, B hi, B lo
 constexpr int BAR_OFF = NST * STAGE_BYTES;         // mbarriers: full[NST] (256 loader arrivals), empty[NST] and done (tcgen05.commit)
 constexpr int SMEM_BYTES = BAR_OFF + 128;
+// A-from-TMEM variant of the layer GEMM (tc_gemm_kernel<..., TS = true>): the activation operand is written by its
+// loader threads straight into tensor memory, so the MMAs read only the weight tiles from shared memory
+// (48 KB per K chunk instead of 96 KB) and the loaders store only those (32 KB instead of 64 KB): the main loop is
+// no longer shared-memory bound.  TMEM: two main sets + the small-term set (384 columns) + two A stages of
+// (hi 32 | lo 32) columns.
+constexpr int TS_NST = 2;
+constexpr int TS_STAGE_BYTES = 2 * TILE_BYTES;       // B hi, B lo
+constexpr int TS_BAR_OFF = TS_NST * TS_STAGE_BYTES;
+constexpr int TS_SMEM_BYTES = TS_BAR_OFF + 128;
+constexpr uint32_t TS_ACOL = 3 * 128;
 constexpr uint32_t TMEM_COLS = 512;                  // four 128-column accumulator sets: three rotating main sets + the small terms
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -72,6 +82,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (lane = row, one 32-bit K element per column), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t dTmem, uint32_t aTmem, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(dTmem), "r"(aTmem), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -157,9 +182,9 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t stageAddr, b
 struct Bars {
     uint32_t full, empty, done;         // shared-space addresses; full + 8*b, empty + 8*b
 };
-__device__ __forceinline__ uint32_t pipe_setup(unsigned char* smem, int tid, int warp, Bars& bars) {
-    uint64_t* bp = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 8 * (2 * NST + 1));
+__device__ __forceinline__ uint32_t pipe_setup(unsigned char* smem, int tid, int warp, Bars& bars, int barOff = BAR_OFF) {
+    uint64_t* bp = reinterpret_cast<uint64_t*>(smem + barOff);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + barOff + 8 * (2 * NST + 1));
     bars.full = smem_u32(bp); bars.empty = smem_u32(bp + NST); bars.done = smem_u32(bp + 2 * NST);
     if (tid == 0) {
 #pragma unroll
@@ -238,7 +263,7 @@ __device__ __forceinline__ float4* qm_ptr(float* base, unsigned int rows, size_t
     return reinterpret_cast<float4*>(base + ((size_t)(n / 4) * rows + prow) * 4);
 }
 
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool TS>
 __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,17 +272,38 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
     const size_t m0 = (size_t)mt * TM;
     const int n0 = nt * TN;
     Bars bars;
-    const uint32_t tmem = pipe_setup(smem, tid, warp, bars);
+    const uint32_t tmem = pipe_setup(smem, tid, warp, bars, TS ? TS_BAR_OFF : BAR_OFF);
     const int nIt = a.K / KC;
 
     if (warp == NTHR / 32) {
-        // ---- MMA warp: the main chain rotates over three column sets (chains of <= K/24 MMAs)
+        // ---- MMA warp: the main chain rotates over three (TS: two) column sets
         if (lane == 0) {
-            const bool ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
-                const int kbg = it * (KC / 8) + kb;
-                fresh = kbg < 3;
-                return kbg % 3;
-            });
+            bool ok = true;
+            if constexpr (TS) {
+                for (int it = 0; it < nIt; ++it) {
+                    const int b = it % TS_NST;
+                    if (ok) ok = mbar_wait(bars.full + 8 * b, (uint32_t)(it / TS_NST) & 1u);
+                    tc_fence_after();
+                    const uint32_t bHi = smem_u32(smem + b * TS_STAGE_BYTES), bLo = bHi + TILE_BYTES;
+                    const uint32_t aHi = tmem + TS_ACOL + b * 64, aLo = aHi + 32;
+#pragma unroll
+                    for (int kb = 0; kb < KC / 8; ++kb) {
+                        const uint64_t dBh = make_desc(bHi + kb * 2 * TILE_LBO), dBl = make_desc(bLo + kb * 2 * TILE_LBO);
+                        mma_tf32_ts(tmem + 2 * TN, aLo + kb * 8, dBh, (it == 0 && kb == 0) ? 0u : 1u);
+                        mma_tf32_ts(tmem + 2 * TN, aHi + kb * 8, dBl, 1u);
+                        const int kbg = it * (KC / 8) + kb;
+                        mma_tf32_ts(tmem + (kbg & 1) * TN, aHi + kb * 8, dBh, kbg < 2 ? 0u : 1u);
+                    }
+                    mma_commit(bars.empty + 8 * b);
+                }
+                mma_commit(bars.done);
+            } else {
+                ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
+                    const int kbg = it * (KC / 8) + kb;
+                    fresh = kbg < 3;
+                    return kbg % 3;
+                });
+            }
             if (!ok) *a.err = 1;
         }
     } else {
@@ -265,13 +311,52 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
         const Opnd oa{a.A + m0 * 4, a.rows}, ob{a.B + (size_t)n0 * 4, (size_t)a.rowsB};
         auto src = [&](int it) { return ChunkSrc{oa, ob, it * KC}; };
         TileRegs ra[2], rb[2];                                                // two K chunks in flight
+        bool ok = true;
+        if constexpr (TS) {
+            // A: thread = its own row (TMEM lane) x 16 K elements (warps 0-3: K 0..15 of the chunk, warps 4-7: K 16..31)
+            const int arow = (warp & 3) * 32 + lane, ahalf = warp >> 2;
+            const uint32_t tA = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TS_ACOL + ahalf * 16;
+            auto loadA = [&](int it, TileRegs& r) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    r.v[j] = __ldg(reinterpret_cast<const float4*>(oa.p + ((size_t)(it * (KC / 4) + ahalf * 4 + j) * oa.ld + arow) * 4));
+            };
+            auto step = [&](int it, TileRegs& rA, TileRegs& rB) {
+                const int b = it % TS_NST;
+                unsigned char* stage = smem + b * TS_STAGE_BYTES;
+                if (it >= TS_NST && ok) ok = mbar_wait(bars.empty + 8 * b, (uint32_t)((it / TS_NST) - 1) & 1u);
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = rA.v[j];
+                    hi[4 * j] = tf32_rn(v.x); hi[4 * j + 1] = tf32_rn(v.y); hi[4 * j + 2] = tf32_rn(v.z); hi[4 * j + 3] = tf32_rn(v.w);
+                    lo[4 * j] = v.x - hi[4 * j]; lo[4 * j + 1] = v.y - hi[4 * j + 1]; lo[4 * j + 2] = v.z - hi[4 * j + 2]; lo[4 * j + 3] = v.w - hi[4 * j + 3];
+                }
+                tc_fence_after();
+                tmem_st16(tA + b * 64, hi);
+                tmem_st16(tA + b * 64 + 32, lo);
+                tile_store_split<true>(rB, stage, stage + TILE_BYTES, tid);
+                if (it + 2 < nIt) { loadA(it + 2, rA); tile_load<true>(ob, (it + 2) * KC, rB, tid); }
+                tmem_wait_st();
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bars.full + 8 * b);
+            };
+            loadA(0, ra[0]); tile_load<true>(ob, 0, rb[0], tid);
+            if (nIt > 1) { loadA(1, ra[1]); tile_load<true>(ob, KC, rb[1], tid); }
+#pragma unroll 1
+            for (int it0 = 0; it0 < nIt; it0 += 2) {
+                step(it0, ra[0], rb[0]);
+                if (it0 + 1 < nIt) step(it0 + 1, ra[1], rb[1]);
+            }
+        } else {
         tile_load<true>(oa, 0, ra[0], tid); tile_load<true>(ob, 0, rb[0], tid);
         if (nIt > 1) { tile_load<true>(oa, KC, ra[1], tid); tile_load<true>(ob, KC, rb[1], tid); }
-        bool ok = true;
 #pragma unroll 1
         for (int it0 = 0; it0 < nIt; it0 += 2) {
             loader_step<true>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
             if (it0 + 1 < nIt) loader_step<true>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
+        }
         }
 
         const int row = (warp & 3) * 32 + lane, half = warp >> 2;
@@ -302,10 +387,10 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
             tmem_ld16(tlane + cb * 16, z);
             tmem_ld16(tlane + TN + cb * 16, t1);
             tmem_ld16(tlane + 2 * TN + cb * 16, t2);
-            tmem_ld16(tlane + 3 * TN + cb * 16, t3);
+            if (!TS) tmem_ld16(tlane + 3 * TN + cb * 16, t3);
             tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) z[c] = (z[c] + t1[c]) + (t2[c] + t3[c]);     // FP32, round to nearest
+            for (int c = 0; c < 16; ++c) z[c] = TS ? (z[c] + t1[c]) + t2[c] : (z[c] + t1[c]) + (t2[c] + t3[c]);     // FP32, round to nearest
             if (EPI == EPI_FWD_VALUE) {
                 // a = act(z + b)   (App. A.2)
 #pragma unroll
@@ -872,15 +957,23 @@ Work carve(void* base, int L, int S, int WP, unsigned int cap) {
     return w;
 }
 
+bool g_ts = true;        // A-from-TMEM variant of the layer GEMMs (VARNET_B200_TC_TS=0 selects the all-shared-memory pipeline)
 template <int EPI> cudaError_t launch_gemm(int act, const GemmArgs& g, int grid, cudaStream_t st) {
-    if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
-    else tc_gemm_kernel<EPI, VN_TANH><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
+    if (g_ts) {
+        if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID, true><<<grid, NTHR_ALL, TS_SMEM_BYTES, st>>>(g);
+        else tc_gemm_kernel<EPI, VN_TANH, true><<<grid, NTHR_ALL, TS_SMEM_BYTES, st>>>(g);
+    } else {
+        if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID, false><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
+        else tc_gemm_kernel<EPI, VN_TANH, false><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
+    }
     return cudaGetLastError();
 }
 template <int EPI> cudaError_t prep_gemm() {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_SIGMOID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_TANH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_SIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_gemm_kernel<EPI, VN_TANH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
 }
 
 template <int S> cudaError_t launch_layer0(int act, const L0Args& a, dim3 grid, cudaStream_t st) {
@@ -919,6 +1012,7 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
 
 cudaError_t vn_tc_prepare(int S, int act) {
     (void)S; (void)act;
+    if (const char* t = getenv("VARNET_B200_TC_TS")) g_ts = atoi(t) != 0;
     cudaError_t e = cudaFuncSetAttribute(tc_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_FWD_VALUE>()) != cudaSuccess) return e;
