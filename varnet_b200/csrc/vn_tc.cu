@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <algorithm>
 #include "vn_tc.h"
 
@@ -263,40 +264,50 @@ __device__ __forceinline__ float4* qm_ptr(float* base, unsigned int rows, size_t
     return reinterpret_cast<float4*>(base + ((size_t)(n / 4) * rows + prow) * 4);
 }
 
+// TS kernels are built for two co-resident CTAs per SM (66 KB of shared memory, <= 112 registers): each CTA needs all
+// 512 TMEM columns, so `tcgen05.alloc` of the second CTA blocks until the first one has drained its accumulators into
+// registers and released them — its prologue (barrier set-up, first global loads) overlaps the other CTA's main loop,
+// and its epilogue arithmetic / stores overlap the other CTA's next main loop.
 template <int EPI, int ACT, bool TS>
-__global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(TS ? NTHR : NTHR_ALL, TS ? 2 : 1) tc_gemm_kernel(const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (*reinterpret_cast<volatile int*>(a.err)) return;                      // an earlier launch lost a barrier: do not spin again
     const int mt = blockIdx.x / a.nTilesN, nt = blockIdx.x - mt * a.nTilesN;
     const size_t m0 = (size_t)mt * TM;
     const int n0 = nt * TN;
+    const int nIt = a.K / KC;
+    const bool loader = TS || warp < NTHR / 32;                               // TS: 8 warps, thread 0 also issues the MMAs (two CTAs per SM need <= 128 registers x 256 threads)
+    const Opnd oa{a.A + m0 * 4, a.rows}, ob{a.B + (size_t)n0 * 4, (size_t)a.rowsB};
+    // TS: thread = its own row (TMEM lane) x 16 K elements (warps 0-3: K 0..15 of the chunk, warps 4-7: K 16..31)
+    const int arow = (warp & 3) * 32 + lane, ahalf = (warp >> 2) & 1;
+    auto loadA = [&](int it, TileRegs& r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            r.v[j] = __ldg(reinterpret_cast<const float4*>(oa.p + ((size_t)(it * (KC / 4) + ahalf * 4 + j) * oa.ld + arow) * 4));
+    };
+    TileRegs ra[2], rb[2];                                                    // two K chunks in flight
+    if (loader) {                                                             // first loads before TMEM is even allocated
+        if (TS) loadA(0, ra[0]); else tile_load<true>(oa, 0, ra[0], tid);
+        tile_load<true>(ob, 0, rb[0], tid);
+        if (nIt > 1) {
+            if (TS) loadA(1, ra[1]); else tile_load<true>(oa, KC, ra[1], tid);
+            tile_load<true>(ob, KC, rb[1], tid);
+        }
+    }
     Bars bars;
     const uint32_t tmem = pipe_setup(smem, tid, warp, bars, TS ? TS_BAR_OFF : BAR_OFF);
-    const int nIt = a.K / KC;
 
-    if (warp == NTHR / 32) {
+    const int row = (warp & 3) * 32 + lane, half = (warp >> 2) & 1;
+    const size_t prow = m0 + row;
+    const int nb = n0 + half * 64;                                            // first of this thread's 64 columns
+    float zs[64];                                                             // this thread's accumulator sums
+    if (!loader) {
         // ---- MMA warp: the main chain rotates over three (TS: two) column sets
         if (lane == 0) {
             bool ok = true;
             if constexpr (TS) {
-                for (int it = 0; it < nIt; ++it) {
-                    const int b = it % TS_NST;
-                    if (ok) ok = mbar_wait(bars.full + 8 * b, (uint32_t)(it / TS_NST) & 1u);
-                    tc_fence_after();
-                    const uint32_t bHi = smem_u32(smem + b * TS_STAGE_BYTES), bLo = bHi + TILE_BYTES;
-                    const uint32_t aHi = tmem + TS_ACOL + b * 64, aLo = aHi + 32;
-#pragma unroll
-                    for (int kb = 0; kb < KC / 8; ++kb) {
-                        const uint64_t dBh = make_desc(bHi + kb * 2 * TILE_LBO), dBl = make_desc(bLo + kb * 2 * TILE_LBO);
-                        mma_tf32_ts(tmem + 2 * TN, aLo + kb * 8, dBh, (it == 0 && kb == 0) ? 0u : 1u);
-                        mma_tf32_ts(tmem + 2 * TN, aHi + kb * 8, dBl, 1u);
-                        const int kbg = it * (KC / 8) + kb;
-                        mma_tf32_ts(tmem + (kbg & 1) * TN, aHi + kb * 8, dBh, kbg < 2 ? 0u : 1u);
-                    }
-                    mma_commit(bars.empty + 8 * b);
-                }
-                mma_commit(bars.done);
+                (void)ok;
             } else {
                 ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
                     const int kbg = it * (KC / 8) + kb;
@@ -307,20 +318,10 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
             if (!ok) *a.err = 1;
         }
     } else {
-        // ---- loaders, then epilogue: thread = one point (TMEM lane), warps 0-3 / 4-7 take the two column halves
-        const Opnd oa{a.A + m0 * 4, a.rows}, ob{a.B + (size_t)n0 * 4, (size_t)a.rowsB};
-        auto src = [&](int it) { return ChunkSrc{oa, ob, it * KC}; };
-        TileRegs ra[2], rb[2];                                                // two K chunks in flight
+        // ---- loaders
         bool ok = true;
         if constexpr (TS) {
-            // A: thread = its own row (TMEM lane) x 16 K elements (warps 0-3: K 0..15 of the chunk, warps 4-7: K 16..31)
-            const int arow = (warp & 3) * 32 + lane, ahalf = warp >> 2;
             const uint32_t tA = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TS_ACOL + ahalf * 16;
-            auto loadA = [&](int it, TileRegs& r) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    r.v[j] = __ldg(reinterpret_cast<const float4*>(oa.p + ((size_t)(it * (KC / 4) + ahalf * 4 + j) * oa.ld + arow) * 4));
-            };
             auto step = [&](int it, TileRegs& rA, TileRegs& rB) {
                 const int b = it % TS_NST;
                 unsigned char* stage = smem + b * TS_STAGE_BYTES;
@@ -341,48 +342,45 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
                 fence_async_smem();
                 tc_fence_before();
                 mbar_arrive(bars.full + 8 * b);
+                if (tid == 0) {
+                    // MMAs of this chunk: small products into set 2, hi*hi alternating between sets 0 and 1
+                    if (ok) ok = mbar_wait(bars.full + 8 * b, (uint32_t)(it / TS_NST) & 1u);
+                    tc_fence_after();
+                    const uint32_t bHi = smem_u32(stage), bLo = bHi + TILE_BYTES;
+                    const uint32_t aHi = tmem + TS_ACOL + b * 64, aLo = aHi + 32;
+#pragma unroll
+                    for (int kb = 0; kb < KC / 8; ++kb) {
+                        const uint64_t dBh = make_desc(bHi + kb * 2 * TILE_LBO), dBl = make_desc(bLo + kb * 2 * TILE_LBO);
+                        mma_tf32_ts(tmem + 2 * TN, aLo + kb * 8, dBh, (it == 0 && kb == 0) ? 0u : 1u);
+                        mma_tf32_ts(tmem + 2 * TN, aHi + kb * 8, dBl, 1u);
+                        const int kbg = it * (KC / 8) + kb;
+                        mma_tf32_ts(tmem + (kbg & 1) * TN, aHi + kb * 8, dBh, kbg < 2 ? 0u : 1u);
+                    }
+                    mma_commit(bars.empty + 8 * b);
+                }
             };
-            loadA(0, ra[0]); tile_load<true>(ob, 0, rb[0], tid);
-            if (nIt > 1) { loadA(1, ra[1]); tile_load<true>(ob, KC, rb[1], tid); }
 #pragma unroll 1
             for (int it0 = 0; it0 < nIt; it0 += 2) {
                 step(it0, ra[0], rb[0]);
                 if (it0 + 1 < nIt) step(it0 + 1, ra[1], rb[1]);
             }
+            if (tid == 0) mma_commit(bars.done);
         } else {
-        tile_load<true>(oa, 0, ra[0], tid); tile_load<true>(ob, 0, rb[0], tid);
-        if (nIt > 1) { tile_load<true>(oa, KC, ra[1], tid); tile_load<true>(ob, KC, rb[1], tid); }
+            auto src = [&](int it) { return ChunkSrc{oa, ob, it * KC}; };
 #pragma unroll 1
-        for (int it0 = 0; it0 < nIt; it0 += 2) {
-            loader_step<true>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
-            if (it0 + 1 < nIt) loader_step<true>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
+            for (int it0 = 0; it0 < nIt; it0 += 2) {
+                loader_step<true>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
+                if (it0 + 1 < nIt) loader_step<true>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
+            }
         }
-        }
-
-        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
-        const size_t prow = m0 + row;
-        const int nb = n0 + half * 64;                                        // first of this thread's 64 columns
-        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
-        // epilogue operands of all 64 columns are requested before the accumulators are complete
-        float av[EPI == EPI_FWD_VALUE ? 1 : 64], xv[(EPI == EPI_ADJ_TANGENT || EPI == EPI_ADJ_VALUE) ? 64 : 1];
-        if (EPI != EPI_FWD_VALUE) {
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.val, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(av[cb * 16 % (EPI == EPI_FWD_VALUE ? 1 : 64)]));
-        }
-        if (EPI == EPI_ADJ_TANGENT) {
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.tan, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_TANGENT ? 64 : 1)]));
-        }
-        if (EPI == EPI_ADJ_VALUE && a.crossMode) {
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) ld16(a.cross, a.rows, prow, nb + cb * 16, reinterpret_cast<float(&)[16]>(xv[cb * 16 % (EPI == EPI_ADJ_VALUE ? 64 : 1)]));
-        }
+        // ---- drain: thread = one point (TMEM lane), warps 0-3 / 4-7 take the two column halves; the accumulator sets are
+        // summed in FP32 (round to nearest) into registers so that tensor memory can be released before the epilogue
         if (ok) ok = mbar_wait(bars.done, 0u);
         if (!ok) *a.err = 1;
         tc_fence_after();
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
-            const int n = nb + cb * 16;
             float z[16], t1[16], t2[16], t3[16];
             tmem_ld16(tlane + cb * 16, z);
             tmem_ld16(tlane + TN + cb * 16, t1);
@@ -390,55 +388,66 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gemm_kernel(const GemmArgs a) 
             if (!TS) tmem_ld16(tlane + 3 * TN + cb * 16, t3);
             tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) z[c] = TS ? (z[c] + t1[c]) + t2[c] : (z[c] + t1[c]) + (t2[c] + t3[c]);     // FP32, round to nearest
-            if (EPI == EPI_FWD_VALUE) {
-                // a = act(z + b)   (App. A.2)
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float bv = (n + c < a.widthOut) ? __ldg(a.bias + n + c) : 0.f;
-                    z[c] = act_f<ACT>(z[c] + bv);
-                }
-            } else if (EPI == EPI_FWD_TANGENT) {
-                // tangent stream: act'(z) * zdot, act' from the value a of this layer
-#pragma unroll
-                for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
-            } else if (EPI == EPI_ADJ_TANGENT) {
-                // dabar_k -> dzbar_k = dabar_k act'; its share of the second-order term: cross += dabar_k * adot_k   (App. A.3)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float* cp = reinterpret_cast<float*>(qm_ptr(a.cross, a.rows, prow, n + 4 * q));
-                    const float c0 = z[4 * q] * xv[(cb * 16 + 4 * q) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
-                    const float c1 = z[4 * q + 1] * xv[(cb * 16 + 4 * q + 1) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
-                    const float c2 = z[4 * q + 2] * xv[(cb * 16 + 4 * q + 2) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
-                    const float c3 = z[4 * q + 3] * xv[(cb * 16 + 4 * q + 3) % (EPI == EPI_ADJ_TANGENT ? 64 : 1)];
-                    if (a.crossMode) red_add_v4(cp, c0, c1, c2, c3);
-                    else *reinterpret_cast<float4*>(cp) = make_float4(c0, c1, c2, c3);
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)]);
-            } else {
-                // abar -> zbar = abar act' + act''/act' * cross
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float aa = av[(cb * 16 + c) % (EPI == EPI_FWD_VALUE ? 1 : 64)], d1 = act_d1<ACT>(aa);
-                    z[c] = a.crossMode ? fmaf(z[c], d1, act_d2r<ACT>(aa) * xv[(cb * 16 + c) % (EPI == EPI_ADJ_VALUE ? 64 : 1)]) : z[c] * d1;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) *qm_ptr(a.outQm, a.rows, prow, n + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-            float* nm = a.outNm + (size_t)n * a.ldNm + prow;
-            if (EPI == EPI_FWD_VALUE || EPI == EPI_FWD_TANGENT) {           // read once, much later (tc_gw): keep it out of the way in L2
-#pragma unroll
-                for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);
-            } else {                                                         // zbar: tc_gw consumes it right after this launch
-#pragma unroll
-                for (int c = 0; c < 16; ++c) nm[(size_t)c * a.ldNm] = z[c];
-            }
+            for (int c = 0; c < 16; ++c) zs[cb * 16 + c] = TS ? (z[c] + t1[c]) + t2[c] : (z[c] + t1[c]) + (t2[c] + t3[c]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+    if (!loader) return;
+
+    // ---- epilogue from registers (operands are quad-major: every access of a warp is a contiguous 512-byte run)
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        const int n = nb + cb * 16;
+        float z[16], av[16], xv[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) z[c] = zs[cb * 16 + c];
+        if (EPI != EPI_FWD_VALUE) ld16(a.val, a.rows, prow, n, av);
+        if (EPI == EPI_ADJ_TANGENT) ld16(a.tan, a.rows, prow, n, xv);
+        if (EPI == EPI_ADJ_VALUE && a.crossMode) ld16(a.cross, a.rows, prow, n, xv);
+        if (EPI == EPI_FWD_VALUE) {
+            // a = act(z + b)   (App. A.2)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float bv = (n + c < a.widthOut) ? __ldg(a.bias + n + c) : 0.f;
+                z[c] = act_f<ACT>(z[c] + bv);
+            }
+        } else if (EPI == EPI_FWD_TANGENT) {
+            // tangent stream: act'(z) * zdot, act' from the value a of this layer
+#pragma unroll
+            for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[c]);
+        } else if (EPI == EPI_ADJ_TANGENT) {
+            // dabar_k -> dzbar_k = dabar_k act'; its share of the second-order term: cross += dabar_k * adot_k   (App. A.3)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float* cp = reinterpret_cast<float*>(qm_ptr(a.cross, a.rows, prow, n + 4 * q));
+                const float c0 = z[4 * q] * xv[4 * q], c1 = z[4 * q + 1] * xv[4 * q + 1];
+                const float c2 = z[4 * q + 2] * xv[4 * q + 2], c3 = z[4 * q + 3] * xv[4 * q + 3];
+                if (a.crossMode) red_add_v4(cp, c0, c1, c2, c3);
+                else *reinterpret_cast<float4*>(cp) = make_float4(c0, c1, c2, c3);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) z[c] *= act_d1<ACT>(av[c]);
+        } else {
+            // abar -> zbar = abar act' + act''/act' * cross
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float d1 = act_d1<ACT>(av[c]);
+                z[c] = a.crossMode ? fmaf(z[c], d1, act_d2r<ACT>(av[c]) * xv[c]) : z[c] * d1;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *qm_ptr(a.outQm, a.rows, prow, n + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+        float* nm = a.outNm + (size_t)n * a.ldNm + prow;
+        if (EPI == EPI_FWD_VALUE || EPI == EPI_FWD_TANGENT) {           // read once, much later (tc_gw): keep it out of the way in L2
+#pragma unroll
+            for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);
+        } else {                                                         // zbar: tc_gw consumes it right after this launch
+#pragma unroll
+            for (int c = 0; c < 16; ++c) nm[(size_t)c * a.ldNm] = z[c];
+        }
+    }
 }
 
 // ------------------------------------------------------------------ weight-gradient GEMM (split-K over points)
@@ -960,8 +969,8 @@ Work carve(void* base, int L, int S, int WP, unsigned int cap) {
 bool g_ts = true;        // A-from-TMEM variant of the layer GEMMs (VARNET_B200_TC_TS=0 selects the all-shared-memory pipeline)
 template <int EPI> cudaError_t launch_gemm(int act, const GemmArgs& g, int grid, cudaStream_t st) {
     if (g_ts) {
-        if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID, true><<<grid, NTHR_ALL, TS_SMEM_BYTES, st>>>(g);
-        else tc_gemm_kernel<EPI, VN_TANH, true><<<grid, NTHR_ALL, TS_SMEM_BYTES, st>>>(g);
+        if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID, true><<<grid, NTHR, TS_SMEM_BYTES, st>>>(g);
+        else tc_gemm_kernel<EPI, VN_TANH, true><<<grid, NTHR, TS_SMEM_BYTES, st>>>(g);
     } else {
         if (act == VN_SIGMOID) tc_gemm_kernel<EPI, VN_SIGMOID, false><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
         else tc_gemm_kernel<EPI, VN_TANH, false><<<grid, NTHR_ALL, SMEM_BYTES, st>>>(g);
@@ -1013,12 +1022,25 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
 cudaError_t vn_tc_prepare(int S, int act) {
     (void)S; (void)act;
     if (const char* t = getenv("VARNET_B200_TC_TS")) g_ts = atoi(t) != 0;
+
     cudaError_t e = cudaFuncSetAttribute(tc_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_FWD_VALUE>()) != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_FWD_TANGENT>()) != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_ADJ_TANGENT>()) != cudaSuccess) return e;
-    return prep_gemm<EPI_ADJ_VALUE>();
+    if ((e = prep_gemm<EPI_ADJ_VALUE>()) != cudaSuccess) return e;
+    if (getenv("VARNET_B200_TC_DEBUG")) {
+        int nb = 0;
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>);
+        for (int pct = -1; pct <= 100; pct += (pct < 0 ? 51 : 10)) {
+            if (pct >= 0) cudaFuncSetAttribute(tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, NTHR, TS_SMEM_BYTES);
+            fprintf(stderr, "[vn_tc] A-from-TMEM layer GEMM: carveout %d%% -> %d CTAs/SM (smem %d B, %d regs, static smem %zu, local %zu)\n", pct, nb, TS_SMEM_BYTES, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes);
+        }
+        cudaFuncSetAttribute(tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, -1);
+    }
+    return cudaSuccess;
 }
 
 cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float* theta, void* work, cudaStream_t st) {
