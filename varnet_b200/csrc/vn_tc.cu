@@ -115,46 +115,61 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tmem) {
 }
 
 // ------------------------------------------------------------------ operand tiles
-// One tile = 128 rows x KC floats, loaded by 256 threads from one of two global layouts:
-//   quad-major  (QM): [K/4][rows][4]  — 16-byte units of four consecutive K of one row, rows contiguous.  This is the
-//                     order of the shared-memory canonical layout itself, so a warp reads 512 contiguous bytes and
-//                     writes four whole core matrices; the GEMM epilogues (thread = row) store it fully coalesced.
-//   row-major   (RM): [rows][ld]      — K contiguous per row (neuron-major activations, K = points, in tc_gw): a
-//                     quarter warp reads one 128-byte row segment and writes its eight K units conflict free thanks
-//                     to the padded TILE_LBO.
-struct Opnd { const float* p; size_t ld; };     // QM: p = base + row0*4, ld = rows of the array; RM: p = base + row0*ld, ld = row stride
+// One tile = 128 rows x KC floats, loaded by 256 threads.  Every activation array of a chunk is stored once, in the
+// quad-major layout [index/4][point][4] (16-byte units of four consecutive neurons of one point, points contiguous):
+//   LAY_QM — layer GEMMs (rows = points, K = neurons): the global order IS the order of the shared-memory canonical
+//            layout, so a warp reads 512 contiguous bytes and writes four whole core matrices, and the GEMM epilogues
+//            (thread = point) store and reload it fully coalesced;
+//   LAY_QT — weight-gradient GEMM (rows = neurons, K = points): a thread reads the four units (neuron quad, points
+//            4pg..4pg+3) — 64 contiguous bytes, a quarter warp 512 — transposes the 4x4 block in registers and writes
+//            four K units (neuron, 4 points); the 16-byte pad on TILE_LBO makes those stores conflict free.
+// No second (neuron-major) copy of the activations exists.
+enum { LAY_QM = 0, LAY_QT = 1 };
+struct Opnd { const float* p; size_t ld; };     // p = array + (first row / 4 for QT, first row for QM) term, ld = points of the array
 struct TileRegs { float4 v[TM * (KC / 4) / NTHR]; };
 
-template <bool QM>
-__device__ __forceinline__ void tile_map(int u, int& k4, int& row) {
-    if (QM) { row = u % TM; k4 = u / TM; } else { k4 = u % (KC / 4); row = u / (KC / 4); }
-}
-template <bool QM>
+template <int LAY>
 __device__ __forceinline__ void tile_load(const Opnd& o, int k0, TileRegs& r, int tid) {
     constexpr int U = TM * (KC / 4) / NTHR;
+    if (LAY == LAY_QM) {
 #pragma unroll
-    for (int i = 0; i < U; ++i) {
-        int k4, row;
-        tile_map<QM>(i * NTHR + tid, k4, row);
-        const float* src = QM ? o.p + ((size_t)(k0 / 4 + k4) * o.ld + row) * 4 : o.p + (size_t)row * o.ld + k0 + k4 * 4;
-        r.v[i] = __ldg(reinterpret_cast<const float4*>(src));
+        for (int i = 0; i < U; ++i) {
+            const int u = i * NTHR + tid, row = u % TM, k4 = u / TM;
+            r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)(k0 / 4 + k4) * o.ld + row) * 4));
+        }
+    } else {
+        static_assert(U == 4 && NTHR == (TM / 4) * (KC / 4), "one 4x4 block per thread");
+        const int n4 = tid / (KC / 4), pg = tid % (KC / 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)n4 * o.ld + k0 + 4 * pg + i) * 4));
     }
 }
 // round to the 10-bit TF32 mantissa (the tensor core itself truncates: a truncated split leaves a one-sided
-// 2^-21 bias per product that grows with K; rounding both halves makes the residual 2^-22 and sign-symmetric)
+// 2^-21 bias per product that grows with K; rounding the high half makes the residual sign-symmetric)
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-template <bool QM>
+__device__ __forceinline__ void store_split(float4 v, unsigned char* hiTile, unsigned char* loTile, uint32_t off) {
+    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+    *reinterpret_cast<float4*>(hiTile + off) = h;
+    *reinterpret_cast<float4*>(loTile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);   // truncated by the tensor core: unbiased here
+}
+template <int LAY>
 __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned char* hiTile, unsigned char* loTile, int tid) {
     constexpr int U = TM * (KC / 4) / NTHR;
+    if (LAY == LAY_QM) {
 #pragma unroll
-    for (int i = 0; i < U; ++i) {
-        int k4, row;
-        tile_map<QM>(i * NTHR + tid, k4, row);
-        const uint32_t off = k4 * TILE_LBO + row * 16;
-        const float4 v = r.v[i];
-        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-        *reinterpret_cast<float4*>(hiTile + off) = h;
-        *reinterpret_cast<float4*>(loTile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);   // sign-symmetric: truncation by the tensor core is unbiased here
+        for (int i = 0; i < U; ++i) {
+            const int u = i * NTHR + tid, row = u % TM, k4 = u / TM;
+            store_split(r.v[i], hiTile, loTile, k4 * TILE_LBO + row * 16);
+        }
+    } else {
+        const int n4 = tid / (KC / 4), pg = tid % (KC / 4);
+        const float4 a = r.v[0], b = r.v[1], c = r.v[2], d = r.v[3];       // points 4pg..4pg+3 of neurons 4n4..4n4+3
+        const uint32_t off = pg * TILE_LBO + (4 * n4) * 16;
+        store_split(make_float4(a.x, b.x, c.x, d.x), hiTile, loTile, off);
+        store_split(make_float4(a.y, b.y, c.y, d.y), hiTile, loTile, off + 16);
+        store_split(make_float4(a.z, b.z, c.z, d.z), hiTile, loTile, off + 32);
+        store_split(make_float4(a.w, b.w, c.w, d.w), hiTile, loTile, off + 48);
     }
 }
 
@@ -203,18 +218,18 @@ __device__ __forceinline__ uint32_t pipe_setup(unsigned char* smem, int tid, int
 // Loader side of one K chunk (256 threads): wait until the MMAs that read this stage three chunks ago are done,
 // write the split tiles, put the chunk after next in flight, publish the stage to the MMA warp.
 struct ChunkSrc { Opnd a, b; int k0; };
-template <bool QM, class F>
+template <int LAY, class F>
 __device__ __forceinline__ void loader_step(unsigned char* smem, const Bars& bars, int it, int nIt, TileRegs& ra, TileRegs& rb,
                                             F&& src, int tid, bool& ok) {
     const int b = it % NST;
     unsigned char* stage = smem + b * STAGE_BYTES;
     if (it >= NST && ok) ok = mbar_wait(bars.empty + 8 * b, (uint32_t)((it / NST) - 1) & 1u);
-    tile_store_split<QM>(ra, stage, stage + TILE_BYTES, tid);
-    tile_store_split<QM>(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
+    tile_store_split<LAY>(ra, stage, stage + TILE_BYTES, tid);
+    tile_store_split<LAY>(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
     if (it + 2 < nIt) {
         const ChunkSrc c = src(it + 2);
-        tile_load<QM>(c.a, c.k0, ra, tid);
-        tile_load<QM>(c.b, c.k0, rb, tid);
+        tile_load<LAY>(c.a, c.k0, ra, tid);
+        tile_load<LAY>(c.b, c.k0, rb, tid);
     }
     fence_async_smem();                 // generic-proxy stores -> visible to the tensor core (async proxy)
     mbar_arrive(bars.full + 8 * b);
@@ -248,7 +263,6 @@ struct GemmArgs {
     const float* tan;                       // ADJ_TANGENT: tangent activation of the layer below, this stream
     float* cross; int crossMode;            // ADJ_TANGENT: 0 = write, 1 = accumulate; ADJ_VALUE: 1 = read, 0 = no tangent streams
     float* outQm;                           // quad-major [N/4][rows][4]
-    float* outNm; unsigned int ldNm;        // neuron-major [n][ldNm]
     int* err;
 };
 
@@ -288,11 +302,11 @@ __global__ void __launch_bounds__(TS ? NTHR : NTHR_ALL, TS ? 2 : 1) tc_gemm_kern
     };
     TileRegs ra[2], rb[2];                                                    // two K chunks in flight
     if (loader) {                                                             // first loads before TMEM is even allocated
-        if (TS) loadA(0, ra[0]); else tile_load<true>(oa, 0, ra[0], tid);
-        tile_load<true>(ob, 0, rb[0], tid);
+        if (TS) loadA(0, ra[0]); else tile_load<LAY_QM>(oa, 0, ra[0], tid);
+        tile_load<LAY_QM>(ob, 0, rb[0], tid);
         if (nIt > 1) {
-            if (TS) loadA(1, ra[1]); else tile_load<true>(oa, KC, ra[1], tid);
-            tile_load<true>(ob, KC, rb[1], tid);
+            if (TS) loadA(1, ra[1]); else tile_load<LAY_QM>(oa, KC, ra[1], tid);
+            tile_load<LAY_QM>(ob, KC, rb[1], tid);
         }
     }
     Bars bars;
@@ -336,8 +350,8 @@ __global__ void __launch_bounds__(TS ? NTHR : NTHR_ALL, TS ? 2 : 1) tc_gemm_kern
                 tc_fence_after();
                 tmem_st16(tA + b * 64, hi);
                 tmem_st16(tA + b * 64 + 32, lo);
-                tile_store_split<true>(rB, stage, stage + TILE_BYTES, tid);
-                if (it + 2 < nIt) { loadA(it + 2, rA); tile_load<true>(ob, (it + 2) * KC, rB, tid); }
+                tile_store_split<LAY_QM>(rB, stage, stage + TILE_BYTES, tid);
+                if (it + 2 < nIt) { loadA(it + 2, rA); tile_load<LAY_QM>(ob, (it + 2) * KC, rB, tid); }
                 tmem_wait_st();
                 fence_async_smem();
                 tc_fence_before();
@@ -369,8 +383,8 @@ __global__ void __launch_bounds__(TS ? NTHR : NTHR_ALL, TS ? 2 : 1) tc_gemm_kern
             auto src = [&](int it) { return ChunkSrc{oa, ob, it * KC}; };
 #pragma unroll 1
             for (int it0 = 0; it0 < nIt; it0 += 2) {
-                loader_step<true>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
-                if (it0 + 1 < nIt) loader_step<true>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
+                loader_step<LAY_QM>(smem, bars, it0, nIt, ra[0], rb[0], src, tid, ok);
+                if (it0 + 1 < nIt) loader_step<LAY_QM>(smem, bars, it0 + 1, nIt, ra[1], rb[1], src, tid, ok);
             }
         }
         // ---- drain: thread = one point (TMEM lane), warps 0-3 / 4-7 take the two column halves; the accumulator sets are
@@ -439,22 +453,14 @@ __global__ void __launch_bounds__(TS ? NTHR : NTHR_ALL, TS ? 2 : 1) tc_gemm_kern
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) *qm_ptr(a.outQm, a.rows, prow, n + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-        float* nm = a.outNm + (size_t)n * a.ldNm + prow;
-        if (EPI == EPI_FWD_VALUE || EPI == EPI_FWD_TANGENT) {           // read once, much later (tc_gw): keep it out of the way in L2
-#pragma unroll
-            for (int c = 0; c < 16; ++c) __stcs(nm + (size_t)c * a.ldNm, z[c]);
-        } else {                                                         // zbar: tc_gw consumes it right after this launch
-#pragma unroll
-            for (int c = 0; c < 16; ++c) nm[(size_t)c * a.ldNm] = z[c];
-        }
     }
 }
 
 // ------------------------------------------------------------------ weight-gradient GEMM (split-K over points)
 struct GwArgs {
-    const float* A; size_t aStream;     // neuron-major activations of layer l-1: [s][i][ld]
-    const float* B; size_t bStream;     // neuron-major zbar of layer l:          [s][j][ld]
-    unsigned int ld;
+    const float* A; size_t aStream;     // quad-major activations of layer l-1: [s][i/4][ld][4]
+    const float* B; size_t bStream;     // quad-major zbar of layer l:          [s][j/4][ld][4]
+    unsigned int ld;                    // points of the arrays
     int S;
     unsigned int nPts, kPts;            // valid (padded to 128) points of the chunk; points per split (multiple of KC)
     int tilesJ, nsplit;
@@ -490,8 +496,8 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
             if (!ok) *a.err = 1;
         }
     } else {
-        const float* Ag = a.A + (size_t)(it_ * TM) * a.ld;
-        const float* Bg = a.B + (size_t)(jt * TN) * a.ld;
+        const float* Ag = a.A + (size_t)(it_ * TM / 4) * a.ld * 4;
+        const float* Bg = a.B + (size_t)(jt * TN / 4) * a.ld * 4;
         auto src = [&](int it) {
             const int s = it / chunks, pc = it - s * chunks;
             return ChunkSrc{Opnd{Ag + s * a.aStream, a.ld}, Opnd{Bg + s * a.bStream, a.ld}, (int)pBeg + pc * KC};
@@ -512,8 +518,8 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
             }
         };
         TileRegs ra[2], rb[2];
-        { const ChunkSrc c = src(0); tile_load<false>(c.a, c.k0, ra[0], tid); tile_load<false>(c.b, c.k0, rb[0], tid); }
-        if (nIt > 1) { const ChunkSrc c = src(1); tile_load<false>(c.a, c.k0, ra[1], tid); tile_load<false>(c.b, c.k0, rb[1], tid); }
+        { const ChunkSrc c = src(0); tile_load<LAY_QT>(c.a, c.k0, ra[0], tid); tile_load<LAY_QT>(c.b, c.k0, rb[0], tid); }
+        if (nIt > 1) { const ChunkSrc c = src(1); tile_load<LAY_QT>(c.a, c.k0, ra[1], tid); tile_load<LAY_QT>(c.b, c.k0, rb[1], tid); }
         bool ok = true;
 #pragma unroll 1
         for (int it0 = 0; it0 < nIt; it0 += 2) {
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
                         drain(((it / GW_EPOCH) - 2) % 3);
                         tc_fence_before();          // the set is overwritten by epoch e+1, whose first stage this thread publishes later
                     }
-                    loader_step<false>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
+                    loader_step<LAY_QT>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
                 }
             }
         }
@@ -583,10 +589,10 @@ __global__ void tc_stage_weights_kernel(NetDesc net, int WP, const float* __rest
 
 struct L0Args {
     TileArgs in; unsigned int base; int WP;
-    float* X; float* Aqm; float* Anm; size_t sQm, sNm; unsigned int cap;
+    float* X; float* Aqm; size_t sQm; unsigned int cap;
 };
 // layer 0 (K = inpDim): a = act(X W0 + b0), tangent k: act'(z) W0[k,:]; also keeps X of the chunk for g(W0).
-// thread = one point x four neurons: coalesced 16-byte quad-major stores, coalesced scalar neuron-major stores
+// thread = one point x four neurons: coalesced 16-byte quad-major stores
 template <int S, int ACT>
 __global__ void __launch_bounds__(256) tc_layer0_kernel(const L0Args a) {
     const TileArgs& A = a.in;
@@ -621,8 +627,6 @@ __global__ void __launch_bounds__(256) tc_layer0_kernel(const L0Args a) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         *reinterpret_cast<float4*>(a.Aqm + s * a.sQm + ((size_t)n4 * a.cap + p) * 4) = make_float4(o[s][0], o[s][1], o[s][2], o[s][3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) __stcs(a.Anm + s * a.sNm + (size_t)(n0 + e) * a.cap + p, o[s][e]);
     }
 }
 
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(256) tc_seed_kernel(const SeedArgs a) {
 struct TopArgs {
     int WP, wlast; const float* wout; unsigned int nPts;
     const float* Aqm; size_t sQm; const float* seeds; unsigned int cap;
-    float* Dqm; float* Dnm; size_t sNm; double* gwout;
+    float* Dqm; double* gwout;
 };
 // top of the adjoint: zbar_{L-1} from the seeds (outer product with w_out), g(w_out).
 // thread = one point x four neurons; a warp walks four 32-point groups and reduces its g(w_out) share once
@@ -774,16 +778,12 @@ __global__ void __launch_bounds__(256) tc_top_kernel(const TopArgs a) {
                 gacc[e] = fmaf(da[e], sd, gacc[e]);
                 cross[e] = fmaf(ab, da[e], cross[e]);
                 o[e] = ab * d1[e];
-                a.Dnm[s * a.sNm + (size_t)(n0 + e) * a.cap + p] = o[e];
             }
             *reinterpret_cast<float4*>(a.Dqm + s * a.sQm + q) = make_float4(o[0], o[1], o[2], o[3]);
         }
         float zb[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            zb[e] = fmaf(s0 * wv[e], d1[e], act_d2r<ACT>(av[e]) * cross[e]);
-            a.Dnm[(size_t)(n0 + e) * a.cap + p] = zb[e];
-        }
+        for (int e = 0; e < 4; ++e) zb[e] = fmaf(s0 * wv[e], d1[e], act_d2r<ACT>(av[e]) * cross[e]);
         *reinterpret_cast<float4*>(a.Dqm + q) = make_float4(zb[0], zb[1], zb[2], zb[3]);
     }
 #pragma unroll
@@ -796,50 +796,63 @@ __global__ void __launch_bounds__(256) tc_top_kernel(const TopArgs a) {
 }
 
 struct RowArgs {
-    const float* Dnm; size_t sNm; unsigned int cap, nPts, len;   // len: points per split (multiple of 128)
-    int rows, width, splits, first; const float* X; int inpDim;
+    const float* Dqm; size_t sQm; unsigned int cap, nPts, len;   // len: points per split (multiple of 128)
+    int quads, width, splits, first, streams; const float* X; int inpDim;
     double* gb; double* gw0;        // gb[j]; gw0[k*width + j] (layer 0 only)
 };
 // bias gradients g(b_l)[j] = sum_p zbar_l[p][j]; for layer 0 also g(W_0)[k][j] = sum_p X[p][k] zbar_0[p][j]
-// plus, for the tangent streams, sum_p dzbar_0^k[p][j] added to row k   (App. A.3, l = 0)
+// plus, for the tangent streams, sum_p dzbar_0^k[p][j] added to row k   (App. A.3, l = 0).
+// warp = (stream, neuron quad, point split); lanes walk the points (coalesced 16-byte quad-major units)
 __global__ void __launch_bounds__(256) tc_rowsum_kernel(const RowArgs a) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (w >= a.rows * a.splits) return;
-    const int rowi = w / a.splits, split = w - rowi * a.splits;
-    const int s = rowi / a.width, j = rowi - s * a.width;
+    if (w >= a.streams * a.quads * a.splits) return;
+    const int split = w % a.splits, qi = w / a.splits;
+    const int s = qi / a.quads, j4 = qi - s * a.quads;
     const unsigned int pBeg = (unsigned int)split * a.len, pEnd = min(pBeg + a.len, a.nPts);
     if (pBeg >= pEnd) return;
-    const float* d = a.Dnm + s * a.sNm + (size_t)j * a.cap;
+    const float* d = a.Dqm + s * a.sQm + (size_t)j4 * a.cap * 4;
     const bool dots = a.first && s == 0;
-    float sum = 0.f, dot[VN_KIN];
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, dot[VN_KIN][4];
 #pragma unroll
-    for (int k = 0; k < VN_KIN; ++k) dot[k] = 0.f;
-    for (unsigned int p = pBeg + lane * 4; p < pEnd; p += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(d + p);
-        sum += (v.x + v.y) + (v.z + v.w);
+    for (int k = 0; k < VN_KIN; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dot[k][e] = 0.f;
+    for (unsigned int p = pBeg + lane; p < pEnd; p += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(d + (size_t)p * 4);
+        sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
         if (dots) {
 #pragma unroll
             for (int k = 0; k < VN_KIN; ++k)
                 if (k < a.inpDim) {
-                    const float4 x = *reinterpret_cast<const float4*>(a.X + (size_t)k * a.cap + p);
-                    dot[k] = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, dot[k]))));
+                    const float x = a.X[(size_t)k * a.cap + p];
+                    dot[k][0] = fmaf(v.x, x, dot[k][0]); dot[k][1] = fmaf(v.y, x, dot[k][1]);
+                    dot[k][2] = fmaf(v.z, x, dot[k][2]); dot[k][3] = fmaf(v.w, x, dot[k][3]);
                 }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum[e] += __shfl_xor_sync(0xffffffffu, sum[e], o);
     if (dots) {
 #pragma unroll
         for (int k = 0; k < VN_KIN; ++k)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot[k][e] += __shfl_xor_sync(0xffffffffu, dot[k][e], o);
     }
     if (lane == 0) {
-        if (s == 0) atomicAdd(a.gb + j, (double)sum);
-        else atomicAdd(a.gw0 + (size_t)(s - 1) * a.width + j, (double)sum);
-        if (dots)
-            for (int k = 0; k < a.inpDim; ++k) atomicAdd(a.gw0 + (size_t)k * a.width + j, (double)dot[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            if (j >= a.width) break;
+            if (s == 0) atomicAdd(a.gb + j, (double)sum[e]);
+            else atomicAdd(a.gw0 + (size_t)(s - 1) * a.width + j, (double)sum[e]);
+            if (dots)
+                for (int k = 0; k < a.inpDim; ++k) atomicAdd(a.gw0 + (size_t)k * a.width + j, (double)dot[k][e]);
+        }
     }
 }
 
@@ -945,21 +958,19 @@ __global__ void tc_grad_out_kernel(const double* __restrict__ g, float* __restri
 
 // ------------------------------------------------------------------ host side
 struct Work {
-    float *Wn, *Wt, *X, *Aqm, *Anm, *Dqm, *Dnm, *seeds, *cross;
-    size_t sQm, sNm, layerStride, bytes;     // stream strides of the quad-major / neuron-major arrays, layer stride
+    float *Wn, *Wt, *X, *Aqm, *Dqm, *seeds, *cross;
+    size_t sQm, layerStride, bytes;          // stream stride of the quad-major arrays, layer stride
 };
 Work carve(void* base, int L, int S, int WP, unsigned int cap) {
     Work w;
     size_t off = 0;
     auto take = [&](size_t nfloats) { float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; };
-    w.sQm = (size_t)cap * WP; w.sNm = (size_t)WP * cap; w.layerStride = (size_t)S * w.sQm;
+    w.sQm = (size_t)cap * WP; w.layerStride = (size_t)S * w.sQm;
     w.Wn = take((size_t)std::max(L - 1, 1) * WP * WP);
     w.Wt = take((size_t)std::max(L - 1, 1) * WP * WP);
     w.X = take((size_t)VN_KIN * cap);
     w.Aqm = take((size_t)L * w.layerStride);
-    w.Anm = take((size_t)L * w.layerStride);
     w.Dqm = take(2 * w.layerStride);
-    w.Dnm = take(2 * w.layerStride);
     w.seeds = take((size_t)S * cap);
     w.cross = take(w.sQm);
     w.bytes = off;
@@ -1014,7 +1025,7 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
     if (const char* w = getenv("VARNET_B200_TC_WAVES")) waves = std::max(1, std::min(16, atoi(w)));
     g->capPts = (unsigned int)numSMs * TM * waves;
     g->workBytes = carve(nullptr, net.L, S, g->WP, g->capPts).bytes;
-    g->smemGemm = SMEM_BYTES;
+    g->smemGemm = SMEM_BYTES;            // upper bound (the A-from-TMEM variant uses TS_SMEM_BYTES)
     g->smemGw = SMEM_BYTES;
     return true;
 }
@@ -1114,7 +1125,7 @@ cudaError_t vn_tc_run(TcJob& j) {
 
         // ---- layer 0
         {
-            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Aqm = w.Aqm; a.Anm = w.Anm; a.sQm = w.sQm; a.sNm = w.sNm; a.cap = cap;
+            L0Args a; a.in = A; a.base = base; a.WP = WP; a.X = w.X; a.Aqm = w.Aqm; a.sQm = w.sQm; a.cap = cap;
             const dim3 grid(nPts / 32, WP / 32);
 #define CALL(SS) launch_layer0<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
@@ -1132,7 +1143,6 @@ cudaError_t vn_tc_run(TcJob& j) {
                 g.bias = A.theta + net.boff[l]; g.widthOut = net.width[l];
                 g.val = w.Aqm + (size_t)l * w.layerStride;
                 g.outQm = w.Aqm + (size_t)l * w.layerStride + sidx * w.sQm;
-                g.outNm = w.Anm + (size_t)l * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx == 0) TCK(launch_gemm<EPI_FWD_VALUE>(act, g, mTiles * g.nTilesN, st));
                 else TCK(launch_gemm<EPI_FWD_TANGENT>(act, g, mTiles * g.nTilesN, st));
@@ -1175,7 +1185,7 @@ cudaError_t vn_tc_run(TcJob& j) {
         {
             TopArgs a; a.WP = WP; a.wlast = net.width[L - 1]; a.wout = A.theta + net.woff[L];
             a.Aqm = w.Aqm + (size_t)(L - 1) * w.layerStride; a.sQm = w.sQm; a.seeds = w.seeds; a.cap = cap; a.nPts = nPts;
-            a.Dqm = w.Dqm; a.Dnm = w.Dnm; a.sNm = w.sNm; a.gwout = j.g64 + net.woff[L];
+            a.Dqm = w.Dqm; a.gwout = j.g64 + net.woff[L];
             const dim3 grid((nPts / 32 + 3) / 4, WP / 32);
 #define CALL(SS) launch_top<SS>(act, a, grid, st)
             TCK(TC_S_SWITCH(S, CALL));
@@ -1184,13 +1194,14 @@ cudaError_t vn_tc_run(TcJob& j) {
         }
         auto rowsum = [&](int l, int curBuf) -> cudaError_t {
             RowArgs r;
-            r.Dnm = w.Dnm + (size_t)curBuf * w.layerStride; r.sNm = w.sNm; r.cap = cap; r.nPts = nPts;
-            r.first = (l == 0); r.rows = (l == 0 ? S : 1) * net.width[l]; r.width = net.width[l];
-            r.splits = std::max(1, std::min<int>((int)(nPts / 1024), (8 * j.numSMs * 8) / std::max(r.rows, 1)));
+            r.Dqm = w.Dqm + (size_t)curBuf * w.layerStride; r.sQm = w.sQm; r.cap = cap; r.nPts = nPts;
+            r.first = (l == 0); r.streams = (l == 0 ? S : 1); r.quads = (net.width[l] + 3) / 4; r.width = net.width[l];
+            const int rows = r.streams * r.quads;
+            r.splits = std::max(1, std::min<int>((int)(nPts / 1024), (8 * j.numSMs * 8) / std::max(rows, 1)));
             r.len = ((nPts + r.splits - 1) / r.splits + TM - 1) / TM * TM;
             r.X = w.X; r.inpDim = net.inpDim;
             r.gb = j.g64 + net.boff[l]; r.gw0 = j.g64 + net.woff[0];
-            const int warps = r.rows * r.splits;
+            const int warps = rows * r.splits;
             tc_rowsum_kernel<<<(warps + 7) / 8, 256, 0, st>>>(r);
             j.launches++;
             return cudaGetLastError();
@@ -1200,8 +1211,8 @@ cudaError_t vn_tc_run(TcJob& j) {
             // gW_l from (A_{l-1}, D_l)
             {
                 GwArgs g{};
-                g.A = w.Anm + (size_t)(l - 1) * w.layerStride; g.aStream = w.sNm;
-                g.B = w.Dnm + (size_t)cur * w.layerStride; g.bStream = w.sNm;
+                g.A = w.Aqm + (size_t)(l - 1) * w.layerStride; g.aStream = w.sQm;
+                g.B = w.Dqm + (size_t)cur * w.layerStride; g.bStream = w.sQm;
                 g.ld = cap; g.S = S; g.nPts = nPts;
                 const int tilesI = (net.width[l - 1] + TM - 1) / TM;
                 g.tilesJ = (net.width[l] + TN - 1) / TN;
@@ -1226,7 +1237,6 @@ cudaError_t vn_tc_run(TcJob& j) {
                 g.tan = w.Aqm + (size_t)(l - 1) * w.layerStride + sidx * w.sQm;
                 g.cross = w.cross;
                 g.outQm = w.Dqm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sQm;
-                g.outNm = w.Dnm + (size_t)(cur ^ 1) * w.layerStride + sidx * w.sNm; g.ldNm = cap;
                 g.err = j.err;
                 if (sidx > 0) { g.crossMode = (sidx == S - 1) ? 0 : 1; TCK(launch_gemm<EPI_ADJ_TANGENT>(act, g, mTiles * g.nTilesN, st)); }
                 else { g.crossMode = S > 1 ? 1 : 0; TCK(launch_gemm<EPI_ADJ_VALUE>(act, g, mTiles * g.nTilesN, st)); }
