@@ -120,9 +120,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tmem) {
 //   LAY_QM — layer GEMMs (rows = points, K = neurons): the global order IS the order of the shared-memory canonical
 //            layout, so a warp reads 512 contiguous bytes and writes four whole core matrices, and the GEMM epilogues
 //            (thread = point) store and reload it fully coalesced;
-//   LAY_QT — weight-gradient GEMM (rows = neurons, K = points): a thread reads the four units (neuron quad, points
-//            4pg..4pg+3) — 64 contiguous bytes, a quarter warp 512 — transposes the 4x4 block in registers and writes
-//            four K units (neuron, 4 points); the 16-byte pad on TILE_LBO makes those stores conflict free.
+//   LAY_QT — weight-gradient GEMM (rows = neurons, K = points): lane = point, so a warp request is again 512
+//            contiguous bytes (one neuron quad x 32 points); the transposition happens in the shared-memory store:
+//            each of the four neurons of a unit is written as a 4-byte scalar into its (neuron, 4 points) K unit —
+//            bank = lane thanks to the 16-byte pad on TILE_LBO, so these stores are conflict free too.
 // No second (neuron-major) copy of the activations exists.
 enum { LAY_QM = 0, LAY_QT = 1 };
 struct Opnd { const float* p; size_t ld; };     // p = array + (first row / 4 for QT, first row for QM) term, ld = points of the array
@@ -138,11 +139,11 @@ __device__ __forceinline__ void tile_load(const Opnd& o, int k0, TileRegs& r, in
             r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)(k0 / 4 + k4) * o.ld + row) * 4));
         }
     } else {
-        static_assert(U == 4 && NTHR == (TM / 4) * (KC / 4), "one 4x4 block per thread");
-        const int n4 = tid / (KC / 4), pg = tid % (KC / 4);
+        static_assert(U == 4 && KC == 32, "warp = four neuron quads x 32 points");
+        const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)n4 * o.ld + k0 + 4 * pg + i) * 4));
+            r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)(4 * warp + i) * o.ld + k0 + lane) * 4));
     }
 }
 // round to the 10-bit TF32 mantissa (the tensor core itself truncates: a truncated split leaves a one-sided
@@ -163,13 +164,17 @@ __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned cha
             store_split(r.v[i], hiTile, loTile, k4 * TILE_LBO + row * 16);
         }
     } else {
-        const int n4 = tid / (KC / 4), pg = tid % (KC / 4);
-        const float4 a = r.v[0], b = r.v[1], c = r.v[2], d = r.v[3];       // points 4pg..4pg+3 of neurons 4n4..4n4+3
-        const uint32_t off = pg * TILE_LBO + (4 * n4) * 16;
-        store_split(make_float4(a.x, b.x, c.x, d.x), hiTile, loTile, off);
-        store_split(make_float4(a.y, b.y, c.y, d.y), hiTile, loTile, off + 16);
-        store_split(make_float4(a.z, b.z, c.z, d.z), hiTile, loTile, off + 32);
-        store_split(make_float4(a.w, b.w, c.w, d.w), hiTile, loTile, off + 48);
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = r.v[i];                                         // neurons 4q..4q+3 (q = 4 warp + i) of point `lane`
+            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            const uint32_t off = (lane >> 2) * TILE_LBO + (16 * warp + 4 * i) * 16 + (lane & 3) * 4;
+            *reinterpret_cast<float*>(hiTile + off) = h.x;       *reinterpret_cast<float*>(loTile + off) = v.x - h.x;
+            *reinterpret_cast<float*>(hiTile + off + 16) = h.y;  *reinterpret_cast<float*>(loTile + off + 16) = v.y - h.y;
+            *reinterpret_cast<float*>(hiTile + off + 32) = h.z;  *reinterpret_cast<float*>(loTile + off + 32) = v.z - h.z;
+            *reinterpret_cast<float*>(hiTile + off + 48) = h.w;  *reinterpret_cast<float*>(loTile + off + 48) = v.w - h.w;
+        }
     }
 }
 
@@ -818,8 +823,14 @@ __global__ void __launch_bounds__(256) tc_rowsum_kernel(const RowArgs a) {
     for (int k = 0; k < VN_KIN; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) dot[k][e] = 0.f;
-    for (unsigned int p = pBeg + lane; p < pEnd; p += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(d + (size_t)p * 4);
+    for (unsigned int p0 = pBeg + lane; p0 < pEnd; p0 += 128) {               // len is a multiple of 128: four independent loads in flight
+        float4 vv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vv[q] = *reinterpret_cast<const float4*>(d + (size_t)(p0 + 32 * q) * 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+        const unsigned int p = p0 + 32 * q;
+        const float4 v = vv[q];
         sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
         if (dots) {
 #pragma unroll
@@ -829,6 +840,7 @@ __global__ void __launch_bounds__(256) tc_rowsum_kernel(const RowArgs a) {
                     dot[k][0] = fmaf(v.x, x, dot[k][0]); dot[k][1] = fmaf(v.y, x, dot[k][1]);
                     dot[k][2] = fmaf(v.z, x, dot[k][2]); dot[k][3] = fmaf(v.w, x, dot[k][3]);
                 }
+        }
         }
     }
 #pragma unroll
