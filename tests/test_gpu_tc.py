@@ -159,3 +159,21 @@ def test_varnet_api_with_wide_network():
         assert len(res.loss) == 30 and np.all(np.isfinite(res.loss))
         assert res.loss[-1] < res.loss[0]
     vn.tfData.sess.close()
+
+
+@pytest.mark.gpu
+def test_shared_memory_operand_pipeline_matches_oracle(monkeypatch):
+    """VARNET_B200_TC_TS=0 selects the layer-GEMM variant that keeps both operands in shared memory (three
+    rotating accumulator sets); it must meet the same bar as the default A-from-TMEM variant."""
+    monkeypatch.setenv("VARNET_B200_TC_TS", "0")
+    rng = np.random.RandomState(3)
+    dim, inpDim, lw = 2, 3, [200, 256, 96]
+    feed = synth_feed(rng, dim, inpDim, 90, 64, 400, 250, True, True)
+    theta = go.glorot_init(inpDim, lw, seed=4)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=True, integWflag=False))
+    ref = go.loss_and_grad(theta, feed, **kw)
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        check_against_oracle(eng, ref, feed, inpDim, lw, True)
+    finally:
+        eng.close()
