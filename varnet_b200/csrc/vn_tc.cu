@@ -470,6 +470,7 @@ struct GwArgs {
     unsigned int nPts, kPts;            // valid (padded to 128) points of the chunk; points per split (multiple of KC)
     int tilesJ, nsplit;
     double* g; int wi, wo;              // g[i*wo + j] += ...   for i < wi, j < wo
+    double* gb;                         // bias gradient g(b_l)[j] += sum_p zbar_{l,0}[p][j] (taken from the B operand by the CTAs of row tile 0)
     int* err;
 };
 
@@ -512,6 +513,17 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
         float acc[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+        // bias gradient: the loader of the zbar operand sees every (point, neuron) of stream 0 exactly once per row tile
+        const bool doBias = a.gb != nullptr && it_ == 0;
+        float bs[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) bs[c] = 0.f;
+        auto biasAcc = [&](int it, const TileRegs& r) {
+            if (doBias && it < chunks) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { bs[4 * i] += r.v[i].x; bs[4 * i + 1] += r.v[i].y; bs[4 * i + 2] += r.v[i].z; bs[4 * i + 3] += r.v[i].w; }
+            }
+        };
         auto drain = [&](int set) {
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
@@ -539,6 +551,7 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
                         drain(((it / GW_EPOCH) - 2) % 3);
                         tc_fence_before();          // the set is overwritten by epoch e+1, whose first stage this thread publishes later
                     }
+                    biasAcc(it, rb[h]);
                     loader_step<LAY_QT>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
                 }
             }
@@ -550,6 +563,16 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
         for (int e = max(0, nEp - 2); e < nEp; ++e) drain(e % 3);           // the last two epochs were not drained in the loop
         drain(3);                                                            // small terms
 
+        if (doBias) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float t = bs[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                const int j = jt * TN + 16 * warp + c;                       // quad 4 warp + c / 4, neuron c % 4 (LAY_QT loader mapping)
+                if (lane == 0 && j < a.wo) atomicAdd(a.gb + j, (double)t);
+            }
+        }
         const int i = it_ * TM + (warp & 3) * 32 + lane;
         if (ok && i < a.wi) {
 #pragma unroll
@@ -1219,7 +1242,6 @@ cudaError_t vn_tc_run(TcJob& j) {
             return cudaGetLastError();
         };
         for (int l = L - 1; l >= 1; --l) {
-            TCK(rowsum(l, cur));
             // gW_l from (A_{l-1}, D_l)
             {
                 GwArgs g{};
@@ -1231,7 +1253,7 @@ cudaError_t vn_tc_run(TcJob& j) {
                 const int tiles = tilesI * g.tilesJ;
                 g.nsplit = std::max(1, std::min<int>(j.numSMs / tiles, (int)(nPts / 256)));
                 g.kPts = ((nPts + g.nsplit - 1) / g.nsplit + KC - 1) / KC * KC;
-                g.g = j.g64 + net.woff[l]; g.wi = net.width[l - 1]; g.wo = net.width[l];
+                g.g = j.g64 + net.woff[l]; g.wi = net.width[l - 1]; g.wo = net.width[l]; g.gb = j.g64 + net.boff[l];
                 g.err = j.err;
                 tc_gw_kernel<<<tiles * g.nsplit, NTHR_ALL, SMEM_BYTES, st>>>(g);
                 TCK(cudaGetLastError());
