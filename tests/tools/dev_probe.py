@@ -1,4 +1,4 @@
-"""Dev probe (GPU box): times the forward and adjoint kernels on a cfg4-like slice."""
+"""Test tooling (uses the oracle; not product code). Dev probe (GPU box): times the forward and adjoint kernels on a cfg4-like slice."""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")

@@ -1,4 +1,4 @@
-"""Dev check (GPU box): tensor-core class vs the FP64 oracle, per loss component and gradient tensor."""
+"""Test tooling (uses the oracle; not product code). Dev check (GPU box): tensor-core class vs the FP64 oracle, per loss component and gradient tensor."""
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")

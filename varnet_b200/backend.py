@@ -117,7 +117,7 @@ def _token(v):
         if flat is not None and flat.size and v.dtype != object:
             n = flat.size
             probe = (float(flat[0]), float(flat[n // 2]), float(flat[-1]))
-        return ("a", id(v), v.shape, str(v.dtype), v.__array_interface__["data"][0], probe)
+        return ("a", id(v), v.shape, v.dtype.char, v.ctypes.data, probe)
     if isinstance(v, (list, tuple)):
         return ("l", tuple(_token(x) for x in v))
     return ("s", v)
