@@ -15,7 +15,8 @@ the [grad | 4 loss scalars] buffer (51 KB).
 Timing: W>=3 warm-up steps, then exactly K steps between barrier+synchronize, CUDA events on the
 launching stream, max over ranks.  Inputs (1.5 GB/GPU at N=1) are far larger than L2 (126 MB), so no
 explicit flush is needed.  `value` = resident-table throughput; `e2e` = the same step with the host
-feed (pinned float32) re-uploaded inside the timed region every step and the loss read back.
+feed (pinned float32) re-uploaded inside the timed region every step and the loss read back (the shim
+routes such steps through vn_loss_grad_fed_f32: chunked copies overlapped with the step's kernels).
 """
 import argparse
 import json
@@ -382,7 +383,7 @@ def main():
                     train_steps_per_sec=1e3 / ms_step, loss=float(loss), table_build_s=t_build,
                     roofline=roofline,
                     e2e=dict(value=P_total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                             ms_per_step=ms_e2e, api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False"),
+                             ms_per_step=ms_e2e, api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f32: copies overlap the kernels)"),
                     gpu_launches=int(launches), clocks=clocks, kernel_info=eng.kernel_info())
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)

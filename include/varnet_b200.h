@@ -131,6 +131,18 @@ int vn_set_weights(vn_engine* e, const float w[3]);
  *                sess.run([optMinimize, loss]) (VarNetUtility.py:1044); single-GPU. */
 int vn_loss(vn_engine* e, float out[4], float* lossVec);
 int vn_loss_grad(vn_engine* e, float out[4]);
+/* vn_loss_grad_fed_*: vn_upload_points_* + vn_loss_grad in one call, for callers that feed every array on
+ * every step like the reference does (sess.run(..., feed_dict), VarNetUtility.py:1044; float64 -> float32
+ * cast + copy per step): the table is uploaded chunk by chunk on a copy stream and the adjoint kernel is
+ * launched per chunk as soon as it has been packed, so the copies overlap the step's kernels.  Same results
+ * as the two separate calls; the caller's arrays are no longer read when the call returns.  Falls back to the
+ * sequential path for small tables, the two-pass (integNum does not divide the tile) and tensor-core classes. */
+int vn_loss_grad_fed_f32(vn_engine* e, const float* Input, const float* gcoef, const float* source, const float* N,
+                         const float* dNt, int64_t nb, int32_t integNum, const float* integW, const float* detJ,
+                         int32_t detJvec, float out[4]);
+int vn_loss_grad_fed_f64(vn_engine* e, const double* Input, const double* gcoef, const double* source, const double* N,
+                         const double* dNt, int64_t nb, int32_t integNum, const double* integW, const double* detJ,
+                         int32_t detJvec, float out[4]);
 int vn_grad_buffer(vn_engine* e, void** device_ptr, int64_t* n_floats);
 int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]);
 int vn_optimizer_step(vn_engine* e, float lr);

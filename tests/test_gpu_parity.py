@@ -229,3 +229,44 @@ def test_deep_and_ragged_networks_match_oracle():
         for name, sl in layer_slices(inpDim, lw):
             assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
         eng.close()
+
+
+@pytest.mark.gpu
+def test_fed_step_overlapping_copies_equals_upload_then_step():
+    """vn_loss_grad_fed (table uploaded chunk by chunk while the adjoint kernel already runs on the first chunks)
+    against vn_upload_points + vn_loss_grad on the same feed, on a table of more than one 4 Mi-row chunk; then the
+    shim path: sess.run with feed_cache=False goes through the fed call and follows the same Adam trajectory."""
+    from varnet_b200._capi import Engine
+    rng = np.random.RandomState(12)
+    dim, inpDim, lw, nb, q = 2, 3, [16, 16], 70000, 64                       # 4.48 M points = 2 chunks
+    P = nb * q
+    X = rng.uniform(-1, 1, (P, inpDim)).astype(np.float32); G = rng.randn(P, dim).astype(np.float32)
+    dNt = rng.randn(P, 1).astype(np.float32)
+    bX = rng.uniform(-1, 1, (500, inpDim)).astype(np.float32); bL = rng.randn(500, 1).astype(np.float32)
+    theta = go.glorot_init(inpDim, lw, seed=2)
+    outs = []
+    for fed in (False, True):
+        eng = Engine(dim, inpDim, lw, "tanh", True)
+        eng.set_params(theta)
+        eng.upload_bic(bX, bL, 300, 2.0)
+        eng.set_weights([3.0, 5.0, 7.0])
+        if fed:
+            eng.loss_grad_fed(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+        else:
+            eng.upload_points(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+        r = eng.loss_grad() if not fed else None
+        if fed:
+            g = np.empty(eng.nparam, dtype=np.float32); o = np.empty(4, dtype=np.float32)
+            import ctypes as C
+            eng._check(eng.lib.vn_get_grad(eng._h, g.ctypes.data_as(C.POINTER(C.c_float)), g.size, o.ctypes.data_as(C.POINTER(C.c_float))))
+            r = dict(loss=o[0], BCloss=o[1], ICloss=o[2], varLoss=o[3], grad=g)
+            lv = eng.loss(lossVec=True)["lossVec"]
+        else:
+            lv = eng.loss(lossVec=True)["lossVec"]
+        outs.append((r, lv))
+        eng.close()
+    a, b = outs
+    for k in ("loss", "BCloss", "ICloss", "varLoss"):
+        assert abs(float(a[0][k]) - float(b[0][k])) <= 1e-6 * abs(float(a[0][k])), k
+    assert rel_inf(b[0]["grad"], a[0]["grad"]) <= 1e-6
+    assert np.array_equal(a[1], b[1])

@@ -52,6 +52,8 @@ SIGNATURES = {
     "vn_set_weights": (C.c_int, [_vp, _f32p]),
     "vn_loss": (C.c_int, [_vp, _f32p, _f32p]),
     "vn_loss_grad": (C.c_int, [_vp, _f32p]),
+    "vn_loss_grad_fed_f32": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _i32, _f32p]),
+    "vn_loss_grad_fed_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32, _f32p]),
     "vn_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "vn_get_grad": (C.c_int, [_vp, _f32p, _i64, _f32p]),
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
@@ -286,6 +288,31 @@ class Engine:
         g = np.empty(self.nparam, dtype=np.float32); out = np.empty(4, dtype=np.float32)
         self._check(self.lib.vn_get_grad(self._h, _ptr(g, C.c_float), g.size, _ptr(out, C.c_float)))
         return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3], grad=g)
+
+    def loss_grad_fed(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None, fetch=False):
+        """upload_points + loss_grad in one call with the copies overlapped (vn_loss_grad_fed_*)."""
+        nb, integNum = int(intShape[0]), int(intShape[1])
+        P = nb * integNum
+        if dtype is None:
+            dtype = np.float32 if np.asarray(Input).dtype == np.float32 else np.float64
+        X = _prep(Input, dtype, (P, self.inpDim))
+        G = _prep(gcoef, dtype, (P, self.dim))
+        S = _prep(source, dtype, (P,)) if self.cfg.isSource else None
+        Nn = _prep(N, dtype, (P,)) if self.cfg.isSource else None
+        T = _prep(dNt, dtype, (P,)) if self.cfg.timeDependent else None
+        W = _prep(integW, dtype).reshape(-1) if self.cfg.integWflag else None
+        D = _prep(detJ, dtype).reshape(-1)
+        if detJvec and D.size != nb:
+            raise ValueError("vector detJ must hold one value per test function")
+        ct = C.c_float if dtype == np.float32 else C.c_double
+        fn = self.lib.vn_loss_grad_fed_f32 if dtype == np.float32 else self.lib.vn_loss_grad_fed_f64
+        out = np.empty(4, dtype=np.float32) if fetch else None
+        self._check(fn(self._h, _ptr(X, ct), _ptr(G, ct), _ptr(S, ct), _ptr(Nn, ct), _ptr(T, ct), nb, integNum,
+                       _ptr(W, ct), _ptr(D, ct), int(bool(detJvec)), _ptr(out, C.c_float)))
+        self.nb = nb
+        if fetch:
+            return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3])
+        return None
 
     def grad_buffer(self):
         p = _vp(); n = _i64()

@@ -152,7 +152,7 @@ class Session:
                 tw.engine.close()
 
     # -- feed handling
-    def _sync_feeds(self, feed, need_points=True, need_bic=True):
+    def _sync_feeds(self, feed, need_points=True, need_bic=True, defer_points=False):
         # fast path for the launch-bound configs: the very same feed dict holding the very same objects as at
         # the previous call has nothing to upload (tokens below are only computed when something was replaced)
         if self._o.feed_cache and feed is not None:
@@ -178,8 +178,12 @@ class Session:
                         mat = {k: (np.asarray(fd[k]) if isinstance(fd.get(k), TableView) else fd.get(k)) for k in names}
                         if getattr(eng, "supports_table_views", False):
                             eng.select_table(0)                     # slot 0 = plain (reference-style) feeds
-                        eng.upload_points(mat["Input"], mat["gcoef"], mat["source"], mat["N"], mat["dNt"],
-                                          fd["intShape"], mat["integW"], mat["detJ"], bool(fd.get("detJvec", False)))
+                        args = (mat["Input"], mat["gcoef"], mat["source"], mat["N"], mat["dNt"],
+                                fd["intShape"], mat["integW"], mat["detJ"], bool(fd.get("detJvec", False)))
+                        if defer_points and hasattr(eng, "loss_grad_fed"):
+                            tw._pending_points = args               # uploaded by the step itself, copies overlapped (vn_loss_grad_fed)
+                        else:
+                            eng.upload_points(*args)
                         tok["points"] = t
                         tok.pop("view", None)
                         self._o.uploads += 1
@@ -300,12 +304,22 @@ class Session:
         towers = self._local_towers()
         dist = _dist()
         if dist is None and len(towers) == 1:
-            loss = towers[0].engine.train_step(o.learning_rate, fetch_loss=True)
+            eng = towers[0].engine
+            pend = towers[0].__dict__.pop("_pending_points", None)
+            if pend is not None:
+                loss = eng.loss_grad_fed(*pend, fetch=True)["loss"]
+                eng.optimizer_step(o.learning_rate)
+                return float(loss)
+            loss = eng.train_step(o.learning_rate, fetch_loss=True)
             return float(loss)
         import torch
         views = []
         for tw in towers:
-            tw.engine.loss_grad(fetch=False)
+            pend = tw.__dict__.pop("_pending_points", None)
+            if pend is not None:
+                tw.engine.loss_grad_fed(*pend, fetch=False)
+            else:
+                tw.engine.loss_grad(fetch=False)
             views.append(tw.engine.grad_tensor())
         if len(towers) > 1:                       # single process, several GPUs: sum on the controller
             ctrl = views[0]
@@ -356,7 +370,7 @@ class Session:
             return out[0] if single else out
 
         train = "optMinimize" in names
-        self._sync_feeds(feed_dict)
+        self._sync_feeds(feed_dict, defer_points=train)
         if train:
             loss = self._train_step()
             o.step_count += 1

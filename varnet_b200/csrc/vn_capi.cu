@@ -274,6 +274,9 @@ struct vn_engine {
     // tensor-core class (wclass == 256): chunk workspace, FP64 gradient accumulator [nparam | loss sum], barrier-timeout flag
     TcGeom tcGeom{};
     DevBuf tcWork, tcAcc, tcErr;
+    // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
+    cudaStream_t copyStream = nullptr;
+    std::vector<cudaEvent_t> fedEvents;
     bool fused = false;          // per-test-function residual reduced inside the adjoint kernel (integNum | TP)
     cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
     cudaStream_t ownStream = nullptr;
@@ -448,6 +451,8 @@ extern "C" int vn_destroy(vn_engine* e) {
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
     if (e->ownStream) cudaStreamDestroy(e->ownStream);
+    if (e->copyStream) cudaStreamDestroy(e->copyStream);
+    for (cudaEvent_t ev : e->fedEvents) cudaEventDestroy(ev);
     for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
@@ -557,9 +562,16 @@ static int ensure_work(vn_engine* e) {
 
 // Upload one point table into the current slot.  X has `nx` columns; the remaining inpDim-nx MLP inputs are
 // per-call constants (vn_set_extra_inputs).  The batch is reset to "whole table, in order".
+// A fed step uploads the table chunk by chunk on the copy stream and launches the adjoint kernel once per chunk
+// on the engine stream as soon as that chunk is packed (cudaStreamWaitEvent): copies overlap the step's kernels.
+struct FedPlan {
+    struct Sub { int tile0, ntiles; cudaEvent_t ev; };
+    std::vector<Sub> subs;
+};
+
 template <typename T>
 static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* src, const T* N, const T* dNt,
-                        int64_t nb, int32_t integNum, const T* integW, const T* detJ, int32_t detJvec) {
+                        int64_t nb, int32_t integNum, const T* integW, const T* detJ, int32_t detJvec, FedPlan* plan = nullptr) {
     if (!e || !X || !G || !detJ) return fail(VN_E_INVALID, "Input, gcoef and detJ are required");
     if (nb < 1 || integNum < 1) return fail(VN_E_INVALID, "intShape must be positive");
     const vn_config& c = e->cfg;
@@ -583,10 +595,67 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
     t->pstride = (P + kPad - 1) / kPad * kPad;
     t->rows = (unsigned int)P; t->nbTab = (unsigned int)nb; t->integNum = (unsigned int)integNum; t->detJvec = detJvec ? 1 : 0;
     CK(t->cols.ensure((size_t)t->ncols * t->pstride * sizeof(float)));
-    CK(cudaMemsetAsync(t->cols.p, 0, (size_t)t->ncols * t->pstride * sizeof(float), e->stream));
     const int rowVals = nx + c.dim + 3;
     const long long chunk = std::min<long long>(kChunk, P);
-    CK(e->stage.ensure((size_t)chunk * rowVals * sizeof(T)));
+    const long long nd = detJvec ? nb : 1;
+    CK(e->stage.ensure(std::max((size_t)chunk * rowVals, (size_t)std::max<long long>(nd, integNum)) * sizeof(T)));
+    if (plan) {
+        // small tables first (they share the staging buffer), then the chunks on the copy stream without host syncs
+        if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+        t->hasIntegW = (c.integWflag && integW) ? 1 : 0;
+        CK(t->detJ.ensure(nd * sizeof(float)));
+        CK(cudaMemcpyAsync(e->stage.p, detJ, nd * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        vn_cast_kernel<T><<<(unsigned)((nd + 255) / 256), 256, 0, e->stream>>>(e->stage.as<T>(), t->detJ.as<float>(), nd);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        if (t->hasIntegW) {
+            CK(t->integW.ensure(integNum * sizeof(float)));
+            CK(cudaMemcpyAsync(e->stage.p, integW, integNum * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+            vn_cast_kernel<T><<<(integNum + 255) / 256, 256, 0, e->stream>>>(e->stage.as<T>(), t->integW.as<float>(), integNum);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(e->stream));
+        }
+        e->launches += 1 + t->hasIntegW;
+        cudaStream_t us = e->copyStream;
+        // only the zero padding behind the last row has to be cleared: every other element is overwritten by the packs
+        if (t->pstride > P)
+            for (int cc = 0; cc < t->ncols; ++cc)
+                CK(cudaMemsetAsync(t->cols.as<float>() + (size_t)cc * t->pstride + P, 0, (size_t)(t->pstride - P) * sizeof(float), us));
+        const int TP = e->gVarAdj.TP;
+        size_t k = 0;
+        for (long long off = 0; off < P; off += chunk, ++k) {
+            const long long n = std::min(chunk, P - off);
+            T* sX = e->stage.as<T>();
+            T* sG = sX + n * nx;
+            T* sT = sG + n * c.dim;
+            T* sS = sT + n;
+            T* sN = sS + n;
+            CK(cudaMemcpyAsync(sX, X + off * nx, n * nx * sizeof(T), cudaMemcpyHostToDevice, us));
+            CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, us));
+            if (t->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+            if (t->colS >= 0) {
+                CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+                CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+            }
+            vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, us>>>(
+                sX, nx, sG, c.dim, t->colT >= 0 ? sT : nullptr, t->colS >= 0 ? sS : nullptr,
+                t->colS >= 0 ? sN : nullptr, t->cols.as<float>(), t->pstride, off, n, t->colX, t->colG, t->colT, t->colS);
+            CK(cudaGetLastError());
+            e->launches++;
+            if (e->fedEvents.size() <= k) {
+                cudaEvent_t ev;
+                CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                e->fedEvents.push_back(ev);
+            }
+            CK(cudaEventRecord(e->fedEvents[k], us));
+            plan->subs.push_back({(int)(off / TP), (int)((n + TP - 1) / TP), e->fedEvents[k]});
+        }
+        t->loaded = true;
+        e->indexed = false;
+        e->nb = t->nbTab;
+        return ensure_work(e);
+    }
+    CK(cudaMemsetAsync(t->cols.p, 0, (size_t)t->ncols * t->pstride * sizeof(float), e->stream));
     for (long long off = 0; off < P; off += chunk) {
         const long long n = std::min(chunk, P - off);
         T* sX = e->stage.as<T>();
@@ -610,9 +679,7 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
     }
     // small tables
     t->hasIntegW = (c.integWflag && integW) ? 1 : 0;
-    const long long nd = detJvec ? nb : 1;
     CK(t->detJ.ensure(nd * sizeof(float)));
-    CK(e->stage.ensure((size_t)std::max<long long>(nd, integNum) * sizeof(T)));
     CK(cudaMemcpyAsync(e->stage.p, detJ, nd * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     vn_cast_kernel<T><<<(unsigned)((nd + 255) / 256), 256, 0, e->stream>>>(e->stage.as<T>(), t->detJ.as<float>(), nd);
     CK(cudaGetLastError());
@@ -837,7 +904,7 @@ static int run_loss_tc(vn_engine* e, bool needGrad) {
     return VN_OK;
 }
 
-static int run_loss(vn_engine* e, bool needGrad) {
+static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (!e->P || !e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
     if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
@@ -859,8 +926,19 @@ static int run_loss(vn_engine* e, bool needGrad) {
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
         ProfScope ps(e, PK_VAR_ADJ);
-        CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
-        e->launches++;
+        if (plan) {
+            // one launch per uploaded chunk, each waiting for its own pack kernel on the copy stream
+            for (size_t k = 0; k < plan->subs.size(); ++k) {
+                CK(cudaStreamWaitEvent(st, plan->subs[k].ev, 0));
+                a.tile0 = plan->subs[k].tile0; a.ntiles = plan->subs[k].ntiles; a.accumulate = k > 0 ? 1 : 0;
+                CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
+                e->launches++;
+            }
+            a.tile0 = 0; a.accumulate = 0;
+        } else {
+            CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
+            e->launches++;
+        }
         nSeg = e->gridVar * (g.NT / 32);
         segPtr = e->lossPart.as<double>();
     } else {
@@ -952,6 +1030,40 @@ extern "C" int vn_loss_grad(vn_engine* e, float out[4]) {
     if (rc) return rc;
     if (out) return read_scalars(e, out);
     return VN_OK;
+}
+// Loss + gradient of a step whose point table arrives with the call (the reference feeds every array on every
+// sess.run, VarNetUtility.py:1044): same result as vn_upload_points_* followed by vn_loss_grad, but the chunked
+// host-to-device copies overlap the step's kernels.  The caller's arrays are no longer read when the call returns.
+template <typename T>
+static int loss_grad_fed(vn_engine* e, const T* X, const T* G, const T* src, const T* N, const T* dNt, int64_t nb,
+                         int32_t integNum, const T* integW, const T* detJ, int32_t detJvec, float out[4]) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    e->nExtra = 0;
+    const long long P = (long long)nb * integNum;
+    const bool overlap = e->wclass != 256 && e->nbi > 0 && P > kChunk && integNum > 0 && (e->gVarAdj.TP % integNum) == 0 &&
+                         kChunk % e->gVarAdj.TP == 0 && kChunk / e->gVarAdj.TP >= e->numSMs && !e->profOn;
+    if (!overlap) {
+        int rc = upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec);
+        if (rc) return rc;
+        rc = run_loss(e, true);
+        if (rc) return rc;
+        return out ? read_scalars(e, out) : VN_OK;
+    }
+    FedPlan plan;
+    int rc = upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec, &plan);
+    if (!rc) rc = run_loss(e, true, &plan);
+    cudaError_t ce = cudaStreamSynchronize(e->copyStream);          // every copy out of the caller's arrays has completed
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(VN_E_CUDA, "copy stream: %s", cudaGetErrorString(ce));
+    return out ? read_scalars(e, out) : VN_OK;
+}
+extern "C" int vn_loss_grad_fed_f32(vn_engine* e, const float* X, const float* G, const float* s, const float* N, const float* dNt,
+                                    int64_t nb, int32_t integNum, const float* iw, const float* dj, int32_t djv, float out[4]) {
+    return loss_grad_fed<float>(e, X, G, s, N, dNt, nb, integNum, iw, dj, djv, out);
+}
+extern "C" int vn_loss_grad_fed_f64(vn_engine* e, const double* X, const double* G, const double* s, const double* N, const double* dNt,
+                                    int64_t nb, int32_t integNum, const double* iw, const double* dj, int32_t djv, float out[4]) {
+    return loss_grad_fed<double>(e, X, G, s, N, dNt, nb, integNum, iw, dj, djv, out);
 }
 extern "C" int vn_grad_buffer(vn_engine* e, void** p, int64_t* n) {
     if (!e || !p || !n) return fail(VN_E_INVALID, "null argument");

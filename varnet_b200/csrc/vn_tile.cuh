@@ -61,6 +61,8 @@ struct TileArgs {
     int dim;                        // spatial dimension (residual kernel: runtime stream roles)
     unsigned int P;                 // valid points (rows)
     int ntiles;
+    int tile0;                      // first tile of this launch (adjoint kernels launched per uploaded chunk, vn_loss_grad_fed)
+    int accumulate;                 // 1: add to the partial slabs / loss partials of the previous launches of this step
     int timeDependent, isSource;
     // variational term
     unsigned int integNum;
@@ -617,11 +619,11 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
     float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
     double lossAcc = 0.0;                                    // lane 0 of each warp (FUSED)
     bool first = true;                                       // first tile of the current FP32 window
-    bool firstFold = true;
+    bool firstFold = !A.accumulate;
     int win = 0;
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
-        const unsigned int base = (unsigned int)tile * TP;
+        const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
         load_inputs<C>(A, m, base);
         if (MODE == MODE_VAR_ADJ) {
             // seeds from the globally reduced R_i: lambda = 2 w2 detJ_i w_q R_i ; ubar = -lambda dNt ; ubar_k = lambda gcoef_k
@@ -840,7 +842,10 @@ __global__ void __launch_bounds__(C::NT, 1) vn_adj_kernel(const __grid_constant_
             firstFold = false; first = true; win = 0;
         }
     }
-    if (FUSED && lane == 0) A.lossPart[blockIdx.x * C::NW + warp] = lossAcc;
+    if (FUSED && lane == 0) {
+        double* lp = A.lossPart + blockIdx.x * C::NW + warp;
+        *lp = A.accumulate ? *lp + lossAcc : lossAcc;
+    }
 }
 
 // ------------------------------------------------------------------ small kernels
