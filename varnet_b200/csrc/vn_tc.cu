@@ -1075,17 +1075,6 @@ cudaError_t vn_tc_prepare(int S, int act) {
     if ((e = prep_gemm<EPI_FWD_TANGENT>()) != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_ADJ_TANGENT>()) != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_ADJ_VALUE>()) != cudaSuccess) return e;
-    if (getenv("VARNET_B200_TC_DEBUG")) {
-        int nb = 0;
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>);
-        for (int pct = -1; pct <= 100; pct += (pct < 0 ? 51 : 10)) {
-            if (pct >= 0) cudaFuncSetAttribute(tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, NTHR, TS_SMEM_BYTES);
-            fprintf(stderr, "[vn_tc] A-from-TMEM layer GEMM: carveout %d%% -> %d CTAs/SM (smem %d B, %d regs, static smem %zu, local %zu)\n", pct, nb, TS_SMEM_BYTES, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes);
-        }
-        cudaFuncSetAttribute(tc_gemm_kernel<EPI_ADJ_TANGENT, VN_TANH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, -1);
-    }
     return cudaSuccess;
 }
 
