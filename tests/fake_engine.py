@@ -27,7 +27,7 @@ class FakeEngine:
         self.theta = np.zeros(self.nparam); self.m = np.zeros(self.nparam); self.v = np.zeros(self.nparam)
         self.step = 0
         self.feed = {"w": np.ones(3)}          # the real engine also starts with unit loss weights
-        self.calls = dict(upload_points=0, upload_bic=0, loss=0, loss_grad=0, step=0, eval=0)
+        self.calls = dict(upload_points=0, upload_bic=0, loss=0, loss_grad=0, loss_grad_fed=0, step=0, eval=0)
         self.gbuf = np.zeros(self.nparam + 4)
         FakeEngine.instances.append(self)
 
@@ -127,6 +127,13 @@ class FakeEngine:
         if fetch:
             return dict(loss=np.float32(r["loss"]), BCloss=np.float32(r["BCloss"]), ICloss=np.float32(r["ICloss"]),
                         varLoss=np.float32(r["varLoss"]), grad=r["grad"].astype(np.float32))
+
+    def loss_grad_fed(self, Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec=False, dtype=None, fetch=False):
+        # same contract as Engine.loss_grad_fed: upload_points + loss_grad in one call
+        self.calls["loss_grad_fed"] += 1
+        self.upload_points(Input, gcoef, source, N, dNt, intShape, integW, detJ, detJvec, dtype=dtype)
+        r = self.loss_grad(fetch=True)
+        return {k: r[k] for k in ("loss", "BCloss", "ICloss", "varLoss")} if fetch else None
 
     def torch_device(self):
         return "cpu"

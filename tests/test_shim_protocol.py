@@ -57,11 +57,20 @@ def test_feed_cache_semantics(shim):
     tf.feed_cache = False
     tData.optimIter(tf)
     assert eng.calls["upload_points"] == 2                                         # reference-style re-feed
+    # plain NumPy feeds (what the reference builds) that change every step go through the fed step
+    from varnet_b200.tables import TableView
+    plain = {k: (np.asarray(v) if isinstance(v, TableView) else v) for k, v in tData.optimFeedicts[0].items()}
+    before = tf.get_parameters().copy()
+    _, loss = tf.sess.run([tf.optMinimize, tf.loss], feed_dict=plain)
+    assert eng.calls["loss_grad_fed"] == 1 and np.isfinite(loss)
+    assert not np.array_equal(before, tf.get_parameters())                         # the optimizer step was applied
+    tData.optimIter(tf)                                                            # back to the view feed: uploaded again (cache off)
     tf.feed_cache = True
     w = np.array([2., 3., 4.])
     tData.updateDictFields('trainW', w, normalizeW=False)
+    n_up = eng.calls["upload_points"]
     tData.optimIter(tf)
-    assert np.allclose(eng.feed["w"], [2., 3., 4.]) and eng.calls["upload_points"] == 2
+    assert np.allclose(eng.feed["w"], [2., 3., 4.]) and eng.calls["upload_points"] == n_up
 
 
 def test_constructor_errors_match_reference_messages(shim):
