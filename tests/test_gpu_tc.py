@@ -177,3 +177,21 @@ def test_shared_memory_operand_pipeline_matches_oracle(monkeypatch):
         check_against_oracle(eng, ref, feed, inpDim, lw, True)
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale,act", [(4.0, "tanh"), (6.0, "sigmoid"), (0.05, "tanh")])
+def test_split_product_is_robust_to_weight_scale(scale, act):
+    """Saturated activations (large weights) and tiny pre-activations (small weights): the hi/lo split keeps FP32-level
+    parity over the whole exponent range the layers see."""
+    rng = np.random.RandomState(5)
+    dim, inpDim, lw = 2, 3, [256, 192, 256]
+    feed = synth_feed(rng, dim, inpDim, 60, 64, 300, 200)
+    theta = (go.glorot_init(inpDim, lw, seed=7) * scale).astype(np.float32)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation=act, timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    ref = go.loss_and_grad(theta, feed, **kw)
+    eng = make_engine(feed, theta=theta, **kw)
+    try:
+        check_against_oracle(eng, ref, feed, inpDim, lw, True)
+    finally:
+        eng.close()
