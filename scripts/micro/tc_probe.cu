@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(128) tc_probe(const float* __restrict__ Ag, co
             const int m = idx / K, k = idx % K;
             sA[((k / 4) * A_LBO + (m / 8) * A_SBO + (m % 8) * 16 + (k % 4) * 4) / 4] = (k == (m % 64)) ? 1.f : 0.f;
         }
-        for (int w = tid; w < N * K; w += 128) sB[w] = (mode == 3 || mode == 5) ? (float)(w / 4 + 1) : (float)(w % 4 + 1);   // +1: zero means "nothing read"
+        // the pattern covers all shared memory behind sA (64 KB), so reads outside the 16 KB operand still show up
+        for (int w = tid; w < (98304 - 32768) / 4; w += 128) sB[w] = (mode == 3 || mode == 5) ? (float)(w / 4 + 1) : (float)(w % 4 + 1);   // +1: zero means "nothing read"
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
