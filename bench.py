@@ -346,6 +346,19 @@ def main():
     ms_e2e /= args.e2e_steps
     tf.feed_cache = True
 
+    # the same table built on the device from the mesh centres + periodic FE tables (vn_generate_table_f64): compare
+    # with table_build_s (host NumPy build + pinning); spare slot, freed again
+    t_gen = None
+    try:
+        eng.select_table(1)
+        t0g = time.perf_counter()
+        workloads.generate_on_device(eng, nx, ny, ntime, n0, n1)
+        eng.synchronize()
+        t_gen = time.perf_counter() - t0g
+        eng.free_table(1)
+        eng.select_table(0)
+    except Exception:
+        t_gen = None
     if rank == 0:
         flop_pt = workloads.algorithmic_flops_per_point(meta["inpDim"], meta["dim"], lw)
         adj_ms, adj_n = prof["var_adj"]
@@ -380,7 +393,7 @@ def main():
         line = dict(metric=METRIC, value=P_total / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic", config=config,
-                    train_steps_per_sec=1e3 / ms_step, loss=float(loss), table_build_s=t_build,
+                    train_steps_per_sec=1e3 / ms_step, loss=float(loss), table_build_s=t_build, device_table_generate_s=t_gen,
                     roofline=roofline,
                     e2e=dict(value=P_total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e, api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f32: copies overlap the kernels)"),

@@ -101,6 +101,21 @@ int vn_upload_bic_f64(vn_engine* e, const double* biInput, const double* biLabel
  *      (on-device permutation; needs integNum % 4 == 0), and trailing MLP inputs that are constant over
  *      a batch (MOR parameters) are passed as scalars instead of re-tiled columns.
  *      vn_upload_table_*: like vn_upload_points_* but Input has only the first `nx` MLP input columns. */
+/* vn_generate_table_f64: build the point table of a UNIFORM space-time mesh with CONSTANT coefficients on the device,
+ * into the current table slot — what VarNet.trainingPoints (VarNet.py:576-586), PDEinpData/trainData
+ * (gcoef = diff*dNx + vel*N, VarNet.py:837) and the periodic FE tables of FE.basisTot (FiniteElement.py:419-432)
+ * produce on the host, without materialising or uploading nT rows.  For test function i = s*nTime + j (space index
+ * slow, time index fast) and Gauss point q:
+ *     Input[i,q,d] = coord[s][d] + hVec[d]*delta[d][q]  (d < dim),   Input[i,q,dim] = tcoord[j] + hVec[dim]*delta[dim][q]
+ *     gcoef[i,q,k] = diff*dN[q][k] + vel[k]*N[q],   dNt[i,q] = dN[q][dim],   source*N = source*N[q]
+ * in float64 with the host's operation order, rounded to float32 like the feed cast: the table is bit-identical to
+ * uploading the host-built arrays.  Generates test functions [tf0, tf0+nb) (one tower's contiguous range).
+ * coord [nSpace][dim], tcoord [nTime] (NULL when not time dependent), hVec [feDim], delta [feDim][integNum],
+ * N [integNum], dN [integNum][feDim], vel [dim], integW [integNum] or NULL; detJ is the scalar Jacobian. */
+int vn_generate_table_f64(vn_engine* e, const double* coord, int64_t nSpace, const double* tcoord, int64_t nTime,
+                          const double* hVec, const double* delta, const double* N, const double* dN,
+                          double diff, const double* vel, double source, int64_t tf0, int64_t nb,
+                          int32_t integNum, const double* integW, double detJ);
 int vn_select_table(vn_engine* e, int32_t slot);
 int vn_table_loaded(const vn_engine* e, int32_t slot);                 /* 1 if the slot holds a table */
 int vn_free_table(vn_engine* e, int32_t slot);

@@ -270,3 +270,36 @@ def test_fed_step_overlapping_copies_equals_upload_then_step():
         assert abs(float(a[0][k]) - float(b[0][k])) <= 1e-6 * abs(float(a[0][k])), k
     assert rel_inf(b[0]["grad"], a[0]["grad"]) <= 1e-6
     assert np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integPnum", [2, 3])
+def test_device_generated_table_is_bit_identical_to_the_uploaded_one(integPnum):
+    """vn_generate_table_f64 (uniform mesh, constant coefficients, table built on the device from the mesh centres and
+    the periodic FE tables) against uploading the host-built arrays of the same test-function range: identical loss
+    bits, lossVec and gradient."""
+    from varnet_b200 import workloads
+    from varnet_b200._capi import Engine
+    nx, ny, ntime, n0, n1 = 9, 7, 6, 37, 301
+    feed, meta = workloads.shard_feed(nx, ny, ntime, n0, n1, integPnum=integPnum, dtype=np.float64)
+    lw = [12, 20]
+    theta = go.glorot_init(3, lw, seed=5)
+    res = []
+    for dev in (False, True):
+        eng = Engine(2, 3, lw, "tanh", True, False, meta["lossOpt"]["integWflag"])
+        eng.set_params(theta)
+        if dev:
+            bic, _ = workloads.generate_on_device(eng, nx, ny, ntime, n0, n1, integPnum=integPnum)
+            assert bic["intShape"] == feed["intShape"]
+        else:
+            eng.upload_points(feed["Input"], feed["gcoef"], feed["source"], feed["N"], feed["dNt"], feed["intShape"],
+                              feed["integW"], feed["detJ"], False)
+        eng.upload_bic(feed["biInput"], feed["biLabel"], feed["bDof"], feed["biDimVal"])
+        eng.set_weights([2.0, 3.0, 5.0])
+        out = eng.loss_grad()
+        lv = eng.loss(lossVec=True)["lossVec"]
+        res.append((out, lv))
+        eng.close()
+    (a, la), (b, lb) = res
+    assert all(np.float32(a[k]) == np.float32(b[k]) for k in ("loss", "BCloss", "ICloss", "varLoss"))
+    assert np.array_equal(la, lb) and np.array_equal(a["grad"], b["grad"])

@@ -45,6 +45,8 @@ SIGNATURES = {
     "vn_select_table": (C.c_int, [_vp, _i32]),
     "vn_table_loaded": (C.c_int, [_vp, _i32]),
     "vn_free_table": (C.c_int, [_vp, _i32]),
+    "vn_generate_table_f64": (C.c_int, [_vp, _f64p, _i64, _f64p, _i64, _f64p, _f64p, _f64p, _f64p, C.c_double, _f64p, C.c_double,
+                                        _i64, _i64, _i32, _f64p, C.c_double]),
     "vn_upload_table_f32": (C.c_int, [_vp, _f32p, _i32, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _i32]),
     "vn_upload_table_f64": (C.c_int, [_vp, _f64p, _i32, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32]),
     "vn_set_batch": (C.c_int, [_vp, C.POINTER(_i32), _i64]),
@@ -253,6 +255,21 @@ class Engine:
         self._check(fn(self._h, _ptr(X, ct), nx, _ptr(G, ct), _ptr(S, ct), _ptr(Nn, ct), _ptr(T, ct), nb, integNum,
                        _ptr(W, ct), _ptr(D, ct), int(bool(detJvec))))
         self.nb = nb
+
+    def generate_table(self, coord, tcoord, hVec, delta, N, dN, diff, vel, source, tf0, nb, integNum, integW, detJ):
+        """Point table of a uniform mesh with constant coefficients, built on the device (vn_generate_table_f64)."""
+        f64 = lambda v, shape=None: None if v is None else np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(shape if shape is not None else -1))
+        feDim = self.dim + (1 if self.cfg.timeDependent else 0)
+        coord = f64(coord, (-1, self.dim)); tc = f64(tcoord) if self.cfg.timeDependent else None
+        h = f64(hVec); d = f64(delta, (feDim, integNum)); Nq = f64(N); dNq = f64(dN, (integNum, feDim)); v = f64(vel)
+        W = f64(integW) if self.cfg.integWflag else None
+        if h.size != feDim or Nq.size != integNum or v.size != self.dim:
+            raise ValueError("hVec/N/vel have the wrong size for this engine")
+        self._check(self.lib.vn_generate_table_f64(self._h, _ptr(coord, C.c_double), coord.shape[0], _ptr(tc, C.c_double),
+                                                   0 if tc is None else tc.size, _ptr(h, C.c_double), _ptr(d, C.c_double),
+                                                   _ptr(Nq, C.c_double), _ptr(dNq, C.c_double), float(diff), _ptr(v, C.c_double),
+                                                   float(source), int(tf0), int(nb), int(integNum), _ptr(W, C.c_double), float(detJ)))
+        self.nb = int(nb)
 
     def upload_bic(self, biInput, biLabel, bDof, biDimVal, dtype=None):
         if dtype is None:

@@ -222,6 +222,37 @@ __global__ void vn_pack_kernel(const T* __restrict__ X, int inpDim, const T* __r
     if (dNt && colT >= 0) cols[(size_t)colT * pstride + gp] = to_f32<T>(dNt[r]);
     if (src && N && colS >= 0) cols[(size_t)colS * pstride + gp] = to_f32<T>(src[r]) * to_f32<T>(N[r]);   // float32 product, as tf.multiply(source, N) (:657)
 }
+// Point table of a uniform space-time mesh with constant coefficients, generated in place (vn_generate_table_f64).
+// Same float64 operation order as the host code it replaces (VarNet.py:576-586,837; no FMA contraction), rounded to
+// float32 like the feed cast, so the table is bit-identical to an uploaded one.
+struct GenArgs {
+    const double* coord; const double* tcoord; long long nTime;
+    double h[VN_MAX_INPDIM];            // element sizes he[d], then ht
+    const double* delta;                // [feDim][q]
+    const double* N; const double* dN;  // [q], [q][feDim]
+    double diff, vel[3], source;
+    long long tf0, n; int q, dim, feDim;
+    float* cols; long long pstride; int colX, colG, colT, colS;
+};
+__global__ void vn_generate_kernel(const GenArgs a) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    const long long i = a.tf0 + r / a.q;
+    const int qq = (int)(r % a.q);
+    const long long s = i / a.nTime, j = i - s * a.nTime;
+    for (int d = 0; d < a.dim; ++d)
+        a.cols[(size_t)(a.colX + d) * a.pstride + r] =
+            __double2float_rn(__dadd_rn(a.coord[s * a.dim + d], __dmul_rn(a.h[d], a.delta[(size_t)d * a.q + qq])));
+    if (a.feDim > a.dim)
+        a.cols[(size_t)(a.colX + a.dim) * a.pstride + r] =
+            __double2float_rn(__dadd_rn(a.tcoord[j], __dmul_rn(a.h[a.dim], a.delta[(size_t)a.dim * a.q + qq])));
+    const double Nq = a.N[qq];
+    for (int k = 0; k < a.dim; ++k)
+        a.cols[(size_t)(a.colG + k) * a.pstride + r] =
+            __double2float_rn(__dadd_rn(__dmul_rn(a.diff, a.dN[(size_t)qq * a.feDim + k]), __dmul_rn(a.vel[k], Nq)));
+    if (a.colT >= 0) a.cols[(size_t)a.colT * a.pstride + r] = __double2float_rn(a.dN[(size_t)qq * a.feDim + a.dim]);
+    if (a.colS >= 0) a.cols[(size_t)a.colS * a.pstride + r] = __double2float_rn(a.source) * __double2float_rn(Nq);
+}
 // residual inputs: X | diff | vel[dim] | diff_dx[dim] | source  ->  SoA columns
 template <typename T>
 __global__ void vn_pack_res_kernel(const T* __restrict__ X, int inpDim, const T* __restrict__ diff,
@@ -704,6 +735,73 @@ static int upload_points(vn_engine* e, const T* X, const T* G, const T* src, con
     if (!e) return fail(VN_E_INVALID, "null engine");
     e->nExtra = 0;
     return upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec);
+}
+
+extern "C" int vn_generate_table_f64(vn_engine* e, const double* coord, int64_t nSpace, const double* tcoord, int64_t nTime,
+                                     const double* hVec, const double* delta, const double* N, const double* dN,
+                                     double diff, const double* vel, double source, int64_t tf0, int64_t nb,
+                                     int32_t integNum, const double* integW, double detJ) {
+    if (!e || !coord || !hVec || !delta || !N || !dN || !vel) return fail(VN_E_INVALID, "null argument");
+    const vn_config& c = e->cfg;
+    const int feDim = c.dim + (c.timeDependent ? 1 : 0);
+    if (c.timeDependent && (!tcoord || nTime < 1)) return fail(VN_E_INVALID, "time coordinates are required for time-dependent problems");
+    if (!c.timeDependent) nTime = 1;
+    if (nb < 1 || integNum < 1 || nSpace < 1) return fail(VN_E_INVALID, "intShape must be positive");
+    if (tf0 < 0 || tf0 + nb > nSpace * nTime) return fail(VN_E_INVALID, "test-function range [%lld, %lld) outside the mesh (%lld)", (long long)tf0, (long long)(tf0 + nb), (long long)(nSpace * nTime));
+    if (c.integWflag && !integW) return fail(VN_E_INVALID, "integW is required when lossOpt['integWflag'] is set");
+    const long long P = (long long)nb * integNum;
+    if (P >= (1ll << 31) - kPad) return fail(VN_E_UNSUPPORTED, "more than 2^31 quadrature points per engine; shard the test functions");
+    CK(cudaSetDevice(c.device));
+    PointSet* t = e->t;
+    drop_graph(t);
+    int col = 0;
+    t->nx = feDim;
+    t->colX = col; col += feDim;
+    t->colG = col; col += c.dim;
+    t->colT = c.timeDependent ? col++ : -1;
+    t->colS = c.isSource ? col++ : -1;
+    t->ncols = col;
+    t->pstride = (P + kPad - 1) / kPad * kPad;
+    t->rows = (unsigned int)P; t->nbTab = (unsigned int)nb; t->integNum = (unsigned int)integNum; t->detJvec = 0;
+    CK(t->cols.ensure((size_t)t->ncols * t->pstride * sizeof(float)));
+    CK(cudaMemsetAsync(t->cols.p, 0, (size_t)t->ncols * t->pstride * sizeof(float), e->stream));
+    // small host tables -> staging (doubles): coord | tcoord | delta | N | dN | integW
+    const size_t nC = (size_t)nSpace * c.dim, nT = c.timeDependent ? (size_t)nTime : 0, nD = (size_t)feDim * integNum;
+    const size_t nTot = nC + nT + nD + (size_t)integNum + nD + (size_t)integNum + 1;
+    CK(e->stage.ensure(nTot * sizeof(double)));
+    double* sC = e->stage.as<double>();
+    double* sT = sC + nC; double* sD = sT + nT; double* sN = sD + nD; double* sdN = sN + integNum; double* sW = sdN + nD;
+    CK(cudaMemcpyAsync(sC, coord, nC * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (nT) CK(cudaMemcpyAsync(sT, tcoord, nT * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sD, delta, nD * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sN, N, (size_t)integNum * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(sdN, dN, nD * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    GenArgs g;
+    memset(&g, 0, sizeof(g));
+    g.coord = sC; g.tcoord = sT; g.nTime = nTime; g.delta = sD; g.N = sN; g.dN = sdN;
+    for (int d = 0; d < feDim; ++d) g.h[d] = hVec[d];
+    g.diff = diff; for (int k = 0; k < c.dim; ++k) g.vel[k] = vel[k];
+    g.source = source; g.tf0 = tf0; g.n = P; g.q = integNum; g.dim = c.dim; g.feDim = feDim;
+    g.cols = t->cols.as<float>(); g.pstride = t->pstride; g.colX = t->colX; g.colG = t->colG; g.colT = t->colT; g.colS = t->colS;
+    vn_generate_kernel<<<(unsigned)((P + 255) / 256), 256, 0, e->stream>>>(g);
+    CK(cudaGetLastError());
+    t->hasIntegW = (c.integWflag && integW) ? 1 : 0;
+    CK(t->detJ.ensure(sizeof(float)));
+    const float dj = (float)detJ;
+    CK(cudaMemcpyAsync(t->detJ.p, &dj, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (t->hasIntegW) {
+        CK(t->integW.ensure(integNum * sizeof(float)));
+        CK(cudaMemcpyAsync(sW, integW, (size_t)integNum * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        vn_cast_kernel<double><<<(integNum + 255) / 256, 256, 0, e->stream>>>(sW, t->integW.as<float>(), integNum);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->launches += 1 + t->hasIntegW;
+    t->loaded = true;
+    e->indexed = false;
+    e->nb = t->nbTab;
+    if (c.inpDim == feDim) e->nExtra = 0;  // otherwise the trailing MLP inputs (MOR parameters) come from vn_set_extra_inputs
+    return ensure_work(e);
 }
 
 extern "C" int vn_select_table(vn_engine* e, int32_t slot) {

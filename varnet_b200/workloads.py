@@ -73,6 +73,33 @@ def shard_feed(nx, ny, ntime, n0=None, n1=None, integPnum=2, dtype=np.float32, w
     return feed, meta
 
 
+def generate_on_device(engine, nx, ny, ntime, n0=None, n1=None, integPnum=2):
+    """The table of `shard_feed(nx, ny, ntime, n0, n1)` built on the device (vn_generate_table_f64): only the mesh
+    centres and the periodic FE tables (a few KB) cross the bus; no nT-row host arrays are materialised.  Returns the
+    boundary/initial part of the feed (small, still built on the host) and the same `meta` as `shard_feed`."""
+    pde = synthetic_pde()
+    domain = pde.domain
+    mesh = domain.getMesh([nx, ny], SYNTH["bDiscNum"])
+    t0, t1 = SYNTH["tInterval"]
+    ht = (t1 - t0) / ntime
+    t_coord = np.linspace(t0 + ht, t1, ntime).reshape(ntime, 1)
+    hVec = np.vstack([np.reshape(mesh.he, [2, 1]), ht])
+    per = FE(3, integPnum).periodic_tables(hVec)
+    q = per["integNum"]
+    nt = mesh.dof * ntime
+    n0 = 0 if n0 is None else n0
+    n1 = nt if n1 is None else n1
+    engine.generate_table(mesh.coordinates, t_coord, hVec, per["delta"], per["N"], per["dN"].T, SYNTH["diff"], SYNTH["vel"], 0.0,
+                          n0, n1 - n0, q, per["intWeight"], per["detJ"])
+    bInput = np.vstack([pair_rows(bc, t_coord) for bc in mesh.bCoordinates])
+    iInput = np.concatenate([mesh.coordinates, np.zeros([mesh.dof, 1])], axis=1)
+    biInput = np.vstack([bInput, iInput])
+    feed = dict(biInput=biInput, biLabel=np.zeros([len(biInput), 1]), bDof=len(bInput), biDimVal=domain.measure,
+                intShape=[n1 - n0, q])
+    meta = dict(nt=nt, integNum=q, dim=2, inpDim=3, timeDependent=True, lossOpt=dict(isSource=False, integWflag=integPnum != 2))
+    return feed, meta
+
+
 def mlp_macs(inpDim, layerWidth):
     dims = [inpDim] + list(layerWidth) + [1]
     return sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
