@@ -100,18 +100,55 @@ __device__ static double block_sum(double v, double* sh) {
     return r;   // valid in thread 0
 }
 
+// TF-1.x Adam (adam.py _apply_dense): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).
+// `corr` = sqrt(1-b2^t)/(1-b1^t) for the step being applied, maintained by vn_advance_kernel.
+__device__ __forceinline__ void adam_update(float* theta, float* m, float* v, int i, float gi, float lr, const double* corr) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float lr_t = lr * (float)corr[0];
+    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+__global__ void vn_adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                               const float* __restrict__ g, int n, float lr, const double* __restrict__ corr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_update(theta, m, v, i, g[i], lr, corr);
+}
+// TF-1.x RMSProp (decay .9, momentum 0, eps 1e-10, ms initialised to ones): ms = .9 ms + .1 g^2;
+// mom = lr*g/sqrt(ms+eps); theta -= mom.
+__device__ __forceinline__ void rmsprop_update(float* theta, float* ms, int i, float gi, float lr) {
+    const float s = 0.9f * ms[i] + 0.1f * gi * gi;
+    ms[i] = s;
+    theta[i] -= lr * gi / sqrtf(s + 1e-10f);
+}
+__global__ void vn_rmsprop_kernel(float* __restrict__ theta, float* __restrict__ ms, const float* __restrict__ g,
+                                  int n, float lr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rmsprop_update(theta, ms, i, g[i], lr);
+}
+__device__ __forceinline__ void advance_step(long long* step, double* corr) {
+    const long long t = step[0] + 1;       // step just applied
+    step[0] = t;
+    const double tn = (double)(t + 1);     // bias correction of the NEXT step
+    corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
+}
+__global__ void vn_advance_kernel(long long* step, double* corr) { advance_step(step, corr); }
+
 // Blocks [0, gridDim.x-1): one WARP per flat parameter sums the per-CTA FP64 slabs: lane c takes slabs
 // c, c+32, ... in order and the lanes are combined by a fixed xor tree (deterministic replacement for
 // TF's gradient accumulation; a serial per-thread walk over ~300 slabs was latency-bound).
 // Last block: the loss scalars loss = w0*bCs + w1*iCs + w2*varLoss (TFModel.py:643-666).
+// With fuseOpt the optimizer update is applied by the same warps and the last block to finish advances the step.
 __global__ void vn_finalize_kernel(FinalArgs A) {
     const NetDesc& net = A.net;
     const PartLayout& pl = A.pl;
     if (blockIdx.x + 1 < gridDim.x) {
-        if (!A.needGrad) return;
         const int lane = threadIdx.x & 31;
         const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (idx >= net.nparam) return;
+        if (A.needGrad && idx < net.nparam) {
         // locate (layer, kind, i, j)
         int l = 0, isBias = 0, i = 0, j = 0;
         for (l = 0; l <= net.L; ++l) {
@@ -143,9 +180,15 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         for (int c = lane; c < A.nBic; c += 32)
             for (int p = 0; p < nslot; ++p) s += __ldcg(A.partBic + (size_t)c * pl.psz + slot[p]);
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) A.gbuf[idx] = (float)s;
-        return;
-    }
+        if (lane == 0) {
+            const float g = (float)s;
+            A.gbuf[idx] = g;
+            // single-GPU training step: apply_gradients fused into the reduction (TFModel.py:313)
+            if (A.fuseOpt == 1) adam_update(A.theta, A.m, A.v, idx, g, A.lr, A.corr);
+            else if (A.fuseOpt == 2) rmsprop_update(A.theta, A.v, idx, g, A.lr);
+        }
+        }
+    } else {
     __shared__ double sh[32];
     double v = 0.0;
     for (int k = threadIdx.x; k < A.nSeg; k += blockDim.x) v += A.segSum[k];
@@ -165,39 +208,23 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         float* o = A.gbuf + net.nparam;
         o[0] = loss; o[1] = bCs; o[2] = iCs; o[3] = varLoss;
     }
+    }
+    if (A.fuseOpt) {
+        // the last block to get here advances the step counter / Adam bias correction: every parameter warp has read
+        // `corr` before its block took a ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(A.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                advance_step(A.step, A.corr);
+                *A.ticket = 0u;
+            }
+        }
+    }
 }
 
-// TF-1.x Adam (adam.py _apply_dense): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).
-// `corr` = sqrt(1-b2^t)/(1-b1^t) for the step being applied, maintained by vn_advance_kernel.
-__global__ void vn_adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
-                               const float* __restrict__ g, int n, float lr, const double* __restrict__ corr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    const float lr_t = lr * (float)corr[0];
-    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
-}
-// TF-1.x RMSProp (decay .9, momentum 0, eps 1e-10, ms initialised to ones): ms = .9 ms + .1 g^2;
-// mom = lr*g/sqrt(ms+eps); theta -= mom.
-__global__ void vn_rmsprop_kernel(float* __restrict__ theta, float* __restrict__ ms, const float* __restrict__ g,
-                                  int n, float lr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float gi = g[i];
-    const float s = 0.9f * ms[i] + 0.1f * gi * gi;
-    ms[i] = s;
-    theta[i] -= lr * gi / sqrtf(s + 1e-10f);
-}
-__global__ void vn_advance_kernel(long long* step, double* corr) {
-    const long long t = step[0] + 1;       // step just applied
-    step[0] = t;
-    const double tn = (double)(t + 1);     // bias correction of the NEXT step
-    corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
-}
+
 __global__ void vn_fill_kernel(float* p, float v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -308,6 +335,10 @@ struct vn_engine {
     // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> fedEvents;
+    // boundary/initial adjoint kernel runs concurrently with the variational one (fork/join, also inside the step graph)
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    DevBuf ticket;               // block counter of the fused finalize + optimizer kernel
     bool fused = false;          // per-test-function residual reduced inside the adjoint kernel (integNum | TP)
     cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
     cudaStream_t ownStream = nullptr;
@@ -406,6 +437,11 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     if (!e) return fail(VN_E_INVALID, "out of host memory");
     e->cfg = *cfg;
     if (cudaStreamCreate(&e->ownStream) == cudaSuccess) e->stream = e->ownStream;
+    if (cudaStreamCreateWithFlags(&e->auxStream, cudaStreamNonBlocking) != cudaSuccess) e->auxStream = nullptr;
+    if (e->auxStream && (cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming) != cudaSuccess)) {
+        cudaStreamDestroy(e->auxStream); e->auxStream = nullptr;
+    }
     e->slots.push_back(new PointSet());
     e->t = e->slots[0];
     build_net(*cfg, &e->net);
@@ -467,6 +503,8 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     CK(e->wts.ensure(4 * sizeof(float)));
     CK(e->stepbuf.ensure(sizeof(long long)));
     CK(e->corrbuf.ensure(sizeof(double)));
+    CK(e->ticket.ensure(sizeof(unsigned int)));
+    CK(cudaMemset(e->ticket.p, 0, sizeof(unsigned int)));
     CK(cudaMemset(e->theta.p, 0, np * sizeof(float)));
     CK(cudaMemset(e->gbuf.p, 0, (np + 4) * sizeof(float)));
     const float w1[4] = {1.f, 1.f, 1.f, 0.f};
@@ -483,12 +521,15 @@ extern "C" int vn_destroy(vn_engine* e) {
     drop_graph(e);
     if (e->ownStream) cudaStreamDestroy(e->ownStream);
     if (e->copyStream) cudaStreamDestroy(e->copyStream);
+    if (e->auxStream) cudaStreamDestroy(e->auxStream);
+    if (e->evFork) cudaEventDestroy(e->evFork);
+    if (e->evJoin) cudaEventDestroy(e->evJoin);
     for (cudaEvent_t ev : e->fedEvents) cudaEventDestroy(ev);
     for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -1002,7 +1043,7 @@ static int run_loss_tc(vn_engine* e, bool needGrad) {
     return VN_OK;
 }
 
-static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) {
+static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, float fuseLr = -1.f) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (!e->P || !e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
     if (!e->nbi) return fail(VN_E_STATE, "vn_upload_bic must be called first to construct training tables!");
@@ -1013,6 +1054,30 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) 
     cudaStream_t st = e->stream;
     if (e->wclass == 256) return run_loss_tc(e, needGrad);
     TileArgs a;
+    // boundary / initial rows: independent of the variational kernels until the final reduction, so they run on the
+    // auxiliary stream next to them (fork here, join before vn_finalize_kernel); sequential when profiling
+    auto launch_bic = [&](cudaStream_t bs) -> int {
+        TileArgs b;
+        bic_args(e, &b);
+        const int mode = needGrad ? MODE_BIC_ADJ : MODE_BIC_FWD;
+        const TileGeom& g = needGrad ? e->gBicAdj : e->gBicFwd;
+        b.ntiles = (int)(e->bstride / g.TP);
+        b.part = e->partBic.as<double>(); b.part32 = e->part32Bic.as<float>(); b.psz = g.pl.psz;
+        b.stash = e->stashBic.as<float>(); b.stashFloats = g.stashFloats;
+        const int grid = needGrad ? e->gridBic : std::min(b.ntiles, 2 * e->numSMs);
+        ProfScope ps(e, PK_BIC);
+        CK(vn_tile_launch(1, e->wclass, c.act, mode, b, grid, g.smemBytes, bs));
+        e->launches++;
+        return VN_OK;
+    };
+    const bool concurrentBic = !e->profOn && e->auxStream != nullptr;
+    if (concurrentBic) {
+        CK(cudaEventRecord(e->evFork, st));
+        CK(cudaStreamWaitEvent(e->auxStream, e->evFork, 0));
+        int rc = launch_bic(e->auxStream);
+        if (rc) return rc;
+        CK(cudaEventRecord(e->evJoin, e->auxStream));
+    }
     var_args(e, &a);
     int nSeg = (int)((e->nb + 255) / 256);
     const double* segPtr = e->segSum.as<double>();
@@ -1070,19 +1135,9 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) 
             e->launches++;
         }
     }
-    // 4. boundary / initial rows
-    bic_args(e, &a);
-    {
-        const int mode = needGrad ? MODE_BIC_ADJ : MODE_BIC_FWD;
-        const TileGeom& g = needGrad ? e->gBicAdj : e->gBicFwd;
-        a.ntiles = (int)(e->bstride / g.TP);
-        a.part = e->partBic.as<double>(); a.part32 = e->part32Bic.as<float>(); a.psz = g.pl.psz;
-        a.stash = e->stashBic.as<float>(); a.stashFloats = g.stashFloats;
-        const int grid = needGrad ? e->gridBic : std::min(a.ntiles, 2 * e->numSMs);
-        ProfScope ps(e, PK_BIC);
-        CK(vn_tile_launch(1, e->wclass, c.act, mode, a, grid, g.smemBytes, st));
-        e->launches++;
-    }
+    // 4. boundary / initial rows (already running on the auxiliary stream unless profiling)
+    if (concurrentBic) CK(cudaStreamWaitEvent(st, e->evJoin, 0));
+    else { int rc = launch_bic(st); if (rc) return rc; }
     // 5. deterministic cross-CTA reduction + loss scalars
     {
         FinalArgs f;
@@ -1094,6 +1149,11 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) 
         f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
+        if (needGrad && fuseLr >= 0.f) {        // vn_train_step on one GPU: optimizer update and step advance inside the reduction
+            f.fuseOpt = c.optimizer == VN_OPT_ADAM ? 1 : 2; f.lr = fuseLr;
+            f.theta = e->theta.as<float>(); f.m = e->m.as<float>(); f.v = e->v.as<float>();
+            f.step = e->stepbuf.as<long long>(); f.corr = e->corrbuf.as<double>(); f.ticket = e->ticket.as<unsigned int>();
+        }
         const int nb = needGrad ? (e->net.nparam + 3) / 4 : 0;          // one warp per parameter, 4 warps per block
         ProfScope ps(e, PK_FINAL);
         vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
@@ -1200,6 +1260,14 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
     if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
     CK(cudaSetDevice(e->cfg.device));
     const bool useGraph = e->graphOK && !e->profOn && e->stream != nullptr;
+    // resident-tile classes: the optimizer update is applied inside vn_finalize_kernel (one kernel less per step);
+    // the tensor-core class and profiling runs keep the separate optimizer kernels
+    const bool fuse = e->wclass != 256 && !e->profOn;
+    auto step_once = [&]() -> int {
+        int rc = run_loss(e, true, nullptr, fuse ? lr : -1.f);
+        if (!rc && !fuse) rc = vn_optimizer_step(e, lr);
+        return rc;
+    };
     PointSet* t = e->t;
     // a captured step stays valid while the table, the batch size / kind and lr are unchanged (the index list,
     // the extra inputs and the loss weights are read from device memory at replay time)
@@ -1218,8 +1286,7 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
         cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
         int rc = VN_OK;
         if (ce == cudaSuccess) {
-            rc = run_loss(e, true);
-            if (!rc) rc = vn_optimizer_step(e, lr);
+            rc = step_once();
             ce = cudaStreamEndCapture(e->stream, &g);
         }
         if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&t->graph, g, 0) != cudaSuccess) {
@@ -1227,9 +1294,7 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
             cudaGetLastError();
             t->graph = nullptr; e->graphOK = false;             // fall back to plain launches for this engine
             e->launches = l0;
-            rc = run_loss(e, true);
-            if (rc) return rc;
-            rc = vn_optimizer_step(e, lr);
+            rc = step_once();
             if (rc) return rc;
         } else {
             cudaGraphDestroy(g);
@@ -1238,9 +1303,7 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
             CK(cudaGraphLaunch(t->graph, e->stream));
         }
     } else {
-        int rc = run_loss(e, true);
-        if (rc) return rc;
-        rc = vn_optimizer_step(e, lr);
+        int rc = step_once();
         if (rc) return rc;
     }
     if (loss_out) {

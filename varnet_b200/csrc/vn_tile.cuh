@@ -867,5 +867,10 @@ struct FinalArgs {
     const float* wts;
     float* gbuf;                            // [nparam | loss, BCloss, ICloss, varLoss]
     int needGrad;
+    // optimizer fused into the reduction (single-GPU vn_train_step): 0 = none, 1 = Adam, 2 = RMSProp
+    int fuseOpt; float lr;
+    float* theta; float* m; float* v;
+    long long* step; double* corr;          // device step counter and Adam bias-correction factor (advanced by the last block)
+    unsigned int* ticket;                   // zero-initialised block counter
 };
 __global__ void vn_finalize_kernel(FinalArgs A);
