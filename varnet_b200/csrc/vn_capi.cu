@@ -456,8 +456,8 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         // tensor-core class: tcgen05 3xTF32 layer GEMMs, activations of a chunk streamed through global memory (vn_tc.h)
         e->wclass = 256;
         if (!vn_tc_geometry(e->net, e->S, e->numSMs, &e->tcGeom)) { delete e; return fail(VN_E_UNSUPPORTED, "no compiled kernel for this configuration"); }
-        if (e->tcGeom.smemGemm > prop.sharedMemPerBlockOptin || e->tcGeom.smemGw > prop.sharedMemPerBlockOptin) {
-            delete e; return fail(VN_E_UNSUPPORTED, "tensor-core class needs %zu B of shared memory per CTA", e->tcGeom.smemGemm);
+        if (e->tcGeom.smemGw > prop.sharedMemPerBlockOptin) {
+            const size_t need = e->tcGeom.smemGw; delete e; return fail(VN_E_UNSUPPORTED, "tensor-core class needs %zu B of shared memory per CTA", need);
         }
         cudaError_t ce = vn_tc_prepare(e->S, act);
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }

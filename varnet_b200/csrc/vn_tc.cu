@@ -1060,7 +1060,7 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
     if (const char* w = getenv("VARNET_B200_TC_WAVES")) waves = std::max(1, std::min(16, atoi(w)));
     g->capPts = (unsigned int)numSMs * TM * waves;
     g->workBytes = carve(nullptr, net.L, S, g->WP, g->capPts).bytes;
-    g->smemGemm = SMEM_BYTES;            // upper bound (the A-from-TMEM variant uses TS_SMEM_BYTES)
+    g->smemGemm = TS_SMEM_BYTES;         // layer GEMMs: A operand in tensor memory, weight tiles in shared memory (VARNET_B200_TC_TS=0: SMEM_BYTES)
     g->smemGw = SMEM_BYTES;
     return true;
 }
