@@ -1,6 +1,7 @@
-// vn_tc.cu — tensor-core kernel class (see vn_tc.h): tcgen05.mma kind::tf32 with the 3xTF32 split,
-// accumulators in TMEM, operands staged in shared memory in the no-swizzle K-major canonical layout
-// (8 rows x 16 bytes core matrices; validated by scripts/micro/tc_probe.cu).
+// vn_tc.cu — tensor-core kernel class (see vn_tc.h): tcgen05.mma kind::tf32 with the 3xTF32 split and accumulators
+// in TMEM.  Layer GEMMs: activation operand written to tensor memory by its loaders, weight tiles in shared memory;
+// weight-gradient GEMM: both operands in shared memory.  Shared-memory operands use the no-swizzle K-major
+// canonical layout (8 rows x 16 bytes core matrices; validated by scripts/micro/tc_probe.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -13,7 +14,7 @@ namespace {
 constexpr int TM = 128;         // rows (points, or input neurons in tc_gw) per CTA tile == TMEM lanes
 constexpr int TN = 128;         // columns (neurons) per CTA tile
 constexpr int NTHR = 256;        // loader / epilogue threads (8 warps)
-constexpr int NTHR_ALL = NTHR + 32;   // + one MMA-issuing warp
+constexpr int NTHR_ALL = NTHR + 32;   // + one MMA-issuing warp (tc_gw_kernel and the all-shared-memory GEMM variant)
 constexpr int KC = 32;           // K floats per pipeline stage (one 128-byte row segment per operand row)
 constexpr uint32_t TILE_SBO = 128;                  // bytes between 8-row groups
 // bytes between 16-byte K units: 128 rows x 16 B, plus one 16-byte pad so that the eight K units of one row
@@ -34,7 +35,7 @@ constexpr int TS_STAGE_BYTES = 2 * TILE_BYTES;       // B hi, B lo
 constexpr int TS_BAR_OFF = TS_NST * TS_STAGE_BYTES;
 constexpr int TS_SMEM_BYTES = TS_BAR_OFF + 128;
 constexpr uint32_t TS_ACOL = 3 * 128;
-constexpr uint32_t TMEM_COLS = 512;                  // four 128-column accumulator sets: three rotating main sets + the small terms
+constexpr uint32_t TMEM_COLS = 512;                  // 128-column accumulator sets (main sets + the small terms) [+ the A stages]
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

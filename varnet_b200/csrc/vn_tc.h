@@ -4,13 +4,14 @@
 // shared memory; at width 128/256 neither fits (one 256x256 layer is 256 KB).  At those widths the hidden
 // layers are real dense contractions (TFModel.py:208-242 Dense layers; 3.5 MFLOP per quadrature point for
 // 4x256), so this class runs them on the 5th-generation tensor cores and streams the activations of a chunk
-// of points through global memory (L2/HBM: ~150 flop/B, far above the ridge).  One chunk = ~2 waves of
-// 128-point tiles; per chunk and layer the step is
-//   forward   Z_s = A_{l-1,s} W_l             tc_gemm<EPI_FWD>   (epilogue: bias, act, act' * tangent)
-//   adjoint   abar_s = D_{l,s} W_l^T          tc_gemm<EPI_ADJ>   (epilogue: through act'/act'' of layer l-1)
-//   gradient  gW_l = sum_{s,p} A_{l-1,s}^T D_{l,s}   tc_gw       (split-K over points, FP64 atomics)
-// with FP32 accuracy from the 3xTF32 split x = hi + lo (hi*hi + lo*hi + hi*lo, FP32 accumulation in TMEM).
-// Layer 0 (K = inpDim <= 8), the output layer, the integrand / per-test-function residual and the bias
+// of points through global memory (L2/HBM: ~150 flop/B, far above the ridge) in one quad-major layout
+// [neuron/4][point][4].  One chunk = 8 waves of 128-point tiles; per chunk, layer and stream the step is
+//   forward   Z_s = A_{l-1,s} W_l             tc_gemm<FWD_VALUE | FWD_TANGENT>   (epilogue: bias, act, act' * tangent)
+//   adjoint   abar_s = D_{l,s} W_l^T          tc_gemm<ADJ_TANGENT | ADJ_VALUE>   (epilogue: through act'/act'' of layer l-1)
+//   gradient  gW_l = sum_{s,p} A_{l-1,s}^T D_{l,s}   tc_gw   (split-K over points, FP64 atomics; also g(b_l))
+// with FP32 accuracy from the 3xTF32 split x = hi + lo (lo*hi + hi*lo + hi*hi) and short accumulation chains
+// (the tensor core accumulates with truncation: several TMEM accumulator sets, summed in FP32 by the epilogue).
+// Layer 0 (K = inpDim <= 8), the output layer, the integrand / per-test-function residual and the layer-0
 // gradients are plain FP32 kernels.  Math: SURVEY.md App. A (TFModel.py:515-714).
 #pragma once
 #include "vn_tile.cuh"
@@ -20,7 +21,7 @@ enum { TC_VAR = 0, TC_BIC = 1, TC_EVAL = 2 };
 struct TcGeom {
     int WP;                 // padded hidden width (128 or 256)
     unsigned int capPts;    // chunk capacity in points (multiple of 128)
-    size_t workBytes;       // workspace for one chunk (activations in both layouts, adjoint ping-pong, staged weights)
+    size_t workBytes;       // workspace for one chunk (quad-major activations of every layer, adjoint ping-pong, staged weights)
     size_t smemGemm, smemGw;
 };
 
@@ -42,7 +43,7 @@ struct TcJob {
     long long launches;     // out: kernels launched
 };
 
-// theta -> zero-padded [WP][WP] copies of the hidden kernels (natural and transposed) inside the workspace
+// theta -> zero-padded quad-major copies of the hidden kernels (both orientations) inside the workspace
 cudaError_t vn_tc_stage_weights(const NetDesc& net, const TcGeom& g, const float* theta, void* work, cudaStream_t st);
 cudaError_t vn_tc_run(TcJob& j);
 // strong-form residual of the evaluation rows described by A (cols: X | kappa | vel | grad kappa | source; outputs A.uout, A.Iw)
