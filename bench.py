@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operator-configs", action="store_true", help="skip the steps/sec legs of configs 1-3")
+    ap.add_argument("--no-width-sweep", action="store_true", help="skip the short width-16/128/256 legs (BASELINE config 5)")
     return ap.parse_args()
 
 
@@ -236,6 +237,35 @@ def operator_config_steps(budget_s=4.0):
     return out
 
 
+def width_sweep(feed, meta, act, P_local, widths=(16, 128, 256), steps=2):
+    """BASELINE.json config 5 on the same mesh and feed: depth-4 tanh MLPs of other widths, a few steps each
+    (resident tables, CUDA events).  Widths above 64 run on the tensor-core class (tcgen05 3xTF32)."""
+    import torch
+    from varnet_b200 import workloads
+    from varnet_b200.backend import TFNN
+    out = {}
+    for wdt in widths:
+        lw = [wdt] * 4
+        tf = TFNN(meta["dim"], meta["inpDim"], lw, "MLP", act, True, None, ["GPU:0"], None, meta["lossOpt"], "adam", 1e-3, seed=0)
+        tw = tf.compTowers[0]
+        fd = {getattr(tw, k): feed[k] for k in ("Input", "gcoef", "source", "N", "dNt", "biInput", "biLabel", "bDof",
+                                                 "intShape", "integW", "biDimVal", "detJvec", "detJ", "w")}
+        tf.sess.run([tf.optMinimize, tf.loss], feed_dict=fd)                 # upload + warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            loss = tf.sess.run([tf.optMinimize, tf.loss], feed_dict=fd)[1]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        flop_pt = workloads.algorithmic_flops_per_point(meta["inpDim"], meta["dim"], lw)
+        out["mlp4x%d" % wdt] = dict(quad_pts_per_sec=P_local / (ms * 1e-3), ms_per_step=ms, algorithmic_tflops=flop_pt * P_local / (ms * 1e-3) / 1e12,
+                                    loss=float(loss), kernel_family=tw.engine.kernel_info().split()[0])
+        tf.sess.close()
+    return out
+
+
 def main():
     args = parse()
     nx, ny, ntime, lw, act = WORKLOADS[args.workload]
@@ -402,6 +432,11 @@ def main():
             r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                                         ms_per_step=r["ms_per_step"], feed_cast_ms_per_step=r["feed_cast_ms"])
+        if world == 1 and not args.no_width_sweep and args.workload == DEFAULT:
+            try:
+                line["width_sweep"] = width_sweep(feed, meta, act, P_local)
+            except Exception as ex:
+                line["width_sweep"] = dict(error=repr(ex))
         if world == 1 and not args.no_operator_configs and not args.no_cpu_baseline:
             try:
                 line["operator_configs"] = operator_config_steps()
