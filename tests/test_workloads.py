@@ -51,3 +51,33 @@ def test_algorithmic_flops_match_survey_table():
     assert workloads.algorithmic_flops_per_point(3, 2, [10, 20]) == 4500
     assert workloads.algorithmic_flops_per_point(3, 1, [10, 20, 30]) == 10320
     assert workloads.algorithmic_flops_per_point(3, 2, [64] * 4) == 225792
+
+
+def test_device_table_arguments_reproduce_the_host_table():
+    """workloads.generate_on_device hands vn_generate_table_f64 the mesh centres and the periodic FE tables; the formulas
+    that kernel evaluates (include/varnet_b200.h), restated here in NumPy float64, must give the float32 table that
+    shard_feed builds on the host, bit for bit (the GPU test checks the kernel itself against the uploaded table)."""
+    class Recorder:
+        def generate_table(self, coord, tcoord, hVec, delta, N, dN, diff, vel, source, tf0, nb, integNum, integW, detJ):
+            self.a = dict(coord=np.asarray(coord, float), tcoord=np.asarray(tcoord, float).ravel(), h=np.asarray(hVec, float).ravel(),
+                          delta=np.asarray(delta, float), N=np.asarray(N, float).ravel(), dN=np.asarray(dN, float),
+                          diff=diff, vel=np.asarray(vel, float), tf0=tf0, nb=nb, q=integNum, detJ=detJ, integW=integW)
+
+    for integPnum in (2, 3):
+        nx, ny, nti, n0, n1 = 5, 4, 3, 7, 41
+        rec = Recorder()
+        bic, meta = workloads.generate_on_device(rec, nx, ny, nti, n0, n1, integPnum=integPnum)
+        a = rec.a
+        feed, meta2 = workloads.shard_feed(nx, ny, nti, n0, n1, integPnum=integPnum, dtype=np.float32)
+        assert meta == meta2 and a["nb"] == n1 - n0 and a["q"] == meta["integNum"]
+        i = a["tf0"] + np.arange(a["nb"])
+        s, j = i // nti, i % nti
+        q = a["q"]
+        dN = a["dN"].reshape(q, 3)
+        X = np.stack([(a["coord"][s, d][:, None] + a["h"][d] * a["delta"][d][None, :]).reshape(-1) for d in range(2)] +
+                     [(a["tcoord"][j][:, None] + a["h"][2] * a["delta"][2][None, :]).reshape(-1)], axis=1).astype(np.float32)
+        G = np.tile(np.stack([a["diff"] * dN[:, k] + a["vel"][k] * a["N"] for k in range(2)], axis=1), [a["nb"], 1]).astype(np.float32)
+        T = np.tile(dN[:, 2:3], [a["nb"], 1]).astype(np.float32)
+        assert np.array_equal(X, feed["Input"]) and np.array_equal(G, feed["gcoef"]) and np.array_equal(T, feed["dNt"])
+        assert a["detJ"] == feed["detJ"] and np.array_equal(bic["biInput"].astype(np.float32), feed["biInput"])
+        assert bic["bDof"] == feed["bDof"] and bic["intShape"] == feed["intShape"]
