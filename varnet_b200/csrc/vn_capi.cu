@@ -13,6 +13,7 @@
 #include "../../include/varnet_b200.h"
 #include "vn_dispatch.h"
 #include "vn_tc.h"
+#include "vn_tc64.h"
 #include <utility>
 
 // ------------------------------------------------------------------ errors
@@ -181,6 +182,7 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             for (int p = 0; p < nslot; ++p) s += __ldcg(A.partBic + (size_t)c * pl.psz + slot[p]);
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
+            if (A.flat) s += A.flat[idx];
             const float g = (float)s;
             A.gbuf[idx] = g;
             // single-GPU training step: apply_gradients fused into the reduction (TFModel.py:313)
@@ -332,6 +334,11 @@ struct vn_engine {
     // tensor-core class (wclass == 256): chunk workspace, FP64 gradient accumulator [nparam | loss sum], barrier-timeout flag
     TcGeom tcGeom{};
     DevBuf tcWork, tcAcc, tcErr;
+    // width-64 tensor-core tile kernel (vn_tc64.h) for the variational term of the 64-wide FMA class
+    bool tc64 = false;           // network and build allow it
+    bool useTc64 = false;        // ... and the current batch does (integNum | 128)
+    Tc64Geom tc64Geom{};
+    DevBuf tc64Img, tc64Flat;
     // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> fedEvents;
@@ -495,6 +502,20 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         if (ce != cudaSuccess) { delete e; return fail(VN_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); }
     }
     }
+    {
+        // 64-wide class: the variational term runs on the tensor-core tile kernel unless VARNET_B200_CLASS=fma
+        const bool wantTc64 = !(forceCls && !strcmp(forceCls, "fma"));
+        if (e->wclass == 64 && wantTc64 && vn_tc64_supported(e->net, e->S)) {
+            vn_tc64_geometry(e->net, e->S, &e->tc64Geom);
+            if (e->tc64Geom.smemBytes <= prop.sharedMemPerBlockOptin && vn_tc64_prepare(e->S, act, e->tc64Geom.smemBytes) == cudaSuccess) {
+                e->tc64 = true;
+                CK(e->tc64Img.ensure((size_t)e->tc64Geom.nImages * 8192 * sizeof(float)));
+                CK(e->tc64Flat.ensure((size_t)e->net.nparam * sizeof(double)));
+                CK(e->tcErr.ensure(sizeof(int)));
+                CK(cudaMemset(e->tcErr.p, 0, sizeof(int)));
+            }
+        }
+    }
     const int np = e->net.nparam;
     CK(e->theta.ensure(np * sizeof(float)));
     CK(e->m.ensure(np * sizeof(float)));
@@ -529,7 +550,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -622,6 +643,17 @@ static int ensure_work(vn_engine* e) {
     const int nSeg = (int)((e->nb + 255) / 256);
     CK(e->segSum.ensure((size_t)std::max(nSeg, 1) * sizeof(double)));
     if (e->wclass == 256) { e->fused = false; e->gridVar = 0; return VN_OK; }     // tensor-core class: chunk workspace is fixed at creation
+    e->useTc64 = e->tc64 && t->integNum > 0 && (128 % t->integNum) == 0;
+    if (e->useTc64) {
+        const long long tiles = (P + 127) / 128;
+        e->gridVar = (int)std::max<long long>(1, std::min<long long>(tiles, e->numSMs));
+        CK(e->partVar.ensure((size_t)e->numSMs * e->tc64Geom.psz * sizeof(double)));
+        CK(e->part32Var.ensure((size_t)e->numSMs * e->tc64Geom.psz * sizeof(float)));
+        CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->numSMs * e->tc64Geom.stashFloats * sizeof(float))));
+        CK(e->lossPart.ensure((size_t)e->numSMs * 8 * sizeof(double)));
+        e->fused = true;
+        return VN_OK;
+    }
     const long long tilesAdj = (P + e->gVarAdj.TP - 1) / e->gVarAdj.TP;
     e->gridVar = (int)std::max<long long>(1, std::min<long long>(tilesAdj, e->numSMs));
     CK(e->partVar.ensure((size_t)e->numSMs * e->gVarAdj.pl.psz * sizeof(double)));
@@ -693,7 +725,7 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
         if (t->pstride > P)
             for (int cc = 0; cc < t->ncols; ++cc)
                 CK(cudaMemsetAsync(t->cols.as<float>() + (size_t)cc * t->pstride + P, 0, (size_t)(t->pstride - P) * sizeof(float), us));
-        const int TP = e->gVarAdj.TP;
+        const int TP = (e->tc64 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
         size_t k = 0;
         for (long long off = 0; off < P; off += chunk, ++k) {
             const long long n = std::min(chunk, P - off);
@@ -1088,18 +1120,35 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
+        const bool tc = e->useTc64;
+        if (tc) {
+            a.ntiles = (int)(((long long)e->P + 127) / 128);
+            a.psz = e->tc64Geom.psz; a.stashFloats = e->tc64Geom.stashFloats;
+            CK(vn_tc64_stage_weights(e->net, e->theta.as<float>(), e->tc64Img.as<float>(), st));
+            e->launches++;
+        }
+        auto launch_var = [&]() -> cudaError_t {
+            if (tc) return vn_tc64_launch(e->S, c.act, a, e->tc64Img.as<float>(), e->tcErr.as<int>(), e->gridVar, e->tc64Geom.smemBytes, st);
+            return vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st);
+        };
+        {
         ProfScope ps(e, PK_VAR_ADJ);
         if (plan) {
             // one launch per uploaded chunk, each waiting for its own pack kernel on the copy stream
             for (size_t k = 0; k < plan->subs.size(); ++k) {
                 CK(cudaStreamWaitEvent(st, plan->subs[k].ev, 0));
                 a.tile0 = plan->subs[k].tile0; a.ntiles = plan->subs[k].ntiles; a.accumulate = k > 0 ? 1 : 0;
-                CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
+                CK(launch_var());
                 e->launches++;
             }
             a.tile0 = 0; a.accumulate = 0;
         } else {
-            CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st));
+            CK(launch_var());
+            e->launches++;
+        }
+        }
+        if (tc) {
+            CK(vn_tc64_reduce(e->net, e->partVar.as<double>(), e->tc64Geom.psz, e->gridVar, e->tc64Flat.as<double>(), st));
             e->launches++;
         }
         nSeg = e->gridVar * (g.NT / 32);
@@ -1144,6 +1193,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         memset(&f, 0, sizeof(f));
         f.net = e->net; f.pl = e->gVarAdj.pl;
         f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
+        if (needGrad && e->fused && e->useTc64) { f.nVar = 0; f.flat = e->tc64Flat.as<double>(); }
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
         f.segSum = segPtr; f.nSeg = nSeg;
         f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
@@ -1166,7 +1216,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
 static int read_scalars(vn_engine* e, float out[4]) {
     CK(cudaMemcpyAsync(out, e->gbuf.as<float>() + e->net.nparam, 4 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     int tcErr = 0;
-    if (e->wclass == 256) CK(cudaMemcpyAsync(&tcErr, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (e->wclass == 256 || e->tc64) CK(cudaMemcpyAsync(&tcErr, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (tcErr) {
         cudaMemsetAsync(e->tcErr.p, 0, sizeof(int), e->stream);       // report once; the next call starts clean
@@ -1198,8 +1248,9 @@ static int loss_grad_fed(vn_engine* e, const T* X, const T* G, const T* src, con
     if (!e) return fail(VN_E_INVALID, "null engine");
     e->nExtra = 0;
     const long long P = (long long)nb * integNum;
-    const bool overlap = e->wclass != 256 && e->nbi > 0 && P > kChunk && integNum > 0 && (e->gVarAdj.TP % integNum) == 0 &&
-                         kChunk % e->gVarAdj.TP == 0 && kChunk / e->gVarAdj.TP >= e->numSMs && !e->profOn;
+    const int fedTP = (e->tc64 && integNum > 0 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
+    const bool overlap = e->wclass != 256 && e->nbi > 0 && P > kChunk && integNum > 0 && (fedTP % integNum) == 0 &&
+                         kChunk % fedTP == 0 && kChunk / fedTP >= e->numSMs && !e->profOn;
     if (!overlap) {
         int rc = upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec);
         if (rc) return rc;
@@ -1437,6 +1488,13 @@ extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
         snprintf(buf, n, "family=tcgen05-3xtf32 class=256 S=%d L=%d WP=%d chunk=%u points gemm(tile=128x128,smem=%zu) gw(smem=%zu) "
                  "workspace=%zuB nparam=%d SMs=%d", e->S, e->net.L, e->tcGeom.WP, e->tcGeom.capPts, e->tcGeom.smemGemm,
                  e->tcGeom.smemGw, e->tcGeom.workBytes, e->net.nparam, e->numSMs);
+        return VN_OK;
+    }
+    if (e->useTc64) {
+        snprintf(buf, n, "family=tcgen05-3xtf32-tile64 class=64 S=%d L=%d var_adj(TP=128,NT=256,smem=%zu,grid=%d,fused-R single pass,"
+                 "stash=%lldB/CTA,A-from-TMEM) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+                 e->S, e->net.L, e->tc64Geom.smemBytes, e->gridVar, (long long)(e->tc64Geom.stashFloats * 4), e->gBicAdj.TP,
+                 e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
         return VN_OK;
     }
     snprintf(buf, n,

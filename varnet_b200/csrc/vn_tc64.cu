@@ -1,0 +1,683 @@
+// vn_tc64.cu — resident-tile tensor-core kernel for hidden widths 33..64 (see vn_tc64.h).
+//
+// Tensor memory map (512 columns x 128 lanes, lane = quadrature point of the tile):
+//   region s = [128 s, 128 s + 128), s < S <= 3 : operand of stream s, hi TF32 half in columns +0..63, lo half in +64..127
+//                                                 (forward: a_{l,s}; adjoint: zbar_{l,s}); between two adjoint layers its
+//                                                 first 64 columns park abar_{l-1,s} (the drained layer-GEMM result)
+//   work     = [384, 512)                        : accumulators of the running GEMM: hi*hi in +0..63 (a chain of 8 MMAs),
+//                                                 hi*lo + lo*hi in +64..127; the weight-gradient GEMM uses all 128 columns
+// The tensor core accumulates with truncation (vn_tc.cu): chains of hi*hi products are kept at <= 16 MMAs and the
+// 2^-11-sized cross products go to their own columns; the sets are summed in FP32 round-to-nearest by the drain.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vn_tc64.h"
+
+namespace {
+
+constexpr int TP = 128;            // points per tile == TMEM lanes
+constexpr int W = 64;              // padded hidden width
+constexpr int NT = 256;            // threads: warp w -> lane quarter w & 3, neuron half w >> 2
+constexpr int FOLD = 16;           // tiles accumulated in the FP32 window slab before the FP64 fold
+constexpr uint32_t SBO = 128;      // bytes between 8-row groups of a canonical K-major operand
+constexpr uint32_t W_LBO = 2048;   // weight images: 128 rows x 16 B per 4-wide K unit
+constexpr uint32_t G_LBO = 2064;   // weight-gradient operands (K = points): + 16 B pad, transposing stores hit 32 banks
+constexpr int WIMG_FLOATS = 8192, WIMG_BYTES = 32768;
+constexpr int G_BYTES = 32 * G_LBO;
+constexpr int OFF_WST = 0;                         // two weight stages
+constexpr int OFF_GA = 2 * WIMG_BYTES;             // [a_hi^T ; a_lo^T]     128 rows x 128 points
+constexpr int OFF_GB = OFF_GA + G_BYTES;           // [zbar_hi^T ; zbar_lo^T]
+constexpr int OFF_PAR = OFF_GB + G_BYTES;
+constexpr int PAR_FLOATS = 2560;                   // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[2][3][128] | us[3][128] | I[128] | R[128]
+constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t COL_WORK = 384;
+
+struct Tc64Args { TileArgs t; const float* wimg; int* err; };
+
+struct SlabLayout { int vecOff, boutOff, psz, nkind; };
+__host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
+    SlabLayout s;
+    s.vecOff = (L - 1) * (TP * W);                 // gw blocks of layers 1..L-1: [128 rows][64]
+    s.nkind = L + 1 + inpDim;                      // gb_0..gb_{L-1} | g(w_out) | gW_0 rows
+    s.boutOff = s.vecOff + s.nkind * 4 * W;        // vec slots: [kind][lane quarter][64]
+    s.psz = s.boutOff + 4;
+    return s;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((SBO >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;                                      // no swizzle
+}
+// D = F32, A = B = TF32, K-major, M = 128
+template <int N> struct IDesc { static constexpr uint32_t v = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t aT, uint64_t db, uint32_t id, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(aT), "l"(db), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(da), "l"(db), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {      // bounded: a lost commit must not hang the GPU
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 20) && !done; ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// ------------------------------------------------------------------ per-thread operand movement (thread = point p x neurons c0..c0+31)
+// hi/lo split of v -> the thread's columns of operand region `reg` (address of the lane quarter, column 128 s)
+__device__ __forceinline__ void put_operand(uint32_t reg, int c0, const float (&v)[32]) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { hi[i] = tf32_rn(v[16 * hf + i]); lo[i] = v[16 * hf + i] - hi[i]; }
+        tmem_st16(reg + c0 + 16 * hf, hi);
+        tmem_st16(reg + 64 + c0 + 16 * hf, lo);
+    }
+}
+// hi + lo == the FP32 value exactly
+__device__ __forceinline__ void get_operand(uint32_t reg, int c0, float (&v)[32]) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float hi[16], lo[16];
+        tmem_ld16(reg + c0 + 16 * hf, hi);
+        tmem_ld16(reg + 64 + c0 + 16 * hf, lo);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * hf + i] = hi[i] + lo[i];
+    }
+}
+__device__ __forceinline__ void put_plain(uint32_t taddr, const float (&v)[32]) {
+    float t[16];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = v[16 * hf + i];
+        tmem_st16(taddr + 16 * hf, t);
+    }
+}
+__device__ __forceinline__ void get_plain(uint32_t taddr, float (&v)[32]) {
+    float t0[16], t1[16];
+    tmem_ld16(taddr, t0);
+    tmem_ld16(taddr + 16, t1);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
+}
+// work accumulators -> z = (hi*hi) + (hi*lo + lo*hi) for the thread's 32 columns
+__device__ __forceinline__ void drain_sum(uint32_t work, int c0, float (&z)[32]) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float m[16], s[16];
+        tmem_ld16(work + c0 + 16 * hf, m);
+        tmem_ld16(work + 64 + c0 + 16 * hf, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[16 * hf + i] = m[i] + s[i];
+    }
+}
+// transposing store: rows = neurons (hi rows 0..63, lo rows 64..127), K = points; a warp's 32 points of one neuron
+// fall into 32 different banks (G_LBO = 2048 + 16)
+__device__ __forceinline__ void put_transposed(unsigned char* G, int p, int c0, const float (&v)[32]) {
+    unsigned char* base = G + (p >> 2) * G_LBO + (p & 3) * 4;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+        const int j = c0 + jj;
+        const float hi = tf32_rn(v[jj]);
+        *reinterpret_cast<float*>(base + (j >> 3) * SBO + (j & 7) * 16) = hi;
+        *reinterpret_cast<float*>(base + (8 + (j >> 3)) * SBO + (j & 7) * 16) = v[jj] - hi;
+    }
+}
+// stash: [(l*S + s)][neuron/4][point][4]
+__device__ __forceinline__ void stash_put(float* st, int slab, int p, int c0, const float (&v)[32]) {
+    float4* b = reinterpret_cast<float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) __stcg(b + u * TP, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+}
+__device__ __forceinline__ void stash_get(const float* st, int slab, int p, int c0, float (&v)[32]) {
+    const float4* b = reinterpret_cast<const float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float4 t = __ldcg(b + u * TP);
+        v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+    }
+}
+// sum over the 32 lanes of v[c]: lane c returns column c  (31 shuffles)
+__device__ __forceinline__ float warp_colsum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int S, int ACT>
+__global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__ Tc64Args K) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TileArgs& A = K.t;
+    const NetDesc& net = A.net;
+    const int L = net.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & 3, h = warp >> 2;
+    const int p = 32 * q + lane;                    // point of the tile == TMEM lane
+    const int c0 = 32 * h;                          // first of this thread's 32 neurons
+
+    float* par = reinterpret_cast<float*>(smem + OFF_PAR);
+    float* W0s = par;                               // [8][64]
+    float* bs = par + 512;                          // [8][64]
+    float* wout = par + 1024;                       // [64]
+    float* misc = par + 1088;                       // [0] = b_out
+    float* usP = par + 1152;                        // [2][3][128] output-layer partial dots of the two neuron halves
+    float* us = usP + 768;                          // [3][128] u_s, then the adjoint seeds
+    float* Ish = us + 384;                          // [128]
+    float* Rsh = Ish + 128;                         // [128]
+    const uint32_t bar = smem_u32(smem + OFF_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8);
+    unsigned char* GA = smem + OFF_GA;
+    unsigned char* GB = smem + OFF_GB;
+
+    if (*reinterpret_cast<volatile int*>(K.err)) return;
+    for (int i = tid; i < PAR_FLOATS; i += NT) par[i] = 0.f;
+    __syncthreads();
+    {
+        const float* __restrict__ th = A.theta;
+        const int w0 = net.width[0];
+        for (int idx = tid; idx < net.inpDim * w0; idx += NT) { const int c = idx / w0, j = idx - c * w0; W0s[c * W + j] = th[net.woff[0] + idx]; }
+        for (int l = 0; l < L; ++l)
+            for (int j = tid; j < net.width[l]; j += NT) bs[l * W + j] = th[net.boff[l] + j];
+        for (int j = tid; j < net.width[L - 1]; j += NT) wout[j] = th[net.woff[L] + j];
+        if (tid == 0) {
+            misc[0] = th[net.boff[L]];
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tslot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);           // this warp's lane quarter
+    const uint32_t work = tq + COL_WORK;
+
+    const SlabLayout sl = slab_layout(L, net.inpDim);
+    float* part = A.part32 + (size_t)blockIdx.x * sl.psz;
+    double* part64 = A.part + (size_t)blockIdx.x * sl.psz;
+    float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
+    const int nImg = 2 * (L - 1);
+    uint32_t phase = 0;
+    bool ok = true;
+    int imgNext = 0;                                 // next weight image of the tile sequence to be consumed
+    double lossAcc = 0.0;
+    bool first = true, firstFold = !A.accumulate;
+    int win = 0;
+
+    // weight image n of the per-tile sequence: forward layers 1..L-1, then adjoint layers L-1..1
+    auto image_of = [&](int n) { return n < L - 1 ? 2 * n : 2 * (2 * L - 3 - n) + 1; };
+    auto prefetch_image = [&](int n) {
+        const float* src = K.wimg + (size_t)image_of(n) * WIMG_FLOATS;
+        float* dst = reinterpret_cast<float*>(smem + OFF_WST + (n & 1) * WIMG_BYTES);
+#pragma unroll
+        for (int i = 0; i < WIMG_BYTES / 16 / NT; ++i) cp_async16(dst + 4 * (i * NT + tid), src + 4 * (i * NT + tid));
+        cp_async_commit();
+    };
+    // the image of this step is complete (issued one step earlier); put the next one in flight into the other stage,
+    // whose last readers (the MMAs of the previous step) have completed
+    auto acquire_image = [&]() -> uint32_t {
+        cp_async_wait_all();
+        fence_async_smem();
+        const int n = imgNext;
+        imgNext = (n + 1 == nImg) ? 0 : n + 1;
+        prefetch_image(imgNext);
+        return smem_u32(smem + OFF_WST + (n & 1) * WIMG_BYTES);
+    };
+    // publish this thread's TMEM / shared-memory writes and finished TMEM reads, then let thread 0 issue
+    auto sync_for_issue = [&]() {
+        tmem_wait_st();
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        if (ok) ok = mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+    };
+    // layer GEMM of stream s: work = A_s [128 x 64] x [W_hi | W_lo]^T, then small += A_s,lo x W_hi
+    auto issue_layer = [&](int s, uint32_t wst) {
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t aHi = tmem + 128 * s, aLo = aHi + 64, d = tmem + COL_WORK;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) {
+                const uint64_t db = make_desc(wst + kb * 2 * W_LBO, W_LBO);
+                mma_ts(d, aHi + kb * 8, db, IDesc<128>::v, kb ? 1u : 0u);
+                mma_ts(d + 64, aLo + kb * 8, db, IDesc<64>::v, 1u);
+            }
+            mma_commit(bar);
+        }
+    };
+    auto issue_gw = [&]() {
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb)
+                mma_ss(tmem + COL_WORK, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
+            mma_commit(bar);
+        }
+    };
+    // this warp's sum over its 32 points of column c0+lane -> the warp's vec slot of `kind`
+    auto vec_add = [&](int kind, float v) {
+        float* slot = part + sl.vecOff + (kind * 4 + q) * W + c0 + lane;
+        if (first) __stcg(slot, v); else atomicAdd(slot, v);
+    };
+
+    prefetch_image(0);
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
+        const unsigned int gp = base + p;
+        const bool valid = gp < A.P;
+        const size_t row = valid ? table_row(A, gp) : 0;
+
+        // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
+        float x[VN_KIN];
+#pragma unroll
+        for (int c = 0; c < VN_KIN; ++c) {
+            x[c] = 0.f;
+            if (c < net.inpDim) {
+                if (c >= A.nxTable) x[c] = __ldg(A.extraX + (c - A.nxTable));
+                else if (!A.tfIndex) x[c] = __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + gp);       // zero padded table
+                else if (valid) x[c] = __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row);
+            }
+        }
+        float d1[32];                                // act'(z_l) of the value stream, kept for the tangent streams
+        {
+            float v[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                float z = bs[c0 + jj];
+#pragma unroll
+                for (int c = 0; c < VN_KIN; ++c)
+                    if (c < net.inpDim) z = fmaf(x[c], W0s[c * W + c0 + jj], z);
+                v[jj] = act_f<ACT>(z);
+                d1[jj] = act_d1<ACT>(v[jj]);
+            }
+            put_operand(tq, c0, v);
+            stash_put(stash, 0, p, c0, v);
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
+                put_operand(tq + 128 * (1 + k), c0, v);
+                stash_put(stash, 1 + k, p, c0, v);
+            }
+        }
+
+        // ---- hidden layers, forward
+        for (int l = 1; l < L; ++l) {
+            const uint32_t wst = acquire_image();
+            const bool last = (l == L - 1);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                sync_for_issue();
+                issue_layer(s, wst);
+                wait_mma();
+                float v[32];
+                drain_sum(work, c0, v);
+                if (s == 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        v[jj] = act_f<ACT>(v[jj] + bs[l * W + c0 + jj]);
+                        d1[jj] = act_d1<ACT>(v[jj]);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] *= d1[jj];
+                }
+                put_operand(tq + 128 * s, c0, v);
+                if (!last) stash_put(stash, l * S + s, p, c0, v);
+                else {
+                    // output layer (Dense(1)): partial dot over this thread's neurons
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 2) { a0 = fmaf(v[jj], wout[c0 + jj], a0); a1 = fmaf(v[jj + 1], wout[c0 + jj + 1], a1); }
+                    usP[(h * 3 + s) * TP + p] = a0 + a1;
+                }
+            }
+        }
+        tmem_wait_st();
+        __syncthreads();
+
+        // ---- u_s, integrand, R_i of the test functions of this tile, loss, adjoint seeds (TFModel.py:653-664)
+        if (tid < TP) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                float u = usP[s * TP + p] + usP[(3 + s) * TP + p];
+                if (s == 0) u += misc[0];
+                us[s * TP + p] = u;
+            }
+            float I = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
+                if (A.timeDependent) I -= us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
+                if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+                if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+            }
+            Ish[p] = I;
+        }
+        __syncthreads();
+        {
+            const int nf = TP / (int)A.integNum;
+            for (int f = warp; f < nf; f += NT / 32) {
+                float r = 0.f;
+                for (int qq = lane; qq < (int)A.integNum; qq += 32) r += Ish[f * A.integNum + qq];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == 0) {
+                    const unsigned int i = base / A.integNum + f;
+                    Rsh[f] = r;
+                    if (i * A.integNum < A.P) {
+                        const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
+                        const float r2 = r * r;
+                        A.R[i] = r;
+                        A.lossVec[i] = dj * r2;
+                        lossAcc += A.detJvec ? (double)dj * (double)r2 : (double)r2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < TP) {
+            float lam = 0.f;
+            if (valid) {
+                const unsigned int i = gp / A.integNum, qq = gp - i * A.integNum;
+                const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
+                const float wq = A.integW ? __ldg(A.integW + qq) : 1.f;
+                lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
+            }
+            us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + row) : 0.f;
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
+        }
+        __syncthreads();
+
+        // ---- adjoint sweep: layer l turns abar_{l,s} into zbar_{l,s} (tangent streams first: the value stream needs
+        // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
+        if (h == 0) {                                                   // g(b_out) = sum_p ubar_0
+            float sb = us[p];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            if (lane == 0) { float* slot = part + sl.boutOff + q; if (first) __stcg(slot, sb); else atomicAdd(slot, sb); }
+        }
+        for (int l = L - 1; l >= 0; --l) {
+            const bool top = (l == L - 1);
+            uint32_t wst = 0;
+            if (l >= 1) wst = acquire_image();
+            float a0[32], cross[32], gwo[32], zb0[S][32];
+            if (top) get_operand(tq, c0, a0); else stash_get(stash, l * S, p, c0, a0);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) { cross[jj] = 0.f; gwo[jj] = 0.f; }
+#pragma unroll
+            for (int si = 0; si < S; ++si) {
+                const int s = (si < S - 1) ? si + 1 : 0;
+                float v[32];
+                if (top) {
+                    const float ub = us[s * TP + p];
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = ub * wout[c0 + jj];
+                } else {
+                    get_plain(tq + 128 * s + c0, v);
+                }
+                if (s > 0) {
+                    float da[32];
+                    if (top) get_operand(tq + 128 * s, c0, da); else stash_get(stash, l * S + s, p, c0, da);
+                    if (top) {
+                        const float ub = us[s * TP + p];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(da[jj], ub, gwo[jj]);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        cross[jj] = fmaf(v[jj], da[jj], cross[jj]);
+                        v[jj] *= act_d1<ACT>(a0[jj]);
+                    }
+                } else {
+                    if (top) {
+                        const float ub = us[p];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(a0[jj], ub, gwo[jj]);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
+                }
+                if (l >= 1) {
+                    put_operand(tq + 128 * s, c0, v);
+                    put_transposed(GB, p, c0, v);
+                    {
+                        float ap[32];
+                        stash_get(stash, (l - 1) * S + s, p, c0, ap);
+                        put_transposed(GA, p, c0, ap);
+                    }
+                    if (s == 0) { const float r = warp_colsum(v, lane); vec_add(l, r); }          // g(b_l) = sum_p zbar_{l,0}
+                    sync_for_issue();
+                    issue_layer(s, wst);
+                    wait_mma();
+                    {
+                        float t[32];
+                        drain_sum(work, c0, t);
+                        put_plain(tq + 128 * s + c0, t);                  // park abar_{l-1,s} in the (now dead) operand region
+                    }
+                    sync_for_issue();
+                    issue_gw();
+                    wait_mma();
+                    {
+                        // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
+                        float g[32];
+                        if (q < 2) drain_sum(work, c0, g); else get_plain(work + c0, g);
+                        float* slot = part + (size_t)(l - 1) * (TP * W) + p * W + c0;
+                        if (first && si == 0) {                            // first write of this window: overwrite
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) zb0[s][jj] = v[jj];
+                }
+            }
+            if (top) { const float r = warp_colsum(gwo, lane); vec_add(L, r); }                  // g(w_out)
+            if (l == 0) {
+                // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
+                {
+                    float t[32];
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) t[jj] = zb0[0][jj];
+                    const float r = warp_colsum(t, lane);
+                    vec_add(0, r);
+                }
+#pragma unroll
+                for (int c = 0; c < VN_KIN; ++c) {
+                    if (c < net.inpDim) {
+                        float t[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            t[jj] = x[c] * zb0[0][jj];
+                            if (c < S - 1) t[jj] += zb0[(c + 1 < S) ? c + 1 : 0][jj];
+                        }
+                        const float r = warp_colsum(t, lane);
+                        vec_add(L + 1 + c, r);
+                    }
+                }
+            }
+        }
+        // the next tile's first MMA overwrites `work` and its layer-0 epilogue the operand regions: both are idle
+        // (every MMA has been waited for, every drain completed before the last sync_for_issue or is thread-local)
+        tmem_wait_ld();
+
+        first = false;
+        if (++win == FOLD || tile + (int)gridDim.x >= A.ntiles) {
+            // fold this thread's slots of the FP32 window into the FP64 slab (single writer per slot)
+            auto put = [&](int idx) {
+                const double v = (double)__ldcg(part + idx);
+                if (firstFold) __stcg(part64 + idx, v); else part64[idx] += v;
+            };
+            for (int l = 1; l < L; ++l)
+                for (int jj = 0; jj < 32; ++jj) put((l - 1) * (TP * W) + p * W + c0 + jj);
+            for (int k = 0; k < sl.nkind; ++k) put(sl.vecOff + (k * 4 + q) * W + c0 + lane);
+            if (h == 0 && lane == 0) put(sl.boutOff + q);
+            firstFold = false; first = true; win = 0;
+        }
+    }
+    cp_async_wait_all();
+    if (lane == 0) {
+        double* lp = A.lossPart + blockIdx.x * (NT / 32) + warp;
+        *lp = A.accumulate ? *lp + lossAcc : lossAcc;
+    }
+    if (!ok) *K.err = 1;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ------------------------------------------------------------------ weight images
+// image 2(l-1)   (forward, B rows n = output neuron, K = input):  n < 64: hi(W_l[k][n]),  n >= 64: lo(W_l[k][n-64])
+// image 2(l-1)+1 (adjoint, B rows n = input neuron,  K = output): n < 64: hi(W_l[n][k]),  n >= 64: lo(W_l[n-64][k])
+__global__ void tc64_prep_kernel(NetDesc net, const float* __restrict__ theta, float* __restrict__ wimg) {
+    const int img = blockIdx.y, l = 1 + (img >> 1), dir = img & 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (n, k)
+    if (e >= 128 * 64) return;
+    const int n = e >> 6, k = e & 63, nn = n & 63;
+    const int wi = net.width[l - 1], wo = net.width[l];
+    const int i = dir ? nn : k, j = dir ? k : nn;
+    const float w = (i < wi && j < wo) ? theta[net.woff[l] + i * wo + j] : 0.f;
+    const float hi = tf32_rn(w);
+    wimg[(size_t)img * WIMG_FLOATS + ((k >> 2) * W_LBO + (n >> 3) * SBO + (n & 7) * 16 + (k & 3) * 4) / 4] = n < 64 ? hi : w - hi;
+}
+
+// ------------------------------------------------------------------ cross-CTA reduction (fixed order)
+__global__ void tc64_reduce_kernel(NetDesc net, const double* __restrict__ slab, int psz, int nCta, double* __restrict__ flat) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= net.nparam) return;
+    const SlabLayout sl = slab_layout(net.L, net.inpDim);
+    int l = 0, isBias = 0, i = 0, j = 0;
+    for (l = 0; l <= net.L; ++l) {
+        const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+        const int wo = l == net.L ? 1 : net.width[l];
+        if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { i = (idx - net.woff[l]) / wo; j = (idx - net.woff[l]) - i * wo; break; }
+        if (idx >= net.boff[l] && idx < net.boff[l] + wo) { isBias = 1; j = idx - net.boff[l]; break; }
+    }
+    int slot[4], nslot = 4;
+    if (l == net.L && isBias) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.boutOff + qq; }
+    else if (l == net.L) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + (net.L * 4 + qq) * W + i; }
+    else if (isBias) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + (l * 4 + qq) * W + j; }
+    else if (l == 0) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + ((net.L + 1 + i) * 4 + qq) * W + j; }
+    else { nslot = 2; slot[0] = (l - 1) * (TP * W) + i * W + j; slot[1] = (l - 1) * (TP * W) + (64 + i) * W + j; }
+    double s = 0.0;
+    for (int c = lane; c < nCta; c += 32)
+        for (int k = 0; k < nslot; ++k) s += __ldcg(slab + (size_t)c * psz + slot[k]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) flat[idx] = s;
+}
+
+template <int S, int ACT> cudaError_t launch_t(const Tc64Args& k, int grid, size_t smem, cudaStream_t st) {
+    tc64_var_kernel<S, ACT><<<grid, NT, smem, st>>>(k);
+    return cudaGetLastError();
+}
+template <int S, int ACT> cudaError_t prepare_t(size_t smem) {
+    return cudaFuncSetAttribute(tc64_var_kernel<S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+}  // namespace
+
+bool vn_tc64_supported(const NetDesc& net, int S) {
+    if (S < 2 || S > 3 || net.L < 2 || net.L > 6 || net.inpDim > VN_KIN) return false;
+    int wmax = 0;
+    for (int l = 0; l < net.L; ++l) wmax = net.width[l] > wmax ? net.width[l] : wmax;
+    return wmax > 32 && wmax <= W;
+}
+void vn_tc64_geometry(const NetDesc& net, int S, Tc64Geom* g) {
+    const SlabLayout sl = slab_layout(net.L, net.inpDim);
+    g->psz = sl.psz;
+    g->smemBytes = SMEM_BYTES;
+    g->stashFloats = (long long)(net.L - 1) * S * TP * W;
+    g->nImages = 2 * (net.L - 1);
+}
+cudaError_t vn_tc64_prepare(int S, int act, size_t smem) {
+    if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem) : prepare_t<2, VN_TANH>(smem);
+    return act == VN_SIGMOID ? prepare_t<3, VN_SIGMOID>(smem) : prepare_t<3, VN_TANH>(smem);
+}
+cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float* wimg, cudaStream_t st) {
+    tc64_prep_kernel<<<dim3(32, 2 * (net.L - 1)), 256, 0, st>>>(net, theta, wimg);
+    return cudaGetLastError();
+}
+cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smem, cudaStream_t st) {
+    Tc64Args k;
+    k.t = a; k.wimg = wimg; k.err = err;
+    if (S == 2) return act == VN_SIGMOID ? launch_t<2, VN_SIGMOID>(k, grid, smem, st) : launch_t<2, VN_TANH>(k, grid, smem, st);
+    return act == VN_SIGMOID ? launch_t<3, VN_SIGMOID>(k, grid, smem, st) : launch_t<3, VN_TANH>(k, grid, smem, st);
+}
+cudaError_t vn_tc64_reduce(const NetDesc& net, const double* slab64, int psz, int nCta, double* flat, cudaStream_t st) {
+    tc64_reduce_kernel<<<(net.nparam + 3) / 4, 128, 0, st>>>(net, slab64, psz, nCta, flat);
+    return cudaGetLastError();
+}
