@@ -201,6 +201,15 @@ __device__ __forceinline__ float warp_colsum(float (&v)[32], int lane) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// Tensor-memory columns (see the header comment).  Forward sweep: the S operand regions + one work accumulator.  Adjoint
+// sweep: one operand region, the parked abar_{l-1,s} (= the hi*hi accumulators of the layer GEMM, fixed up in place
+// with the cross products), the cross-product columns and the weight-gradient accumulator, so that the layer GEMM and
+// the weight-gradient GEMM of a step are issued together and waited for once.
+constexpr uint32_t COL_OP = 0;          // adjoint: zbar_{l,s} hi | lo
+constexpr uint32_t COL_PARK = 128;      //          + 64 s: abar_{l-1,s}
+constexpr uint32_t COL_SMALL = 320;     //          hi*lo + lo*hi of the running layer GEMM
+constexpr uint32_t COL_GW = 384;        //          weight-gradient accumulator (128 columns)
+
 template <int S, int ACT>
 __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__ Tc64Args K) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -251,7 +260,6 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = *tslot;
     const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);           // this warp's lane quarter
-    const uint32_t work = tq + COL_WORK;
 
     const SlabLayout sl = slab_layout(L, net.inpDim);
     float* part = A.part32 + (size_t)blockIdx.x * sl.psz;
@@ -274,8 +282,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         for (int i = 0; i < WIMG_BYTES / 16 / NT; ++i) cp_async16(dst + 4 * (i * NT + tid), src + 4 * (i * NT + tid));
         cp_async_commit();
     };
-    // the image of this step is complete (issued one step earlier); put the next one in flight into the other stage,
-    // whose last readers (the MMAs of the previous step) have completed
+    // the image of this layer is complete (issued one layer earlier); put the next one in flight into the other stage,
+    // whose last readers (the MMAs of the previous layer) have completed
     auto acquire_image = [&]() -> uint32_t {
         cp_async_wait_all();
         fence_async_smem();
@@ -297,8 +305,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         __syncwarp();
         tc_fence_after();
     };
-    // layer GEMM of stream s: work = A_s [128 x 64] x [W_hi | W_lo]^T, then small += A_s,lo x W_hi
-    auto issue_layer = [&](int s, uint32_t wst) {
+    // forward layer GEMM of stream s: work = A_s x [W_hi | W_lo]^T (hi*hi | hi*lo), then the second half += A_s,lo x W_hi
+    auto issue_fwd = [&](int s, uint32_t wst) {
         if (tid == 0) {
             tc_fence_after();
             const uint32_t aHi = tmem + 128 * s, aLo = aHi + 64, d = tmem + COL_WORK;
@@ -311,20 +319,31 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             mma_commit(bar);
         }
     };
-    auto issue_gw = [&]() {
+    // adjoint step of stream s: abar_{l-1,s} = zbar_{l,s} W_l^T (hi*hi -> park s, cross products -> small) and
+    // gW_l (+)= [a_hi ; a_lo]^T-rows x [zbar_hi ; zbar_lo]^T-rows over the 128 points of the tile
+    auto issue_adj = [&](int s, uint32_t wst) {
         if (tid == 0) {
             tc_fence_after();
+            const uint32_t aHi = tmem + COL_OP, aLo = aHi + 64, dMain = tmem + COL_PARK + 64 * s, dSmall = tmem + COL_SMALL;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) {
+                const uint64_t dbh = make_desc(wst + kb * 2 * W_LBO, W_LBO);
+                const uint64_t dbl = make_desc(wst + 8 * SBO + kb * 2 * W_LBO, W_LBO);          // rows 64..127: the lo half
+                mma_ts(dMain, aHi + kb * 8, dbh, IDesc<64>::v, kb ? 1u : 0u);
+                mma_ts(dSmall, aHi + kb * 8, dbl, IDesc<64>::v, kb ? 1u : 0u);
+                mma_ts(dSmall, aLo + kb * 8, dbh, IDesc<64>::v, 1u);
+            }
             const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb)
-                mma_ss(tmem + COL_WORK, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
+                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
             mma_commit(bar);
         }
     };
     // this warp's sum over its 32 points of column c0+lane -> the warp's vec slot of `kind`
-    auto vec_add = [&](int kind, float v) {
+    auto vec_add = [&](int kind, float v, bool overwrite) {
         float* slot = part + sl.vecOff + (kind * 4 + q) * W + c0 + lane;
-        if (first) __stcg(slot, v); else atomicAdd(slot, v);
+        if (overwrite) __stcg(slot, v); else atomicAdd(slot, v);
     };
 
     prefetch_image(0);
@@ -334,33 +353,27 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         const unsigned int gp = base + p;
         const bool valid = gp < A.P;
         const size_t row = valid ? table_row(A, gp) : 0;
+        auto input = [&](int c) -> float {
+            if (c >= A.nxTable) return __ldg(A.extraX + (c - A.nxTable));
+            if (!A.tfIndex) return __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + gp);                // zero padded table
+            return valid ? __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row) : 0.f;
+        };
 
         // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
-        float x[VN_KIN];
-#pragma unroll
-        for (int c = 0; c < VN_KIN; ++c) {
-            x[c] = 0.f;
-            if (c < net.inpDim) {
-                if (c >= A.nxTable) x[c] = __ldg(A.extraX + (c - A.nxTable));
-                else if (!A.tfIndex) x[c] = __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + gp);       // zero padded table
-                else if (valid) x[c] = __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row);
-            }
-        }
         float d1[32];                                // act'(z_l) of the value stream, kept for the tangent streams
         {
             float v[32];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                float z = bs[c0 + jj];
+            for (int jj = 0; jj < 32; ++jj) v[jj] = bs[c0 + jj];
+            for (int c = 0; c < net.inpDim; ++c) {
+                const float xc = input(c);
 #pragma unroll
-                for (int c = 0; c < VN_KIN; ++c)
-                    if (c < net.inpDim) z = fmaf(x[c], W0s[c * W + c0 + jj], z);
-                v[jj] = act_f<ACT>(z);
-                d1[jj] = act_d1<ACT>(v[jj]);
+                for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(xc, W0s[c * W + c0 + jj], v[jj]);
             }
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) { v[jj] = act_f<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
             put_operand(tq, c0, v);
             stash_put(stash, 0, p, c0, v);
-#pragma unroll
             for (int k = 0; k < S - 1; ++k) {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
@@ -369,17 +382,25 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
         }
 
-        // ---- hidden layers, forward
-        for (int l = 1; l < L; ++l) {
-            const uint32_t wst = acquire_image();
-            const bool last = (l == L - 1);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                sync_for_issue();
-                issue_layer(s, wst);
+        // ---- hidden layers, forward: the GEMM of the next (layer, stream) step is issued before this step's epilogue
+        // arithmetic, so the tensor core runs under the activation functions
+        {
+            const int nfs = (L - 1) * S;
+            uint32_t wst = acquire_image();
+            sync_for_issue();
+            issue_fwd(0, wst);
+            int l = 1, s = 0;
+            for (int k = 0; k < nfs; ++k) {
                 wait_mma();
                 float v[32];
-                drain_sum(work, c0, v);
+                drain_sum(tq + COL_WORK, c0, v);
+                int ln = l, sn = s + 1;
+                if (sn == S) { sn = 0; ln = l + 1; }
+                if (k + 1 < nfs) {
+                    if (sn == 0) wst = acquire_image();
+                    sync_for_issue();
+                    issue_fwd(sn, wst);
+                }
                 if (s == 0) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
@@ -391,14 +412,15 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     for (int jj = 0; jj < 32; ++jj) v[jj] *= d1[jj];
                 }
                 put_operand(tq + 128 * s, c0, v);
-                if (!last) stash_put(stash, l * S + s, p, c0, v);
-                else {
+                stash_put(stash, l * S + s, p, c0, v);
+                if (l == L - 1) {
                     // output layer (Dense(1)): partial dot over this thread's neurons
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int jj = 0; jj < 32; jj += 2) { a0 = fmaf(v[jj], wout[c0 + jj], a0); a1 = fmaf(v[jj + 1], wout[c0 + jj + 1], a1); }
                     usP[(h * 3 + s) * TP + p] = a0 + a1;
                 }
+                l = ln; s = sn;
             }
         }
         tmem_wait_st();
@@ -458,120 +480,123 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         }
         __syncthreads();
 
-        // ---- adjoint sweep: layer l turns abar_{l,s} into zbar_{l,s} (tangent streams first: the value stream needs
-        // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
-        if (h == 0) {                                                   // g(b_out) = sum_p ubar_0
+        // ---- output layer gradients: g(b_out) = sum_p ubar_0, g(w_out)[j] = sum_{s,p} a_{L-1,s}[p][j] ubar_s[p]
+        // (a_{L-1,s} is still in the forward operand regions)
+        if (h == 0) {
             float sb = us[p];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
             if (lane == 0) { float* slot = part + sl.boutOff + q; if (first) __stcg(slot, sb); else atomicAdd(slot, sb); }
         }
-        for (int l = L - 1; l >= 0; --l) {
-            const bool top = (l == L - 1);
-            uint32_t wst = 0;
-            if (l >= 1) wst = acquire_image();
-            float a0[32], cross[32], gwo[32], zb0[S][32];
-            if (top) get_operand(tq, c0, a0); else stash_get(stash, l * S, p, c0, a0);
+        {
+            float gwo[32];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) { cross[jj] = 0.f; gwo[jj] = 0.f; }
+            for (int jj = 0; jj < 32; ++jj) gwo[jj] = 0.f;
+            for (int s = 0; s < S; ++s) {
+                float a[32];
+                get_operand(tq + 128 * s, c0, a);
+                const float ub = us[s * TP + p];
 #pragma unroll
-            for (int si = 0; si < S; ++si) {
-                const int s = (si < S - 1) ? si + 1 : 0;
-                float v[32];
-                if (top) {
-                    const float ub = us[s * TP + p];
+                for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(a[jj], ub, gwo[jj]);
+            }
+            const float r = warp_colsum(gwo, lane);
+            vec_add(L, r, first);
+        }
+
+        // ---- adjoint sweep: step (l, s) turns abar_{l,s} into zbar_{l,s} (tangent streams first: the value stream needs
+        // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
+        {
+            float a0[32], dpre[32], apre[32], cross[32];
+            stash_get(stash, (L - 1) * S, p, c0, a0);
+            stash_get(stash, (L - 1) * S + 1, p, c0, dpre);
+            stash_get(stash, (L - 2) * S + 1, p, c0, apre);
+            for (int l = L - 1; l >= 0; --l) {
+                uint32_t wst = 0;
+                if (l >= 1) wst = acquire_image();
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) v[jj] = ub * wout[c0 + jj];
-                } else {
-                    get_plain(tq + 128 * s + c0, v);
-                }
-                if (s > 0) {
-                    float da[32];
-                    if (top) get_operand(tq + 128 * s, c0, da); else stash_get(stash, l * S + s, p, c0, da);
-                    if (top) {
+                for (int jj = 0; jj < 32; ++jj) cross[jj] = 0.f;
+                for (int si = 0; si < S; ++si) {
+                    const int s = (si < S - 1) ? si + 1 : 0;
+                    float v[32];
+                    if (l == L - 1) {
                         const float ub = us[s * TP + p];
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(da[jj], ub, gwo[jj]);
+                        for (int jj = 0; jj < 32; ++jj) v[jj] = ub * wout[c0 + jj];
+                    } else {
+                        get_plain(tq + COL_PARK + 64 * s + c0, v);
                     }
+                    if (s > 0) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        cross[jj] = fmaf(v[jj], da[jj], cross[jj]);
-                        v[jj] *= act_d1<ACT>(a0[jj]);
-                    }
-                } else {
-                    if (top) {
-                        const float ub = us[p];
+                        for (int jj = 0; jj < 32; ++jj) { cross[jj] = fmaf(v[jj], dpre[jj], cross[jj]); v[jj] *= act_d1<ACT>(a0[jj]); }
+                    } else {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(a0[jj], ub, gwo[jj]);
+                        for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
                     }
+                    // next step (ln, sn)
+                    int ln = l, sn = (si + 1 < S - 1) ? si + 2 : 0;
+                    if (si + 1 == S) { ln = l - 1; sn = 1; }
+                    if (l >= 1) {
+                        put_operand(tq + COL_OP, c0, v);
+                        put_transposed(GB, p, c0, v);
+                        put_transposed(GA, p, c0, apre);
+                        if (s == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
-                }
-                if (l >= 1) {
-                    put_operand(tq + 128 * s, c0, v);
-                    put_transposed(GB, p, c0, v);
-                    {
-                        float ap[32];
-                        stash_get(stash, (l - 1) * S + s, p, c0, ap);
-                        put_transposed(GA, p, c0, ap);
-                    }
-                    if (s == 0) { const float r = warp_colsum(v, lane); vec_add(l, r); }          // g(b_l) = sum_p zbar_{l,0}
-                    sync_for_issue();
-                    issue_layer(s, wst);
-                    wait_mma();
-                    {
-                        float t[32];
-                        drain_sum(work, c0, t);
-                        put_plain(tq + 128 * s + c0, t);                  // park abar_{l-1,s} in the (now dead) operand region
-                    }
-                    sync_for_issue();
-                    issue_gw();
-                    wait_mma();
-                    {
-                        // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
-                        float g[32];
-                        if (q < 2) drain_sum(work, c0, g); else get_plain(work + c0, g);
-                        float* slot = part + (size_t)(l - 1) * (TP * W) + p * W + c0;
-                        if (first && si == 0) {                            // first write of this window: overwrite
+                            for (int jj = 0; jj < 32; ++jj) a0[jj] = apre[jj];                  // a_{l-1,0}: the value activations of the next layer down
+                            const float r = warp_colsum(v, lane);                                // g(b_l) = sum_p zbar_{l,0}
+                            vec_add(l, r, first);
+                        }
+                        sync_for_issue();
+                        issue_adj(s, wst);
+                        // stash rows of the next step, in flight while the tensor core runs
+                        if (ln >= 0) {
+                            if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre);
+                            if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre);
+                        }
+                        wait_mma();
+                        {
+                            float t[32], u[32];
+                            get_plain(tq + COL_PARK + 64 * s + c0, t);
+                            get_plain(tq + COL_SMALL + c0, u);
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                            for (int jj = 0; jj < 32; ++jj) t[jj] += u[jj];
+                            put_plain(tq + COL_PARK + 64 * s + c0, t);
+                        }
+                        {
+                            // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
+                            float g[32];
+                            if (q < 2) drain_sum(tq + COL_GW, c0, g); else get_plain(tq + COL_GW + c0, g);
+                            float* slot = part + (size_t)(l - 1) * (TP * W) + p * W + c0;
+                            if (first && si == 0) {                            // first write of this window: overwrite
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                            }
+                        }
+                        tmem_wait_st();
+                    } else {
+                        // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
+                        if (ln >= 0 && sn > 0) stash_get(stash, sn, p, c0, dpre);
+                        if (s > 0) {
+                            const float r = warp_colsum(v, lane);
+                            vec_add(L + 1 + (s - 1), r, first);
                         } else {
+                            for (int c = 0; c < net.inpDim; ++c) {
+                                const float xc = input(c);
+                                float t[32];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                                for (int jj = 0; jj < 32; ++jj) t[jj] = xc * v[jj];
+                                const float r = warp_colsum(t, lane);
+                                vec_add(L + 1 + c, r, first && c >= S - 1);
+                            }
+                            const float r = warp_colsum(v, lane);
+                            vec_add(0, r, first);
                         }
-                    }
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) zb0[s][jj] = v[jj];
-                }
-            }
-            if (top) { const float r = warp_colsum(gwo, lane); vec_add(L, r); }                  // g(w_out)
-            if (l == 0) {
-                // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
-                {
-                    float t[32];
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) t[jj] = zb0[0][jj];
-                    const float r = warp_colsum(t, lane);
-                    vec_add(0, r);
-                }
-#pragma unroll
-                for (int c = 0; c < VN_KIN; ++c) {
-                    if (c < net.inpDim) {
-                        float t[32];
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            t[jj] = x[c] * zb0[0][jj];
-                            if (c < S - 1) t[jj] += zb0[(c + 1 < S) ? c + 1 : 0][jj];
-                        }
-                        const float r = warp_colsum(t, lane);
-                        vec_add(L + 1 + c, r);
                     }
                 }
             }
         }
-        // the next tile's first MMA overwrites `work` and its layer-0 epilogue the operand regions: both are idle
-        // (every MMA has been waited for, every drain completed before the last sync_for_issue or is thread-local)
         tmem_wait_ld();
 
         first = false;
@@ -660,7 +685,7 @@ void vn_tc64_geometry(const NetDesc& net, int S, Tc64Geom* g) {
     const SlabLayout sl = slab_layout(net.L, net.inpDim);
     g->psz = sl.psz;
     g->smemBytes = SMEM_BYTES;
-    g->stashFloats = (long long)(net.L - 1) * S * TP * W;
+    g->stashFloats = (long long)net.L * S * TP * W;
     g->nImages = 2 * (net.L - 1);
 }
 cudaError_t vn_tc64_prepare(int S, int act, size_t smem) {

@@ -20,7 +20,7 @@
 struct Tc64Geom {
     int psz;                // floats (FP32 window) / doubles (FP64) of one CTA's gradient slab
     size_t smemBytes;
-    long long stashFloats;  // per-CTA activation stash (layers 0..L-2, all streams)
+    long long stashFloats;  // per-CTA activation stash (all hidden layers, all streams)
     int nImages;            // staged weight images (2 per hidden-to-hidden layer), 8192 floats each
 };
 
