@@ -650,7 +650,7 @@ static int ensure_work(vn_engine* e) {
         CK(e->partVar.ensure((size_t)e->numSMs * e->tc64Geom.psz * sizeof(double)));
         CK(e->part32Var.ensure((size_t)e->numSMs * e->tc64Geom.psz * sizeof(float)));
         CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->numSMs * e->tc64Geom.stashFloats * sizeof(float))));
-        CK(e->lossPart.ensure((size_t)e->numSMs * 8 * sizeof(double)));
+        CK(e->lossPart.ensure((size_t)e->numSMs * e->tc64Geom.lossSlots * sizeof(double)));
         e->fused = true;
         return VN_OK;
     }
@@ -1151,7 +1151,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             CK(vn_tc64_reduce(e->net, e->partVar.as<double>(), e->tc64Geom.psz, e->gridVar, e->tc64Flat.as<double>(), st));
             e->launches++;
         }
-        nSeg = e->gridVar * (g.NT / 32);
+        nSeg = e->gridVar * (tc ? e->tc64Geom.lossSlots : g.NT / 32);
         segPtr = e->lossPart.as<double>();
     } else {
         // 1. forward over all quadrature points -> weighted integrand
@@ -1491,7 +1491,7 @@ extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
         return VN_OK;
     }
     if (e->useTc64) {
-        snprintf(buf, n, "family=tcgen05-3xtf32-tile64 class=64 S=%d L=%d var_adj(TP=128,NT=256,smem=%zu,grid=%d,fused-R single pass,"
+        snprintf(buf, n, "family=tcgen05-3xtf32-tile64 class=64 S=%d L=%d var_adj(TP=128,NT=512,smem=%zu,grid=%d,fused-R single pass,"
                  "stash=%lldB/CTA,A-from-TMEM) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
                  e->S, e->net.L, e->tc64Geom.smemBytes, e->gridVar, (long long)(e->tc64Geom.stashFloats * 4), e->gBicAdj.TP,
                  e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);

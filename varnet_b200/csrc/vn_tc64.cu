@@ -16,7 +16,9 @@ namespace {
 
 constexpr int TP = 128;            // points per tile == TMEM lanes
 constexpr int W = 64;              // padded hidden width
-constexpr int NT = 256;            // threads: warp w -> lane quarter w & 3, neuron half w >> 2
+constexpr int NH = 4;              // neuron groups: warp w -> lane quarter w & 3, neuron group w >> 2
+constexpr int CPT = W / NH;        // neurons (columns) per thread
+constexpr int NT = 128 * NH;       // threads
 constexpr int FOLD = 16;           // tiles accumulated in the FP32 window slab before the FP64 fold
 constexpr uint32_t SBO = 128;      // bytes between 8-row groups of a canonical K-major operand
 constexpr uint32_t W_LBO = 2048;   // weight images: 128 rows x 16 B per 4-wide K unit
@@ -27,7 +29,7 @@ constexpr int OFF_WST = 0;                         // two weight stages
 constexpr int OFF_GA = 2 * WIMG_BYTES;             // [a_hi^T ; a_lo^T]     128 rows x 128 points
 constexpr int OFF_GB = OFF_GA + G_BYTES;           // [zbar_hi^T ; zbar_lo^T]
 constexpr int OFF_PAR = OFF_GB + G_BYTES;
-constexpr int PAR_FLOATS = 2560;                   // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[2][3][128] | us[3][128] | I[128] | R[128]
+constexpr int PAR_FLOATS = 1152 + NH * 384 + 640;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128]
 constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
@@ -106,11 +108,11 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
-// ------------------------------------------------------------------ per-thread operand movement (thread = point p x neurons c0..c0+31)
-// hi/lo split of v -> the thread's columns of operand region `reg` (address of the lane quarter, column 128 s)
-__device__ __forceinline__ void put_operand(uint32_t reg, int c0, const float (&v)[32]) {
+// ------------------------------------------------------------------ per-thread operand movement (thread = point p x neurons c0..c0+CPT-1)
+// hi/lo split of v -> the thread's columns of operand region `reg` (address of the lane quarter, first column of the region)
+__device__ __forceinline__ void put_operand(uint32_t reg, int c0, const float (&v)[CPT]) {
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hf = 0; hf < CPT / 16; ++hf) {
         float hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { hi[i] = tf32_rn(v[16 * hf + i]); lo[i] = v[16 * hf + i] - hi[i]; }
@@ -119,9 +121,9 @@ __device__ __forceinline__ void put_operand(uint32_t reg, int c0, const float (&
     }
 }
 // hi + lo == the FP32 value exactly
-__device__ __forceinline__ void get_operand(uint32_t reg, int c0, float (&v)[32]) {
+__device__ __forceinline__ void get_operand(uint32_t reg, int c0, float (&v)[CPT]) {
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hf = 0; hf < CPT / 16; ++hf) {
         float hi[16], lo[16];
         tmem_ld16(reg + c0 + 16 * hf, hi);
         tmem_ld16(reg + 64 + c0 + 16 * hf, lo);
@@ -130,30 +132,32 @@ __device__ __forceinline__ void get_operand(uint32_t reg, int c0, float (&v)[32]
         for (int i = 0; i < 16; ++i) v[16 * hf + i] = hi[i] + lo[i];
     }
 }
-__device__ __forceinline__ void put_plain(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void put_plain(uint32_t taddr, const float (&v)[CPT]) {
     float t[16];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hf = 0; hf < CPT / 16; ++hf) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) t[i] = v[16 * hf + i];
         tmem_st16(taddr + 16 * hf, t);
     }
 }
-__device__ __forceinline__ void get_plain(uint32_t taddr, float (&v)[32]) {
-    float t0[16], t1[16];
-    tmem_ld16(taddr, t0);
-    tmem_ld16(taddr + 16, t1);
-    tmem_wait_ld();
+__device__ __forceinline__ void get_plain(uint32_t taddr, float (&v)[CPT]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
+    for (int hf = 0; hf < CPT / 16; ++hf) {
+        float t[16];
+        tmem_ld16(taddr + 16 * hf, t);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * hf + i] = t[i];
+    }
 }
-// work accumulators -> z = (hi*hi) + (hi*lo + lo*hi) for the thread's 32 columns
-__device__ __forceinline__ void drain_sum(uint32_t work, int c0, float (&z)[32]) {
+// two accumulator sets `a` and `b` (addresses of the thread's first column) -> their FP32 sum
+__device__ __forceinline__ void drain_sum2(uint32_t a, uint32_t b, float (&z)[CPT]) {
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hf = 0; hf < CPT / 16; ++hf) {
         float m[16], s[16];
-        tmem_ld16(work + c0 + 16 * hf, m);
-        tmem_ld16(work + 64 + c0 + 16 * hf, s);
+        tmem_ld16(a + 16 * hf, m);
+        tmem_ld16(b + 16 * hf, s);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[16 * hf + i] = m[i] + s[i];
@@ -161,44 +165,53 @@ __device__ __forceinline__ void drain_sum(uint32_t work, int c0, float (&z)[32])
 }
 // transposing store: rows = neurons (hi rows 0..63, lo rows 64..127), K = points; a warp's 32 points of one neuron
 // fall into 32 different banks (G_LBO = 2048 + 16)
-__device__ __forceinline__ void put_transposed(unsigned char* G, int p, int c0, const float (&v)[32]) {
-    unsigned char* base = G + (p >> 2) * G_LBO + (p & 3) * 4;
+__device__ __forceinline__ void put_transposed(unsigned char* G, int p, int c0, const float (&v)[CPT]) {
+    unsigned char* base = G + (p >> 2) * G_LBO + (p & 3) * 4 + (c0 >> 3) * SBO;
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-        const int j = c0 + jj;
+    for (int jj = 0; jj < CPT; ++jj) {
         const float hi = tf32_rn(v[jj]);
-        *reinterpret_cast<float*>(base + (j >> 3) * SBO + (j & 7) * 16) = hi;
-        *reinterpret_cast<float*>(base + (8 + (j >> 3)) * SBO + (j & 7) * 16) = v[jj] - hi;
+        *reinterpret_cast<float*>(base + (jj >> 3) * SBO + (jj & 7) * 16) = hi;
+        *reinterpret_cast<float*>(base + (8 + (jj >> 3)) * SBO + (jj & 7) * 16) = v[jj] - hi;
     }
 }
 // stash: [(l*S + s)][neuron/4][point][4]
-__device__ __forceinline__ void stash_put(float* st, int slab, int p, int c0, const float (&v)[32]) {
+__device__ __forceinline__ void stash_put(float* st, int slab, int p, int c0, const float (&v)[CPT]) {
     float4* b = reinterpret_cast<float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) __stcg(b + u * TP, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+    for (int u = 0; u < CPT / 4; ++u) __stcg(b + u * TP, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
 }
-__device__ __forceinline__ void stash_get(const float* st, int slab, int p, int c0, float (&v)[32]) {
+__device__ __forceinline__ void stash_get(const float* st, int slab, int p, int c0, float (&v)[CPT]) {
     const float4* b = reinterpret_cast<const float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < CPT / 4; ++u) {
         const float4 t = __ldcg(b + u * TP);
         v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
     }
 }
-// sum over the 32 lanes of v[c]: lane c returns column c  (31 shuffles)
-__device__ __forceinline__ float warp_colsum(float (&v)[32], int lane) {
+// sum over the 32 lanes of v[c], c < CPT: the lanes with index >> COLSUM_SHIFT == c return column c
+__device__ __forceinline__ float warp_colsum(float (&v)[CPT], int lane) {
+    int n = CPT;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
+        if (n > 1) {
+            const bool up = (lane & off) != 0;
+            const int hn = n >> 1;
 #pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = up ? v[i] : v[i + off];
-            const float keep = up ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            for (int i = 0; i < CPT / 2; ++i) {
+                if (i < hn) {
+                    const float send = up ? v[i] : v[i + hn];
+                    const float keep = up ? v[i + hn] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            n = hn;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
         }
     }
     return v[0];
 }
+constexpr int COLSUM_SHIFT = (CPT == 32) ? 0 : (CPT == 16 ? 1 : 2);      // column of the returned sum = lane >> COLSUM_SHIFT
 
 // ------------------------------------------------------------------ the kernel
 // Tensor-memory columns (see the header comment).  Forward sweep: the S operand regions + one work accumulator.  Adjoint
@@ -219,15 +232,15 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = warp & 3, h = warp >> 2;
     const int p = 32 * q + lane;                    // point of the tile == TMEM lane
-    const int c0 = 32 * h;                          // first of this thread's 32 neurons
+    const int c0 = CPT * h;                         // first of this thread's CPT neurons
 
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     float* W0s = par;                               // [8][64]
     float* bs = par + 512;                          // [8][64]
     float* wout = par + 1024;                       // [64]
     float* misc = par + 1088;                       // [0] = b_out
-    float* usP = par + 1152;                        // [2][3][128] output-layer partial dots of the two neuron halves
-    float* us = usP + 768;                          // [3][128] u_s, then the adjoint seeds
+    float* usP = par + 1152;                        // [NH][3][128] output-layer partial dots of the neuron groups
+    float* us = usP + NH * 384;                          // [3][128] u_s, then the adjoint seeds
     float* Ish = us + 384;                          // [128]
     float* Rsh = Ish + 128;                         // [128]
     const uint32_t bar = smem_u32(smem + OFF_BAR);
@@ -342,7 +355,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     };
     // this warp's sum over its 32 points of column c0+lane -> the warp's vec slot of `kind`
     auto vec_add = [&](int kind, float v, bool overwrite) {
-        float* slot = part + sl.vecOff + (kind * 4 + q) * W + c0 + lane;
+        if (lane & ((1 << COLSUM_SHIFT) - 1)) return;
+        float* slot = part + sl.vecOff + (kind * 4 + q) * W + c0 + (lane >> COLSUM_SHIFT);
         if (overwrite) __stcg(slot, v); else atomicAdd(slot, v);
     };
 
@@ -360,23 +374,23 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         };
 
         // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
-        float d1[32];                                // act'(z_l) of the value stream, kept for the tangent streams
+        float d1[CPT];                                // act'(z_l) of the value stream, kept for the tangent streams
         {
-            float v[32];
+            float v[CPT];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = bs[c0 + jj];
+            for (int jj = 0; jj < CPT; ++jj) v[jj] = bs[c0 + jj];
             for (int c = 0; c < net.inpDim; ++c) {
                 const float xc = input(c);
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(xc, W0s[c * W + c0 + jj], v[jj]);
+                for (int jj = 0; jj < CPT; ++jj) v[jj] = fmaf(xc, W0s[c * W + c0 + jj], v[jj]);
             }
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) { v[jj] = act_f<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
+            for (int jj = 0; jj < CPT; ++jj) { v[jj] = act_f<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
             put_operand(tq, c0, v);
             stash_put(stash, 0, p, c0, v);
             for (int k = 0; k < S - 1; ++k) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
+                for (int jj = 0; jj < CPT; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
                 put_operand(tq + 128 * (1 + k), c0, v);
                 stash_put(stash, 1 + k, p, c0, v);
             }
@@ -392,8 +406,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             int l = 1, s = 0;
             for (int k = 0; k < nfs; ++k) {
                 wait_mma();
-                float v[32];
-                drain_sum(tq + COL_WORK, c0, v);
+                float v[CPT];
+                drain_sum2(tq + COL_WORK + c0, tq + COL_WORK + 64 + c0, v);
                 int ln = l, sn = s + 1;
                 if (sn == S) { sn = 0; ln = l + 1; }
                 if (k + 1 < nfs) {
@@ -403,13 +417,13 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 }
                 if (s == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
+                    for (int jj = 0; jj < CPT; ++jj) {
                         v[jj] = act_f<ACT>(v[jj] + bs[l * W + c0 + jj]);
                         d1[jj] = act_d1<ACT>(v[jj]);
                     }
                 } else {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) v[jj] *= d1[jj];
+                    for (int jj = 0; jj < CPT; ++jj) v[jj] *= d1[jj];
                 }
                 put_operand(tq + 128 * s, c0, v);
                 stash_put(stash, l * S + s, p, c0, v);
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     // output layer (Dense(1)): partial dot over this thread's neurons
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj += 2) { a0 = fmaf(v[jj], wout[c0 + jj], a0); a1 = fmaf(v[jj + 1], wout[c0 + jj + 1], a1); }
+                    for (int jj = 0; jj < CPT; jj += 2) { a0 = fmaf(v[jj], wout[c0 + jj], a0); a1 = fmaf(v[jj + 1], wout[c0 + jj + 1], a1); }
                     usP[(h * 3 + s) * TP + p] = a0 + a1;
                 }
                 l = ln; s = sn;
@@ -430,7 +444,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         if (tid < TP) {
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                float u = usP[s * TP + p] + usP[(3 + s) * TP + p];
+                float u = 0.f;
+#pragma unroll
+                for (int g = 0; g < NH; ++g) u += usP[(g * 3 + s) * TP + p];
                 if (s == 0) u += misc[0];
                 us[s * TP + p] = u;
             }
@@ -489,15 +505,15 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             if (lane == 0) { float* slot = part + sl.boutOff + q; if (first) __stcg(slot, sb); else atomicAdd(slot, sb); }
         }
         {
-            float gwo[32];
+            float gwo[CPT];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) gwo[jj] = 0.f;
+            for (int jj = 0; jj < CPT; ++jj) gwo[jj] = 0.f;
             for (int s = 0; s < S; ++s) {
-                float a[32];
+                float a[CPT];
                 get_operand(tq + 128 * s, c0, a);
                 const float ub = us[s * TP + p];
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) gwo[jj] = fmaf(a[jj], ub, gwo[jj]);
+                for (int jj = 0; jj < CPT; ++jj) gwo[jj] = fmaf(a[jj], ub, gwo[jj]);
             }
             const float r = warp_colsum(gwo, lane);
             vec_add(L, r, first);
@@ -506,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // ---- adjoint sweep: step (l, s) turns abar_{l,s} into zbar_{l,s} (tangent streams first: the value stream needs
         // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
         {
-            float a0[32], dpre[32], apre[32], cross[32];
+            float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
             stash_get(stash, (L - 1) * S, p, c0, a0);
             stash_get(stash, (L - 1) * S + 1, p, c0, dpre);
             stash_get(stash, (L - 2) * S + 1, p, c0, apre);
@@ -514,23 +530,23 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 uint32_t wst = 0;
                 if (l >= 1) wst = acquire_image();
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) cross[jj] = 0.f;
+                for (int jj = 0; jj < CPT; ++jj) cross[jj] = 0.f;
                 for (int si = 0; si < S; ++si) {
                     const int s = (si < S - 1) ? si + 1 : 0;
-                    float v[32];
+                    float v[CPT];
                     if (l == L - 1) {
                         const float ub = us[s * TP + p];
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) v[jj] = ub * wout[c0 + jj];
+                        for (int jj = 0; jj < CPT; ++jj) v[jj] = ub * wout[c0 + jj];
                     } else {
                         get_plain(tq + COL_PARK + 64 * s + c0, v);
                     }
                     if (s > 0) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) { cross[jj] = fmaf(v[jj], dpre[jj], cross[jj]); v[jj] *= act_d1<ACT>(a0[jj]); }
+                        for (int jj = 0; jj < CPT; ++jj) { cross[jj] = fmaf(v[jj], dpre[jj], cross[jj]); v[jj] *= act_d1<ACT>(a0[jj]); }
                     } else {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
+                        for (int jj = 0; jj < CPT; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
                     }
                     // next step (ln, sn)
                     int ln = l, sn = (si + 1 < S - 1) ? si + 2 : 0;
@@ -541,7 +557,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         put_transposed(GA, p, c0, apre);
                         if (s == 0) {
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) a0[jj] = apre[jj];                  // a_{l-1,0}: the value activations of the next layer down
+                            for (int jj = 0; jj < CPT; ++jj) a0[jj] = apre[jj];                  // a_{l-1,0}: the value activations of the next layer down
                             const float r = warp_colsum(v, lane);                                // g(b_l) = sum_p zbar_{l,0}
                             vec_add(l, r, first);
                         }
@@ -554,24 +570,21 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         }
                         wait_mma();
                         {
-                            float t[32], u[32];
-                            get_plain(tq + COL_PARK + 64 * s + c0, t);
-                            get_plain(tq + COL_SMALL + c0, u);
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) t[jj] += u[jj];
+                            float t[CPT];
+                            drain_sum2(tq + COL_PARK + 64 * s + c0, tq + COL_SMALL + c0, t);
                             put_plain(tq + COL_PARK + 64 * s + c0, t);
                         }
                         {
                             // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
-                            float g[32];
-                            if (q < 2) drain_sum(tq + COL_GW, c0, g); else get_plain(tq + COL_GW + c0, g);
+                            float g[CPT];
+                            if (q < 2) drain_sum2(tq + COL_GW + c0, tq + COL_GW + 64 + c0, g); else get_plain(tq + COL_GW + c0, g);
                             float* slot = part + (size_t)(l - 1) * (TP * W) + p * W + c0;
                             if (first && si == 0) {                            // first write of this window: overwrite
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                                for (int u = 0; u < CPT / 4; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
                             } else {
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                                for (int u = 0; u < CPT / 4; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
                             }
                         }
                         tmem_wait_st();
@@ -584,9 +597,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         } else {
                             for (int c = 0; c < net.inpDim; ++c) {
                                 const float xc = input(c);
-                                float t[32];
+                                float t[CPT];
 #pragma unroll
-                                for (int jj = 0; jj < 32; ++jj) t[jj] = xc * v[jj];
+                                for (int jj = 0; jj < CPT; ++jj) t[jj] = xc * v[jj];
                                 const float r = warp_colsum(t, lane);
                                 vec_add(L + 1 + c, r, first && c >= S - 1);
                             }
@@ -607,8 +620,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 if (firstFold) __stcg(part64 + idx, v); else part64[idx] += v;
             };
             for (int l = 1; l < L; ++l)
-                for (int jj = 0; jj < 32; ++jj) put((l - 1) * (TP * W) + p * W + c0 + jj);
-            for (int k = 0; k < sl.nkind; ++k) put(sl.vecOff + (k * 4 + q) * W + c0 + lane);
+                for (int jj = 0; jj < CPT; ++jj) put((l - 1) * (TP * W) + p * W + c0 + jj);
+            if ((lane & ((1 << COLSUM_SHIFT) - 1)) == 0)
+                for (int k = 0; k < sl.nkind; ++k) put(sl.vecOff + (k * 4 + q) * W + c0 + (lane >> COLSUM_SHIFT));
             if (h == 0 && lane == 0) put(sl.boutOff + q);
             firstFold = false; first = true; win = 0;
         }
@@ -687,6 +701,7 @@ void vn_tc64_geometry(const NetDesc& net, int S, Tc64Geom* g) {
     g->smemBytes = SMEM_BYTES;
     g->stashFloats = (long long)net.L * S * TP * W;
     g->nImages = 2 * (net.L - 1);
+    g->lossSlots = NT / 32;
 }
 cudaError_t vn_tc64_prepare(int S, int act, size_t smem) {
     if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem) : prepare_t<2, VN_TANH>(smem);

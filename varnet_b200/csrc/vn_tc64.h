@@ -22,6 +22,7 @@ struct Tc64Geom {
     size_t smemBytes;
     long long stashFloats;  // per-CTA activation stash (all hidden layers, all streams)
     int nImages;            // staged weight images (2 per hidden-to-hidden layer), 8192 floats each
+    int lossSlots;          // loss partials written per CTA (A.lossPart)
 };
 
 bool vn_tc64_supported(const NetDesc& net, int S);
@@ -29,7 +30,7 @@ void vn_tc64_geometry(const NetDesc& net, int S, Tc64Geom* g);
 cudaError_t vn_tc64_prepare(int S, int act, size_t smemBytes);
 // theta -> hi/lo canonical K-major images [W_hi | W_lo] (forward) and [W^T_hi | W^T_lo] (adjoint) per layer
 cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float* wimg, cudaStream_t st);
-// a: as for vn_adj_kernel<MODE_VAR_FUSED> (part/part32/psz/stash/stashFloats/lossPart sized from Tc64Geom, 8 loss partials per CTA)
+// a: as for vn_adj_kernel<MODE_VAR_FUSED> (part/part32/psz/stash/stashFloats/lossPart sized from Tc64Geom)
 cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smemBytes,
                            cudaStream_t st);
 // fixed-order sum of the per-CTA FP64 slabs -> flat[nparam] in reference variable order
