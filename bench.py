@@ -416,7 +416,9 @@ def main():
             # tensor-core class: the layer GEMMs run as 3xTF32 (three tcgen05.mma kind::tf32 per algorithmic product);
             # the bound is the TF32 tensor peak = half the measured dense bf16 figure (sustained: kernel timed inside a long step)
             tf32_peak = 0.5 * pk["bf16_tflops"]
-            roofline.update(bound="tensor", peak=tf32_peak, frac=achieved / tf32_peak, kernel="tc_gemm_kernel / tc_gw_kernel pipeline (vn_tc.cu)",
+            tile64 = "tile64" in eng.kernel_info()
+            roofline.update(bound="tensor", peak=tf32_peak, frac=achieved / tf32_peak,
+                            kernel="tc64_var_kernel (vn_tc64.cu: resident 128-point tiles, A-from-TMEM 3xTF32)" if tile64 else "tc_gemm_kernel / tc_gw_kernel pipeline (vn_tc.cu)",
                             peak_source="0.5 x dense bf16 (%s): TF32 runs at half the bf16 rate" % pk["source"],
                             executed_mma_tflops=3.0 * achieved, executed_frac=3.0 * achieved / tf32_peak,
                             fp32_fma_peak=peak_tf, frac_of_fp32_fma_peak=achieved / peak_tf if peak_tf else None)

@@ -14,6 +14,7 @@ CASES = [
     (1, 2, [64, 64], "sigmoid", True, True, False, False, 70, 16, 150, 100),
     (2, 3, [40, 64, 50], "tanh", True, True, True, True, 33, 32, 70, 40),
     (2, 5, [48, 33, 64, 64, 40], "sigmoid", True, False, False, False, 129, 64, 70, 40),
+    (1, 2, [64, 64, 64, 64, 64, 64], "tanh", True, False, False, False, 300, 32, 70, 40),
 ]
 
 

@@ -505,7 +505,7 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     {
         // 64-wide class: the variational term runs on the tensor-core tile kernel unless VARNET_B200_CLASS=fma
         const bool wantTc64 = !(forceCls && !strcmp(forceCls, "fma"));
-        if (e->wclass == 64 && wantTc64 && vn_tc64_supported(e->net, e->S)) {
+        if ((e->wclass == 64 || e->wclass == 164) && wantTc64 && vn_tc64_supported(e->net, e->S)) {
             vn_tc64_geometry(e->net, e->S, &e->tc64Geom);
             if (e->tc64Geom.smemBytes <= prop.sharedMemPerBlockOptin && vn_tc64_prepare(e->S, act, e->tc64Geom.smemBytes) == cudaSuccess) {
                 e->tc64 = true;
