@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     float* us = usP + NH * 384;                          // [3][128] u_s, then the adjoint seeds
     float* Ish = us + 384;                          // [128]
     float* Rsh = Ish + 128;                         // [128]
-    const uint32_t bar = smem_u32(smem + OFF_BAR);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8);
+    const uint32_t bar = smem_u32(smem + OFF_BAR);            // forward GEMMs / adjoint layer GEMM
+    const uint32_t barGw = bar + 8;                             // weight-gradient GEMM
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
     unsigned char* GA = smem + OFF_GA;
     unsigned char* GB = smem + OFF_GB;
 
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         if (tid == 0) {
             misc[0] = th[net.boff[L]];
             mbar_init(bar, 1);
+            mbar_init(barGw, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     double* part64 = A.part + (size_t)blockIdx.x * sl.psz;
     float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
     const int nImg = 2 * (L - 1);
-    uint32_t phase = 0;
+    uint32_t phase = 0, phaseGw = 0;
     bool ok = true;
     int imgNext = 0;                                 // next weight image of the tile sequence to be consumed
     double lossAcc = 0.0;
@@ -318,6 +320,12 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         __syncwarp();
         tc_fence_after();
     };
+    auto wait_gw = [&]() {
+        if (ok) ok = mbar_wait(barGw, phaseGw);
+        phaseGw ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+    };
     // forward layer GEMM of stream s: work = A_s x [W_hi | W_lo]^T (hi*hi | hi*lo), then the second half += A_s,lo x W_hi
     auto issue_fwd = [&](int s, uint32_t wst) {
         if (tid == 0) {
@@ -334,9 +342,15 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     };
     // adjoint step of stream s: abar_{l-1,s} = zbar_{l,s} W_l^T (hi*hi -> park s, cross products -> small) and
     // gW_l (+)= [a_hi ; a_lo]^T-rows x [zbar_hi ; zbar_lo]^T-rows over the 128 points of the tile
+    // (the weight-gradient GEMM goes first and has its own barrier: its accumulators are drained under the layer GEMM)
     auto issue_adj = [&](int s, uint32_t wst) {
         if (tid == 0) {
             tc_fence_after();
+            const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb)
+                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
+            mma_commit(barGw);
             const uint32_t aHi = tmem + COL_OP, aLo = aHi + 64, dMain = tmem + COL_PARK + 64 * s, dSmall = tmem + COL_SMALL;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
@@ -346,10 +360,6 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 mma_ts(dSmall, aHi + kb * 8, dbl, IDesc<64>::v, kb ? 1u : 0u);
                 mma_ts(dSmall, aLo + kb * 8, dbh, IDesc<64>::v, 1u);
             }
-            const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
-#pragma unroll
-            for (int kb = 0; kb < 16; ++kb)
-                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
             mma_commit(bar);
         }
     };
@@ -568,12 +578,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                             if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre);
                             if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre);
                         }
-                        wait_mma();
-                        {
-                            float t[CPT];
-                            drain_sum2(tq + COL_PARK + 64 * s + c0, tq + COL_SMALL + c0, t);
-                            put_plain(tq + COL_PARK + 64 * s + c0, t);
-                        }
+                        wait_gw();
                         {
                             // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
                             float g[CPT];
@@ -586,6 +591,12 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
 #pragma unroll
                                 for (int u = 0; u < CPT / 4; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
                             }
+                        }
+                        wait_mma();
+                        {
+                            float t[CPT];
+                            drain_sum2(tq + COL_PARK + 64 * s + c0, tq + COL_SMALL + c0, t);
+                            put_plain(tq + COL_PARK + 64 * s + c0, t);                  // park abar_{l-1,s} in place
                         }
                         tmem_wait_st();
                     } else {
