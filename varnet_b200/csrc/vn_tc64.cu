@@ -106,6 +106,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// activation of this kernel class: tanh as 1 - 2 / (exp(2|x|) + 1) on the special-function unit (7 instructions against ~25
+// for tanhf; absolute error ~1e-7, the size of the FP32 rounding of the pre-activation itself); sigmoid as in vn_tile.cuh
+template <int ACT> __device__ __forceinline__ float act64(float z) {
+    if (ACT == VN_SIGMOID) return act_f<VN_SIGMOID>(z);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(z) * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return copysignf(fmaf(-2.0f, r, 1.0f), z);
+}
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ------------------------------------------------------------------ per-thread operand movement (thread = point p x neurons c0..c0+CPT-1)
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 for (int jj = 0; jj < CPT; ++jj) v[jj] = fmaf(xc, W0s[c * W + c0 + jj], v[jj]);
             }
 #pragma unroll
-            for (int jj = 0; jj < CPT; ++jj) { v[jj] = act_f<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
+            for (int jj = 0; jj < CPT; ++jj) { v[jj] = act64<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
             put_operand(tq, c0, v);
             stash_put(stash, 0, p, c0, v);
             for (int k = 0; k < S - 1; ++k) {
@@ -428,7 +437,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 if (s == 0) {
 #pragma unroll
                     for (int jj = 0; jj < CPT; ++jj) {
-                        v[jj] = act_f<ACT>(v[jj] + bs[l * W + c0 + jj]);
+                        v[jj] = act64<ACT>(v[jj] + bs[l * W + c0 + jj]);
                         d1[jj] = act_d1<ACT>(v[jj]);
                     }
                 } else {
