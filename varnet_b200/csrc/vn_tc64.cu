@@ -183,19 +183,31 @@ __device__ __forceinline__ void put_transposed(unsigned char* G, int p, int c0, 
         *reinterpret_cast<float*>(base + (8 + (jj >> 3)) * SBO + (jj & 7) * 16) = v[jj] - hi;
     }
 }
-// stash: [(l*S + s)][neuron/4][point][4]
-__device__ __forceinline__ void stash_put(float* st, int slab, int p, int c0, const float (&v)[CPT]) {
+// stash: [(l*S + s)][neuron/4][point][4].  The 148 per-CTA slabs (57 MB at 4x64) are rewritten by every tile: they are
+// written and read with an L2 evict_last policy (and the streamed point table with evict_first) so that they stay in the
+// 126 MB L2 instead of being written back to HBM tile after tile.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ float ldg_stream(const float* ptr, uint64_t pol) {
+    float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol)); return v;
+}
+__device__ __forceinline__ void stash_put(float* st, int slab, int p, int c0, const float (&v)[CPT], uint64_t pol) {
     float4* b = reinterpret_cast<float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
 #pragma unroll
-    for (int u = 0; u < CPT / 4; ++u) __stcg(b + u * TP, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+    for (int u = 0; u < CPT / 4; ++u)
+        asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(b + u * TP), "f"(v[4 * u]), "f"(v[4 * u + 1]),
+                     "f"(v[4 * u + 2]), "f"(v[4 * u + 3]), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void stash_get(const float* st, int slab, int p, int c0, float (&v)[CPT]) {
+__device__ __forceinline__ void stash_get(const float* st, int slab, int p, int c0, float (&v)[CPT], uint64_t pol) {
     const float4* b = reinterpret_cast<const float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
 #pragma unroll
-    for (int u = 0; u < CPT / 4; ++u) {
-        const float4 t = __ldcg(b + u * TP);
-        v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
-    }
+    for (int u = 0; u < CPT / 4; ++u)
+        asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v[4 * u]), "=f"(v[4 * u + 1]), "=f"(v[4 * u + 2]),
+                     "=f"(v[4 * u + 3]) : "l"(b + u * TP), "l"(pol) : "memory");
 }
 // sum over the 32 lanes of v[c], c < CPT: the lanes with index >> COLSUM_SHIFT == c return column c
 __device__ __forceinline__ float warp_colsum(float (&v)[CPT], int lane) {
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     const uint32_t tmem = *tslot;
     const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);           // this warp's lane quarter
 
+    const uint64_t polLast = policy_evict_last(), polFirst = policy_evict_first();
     const SlabLayout sl = slab_layout(L, net.inpDim);
     float* part = A.part32 + (size_t)blockIdx.x * sl.psz;
     double* part64 = A.part + (size_t)blockIdx.x * sl.psz;
@@ -388,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         const size_t row = valid ? table_row(A, gp) : 0;
         auto input = [&](int c) -> float {
             if (c >= A.nxTable) return __ldg(A.extraX + (c - A.nxTable));
-            if (!A.tfIndex) return __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + gp);                // zero padded table
+            if (!A.tfIndex) return ldg_stream(A.cols + (size_t)(A.colX + c) * A.pstride + gp, polFirst);  // zero padded table
             return valid ? __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row) : 0.f;
         };
 
@@ -406,12 +419,12 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
 #pragma unroll
             for (int jj = 0; jj < CPT; ++jj) { v[jj] = act64<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
             put_operand(tq, c0, v);
-            stash_put(stash, 0, p, c0, v);
+            stash_put(stash, 0, p, c0, v, polLast);
             for (int k = 0; k < S - 1; ++k) {
 #pragma unroll
                 for (int jj = 0; jj < CPT; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
                 put_operand(tq + 128 * (1 + k), c0, v);
-                stash_put(stash, 1 + k, p, c0, v);
+                stash_put(stash, 1 + k, p, c0, v, polLast);
             }
         }
 
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     for (int jj = 0; jj < CPT; ++jj) v[jj] *= d1[jj];
                 }
                 put_operand(tq + 128 * s, c0, v);
-                stash_put(stash, l * S + s, p, c0, v);
+                stash_put(stash, l * S + s, p, c0, v, polLast);
                 if (l == L - 1) {
                     // output layer (Dense(1)): partial dot over this thread's neurons
                     float a0 = 0.f, a1 = 0.f;
@@ -542,9 +555,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
         {
             float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
-            stash_get(stash, (L - 1) * S, p, c0, a0);
-            stash_get(stash, (L - 1) * S + 1, p, c0, dpre);
-            stash_get(stash, (L - 2) * S + 1, p, c0, apre);
+            stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
+            stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
+            stash_get(stash, (L - 2) * S + 1, p, c0, apre, polLast);
             for (int l = L - 1; l >= 0; --l) {
                 uint32_t wst = 0;
                 if (l >= 1) wst = acquire_image();
@@ -584,8 +597,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         issue_adj(s, wst);
                         // stash rows of the next step, in flight while the tensor core runs
                         if (ln >= 0) {
-                            if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre);
-                            if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre);
+                            if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre, polLast);
+                            if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre, polLast);
                         }
                         wait_gw();
                         {
@@ -610,7 +623,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         tmem_wait_st();
                     } else {
                         // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
-                        if (ln >= 0 && sn > 0) stash_get(stash, sn, p, c0, dpre);
+                        if (ln >= 0 && sn > 0) stash_get(stash, sn, p, c0, dpre, polLast);
                         if (s > 0) {
                             const float r = warp_colsum(v, lane);
                             vec_add(L + 1 + (s - 1), r, first);
