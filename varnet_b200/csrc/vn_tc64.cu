@@ -19,7 +19,7 @@ constexpr int W = 64;              // padded hidden width
 constexpr int NH = 4;              // neuron groups: warp w -> lane quarter w & 3, neuron group w >> 2
 constexpr int CPT = W / NH;        // neurons (columns) per thread
 constexpr int NT = 128 * NH;       // threads
-constexpr int FOLD = 16;           // tiles accumulated in the FP32 window slab before the FP64 fold
+constexpr int FOLD = 32;           // tiles accumulated in the FP32 window slab before the FP64 fold
 constexpr uint32_t SBO = 128;      // bytes between 8-row groups of a canonical K-major operand
 constexpr uint32_t W_LBO = 2048;   // weight images: 128 rows x 16 B per 4-wide K unit
 constexpr uint32_t G_LBO = 2064;   // weight-gradient operands (K = points): + 16 B pad, transposing stores hit 32 banks
@@ -39,12 +39,16 @@ struct Tc64Args { TileArgs t; const float* wimg; int* err; };
 struct SlabLayout { int vecOff, boutOff, psz, nkind; };
 __host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
     SlabLayout s;
-    s.vecOff = (L - 1) * (TP * W);                 // gw blocks of layers 1..L-1: [128 rows][64]
+    s.vecOff = (L - 1) * (TP * W);                 // gw blocks of layers 1..L-1: [64/4 column quads][128 rows][4] (see gw_slot)
     s.nkind = L + 1 + inpDim;                      // gb_0..gb_{L-1} | g(w_out) | gW_0 rows
     s.boutOff = s.vecOff + s.nkind * 4 * W;        // vec slots: [kind][lane quarter][64]
     s.psz = s.boutOff + 4;
     return s;
 }
+
+// slot of gW-block element (row r of the 128 accumulator rows, column j): quad-major, so that the 32 threads of a warp
+// (consecutive rows, the same column quad) touch 512 contiguous bytes per 16-byte reduction
+__host__ __device__ inline int gw_slot(int l, int r, int j) { return (l - 1) * (TP * W) + (((j >> 2) * TP + r) << 2) + (j & 3); }
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -605,13 +609,13 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                             // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
                             float g[CPT];
                             if (q < 2) drain_sum2(tq + COL_GW + c0, tq + COL_GW + 64 + c0, g); else get_plain(tq + COL_GW + c0, g);
-                            float* slot = part + (size_t)(l - 1) * (TP * W) + p * W + c0;
+                            float* slot = part + gw_slot(l, p, c0);
                             if (first && si == 0) {                            // first write of this window: overwrite
 #pragma unroll
-                                for (int u = 0; u < CPT / 4; ++u) __stcg(reinterpret_cast<float4*>(slot) + u, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                                for (int u = 0; u < CPT / 4; ++u) __stcg(reinterpret_cast<float4*>(slot) + u * TP, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
                             } else {
 #pragma unroll
-                                for (int u = 0; u < CPT / 4; ++u) red_add_v4(slot + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                                for (int u = 0; u < CPT / 4; ++u) red_add_v4(slot + 4 * u * TP, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
                             }
                         }
                         wait_mma();
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 if (firstFold) __stcg(part64 + idx, v); else part64[idx] += v;
             };
             for (int l = 1; l < L; ++l)
-                for (int jj = 0; jj < CPT; ++jj) put((l - 1) * (TP * W) + p * W + c0 + jj);
+                for (int jj = 0; jj < CPT; ++jj) put(gw_slot(l, p, c0 + jj));
             if ((lane & ((1 << COLSUM_SHIFT) - 1)) == 0)
                 for (int k = 0; k < sl.nkind; ++k) put(sl.vecOff + (k * 4 + q) * W + c0 + (lane >> COLSUM_SHIFT));
             if (h == 0 && lane == 0) put(sl.boutOff + q);
@@ -704,7 +708,7 @@ __global__ void tc64_reduce_kernel(NetDesc net, const double* __restrict__ slab,
     else if (l == net.L) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + (net.L * 4 + qq) * W + i; }
     else if (isBias) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + (l * 4 + qq) * W + j; }
     else if (l == 0) { for (int qq = 0; qq < 4; ++qq) slot[qq] = sl.vecOff + ((net.L + 1 + i) * 4 + qq) * W + j; }
-    else { nslot = 2; slot[0] = (l - 1) * (TP * W) + i * W + j; slot[1] = (l - 1) * (TP * W) + (64 + i) * W + j; }
+    else { nslot = 2; slot[0] = gw_slot(l, i, j); slot[1] = gw_slot(l, 64 + i, j); }
     double s = 0.0;
     for (int c = lane; c < nCta; c += 32)
         for (int k = 0; k < nslot; ++k) s += __ldcg(slab + (size_t)c * psz + slot[k]);
