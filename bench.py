@@ -90,8 +90,36 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.samples, self.stop_flag = None, [], False
+
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        # NVML polled every 5 ms from a thread (short timed regions at N=8 are over before nvidia-smi prints its first line)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nvml = (nv, h)
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -106,6 +134,14 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            bits = dict(sw_power_cap=0x4, hw_slowdown=0x8, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40)
+            reasons = sorted(k for k, b in bits.items() if any(r & b for _, _, r in self.samples))
+            sm = [x[0] for x in self.samples]
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.smax, reasons=reasons,
+                        power_w_max=max(x[1] for x in self.samples) if self.samples else None, samples=len(sm), source="nvml")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -237,15 +273,20 @@ def operator_config_steps(budget_s=4.0):
     return out
 
 
-def width_sweep(feed, meta, act, P_local, widths=(16, 128, 256), steps=2):
+def width_sweep(feed, meta, act, P_local, widths=(16, 64, 128, 256), steps=2):
     """BASELINE.json config 5 on the same mesh and feed: depth-4 tanh MLPs of other widths, a few steps each
-    (resident tables, CUDA events).  Widths above 64 run on the tensor-core class (tcgen05 3xTF32)."""
+    (resident tables, CUDA events).  Widths above 64 run on the tensor-core class (tcgen05 3xTF32); the width-64 leg
+    is the FP32-FMA tile kernel (VARNET_B200_CLASS=fma) for the FMA-vs-tensor-core crossover at the headline width —
+    the main line of this run is the same network on the tensor-core tile kernel."""
     import torch
     from varnet_b200 import workloads
     from varnet_b200.backend import TFNN
     out = {}
     for wdt in widths:
         lw = [wdt] * 4
+        prev = os.environ.get("VARNET_B200_CLASS")
+        if wdt == 64:
+            os.environ["VARNET_B200_CLASS"] = "fma"
         tf = TFNN(meta["dim"], meta["inpDim"], lw, "MLP", act, True, None, ["GPU:0"], None, meta["lossOpt"], "adam", 1e-3, seed=0)
         tw = tf.compTowers[0]
         fd = {getattr(tw, k): feed[k] for k in ("Input", "gcoef", "source", "N", "dNt", "biInput", "biLabel", "bDof",
@@ -260,7 +301,12 @@ def width_sweep(feed, meta, act, P_local, widths=(16, 128, 256), steps=2):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         flop_pt = workloads.algorithmic_flops_per_point(meta["inpDim"], meta["dim"], lw)
-        out["mlp4x%d" % wdt] = dict(quad_pts_per_sec=P_local / (ms * 1e-3), ms_per_step=ms, algorithmic_tflops=flop_pt * P_local / (ms * 1e-3) / 1e12,
+        if wdt == 64:
+            if prev is None:
+                os.environ.pop("VARNET_B200_CLASS", None)
+            else:
+                os.environ["VARNET_B200_CLASS"] = prev
+        out["mlp4x%d%s" % (wdt, "_fma" if wdt == 64 else "")] = dict(quad_pts_per_sec=P_local / (ms * 1e-3), ms_per_step=ms, algorithmic_tflops=flop_pt * P_local / (ms * 1e-3) / 1e12,
                                     loss=float(loss), kernel_family=tw.engine.kernel_info().split()[0])
         tf.sess.close()
     return out
