@@ -91,6 +91,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
         self.nvml, self.samples, self.stop_flag = None, [], False
+        self.period = 0.02          # NVML queries take driver locks: keep the polling light (and on rank 0 only)
 
     def _poll_nvml(self):
         nv, h = self.nvml
@@ -105,10 +106,10 @@ class ClockSampler:
                 self.samples.append((float(sm), pw, int(rs)))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period)
 
     def start(self):
-        # NVML polled every 5 ms from a thread (short timed regions at N=8 are over before nvidia-smi prints its first line)
+        # NVML polled from a thread (short timed regions at N=8 are over before nvidia-smi prints its first line)
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -384,7 +385,8 @@ def main():
     eng.profile_read()
     sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -392,7 +394,7 @@ def main():
         loss = step()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
     prof = eng.profile_read()
