@@ -409,6 +409,15 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             return valid ? __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row) : 0.f;
         };
 
+        // table columns of the CTA's next tile -> L2 (the table streams from HBM once; 24 lines of 128 B per tile)
+        if (!A.tfIndex && tile + (int)gridDim.x < A.ntiles) {
+            const int nc = A.nxTable + (S - 1) + (A.colT >= 0 ? 1 : 0) + (A.colS >= 0 ? 1 : 0);
+            if (tid < nc * 4) {
+                const float* nx = A.cols + (size_t)(A.colX + (tid >> 2)) * A.pstride + (size_t)(A.tile0 + tile + (int)gridDim.x) * TP + (tid & 3) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            }
+        }
+
         // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
         float d1[CPT];                                // act'(z_l) of the value stream, kept for the tangent streams
         {
