@@ -160,6 +160,13 @@ int vn_loss_grad_fed_f64(vn_engine* e, const double* Input, const double* gcoef,
                          int32_t detJvec, float out[4]);
 int vn_grad_buffer(vn_engine* e, void** device_ptr, int64_t* n_floats);
 int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]);
+/* lossVec[nb] = detJ_i R_i^2 (TFModel.py:668) as left by the last vn_loss / vn_loss_grad / vn_train_step of the
+ * current batch (the fused adjoint kernels write it themselves); synchronises. */
+int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb);
+/* Synchronises and reports a failure recorded by the asynchronous part of earlier calls (tensor-core classes: an
+ * expired mbarrier wait; the step that hit it published NaN and skipped its optimizer update).  Clears the flag.
+ * For callers that run steps without fetching the loss (vn_loss_grad(e, NULL), vn_train_step(e, lr, NULL)). */
+int vn_check_error(vn_engine* e);
 int vn_optimizer_step(vn_engine* e, float lr);
 int vn_train_step(vn_engine* e, float lr, float* loss_out);
 

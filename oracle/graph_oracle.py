@@ -118,7 +118,7 @@ def mlp_forward(theta, X, inpDim, layerWidth, act, ndir):
         if l == 0:
             dz = np.broadcast_to(Ws[0][:ndir, None, :], (ndir,) + z.shape)
         else:
-            dz = da @ Ws[l]
+            dz = (da.reshape(-1, da.shape[-1]) @ Ws[l]).reshape(ndir, z.shape[0], -1)    # one BLAS call for all tangents
         a = _act(z, act)
         da = _d1(a, act)[None] * dz
         A.append(a); dA.append(da)
@@ -240,7 +240,7 @@ def loss_and_grad(theta, feed, dim, inpDim, layerWidth, activation, timeDependen
     ubar = -lam * dNt if timeDependent else np.zeros(P, dtype=dtype)
     ukbar = lam[None, :] * gcoef.T                       # [dim,P]
     aL, daL = A[L - 1], dA[L - 1]
-    gW[L][:, 0] += aL.T @ ubar + np.einsum("kpj,kp->j", daL, ukbar)
+    gW[L][:, 0] += aL.T @ ubar + daL.reshape(-1, daL.shape[-1]).T @ ukbar.reshape(-1)
     gb[L][0] += ubar.sum()
     abar = ubar[:, None] * Ws[L][:, 0][None, :]
     dabar = ukbar[:, :, None] * Ws[L][:, 0][None, None, :]
@@ -248,12 +248,12 @@ def loss_and_grad(theta, feed, dim, inpDim, layerWidth, activation, timeDependen
         a, da = A[l], dA[l]
         d1 = _d1(a, act)
         dzbar = dabar * d1[None]
-        zbar = abar * d1 + _d2_over_d1(a, act) * np.einsum("kpj,kpj->pj", dabar, da)
+        zbar = abar * d1 + _d2_over_d1(a, act) * (dabar * da).sum(axis=0)
         if l > 0:
             ap, dap = A[l - 1], dA[l - 1]
-            gW[l] += ap.T @ zbar + np.einsum("kpi,kpj->ij", dap, dzbar)
+            gW[l] += ap.T @ zbar + dap.reshape(-1, dap.shape[-1]).T @ dzbar.reshape(-1, dzbar.shape[-1])
             abar = zbar @ Ws[l].T
-            dabar = dzbar @ Ws[l].T
+            dabar = (dzbar.reshape(-1, dzbar.shape[-1]) @ Ws[l].T).reshape(dzbar.shape[0], dzbar.shape[1], -1)
         else:
             gW[0] += X.T @ zbar
             gW[0][:dim, :] += dzbar.sum(axis=1)
@@ -384,3 +384,49 @@ def rmsprop_step(theta, g, ms, mom, lr=1e-3, decay=0.9, momentum=0.0, eps=1e-10)
     ms = decay * ms + (1 - decay) * g * g
     mom = momentum * mom + lr * g / np.sqrt(ms + eps)
     return theta - mom, ms, mom
+
+
+def loss_and_grad_chunked(theta, feed, chunk_tf=1024, workers=None, **kw):
+    """`loss_and_grad` on a large feed, evaluated chunk by chunk over the test functions.
+
+    The variational loss and its gradient are sums over test functions (TFModel.py:662-664) and the
+    boundary/initial term does not depend on them, so the feed is cut into ranges of `chunk_tf` test
+    functions: the first chunk carries the full loss weights, the others w = [0, 0, w2].  Chunks run on a
+    thread pool (NumPy releases the GIL in BLAS and ufunc loops) with BLAS itself limited to one thread per
+    call: OpenBLAS 0.3.30's pthreads pool gave wrong, run-to-run varying products when entered from eight
+    Python threads at once (seen here: gradient off by up to 2.6 relative).  Same dict as `loss_and_grad`."""
+    import concurrent.futures as cf
+    import os
+    from threadpoolctl import threadpool_limits
+    nb, integNum = [int(v) for v in feed["intShape"]]
+    w = np.asarray(feed["w"], dtype=np.float64).reshape(3)
+    detJvec = bool(feed.get("detJvec", False))
+
+    def piece(lo):
+        hi = min(nb, lo + chunk_tf)
+        f = dict(feed)
+        for k in ("Input", "gcoef", "source", "N", "dNt"):
+            v = feed.get(k)
+            if isinstance(v, np.ndarray) and v.dtype != object and v.shape[0] == nb * integNum:
+                f[k] = v[lo * integNum:hi * integNum]
+        if detJvec:
+            f["detJ"] = np.asarray(feed["detJ"]).reshape(-1)[lo:hi]
+        f["intShape"] = [hi - lo, integNum]
+        f["w"] = w if lo == 0 else np.array([0.0, 0.0, w[2]])
+        return loss_and_grad(theta, f, **kw)
+
+    starts = list(range(0, nb, chunk_tf))
+    workers = workers or min(len(starts), os.cpu_count() or 1)
+    if workers > 1:
+        with threadpool_limits(limits=1), cf.ThreadPoolExecutor(max_workers=workers) as ex:
+            outs = list(ex.map(piece, starts))
+    else:
+        outs = [piece(lo) for lo in starts]
+    first = outs[0]
+    varLoss = float(sum(o["varLoss"] for o in outs))
+    res = dict(BCloss=first["BCloss"], ICloss=first["ICloss"], varLoss=varLoss,
+               loss=w[0] * first["BCloss"] + w[1] * first["ICloss"] + w[2] * varLoss,
+               lossVec=np.concatenate([o["lossVec"] for o in outs]), R=np.concatenate([o["R"] for o in outs]),
+               Rabs=np.concatenate([o["Rabs"] for o in outs]), detJ=np.concatenate([o["detJ"] for o in outs]))
+    res["grad"] = None if first["grad"] is None else np.sum([o["grad"] for o in outs], axis=0)
+    return res

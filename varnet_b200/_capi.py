@@ -58,6 +58,8 @@ SIGNATURES = {
     "vn_loss_grad_fed_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32, _f32p]),
     "vn_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "vn_get_grad": (C.c_int, [_vp, _f32p, _i64, _f32p]),
+    "vn_get_lossvec": (C.c_int, [_vp, _f32p, _i64]),
+    "vn_check_error": (C.c_int, [_vp]),
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
     "vn_eval_f32": (C.c_int, [_vp, _f32p, _i64, _f32p]),
@@ -330,6 +332,15 @@ class Engine:
         if fetch:
             return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3])
         return None
+
+    def get_lossvec(self):
+        """lossVec of the last loss / loss_grad / train_step call (written by the kernel that ran)."""
+        lv = np.empty(self.nb, dtype=np.float32)
+        self._check(self.lib.vn_get_lossvec(self._h, _ptr(lv, C.c_float), lv.size))
+        return lv
+
+    def check_error(self):
+        self._check(self.lib.vn_check_error(self._h))
 
     def grad_buffer(self):
         p = _vp(); n = _i64()

@@ -159,7 +159,9 @@ class Session:
             sig = (id(feed), tuple(map(id, feed.values())))
             if sig == getattr(self, "_last_sig", None):
                 return None
-            self._last_sig = sig
+            self._last_sig = None                 # set again only after every upload below succeeded
+        else:
+            sig = None
         by_tower = {}
         for key, val in (feed or {}).items():
             if isinstance(key, Node) and key.tower is not None:
@@ -185,6 +187,9 @@ class Session:
                         else:
                             eng.upload_points(*args)
                         tok["points"] = t
+                        # the token is built from id()/data pointers: keep the arrays alive while it is cached, so a
+                        # freed array's id and buffer cannot be recycled by a new feed that would then look unchanged
+                        tok["points_refs"] = tuple(fd.get(k) for k in names)
                         tok.pop("view", None)
                         self._o.uploads += 1
             if need_bic and "biInput" in fd:
@@ -193,6 +198,7 @@ class Session:
                 if tok.get("bic") != t or not self._o.feed_cache:
                     eng.upload_bic(fd["biInput"], fd["biLabel"], int(fd["bDof"]), float(fd["biDimVal"]))
                     tok["bic"] = t
+                    tok["bic_refs"] = tuple(fd.get(k) for k in names)
                     self._o.uploads += 1
             if "w" in fd:
                 w = np.asarray(fd["w"], dtype=np.float64).reshape(3)
@@ -200,6 +206,9 @@ class Session:
                 if tok.get("w") != t:
                     eng.set_weights(w)
                     tok["w"] = t
+        if sig is not None:
+            self._last_sig = sig
+            self._last_feed_refs = (feed, tuple(feed.values()))     # same reason: ids in `sig` stay unique while cached
         return by_tower
 
     # -- device-resident tables: the feed carries TableViews (lazy gathers) instead of gathered copies
@@ -233,6 +242,7 @@ class Session:
             else:
                 slot = 1 + len(slots)                                   # slot 0 is reserved for plain feeds
         slots[key] = slot
+        tw.__dict__.setdefault("_slot_refs", {})[slot] = tuple(base(k) for k in ("Input", "gcoef", "source", "N", "dNt"))   # pins the ids in `key`
         if tok.get("view_slot") != slot or fresh:
             eng.select_table(slot)
             tok["view_slot"] = slot
@@ -352,9 +362,10 @@ class Session:
             return None if single else out
 
         if "model" in names or "residual" in names:
-            tw0 = o.compTowers[0]
-            if not tw0.local:
-                raise RuntimeError("evaluation nodes live on tower 0; call from the rank that owns it")
+            # the weights are shared by all towers (TFModel.py:180) and every engine holds the same copy, so the
+            # evaluation nodes run on this process's own tower: under torchrun every rank gets the same values
+            # without a collective (residual-driven resampling calls this on all ranks, VarNet.py:1696-1966)
+            tw0 = self._local_towers()[0]
             fd = {k.name: v for k, v in (feed_dict or {}).items() if isinstance(k, Node)}
             X = fd["Input"]
             u = res = None
@@ -488,7 +499,8 @@ class TFNN:
         self.controller = self.processors[0] if controller is None else controller
         self.lossOpt, self.optimizer_name, self.learning_rate = lossOpt, optimizer_name, learning_rate
         self.uploads, self.step_count = 0, 0
-        # True: a feed array is uploaded only when it is replaced by a new object; False: every
+        # True: a feed array is uploaded only when it is replaced by a new object (in-place edits of a fed array are NOT
+        # seen: replace the dict entry, as updateDictFields / shuffleTrainData do); False: every
         # sess.run re-uploads its feeds, like the reference's per-step feed (VarNetUtility.py:1044)
         self.feed_cache = True
         self.max_resident_tables = 64       # LRU bound on device-resident point tables per tower

@@ -112,9 +112,10 @@ __device__ __forceinline__ void adam_update(float* theta, float* m, float* v, in
     theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 __global__ void vn_adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
-                               const float* __restrict__ g, int n, float lr, const double* __restrict__ corr) {
+                               const float* __restrict__ g, int n, float lr, const double* __restrict__ corr,
+                               const int* __restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (err && *err)) return;         // poisoned step (expired mbarrier wait): keep the weights
     adam_update(theta, m, v, i, g[i], lr, corr);
 }
 // TF-1.x RMSProp (decay .9, momentum 0, eps 1e-10, ms initialised to ones): ms = .9 ms + .1 g^2;
@@ -125,9 +126,9 @@ __device__ __forceinline__ void rmsprop_update(float* theta, float* ms, int i, f
     theta[i] -= lr * gi / sqrtf(s + 1e-10f);
 }
 __global__ void vn_rmsprop_kernel(float* __restrict__ theta, float* __restrict__ ms, const float* __restrict__ g,
-                                  int n, float lr) {
+                                  int n, float lr, const int* __restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (err && *err)) return;
     rmsprop_update(theta, ms, i, g[i], lr);
 }
 __device__ __forceinline__ void advance_step(long long* step, double* corr) {
@@ -136,7 +137,7 @@ __device__ __forceinline__ void advance_step(long long* step, double* corr) {
     const double tn = (double)(t + 1);     // bias correction of the NEXT step
     corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
 }
-__global__ void vn_advance_kernel(long long* step, double* corr) { advance_step(step, corr); }
+__global__ void vn_advance_kernel(long long* step, double* corr, const int* err) { if (!(err && *err)) advance_step(step, corr); }
 
 // Blocks [0, gridDim.x-1): one WARP per flat parameter sums the per-CTA FP64 slabs: lane c takes slabs
 // c, c+32, ... in order and the lanes are combined by a fixed xor tree (deterministic replacement for
@@ -146,6 +147,9 @@ __global__ void vn_advance_kernel(long long* step, double* corr) { advance_step(
 __global__ void vn_finalize_kernel(FinalArgs A) {
     const NetDesc& net = A.net;
     const PartLayout& pl = A.pl;
+    // a tensor-core kernel of this step gave up on an mbarrier wait: its partial slabs are stale.  Publish NaN and leave
+    // the weights alone, so the caller sees the failure in the very step it happened (the host also reads the flag).
+    const bool bad = A.err != nullptr && *reinterpret_cast<const volatile int*>(A.err) != 0;
     if (blockIdx.x + 1 < gridDim.x) {
         const int lane = threadIdx.x & 31;
         const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -183,10 +187,11 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
             if (A.flat) s += A.flat[idx];
-            const float g = (float)s;
+            const float g = bad ? __int_as_float(0x7fc00000) : (float)s;
             A.gbuf[idx] = g;
             // single-GPU training step: apply_gradients fused into the reduction (TFModel.py:313)
-            if (A.fuseOpt == 1) adam_update(A.theta, A.m, A.v, idx, g, A.lr, A.corr);
+            if (bad) { }
+            else if (A.fuseOpt == 1) adam_update(A.theta, A.m, A.v, idx, g, A.lr, A.corr);
             else if (A.fuseOpt == 2) rmsprop_update(A.theta, A.v, idx, g, A.lr);
         }
         }
@@ -206,7 +211,7 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         const float varLoss = A.detJvec ? (float)segTot : A.detJ[0] * (float)segTot;   // detJ moved outside the sum (:664)
         const float bCs = (float)(sb / (double)A.bDof);                                  // 0/0 -> nan like tf.reduce_mean
         const float iCs = A.timeDependent ? (float)(si / (double)(A.nbi - A.bDof)) : 0.f;
-        const float loss = A.wts[0] * bCs + A.wts[1] * iCs + A.wts[2] * varLoss;
+        const float loss = bad ? __int_as_float(0x7fc00000) : A.wts[0] * bCs + A.wts[1] * iCs + A.wts[2] * varLoss;
         float* o = A.gbuf + net.nparam;
         o[0] = loss; o[1] = bCs; o[2] = iCs; o[3] = varLoss;
     }
@@ -219,7 +224,7 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             __threadfence();
             const unsigned int t = atomicAdd(A.ticket, 1u);
             if (t == gridDim.x - 1) {
-                advance_step(A.step, A.corr);
+                if (!bad) advance_step(A.step, A.corr);
                 *A.ticket = 0u;
             }
         }
@@ -304,17 +309,20 @@ __global__ void vn_cast_kernel(const T* __restrict__ in, float* __restrict__ out
 
 // ------------------------------------------------------------------ engine
 enum { PK_VAR_FWD = 0, PK_SEG = 1, PK_VAR_ADJ = 2, PK_BIC = 3, PK_FINAL = 4, PK_OPT = 5 };
+// Bumped whenever a live device buffer is freed and re-allocated: captured step graphs bake device pointers in, so a graph
+// captured in an older epoch must not be replayed (vn_train_step compares PointSet::graphEpoch with it).
+static long long g_reallocEpoch = 0;
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
     cudaError_t ensure(size_t need) {
         if (need <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) { cudaFree(p); ++g_reallocEpoch; }
         p = nullptr; bytes = 0;
         cudaError_t e = cudaMalloc(&p, need);
         if (e == cudaSuccess) bytes = need;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) { cudaFree(p); ++g_reallocEpoch; } p = nullptr; bytes = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -325,6 +333,7 @@ struct PointSet {
     int colX = 0, colG = 0, colT = -1, colS = -1, ncols = 0, nx = 0;
     bool loaded = false;
     cudaGraphExec_t graph = nullptr; float graphLr = -1.f; int graphLaunches = 0; unsigned int graphNb = 0; bool graphIndexed = false;
+    long long graphEpoch = -1;   // g_reallocEpoch at capture time
 };
 
 struct vn_engine {
@@ -1069,6 +1078,7 @@ static int run_loss_tc(vn_engine* e, bool needGrad) {
     f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
     f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
     f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = 0;
+    f.err = e->tcErr.as<int>();
     vn_finalize_kernel<<<1, 128, 0, st>>>(f);         // loss scalars only
     CK(cudaGetLastError());
     e->launches++;
@@ -1199,6 +1209,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
         f.cj = e->cj.as<float>(); f.nbi = e->nbi; f.bDof = e->bDof; f.timeDependent = c.timeDependent;
         f.wts = e->wts.as<float>(); f.gbuf = e->gbuf.as<float>(); f.needGrad = needGrad ? 1 : 0;
+        f.err = e->tc64 ? e->tcErr.as<int>() : nullptr;
         if (needGrad && fuseLr >= 0.f) {        // vn_train_step on one GPU: optimizer update and step advance inside the reduction
             f.fuseOpt = c.optimizer == VN_OPT_ADAM ? 1 : 2; f.lr = fuseLr;
             f.theta = e->theta.as<float>(); f.m = e->m.as<float>(); f.v = e->v.as<float>();
@@ -1288,6 +1299,26 @@ extern "C" int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]) {
     CK(cudaStreamSynchronize(e->stream));
     return VN_OK;
 }
+extern "C" int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb) {
+    if (!e || !lossVec) return fail(VN_E_INVALID, "null argument");
+    if (nb != (int64_t)e->nb || !e->lossVec.p) return fail(VN_E_STATE, "lossVec holds %u values (asked for %lld); call vn_loss / vn_loss_grad first", e->nb, (long long)nb);
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(lossVec, e->lossVec.p, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return VN_OK;
+}
+extern "C" int vn_check_error(vn_engine* e) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    int tcErr = 0;
+    if (e->tcErr.p) CK(cudaMemcpyAsync(&tcErr, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (tcErr) {
+        cudaMemsetAsync(e->tcErr.p, 0, sizeof(int), e->stream);
+        return fail(VN_E_CUDA, "tensor-core pipeline: an mbarrier wait expired (results since the last check are invalid)");
+    }
+    return VN_OK;
+}
 extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
@@ -1296,12 +1327,12 @@ extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
     ProfScope ps(e, PK_OPT);
     if (e->cfg.optimizer == VN_OPT_ADAM)
         vn_adam_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->m.as<float>(), e->v.as<float>(),
-                                                                e->gbuf.as<float>(), np, lr, e->corrbuf.as<double>());
+                                                                e->gbuf.as<float>(), np, lr, e->corrbuf.as<double>(), e->tcErr.as<int>());
     else
         vn_rmsprop_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->v.as<float>(),
-                                                                   e->gbuf.as<float>(), np, lr);
+                                                                   e->gbuf.as<float>(), np, lr, e->tcErr.as<int>());
     CK(cudaGetLastError());
-    vn_advance_kernel<<<1, 1, 0, e->stream>>>(e->stepbuf.as<long long>(), e->corrbuf.as<double>());
+    vn_advance_kernel<<<1, 1, 0, e->stream>>>(e->stepbuf.as<long long>(), e->corrbuf.as<double>(), e->tcErr.as<int>());
     CK(cudaGetLastError());
     e->launches += 2;
     return VN_OK;
@@ -1322,7 +1353,8 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
     PointSet* t = e->t;
     // a captured step stays valid while the table, the batch size / kind and lr are unchanged (the index list,
     // the extra inputs and the loss weights are read from device memory at replay time)
-    if (useGraph && t->graph && t->graphLr == lr && t->graphNb == e->nb && t->graphIndexed == e->indexed) {
+    if (useGraph && t->graph && t->graphLr == lr && t->graphNb == e->nb && t->graphIndexed == e->indexed &&
+        t->graphEpoch == g_reallocEpoch) {
         CK(cudaGraphLaunch(t->graph, e->stream));
         e->launches += t->graphLaunches;
     } else if (useGraph) {
@@ -1350,7 +1382,7 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
         } else {
             cudaGraphDestroy(g);
             t->graphLr = lr; t->graphLaunches = (int)(e->launches - l0);
-            t->graphNb = e->nb; t->graphIndexed = e->indexed;
+            t->graphNb = e->nb; t->graphIndexed = e->indexed; t->graphEpoch = g_reallocEpoch;
             CK(cudaGraphLaunch(t->graph, e->stream));
         }
     } else {
@@ -1358,8 +1390,12 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
         if (rc) return rc;
     }
     if (loss_out) {
-        CK(cudaMemcpyAsync(loss_out, e->gbuf.as<float>() + e->net.nparam, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
+        // the loss read is also where an expired tensor-core barrier wait of this (or an earlier unfetched) step surfaces:
+        // the reduction kernel published NaN and skipped the optimizer update, here the caller gets VN_E_CUDA
+        float sc[4];
+        int rc = read_scalars(e, sc);
+        *loss_out = sc[0];
+        if (rc) return rc;
     }
     return VN_OK;
 }

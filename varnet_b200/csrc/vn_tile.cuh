@@ -873,5 +873,6 @@ struct FinalArgs {
     float* theta; float* m; float* v;
     long long* step; double* corr;          // device step counter and Adam bias-correction factor (advanced by the last block)
     unsigned int* ticket;                   // zero-initialised block counter
+    const int* err;                         // tensor-core classes: non-zero = an mbarrier wait expired in this step (or nullptr)
 };
 __global__ void vn_finalize_kernel(FinalArgs A);

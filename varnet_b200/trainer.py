@@ -25,10 +25,38 @@ from .hostutil import (is_empty, is_none, is_number, l2_err, pair_rows, rejectio
 from .tables import FIXData, ManageTrainData, TableView
 
 
+def _rank():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank()
+    except Exception:
+        pass
+    return 0
+
+
+def sync_numpy_rng():
+    """Under torchrun every rank builds the same tables and slices its own tower out of them, so the `np.random`
+    draws of the 'random' / 'optimal' sampling schemes must agree across ranks: rank 0 draws a seed from its own
+    generator, broadcasts it, and every rank re-seeds with it.  No-op in a single process."""
+    try:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+    except Exception:
+        return
+    box = [int(np.random.randint(0, 2 ** 31 - 1))]
+    dist.broadcast_object_list(box, src=0)
+    np.random.seed(box[0])
+
+
 class TrainLog:
-    """Minimal text logger standing in for `TrainResult` (VarNetUtility.py:1149-1757)."""
+    """Minimal text logger standing in for `TrainResult` (VarNetUtility.py:1149-1757).  Under torchrun only
+    rank 0 writes the case file (the ranks share `folderpath`)."""
 
     def __init__(self, folderpath, verbose=True, saveFreq=100):
+        self._writer = _rank() == 0
+        verbose = verbose and self._writer
         self.folderpath, self.verbose, self.saveFreq = folderpath, verbose, saveFreq
         self.loss, self.lossComp, self.residual, self.error, self.inpIter = [], [], [], [], []
         self.trainWeight = None
@@ -37,6 +65,8 @@ class TrainLog:
         self._path = os.path.join(folderpath, 'caseData.txt')
 
     def writeCase(self, string):
+        if not self._writer:
+            return
         with open(self._path, 'a') as f:
             f.write(string + '\n')
 
@@ -49,6 +79,8 @@ class TrainLog:
                  'parameters: %d  processors: %s  optimizer: %s  learning rate: %g' %
                  (tf.model.count_params(), tf.processors, tf.optimizer_name, tf.learning_rate),
                  'training arguments: %s' % {k: v for k, v in argDict.items() if k != 'self'}]
+        if not self._writer:
+            return
         with open(self._path, 'w') as f:
             f.write('\n'.join(lines) + '\n')
 
@@ -118,6 +150,8 @@ class VarNet:
     def trainingPoints(self, smpScheme='uniform', frac=0.5, addTrainPts=True, suppFactor=1.0):
         """Quadrature-point coordinates Input[nT, feDim]: centre + h*delta, space index slow, time
         index fast, Gauss index fastest (VarNet.py:576-586)."""
+        if smpScheme != 'uniform':
+            sync_numpy_rng()                  # identical draws on every rank (each slices its tower from the same tables)
         if smpScheme == 'optimal':
             return self.optTrainPoints(frac, addTrainPts, suppFactor)
         rfrac = frac if smpScheme == 'random' else 0.
@@ -212,7 +246,7 @@ class VarNet:
         mesh = domain.getMesh([math.ceil(keep * d) for d in self.discNum], bDisc2)
         uniform_part, biDof2 = self.biTrainPoints(mesh, t_coord)
         biDof1 = [math.ceil(frac * b) for b in biDof] if addTrainPts else list(np.array(biDof) - np.array(biDof2))
-        tw = tf.compTowers[0]
+        tw = next(t for t in tf.compTowers if t.local)          # weights are replicated: every rank evaluates locally
 
         def resfun(rows=None):
             rows = fd.uniform_biInput if rows is None else rows
