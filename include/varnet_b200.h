@@ -190,6 +190,10 @@ int vn_profile_enable(vn_engine* e, int on);
 int vn_profile_read(vn_engine* e, double ms[VN_PROF_SLOTS], int64_t counts[VN_PROF_SLOTS]);
 int vn_fp32_peak_tflops(int device, int reps, double* tflops);
 
+/* Development aid: cycle counters of the phases of the width-64 tensor-core tile kernel (CTA 0, one thread) for the
+ * last launch; filled only when the environment variable VARNET_B200_TC64_TIMING is set.  See scripts/tc64_phases.py. */
+int vn_debug_tc64_timing(int64_t out[16]);
+
 /* ---- introspection for tests / bench --------------------------------------- */
 int vn_kernel_info(const vn_engine* e, char* buf, size_t buflen);   /* kernel family, tile, smem */
 int64_t vn_launch_count(const vn_engine* e);                         /* kernels launched so far */

@@ -36,6 +36,23 @@ def check_against_oracle(eng, ref, feed, inpDim, lw, td):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES[:4], ids=[str(c[2]) + c[3] + ("_d%d" % c[0]) for c in CASES[:4]])
+def test_tile64_v2_schedule_matches_oracle(case):
+    """The warp-specialised, software-pipelined schedule of the same kernel (VARNET_B200_TC64=v2: issuing warp, mbarrier
+    hand-offs, cross-products-first single accumulator) holds the same 1e-5 bar; run in a subprocess because the schedule is
+    chosen once per process."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import tests.test_gpu_tc64 as t\n"
+            "t.test_tile64_tensor_core_kernel_matches_oracle(%r)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), case))
+    env = dict(os.environ, VARNET_B200_TC64="v2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES, ids=[str(c[2]) + c[3] + ("_d%d" % c[0]) for c in CASES])
 def test_tile64_tensor_core_kernel_matches_oracle(case):
     dim, inpDim, lw, act, td, src, iw, dvec, nb, integNum, nbi, bDof = case

@@ -60,6 +60,7 @@ SIGNATURES = {
     "vn_get_grad": (C.c_int, [_vp, _f32p, _i64, _f32p]),
     "vn_get_lossvec": (C.c_int, [_vp, _f32p, _i64]),
     "vn_check_error": (C.c_int, [_vp]),
+    "vn_debug_tc64_timing": (C.c_int, [C.POINTER(_i64)]),
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
     "vn_eval_f32": (C.c_int, [_vp, _f32p, _i64, _f32p]),

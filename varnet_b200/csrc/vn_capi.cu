@@ -516,7 +516,14 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
         const bool wantTc64 = !(forceCls && !strcmp(forceCls, "fma"));
         if ((e->wclass == 64 || e->wclass == 164) && wantTc64 && vn_tc64_supported(e->net, e->S)) {
             vn_tc64_geometry(e->net, e->S, &e->tc64Geom);
-            if (e->tc64Geom.smemBytes <= prop.sharedMemPerBlockOptin && vn_tc64_prepare(e->S, act, e->tc64Geom.smemBytes) == cudaSuccess) {
+            // no silent fall-back to the 2.5x slower FMA tiles: a build whose tensor-core kernel cannot be configured is an error
+            if (e->tc64Geom.smemBytes > prop.sharedMemPerBlockOptin) {
+                const size_t need = e->tc64Geom.smemBytes; delete e;
+                return fail(VN_E_UNSUPPORTED, "width-64 tensor-core tile kernel needs %zu B of shared memory per CTA (set VARNET_B200_CLASS=fma for the FMA tiles)", need);
+            }
+            cudaError_t ce64 = vn_tc64_prepare(e->S, act, e->tc64Geom.smemBytes);
+            if (ce64 != cudaSuccess) { delete e; return fail(VN_E_CUDA, "width-64 tensor-core tile kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(ce64)); }
+            {
                 e->tc64 = true;
                 CK(e->tc64Img.ensure((size_t)e->tc64Geom.nImages * 8192 * sizeof(float)));
                 CK(e->tc64Flat.ensure((size_t)e->net.nparam * sizeof(double)));
@@ -1306,6 +1313,12 @@ extern "C" int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb) {
     CK(cudaMemcpyAsync(lossVec, e->lossVec.p, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return VN_OK;
+}
+extern "C" int vn_debug_tc64_timing(int64_t out[16]) {
+    long long t[16] = {0};
+    const int ok = vn_tc64_read_timing(t);
+    for (int i = 0; i < 16; ++i) out[i] = t[i];
+    return ok ? VN_OK : VN_E_STATE;
 }
 extern "C" int vn_check_error(vn_engine* e) {
     if (!e) return fail(VN_E_INVALID, "null engine");

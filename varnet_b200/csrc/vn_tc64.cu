@@ -10,6 +10,8 @@
 // 2^-11-sized cross products go to their own columns; the sets are summed in FP32 round-to-nearest by the drain.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "vn_tc64.h"
 
 namespace {
@@ -34,7 +36,7 @@ constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
 
-struct Tc64Args { TileArgs t; const float* wimg; int* err; };
+struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING)
 
 struct SlabLayout { int vecOff, boutOff, psz, nkind; };
 __host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
@@ -80,9 +82,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {      // bounded: a lost commit must not hang the GPU
     uint32_t done = 0;
-    for (int spin = 0; spin < (1 << 20) && !done; ++spin)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    long long t0 = 0;
+    for (int spin = 0; !done; ++spin) {
+        // suspend-time hint (ns): a waiting warp sleeps in the barrier unit instead of spinning through the issue slots of
+        // the three working warps that share its scheduler; it is woken as soon as the phase completes
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (!done && (spin & 63) == 63) {                      // ~0.1 s at 2 GHz, measured on the clock (a try_wait may itself suspend)
+            const long long t = clock64();
+            if (t0 == 0) t0 = t; else if (t - t0 > 200000000ll) break;
+        }
+    }
     return done != 0;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
@@ -684,6 +694,570 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ==================================================================================================================
+// v2: warp-specialised, software-pipelined version of the tile kernel (round 2).
+//
+//  * 17 warps: 16 worker warps (thread = point x 16 neurons, as above) + ONE issuing warp.  The workers never execute
+//    MMA-issue code and there is no __syncthreads on the issue path: workers -> issuer hand-offs are mbarriers with one
+//    arrival per worker warp, issuer -> workers hand-offs are tcgen05.commit -> mbarrier.
+//  * every FP32 product still comes from three TF32 MMAs, but all three now accumulate into ONE 64-column accumulator,
+//    cross products first: while only the 2^-11-sized terms have been added the accumulator is small and the tensor
+//    core's truncating accumulate costs nothing; the chain of full-size hi*hi additions stays at 8 MMAs.  No separate
+//    cross-product columns, no drain-and-add fix-up: a forward step reads 16 columns once, and the adjoint layer GEMM
+//    leaves abar_{l-1,s} parked in tensor memory in its final form.
+//  * forward: two accumulators ping-pong, so the GEMM of step k+1 runs under the epilogue of step k.
+//  * adjoint: per step the weight-gradient GEMM is issued first, the layer GEMM second.  While the tensor core runs
+//    step k the workers already compute zbar of step k+1 from the parked abar (under the weight-gradient GEMM), then
+//    drain the weight-gradient accumulator and rewrite the transposed shared-memory operands (under the layer GEMM; the
+//    operand pair is 129 KB, a second one does not fit), and store the tensor-memory operand once the layer GEMM is done.
+//  * the weight images are brought in by the issuing warp with one 32 KB bulk copy (cp.async.bulk -> mbarrier) each;
+//    the inputs and integrand coefficients of the CTA's next tile are prefetched into shared memory with cp.async.
+//  * g(w_out) needs sum_s a_{L-1,s} * coef_s per point: it is accumulated in registers by the epilogues of the last
+//    layer and scaled by lambda once R_i is known, instead of re-reading the three operands from tensor memory.
+//
+// Tensor-memory columns.  Forward: operand of stream s [128 s, 128 s + 128) (hi | lo), accumulators [384,448), [448,512).
+// Adjoint: operand [0,128), parked abar_{l-1,s} [128 + 64 s, +64), weight-gradient accumulator [384,512).
+namespace v2 {
+
+constexpr int NWORK = 512;                         // worker threads (16 warps)
+constexpr int NT2 = NWORK + 128;                   // + the issuing warp's warpgroup (registers are allocated per 4 warps: a lone
+                                                   //   17th warp would cost as much as four and cap the kernel at 96 registers)
+constexpr int NXIN = 12;                           // prefetched per-point values: <= 8 inputs | dNt | gcoef_0..1 | source*N
+constexpr int OFF2_WST = 0;
+constexpr int OFF2_G = 2 * WIMG_BYTES;             // GA | GB (64.5 KB each: hi and lo rows; no room for a second pair)
+constexpr int OFF2_PAR = OFF2_G + 2 * G_BYTES;
+static_assert(OFF2_PAR + (1152 + NH * 384 + 768 + 2 * NXIN * TP) * 4 + 160 + 128 <= 232448, "shared memory of the v2 tile kernel");
+constexpr int PAR2_FLOATS = 1152 + NH * 384 + 768 + 2 * NXIN * TP;   // v1 block | lam[128] | xin[2][NXIN][128]
+constexpr int OFF2_BAR = OFF2_PAR + PAR2_FLOATS * 4;
+constexpr int OFF2_TIM = OFF2_BAR + 160;             // 16 x int64 phase timers of thread 0 (debug)
+constexpr int SMEM2_BYTES = OFF2_TIM + 128;
+constexpr uint32_t COL2_ACC = 384;                 // forward accumulators: + 64 (k & 1)
+constexpr uint32_t COL2_CROSS = 320;               // adjoint: second-order term sum_k abar_k (.) adot_k of the running layer (FP32)
+enum { B_STEPF = 0, B_STEPA = 2, B_ACC = 4, B_LAYER = 6, B_GW = 7, B_WFULL = 8, B_WFREE = 10, NBAR = 12 };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(NT2, 1) tc64_var_kernel_v2(const __grid_constant__ Tc64Args K) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TileArgs& A = K.t;
+    const NetDesc& net = A.net;
+    const int L = net.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    float* par = reinterpret_cast<float*>(smem + OFF2_PAR);
+    float* W0s = par;                               // [8][64]
+    float* bs = par + 512;                          // [8][64]
+    float* wout = par + 1024;                       // [64]
+    float* misc = par + 1088;                       // [0] = b_out
+    float* usP = par + 1152;                        // [NH][3][128] output-layer partial dots of the neuron groups
+    float* us = usP + NH * 384;                     // [3][128] u_s, then the adjoint seeds
+    float* Ish = us + 384;                          // [128]
+    float* Rsh = Ish + 128;                         // [128]
+    float* lamS = Rsh + 128;                        // [128]
+    float* xin = lamS + 128;                        // [2][NXIN][128]
+    const uint32_t bar0 = smem_u32(smem + OFF2_BAR);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF2_BAR + 8 * NBAR);
+
+    if (*reinterpret_cast<volatile int*>(K.err)) return;
+    for (int i = tid; i < PAR2_FLOATS; i += NT2) par[i] = 0.f;
+    __syncthreads();
+    {
+        const float* __restrict__ th = A.theta;
+        const int w0 = net.width[0];
+        for (int idx = tid; idx < net.inpDim * w0; idx += NT2) { const int c = idx / w0, j = idx - c * w0; W0s[c * W + j] = th[net.woff[0] + idx]; }
+        for (int l = 0; l < L; ++l)
+            for (int j = tid; j < net.width[l]; j += NT2) bs[l * W + j] = th[net.boff[l] + j];
+        for (int j = tid; j < net.width[L - 1]; j += NT2) wout[j] = th[net.woff[L] + j];
+        if (tid == 0) {
+            misc[0] = th[net.boff[L]];
+            for (int i = 0; i < NBAR; ++i) {
+                const bool fromWorkers = i < B_ACC;
+                mbar_init(BAR(i), fromWorkers ? 16u : 1u);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tslot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    const int nfs = (L - 1) * S;                    // MMA steps of a sweep: (layer 1..L-1) x streams
+    const int nImg = 2 * (L - 1);
+    bool ok = true;
+
+    if (warp >= NWORK / 32) {
+        // ============================================================ issuing warp (one elected lane) + 3 idle warps of its warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");         // hand the registers to the workers
+        if (warp == NWORK / 32 && elect_one()) {
+            uint32_t phase = 0;                     // bit i: phase parity this thread waits for next on barrier i
+            int nLoaded = 0, nUsed = 0, rLoad = 0;  // weight images of the whole launch: loaded / consumed (stage = n & 1); rLoad = nLoaded % nImg
+            const int nTotal = ((A.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * nImg;
+            auto wait = [&](int i) { if (ok) ok = mbar_wait(BAR(i), (phase >> i) & 1u); phase ^= 1u << i; };
+            auto load_next = [&]() {                // image nLoaded -> stage nLoaded & 1 (its previous user: image nLoaded - 2)
+                if (nLoaded >= nTotal) return;
+                const int st = nLoaded & 1;
+                if (nLoaded >= 2) wait(B_WFREE + st);
+                const int img = rLoad < L - 1 ? 2 * rLoad : 2 * (2 * L - 3 - rLoad) + 1;     // forward layers 1..L-1, then adjoint layers L-1..1
+                mbar_expect_tx(BAR(B_WFULL + st), WIMG_BYTES);
+                bulk_g2s(smem_u32(smem + OFF2_WST + st * WIMG_BYTES), K.wimg + (size_t)img * WIMG_FLOATS, WIMG_BYTES, BAR(B_WFULL + st));
+                ++nLoaded;
+                if (++rLoad == nImg) rLoad = 0;
+            };
+            auto acquire = [&]() -> uint32_t {      // image nUsed is in shared memory
+                const int st = nUsed & 1;
+                wait(B_WFULL + st);
+                ++nUsed;
+                return smem_u32(smem + OFF2_WST + st * WIMG_BYTES);
+            };
+            // d (64 columns) = A x W as 3xTF32, cross products first: lo*hi, hi*lo, then the chain of 8 hi*hi
+            auto issue_layer = [&](uint32_t aHi, uint32_t wst, uint32_t d) {
+                const uint32_t aLo = aHi + 64;
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) mma_ts(d, aLo + kb * 8, make_desc(wst + kb * 2 * W_LBO, W_LBO), IDesc<64>::v, kb ? 1u : 0u);
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) mma_ts(d, aHi + kb * 8, make_desc(wst + 8 * SBO + kb * 2 * W_LBO, W_LBO), IDesc<64>::v, 1u);
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) mma_ts(d, aHi + kb * 8, make_desc(wst + kb * 2 * W_LBO, W_LBO), IDesc<64>::v, 1u);
+            };
+            load_next();
+            for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+                // ---- forward: event j = 0: layer 0 done; j >= 1: epilogue of step j-1 done.  Step k needs event max(0, k-1).
+                uint32_t wst = 0;
+                for (int j = 0; j <= nfs; ++j) {
+                    wait(B_STEPF + (j & 1));
+                    tc_fence_after();
+                    const int k0 = j == 0 ? 0 : j + 1, k1 = j == 0 ? 1 : j + 1;
+                    for (int k = k0; k <= k1 && k < nfs; ++k) {
+                        const int s = k % S;
+                        if (s == 0) wst = acquire();
+                        issue_layer(tmem + 128 * s, wst, tmem + COL2_ACC + 64 * (k & 1));
+                        mma_commit(BAR(B_ACC + (k & 1)));
+                        if (s == S - 1) mma_commit(BAR(B_WFREE + ((nUsed - 1) & 1)));
+                        if (s == 0) load_next();
+                    }
+                }
+                // ---- adjoint: step k = (layer L-1-k/S, stream order 1..S-1, 0).  The workers have drained the weight-gradient
+                // accumulator of step k-1 and rewritten both operand sets before they signal step k.
+                for (int k = 0; k < nfs; ++k) {
+                    const int si = k % S, s = (si < S - 1) ? si + 1 : 0;
+                    wait(B_STEPA + (k & 1));
+                    tc_fence_after();
+                    const uint32_t ga = smem_u32(smem + OFF2_G), gb = ga + G_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < 16; ++kb)
+                        mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
+                    mma_commit(BAR(B_GW));
+                    if (si == 0) wst = acquire();
+                    issue_layer(tmem + COL_OP, wst, tmem + COL_PARK + 64 * s);
+                    mma_commit(BAR(B_LAYER));
+                    if (si == S - 1) mma_commit(BAR(B_WFREE + ((nUsed - 1) & 1)));
+                    if (si == 0) load_next();
+                }
+            }
+            if (!ok) *K.err = 1;
+        }
+        __syncwarp();
+    } else {
+        // ============================================================ worker warps
+        // the pool only holds what the issuing warpgroup gave back: 640 x 96 at launch = 512 x 112 + 128 x 24 + 1024 spare
+        // (asking for 120 would need more than was released and block forever)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int q = warp & 3, h = warp >> 2;
+        const int p = 32 * q + lane;                    // point of the tile == TMEM lane
+        const int c0 = CPT * h;                         // first of this thread's CPT neurons
+        const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16);
+        const uint64_t polLast = policy_evict_last();
+        const SlabLayout sl = slab_layout(L, net.inpDim);
+        float* part = A.part32 + (size_t)blockIdx.x * sl.psz;
+        double* part64 = A.part + (size_t)blockIdx.x * sl.psz;
+        float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
+        uint32_t phase = 0;                             // bit i: phase parity this thread waits for next on barrier i
+        double lossAcc = 0.0;
+        bool first = true, firstFold = !A.accumulate;
+        int win = 0;
+
+        auto wait = [&](int i) {
+            if (ok) ok = mbar_wait(BAR(i), (phase >> i) & 1u);
+            phase ^= 1u << i;
+            __syncwarp();
+            tc_fence_after();
+        };
+        // publish this thread's TMEM / shared-memory writes and finished TMEM reads, one arrival per warp
+        auto signal = [&](uint32_t b) {
+            tmem_wait_st();
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b);
+        };
+        auto vec_add = [&](int kind, float v, bool overwrite) {
+            if (lane & ((1 << COLSUM_SHIFT) - 1)) return;
+            float* slot = part + sl.vecOff + (kind * 4 + q) * W + c0 + (lane >> COLSUM_SHIFT);
+            if (overwrite) __stcg(slot, v); else atomicAdd(slot, v);
+        };
+        // prefetched per-point values of a tile: xin[buf][c][p], c < nxTable: inputs; 8: dNt; 9, 10: gcoef; 11: source*N.
+        // Thread (p, h) fetches columns h, h + 4, h + 8.
+        const int XT = 8, XG = 9, XS = 11;
+        auto prefetch_inputs = [&](int tile, int buf) {
+            const unsigned int gp = (unsigned int)(A.tile0 + tile) * TP + p;
+            const bool valid = gp < A.P;
+            const size_t row = valid ? table_row(A, gp) : 0;
+            float* dst = xin + (size_t)buf * NXIN * TP + p;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int c = h + 4 * u;
+                int col = -1;
+                if (c < A.nxTable) col = A.colX + c;
+                else if (c == XT) col = A.colT;
+                else if (c >= XG && c < XG + S - 1) col = A.colG + (c - XG);
+                else if (c == XS) col = A.colS;
+                if (col >= 0) cp_async4(dst + c * TP, A.cols + (size_t)col * A.pstride + (A.tfIndex ? row : (size_t)gp));
+            }
+            cp_async_commit();
+        };
+        prefetch_inputs(blockIdx.x, 0);
+        int xb = 0;
+        // optional phase timing of one thread (CTA 0, thread 0): slot i accumulates the cycles since the previous mark
+        long long* timS = reinterpret_cast<long long*>(smem + OFF2_TIM);
+        const bool timOn = K.timing != nullptr && blockIdx.x == 0 && tid == 0;
+        if (timOn) { for (int i = 0; i < 15; ++i) timS[i] = 0; timS[15] = clock64(); }
+        auto TIM = [&](int i) { if (timOn) { const long long t = clock64(); timS[i] += t - timS[15]; timS[15] = t; } };
+
+        for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+            const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
+            const unsigned int gp = base + p;
+            const bool valid = gp < A.P;
+            const float* xv = xin + (size_t)xb * NXIN * TP + p;
+            cp_async_wait_all();
+            worker_bar();                                  // every worker's prefetched values of this tile are in shared memory
+            TIM(0);
+            auto input = [&](int c) -> float {
+                if (c >= A.nxTable) return __ldg(A.extraX + (c - A.nxTable));
+                return valid ? xv[c * TP] : 0.f;
+            };
+            // coefficient of stream s in the integrand I = sum_k du_k gcoef_k - u dNt (TFModel.py:653-657)
+            float cf[S];
+            cf[0] = (A.timeDependent && valid) ? -xv[XT * TP] : 0.f;
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k) cf[1 + k] = valid ? xv[(XG + k) * TP] : 0.f;
+
+            // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
+            float d1[CPT];                                // act'(z_l) of the value stream, kept for the tangent streams
+            {
+                float v[CPT];
+#pragma unroll
+                for (int jj = 0; jj < CPT; ++jj) v[jj] = bs[c0 + jj];
+                for (int c = 0; c < net.inpDim; ++c) {
+                    const float xc = input(c);
+#pragma unroll
+                    for (int jj = 0; jj < CPT; ++jj) v[jj] = fmaf(xc, W0s[c * W + c0 + jj], v[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < CPT; ++jj) { v[jj] = act64<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
+                put_operand(tq, c0, v);
+                stash_put(stash, 0, p, c0, v, polLast);
+                for (int k = 0; k < S - 1; ++k) {
+#pragma unroll
+                    for (int jj = 0; jj < CPT; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
+                    put_operand(tq + 128 * (1 + k), c0, v);
+                    stash_put(stash, 1 + k, p, c0, v, polLast);
+                }
+            }
+            signal(BAR(B_STEPF));                          // forward event 0
+            TIM(1);
+            if (tile + (int)gridDim.x < A.ntiles) prefetch_inputs(tile + (int)gridDim.x, xb ^ 1);
+
+            // ---- hidden layers, forward: epilogue of step k while the tensor core runs step k+1
+            float tw[CPT];                                 // sum_s a_{L-1,s} coef_s: g(w_out) before the scaling by lambda
+#pragma unroll
+            for (int jj = 0; jj < CPT; ++jj) tw[jj] = 0.f;
+            {
+                int l = 1, s = 0;
+                for (int k = 0; k < nfs; ++k) {
+                    TIM(2);
+                    wait(B_ACC + (k & 1));
+                    TIM(3);
+                    float v[CPT];
+                    get_plain(tq + COL2_ACC + 64 * (k & 1) + c0, v);
+                    if (s == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < CPT; ++jj) {
+                            v[jj] = act64<ACT>(v[jj] + bs[l * W + c0 + jj]);
+                            d1[jj] = act_d1<ACT>(v[jj]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < CPT; ++jj) v[jj] *= d1[jj];
+                    }
+                    put_operand(tq + 128 * s, c0, v);
+                    signal(BAR(B_STEPF + ((k + 1) & 1)));      // forward event k+1: accumulator drained, operand written
+                    stash_put(stash, l * S + s, p, c0, v, polLast);
+                    if (l == L - 1) {
+                        // output layer (Dense(1)): partial dot over this thread's neurons
+                        float a0 = 0.f, a1 = 0.f;
+                        const float cs = s == 0 ? cf[0] : (s == 1 ? cf[1] : cf[S - 1]);
+#pragma unroll
+                        for (int jj = 0; jj < CPT; jj += 2) {
+                            a0 = fmaf(v[jj], wout[c0 + jj], a0); a1 = fmaf(v[jj + 1], wout[c0 + jj + 1], a1);
+                            tw[jj] = fmaf(v[jj], cs, tw[jj]); tw[jj + 1] = fmaf(v[jj + 1], cs, tw[jj + 1]);
+                        }
+                        usP[(h * 3 + s) * TP + p] = a0 + a1;
+                    }
+                    if (++s == S) { s = 0; ++l; }
+                }
+            }
+            TIM(2);
+            worker_bar();
+
+            // ---- u_s, integrand, R_i of the test functions of this tile, loss, adjoint seeds (TFModel.py:653-664)
+            if (tid < TP) {
+                float u[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int g = 0; g < NH; ++g) a += usP[(g * 3 + s) * TP + p];
+                    u[s] = a;
+                }
+                u[0] += misc[0];
+                float I = 0.f;
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < S - 1; ++k) I = fmaf(u[1 + k], cf[1 + k], I);
+                    if (A.timeDependent) I = fmaf(u[0], cf[0], I);
+                    if (A.isSource) I -= xv[XS * TP];
+                    if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
+                }
+                Ish[p] = I;
+            }
+            worker_bar();
+            {
+                const int nf = TP / (int)A.integNum;
+                for (int f = warp; f < nf; f += NWORK / 32) {
+                    float r = 0.f;
+                    for (int qq = lane; qq < (int)A.integNum; qq += 32) r += Ish[f * A.integNum + qq];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                    if (lane == 0) {
+                        const unsigned int i = base / A.integNum + f;
+                        Rsh[f] = r;
+                        if (i * A.integNum < A.P) {
+                            const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
+                            const float r2 = r * r;
+                            A.R[i] = r;
+                            A.lossVec[i] = dj * r2;
+                            lossAcc += A.detJvec ? (double)dj * (double)r2 : (double)r2;
+                        }
+                    }
+                }
+            }
+            worker_bar();
+            if (tid < TP) {
+                float lam = 0.f;
+                if (valid) {
+                    const unsigned int i = gp / A.integNum, qq = gp - i * A.integNum;
+                    const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, i)) : __ldg(A.detJ);
+                    const float wq = A.integW ? __ldg(A.integW + qq) : 1.f;
+                    lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
+                }
+                lamS[p] = lam;
+#pragma unroll
+                for (int s = 0; s < S; ++s) us[s * TP + p] = lam * cf[s];        // adjoint seeds ubar_s
+            }
+            worker_bar();
+
+            // ---- output layer gradients: g(b_out) = sum_p ubar_0, g(w_out)[j] = sum_p lambda_p sum_s a_{L-1,s}[p][j] coef_s[p]
+            if (h == 0) {
+                float sb = us[p];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                if (lane == 0) { float* slot = part + sl.boutOff + q; if (first) __stcg(slot, sb); else atomicAdd(slot, sb); }
+            }
+            {
+                const float lam = lamS[p];
+#pragma unroll
+                for (int jj = 0; jj < CPT; ++jj) tw[jj] *= lam;
+                const float r = warp_colsum(tw, lane);
+                vec_add(L, r, first);
+            }
+
+            // ---- adjoint sweep.  Step k: zbar_{l,s} from the parked abar_{l,s} (tangent streams first: the value stream needs
+            // their second-order term); the tensor core then computes abar_{l-1,s} = zbar_{l,s} W_l^T into the park of s and
+            // gW_l += a_{l-1,s}^T zbar_{l,s}.  The preparation of step k overlaps the MMAs of step k-1.
+            {
+                // the second-order term of a layer is accumulated over its tangent steps in spare tensor-memory columns (16 registers
+                // that would otherwise be spilled: a0, dpre, apre, the step's zbar and the drained gradient tile are live together)
+                float a0[CPT], dpre[CPT], apre[CPT];
+                stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
+                stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
+                stash_get(stash, (L - 2) * S + 1, p, c0, apre, polLast);
+                unsigned char* GA = smem + OFF2_G;
+                unsigned char* GB = GA + G_BYTES;
+                TIM(4);
+                // drain of the weight-gradient accumulator of a step of layer ld (fd: first stream of the layer) into the FP32 window slab
+                auto drain_gw = [&](int ld, bool fd) {
+                    TIM(5);
+                    wait(B_GW);
+                    TIM(6);
+                    // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
+                    float g[CPT];
+                    if (q < 2) drain_sum2(tq + COL_GW + c0, tq + COL_GW + 64 + c0, g); else get_plain(tq + COL_GW + c0, g);
+                    float* slot = part + gw_slot(ld, p, c0);
+                    if (first && fd) {                                 // first write of this window: overwrite
+#pragma unroll
+                        for (int u = 0; u < CPT / 4; ++u) __stcg(reinterpret_cast<float4*>(slot) + u * TP, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < CPT / 4; ++u) red_add_v4(slot + 4 * u * TP, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+                    }
+                };
+                int k = 0;
+                for (int l = L - 1; l >= 0; --l) {
+                    for (int si = 0; si < S; ++si, ++k) {
+                        const int s = (si < S - 1) ? si + 1 : 0;
+                        // next step (ln, sn)
+                        int ln = l, sn = (si + 1 < S - 1) ? si + 2 : 0;
+                        if (si + 1 == S) { ln = l - 1; sn = 1; }
+                        if (k == nfs) {                                          // entering layer 0: finish the last MMA step
+                            drain_gw(1, false);
+                            wait(B_LAYER);
+                            TIM(9);
+                        }
+                        float v[CPT];
+                        if (l == L - 1) {
+                            const float ub = us[s * TP + p];
+#pragma unroll
+                            for (int jj = 0; jj < CPT; ++jj) v[jj] = ub * wout[c0 + jj];
+                        } else {
+                            get_plain(tq + COL_PARK + 64 * s + c0, v);           // abar_{l,s}: its layer GEMM (step k-S) has completed
+                        }
+                        if (s > 0) {
+                            float cross[CPT];
+                            if (si == 0) {
+#pragma unroll
+                                for (int jj = 0; jj < CPT; ++jj) cross[jj] = v[jj] * dpre[jj];
+                            } else {
+                                get_plain(tq + COL2_CROSS + c0, cross);
+#pragma unroll
+                                for (int jj = 0; jj < CPT; ++jj) cross[jj] = fmaf(v[jj], dpre[jj], cross[jj]);
+                            }
+                            put_plain(tq + COL2_CROSS + c0, cross);              // tcgen05.wait::st: in signal() below, before the next step reads it
+#pragma unroll
+                            for (int jj = 0; jj < CPT; ++jj) v[jj] *= act_d1<ACT>(a0[jj]);
+                        } else {
+                            float cross[CPT];
+                            get_plain(tq + COL2_CROSS + c0, cross);
+#pragma unroll
+                            for (int jj = 0; jj < CPT; ++jj) v[jj] = fmaf(v[jj], act_d1<ACT>(a0[jj]), act_d2r<ACT>(a0[jj]) * cross[jj]);
+                        }
+                        // tangent activations of the next step: in flight from here on
+                        if (ln >= 0 && sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre, polLast);
+                        if (l >= 1) {
+                            if (k >= 1) drain_gw(L - 1 - (k - 1) / S, ((k - 1) % S) == 0);     // step k-1; its operands in shared memory are free now
+                            put_transposed(GB, p, c0, v);
+                            put_transposed(GA, p, c0, apre);
+                            if (s == 0) {
+#pragma unroll
+                                for (int jj = 0; jj < CPT; ++jj) a0[jj] = apre[jj];      // a_{l-1,0}: the value activations of the next layer down
+                            }
+                            if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre, polLast);
+                            TIM(7);
+                            if (k >= 1) wait(B_LAYER);                           // layer GEMM of step k-1 done: the operand region is free
+                            TIM(8);
+                            put_operand(tq + COL_OP, c0, v);
+                            signal(BAR(B_STEPA + (k & 1)));
+                            if (s == 0) {
+                                const float r = warp_colsum(v, lane);            // g(b_l) = sum_p zbar_{l,0}
+                                vec_add(l, r, first);
+                            }
+                        } else {
+                            // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
+                            if (s > 0) {
+                                const float r = warp_colsum(v, lane);
+                                vec_add(L + 1 + (s - 1), r, first);
+                            } else {
+                                for (int c = 0; c < net.inpDim; ++c) {
+                                    const float xc = input(c);
+                                    float t[CPT];
+#pragma unroll
+                                    for (int jj = 0; jj < CPT; ++jj) t[jj] = xc * v[jj];
+                                    const float r = warp_colsum(t, lane);
+                                    vec_add(L + 1 + c, r, first && c >= S - 1);
+                                }
+                                const float r = warp_colsum(v, lane);
+                                vec_add(0, r, first);
+                            }
+                        }
+                    }
+                }
+            }
+            tmem_wait_ld();
+            TIM(10);
+
+            first = false;
+            if (++win == FOLD || tile + (int)gridDim.x >= A.ntiles) {
+                // fold this thread's slots of the FP32 window into the FP64 slab (single writer per slot)
+                auto put = [&](int idx) {
+                    const double v = (double)__ldcg(part + idx);
+                    if (firstFold) __stcg(part64 + idx, v); else part64[idx] += v;
+                };
+                for (int l = 1; l < L; ++l)
+                    for (int jj = 0; jj < CPT; ++jj) put(gw_slot(l, p, c0 + jj));
+                if ((lane & ((1 << COLSUM_SHIFT) - 1)) == 0)
+                    for (int kk = 0; kk < sl.nkind; ++kk) put(sl.vecOff + (kk * 4 + q) * W + c0 + (lane >> COLSUM_SHIFT));
+                if (h == 0 && lane == 0) put(sl.boutOff + q);
+                firstFold = false; first = true; win = 0;
+            }
+            xb ^= 1;
+            TIM(11);
+        }
+        if (timOn) for (int i = 0; i < 15; ++i) K.timing[i] = timS[i];
+        cp_async_wait_all();
+        if (lane == 0) {
+            double* lp = A.lossPart + blockIdx.x * (NWORK / 32) + warp;
+            *lp = A.accumulate ? *lp + lossAcc : lossAcc;
+        }
+        if (!ok) *K.err = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+template <int S, int ACT> cudaError_t launch_t(const Tc64Args& k, int grid, size_t smem, cudaStream_t st) {
+    tc64_var_kernel_v2<S, ACT><<<grid, NT2, smem, st>>>(k);
+    return cudaGetLastError();
+}
+template <int S, int ACT> cudaError_t prepare_t(size_t smem) {
+    return cudaFuncSetAttribute(tc64_var_kernel_v2<S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+}  // namespace v2
+
 // ------------------------------------------------------------------ weight images
 // image 2(l-1)   (forward, B rows n = output neuron, K = input):  n < 64: hi(W_l[k][n]),  n >= 64: lo(W_l[k][n-64])
 // image 2(l-1)+1 (adjoint, B rows n = input neuron,  K = output): n < 64: hi(W_l[n][k]),  n >= 64: lo(W_l[n-64][k])
@@ -735,6 +1309,20 @@ template <int S, int ACT> cudaError_t prepare_t(size_t smem) {
 
 }  // namespace
 
+static long long* g_timBuf = nullptr;       // phase cycle counters of the last v2 launch (CTA 0, thread 0), VARNET_B200_TC64_TIMING=1
+int vn_tc64_read_timing(long long out[16]) {
+    if (!g_timBuf) return 0;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, g_timBuf, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
+}
+// Two schedules of the same tile algorithm.  Default: the round-1 kernel (512 threads, MMAs issued by a worker thread between
+// __syncthreads).  VARNET_B200_TC64=v2 selects the warp-specialised, software-pipelined kernel of round 2: parity-green and
+// bitwise reproducible too, but measured 3 % SLOWER on the headline workload (163.6 vs 158.3 ms per 6.4e7-point step): with the
+// MMA waits overlapped, a tile is bound by the workers' own instruction stream (profiles/r2_tc64_v2.md has the phase table).
+static bool use_v1() {
+    static const int v = [] { const char* e = getenv("VARNET_B200_TC64"); return (e && !strcmp(e, "v2")) ? 0 : 1; }();
+    return v != 0;
+}
 bool vn_tc64_supported(const NetDesc& net, int S) {
     if (S < 2 || S > 3 || net.L < 2 || net.L > 6 || net.inpDim > VN_KIN) return false;
     int wmax = 0;
@@ -744,14 +1332,18 @@ bool vn_tc64_supported(const NetDesc& net, int S) {
 void vn_tc64_geometry(const NetDesc& net, int S, Tc64Geom* g) {
     const SlabLayout sl = slab_layout(net.L, net.inpDim);
     g->psz = sl.psz;
-    g->smemBytes = SMEM_BYTES;
+    g->smemBytes = use_v1() ? SMEM_BYTES : v2::SMEM2_BYTES;
     g->stashFloats = (long long)net.L * S * TP * W;
     g->nImages = 2 * (net.L - 1);
     g->lossSlots = NT / 32;
 }
 cudaError_t vn_tc64_prepare(int S, int act, size_t smem) {
-    if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem) : prepare_t<2, VN_TANH>(smem);
-    return act == VN_SIGMOID ? prepare_t<3, VN_SIGMOID>(smem) : prepare_t<3, VN_TANH>(smem);
+    if (use_v1()) {
+        if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem) : prepare_t<2, VN_TANH>(smem);
+        return act == VN_SIGMOID ? prepare_t<3, VN_SIGMOID>(smem) : prepare_t<3, VN_TANH>(smem);
+    }
+    if (S == 2) return act == VN_SIGMOID ? v2::prepare_t<2, VN_SIGMOID>(smem) : v2::prepare_t<2, VN_TANH>(smem);
+    return act == VN_SIGMOID ? v2::prepare_t<3, VN_SIGMOID>(smem) : v2::prepare_t<3, VN_TANH>(smem);
 }
 cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float* wimg, cudaStream_t st) {
     tc64_prep_kernel<<<dim3(32, 2 * (net.L - 1)), 256, 0, st>>>(net, theta, wimg);
@@ -759,9 +1351,18 @@ cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float*
 }
 cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smem, cudaStream_t st) {
     Tc64Args k;
-    k.t = a; k.wimg = wimg; k.err = err;
-    if (S == 2) return act == VN_SIGMOID ? launch_t<2, VN_SIGMOID>(k, grid, smem, st) : launch_t<2, VN_TANH>(k, grid, smem, st);
-    return act == VN_SIGMOID ? launch_t<3, VN_SIGMOID>(k, grid, smem, st) : launch_t<3, VN_TANH>(k, grid, smem, st);
+    k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr;
+    static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
+    if (timWanted && !use_v1()) {
+        if (!g_timBuf) { cudaMalloc(&g_timBuf, 16 * sizeof(long long)); cudaMemset(g_timBuf, 0, 16 * sizeof(long long)); }
+        k.timing = g_timBuf;
+    }
+    if (use_v1()) {
+        if (S == 2) return act == VN_SIGMOID ? launch_t<2, VN_SIGMOID>(k, grid, smem, st) : launch_t<2, VN_TANH>(k, grid, smem, st);
+        return act == VN_SIGMOID ? launch_t<3, VN_SIGMOID>(k, grid, smem, st) : launch_t<3, VN_TANH>(k, grid, smem, st);
+    }
+    if (S == 2) return act == VN_SIGMOID ? v2::launch_t<2, VN_SIGMOID>(k, grid, smem, st) : v2::launch_t<2, VN_TANH>(k, grid, smem, st);
+    return act == VN_SIGMOID ? v2::launch_t<3, VN_SIGMOID>(k, grid, smem, st) : v2::launch_t<3, VN_TANH>(k, grid, smem, st);
 }
 cudaError_t vn_tc64_reduce(const NetDesc& net, const double* slab64, int psz, int nCta, double* flat, cudaStream_t st) {
     tc64_reduce_kernel<<<(net.nparam + 3) / 4, 128, 0, st>>>(net, slab64, psz, nCta, flat);

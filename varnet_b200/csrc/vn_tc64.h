@@ -35,3 +35,5 @@ cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg,
                            cudaStream_t st);
 // fixed-order sum of the per-CTA FP64 slabs -> flat[nparam] in reference variable order
 cudaError_t vn_tc64_reduce(const NetDesc& net, const double* slab64, int psz, int nCta, double* flat, cudaStream_t st);
+// debug: phase cycle counters of CTA 0 / thread 0 of the last v2 launch (only filled when VARNET_B200_TC64_TIMING is set)
+int vn_tc64_read_timing(long long out[16]);
