@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--store-reference", action="store_true", help="N=1: write loss / ||grad|| of the seeded step to profiles/n1_reference.json")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operator-configs", action="store_true", help="skip the steps/sec legs of configs 1-3")
@@ -62,8 +63,8 @@ def parse():
 
 def measured_traffic(workload):
     """DRAM bytes per launch of the dominant kernel on this workload, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json; regenerate with scripts/make_traffic_json.py)."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    `ncu` capture of this build (profiles/r2_traffic.json; regenerate with scripts/make_traffic_json.py)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
             t = json.load(f)
@@ -210,7 +211,39 @@ def run_cpu(args, nx, ny, ntime, lw, act, steps, warmup, budget_s=None):
                        "double back-prop + TF-Adam, %d threads" % (sample_tf, nx * ny * ntime, P, cores))
 
 
-def operator_config_steps(budget_s=4.0):
+def operator_cpu_baseline(feed, kw, seconds):
+    """The reference's CPU path (torch FP32 double back-prop + TF-Adam, oracle/torch_oracle.py) on one feed dict of an
+    operator config, with all host threads and with one thread."""
+    import torch
+    from oracle import torch_oracle, graph_oracle
+    nb, q = [int(v) for v in feed["intShape"]]
+    cap = 16384                                   # bounded sample for the 15.36 M-point config
+    if nb > cap:
+        feed = dict(feed)
+        for k in ("Input", "gcoef", "source", "N", "dNt"):
+            v = feed.get(k)
+            if isinstance(v, np.ndarray) and v.dtype != object and v.shape[0] == nb * q:
+                feed[k] = v[:cap * q]
+        feed["intShape"] = [cap, q]
+        nb = cap
+    theta = graph_oracle.glorot_init(kw["inpDim"], kw["layerWidth"], seed=0)
+    out = {}
+    for label, threads in (("all_threads", os.cpu_count() or 1), ("one_thread", 1)):
+        st = torch_oracle.CpuStepper(theta, feed, kw["dim"], kw["inpDim"], kw["layerWidth"], kw["activation"], kw["timeDependent"],
+                                     kw["lossOpt"], threads=threads)
+        st.step()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds or n < 2:
+            st.step(); n += 1
+        dt = (time.perf_counter() - t0) / n
+        out[label] = dict(cores=threads, ms_per_step=dt * 1e3, steps_per_sec=1.0 / dt, quad_pts_per_sec=nb * q / dt)
+    torch.set_num_threads(os.cpu_count() or 1)
+    out["kind"] = "port"
+    out["sample"] = "%d test functions x %d points of the config's first feed dict" % (nb, q)
+    return out
+
+
+def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
     """train steps/sec of BASELINE.json configs 1-3 (the reference's operator scripts) on one GPU: each is
     built with the reference API of the host mirror and driven through ManageTrainData.optimIter ->
     TFNN.sess.run([optMinimize, loss]) exactly like VarNet.train's hot loop (VarNet.py:1350-1352)."""
@@ -218,17 +251,18 @@ def operator_config_steps(budget_s=4.0):
     from varnet_b200 import ManageTrainData
     pi = np.pi
     out = {}
+    procs = 'GPU:0' if world == 1 else ['GPU:%d' % i for i in range(world)]
 
     def cfg1():
         pde = varnet_b200.ADPDE(varnet_b200.Domain1D(), diff=0.1 / pi, vel=1.0, timeDependent=True, tInterval=[0, 2.0],
                                 IC=lambda x: -np.sin(pi * x))
-        return varnet_b200.VarNet(pde, layerWidth=[20], discNum=20, bDiscNum=None, tDiscNum=300, processors='GPU:0', seed=0), None, False
+        return varnet_b200.VarNet(pde, layerWidth=[20], discNum=20, bDiscNum=None, tDiscNum=300, processors=procs, seed=0), None, False
 
     def cfg2():
         v = np.array([[0.0, -0.5], [0.0, -0.2], [0.0, 0.2], [0.0, 0.5], [2.0, 0.5], [2.0, -0.5]])
         pde = varnet_b200.ADPDE(varnet_b200.PolygonDomain2D(v), diff=1.e-3, vel=[1., 0.], tInterval=[0, 1.5],
                                 BCs=[[], [0.0, 1.0, 1.0], [], [], [], []], IC=0.0)
-        return varnet_b200.VarNet(pde, layerWidth=[10, 20], discNum=[80, 40], bDiscNum=40, tDiscNum=75, processors='GPU:0', seed=0), None, False
+        return varnet_b200.VarNet(pde, layerWidth=[10, 20], discNum=[80, 40], bDiscNum=40, tDiscNum=75, processors=procs, seed=0), None, False
 
     def diffFun(x, t=0, D=0.1 / pi):
         return D * np.ones([np.shape(x)[0], 1])
@@ -239,7 +273,7 @@ def operator_config_steps(budget_s=4.0):
                                 IC=lambda x: -np.sin(pi * x), MORvar=mor)
         disc = lambda n=6: np.array([0.003 * (11 ** (k / (n - 1))) for k in range(n)])[np.newaxis].T
         return varnet_b200.VarNet(pde, layerWidth=[10, 20, 30], discNum=150, bDiscNum=75, tDiscNum=800, MORdiscScheme=disc,
-                                  processors='GPU:0', seed=0), 20, True
+                                  processors=procs, seed=0), 20, True
 
     for name, build in (("Operator_1Dt", cfg1), ("Operator_2Dt", cfg2), ("Operator_1DtMOR", cfg3)):
         t_build = time.perf_counter()
@@ -263,13 +297,35 @@ def operator_config_steps(budget_s=4.0):
                 n += tData.batchNum
             return n
         epoch()                                        # warm-up (also caches the MOR batches on the host)
+        # every rank runs the same number of epochs (the steps contain a collective): fixed count from a short calibration
+        t0 = time.perf_counter()
+        n_cal = epoch()
+        t_cal = time.perf_counter() - t0
+        n_epochs = max(1, int(budget_s / max(t_cal, 1e-6)))
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            box = torch.tensor([n_epochs], dtype=torch.int64, device="cuda")
+            dist.broadcast(box, src=0)
+            n_epochs = int(box[0])
+            dist.barrier()
         steps, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < budget_s:
+        for _ in range(n_epochs):
             steps += epoch()
         dt = time.perf_counter() - t0
-        P = int(np.prod(tData.optimFeedicts[0][tf.compTowers[0].intShape]))
+        tw_loc = next(t for t in tf.compTowers if t.local)
+        P = int(np.prod(tData.optimFeedicts[0][tw_loc.intShape])) * world
         out[name] = dict(steps_per_sec=steps / dt, quad_points_per_step=P, quad_pts_per_sec=steps * P / dt,
-                         steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build)
+                         steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build, n_gpus=world)
+        if cpu_seconds > 0 and rank == 0:
+            f0 = {k.name: (np.array(v) if type(v).__name__ == "TableView" else v) for k, v in tData.optimFeedicts[0].items()
+                  if getattr(k, "tower", None) == tw_loc.index}
+            kw = dict(dim=tf.dim, inpDim=tf.inpDim, layerWidth=list(tf.layerWidth), activation="sigmoid", timeDependent=tf.timeDependent,
+                      lossOpt=tf.lossOpt)
+            try:
+                out[name]["cpu_baseline"] = operator_cpu_baseline(f0, kw, cpu_seconds)
+            except Exception as ex:
+                out[name]["cpu_baseline"] = dict(error=repr(ex))
         tf.sess.close()
     return out
 
@@ -379,50 +435,124 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity of the step itself, before any update: loss and ||grad|| of the seeded weights on this table, summed over
+    # the towers.  At N = 1 they are compared with the stored reference (profiles/n1_reference.json, written by an N = 1 run
+    # with --store-reference); at N > 1 a deviation above 1e-6 relative fails the run (exit code 3): the all-reduced
+    # N-tower step must be the 1-tower step.
+    g0, loss0 = tf.sess.run([tf.grad, tf.loss], feed_dict=fd)
+    gnorm0 = float(np.linalg.norm(g0.astype(np.float64)))
+    parity = dict(loss=float(loss0), grad_norm=gnorm0)
+    ref_path = os.path.join(ROOT, "profiles", "n1_reference.json")
+    stored = {}
+    if os.path.exists(ref_path):
+        with open(ref_path) as f:
+            stored = json.load(f)
+    parity_fail = False
+    if args.workload in stored:
+        r0 = stored[args.workload]
+        parity["stored_n1"] = r0
+        parity["rel_diff_loss"] = abs(float(loss0) - r0["loss"]) / abs(r0["loss"])
+        parity["rel_diff_grad_norm"] = abs(gnorm0 - r0["grad_norm"]) / abs(r0["grad_norm"])
+        parity_fail = world > 1 and max(parity["rel_diff_loss"], parity["rel_diff_grad_norm"]) > 1e-6
+    if args.store_reference and world == 1 and rank == 0:
+        stored[args.workload] = dict(loss=float(loss0), grad_norm=gnorm0, kernel=eng.kernel_info().split()[0])
+        with open(ref_path, "w") as f:
+            json.dump(stored, f, indent=1, sort_keys=True)
+
     for _ in range(max(args.warmup, 3)):
         loss = step()
-    eng.profile_enable(True)
-    eng.profile_read()
+    # ---- timed region: the PRODUCT step (CUDA graph, optimizer fused into the reduction at N = 1, all-reduce inside the
+    # graph at N > 1, boundary/initial rows on the auxiliary stream).  Every step also gets its own event pair so that a
+    # straggling rank or step can be named.
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for k in range(args.steps):
         loss = step()
-    ev1.record()
+        evs[k + 1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
+    ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     launches = eng.launch_count() - l0
+
+    # ---- profiled leg (separate, not the timed region): per-kernel CUDA events inside the engine; plain launches, the
+    # optimizer as separate kernels, boundary/initial rows in sequence
+    eng.profile_enable(True)
+    eng.profile_read()
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(min(args.steps, 3)):
+        loss = step()
+    pe1.record()
+    barrier()
+    ms_prof = pe0.elapsed_time(pe1) / min(args.steps, 3)
     prof = eng.profile_read()
     eng.profile_enable(False)
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+
+    # ---- the collective alone: K all-reduces of the [grad | 4 scalars] buffer back to back (N > 1, native communicator)
+    ms_comm = None
+    if world > 1 and tf.native_comm:
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(20):
+            eng.allreduce_grad()
+        eng.synchronize()
+        c1.record()
+        torch.cuda.synchronize()
+        ms_comm = c0.elapsed_time(c1) / 20
+
+    kernel_ms_rank = prof["var_adj"][0] / max(prof["var_adj"][1], 1)
+    per_rank = dict(rank=rank, total_ms=ms, step_ms=step_ms, kernel_ms=kernel_ms_rank, allreduce_ms=ms_comm)
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank)
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, launches = float(tmax[0]), int(tsum[1])
+    else:
+        gathered = [per_rank]
     ms_step = ms / args.steps
 
-    # ---- e2e: host feed re-uploaded inside the timed region every step (pinned float32 -> H2D), loss read back
-    tf.feed_cache = False
-    step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.e2e_steps):
-        loss = step()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        te = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ms_e2e = float(te[0])
-    ms_e2e /= args.e2e_steps
-    tf.feed_cache = True
+    # ---- e2e legs: the host feed is re-uploaded inside the timed region every step and the loss is read back.
+    #   f32_pinned: float32 arrays in pinned host memory (the friendliest caller);
+    #   f64_pageable: what the reference's callers hand over (VarNetUtility.py:840-854): float64 NumPy arrays in pageable
+    #   memory, cast to float32 on the device (vn_loss_grad_fed_f64).
+    def e2e_leg(feed_dict, nsteps):
+        tf.feed_cache = False
+        step_fd = lambda: tf.sess.run([tf.optMinimize, tf.loss], feed_dict=feed_dict)[1]
+        step_fd()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(nsteps):
+            lv = step_fd()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        m = max(e0.elapsed_time(e1), wall)            # host-side staging (pageable copies) is part of the step
+        if world > 1:
+            te = torch.tensor([m], dtype=torch.float64, device="cuda")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            m = float(te[0])
+        tf.feed_cache = True
+        return m / nsteps, float(lv)
+
+    ms_e2e, _ = e2e_leg(fd, args.e2e_steps)
+    fd64 = dict(fd)
+    for k in ("Input", "gcoef", "dNt", "biInput", "biLabel"):
+        fd64[getattr(tw, k)] = np.asarray(feed[k], dtype=np.float64)            # pageable float64 copies
+    h2d64 = sum(fd64[getattr(tw, k)].nbytes for k in ("Input", "gcoef", "dNt", "biInput", "biLabel"))
+    ms_e2e64, _ = e2e_leg(fd64, args.e2e_steps)
+    del fd64
 
     # the same table built on the device from the mesh centres + periodic FE tables (vn_generate_table_f64): compare
     # with table_build_s (host NumPy build + pinning); spare slot, freed again
@@ -470,13 +600,27 @@ def main():
                             peak_source="0.5 x dense bf16 (%s): TF32 runs at half the bf16 rate" % pk["source"],
                             executed_mma_tflops=3.0 * achieved, executed_frac=3.0 * achieved / tf32_peak,
                             fp32_fma_peak=peak_tf, frac_of_fp32_fma_peak=achieved / peak_tf if peak_tf else None)
+        all_steps = np.array([g["step_ms"] for g in gathered])                      # [rank][step]
+        slow = int(np.argmax([g["total_ms"] for g in gathered]))
+        ranks = dict(step_ms_min=float(all_steps.min()), step_ms_median=float(np.median(all_steps)), step_ms_max=float(all_steps.max()),
+                     per_rank_mean_ms=[float(np.mean(g["step_ms"])) for g in gathered], slowest_rank=slow,
+                     per_rank_kernel_ms=[float(g["kernel_ms"]) for g in gathered],
+                     allreduce_ms=(None if gathered[0]["allreduce_ms"] is None else float(max(g["allreduce_ms"] for g in gathered))),
+                     comm="native NCCL communicator inside the step graph (vn_comm_init)" if getattr(tf, "native_comm", False) else
+                          ("torch.distributed all_reduce" if world > 1 else "none"))
         line = dict(metric=METRIC, value=P_total / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic", config=config,
-                    train_steps_per_sec=1e3 / ms_step, loss=float(loss), table_build_s=t_build, device_table_generate_s=t_gen,
+                    train_steps_per_sec=1e3 / ms_step, loss=float(loss), parity=parity, table_build_s=t_build, device_table_generate_s=t_gen,
+                    timed_path="product step: one CUDA graph per step (kernels, %s optimizer)" % ("all-reduce," if world > 1 else "fused"),
+                    profiled_ms_per_step=ms_prof, ranks=ranks,
                     roofline=roofline,
                     e2e=dict(value=P_total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                             ms_per_step=ms_e2e, api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f32: copies overlap the kernels)"),
+                             ms_per_step=ms_e2e, steps=args.e2e_steps, feed="float32, pinned host memory",
+                             api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f32: copies overlap the kernels)"),
+                    e2e_f64=dict(value=P_total / (ms_e2e64 * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d64), d2h_bytes_per_step=4,
+                                 ms_per_step=ms_e2e64, steps=args.e2e_steps, feed="float64 NumPy arrays in pageable memory, as the reference's callers feed them (VarNetUtility.py:840-854)",
+                                 api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f64)"),
                     gpu_launches=int(launches), clocks=clocks, kernel_info=eng.kernel_info())
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)
@@ -487,16 +631,26 @@ def main():
                 line["width_sweep"] = width_sweep(feed, meta, act, P_local)
             except Exception as ex:
                 line["width_sweep"] = dict(error=repr(ex))
-        if world == 1 and not args.no_operator_configs and not args.no_cpu_baseline:
-            try:
-                line["operator_configs"] = operator_config_steps()
-            except Exception as ex:                      # never lose the headline line to an auxiliary leg
-                line["operator_configs"] = dict(error=repr(ex))
+    tf.sess.close()
+    # ---- train steps/sec of the reference's own three operator configurations (BASELINE.json configs 1-3) at this N: every
+    # rank takes part (its tower of each config), rank 0 reports.  They are launch-bound and do not scale: reported, not hidden.
+    opcfg = None
+    if not args.no_operator_configs:
+        try:
+            opcfg = operator_config_steps(world, rank, budget_s=4.0 if world == 1 else 2.0,
+                                          cpu_seconds=(0.0 if (args.no_cpu_baseline or world > 1) else 2.0))
+        except Exception as ex:                          # never lose the headline line to an auxiliary leg
+            opcfg = dict(error=repr(ex))
+    if rank == 0:
+        if opcfg is not None:
+            line["operator_configs"] = opcfg
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    tf.sess.close()
+    if parity_fail:
+        sys.stderr.write("bench.py: N=%d step differs from the stored N=1 step: %s\n" % (world, json.dumps(parity)))
+        return 3
     return 0
 
 

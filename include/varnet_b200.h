@@ -160,6 +160,7 @@ int vn_loss_grad_fed_f64(vn_engine* e, const double* Input, const double* gcoef,
                          int32_t detJvec, float out[4]);
 int vn_grad_buffer(vn_engine* e, void** device_ptr, int64_t* n_floats);
 int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]);
+int vn_get_scalars(vn_engine* e, float out[4]);     /* {loss, BCloss, ICloss, varLoss} of the gradient buffer; synchronises */
 /* lossVec[nb] = detJ_i R_i^2 (TFModel.py:668) as left by the last vn_loss / vn_loss_grad / vn_train_step of the
  * current batch (the fused adjoint kernels write it themselves); synchronises. */
 int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb);
@@ -169,6 +170,18 @@ int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb);
 int vn_check_error(vn_engine* e);
 int vn_optimizer_step(vn_engine* e, float lr);
 int vn_train_step(vn_engine* e, float lr, float* loss_out);
+
+/* ---- multi-GPU (one handle per GPU, one process per GPU): the towers' gradients and losses are summed like
+ *      TFNN.sum_grads / optimSetup do on the controller (TFModel.py:315-319,342-377), with one NCCL all-reduce of the
+ *      gradient buffer over NVLink.  NCCL is bound at run time (dlopen): `nccl_lib` may name the library, NULL uses the
+ *      libnccl.so.2 already loaded into the process.  Protocol: tower 0 calls vn_comm_unique_id and ships the 128 bytes
+ *      to the other processes (any host-side channel), then every tower calls vn_comm_init (collective).  From then on
+ *      vn_train_step = kernels -> all-reduce -> optimizer update on the engine's stream, captured as ONE CUDA graph;
+ *      vn_allreduce_grad is the same collective for callers that sequence vn_loss_grad / vn_optimizer_step themselves. */
+int vn_comm_unique_id(const char* nccl_lib, void* id128);
+int vn_comm_init(vn_engine* e, const char* nccl_lib, const void* id128, int32_t rank, int32_t world);
+int vn_comm_world(const vn_engine* e);
+int vn_allreduce_grad(vn_engine* e);
 
 /* ---- evaluation (VarNetUtility.runSession, VarNetUtility.py:1098-1142)
  * vn_eval:     u = model(X), X[n,inpDim] host row-major, u[n].

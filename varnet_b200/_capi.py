@@ -58,11 +58,16 @@ SIGNATURES = {
     "vn_loss_grad_fed_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _i32, _f64p, _f64p, _i32, _f32p]),
     "vn_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "vn_get_grad": (C.c_int, [_vp, _f32p, _i64, _f32p]),
+    "vn_get_scalars": (C.c_int, [_vp, _f32p]),
     "vn_get_lossvec": (C.c_int, [_vp, _f32p, _i64]),
     "vn_check_error": (C.c_int, [_vp]),
     "vn_debug_tc64_timing": (C.c_int, [C.POINTER(_i64)]),
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
+    "vn_comm_unique_id": (C.c_int, [C.c_char_p, _vp]),
+    "vn_comm_init": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _i32]),
+    "vn_comm_world": (C.c_int, [_vp]),
+    "vn_allreduce_grad": (C.c_int, [_vp]),
     "vn_eval_f32": (C.c_int, [_vp, _f32p, _i64, _f32p]),
     "vn_eval_f64": (C.c_int, [_vp, _f64p, _i64, _f32p]),
     "vn_residual_f64": (C.c_int, [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _i64, _f32p, _f32p]),
@@ -334,6 +339,11 @@ class Engine:
             return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3])
         return None
 
+    def get_scalars(self):
+        out = np.empty(4, dtype=np.float32)
+        self._check(self.lib.vn_get_scalars(self._h, _ptr(out, C.c_float)))
+        return dict(loss=out[0], BCloss=out[1], ICloss=out[2], varLoss=out[3])
+
     def get_lossvec(self):
         """lossVec of the last loss / loss_grad / train_step call (written by the kernel that ran)."""
         lv = np.empty(self.nb, dtype=np.float32)
@@ -364,6 +374,26 @@ class Engine:
         dev = self.torch_device()
         with torch.cuda.device(dev):
             return torch.as_tensor(v, device=dev)
+
+    # -- multi-GPU: the tower's own NCCL communicator (include/varnet_b200.h, "multi-GPU")
+    @staticmethod
+    def comm_unique_id(nccl_lib=None):
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.vn_comm_unique_id(nccl_lib.encode() if nccl_lib else None, C.cast(buf, _vp))
+        if rc != 0:
+            raise EngineError(rc, lib.vn_last_error().decode())
+        return bytes(buf.raw)
+
+    def comm_init(self, unique_id, rank, world, nccl_lib=None):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.vn_comm_init(self._h, nccl_lib.encode() if nccl_lib else None, C.cast(buf, _vp), int(rank), int(world)))
+
+    def comm_world(self):
+        return int(self.lib.vn_comm_world(self._h))
+
+    def allreduce_grad(self):
+        self._check(self.lib.vn_allreduce_grad(self._h))
 
     def optimizer_step(self, lr):
         self._check(self.lib.vn_optimizer_step(self._h, float(lr)))

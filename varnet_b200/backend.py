@@ -322,6 +322,19 @@ class Session:
                 return float(loss)
             loss = eng.train_step(o.learning_rate, fetch_loss=True)
             return float(loss)
+        if dist is not None and o.native_comm and len(towers) == 1:
+            # one process per GPU: the tower's own NCCL communicator sums [grad | losses] on the engine's stream between
+            # the reduction kernel and the optimizer update (one captured graph per step, include/varnet_b200.h "multi-GPU")
+            eng = towers[0].engine
+            pend = towers[0].__dict__.pop("_pending_points", None)
+            if pend is not None:
+                eng.loss_grad_fed(*pend, fetch=False)
+                eng.allreduce_grad()
+                eng.optimizer_step(o.learning_rate)
+                return float(eng.get_scalars()["loss"])
+            return float(eng.train_step(o.learning_rate, fetch_loss=True))
+        # portable path (several towers in one process, or no native communicator): sum through torch.  The engine runs on its
+        # own stream, so it is drained before torch touches the gradient buffer and torch's work is drained before the update.
         import torch
         views = []
         for tw in towers:
@@ -331,23 +344,52 @@ class Session:
             else:
                 tw.engine.loss_grad(fetch=False)
             views.append(tw.engine.grad_tensor())
+        for tw in towers:
+            tw.engine.synchronize()
         if len(towers) > 1:                       # single process, several GPUs: sum on the controller
             ctrl = views[0]
-            for tw in towers:
-                tw.engine.synchronize()
             total = ctrl.clone()
             for v in views[1:]:
                 total += v.to(ctrl.device)
             for v in views:
                 v.copy_(total.to(v.device))
-            if ctrl.is_cuda:
-                torch.cuda.synchronize()
         if dist is not None:
-            dist.all_reduce(views[0])             # NCCL SUM over NVLink: [grad | loss, BCloss, ICloss, varLoss]
+            dist.all_reduce(views[0])             # SUM over the ranks: [grad | loss, BCloss, ICloss, varLoss]
+        if views[0].is_cuda:
+            for v in views:
+                torch.cuda.synchronize(v.device)
         for tw in towers:
             tw.engine.optimizer_step(o.learning_rate)
         n = towers[0].engine.nparam
         return float(views[0][n].item())
+
+    def _gradients(self):
+        o = self._o
+        towers = self._local_towers()
+        dist = _dist()
+        for tw in towers:
+            tw.engine.loss_grad(fetch=False)
+        if dist is not None and o.native_comm and len(towers) == 1:
+            towers[0].engine.allreduce_grad()
+            towers[0].engine.synchronize()
+            v = towers[0].engine.grad_tensor()
+        else:
+            import torch
+            for tw in towers:
+                tw.engine.synchronize()
+            v = towers[0].engine.grad_tensor()
+            if len(towers) > 1:
+                v = v.clone()
+                for tw in towers[1:]:
+                    v += tw.engine.grad_tensor().to(v.device)
+            if dist is not None:
+                v = v.clone()
+                dist.all_reduce(v)
+            if v.is_cuda:
+                torch.cuda.synchronize(v.device)
+        n = towers[0].engine.nparam
+        arr = v.detach().cpu().numpy()
+        return arr[:n].copy(), float(arr[n])
 
     # -- the protocol
     def run(self, fetches, feed_dict=None):
@@ -381,6 +423,13 @@ class Session:
             return out[0] if single else out
 
         train = "optMinimize" in names
+        if "grad" in names and not train:
+            # [grad, loss]: d loss / d theta summed over the towers (NNModel.computeGrad + TFNN.sum_grads), no update
+            self._sync_feeds(feed_dict)
+            g, loss = self._gradients()
+            for i, nm in enumerate(names):
+                out[i] = g if nm == "grad" else (np.float32(loss) if nm == "loss" else None)
+            return out[0] if single else out
         self._sync_feeds(feed_dict, defer_points=train)
         if train:
             loss = self._train_step()
@@ -529,14 +578,36 @@ class TFNN:
         # lazy-gather feeds (tables.TableView) are understood when every local engine keeps tables resident
         self.supports_table_views = all(getattr(tw.engine, "supports_table_views", False)
                                         for tw in self.compTowers if tw.local)
+        self.native_comm = self._setup_native_comm(dist)
         self.graph = _Graph()
         self.loss, self.BCloss, self.ICloss = Node("loss"), Node("BCloss"), Node("ICloss")
         self.varLoss, self.lossVec = Node("varLoss"), Node("lossVec")
+        self.grad = Node("grad")             # summed tower gradients (TFNN.sum_grads, TFModel.py:342-377) as one flat vector
         self.optMinimize, self.step = Node("optMinimize"), Node("step")
         self.saver = Saver(self)
         self.sess = Session(self)
         _TFCompat.current = self
         self.initialize_variables()
+
+    def _setup_native_comm(self, dist):
+        """One NCCL communicator over the towers, owned by the engines (vn_comm_init): rank 0 draws the unique id, the
+        ranks exchange it through the existing process group.  VARNET_B200_COMM=torch keeps the portable torch path."""
+        if dist is None or os.environ.get("VARNET_B200_COMM", "").lower() == "torch":
+            return False
+        local = [tw for tw in self.compTowers if tw.local]
+        if len(local) != 1 or not hasattr(local[0].engine, "comm_init") or dist.get_backend() != "nccl":
+            return False
+        box = [None]
+        try:
+            if self.rank == 0:
+                box[0] = type(local[0].engine).comm_unique_id()
+        except Exception as ex:                        # no NCCL in the process: every rank must take the same branch
+            box[0] = ex
+        dist.broadcast_object_list(box, src=0)
+        if not isinstance(box[0], (bytes, bytearray)):
+            return False
+        local[0].engine.comm_init(box[0], self.rank, self.world_size)
+        return True
 
     # weights are shared by all towers (TFModel.py:180): every engine holds the same copy
     def initialize_variables(self):

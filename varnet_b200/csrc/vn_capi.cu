@@ -1,5 +1,6 @@
 // vn_capi.cu — C ABI (include/varnet_b200.h) + the small reduction / optimizer / packing kernels.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -29,6 +30,42 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* vn_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------ NCCL, bound at run time
+// The engine does not link NCCL: the few entry points it needs are resolved with dlopen/dlsym from the library that is
+// already in the process (torch's bundled libnccl.so.2, RTLD_NOLOAD first) or from a path given by the caller, so one
+// build serves single-GPU hosts without NCCL and 8-GPU boxes alike.  Types/constants as in nccl.h (2.x ABI).
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;              // ncclUniqueId
+    typedef void* Comm;                                           // ncclComm_t
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    void* handle = nullptr;
+    bool ok() const { return GetUniqueId && CommInitRank && AllReduce && CommDestroy; }
+};
+static NcclApi g_nccl;
+static int nccl_load(const char* path) {
+    if (g_nccl.ok()) return VN_OK;
+    void* h = nullptr;
+    if (path && *path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // already loaded by the host framework
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(VN_E_STATE, "NCCL library not found: %s", dlerror());
+    g_nccl.handle = h;
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(NcclApi::UniqueId*)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(NcclApi::Comm*, int, NcclApi::UniqueId, int)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, NcclApi::Comm, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(NcclApi::Comm)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.ok()) return fail(VN_E_STATE, "NCCL library lacks the expected entry points");
+    return VN_OK;
+}
+static const char* nccl_err(int rc) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error"; }
+enum { kNcclFloat32 = 7, kNcclSum = 0 };
 
 // ------------------------------------------------------------------ dispatch over kernel classes
 bool vn_tile_geometry(int S, int cls, int act, int mode, int L, TileGeom* g) {
@@ -383,6 +420,9 @@ struct vn_engine {
     TileGeom gVarFwd, gVarAdj, gBicFwd, gBicAdj, gEval, gRes;
     bool weightsSet = false;
     bool resOK = true;           // strong-form residual kernel available for this depth/width
+    // multi-GPU: this tower's own NCCL communicator (vn_comm_init); the step's all-reduce runs on the engine stream
+    void* comm = nullptr; int commRank = 0, commWorld = 1;
+    void* l2WindowPtr = nullptr; size_t l2WindowBytes = 0; cudaStream_t l2WindowStream = nullptr;   // persisting-L2 window (set_stash_window)
     // optional per-kernel CUDA-event timing (vn_profile_enable / vn_profile_read)
     bool profOn = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profPending[VN_PROF_SLOTS];
@@ -556,6 +596,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     drop_graph(e);
+    if (e->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
     if (e->ownStream) cudaStreamDestroy(e->ownStream);
     if (e->copyStream) cudaStreamDestroy(e->copyStream);
     if (e->auxStream) cudaStreamDestroy(e->auxStream);
@@ -648,6 +689,33 @@ extern "C" int vn_set_weights(vn_engine* e, const float w[3]) {
 // ------------------------------------------------------------------ uploads
 static const long long kChunk = 1 << 22;    // rows per staging chunk
 
+// The per-CTA activation stash is rewritten by every tile and read back a few microseconds later: it belongs in L2.  The
+// kernels already tag these accesses evict_last, but that is only a hint (round 1: 15.4 GB of stash write-back per 6.4e7-point
+// launch).  Here the stash is additionally declared a PERSISTING access-policy window of the engine's stream, with the L2
+// set-aside sized for it, and the rest of the step's traffic (the streamed point table) as streaming.  Best effort: a device
+// that refuses any of the calls simply keeps the hints.  VARNET_B200_L2_PERSIST=0 disables it (A/B measurements).
+static void set_stash_window(vn_engine* e) {
+    static const bool off = [] { const char* v = getenv("VARNET_B200_L2_PERSIST"); return v && !strcmp(v, "0"); }();
+    if (off || !e->stashVar.p || e->stashVar.bytes < (1u << 20) || !e->stream) return;
+    if (e->l2WindowPtr == e->stashVar.p && e->l2WindowBytes == e->stashVar.bytes && e->l2WindowStream == e->stream) return;
+    int maxPersist = 0, maxWindow = 0;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, e->cfg.device);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, e->cfg.device);
+    if (maxPersist <= 0 || maxWindow <= 0) { cudaGetLastError(); return; }
+    const size_t want = std::min<size_t>(e->stashVar.bytes, (size_t)maxPersist);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = e->stashVar.p;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(e->stashVar.bytes, (size_t)maxWindow);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { cudaGetLastError(); return; }
+    e->l2WindowPtr = e->stashVar.p; e->l2WindowBytes = e->stashVar.bytes; e->l2WindowStream = e->stream;
+    drop_graph(e);          // captured kernel nodes carry the window they were captured with
+}
+
 // size the per-batch work buffers and pick the single-pass (fused residual) path when integNum | TP
 static int ensure_work(vn_engine* e) {
     PointSet* t = e->t;
@@ -668,6 +736,7 @@ static int ensure_work(vn_engine* e) {
         CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->numSMs * e->tc64Geom.stashFloats * sizeof(float))));
         CK(e->lossPart.ensure((size_t)e->numSMs * e->tc64Geom.lossSlots * sizeof(double)));
         e->fused = true;
+        set_stash_window(e);
         return VN_OK;
     }
     const long long tilesAdj = (P + e->gVarAdj.TP - 1) / e->gVarAdj.TP;
@@ -677,6 +746,7 @@ static int ensure_work(vn_engine* e) {
     CK(e->stashVar.ensure(std::max<size_t>(16, (size_t)e->numSMs * e->gVarAdj.stashFloats * sizeof(float))));
     CK(e->lossPart.ensure((size_t)e->numSMs * (e->gVarAdj.NT / 32) * sizeof(double)));
     e->fused = (e->gVarAdj.TP % t->integNum) == 0;
+    set_stash_window(e);
     return VN_OK;
 }
 
@@ -1306,6 +1376,50 @@ extern "C" int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]) {
     CK(cudaStreamSynchronize(e->stream));
     return VN_OK;
 }
+// ---- multi-GPU: one handle per GPU, one NCCL communicator over the towers.
+extern "C" int vn_comm_unique_id(const char* nccl_lib, void* id128) {
+    if (!id128) return fail(VN_E_INVALID, "null argument");
+    int rc = nccl_load(nccl_lib);
+    if (rc) return rc;
+    NcclApi::UniqueId id;
+    const int nr = g_nccl.GetUniqueId(&id);
+    if (nr != 0) return fail(VN_E_CUDA, "ncclGetUniqueId: %s", nccl_err(nr));
+    memcpy(id128, &id, sizeof(id));
+    return VN_OK;
+}
+extern "C" int vn_comm_init(vn_engine* e, const char* nccl_lib, const void* id128, int32_t rank, int32_t world) {
+    if (!e || !id128) return fail(VN_E_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(VN_E_INVALID, "rank %d outside the world of %d towers", rank, world);
+    int rc = nccl_load(nccl_lib);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->comm) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
+    NcclApi::UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NcclApi::Comm c = nullptr;
+    const int nr = g_nccl.CommInitRank(&c, world, id, rank);
+    if (nr != 0) return fail(VN_E_CUDA, "ncclCommInitRank: %s", nccl_err(nr));
+    e->comm = c; e->commRank = rank; e->commWorld = world;
+    drop_graph(e);
+    return VN_OK;
+}
+extern "C" int vn_comm_world(const vn_engine* e) { return (e && e->comm) ? e->commWorld : 1; }
+// SUM of the gradient buffer [grad | loss, BCloss, ICloss, varLoss] over the towers, on the engine's stream, in place
+// (TFNN.sum_grads, TFModel.py:342-377).  Ordered after the kernels of vn_loss_grad and before vn_optimizer_step by stream order.
+extern "C" int vn_allreduce_grad(vn_engine* e) {
+    if (!e) return fail(VN_E_INVALID, "null engine");
+    if (!e->comm) return fail(VN_E_STATE, "vn_comm_init has not been called on this tower");
+    CK(cudaSetDevice(e->cfg.device));
+    const int nr = g_nccl.AllReduce(e->gbuf.p, e->gbuf.p, (size_t)e->net.nparam + 4, kNcclFloat32, kNcclSum, e->comm, e->stream);
+    if (nr != 0) return fail(VN_E_CUDA, "ncclAllReduce: %s", nccl_err(nr));
+    e->launches++;
+    return VN_OK;
+}
+extern "C" int vn_get_scalars(vn_engine* e, float out[4]) {
+    if (!e || !out) return fail(VN_E_INVALID, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    return read_scalars(e, out);
+}
 extern "C" int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb) {
     if (!e || !lossVec) return fail(VN_E_INVALID, "null argument");
     if (nb != (int64_t)e->nb || !e->lossVec.p) return fail(VN_E_STATE, "lossVec holds %u values (asked for %lld); call vn_loss / vn_loss_grad first", e->nb, (long long)nb);
@@ -1357,9 +1471,12 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
     const bool useGraph = e->graphOK && !e->profOn && e->stream != nullptr;
     // resident-tile classes: the optimizer update is applied inside vn_finalize_kernel (one kernel less per step);
     // the tensor-core class and profiling runs keep the separate optimizer kernels
-    const bool fuse = e->wclass != 256 && !e->profOn;
+    // With a communicator (vn_comm_init) the gradient buffer is all-reduced between the reduction and the update, on the
+    // same stream, and {kernels, ncclAllReduce, optimizer} are captured into the step graph together.
+    const bool fuse = e->wclass != 256 && !e->profOn && !e->comm;
     auto step_once = [&]() -> int {
         int rc = run_loss(e, true, nullptr, fuse ? lr : -1.f);
+        if (!rc && e->comm) rc = vn_allreduce_grad(e);
         if (!rc && !fuse) rc = vn_optimizer_step(e, lr);
         return rc;
     };
