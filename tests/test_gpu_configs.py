@@ -217,3 +217,37 @@ def test_no_initial_rows_gives_nan_like_tf_mean_of_empty():
     out = eng.loss()
     assert np.isnan(out["ICloss"]) and np.isfinite(out["BCloss"]) and np.isfinite(out["varLoss"])
     eng.close()
+
+
+@pytest.mark.parametrize("name,scale,batchNum", [("Operator_1Dt", 0.3, None), ("Operator_2Dt", 0.12, 3), ("Operator_1DtMOR", 0.06, 4)])
+def test_trainer_generates_uniform_tables_on_the_device(name, scale, batchNum):
+    """SURVEY section 8 f-2 wired into the host mirror: for a uniform mesh with constant coefficients (also a MOR batch whose
+    parameter is a single diffusivity) `trainData` attaches a generation recipe and the shim calls vn_generate_table_f64
+    instead of uploading nT-row arrays.  Loss and the full gradient are BIT-IDENTICAL to the uploaded-table path, for
+    every mini-batch and MOR batch."""
+    import varnet_b200
+    results = {}
+    for auto in (True, False):
+        vn = configs.BUILDERS[name](varnet_b200, scale, seed=11)
+        tf = vn.tfData
+        tf.auto_generate = auto
+        fd = vn.fixData
+        fd.setFEdata()
+        Input, _, biInput, _ = vn.trainingPoints()
+        disc = None if vn.PDE.MORvar is None else vn.PDE.MORvar.discretizeArg(vn.MORdiscScheme)
+        tData = varnet_b200.ManageTrainData(Input, biInput, batchNum, None, False, fd.MORbatchNum)
+        out = []
+        for mb in range(fd.MORbatchNum):
+            tData = vn.trainData(mb, disc, tData)
+            if mb == 0:
+                tData.updateDictFields('trainW', np.array([10.0, 10.0, 1.0]), normalizeW=False)
+            for fdict in tData.optimFeedicts:
+                g, loss = tf.sess.run([tf.grad, tf.loss], feed_dict=fdict)
+                out.append((np.float32(loss), g.copy()))
+        results[auto] = (out, tf.generated, tf.uploads)
+        tf.sess.close()
+    on, off = results[True], results[False]
+    assert on[1] >= fd.MORbatchNum and off[1] == 0                   # one generated table per MOR batch, none when switched off
+    assert len(on[0]) == len(off[0]) > 0
+    for (la, ga), (lb, gb) in zip(on[0], off[0]):
+        assert la == lb and np.array_equal(ga, gb)

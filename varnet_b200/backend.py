@@ -249,9 +249,17 @@ class Session:
             tok.pop("view_batch", None)
         if fresh:
             nbTab = len(X.base) // X.integNum
-            eng.upload_table(X.base, base("gcoef"), base("source"), base("N"), base("dNt"), [nbTab, X.integNum],
-                             fd.get("integW"), detJ.base if isinstance(detJ, TableView) else detJ, detJvec,
-                             nx=X.base.shape[1])
+            gen = getattr(fd.get("gcoef"), "gen", None)
+            if gen is not None and o.auto_generate and hasattr(eng, "generate_table") and gen["nb"] == nbTab and not detJvec:
+                # uniform mesh + constant coefficients: the table is rebuilt on the device from the mesh centres and the
+                # periodic FE tables (a few KB cross the bus instead of nT rows x 8 columns; bit-identical result)
+                eng.generate_table(gen["coord"], gen["tcoord"], gen["hVec"], gen["delta"], gen["N"], gen["dN"], gen["diff"],
+                                   gen["vel"], gen["source"], 0, nbTab, X.integNum, gen["integW"], gen["detJ"])
+                o.generated += 1
+            else:
+                eng.upload_table(X.base, base("gcoef"), base("source"), base("N"), base("dNt"), [nbTab, X.integNum],
+                                 fd.get("integW"), detJ.base if isinstance(detJ, TableView) else detJ, detJvec,
+                                 nx=X.base.shape[1])
             o.uploads += 1
         extra = None if X.extra is None else tuple(np.asarray(X.extra, dtype=np.float32).ravel().tolist())
         if tok.get("view_extra") != extra or fresh:
@@ -547,7 +555,9 @@ class TFNN:
         self.processors = ['/device:GPU:%d' % d for d in devices]
         self.controller = self.processors[0] if controller is None else controller
         self.lossOpt, self.optimizer_name, self.learning_rate = lossOpt, optimizer_name, learning_rate
-        self.uploads, self.step_count = 0, 0
+        self.uploads, self.step_count, self.generated = 0, 0, 0
+        # uniform-mesh / constant-coefficient tables are generated on the device instead of uploaded (vn_generate_table_f64)
+        self.auto_generate = os.environ.get("VARNET_B200_AUTO_GENERATE", "1") != "0"
         # True: a feed array is uploaded only when it is replaced by a new object (in-place edits of a fed array are NOT
         # seen: replace the dict entry, as updateDictFields / shuffleTrainData do); False: every
         # sess.run re-uploads its feeds, like the reference's per-step feed (VarNetUtility.py:1044)

@@ -1200,7 +1200,8 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
     var_args(e, &a);
     int nSeg = (int)((e->nb + 255) / 256);
     const double* segPtr = e->segSum.as<double>();
-    if (needGrad && e->fused) {
+    const bool tcFwd = !needGrad && e->fused && e->useTc64 && vn_tc64_forward_only_available();   // loss-only pass on the tensor-core tile kernel
+    if ((needGrad && e->fused) || tcFwd) {
         // single pass: forward, in-tile residual reduction, adjoint (MODE_VAR_FUSED)
         const TileGeom& g = e->gVarAdj;
         a.ntiles = (int)(((long long)e->P + g.TP - 1) / g.TP);
@@ -1215,7 +1216,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             e->launches++;
         }
         auto launch_var = [&]() -> cudaError_t {
-            if (tc) return vn_tc64_launch(e->S, c.act, a, e->tc64Img.as<float>(), e->tcErr.as<int>(), e->gridVar, e->tc64Geom.smemBytes, st);
+            if (tc) return vn_tc64_launch(e->S, c.act, a, e->tc64Img.as<float>(), e->tcErr.as<int>(), e->gridVar, e->tc64Geom.smemBytes, st, tcFwd ? 1 : 0);
             return vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st);
         };
         {
@@ -1234,7 +1235,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             e->launches++;
         }
         }
-        if (tc) {
+        if (tc && needGrad) {
             CK(vn_tc64_reduce(e->net, e->partVar.as<double>(), e->tc64Geom.psz, e->gridVar, e->tc64Flat.as<double>(), st));
             e->launches++;
         }

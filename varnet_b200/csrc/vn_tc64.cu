@@ -36,7 +36,7 @@ constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
 
-struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING)
+struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; int fwdOnly; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING); fwdOnly: loss / lossVec / R only (v1 schedule)
 
 struct SlabLayout { int vecOff, boutOff, psz, nkind; };
 __host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     float* part = A.part32 + (size_t)blockIdx.x * sl.psz;
     double* part64 = A.part + (size_t)blockIdx.x * sl.psz;
     float* stash = A.stash + (size_t)blockIdx.x * A.stashFloats;
-    const int nImg = 2 * (L - 1);
+    const int nImg = K.fwdOnly ? (L - 1) : 2 * (L - 1);      // forward-only launches cycle through the forward images only
     uint32_t phase = 0, phaseGw = 0;
     bool ok = true;
     int imgNext = 0;                                 // next weight image of the tile sequence to be consumed
@@ -326,9 +326,11 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
 
     // weight image n of the per-tile sequence: forward layers 1..L-1, then adjoint layers L-1..1
     auto image_of = [&](int n) { return n < L - 1 ? 2 * n : 2 * (2 * L - 3 - n) + 1; };
-    auto prefetch_image = [&](int n) {
+    int stage = 0;                                   // shared-memory stage of the image in flight (the stages alternate; with an
+                                                     // odd image count per tile - forward-only launches - n & 1 would not)
+    auto prefetch_image = [&](int n, int st) {
         const float* src = K.wimg + (size_t)image_of(n) * WIMG_FLOATS;
-        float* dst = reinterpret_cast<float*>(smem + OFF_WST + (n & 1) * WIMG_BYTES);
+        float* dst = reinterpret_cast<float*>(smem + OFF_WST + st * WIMG_BYTES);
 #pragma unroll
         for (int i = 0; i < WIMG_BYTES / 16 / NT; ++i) cp_async16(dst + 4 * (i * NT + tid), src + 4 * (i * NT + tid));
         cp_async_commit();
@@ -338,10 +340,11 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     auto acquire_image = [&]() -> uint32_t {
         cp_async_wait_all();
         fence_async_smem();
-        const int n = imgNext;
+        const int n = imgNext, st = stage;
         imgNext = (n + 1 == nImg) ? 0 : n + 1;
-        prefetch_image(imgNext);
-        return smem_u32(smem + OFF_WST + (n & 1) * WIMG_BYTES);
+        stage ^= 1;
+        prefetch_image(imgNext, stage);
+        return smem_u32(smem + OFF_WST + st * WIMG_BYTES);
     };
     // publish this thread's TMEM / shared-memory writes and finished TMEM reads, then let thread 0 issue
     auto sync_for_issue = [&]() {
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         if (overwrite) __stcg(slot, v); else atomicAdd(slot, v);
     };
 
-    prefetch_image(0);
+    prefetch_image(0, 0);
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
@@ -442,12 +445,12 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
 #pragma unroll
             for (int jj = 0; jj < CPT; ++jj) { v[jj] = act64<ACT>(v[jj]); d1[jj] = act_d1<ACT>(v[jj]); }
             put_operand(tq, c0, v);
-            stash_put(stash, 0, p, c0, v, polLast);
+            if (!K.fwdOnly) stash_put(stash, 0, p, c0, v, polLast);
             for (int k = 0; k < S - 1; ++k) {
 #pragma unroll
                 for (int jj = 0; jj < CPT; ++jj) v[jj] = d1[jj] * W0s[k * W + c0 + jj];
                 put_operand(tq + 128 * (1 + k), c0, v);
-                stash_put(stash, 1 + k, p, c0, v, polLast);
+                if (!K.fwdOnly) stash_put(stash, 1 + k, p, c0, v, polLast);
             }
         }
 
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     for (int jj = 0; jj < CPT; ++jj) v[jj] *= d1[jj];
                 }
                 put_operand(tq + 128 * s, c0, v);
-                stash_put(stash, l * S + s, p, c0, v, polLast);
+                if (!K.fwdOnly) stash_put(stash, l * S + s, p, c0, v, polLast);
                 if (l == L - 1) {
                     // output layer (Dense(1)): partial dot over this thread's neurons
                     float a0 = 0.f, a1 = 0.f;
@@ -537,6 +540,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
         }
         __syncthreads();
+        if (K.fwdOnly) continue;                       // loss-only pass (splitLoss, trainWeight): R_i, lossVec and the loss partial are done
         if (tid < TP) {
             float lam = 0.f;
             if (valid) {
@@ -1349,9 +1353,11 @@ cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float*
     tc64_prep_kernel<<<dim3(32, 2 * (net.L - 1)), 256, 0, st>>>(net, theta, wimg);
     return cudaGetLastError();
 }
-cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smem, cudaStream_t st) {
+bool vn_tc64_forward_only_available() { return use_v1(); }
+cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smem, cudaStream_t st, int fwdOnly) {
     Tc64Args k;
-    k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr;
+    k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr; k.fwdOnly = fwdOnly;
+    if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
         if (!g_timBuf) { cudaMalloc(&g_timBuf, 16 * sizeof(long long)); cudaMemset(g_timBuf, 0, 16 * sizeof(long long)); }

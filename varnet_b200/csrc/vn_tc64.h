@@ -31,8 +31,10 @@ cudaError_t vn_tc64_prepare(int S, int act, size_t smemBytes);
 // theta -> hi/lo canonical K-major images [W_hi | W_lo] (forward) and [W^T_hi | W^T_lo] (adjoint) per layer
 cudaError_t vn_tc64_stage_weights(const NetDesc& net, const float* theta, float* wimg, cudaStream_t st);
 // a: as for vn_adj_kernel<MODE_VAR_FUSED> (part/part32/psz/stash/stashFloats/lossPart sized from Tc64Geom)
+// fwdOnly: loss-only pass (R, lossVec, loss partials; no stash, no gradients) — available in the default schedule only
 cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smemBytes,
-                           cudaStream_t st);
+                           cudaStream_t st, int fwdOnly = 0);
+bool vn_tc64_forward_only_available();
 // fixed-order sum of the per-CTA FP64 slabs -> flat[nparam] in reference variable order
 cudaError_t vn_tc64_reduce(const NetDesc& net, const double* slab64, int psz, int nCta, double* flat, cudaStream_t st);
 // debug: phase cycle counters of CTA 0 / thread 0 of the last v2 launch (only filled when VARNET_B200_TC64_TIMING is set)

@@ -30,8 +30,11 @@ class TableView:
     only the index list / the constants; any other consumer gets the materialised array via
     `np.asarray(view)`, bit-identical to the reference's copy."""
 
-    def __init__(self, base, tf=None, integNum=1, extra=None):
+    def __init__(self, base, tf=None, integNum=1, extra=None, gen=None):
         self.base, self.tf, self.integNum = base, tf, int(integNum)
+        # optional recipe (trainer.VarNet._gen_spec) from which a backend can rebuild `base` and its sibling tables on the device
+        # instead of receiving them (uniform mesh, constant coefficients: SURVEY section 8 f-2)
+        self.gen = gen
         self.extra = None if extra is None or np.size(extra) == 0 else np.asarray(extra, dtype=float).reshape(1, -1)
         n = len(base) if tf is None else len(tf) * self.integNum
         self.shape = (n, base.shape[1] + (0 if self.extra is None else self.extra.shape[1]))
@@ -63,7 +66,7 @@ class TableView:
         """Restrict an all-rows view to the test functions `tf`."""
         if self.tf is not None:
             raise ValueError('view is already restricted')
-        return TableView(self.base, tf, integNum, self.extra)
+        return TableView(self.base, tf, integNum, self.extra, self.gen)
 
 
 class FIXData:
@@ -224,6 +227,7 @@ class ManageTrainData:
         given = dict(biLabel=biLabel, gcoef=gcoef, source=sourceVal, diff=diff, vel=vel)
         self.MORinp.append(inpMOR)
         self.fieldNames.append(fieldnames)
+        self.__dict__.setdefault("MORgenSpec", []).append(getattr(self, "genSpec", None))
         self.MORdata.append([given[k] for k in ('biLabel', 'gcoef', 'source', 'diff', 'vel') if k in fieldnames])
         if len(self.MORinp) == self.MORbatchNum:
             self.MORdataSaved = True
@@ -234,6 +238,8 @@ class ManageTrainData:
         if batch < 0 or batch > self.MORbatchNum:
             raise ValueError('batch number out of range!')
         inpMOR, names, data = self.MORinp[batch], self.fieldNames[batch], list(self.MORdata[batch])
+        specs = getattr(self, "MORgenSpec", None)
+        self.genSpec = specs[batch] if specs else None
         if getattr(self, "_views", False):
             self.InpuTot = TableView(self.Input, None, 1, inpMOR)           # the MOR columns stay constants
         else:
@@ -284,13 +290,13 @@ class ManageTrainData:
             return TableView(table, bInd, 1)
         return table[bInd, :]
 
-    def _take(self, table, bInd, pts):
+    def _take(self, table, bInd, pts, gen=None):
         """Rows of a per-point table for the test functions bInd: a lazy TableView when the backend keeps
         tables resident, else the reference's host gather `table[pts, :]`."""
         if getattr(self, "_views", False) and self.integNum % 4 == 0:
             if isinstance(table, TableView):
                 return table.take(bInd, self.integNum)
-            return TableView(table, bInd, self.integNum)
+            return TableView(table, bInd, self.integNum, gen=gen)
         if isinstance(table, TableView):
             table = table.materialize()
         return table[pts, :]
@@ -323,7 +329,7 @@ class ManageTrainData:
             fd[tw.Input] = self._take(InpuTot, bInd, pts)
             fd[tw.biInput] = biInpuTot
             fd[tw.biLabel] = biLabel
-            fd[tw.gcoef] = self._take(gcoef, bInd, pts)
+            fd[tw.gcoef] = self._take(gcoef, bInd, pts, gen=getattr(self, "genSpec", None))
             fd[tw.source] = self._take(sourceVal, bInd, pts)
             fd[tw.N] = self._take(fixData.N, bInd, pts)
             fd[tw.bDof] = fixData.bDofsum
@@ -360,7 +366,7 @@ class ManageTrainData:
             if 'InpuTot' in fieldnames:
                 fd[tw.Input] = self._take(self.InpuTot, bInd, pts)
             if 'gcoef' in fieldnames:
-                fd[tw.gcoef] = self._take(self.gcoef, bInd, pts)
+                fd[tw.gcoef] = self._take(self.gcoef, bInd, pts, gen=getattr(self, "genSpec", None))
             if 'source' in fieldnames:
                 fd[tw.source] = self._take(self.sourceVal, bInd, pts)
 
@@ -389,7 +395,7 @@ class ManageTrainData:
             fd[tw.biInput] = biInpuTot[biInd, :]
             fd[tw.biLabel] = biLabel[biInd, :]
             fd[tw.Input] = self._take(InpuTot, bInd, pts)
-            fd[tw.gcoef] = self._take(gcoef, bInd, pts)
+            fd[tw.gcoef] = self._take(gcoef, bInd, pts, gen=getattr(self, "genSpec", None))
             fd[tw.source] = self._take(sourceVal, bInd, pts)
             if fixData.detJvec or self._views:
                 fd[tw.N] = self._take(fixData.N, bInd, pts)

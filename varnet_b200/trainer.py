@@ -178,8 +178,30 @@ class VarNet:
             tc = np.tile(t_coord, reps=[fd.dof, 1]) + ht * delta[-1, :]
             cols.append(tc.reshape(nT))
         Input = np.stack(cols, axis=1)
+        # what a backend needs to rebuild this table on the device (only valid for the plain uniform mesh)
+        self._uniform_mesh = dict(Input=Input, coord=coord, t_coord=(t_coord if td else None)) if smpScheme == 'uniform' else None
         biInput, biDof = self.biTrainPoints(mesh, t_coord)
         return Input, [], biInput, biDof
+
+    def _gen_spec(self, Input, diff, vel, src):
+        """Recipe for building this batch's point table on the device (vn_generate_table_f64) instead of uploading
+        nT-row arrays: valid when `Input` is the uniform-mesh table of `trainingPoints()` and the PDE coefficients are
+        constants over the batch (constant kappa / velocity, or a MOR batch whose parameter is one value).  The
+        device formulas and operation order are those of `trainingPoints` / `trainData` (VarNet.py:576-586,837), so the
+        generated table is bit-identical to the uploaded one (tests/test_gpu_parity.py)."""
+        um = getattr(self, "_uniform_mesh", None)
+        fd = self.fixData
+        if um is None or um["Input"] is not Input or fd.detJvec or self.tfData.lossOpt['isSource']:
+            return None
+        const = lambda a: a is not None and np.size(a) > 0 and float(np.ptp(np.asarray(a, dtype=float), axis=0).max()) == 0.0
+        if not (const(diff) and const(vel)):
+            return None
+        q = fd.integNum
+        dN = np.hstack([fd.dNx[:q], fd.dNt[:q]]) if fd.timeDependent else fd.dNx[:q]
+        return dict(coord=um["coord"], tcoord=um["t_coord"], hVec=fd.hVec, delta=fd.delta, N=fd.N[:q], dN=dN,
+                    diff=float(np.asarray(diff, dtype=float).reshape(-1)[0]),
+                    vel=np.asarray(vel, dtype=float).reshape(-1, self.dim)[0].copy(), source=0.0,
+                    nb=fd.nt, integNum=q, integW=fd.integW, detJ=fd.detJ)
 
     # ------------------------------------------------------------------ residual-driven sampling
     def optTrainPoints(self, frac=0.25, addTrainPts=True, suppFactor=1.0):
@@ -412,6 +434,10 @@ class VarNet:
             biInpuTot = [] if resCalc else np.hstack([biInput, np.tile(MORinpNN, reps=[int(np.sum(fd.biDof)), 1])])
         else:
             InpuTot, biInpuTot = Input, biInput
+        if not resCalc and gcoef is not None:
+            d_now = diff if diff is not None else diff0
+            v_now = vel if vel is not None else vel0
+            tData.genSpec = self._gen_spec(Input, d_now, v_now, src)
         tData.updateData(InpuTot, biInpuTot, biLabel, gcoef, src, diff, vel, MORinpNN)
         if fresh and not resCalc:
             tData.trainDicts(fd, self.tfData)
