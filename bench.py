@@ -288,20 +288,32 @@ def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
         t_build = time.perf_counter() - t_build
         tf = vn.tfData
 
-        def epoch():
+        chunked = fd.MORbatchNum == 1 and tData.batchNum == 1     # what VarNet.train(stepsPerCall=64) does for such configs
+
+        def epochs(n):
+            """n epochs exactly as VarNet.train takes them; returns the number of optimizer steps."""
             nonlocal tData
-            n = 0
-            for b in range(fd.MORbatchNum):
-                tData = vn.trainData(b, disc, tData)
-                tData.optimIter(tf)
-                n += tData.batchNum
-            return n
-        epoch()                                        # warm-up (also caches the MOR batches on the host)
+            if chunked:
+                done = 0
+                while done < n:
+                    k = min(64, n - done)
+                    tData.optimIterMany(tf, k)
+                    done += k
+                return n
+            steps = 0
+            for _ in range(n):
+                for b in range(fd.MORbatchNum):
+                    tData = vn.trainData(b, disc, tData)
+                    tData.optimIter(tf)
+                    steps += tData.batchNum
+            return steps
+        epochs(1)                                      # warm-up (also caches the MOR batches on the host)
         # every rank runs the same number of epochs (the steps contain a collective): fixed count from a short calibration
+        n_cal = 64 if chunked else 1
         t0 = time.perf_counter()
-        n_cal = epoch()
-        t_cal = time.perf_counter() - t0
-        n_epochs = max(1, int(budget_s / max(t_cal, 1e-6)))
+        epochs(n_cal)
+        t_cal = (time.perf_counter() - t0) / n_cal
+        n_epochs = max(1, int(budget_s / max(t_cal, 1e-7)))
         if world > 1:
             import torch
             import torch.distributed as dist
@@ -309,14 +321,14 @@ def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
             dist.broadcast(box, src=0)
             n_epochs = int(box[0])
             dist.barrier()
-        steps, t0 = 0, time.perf_counter()
-        for _ in range(n_epochs):
-            steps += epoch()
+        t0 = time.perf_counter()
+        steps = epochs(n_epochs)
         dt = time.perf_counter() - t0
         tw_loc = next(t for t in tf.compTowers if t.local)
         P = int(np.prod(tData.optimFeedicts[0][tw_loc.intShape])) * world
         out[name] = dict(steps_per_sec=steps / dt, quad_points_per_step=P, quad_pts_per_sec=steps * P / dt,
-                         steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build, n_gpus=world)
+                         steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build, n_gpus=world,
+                         host_round_trips="one per 64 steps (vn_train_steps)" if chunked else "one per step")
         if cpu_seconds > 0 and rank == 0:
             f0 = {k.name: (np.array(v) if type(v).__name__ == "TableView" else v) for k, v in tData.optimFeedicts[0].items()
                   if getattr(k, "tower", None) == tw_loc.index}

@@ -170,6 +170,9 @@ int vn_get_lossvec(vn_engine* e, float* lossVec, int64_t nb);
 int vn_check_error(vn_engine* e);
 int vn_optimizer_step(vn_engine* e, float lr);
 int vn_train_step(vn_engine* e, float lr, float* loss_out);
+/* k steps on the current batch back to back (the captured step graph replayed k times, the k losses returned together):
+ * k x sess.run([optMinimize, loss]) on an unchanged feed with one host round trip.  k <= 4096. */
+int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses);
 
 /* ---- multi-GPU (one handle per GPU, one process per GPU): the towers' gradients and losses are summed like
  *      TFNN.sum_grads / optimSetup do on the controller (TFModel.py:315-319,342-377), with one NCCL all-reduce of the

@@ -1,15 +1,29 @@
-"""profiles/r1_traffic.json from an `ncu --set full` capture of the dominant kernel on the bench workload."""
-import csv, json, subprocess, sys
-rep, workload = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-names, units, vals = rows[0], rows[1], rows[2]
-def get(n):
-    i = names.index(n); v = float(vals[i].replace(",", "")); u = units[i]
-    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-out = dict(workload=workload, kernel=vals[names.index("Kernel Name")][:80], dram_read_bytes=get("dram__bytes_read.sum"),
-           dram_write_bytes=get("dram__bytes_write.sum"), source=rep.split("/")[-1],
-           duration_ms_under_ncu=float(vals[names.index("gpu__time_duration.sum")]) * {"us": 1e-3, "ms": 1, "s": 1e3, "ns": 1e-6}[units[names.index("gpu__time_duration.sum")]])
-out["dram_bytes_per_launch"] = out["dram_read_bytes"] + out["dram_write_bytes"]
-json.dump(out, open("profiles/r1_traffic.json", "w"), indent=1)
-print(out)
+"""profiles/r2_traffic.json from the `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv`
+launch record of the dominant kernel on the bench workload (one cfg-4 launch of tc64_var_kernel):
+
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        -k regex:tc64_var -s 5 -c 1 --csv --log-file gpurun_out/traffic.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-width-sweep --no-operator-configs --e2e-steps 1
+    python scripts/make_traffic_json.py gpurun_out/traffic.csv synthetic_2dt_1e6x64_mlp4x64_tanh [other.csv label ...]
+"""
+import csv, json, sys
+
+
+def read(path):
+    vals, kernel = {}, None
+    for r in csv.reader(open(path)):
+        if len(r) >= 15 and r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            vals[r[12]] = float(r[14].replace(",", "")); kernel = r[4]
+    return dict(kernel=kernel[:80], dram_read_bytes=vals["dram__bytes_read.sum"], dram_write_bytes=vals["dram__bytes_write.sum"],
+                duration_ms_under_ncu=vals["gpu__time_duration.sum"] * 1e-6,
+                dram_bytes_per_launch=vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], source=path.split("/")[-1])
+
+
+out = read(sys.argv[1])
+out["workload"] = sys.argv[2]
+out["algorithmic_bytes_per_launch"] = 24 * 64000000
+out["ratio_to_algorithmic"] = out["dram_bytes_per_launch"] / out["algorithmic_bytes_per_launch"]
+rest = sys.argv[3:]
+out["variants"] = {label: read(path) for path, label in zip(rest[0::2], rest[1::2])}
+json.dump(out, open("profiles/r2_traffic.json", "w"), indent=1)
+print(json.dumps(out, indent=1))

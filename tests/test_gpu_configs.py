@@ -251,3 +251,30 @@ def test_trainer_generates_uniform_tables_on_the_device(name, scale, batchNum):
     assert len(on[0]) == len(off[0]) > 0
     for (la, ga), (lb, gb) in zip(on[0], off[0]):
         assert la == lb and np.array_equal(ga, gb)
+
+
+def test_train_steps_equals_single_steps():
+    """vn_train_steps (k steps per host round trip: the step graph replayed k times, losses from the device ring) gives the
+    same losses and the same weights, bit for bit, as k vn_train_step calls; VarNet.train uses it through stepsPerCall."""
+    import varnet_b200
+    rng = np.random.RandomState(3)
+    feed = synth_feed(rng, 1, 2, 600, 16, 62, 60)
+    lw = [20]
+    theta = go.glorot_init(2, lw, seed=4)
+    kw = dict(dim=1, inpDim=2, layerWidth=lw, activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    a = make_engine(feed, theta=theta, **kw)
+    b = make_engine(feed, theta=theta, **kw)
+    one = np.array([a.train_step(1e-3) for _ in range(37)], dtype=np.float32)
+    many = np.concatenate([b.train_steps(1e-3, 5), b.train_steps(1e-3, 32)])
+    assert np.array_equal(one, many)
+    assert np.array_equal(a.get_params(), b.get_params())
+    a.close(); b.close()
+    # the trainer's chunked epochs reproduce the per-epoch loop
+    hist = {}
+    for spc in (1, 16):
+        vn = configs.operator_1dt(varnet_b200, 0.3, seed=5)
+        with tempfile.TemporaryDirectory() as d:
+            res = vn.train(d, weight=[10., 10., 1.], epochNum=50, saveFreq=20, verbose=False, stepsPerCall=spc)
+        hist[spc] = (np.array(res.loss, dtype=np.float64), vn.tfData.get_parameters().copy())
+        vn.tfData.sess.close()
+    assert np.array_equal(hist[1][0], hist[16][0]) and np.array_equal(hist[1][1], hist[16][1])

@@ -64,6 +64,7 @@ SIGNATURES = {
     "vn_debug_tc64_timing": (C.c_int, [C.POINTER(_i64)]),
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
+    "vn_train_steps": (C.c_int, [_vp, C.c_float, _i32, _f32p]),
     "vn_comm_unique_id": (C.c_int, [C.c_char_p, _vp]),
     "vn_comm_init": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _i32]),
     "vn_comm_world": (C.c_int, [_vp]),
@@ -405,6 +406,12 @@ class Engine:
             return np.float32(out.value)
         self._check(self.lib.vn_train_step(self._h, float(lr), None))
         return None
+
+    def train_steps(self, lr, k):
+        """k optimizer steps on the current batch with one host round trip; returns the k losses."""
+        out = np.empty(int(k), dtype=np.float32)
+        self._check(self.lib.vn_train_steps(self._h, float(lr), int(k), _ptr(out, C.c_float)))
+        return out
 
     # -- evaluation
     def eval(self, X):

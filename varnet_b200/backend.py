@@ -371,6 +371,26 @@ class Session:
         n = towers[0].engine.nparam
         return float(views[0][n].item())
 
+    def run_many(self, feed_dict, k):
+        """k x `run([optMinimize, loss], feed_dict)` on an unchanged feed: the list of the k losses.  One tower per process
+        (single GPU, or torchrun with the native communicator): the engine replays its captured step graph k times and
+        the losses come back in one transfer (vn_train_steps); otherwise k ordinary runs."""
+        o = self._o
+        towers = self._local_towers()
+        k = int(k)
+        fast = (k > 1 and len(towers) == 1 and hasattr(towers[0].engine, "train_steps") and o.feed_cache and
+                (_dist() is None or o.native_comm))
+        if not fast:
+            return [self.run([o.optMinimize, o.loss], feed_dict)[1] for _ in range(k)]
+        self._sync_feeds(feed_dict)
+        out = []
+        while k > 0:
+            n = min(k, 4096)
+            out.extend(np.float32(v) for v in towers[0].engine.train_steps(o.learning_rate, n))
+            k -= n
+        o.step_count += len(out)
+        return out
+
     def _gradients(self):
         o = self._o
         towers = self._local_towers()

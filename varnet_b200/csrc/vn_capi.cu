@@ -174,7 +174,10 @@ __device__ __forceinline__ void advance_step(long long* step, double* corr) {
     const double tn = (double)(t + 1);     // bias correction of the NEXT step
     corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
 }
-__global__ void vn_advance_kernel(long long* step, double* corr, const int* err) { if (!(err && *err)) advance_step(step, corr); }
+__global__ void vn_advance_kernel(long long* step, double* corr, const int* err, float* lossRing, int ringSize, const float* lossPtr) {
+    if (lossRing) lossRing[(unsigned long long)step[0] % (unsigned long long)ringSize] = *lossPtr;       // loss of the step being applied
+    if (!(err && *err)) advance_step(step, corr);
+}
 
 // Blocks [0, gridDim.x-1): one WARP per flat parameter sums the per-CTA FP64 slabs: lane c takes slabs
 // c, c+32, ... in order and the lanes are combined by a fixed xor tree (deterministic replacement for
@@ -251,6 +254,9 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         const float loss = bad ? __int_as_float(0x7fc00000) : A.wts[0] * bCs + A.wts[1] * iCs + A.wts[2] * varLoss;
         float* o = A.gbuf + net.nparam;
         o[0] = loss; o[1] = bCs; o[2] = iCs; o[3] = varLoss;
+        // loss history of back-to-back steps (vn_train_steps): the step counter is advanced only after every block of this
+        // grid has taken its ticket, i.e. after this store
+        if (A.fuseOpt && A.lossRing) A.lossRing[(unsigned long long)A.step[0] % (unsigned long long)A.ringSize] = loss;
     }
     }
     if (A.fuseOpt) {
@@ -405,7 +411,7 @@ struct vn_engine {
     bool indexed = false;        // batch = index list into the table (else: the whole table in order)
     int nExtra = 0;              // trailing MLP inputs supplied as per-call constants (MOR parameters)
     // parameters + optimizer
-    DevBuf theta, m, v, gbuf, wts, stepbuf, corrbuf;
+    DevBuf theta, m, v, gbuf, wts, stepbuf, corrbuf, lossRing;
     // interior points of the current batch (P = nb * integNum)
     DevBuf Iw, R, lossVec, segSum;
     unsigned int P = 0, nb = 0;
@@ -446,6 +452,7 @@ struct ProfScope {
 };
 
 static const int kPad = 256;
+static const int kLossRing = 4096;      // loss history kept on the device for back-to-back steps (vn_train_steps)
 
 static void drop_graph(PointSet* t) {
     if (t && t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
@@ -581,6 +588,7 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
     CK(e->stepbuf.ensure(sizeof(long long)));
     CK(e->corrbuf.ensure(sizeof(double)));
     CK(e->ticket.ensure(sizeof(unsigned int)));
+    CK(e->lossRing.ensure(kLossRing * sizeof(float)));
     CK(cudaMemset(e->ticket.p, 0, sizeof(unsigned int)));
     CK(cudaMemset(e->theta.p, 0, np * sizeof(float)));
     CK(cudaMemset(e->gbuf.p, 0, (np + 4) * sizeof(float)));
@@ -607,7 +615,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->lossRing};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -1292,6 +1300,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             f.fuseOpt = c.optimizer == VN_OPT_ADAM ? 1 : 2; f.lr = fuseLr;
             f.theta = e->theta.as<float>(); f.m = e->m.as<float>(); f.v = e->v.as<float>();
             f.step = e->stepbuf.as<long long>(); f.corr = e->corrbuf.as<double>(); f.ticket = e->ticket.as<unsigned int>();
+            f.lossRing = e->lossRing.as<float>(); f.ringSize = kLossRing;
         }
         const int nb = needGrad ? (e->net.nparam + 3) / 4 : 0;          // one warp per parameter, 4 warps per block
         ProfScope ps(e, PK_FINAL);
@@ -1460,12 +1469,13 @@ extern "C" int vn_optimizer_step(vn_engine* e, float lr) {
         vn_rmsprop_kernel<<<(np + 255) / 256, 256, 0, e->stream>>>(e->theta.as<float>(), e->v.as<float>(),
                                                                    e->gbuf.as<float>(), np, lr, e->tcErr.as<int>());
     CK(cudaGetLastError());
-    vn_advance_kernel<<<1, 1, 0, e->stream>>>(e->stepbuf.as<long long>(), e->corrbuf.as<double>(), e->tcErr.as<int>());
+    vn_advance_kernel<<<1, 1, 0, e->stream>>>(e->stepbuf.as<long long>(), e->corrbuf.as<double>(), e->tcErr.as<int>(),
+                                              e->lossRing.as<float>(), kLossRing, e->gbuf.as<float>() + np);
     CK(cudaGetLastError());
     e->launches += 2;
     return VN_OK;
 }
-extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
+static int train_step_enqueue(vn_engine* e, float lr) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (lr < 0.f) return fail(VN_E_INVALID, "learning rate must be positive!");
     CK(cudaSetDevice(e->cfg.device));
@@ -1520,15 +1530,41 @@ extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
         int rc = step_once();
         if (rc) return rc;
     }
+    return VN_OK;
+}
+extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
+    int rc = train_step_enqueue(e, lr);
+    if (rc) return rc;
     if (loss_out) {
         // the loss read is also where an expired tensor-core barrier wait of this (or an earlier unfetched) step surfaces:
         // the reduction kernel published NaN and skipped the optimizer update, here the caller gets VN_E_CUDA
         float sc[4];
-        int rc = read_scalars(e, sc);
+        rc = read_scalars(e, sc);
         *loss_out = sc[0];
         if (rc) return rc;
     }
     return VN_OK;
+}
+// k optimizer steps on the current batch back to back, one host round trip: the captured step graph is replayed k times and
+// the k losses come back together (the reference reads the loss of every step, VarNetUtility.py:1044, but only acts on it
+// per epoch: tolerance test VarNet.py:1378, bookkeeping every saveFreq epochs).  For the launch-bound operator configurations
+// this removes the per-step synchronisation and readback.  k <= 4096.
+extern "C" int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses) {
+    if (!e || !losses) return fail(VN_E_INVALID, "null argument");
+    if (k < 1 || k > kLossRing) return fail(VN_E_INVALID, "k must be in [1, %d]", kLossRing);
+    CK(cudaSetDevice(e->cfg.device));
+    long long step0 = 0;
+    CK(cudaMemcpyAsync(&step0, e->stepbuf.p, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < k; ++i) {
+        int rc = train_step_enqueue(e, lr);
+        if (rc) return rc;
+    }
+    const int a = (int)(step0 % kLossRing), n1 = std::min(k, kLossRing - a);
+    CK(cudaMemcpyAsync(losses, e->lossRing.as<float>() + a, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (k > n1) CK(cudaMemcpyAsync(losses + n1, e->lossRing.as<float>(), (size_t)(k - n1) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    float sc[4];
+    return read_scalars(e, sc);              // synchronises; reports an expired tensor-core barrier wait
 }
 
 // ------------------------------------------------------------------ evaluation

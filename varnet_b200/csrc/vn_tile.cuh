@@ -874,5 +874,6 @@ struct FinalArgs {
     long long* step; double* corr;          // device step counter and Adam bias-correction factor (advanced by the last block)
     unsigned int* ticket;                   // zero-initialised block counter
     const int* err;                         // tensor-core classes: non-zero = an mbarrier wait expired in this step (or nullptr)
+    float* lossRing; int ringSize;          // fused optimizer: loss of step t is also left in lossRing[t % ringSize] (vn_train_steps)
 };
 __global__ void vn_finalize_kernel(FinalArgs A);

@@ -415,6 +415,15 @@ class ManageTrainData:
             total += val
         return total
 
+    def optimIterMany(self, tfData, epochs):
+        """`epochs` consecutive optimIter() calls on unchanged feeds; returns the list of their summed losses.  With a single
+        mini-batch per epoch the backend takes all the steps in one call (Session.run_many)."""
+        if not hasattr(self, 'optimFeedicts'):
+            raise Exception('\'trainDicts\' must be called first to construct training dictionaries!')
+        if len(self.optimFeedicts) == 1 and hasattr(tfData.sess, "run_many"):
+            return list(tfData.sess.run_many(self.optimFeedicts[0], epochs))
+        return [self.optimIter(tfData) for _ in range(int(epochs))]
+
     def splitLoss(self, tfData, lossVecflag):
         if not hasattr(self, 'optimFeedicts'):
             raise Exception('\'trainDicts\' must be called first to construct training dictionaries!')

@@ -489,7 +489,13 @@ class VarNet:
               saveFreq=100, pltReplace=True, saveMORdata=False, frac=None, addTrainPts=True, suppFactor=1.0,
               multiTrainUpd=False, trainUpdelay=2e4, tolUpd=0.01, reinitrain=True, updateWeights=False,
               normalizeW=False, adjustWeight=False, useOriginalW=False, batchNum=None, batchLen=None,
-              shuffleData=False, shuffleFreq=1):
+              shuffleData=False, shuffleFreq=1, stepsPerCall=64):
+        """The reference's training loop (VarNet.py:1197-1421).  `stepsPerCall` (extension): when an epoch is one optimizer step on
+        unchanged feeds (no MOR batches, one mini-batch, no shuffling, no pending re-sampling) up to that many epochs are
+        taken per backend call, never across a `saveFreq` boundary; the per-epoch bookkeeping, the `tol` test and the loss
+        history are applied to each returned loss in order.  If the tolerance is met inside a chunk the history stops at that
+        epoch while the weights have seen the rest of the chunk (at most stepsPerCall-1 further steps).  stepsPerCall=1
+        restores the reference's one-host-round-trip-per-epoch behaviour exactly."""
         if folderpath is None or is_empty(folderpath):
             raise ValueError('a folder path must be provided to backup the trained model!')
         self.folderpath = folderpath
@@ -537,51 +543,65 @@ class VarNet:
         tp_epoch, tp_updates = 1, 0
         resVal = err = lossComp = lossVec = None
         best = os.path.join(folderpath, 'best_model')
-        for epoch in range(1, epochNum + 1):
+        epoch, stop = 0, False
+        while epoch < epochNum and not stop:
+            # epochs that can be taken in one backend call
+            K = 1
+            if (stepsPerCall and stepsPerCall > 1 and fixData.MORbatchNum == 1 and not shuffleData and
+                    getattr(tData, 'batchNum', None) == 1 and hasattr(tData, 'optimFeedicts') and not tData.inputUpdated and
+                    (smpScheme == 'uniform' or (tp_updates > 0 and not multiTrainUpd))):
+                K = int(max(1, min(stepsPerCall, epochNum - epoch, saveFreq - epoch % saveFreq)))
             t0 = time.perf_counter()
-            current_loss = 0
-            for batch in range(fixData.MORbatchNum):
-                tData = self.trainData(batch, MORdiscArg, tData)
-                current_loss += tData.optimIter(tf)
+            if K > 1:
+                losses = tData.optimIterMany(tf, K)
+            else:
+                current_loss = 0
+                for batch in range(fixData.MORbatchNum):
+                    tData = self.trainData(batch, MORdiscArg, tData)
+                    current_loss += tData.optimIter(tf)
+                losses = [current_loss]
             epoch_time += time.perf_counter() - t0
-            if shuffleData and epoch % shuffleFreq == 0:
-                tData.shuffleTrainData(fixData)
-            if epoch % saveFreq == 0:
-                if min_loss > current_loss:
-                    min_loss = current_loss
-                    if tf.rank == 0:
-                        tf.saver.save(tf.sess, best, global_step=epoch)
-                try:
-                    resVal, _, err, _ = self.residual()
-                except Exception as ex:                                 # monitoring only
-                    resVal, err = None, None
-                    self.trainRes.writeCase('residual monitoring unavailable: %s' % ex)
-                lossComp, _, lossVec = self.splitLoss(tData0, fixData0)
-            self.trainRes.iterOutput(epoch, current_loss, min_loss, epoch_time, resVal, err, lossComp, lossVec)
-            if current_loss < tol:
-                self.trainRes.writeCase('Training completed!')
-                if verbose:
-                    print('Training completed!')
-                break
-            if smpScheme != 'uniform' and (multiTrainUpd or tp_updates == 0) and (epoch - tp_epoch) >= (trainUpdelay - 1):
-                recent = np.array(self.trainRes.loss[-5:])
-                drop = recent[:-1] - recent[1:]
-                if np.sum(drop[drop > 0]) / recent[-1] < tolUpd:          # plateau: re-sample (VarNet.py:1385-1421)
-                    min_loss = float('inf')
-                    tp_epoch, tp_updates = epoch, tp_updates + 1
-                    self.trainRes.inpIter.append(epoch)
-                    Input, _, biInput, _ = self.trainingPoints(smpScheme, frac, addTrainPts, suppFactor)
-                    if addTrainPts:
-                        fixData = self.fixData
-                    tData = ManageTrainData(Input, biInput, batchNum, batchLen, saveMORdata, fixData.MORbatchNum)
-                    self.trainRes.writeCase('Training points updated at epoch %d.' % epoch)
-                    if reinitrain:
-                        tf.sess.run(GlobalInit())
-                        self.trainRes.writeCase('trainable variables reinitialized.')
-                    if adjustWeight:
-                        weight = [5 * w for w in weight[:-1]] + [weight[-1]]
-                    trainW, tData, _ = self.trainWeight(weight, tData, MORdiscArg, normalizeW, useOriginalW)
-                    tData.updateDictFields('trainW', trainW)
+            for current_loss in losses:
+                epoch += 1
+                if shuffleData and epoch % shuffleFreq == 0:
+                    tData.shuffleTrainData(fixData)
+                if epoch % saveFreq == 0:
+                    if min_loss > current_loss:
+                        min_loss = current_loss
+                        if tf.rank == 0:
+                            tf.saver.save(tf.sess, best, global_step=epoch)
+                    try:
+                        resVal, _, err, _ = self.residual()
+                    except Exception as ex:                                 # monitoring only
+                        resVal, err = None, None
+                        self.trainRes.writeCase('residual monitoring unavailable: %s' % ex)
+                    lossComp, _, lossVec = self.splitLoss(tData0, fixData0)
+                self.trainRes.iterOutput(epoch, current_loss, min_loss, epoch_time, resVal, err, lossComp, lossVec)
+                if current_loss < tol:
+                    self.trainRes.writeCase('Training completed!')
+                    if verbose:
+                        print('Training completed!')
+                    stop = True
+                    break
+                if smpScheme != 'uniform' and (multiTrainUpd or tp_updates == 0) and (epoch - tp_epoch) >= (trainUpdelay - 1):
+                    recent = np.array(self.trainRes.loss[-5:])
+                    drop = recent[:-1] - recent[1:]
+                    if np.sum(drop[drop > 0]) / recent[-1] < tolUpd:          # plateau: re-sample (VarNet.py:1385-1421)
+                        min_loss = float('inf')
+                        tp_epoch, tp_updates = epoch, tp_updates + 1
+                        self.trainRes.inpIter.append(epoch)
+                        Input, _, biInput, _ = self.trainingPoints(smpScheme, frac, addTrainPts, suppFactor)
+                        if addTrainPts:
+                            fixData = self.fixData
+                        tData = ManageTrainData(Input, biInput, batchNum, batchLen, saveMORdata, fixData.MORbatchNum)
+                        self.trainRes.writeCase('Training points updated at epoch %d.' % epoch)
+                        if reinitrain:
+                            tf.sess.run(GlobalInit())
+                            self.trainRes.writeCase('trainable variables reinitialized.')
+                        if adjustWeight:
+                            weight = [5 * w for w in weight[:-1]] + [weight[-1]]
+                        trainW, tData, _ = self.trainWeight(weight, tData, MORdiscArg, normalizeW, useOriginalW)
+                        tData.updateDictFields('trainW', trainW)
         return self.trainRes
 
     # ------------------------------------------------------------------ evaluation
