@@ -168,6 +168,26 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(sm))
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU (one process per GPU under torchrun): the pinned host
+    feed of the e2e legs is then allocated on the NUMA node whose PCIe root the GPU hangs off, instead of wherever the
+    launcher happened to start the process.  Best effort; returns the CPU count it bound to, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_feed(nx, ny, ntime, sample_tf):
     """Bounded sample of the same workload for the CPU legs: the first `sample_tf` test functions."""
     from varnet_b200 import workloads
@@ -410,6 +430,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the varnet_b200 engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    # N > 1: pinned staging buffers are first-touched on the GPU's own NUMA node (N = 1 keeps all cores for the CPU-baseline legs)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from varnet_b200 import workloads
@@ -477,9 +499,11 @@ def main():
     # graph at N > 1, boundary/initial rows on the auxiliary stream).  Every step also gets its own event pair so that a
     # straggling rank or step can be named.
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()            # before the barrier: starting the NVML thread takes milliseconds that the other ranks would
+                                   # otherwise spend waiting for rank 0 inside the first timed all-reduce
+        time.sleep(0.05)
+    barrier()
     l0 = eng.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
@@ -633,7 +657,7 @@ def main():
                     e2e_f64=dict(value=P_total / (ms_e2e64 * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d64), d2h_bytes_per_step=4,
                                  ms_per_step=ms_e2e64, steps=args.e2e_steps, feed="float64 NumPy arrays in pageable memory, as the reference's callers feed them (VarNetUtility.py:840-854)",
                                  api="TFNN.sess.run([optMinimize, loss], feed_dict) with feed_cache=False (vn_loss_grad_fed_f64)"),
-                    gpu_launches=int(launches), clocks=clocks, kernel_info=eng.kernel_info())
+                    gpu_launches=int(launches), clocks=clocks, kernel_info=eng.kernel_info(), cpus_bound_to_gpu_numa_node=numa)
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args, nx, ny, ntime, lw, act, steps=50, warmup=1, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
