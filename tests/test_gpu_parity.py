@@ -232,8 +232,10 @@ def test_deep_and_ragged_networks_match_oracle():
 
 
 @pytest.mark.gpu
-def test_fed_step_overlapping_copies_equals_upload_then_step():
-    """vn_loss_grad_fed (table uploaded chunk by chunk while the adjoint kernel already runs on the first chunks)
+@pytest.mark.parametrize("feed_dtype", [np.float32, np.float64])
+def test_fed_step_overlapping_copies_equals_upload_then_step(feed_dtype):
+    """vn_loss_grad_fed (table uploaded chunk by chunk while the adjoint kernel already runs on the first chunks; pageable NumPy
+    arrays — float32 or the reference's float64 — go through the multi-threaded pinned bounce buffers)
     against vn_upload_points + vn_loss_grad on the same feed, on a table of more than one 4 Mi-row chunk; then the
     shim path: sess.run with feed_cache=False goes through the fed call and follows the same Adam trajectory."""
     from varnet_b200._capi import Engine
@@ -251,7 +253,7 @@ def test_fed_step_overlapping_copies_equals_upload_then_step():
         eng.upload_bic(bX, bL, 300, 2.0)
         eng.set_weights([3.0, 5.0, 7.0])
         if fed:
-            eng.loss_grad_fed(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+            eng.loss_grad_fed(X.astype(feed_dtype), G.astype(feed_dtype), None, None, dNt.astype(feed_dtype), [nb, q], None, 1.3e-6, False)
         else:
             eng.upload_points(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
         r = eng.loss_grad() if not fed else None

@@ -7,7 +7,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -350,6 +355,62 @@ __global__ void vn_cast_kernel(const T* __restrict__ in, float* __restrict__ out
     if (r < n) out[r] = to_f32<T>(in[r]);
 }
 
+// ------------------------------------------------------------------ host staging of pageable feeds
+// cudaMemcpyAsync out of pageable memory is staged by the driver with one host thread (~11 GB/s measured for the 3 GB float64
+// feed of a cfg-4 step).  The fed step instead copies each sub-chunk of the caller's arrays into one of two engine-owned pinned
+// buffers with a few host threads and lets the DMA engine take it from there, so the host copy of sub-chunk k+1 overlaps the
+// transfer of sub-chunk k.  A tiny persistent pool: run(n, f) executes f(0..n-1) on the workers and the caller.
+class HostPool {
+public:
+    explicit HostPool(int nthreads) {
+        for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        if (n <= 0) return;
+        { std::lock_guard<std::mutex> lk(m_); f_ = &f; next_ = 0; total_ = n; done_ = 0; ++gen_; }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cvDone_.wait(lk, [this] { return done_ == total_; });
+        f_ = nullptr;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+private:
+    void work() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            { std::lock_guard<std::mutex> lk(m_); if (!f_ || next_ >= total_) return; i = next_++; f = f_; }
+            (*f)(i);
+            { std::lock_guard<std::mutex> lk(m_); if (++done_ == total_) cvDone_.notify_all(); }
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, cvDone_;
+    const std::function<void(int)>* f_ = nullptr;
+    int next_ = 0, total_ = 0, done_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 // ------------------------------------------------------------------ engine
 enum { PK_VAR_FWD = 0, PK_SEG = 1, PK_VAR_ADJ = 2, PK_BIC = 3, PK_FINAL = 4, PK_OPT = 5 };
 // Bumped whenever a live device buffer is freed and re-allocated: captured step graphs bake device pointers in, so a graph
@@ -394,6 +455,9 @@ struct vn_engine {
     // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> fedEvents;
+    // pageable feeds: two pinned bounce buffers, the event of the last transfer out of each, and the copy threads
+    void* pin[2] = {nullptr, nullptr}; size_t pinBytes = 0; cudaEvent_t pinEv[2] = {nullptr, nullptr}; int pinNext = 0;
+    HostPool* pool = nullptr;
     // boundary/initial adjoint kernel runs concurrently with the variational one (fork/join, also inside the step graph)
     cudaStream_t auxStream = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -611,6 +675,8 @@ extern "C" int vn_destroy(vn_engine* e) {
     if (e->evFork) cudaEventDestroy(e->evFork);
     if (e->evJoin) cudaEventDestroy(e->evJoin);
     for (cudaEvent_t ev : e->fedEvents) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pinEv[i]) cudaEventDestroy(e->pinEv[i]); }
+    delete e->pool;
     for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
@@ -764,8 +830,71 @@ static int ensure_work(vn_engine* e) {
 // on the engine stream as soon as that chunk is packed (cudaStreamWaitEvent): copies overlap the step's kernels.
 struct FedPlan {
     struct Sub { int tile0, ntiles; cudaEvent_t ev; };
-    std::vector<Sub> subs;
+    // chunk k of the table: staged, copied and packed on the copy stream when run_loss asks for it, so that the host-side staging
+    // of chunk k+1 (pageable feeds) runs while the kernel of chunk k is already executing.  Returns 1 (produced), 0 (done), < 0 (error).
+    std::function<int(size_t, Sub*)> produce;
 };
+
+static const long long kSubChunk = 1 << 20;      // rows per pinned bounce buffer
+static int ensure_stager(vn_engine* e, size_t bytes) {
+    if (!e->pool) {
+        int n = 8;
+        if (const char* v = getenv("VARNET_B200_STAGE_THREADS")) n = atoi(v);
+        const int hw = (int)std::thread::hardware_concurrency();
+        n = std::max(1, std::min(n, hw > 0 ? hw : 1));
+        e->pool = new HostPool(n - 1);
+    }
+    if (bytes > e->pinBytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (e->pinEv[i]) CK(cudaEventSynchronize(e->pinEv[i]));
+            if (e->pin[i]) { cudaFreeHost(e->pin[i]); e->pin[i] = nullptr; }
+            CK(cudaHostAlloc(&e->pin[i], bytes, cudaHostAllocDefault));
+            if (!e->pinEv[i]) CK(cudaEventCreateWithFlags(&e->pinEv[i], cudaEventDisableTiming));
+        }
+        e->pinBytes = bytes;
+    }
+    return VN_OK;
+}
+// rows [off, off + n) of the caller's pageable arrays -> the device staging blocks, through the pinned bounce buffers
+template <typename T>
+static int stage_pageable(vn_engine* e, cudaStream_t us, const T* X, int nx, const T* G, int dim, const T* dNt, const T* src, const T* N,
+                          long long off, long long n, T* sX, T* sG, T* sT, T* sS, T* sN) {
+    const int rowVals = nx + dim + (dNt ? 1 : 0) + (src ? 2 : 0);
+    int rc = ensure_stager(e, (size_t)kSubChunk * rowVals * sizeof(T));
+    if (rc) return rc;
+    for (long long r0 = 0; r0 < n; r0 += kSubChunk) {
+        const long long m = std::min(kSubChunk, n - r0);
+        const int b = e->pinNext;
+        e->pinNext ^= 1;
+        CK(cudaEventSynchronize(e->pinEv[b]));           // the previous transfer out of this buffer has finished
+        T* pX = reinterpret_cast<T*>(e->pin[b]);
+        T* pG = pX + m * nx;
+        T* pT = pG + m * dim;
+        T* pS = pT + (dNt ? m : 0);
+        T* pN = pS + (src ? m : 0);
+        struct Seg { void* dst; const void* srcp; size_t bytes; };
+        Seg segs[5] = {{pX, X + (off + r0) * nx, (size_t)m * nx * sizeof(T)}, {pG, G + (off + r0) * dim, (size_t)m * dim * sizeof(T)},
+                       {pT, dNt ? dNt + off + r0 : nullptr, dNt ? (size_t)m * sizeof(T) : 0}, {pS, src ? src + off + r0 : nullptr, src ? (size_t)m * sizeof(T) : 0},
+                       {pN, N && src ? N + off + r0 : nullptr, (N && src) ? (size_t)m * sizeof(T) : 0}};
+        const int parts = e->pool->size();
+        e->pool->run(parts, [&](int i) {
+            for (const Seg& sg : segs) {
+                if (!sg.bytes) continue;
+                const size_t lo = sg.bytes * (size_t)i / parts / 64 * 64, hi = (i + 1 == parts) ? sg.bytes : sg.bytes * (size_t)(i + 1) / parts / 64 * 64;
+                if (hi > lo) memcpy(static_cast<char*>(sg.dst) + lo, static_cast<const char*>(sg.srcp) + lo, hi - lo);
+            }
+        });
+        CK(cudaMemcpyAsync(sX + r0 * nx, pX, (size_t)m * nx * sizeof(T), cudaMemcpyHostToDevice, us));
+        CK(cudaMemcpyAsync(sG + r0 * dim, pG, (size_t)m * dim * sizeof(T), cudaMemcpyHostToDevice, us));
+        if (dNt) CK(cudaMemcpyAsync(sT + r0, pT, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
+        if (src) {
+            CK(cudaMemcpyAsync(sS + r0, pS, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
+            CK(cudaMemcpyAsync(sN + r0, pN, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
+        }
+        CK(cudaEventRecord(e->pinEv[b], us));
+    }
+    return VN_OK;
+}
 
 template <typename T>
 static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* src, const T* N, const T* dNt,
@@ -820,20 +949,30 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
             for (int cc = 0; cc < t->ncols; ++cc)
                 CK(cudaMemsetAsync(t->cols.as<float>() + (size_t)cc * t->pstride + P, 0, (size_t)(t->pstride - P) * sizeof(float), us));
         const int TP = (e->tc64 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
-        size_t k = 0;
-        for (long long off = 0; off < P; off += chunk, ++k) {
+        // pageable caller arrays (what NumPy hands over) are staged through pinned bounce buffers by a few host threads
+        static const bool stagerOff = [] { const char* v = getenv("VARNET_B200_STAGE_THREADS"); return v && atoi(v) <= 0; }();
+        const bool pageable = !stagerOff && is_pageable(X) && is_pageable(G);
+        plan->produce = [=](size_t k, FedPlan::Sub* out) -> int {
+            const long long off = (long long)k * chunk;
+            if (off >= P) return 0;
             const long long n = std::min(chunk, P - off);
             T* sX = e->stage.as<T>();
             T* sG = sX + n * nx;
             T* sT = sG + n * c.dim;
             T* sS = sT + n;
             T* sN = sS + n;
-            CK(cudaMemcpyAsync(sX, X + off * nx, n * nx * sizeof(T), cudaMemcpyHostToDevice, us));
-            CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, us));
-            if (t->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
-            if (t->colS >= 0) {
-                CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
-                CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+            if (pageable) {
+                int rcs = stage_pageable<T>(e, us, X, nx, G, c.dim, t->colT >= 0 ? dNt : nullptr, t->colS >= 0 ? src : nullptr,
+                                            t->colS >= 0 ? N : nullptr, off, n, sX, sG, sT, sS, sN);
+                if (rcs) return rcs;
+            } else {
+                CK(cudaMemcpyAsync(sX, X + off * nx, n * nx * sizeof(T), cudaMemcpyHostToDevice, us));
+                CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, us));
+                if (t->colT >= 0) CK(cudaMemcpyAsync(sT, dNt + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+                if (t->colS >= 0) {
+                    CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+                    CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
+                }
             }
             vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, us>>>(
                 sX, nx, sG, c.dim, t->colT >= 0 ? sT : nullptr, t->colS >= 0 ? sS : nullptr,
@@ -846,8 +985,9 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
                 e->fedEvents.push_back(ev);
             }
             CK(cudaEventRecord(e->fedEvents[k], us));
-            plan->subs.push_back({(int)(off / TP), (int)((n + TP - 1) / TP), e->fedEvents[k]});
-        }
+            *out = {(int)(off / TP), (int)((n + TP - 1) / TP), e->fedEvents[k]};
+            return 1;
+        };
         t->loaded = true;
         e->indexed = false;
         e->nb = t->nbTab;
@@ -1231,9 +1371,13 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         ProfScope ps(e, PK_VAR_ADJ);
         if (plan) {
             // one launch per uploaded chunk, each waiting for its own pack kernel on the copy stream
-            for (size_t k = 0; k < plan->subs.size(); ++k) {
-                CK(cudaStreamWaitEvent(st, plan->subs[k].ev, 0));
-                a.tile0 = plan->subs[k].tile0; a.ntiles = plan->subs[k].ntiles; a.accumulate = k > 0 ? 1 : 0;
+            for (size_t k = 0;; ++k) {
+                FedPlan::Sub sub;
+                const int pr = plan->produce(k, &sub);
+                if (pr < 0) return pr;
+                if (pr == 0) break;
+                CK(cudaStreamWaitEvent(st, sub.ev, 0));
+                a.tile0 = sub.tile0; a.ntiles = sub.ntiles; a.accumulate = k > 0 ? 1 : 0;
                 CK(launch_var());
                 e->launches++;
             }
