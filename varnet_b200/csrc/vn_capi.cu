@@ -855,41 +855,45 @@ static int ensure_stager(vn_engine* e, size_t bytes) {
     }
     return VN_OK;
 }
-// rows [off, off + n) of the caller's pageable arrays -> the device staging blocks, through the pinned bounce buffers
+// rows [off, off + n) of the caller's pageable arrays -> the device staging blocks, through the pinned bounce buffers.  The host
+// threads also do the feed cast: float64 arrays are rounded to float32 (round-to-nearest-even, the same rounding as the
+// placeholder cast and as __double2float_rn) while they are copied, which halves the pinned traffic and the PCIe transfer.
 template <typename T>
 static int stage_pageable(vn_engine* e, cudaStream_t us, const T* X, int nx, const T* G, int dim, const T* dNt, const T* src, const T* N,
-                          long long off, long long n, T* sX, T* sG, T* sT, T* sS, T* sN) {
+                          long long off, long long n, float* sX, float* sG, float* sT, float* sS, float* sN) {
     const int rowVals = nx + dim + (dNt ? 1 : 0) + (src ? 2 : 0);
-    int rc = ensure_stager(e, (size_t)kSubChunk * rowVals * sizeof(T));
+    int rc = ensure_stager(e, (size_t)kSubChunk * rowVals * sizeof(float));
     if (rc) return rc;
     for (long long r0 = 0; r0 < n; r0 += kSubChunk) {
         const long long m = std::min(kSubChunk, n - r0);
         const int b = e->pinNext;
         e->pinNext ^= 1;
         CK(cudaEventSynchronize(e->pinEv[b]));           // the previous transfer out of this buffer has finished
-        T* pX = reinterpret_cast<T*>(e->pin[b]);
-        T* pG = pX + m * nx;
-        T* pT = pG + m * dim;
-        T* pS = pT + (dNt ? m : 0);
-        T* pN = pS + (src ? m : 0);
-        struct Seg { void* dst; const void* srcp; size_t bytes; };
-        Seg segs[5] = {{pX, X + (off + r0) * nx, (size_t)m * nx * sizeof(T)}, {pG, G + (off + r0) * dim, (size_t)m * dim * sizeof(T)},
-                       {pT, dNt ? dNt + off + r0 : nullptr, dNt ? (size_t)m * sizeof(T) : 0}, {pS, src ? src + off + r0 : nullptr, src ? (size_t)m * sizeof(T) : 0},
-                       {pN, N && src ? N + off + r0 : nullptr, (N && src) ? (size_t)m * sizeof(T) : 0}};
+        float* pX = reinterpret_cast<float*>(e->pin[b]);
+        float* pG = pX + m * nx;
+        float* pT = pG + m * dim;
+        float* pS = pT + (dNt ? m : 0);
+        float* pN = pS + (src ? m : 0);
+        struct Seg { float* dst; const T* srcp; size_t count; };
+        Seg segs[5] = {{pX, X + (off + r0) * nx, (size_t)m * nx}, {pG, G + (off + r0) * dim, (size_t)m * dim},
+                       {pT, dNt ? dNt + off + r0 : nullptr, dNt ? (size_t)m : 0}, {pS, src ? src + off + r0 : nullptr, src ? (size_t)m : 0},
+                       {pN, (N && src) ? N + off + r0 : nullptr, (N && src) ? (size_t)m : 0}};
         const int parts = e->pool->size();
         e->pool->run(parts, [&](int i) {
             for (const Seg& sg : segs) {
-                if (!sg.bytes) continue;
-                const size_t lo = sg.bytes * (size_t)i / parts / 64 * 64, hi = (i + 1 == parts) ? sg.bytes : sg.bytes * (size_t)(i + 1) / parts / 64 * 64;
-                if (hi > lo) memcpy(static_cast<char*>(sg.dst) + lo, static_cast<const char*>(sg.srcp) + lo, hi - lo);
+                if (!sg.count) continue;
+                const size_t lo = sg.count * (size_t)i / parts / 16 * 16, hi = (i + 1 == parts) ? sg.count : sg.count * (size_t)(i + 1) / parts / 16 * 16;
+                float* __restrict__ d = sg.dst;
+                const T* __restrict__ sp = sg.srcp;
+                for (size_t j = lo; j < hi; ++j) d[j] = (float)sp[j];
             }
         });
-        CK(cudaMemcpyAsync(sX + r0 * nx, pX, (size_t)m * nx * sizeof(T), cudaMemcpyHostToDevice, us));
-        CK(cudaMemcpyAsync(sG + r0 * dim, pG, (size_t)m * dim * sizeof(T), cudaMemcpyHostToDevice, us));
-        if (dNt) CK(cudaMemcpyAsync(sT + r0, pT, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
+        CK(cudaMemcpyAsync(sX + r0 * nx, pX, (size_t)m * nx * sizeof(float), cudaMemcpyHostToDevice, us));
+        CK(cudaMemcpyAsync(sG + r0 * dim, pG, (size_t)m * dim * sizeof(float), cudaMemcpyHostToDevice, us));
+        if (dNt) CK(cudaMemcpyAsync(sT + r0, pT, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, us));
         if (src) {
-            CK(cudaMemcpyAsync(sS + r0, pS, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
-            CK(cudaMemcpyAsync(sN + r0, pN, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, us));
+            CK(cudaMemcpyAsync(sS + r0, pS, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, us));
+            CK(cudaMemcpyAsync(sN + r0, pN, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, us));
         }
         CK(cudaEventRecord(e->pinEv[b], us));
     }
@@ -962,9 +966,18 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
             T* sS = sT + n;
             T* sN = sS + n;
             if (pageable) {
+                // staged and cast to float32 by the host threads: the device blocks and the pack kernel are float
+                float* fX = e->stage.as<float>();
+                float* fG = fX + n * nx;
+                float* fT = fG + n * c.dim;
+                float* fS = fT + n;
+                float* fN = fS + n;
                 int rcs = stage_pageable<T>(e, us, X, nx, G, c.dim, t->colT >= 0 ? dNt : nullptr, t->colS >= 0 ? src : nullptr,
-                                            t->colS >= 0 ? N : nullptr, off, n, sX, sG, sT, sS, sN);
+                                            t->colS >= 0 ? N : nullptr, off, n, fX, fG, fT, fS, fN);
                 if (rcs) return rcs;
+                vn_pack_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, us>>>(
+                    fX, nx, fG, c.dim, t->colT >= 0 ? fT : nullptr, t->colS >= 0 ? fS : nullptr,
+                    t->colS >= 0 ? fN : nullptr, t->cols.as<float>(), t->pstride, off, n, t->colX, t->colG, t->colT, t->colS);
             } else {
                 CK(cudaMemcpyAsync(sX, X + off * nx, n * nx * sizeof(T), cudaMemcpyHostToDevice, us));
                 CK(cudaMemcpyAsync(sG, G + off * c.dim, n * c.dim * sizeof(T), cudaMemcpyHostToDevice, us));
@@ -973,10 +986,10 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
                     CK(cudaMemcpyAsync(sS, src + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
                     CK(cudaMemcpyAsync(sN, N + off, n * sizeof(T), cudaMemcpyHostToDevice, us));
                 }
+                vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, us>>>(
+                    sX, nx, sG, c.dim, t->colT >= 0 ? sT : nullptr, t->colS >= 0 ? sS : nullptr,
+                    t->colS >= 0 ? sN : nullptr, t->cols.as<float>(), t->pstride, off, n, t->colX, t->colG, t->colT, t->colS);
             }
-            vn_pack_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, us>>>(
-                sX, nx, sG, c.dim, t->colT >= 0 ? sT : nullptr, t->colS >= 0 ? sS : nullptr,
-                t->colS >= 0 ? sN : nullptr, t->cols.as<float>(), t->pstride, off, n, t->colX, t->colG, t->colT, t->colS);
             CK(cudaGetLastError());
             e->launches++;
             if (e->fedEvents.size() <= k) {
