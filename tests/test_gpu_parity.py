@@ -275,16 +275,17 @@ def test_fed_step_overlapping_copies_equals_upload_then_step(feed_dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("integPnum", [2, 3])
-def test_device_generated_table_is_bit_identical_to_the_uploaded_one(integPnum):
+@pytest.mark.parametrize("integPnum,lw", [(2, [12, 20]), (3, [12, 20]), (2, [64, 64, 64, 64]), (2, [48, 64])])
+def test_device_generated_table_is_bit_identical_to_the_uploaded_one(integPnum, lw):
     """vn_generate_table_f64 (uniform mesh, constant coefficients, table built on the device from the mesh centres and
     the periodic FE tables) against uploading the host-built arrays of the same test-function range: identical loss
-    bits, lossVec and gradient."""
+    bits, lossVec and gradient.  For the 33-64-wide class no table is materialised at all: the tensor-core tile kernel
+    regenerates every row from the centre of its test function (`in-kernel` in kernel_info), also under a mini-batch
+    index list."""
     from varnet_b200 import workloads
     from varnet_b200._capi import Engine
     nx, ny, ntime, n0, n1 = 9, 7, 6, 37, 301
     feed, meta = workloads.shard_feed(nx, ny, ntime, n0, n1, integPnum=integPnum, dtype=np.float64)
-    lw = [12, 20]
     theta = go.glorot_init(3, lw, seed=5)
     res = []
     for dev in (False, True):
@@ -300,8 +301,14 @@ def test_device_generated_table_is_bit_identical_to_the_uploaded_one(integPnum):
         eng.set_weights([2.0, 3.0, 5.0])
         out = eng.loss_grad()
         lv = eng.loss(lossVec=True)["lossVec"]
-        res.append((out, lv))
+        if dev and max(lw) > 32:
+            assert "in-kernel" in eng.kernel_info()
+        idx = np.random.RandomState(1).permutation(n1 - n0)[:97].astype(np.int32)      # mini-batch = index list into the table
+        eng.set_batch(idx)
+        sub = eng.loss_grad()
+        res.append((out, lv, sub))
         eng.close()
-    (a, la), (b, lb) = res
+    (a, la, sa), (b, lb, sb) = res
     assert all(np.float32(a[k]) == np.float32(b[k]) for k in ("loss", "BCloss", "ICloss", "varLoss"))
     assert np.array_equal(la, lb) and np.array_equal(a["grad"], b["grad"])
+    assert np.float32(sa["loss"]) == np.float32(sb["loss"]) and np.array_equal(sa["grad"], sb["grad"])

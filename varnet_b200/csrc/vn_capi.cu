@@ -436,6 +436,9 @@ struct PointSet {
     long long pstride = 0; unsigned int rows = 0, nbTab = 0, integNum = 0; int detJvec = 0, hasIntegW = 0;
     int colX = 0, colG = 0, colT = -1, colS = -1, ncols = 0, nx = 0;
     bool loaded = false;
+    // in-kernel generation (vn_generate_table_f64 on an engine whose variational passes all run on the tensor-core tile kernel):
+    // no materialised columns, only the mesh centres and the q-periodic tables
+    bool inKernel = false; DevBuf genBuf; GenTab genTab{};
     cudaGraphExec_t graph = nullptr; float graphLr = -1.f; int graphLaunches = 0; unsigned int graphNb = 0; bool graphIndexed = false;
     long long graphEpoch = -1;   // g_reallocEpoch at capture time
 };
@@ -677,7 +680,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     for (cudaEvent_t ev : e->fedEvents) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pinEv[i]) cudaEventDestroy(e->pinEv[i]); }
     delete e->pool;
-    for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); delete t; }
+    for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); t->genBuf.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
@@ -916,6 +919,7 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
     CK(cudaSetDevice(c.device));
     PointSet* t = e->t;
     drop_graph(t);
+    t->inKernel = false;
     int col = 0;
     t->nx = nx;
     t->colX = col; col += nx;
@@ -1083,6 +1087,55 @@ extern "C" int vn_generate_table_f64(vn_engine* e, const double* coord, int64_t 
     t->ncols = col;
     t->pstride = (P + kPad - 1) / kPad * kPad;
     t->rows = (unsigned int)P; t->nbTab = (unsigned int)nb; t->integNum = (unsigned int)integNum; t->detJvec = 0;
+    // Engines whose variational passes (loss and loss + gradient) all run on the tensor-core tile kernel never read a materialised
+    // table: the kernel regenerates each row from the centre of its test function (GenTab).  Nothing of size nT is allocated.
+    static const bool inKernelOff = [] { const char* v = getenv("VARNET_B200_INKERNEL_GEN"); return v && !strcmp(v, "0"); }();
+    t->inKernel = !inKernelOff && e->tc64 && vn_tc64_forward_only_available() && (128 % integNum) == 0 && c.dim <= 2 && integNum <= 4096;
+    if (t->inKernel) {
+        const size_t nC = (size_t)nSpace * c.dim, nTm = c.timeDependent ? (size_t)nTime : 0, nH = (size_t)feDim * integNum;
+        std::vector<double> hd(nH);
+        for (int d = 0; d < feDim; ++d)
+            for (int q = 0; q < integNum; ++q) { volatile double pr = hVec[d] * delta[(size_t)d * integNum + q]; hd[(size_t)d * integNum + q] = pr; }
+        std::vector<float> coef((size_t)integNum * 4, 0.f);
+        for (int q = 0; q < integNum; ++q) {
+            for (int k = 0; k < c.dim; ++k) {
+                volatile double p1 = diff * dN[(size_t)q * feDim + k];      // separate roundings, as NumPy evaluates diff*dNx + vel*N
+                volatile double p2 = vel[k] * N[q];
+                volatile double sm = p1 + p2;
+                coef[(size_t)q * 4 + k] = (float)sm;
+            }
+            if (c.timeDependent) coef[(size_t)q * 4 + 2] = (float)dN[(size_t)q * feDim + c.dim];
+            coef[(size_t)q * 4 + 3] = (float)source * (float)N[q];
+        }
+        const size_t bytes = (nC + nTm + nH) * sizeof(double) + coef.size() * sizeof(float);
+        CK(t->genBuf.ensure(bytes));
+        double* dC = t->genBuf.as<double>();
+        double* dT = dC + nC; double* dH = dT + nTm; float* dF = reinterpret_cast<float*>(dH + nH);
+        CK(cudaMemcpyAsync(dC, coord, nC * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (nTm) CK(cudaMemcpyAsync(dT, tcoord, nTm * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dH, hd.data(), nH * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dF, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));          // hd / coef are locals
+        t->genTab.coord = dC; t->genTab.tcoord = nTm ? dT : nullptr; t->genTab.hd = dH; t->genTab.coef = dF;
+        t->genTab.nTime = nTime; t->genTab.tf0 = tf0; t->genTab.q = integNum; t->genTab.dim = c.dim; t->genTab.feDim = feDim;
+        t->cols.release();
+        t->hasIntegW = (c.integWflag && integW) ? 1 : 0;
+        CK(t->detJ.ensure(sizeof(float)));
+        const float djk = (float)detJ;
+        CK(cudaMemcpyAsync(t->detJ.p, &djk, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (t->hasIntegW) {
+            std::vector<float> wf(integNum);
+            for (int q = 0; q < integNum; ++q) wf[q] = (float)integW[q];
+            CK(t->integW.ensure(integNum * sizeof(float)));
+            CK(cudaMemcpyAsync(t->integW.p, wf.data(), integNum * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
+        CK(cudaStreamSynchronize(e->stream));
+        t->loaded = true;
+        e->indexed = false;
+        e->nb = t->nbTab;
+        if (c.inpDim == feDim) e->nExtra = 0;
+        return ensure_work(e);
+    }
     CK(t->cols.ensure((size_t)t->ncols * t->pstride * sizeof(float)));
     CK(cudaMemsetAsync(t->cols.p, 0, (size_t)t->ncols * t->pstride * sizeof(float), e->stream));
     // small host tables -> staging (doubles): coord | tcoord | delta | N | dN | integW
@@ -1146,7 +1199,7 @@ extern "C" int vn_free_table(vn_engine* e, int32_t slot) {
     CK(cudaStreamSynchronize(e->stream));
     PointSet* t = e->slots[slot];
     drop_graph(t);
-    t->cols.release(); t->integW.release(); t->detJ.release();
+    t->cols.release(); t->integW.release(); t->detJ.release(); t->genBuf.release(); t->inKernel = false;
     t->loaded = false; t->rows = t->nbTab = 0;
     if (t == e->t) { e->nb = 0; e->P = 0; }
     return VN_OK;
@@ -1262,6 +1315,7 @@ static void var_args(const vn_engine* e, TileArgs* a) {
     const PointSet* t = e->t;
     a->cols = t->cols.as<float>(); a->pstride = t->pstride;
     a->colX = t->colX; a->colG = t->colG; a->colT = t->colT; a->colS = t->colS;
+    a->useGen = t->inKernel ? 1 : 0; a->gen = t->genTab;
     a->nxTable = t->nx; a->extraX = e->extraX.as<float>();
     a->tfIndex = e->indexed ? e->batchIdx.as<int>() : nullptr;
     a->P = e->P;
@@ -1852,8 +1906,9 @@ extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
     }
     if (e->useTc64) {
         snprintf(buf, n, "family=tcgen05-3xtf32-tile64 class=64 S=%d L=%d var_adj(TP=128,NT=512,smem=%zu,grid=%d,fused-R single pass,"
-                 "stash=%lldB/CTA,A-from-TMEM) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
-                 e->S, e->net.L, e->tc64Geom.smemBytes, e->gridVar, (long long)(e->tc64Geom.stashFloats * 4), e->gBicAdj.TP,
+                 "stash=%lldB/CTA,A-from-TMEM%s) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+                 e->S, e->net.L, e->tc64Geom.smemBytes, e->gridVar, (long long)(e->tc64Geom.stashFloats * 4),
+                 (e->t && e->t->inKernel) ? ",table=in-kernel generation" : "", e->gBicAdj.TP,
                  e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
         return VN_OK;
     }

@@ -415,15 +415,34 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
         const unsigned int gp = base + p;
         const bool valid = gp < A.P;
-        const size_t row = valid ? table_row(A, gp) : 0;
+        const size_t row = (valid && !A.useGen) ? table_row(A, gp) : 0;
+        // in-kernel table generation: this point's test function (space node gs, time node gj) and Gauss index gq
+        long long gs = 0, gj = 0;
+        int gq = 0;
+        if (A.useGen && valid) {
+            const unsigned int b = gp / A.integNum;
+            gq = (int)(gp - b * A.integNum);
+            const long long i = A.gen.tf0 + (long long)table_tf(A, b);
+            gs = i / A.gen.nTime; gj = i - gs * A.gen.nTime;
+        }
+        auto coefv = [&](int k) -> float {               // 0, 1: gcoef; 2: dNt; 3: source*N
+            if (A.useGen) return __ldg(A.gen.coef + gq * 4 + k);
+            const int col = k < 2 ? A.colG + k : (k == 2 ? A.colT : A.colS);
+            return __ldg(A.cols + (size_t)col * A.pstride + row);
+        };
         auto input = [&](int c) -> float {
             if (c >= A.nxTable) return __ldg(A.extraX + (c - A.nxTable));
+            if (A.useGen) {
+                if (!valid) return 0.f;
+                const double ctr = c < A.gen.dim ? __ldg(A.gen.coord + gs * A.gen.dim + c) : __ldg(A.gen.tcoord + gj);
+                return __double2float_rn(__dadd_rn(ctr, __ldg(A.gen.hd + (size_t)c * A.gen.q + gq)));
+            }
             if (!A.tfIndex) return ldg_stream(A.cols + (size_t)(A.colX + c) * A.pstride + gp, polFirst);  // zero padded table
             return valid ? __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row) : 0.f;
         };
 
         // table columns of the CTA's next tile -> L2 (the table streams from HBM once; 24 lines of 128 B per tile)
-        if (!A.tfIndex && tile + (int)gridDim.x < A.ntiles) {
+        if (!A.tfIndex && !A.useGen && tile + (int)gridDim.x < A.ntiles) {
             const int nc = A.nxTable + (S - 1) + (A.colT >= 0 ? 1 : 0) + (A.colS >= 0 ? 1 : 0);
             if (tid < nc * 4) {
                 const float* nx = A.cols + (size_t)(A.colX + (tid >> 2)) * A.pstride + (size_t)(A.tile0 + tile + (int)gridDim.x) * TP + (tid & 3) * 32;
@@ -511,9 +530,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             float I = 0.f;
             if (valid) {
 #pragma unroll
-                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row), I);
-                if (A.timeDependent) I -= us[p] * __ldg(A.cols + (size_t)A.colT * A.pstride + row);
-                if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], coefv(k), I);
+                if (A.timeDependent) I -= us[p] * coefv(2);
+                if (A.isSource) I -= coefv(3);
                 if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
             }
             Ish[p] = I;
@@ -549,9 +568,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 const float wq = A.integW ? __ldg(A.integW + qq) : 1.f;
                 lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
             }
-            us[p] = A.timeDependent ? -lam * __ldg(A.cols + (size_t)A.colT * A.pstride + row) : 0.f;
+            us[p] = A.timeDependent ? -lam * coefv(2) : 0.f;
 #pragma unroll
-            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
+            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * coefv(k);
         }
         __syncthreads();
 

@@ -48,6 +48,19 @@ struct NetDesc {
     int nparam;
 };
 
+// In-kernel table generation: for a uniform space-time mesh with constant coefficients the point table is
+// periodic in the Gauss index q, so a kernel can rebuild a row from the centre of its test function instead of reading it:
+//   X[i,q,d] = coord[s][d] + hd[d][q]  (d < dim),  X[i,q,dim] = tcoord[j] + hd[dim][q],  i = tf0 + table test function = s*nTime + j
+// in float64 exactly as the host does (VarNet.py:576-586), rounded to float32; gcoef / dNt / source*N come from a q-indexed table.
+struct GenTab {
+    const double* coord;            // [nSpace][dim] centres
+    const double* tcoord;           // [nTime] or nullptr
+    const double* hd;               // [feDim][q]: h[d] * delta[d][q]
+    const float* coef;              // [q][4]: gcoef_0, gcoef_1, dNt, source*N (float32, rounded like the feed cast)
+    long long nTime, tf0;
+    int q, dim, feDim;
+};
+
 struct TileArgs {
     NetDesc net;
     const float* theta;             // flat parameters (device)
@@ -57,6 +70,8 @@ struct TileArgs {
     int colD, colDD;                // residual: diffusivity column, first grad(kappa) column
     int nxTable;                    // MLP input columns stored in the table; inputs [nxTable, inpDim) are constants
     const float* extraX;            // [inpDim - nxTable] constant trailing inputs (MOR parameters), device
+    int useGen;                     // 1: no materialised table, rows are regenerated from `gen` (tensor-core tile kernel only)
+    GenTab gen;
     const int* tfIndex;             // mini-batch: table test-function index of batch slot b, or nullptr (identity)
     int dim;                        // spatial dimension (residual kernel: runtime stream roles)
     unsigned int P;                 // valid points (rows)
