@@ -95,6 +95,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {      
     }
     return done != 0;
 }
+// one lane of a converged warp (elect.sync): ptxas then knows the MMA operands are uniform and emits back-to-back UTCHMMA instead
+// of an ELECT / BRA.U.ANY loop around each of them
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
     uint32_t u[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     };
     // forward layer GEMM of stream s: work = A_s x [W_hi | W_lo]^T (hi*hi | hi*lo), then the second half += A_s,lo x W_hi
     auto issue_fwd = [&](int s, uint32_t wst) {
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t aHi = tmem + 128 * s, aLo = aHi + 64, d = tmem + COL_WORK;
 #pragma unroll
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     // gW_l (+)= [a_hi ; a_lo]^T-rows x [zbar_hi ; zbar_lo]^T-rows over the 128 points of the tile
     // (the weight-gradient GEMM goes first and has its own barrier: its accumulators are drained under the layer GEMM)
     auto issue_adj = [&](int s, uint32_t wst) {
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
 #pragma unroll
@@ -767,11 +774,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
 }
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -1340,8 +1342,9 @@ int vn_tc64_read_timing(long long out[16]) {
 }
 // Two schedules of the same tile algorithm.  Default: the round-1 kernel (512 threads, MMAs issued by a worker thread between
 // __syncthreads).  VARNET_B200_TC64=v2 selects the warp-specialised, software-pipelined kernel of round 2: parity-green and
-// bitwise reproducible too, but measured 3 % SLOWER on the headline workload (163.6 vs 158.3 ms per 6.4e7-point step): with the
-// MMA waits overlapped, a tile is bound by the workers' own instruction stream (profiles/r2_tc64_v2.md has the phase table).
+// bitwise reproducible too, and measured within 1 % of the default on the headline workload (167.3 vs 165.9 ms per 6.4e7-point
+// step, same box): with the MMA waits overlapped, a tile is bound by the workers' own instruction stream
+// (profiles/r2_tc64_v2.md has the phase table).
 static bool use_v1() {
     static const int v = [] { const char* e = getenv("VARNET_B200_TC64"); return (e && !strcmp(e, "v2")) ? 0 : 1; }();
     return v != 0;
