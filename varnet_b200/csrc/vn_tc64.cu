@@ -21,7 +21,7 @@ constexpr int W = 64;              // padded hidden width
 constexpr int NH = 4;              // neuron groups: warp w -> lane quarter w & 3, neuron group w >> 2
 constexpr int CPT = W / NH;        // neurons (columns) per thread
 constexpr int NT = 128 * NH;       // threads
-constexpr int FOLD = 32;           // tiles accumulated in the FP32 window slab before the FP64 fold
+constexpr int FOLD = 128;          // tiles accumulated in the FP32 window slab before the FP64 fold (VARNET_B200_TC64_FOLD)
 constexpr uint32_t SBO = 128;      // bytes between 8-row groups of a canonical K-major operand
 constexpr uint32_t W_LBO = 2048;   // weight images: 128 rows x 16 B per 4-wide K unit
 constexpr uint32_t G_LBO = 2064;   // weight-gradient operands (K = points): + 16 B pad, transposing stores hit 32 banks
@@ -36,7 +36,7 @@ constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
 
-struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; int fwdOnly; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING); fwdOnly: loss / lossVec / R only (v1 schedule)
+struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; int fwdOnly; int fold; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING); fwdOnly: loss / lossVec / R only (v1 schedule)
 
 struct SlabLayout { int vecOff, boutOff, psz, nkind; };
 __host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
@@ -389,14 +389,14 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     // adjoint step of stream s: abar_{l-1,s} = zbar_{l,s} W_l^T (hi*hi -> park s, cross products -> small) and
     // gW_l (+)= [a_hi ; a_lo]^T-rows x [zbar_hi ; zbar_lo]^T-rows over the 128 points of the tile
     // (the weight-gradient GEMM goes first and has its own barrier: its accumulators are drained under the layer GEMM)
-    auto issue_adj = [&](int s, uint32_t wst) {
+    auto issue_adj = [&](int s, uint32_t wst, uint32_t gwAcc, bool gwLast) {
         if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb)
-                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : 0u);
-            mma_commit(barGw);
+                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : gwAcc);
+            if (gwLast) mma_commit(barGw);              // drained after the last stream only; earlier streams are covered by `bar`
             const uint32_t aHi = tmem + COL_OP, aLo = aHi + 64, dMain = tmem + COL_PARK + 64 * s, dSmall = tmem + COL_SMALL;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
@@ -613,7 +613,6 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             stash_get(stash, (L - 2) * S + 1, p, c0, apre, polLast);
             for (int l = L - 1; l >= 0; --l) {
                 uint32_t wst = 0;
-                if (l >= 1) wst = acquire_image();
 #pragma unroll
                 for (int jj = 0; jj < CPT; ++jj) cross[jj] = 0.f;
                 for (int si = 0; si < S; ++si) {
@@ -637,6 +636,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     int ln = l, sn = (si + 1 < S - 1) ? si + 2 : 0;
                     if (si + 1 == S) { ln = l - 1; sn = 1; }
                     if (l >= 1) {
+                        if (si == 0) wst = acquire_image();
                         put_operand(tq + COL_OP, c0, v);
                         put_transposed(GB, p, c0, v);
                         put_transposed(GA, p, c0, apre);
@@ -647,19 +647,20 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                             vec_add(l, r, first);
                         }
                         sync_for_issue();
-                        issue_adj(s, wst);
+                        issue_adj(s, wst, si > 0 ? 1u : 0u, si == S - 1);
                         // stash rows of the next step, in flight while the tensor core runs
                         if (ln >= 0) {
                             if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre, polLast);
                             if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre, polLast);
                         }
-                        wait_gw();
-                        {
+                        if (si == S - 1) {
+                            wait_gw();
+                            // the S streams of a layer are ONE K = S*128 contraction (a chain of 16 S <= 48 hi*hi MMAs), drained once:
                             // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
                             float g[CPT];
                             if (q < 2) drain_sum2(tq + COL_GW + c0, tq + COL_GW + 64 + c0, g); else get_plain(tq + COL_GW + c0, g);
                             float* slot = part + gw_slot(l, p, c0);
-                            if (first && si == 0) {                            // first write of this window: overwrite
+                            if (first) {                                       // first write of this window: overwrite
 #pragma unroll
                                 for (int u = 0; u < CPT / 4; ++u) __stcg(reinterpret_cast<float4*>(slot) + u * TP, make_float4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]));
                             } else {
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         tmem_wait_ld();
 
         first = false;
-        if (++win == FOLD || tile + (int)gridDim.x >= A.ntiles) {
+        if (++win == K.fold || tile + (int)gridDim.x >= A.ntiles) {
             // fold this thread's slots of the FP32 window into the FP64 slab (single writer per slot)
             auto put = [&](int idx) {
                 const double v = (double)__ldcg(part + idx);
@@ -1379,6 +1380,8 @@ bool vn_tc64_forward_only_available() { return use_v1(); }
 cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg, int* err, int grid, size_t smem, cudaStream_t st, int fwdOnly) {
     Tc64Args k;
     k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr; k.fwdOnly = fwdOnly;
+    static const int fold = [] { const char* e = getenv("VARNET_B200_TC64_FOLD"); const int v = e ? atoi(e) : FOLD; return v > 0 ? v : FOLD; }();
+    k.fold = fold;
     if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
