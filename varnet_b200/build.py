@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvarnet_b200.so")
-SOURCES = ["vn_capi.cu", "vn_inst_w16.cu", "vn_inst_w32.cu", "vn_inst_w64.cu", "vn_inst_w64d.cu", "vn_tc.cu", "vn_tc64.cu", "vn_extra.cu"]
+SOURCES = ["vn_capi.cu", "vn_inst_w16.cu", "vn_inst_w32.cu", "vn_inst_w64.cu", "vn_inst_w64d.cu", "vn_tc.cu", "vn_tc64.cu", "vn_tpp.cu", "vn_extra.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

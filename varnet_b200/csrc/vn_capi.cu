@@ -20,6 +20,7 @@
 #include "vn_dispatch.h"
 #include "vn_tc.h"
 #include "vn_tc64.h"
+#include "vn_tpp.h"
 #include <utility>
 
 // ------------------------------------------------------------------ errors
@@ -455,6 +456,12 @@ struct vn_engine {
     bool useTc64 = false;        // ... and the current batch does (integNum | 128)
     Tc64Geom tc64Geom{};
     DevBuf tc64Img, tc64Flat;
+    // thread-per-point kernel (vn_tpp.h) for the variational term of narrow networks (every hidden width <= 32)
+    bool tpp = false;            // network and build allow it (>= 2 CTAs per SM)
+    bool useTpp = false;         // ... and the current batch does (integNum | 128)
+    TppLayout tppLay{};
+    int tppCtas = 0;             // resident CTAs per SM
+    DevBuf tppFlat;
     // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> fedEvents;
@@ -646,6 +653,23 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
             }
         }
     }
+    {
+        // narrow networks: the variational term runs on the thread-per-point kernel unless VARNET_B200_CLASS=fma; networks whose
+        // per-point rows leave room for fewer than two CTAs per SM stay on the FMA tiles (a class choice, both are CUDA kernels)
+        const bool wantTpp = !(forceCls && !strcmp(forceCls, "fma"));
+        if ((e->wclass == 16 || e->wclass == 32) && wantTpp && vn_tpp_supported(e->net, e->S)) {
+            vn_tpp_layout(e->net, e->S, &e->tppLay);
+            if (e->tppLay.smemBytes * 2 + 2048 <= prop.sharedMemPerMultiprocessor && e->tppLay.smemBytes <= prop.sharedMemPerBlockOptin) {
+                int ctas = 0;
+                cudaError_t cet = vn_tpp_prepare(e->S, act, e->tppLay.smemBytes, &ctas);
+                if (cet != cudaSuccess) { delete e; return fail(VN_E_CUDA, "thread-per-point kernel: %s", cudaGetErrorString(cet)); }
+                if (ctas >= 2) {
+                    e->tpp = true; e->tppCtas = ctas;
+                    CK(e->tppFlat.ensure((size_t)e->net.nparam * sizeof(double)));
+                }
+            }
+        }
+    }
     const int np = e->net.nparam;
     CK(e->theta.ensure(np * sizeof(float)));
     CK(e->m.ensure(np * sizeof(float)));
@@ -684,7 +708,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->lossRing};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->tppFlat, &e->lossRing};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -814,6 +838,17 @@ static int ensure_work(vn_engine* e) {
         CK(e->lossPart.ensure((size_t)e->numSMs * e->tc64Geom.lossSlots * sizeof(double)));
         e->fused = true;
         set_stash_window(e);
+        return VN_OK;
+    }
+    e->useTpp = e->tpp && t->integNum > 0 && (128 % t->integNum) == 0;
+    if (e->useTpp) {
+        // balanced persistent grid: every CTA gets the same number of 128-point tiles (+-1)
+        const long long tiles = std::max<long long>(1, (P + 127) / 128), cap = (long long)e->numSMs * e->tppCtas;
+        const long long rounds = (tiles + cap - 1) / cap;
+        e->gridVar = (int)((tiles + rounds - 1) / rounds);
+        CK(e->partVar.ensure((size_t)cap * e->tppLay.npatch * 64 * sizeof(double)));
+        CK(e->lossPart.ensure((size_t)cap * 4 * sizeof(double)));
+        e->fused = true;
         return VN_OK;
     }
     const long long tilesAdj = (P + e->gVarAdj.TP - 1) / e->gVarAdj.TP;
@@ -956,7 +991,7 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
         if (t->pstride > P)
             for (int cc = 0; cc < t->ncols; ++cc)
                 CK(cudaMemsetAsync(t->cols.as<float>() + (size_t)cc * t->pstride + P, 0, (size_t)(t->pstride - P) * sizeof(float), us));
-        const int TP = (e->tc64 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
+        const int TP = ((e->tc64 || e->tpp) && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
         // pageable caller arrays (what NumPy hands over) are staged through pinned bounce buffers by a few host threads
         static const bool stagerOff = [] { const char* v = getenv("VARNET_B200_STAGE_THREADS"); return v && atoi(v) <= 0; }();
         const bool pageable = !stagerOff && is_pageable(X) && is_pageable(G);
@@ -1423,7 +1458,8 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         a.part = e->partVar.as<double>(); a.part32 = e->part32Var.as<float>(); a.psz = g.pl.psz;
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
-        const bool tc = e->useTc64;
+        const bool tc = e->useTc64, tpp = e->useTpp && needGrad;
+        if (tpp) { a.ntiles = (int)(((long long)e->P + 127) / 128); a.psz = e->tppLay.npatch * 64; }
         if (tc) {
             a.ntiles = (int)(((long long)e->P + 127) / 128);
             a.psz = e->tc64Geom.psz; a.stashFloats = e->tc64Geom.stashFloats;
@@ -1431,6 +1467,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             e->launches++;
         }
         auto launch_var = [&]() -> cudaError_t {
+            if (tpp) return vn_tpp_launch(e->S, c.act, a, e->tppLay, e->gridVar, st);
             if (tc) return vn_tc64_launch(e->S, c.act, a, e->tc64Img.as<float>(), e->tcErr.as<int>(), e->gridVar, e->tc64Geom.smemBytes, st, tcFwd ? 1 : 0);
             return vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FUSED, a, e->gridVar, g.smemBytes, st);
         };
@@ -1458,7 +1495,11 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             CK(vn_tc64_reduce(e->net, e->partVar.as<double>(), e->tc64Geom.psz, e->gridVar, e->tc64Flat.as<double>(), st));
             e->launches++;
         }
-        nSeg = e->gridVar * (tc ? e->tc64Geom.lossSlots : g.NT / 32);
+        if (tpp) {
+            CK(vn_tpp_reduce(e->net, e->tppLay, e->partVar.as<double>(), e->gridVar, e->tppFlat.as<double>(), st));
+            e->launches++;
+        }
+        nSeg = e->gridVar * (tc ? e->tc64Geom.lossSlots : (tpp ? 4 : g.NT / 32));
         segPtr = e->lossPart.as<double>();
     } else {
         // 1. forward over all quadrature points -> weighted integrand
@@ -1501,6 +1542,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         f.net = e->net; f.pl = e->gVarAdj.pl;
         f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
         if (needGrad && e->fused && e->useTc64) { f.nVar = 0; f.flat = e->tc64Flat.as<double>(); }
+        if (needGrad && e->fused && e->useTpp) { f.nVar = 0; f.flat = e->tppFlat.as<double>(); }
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
         f.segSum = segPtr; f.nSeg = nSeg;
         f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
@@ -1557,7 +1599,7 @@ static int loss_grad_fed(vn_engine* e, const T* X, const T* G, const T* src, con
     if (!e) return fail(VN_E_INVALID, "null engine");
     e->nExtra = 0;
     const long long P = (long long)nb * integNum;
-    const int fedTP = (e->tc64 && integNum > 0 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
+    const int fedTP = ((e->tc64 || e->tpp) && integNum > 0 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
     const bool overlap = e->wclass != 256 && e->nbi > 0 && P > kChunk && integNum > 0 && (fedTP % integNum) == 0 &&
                          kChunk % fedTP == 0 && kChunk / fedTP >= e->numSMs && !e->profOn;
     if (!overlap) {
@@ -1909,6 +1951,13 @@ extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
                  "stash=%lldB/CTA,A-from-TMEM%s) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
                  e->S, e->net.L, e->tc64Geom.smemBytes, e->gridVar, (long long)(e->tc64Geom.stashFloats * 4),
                  (e->t && e->t->inKernel) ? ",table=in-kernel generation" : "", e->gBicAdj.TP,
+                 e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
+        return VN_OK;
+    }
+    if (e->useTpp) {
+        snprintf(buf, n, "family=fp32-thread-per-point class=%d S=%d L=%d var_adj(TP=128,NT=128,smem=%zu,grid=%d,%d CTAs/SM,fused-R single pass,"
+                 "%d gradient patches) var_fwd(fp32-fma-tile,TP=%d) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+                 e->wclass, e->S, e->net.L, e->tppLay.smemBytes, e->gridVar, e->tppCtas, e->tppLay.npatch, e->gVarFwd.TP, e->gBicAdj.TP,
                  e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
         return VN_OK;
     }

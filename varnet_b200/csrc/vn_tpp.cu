@@ -1,0 +1,481 @@
+// vn_tpp.cu — thread-per-point FP32 kernel for narrow networks (see vn_tpp.h).
+//
+// Shared memory of a CTA (T = 128 threads = 128 quadrature points per tile):
+//   weights : W_l as [in][wp_l], W_l^T as [out][wp_{l-1}] (l >= 1), biases, w_out, b_out   (zero padded to multiples of 8)
+//   rows    : [nrows][T] — row r of thread `tid` is rows[r * T + tid]
+//               rowA[l] + s * w_l + k : a_{l,s}[k], later overwritten in place by zbar_{l,s}[k]
+//               rowX + c              : input x_c        rowU + s : adjoint seed ubar_s
+//               rowOne / rowZero      : constant rows (bias row of the weight-gradient patches, padding)
+//   gacc    : [npatch][64] FP64 weight-gradient patches of this CTA (all its tiles)
+// Per tile: thread-local forward sweep -> integrand -> R_i (warp segment sums) -> seeds -> for block = L, L-1, .., 0:
+//   [barrier] patches of block (cross-thread contraction over the 128 points) [barrier] zbar of the next layer down in place.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vn_tpp.h"
+
+namespace {
+
+constexpr int T = 128;             // threads per CTA == points per tile
+constexpr int NW = T / 32;
+
+struct TppArgs { TileArgs t; TppLayout lay; };
+
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+// transposing warp reduction of N per-lane values: N = 64 leaves elements 2*lane and 2*lane+1 in v[0], v[1];
+// N = 8 leaves element lane >> 2 in v[0] (on all four lanes of the group)
+template <int N> __device__ __forceinline__ void bfly(float (&v)[N], int lane) {
+    int n = N;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            const bool up = (lane & off) != 0;
+            const int hn = n >> 1;
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                if (i < hn) {
+                    const float send = up ? v[i] : v[i + hn];
+                    const float keep = up ? v[i + hn] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            n = hn;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+}
+
+// zbar_{l,s}[k] from abar_{l,s}[k], in place of a_{l,s}[k] (a = this thread's column of layer l, w rows per stream):
+//   zbar_s = abar_s act'(z)            (tangent streams)
+//   zbar_0 = abar_0 act'(z) + act''(z) sum_s abar_s zdot_s,  act''(z) zdot_s = (act''/act')(a_0) * adot_s      
+template <int S, int ACT> __device__ __forceinline__ void zbar_in_place(float* a, int w, int k, const float (&abar)[S]) {
+    const float a0 = a[k * T];
+    const float d1 = act_d1<ACT>(a0);
+    float cross = 0.f;
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+        float* q = a + (s * w + k) * T;
+        cross = fmaf(abar[s], *q, cross);
+        *q = abar[s] * d1;
+    }
+    a[k * T] = fmaf(abar[0], d1, act_d2r<ACT>(a0) * cross);
+}
+
+// Weight-gradient block `blk` (0..L-1: [a_{blk-1}; 1]^T zbar_blk, gW rows then the bias row; L: the output layer, one column):
+// warp `warp` takes 8x8 patches round-robin and contracts them over the T points of the tile.
+template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, const float* rows, double* gacc, int blk, int lane, int warp) {
+    const int L = Y.L;
+    const int win = blk == 0 ? Y.inpDim : Y.w[blk - 1];
+    const int ncols = blk == L ? 1 : Y.w[blk];
+    const int zrow0 = blk == L ? Y.rowU : Y.rowA[blk];
+    const int arow0 = blk == 0 ? Y.rowX : Y.rowA[blk - 1];
+    const int ncb = Y.ncb[blk], nrb = (win + 8) >> 3;
+    for (int pi = warp; pi < nrb * ncb; pi += NW) {
+        const int rb = pi / ncb, cb = pi - rb * ncb;
+        double* g = gacc + (size_t)(Y.patch0[blk] + pi) * 64;
+        auto a_row = [&](int s, int r) -> int {           // shared-memory row of operand row r, stream s (warp-uniform)
+            if (r < win) return blk == 0 ? (s == 0 ? arow0 + r : (r == s - 1 ? Y.rowOne : Y.rowZero)) : arow0 + s * win + r;
+            return (r == win && s == 0) ? Y.rowOne : Y.rowZero;
+        };
+        if (ncols == 1) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int ao[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ao[i] = a_row(s, rb * 8 + i) * T;
+                const int zo = (zrow0 + s) * T;
+#pragma unroll
+                for (int it = 0; it < T / 64; ++it) {
+                    const int p = 2 * lane + 64 * it;
+                    const float2 z = lds2(rows + zo + p);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 a = lds2(rows + ao[i] + p);
+                        acc[i] = fmaf(a.x, z.x, acc[i]);
+                        acc[i] = fmaf(a.y, z.y, acc[i]);
+                    }
+                }
+            }
+            bfly<8>(acc, lane);
+            if ((lane & 3) == 0) g[(lane >> 2) * 8] += (double)acc[0];
+        } else {
+            float acc[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int ao[8], zo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ao[i] = a_row(s, rb * 8 + i) * T;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int c = cb * 8 + j; zo[j] = (c < ncols ? zrow0 + s * ncols + c : Y.rowZero) * T; }
+#pragma unroll
+                for (int it = 0; it < T / 64; ++it) {
+                    const int p = 2 * lane + 64 * it;
+                    float2 a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = lds2(rows + ao[i] + p);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 z = lds2(rows + zo[j] + p);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            acc[i * 8 + j] = fmaf(a[i].x, z.x, acc[i * 8 + j]);
+                            acc[i * 8 + j] = fmaf(a[i].y, z.y, acc[i * 8 + j]);
+                        }
+                    }
+                }
+            }
+            bfly<64>(acc, lane);
+            g[2 * lane] += (double)acc[0];
+            g[2 * lane + 1] += (double)acc[1];
+        }
+    }
+}
+
+template <int S, int ACT>
+__global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ TppArgs K) {
+    extern __shared__ __align__(16) float smem[];
+    const TileArgs& A = K.t;
+    const TppLayout& Y = K.lay;
+    const NetDesc& net = A.net;
+    const int L = Y.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* wts = smem;
+    float* rows = smem + Y.wfloats;
+    double* gacc = reinterpret_cast<double*>(rows + (size_t)Y.nrows * T);
+    float* segW = reinterpret_cast<float*>(gacc + (size_t)Y.npatch * 64);
+
+    for (int i = tid; i < Y.wfloats; i += T) wts[i] = 0.f;
+    for (int i = tid; i < Y.npatch * 64; i += T) gacc[i] = 0.0;
+    rows[Y.rowOne * T + tid] = 1.f;
+    rows[Y.rowZero * T + tid] = 0.f;
+    __syncthreads();
+    {
+        const float* __restrict__ th = A.theta;
+        for (int l = 0; l < L; ++l) {
+            const int wi = l == 0 ? Y.inpDim : Y.w[l - 1], wo = Y.w[l];
+            for (int idx = tid; idx < wi * wo; idx += T) {
+                const int i = idx / wo, j = idx - i * wo;
+                const float v = th[net.woff[l] + idx];
+                wts[Y.offW[l] + i * Y.wp[l] + j] = v;
+                if (l >= 1) wts[Y.offWT[l] + j * Y.wp[l - 1] + i] = v;
+            }
+            for (int j = tid; j < wo; j += T) wts[Y.offB[l] + j] = th[net.boff[l] + j];
+        }
+        for (int j = tid; j < Y.w[L - 1]; j += T) wts[Y.offW[L] + j] = th[net.woff[L] + j];
+        if (tid == 0) wts[Y.offB[L]] = th[net.boff[L]];
+    }
+    __syncthreads();
+
+    const unsigned int integNum = A.integNum;
+    const int nshuf = integNum < 32u ? (int)integNum : 32;
+    double lossAcc = 0.0;
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const unsigned int gp = (unsigned int)(A.tile0 + tile) * T + tid;
+        const bool valid = gp < A.P;
+        const size_t row = valid ? table_row(A, gp) : 0;
+
+        // ---- inputs
+        float x[VN_KIN];
+#pragma unroll
+        for (int c = 0; c < VN_KIN; ++c) {
+            x[c] = 0.f;
+            if (c < Y.inpDim) {
+                if (c >= A.nxTable) x[c] = __ldg(A.extraX + (c - A.nxTable));
+                else if (valid) x[c] = __ldg(A.cols + (size_t)(A.colX + c) * A.pstride + row);
+                rows[(Y.rowX + c) * T + tid] = x[c];
+            }
+        }
+        // ---- layer 0 (K = inpDim); stream 1+k is seeded with the unit vector e_k: zdot_{0,1+k} = W_0[k][:]
+        {
+            const int w0 = Y.w[0], wp0 = Y.wp[0];
+            const float* W0 = wts + Y.offW[0];
+            const float* b0 = wts + Y.offB[0];
+            float* a0 = rows + Y.rowA[0] * T + tid;
+            for (int j0 = 0; j0 < w0; j0 += 8) {
+                float z[8], wk[S - 1][8];
+                { const float4 ba = lds4(b0 + j0), bb = lds4(b0 + j0 + 4);
+                  z[0] = ba.x; z[1] = ba.y; z[2] = ba.z; z[3] = ba.w; z[4] = bb.x; z[5] = bb.y; z[6] = bb.z; z[7] = bb.w; }
+#pragma unroll
+                for (int c = 0; c < VN_KIN; ++c) {
+                    if (c < Y.inpDim) {
+                        const float4 wa = lds4(W0 + c * wp0 + j0), wb = lds4(W0 + c * wp0 + j0 + 4);
+                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) z[i] = fmaf(x[c], wv[i], z[i]);
+                        if (c < S - 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) wk[c][i] = wv[i];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (j0 + i < w0) {
+                        const float a = act_f<ACT>(z[i]);
+                        const float d1 = act_d1<ACT>(a);
+                        a0[(j0 + i) * T] = a;
+#pragma unroll
+                        for (int k = 0; k < S - 1; ++k) a0[((1 + k) * w0 + j0 + i) * T] = d1 * wk[k][i];
+                    }
+                }
+            }
+        }
+        // ---- hidden layers: a_{l,0} = act(a_{l-1,0} W_l + b_l), a_{l,s} = act'(z_l) (a_{l-1,s} W_l)
+        for (int l = 1; l < L; ++l) {
+            const int wi = Y.w[l - 1], wo = Y.w[l], wpo = Y.wp[l];
+            const float* Wl = wts + Y.offW[l];
+            const float* bl = wts + Y.offB[l];
+            const float* ain = rows + Y.rowA[l - 1] * T + tid;
+            float* aout = rows + Y.rowA[l] * T + tid;
+            for (int j0 = 0; j0 < wo; j0 += 8) {
+                float acc[S][8];
+                { const float4 ba = lds4(bl + j0), bb = lds4(bl + j0 + 4);
+                  acc[0][0] = ba.x; acc[0][1] = ba.y; acc[0][2] = ba.z; acc[0][3] = ba.w; acc[0][4] = bb.x; acc[0][5] = bb.y; acc[0][6] = bb.z; acc[0][7] = bb.w; }
+#pragma unroll
+                for (int s = 1; s < S; ++s)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[s][i] = 0.f;
+#pragma unroll 2
+                for (int k = 0; k < wi; ++k) {
+                    const float4 wa = lds4(Wl + k * wpo + j0), wb = lds4(Wl + k * wpo + j0 + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const float a = ain[(s * wi + k) * T];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[s][i] = fmaf(a, wv[i], acc[s][i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (j0 + i < wo) {
+                        const float a = act_f<ACT>(acc[0][i]);
+                        const float d1 = act_d1<ACT>(a);
+                        aout[(j0 + i) * T] = a;
+#pragma unroll
+                        for (int s = 1; s < S; ++s) aout[(s * wo + j0 + i) * T] = d1 * acc[s][i];
+                    }
+                }
+            }
+        }
+        // ---- output layer (Dense(1), linear): u_0 = u, u_{1+k} = du/dx_k
+        float u[S];
+        {
+            const int w = Y.w[L - 1];
+            const float* wo = wts + Y.offW[L];
+            const float* aL = rows + Y.rowA[L - 1] * T + tid;
+#pragma unroll
+            for (int s = 0; s < S; ++s) u[s] = 0.f;
+            for (int k = 0; k < w; ++k) {
+                const float wv = wo[k];
+#pragma unroll
+                for (int s = 0; s < S; ++s) u[s] = fmaf(aL[(s * w + k) * T], wv, u[s]);
+            }
+            u[0] += wts[Y.offB[L]];
+        }
+        // ---- integrand I = sum_k u_k gcoef_k - u dNt - source N, times integW_q (TFModel.py:653-660)
+        float gco[S - 1], dnt = 0.f, wq = 1.f;
+        const unsigned int itf = gp / integNum, q = gp - itf * integNum;
+        float I = 0.f;
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) gco[k] = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k) {
+                gco[k] = __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
+                I = fmaf(u[1 + k], gco[k], I);
+            }
+            if (A.timeDependent) { dnt = __ldg(A.cols + (size_t)A.colT * A.pstride + row); I -= u[0] * dnt; }
+            if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+            if (A.integW) { wq = __ldg(A.integW + q); I *= wq; }
+        }
+        // ---- R_i = sum_q I_iq: the integNum points of a test function are consecutive threads (integNum | T, a power of two)
+        float r = I;
+        for (int off = 1; off < nshuf; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+        if (integNum > 32u) {
+            if (lane == 0) segW[warp] = r;
+            __syncthreads();
+            const int g = (int)(integNum >> 5), w0 = warp & ~(g - 1);
+            float t = 0.f;
+            for (int i = 0; i < g; ++i) t += segW[w0 + i];
+            r = t;
+        }
+        float lam = 0.f;
+        if (valid) {
+            const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, itf)) : __ldg(A.detJ);
+            if (q == 0) {
+                const float r2 = r * r;
+                A.R[itf] = r;
+                A.lossVec[itf] = dj * r2;
+                lossAcc += A.detJvec ? (double)dj * (double)r2 : (double)r2;
+            }
+            lam = 2.f * __ldg(A.wts + 2) * dj * wq * r;      // d(w2 varLoss)/dI_p
+        }
+        float ub[S];
+        ub[0] = A.timeDependent ? -lam * dnt : 0.f;
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) ub[1 + k] = lam * gco[k];
+#pragma unroll
+        for (int s = 0; s < S; ++s) rows[(Y.rowU + s) * T + tid] = ub[s];
+
+        // ---- output-layer gradients (block L) need a_{L-1} before it is overwritten
+        __syncthreads();
+        phase_b<S>(Y, rows, gacc, L, lane, warp);
+        __syncthreads();
+        {
+            const int w = Y.w[L - 1];
+            const float* wo = wts + Y.offW[L];
+            float* aL = rows + Y.rowA[L - 1] * T + tid;
+            for (int k = 0; k < w; ++k) {
+                const float wv = wo[k];
+                float ab[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) ab[s] = ub[s] * wv;
+                zbar_in_place<S, ACT>(aL, w, k, ab);
+            }
+        }
+        for (int l = L - 1;; --l) {
+            __syncthreads();
+            phase_b<S>(Y, rows, gacc, l, lane, warp);
+            if (l == 0) break;
+            __syncthreads();
+            // abar_{l-1,s} = zbar_{l,s} W_l^T, then zbar_{l-1} in place of a_{l-1}
+            const int wo = Y.w[l], wi = Y.w[l - 1], wpi = Y.wp[l - 1];
+            const float* WT = wts + Y.offWT[l];
+            const float* zl = rows + Y.rowA[l] * T + tid;
+            float* am = rows + Y.rowA[l - 1] * T + tid;
+            for (int k0 = 0; k0 < wi; k0 += 8) {
+                float acc[S][8];
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[s][i] = 0.f;
+#pragma unroll 2
+                for (int j = 0; j < wo; ++j) {
+                    const float4 wa = lds4(WT + j * wpi + k0), wb = lds4(WT + j * wpi + k0 + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const float z = zl[(s * wo + j) * T];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[s][i] = fmaf(z, wv[i], acc[s][i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (k0 + i < wi) {
+                        float ab[S];
+#pragma unroll
+                        for (int s = 0; s < S; ++s) ab[s] = acc[s][i];
+                        zbar_in_place<S, ACT>(am, wi, k0 + i, ab);
+                    }
+                }
+            }
+        }
+        __syncthreads();           // block 0 has read the input rows and zbar_0 before the next tile overwrites them
+    }
+
+    // ---- per-CTA results: FP64 patches (fixed-order sum over CTAs in tpp_reduce_kernel), loss partial per warp
+    __syncthreads();
+    {
+        double* slab = A.part + (size_t)blockIdx.x * A.psz;
+        for (int i = tid; i < Y.npatch * 64; i += T) slab[i] = A.accumulate ? slab[i] + gacc[i] : gacc[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lossAcc += __shfl_xor_sync(0xffffffffu, lossAcc, o);
+    if (lane == 0) {
+        double* lp = A.lossPart + blockIdx.x * NW + warp;
+        *lp = A.accumulate ? *lp + lossAcc : lossAcc;
+    }
+}
+
+// flat[idx] = sum over CTAs of the patch entry of parameter idx (one warp per parameter, lanes take CTAs c, c+32, ... in order)
+__global__ void tpp_reduce_kernel(NetDesc net, TppLayout Y, const double* __restrict__ slab, int nCta, double* __restrict__ flat) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= net.nparam) return;
+    int l = 0, row = 0, col = 0;
+    for (l = 0; l <= net.L; ++l) {
+        const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+        const int wo = l == net.L ? 1 : net.width[l];
+        if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { row = (idx - net.woff[l]) / wo; col = (idx - net.woff[l]) - row * wo; break; }
+        if (idx >= net.boff[l] && idx < net.boff[l] + wo) { row = wi; col = idx - net.boff[l]; break; }
+    }
+    const int slot = (Y.patch0[l] + (row >> 3) * Y.ncb[l] + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7);
+    const int psz = Y.npatch * 64;
+    double s = 0.0;
+    for (int c = lane; c < nCta; c += 32) s += __ldcg(slab + (size_t)c * psz + slot);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) flat[idx] = s;
+}
+
+template <int S, int ACT> cudaError_t launch_t(const TppArgs& k, int grid, cudaStream_t st) {
+    tpp_var_kernel<S, ACT><<<grid, T, k.lay.smemBytes, st>>>(k);
+    return cudaGetLastError();
+}
+template <int S, int ACT> cudaError_t prepare_t(size_t smem, int* ctas) {
+    cudaError_t e = cudaFuncSetAttribute(tpp_var_kernel<S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, tpp_var_kernel<S, ACT>, T, smem);
+}
+
+}  // namespace
+
+bool vn_tpp_supported(const NetDesc& net, int S) {
+    if (S < 2 || S > 3 || net.L < 1 || net.L > VN_MAX_LAYERS || net.inpDim > VN_KIN || net.inpDim < S - 1) return false;
+    for (int l = 0; l < net.L; ++l)
+        if (net.width[l] < 1 || net.width[l] > 32) return false;
+    return true;
+}
+void vn_tpp_layout(const NetDesc& net, int S, TppLayout* Y) {
+    *Y = TppLayout{};
+    Y->L = net.L; Y->S = S; Y->inpDim = net.inpDim;
+    int r = 0;
+    for (int l = 0; l < net.L; ++l) { Y->w[l] = net.width[l]; Y->wp[l] = (net.width[l] + 7) & ~7; Y->rowA[l] = r; r += S * net.width[l]; }
+    Y->rowX = r; r += net.inpDim;
+    Y->rowU = r; r += S;
+    Y->rowOne = r++; Y->rowZero = r++;
+    Y->nrows = r;
+    int o = 0;
+    for (int l = 0; l < net.L; ++l) {
+        const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+        Y->offW[l] = o; o += wi * Y->wp[l];
+        if (l >= 1) { Y->offWT[l] = o; o += net.width[l] * Y->wp[l - 1]; }
+        Y->offB[l] = o; o += Y->wp[l];
+    }
+    Y->offW[net.L] = o; o += Y->wp[net.L - 1];
+    Y->offB[net.L] = o; o += 4;
+    Y->wfloats = o;
+    int p = 0;
+    for (int b = 0; b <= net.L; ++b) {
+        const int win = b == 0 ? net.inpDim : net.width[b - 1];
+        const int ncols = b == net.L ? 1 : net.width[b];
+        Y->ncb[b] = (ncols + 7) >> 3;
+        Y->patch0[b] = p;
+        p += ((win + 8) >> 3) * Y->ncb[b];
+    }
+    Y->patch0[net.L + 1] = p;
+    Y->npatch = p;
+    Y->smemBytes = ((size_t)Y->wfloats + (size_t)Y->nrows * T) * sizeof(float) + (size_t)p * 64 * sizeof(double) + 64;
+}
+cudaError_t vn_tpp_prepare(int S, int act, size_t smem, int* ctas) {
+    if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem, ctas) : prepare_t<2, VN_TANH>(smem, ctas);
+    return act == VN_SIGMOID ? prepare_t<3, VN_SIGMOID>(smem, ctas) : prepare_t<3, VN_TANH>(smem, ctas);
+}
+cudaError_t vn_tpp_launch(int S, int act, const TileArgs& a, const TppLayout& lay, int grid, cudaStream_t st) {
+    TppArgs k;
+    k.t = a; k.lay = lay;
+    if (S == 2) return act == VN_SIGMOID ? launch_t<2, VN_SIGMOID>(k, grid, st) : launch_t<2, VN_TANH>(k, grid, st);
+    return act == VN_SIGMOID ? launch_t<3, VN_SIGMOID>(k, grid, st) : launch_t<3, VN_TANH>(k, grid, st);
+}
+cudaError_t vn_tpp_reduce(const NetDesc& net, const TppLayout& lay, const double* slab, int nCta, double* flat, cudaStream_t st) {
+    tpp_reduce_kernel<<<(net.nparam + 3) / 4, 128, 0, st>>>(net, lay, slab, nCta, flat);
+    return cudaGetLastError();
+}
