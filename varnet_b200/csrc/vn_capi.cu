@@ -846,7 +846,7 @@ static int ensure_work(vn_engine* e) {
         const long long tiles = std::max<long long>(1, (P + 127) / 128), cap = (long long)e->numSMs * e->tppCtas;
         const long long rounds = (tiles + cap - 1) / cap;
         e->gridVar = (int)((tiles + rounds - 1) / rounds);
-        CK(e->partVar.ensure((size_t)cap * e->tppLay.npatch * 64 * sizeof(double)));
+        CK(e->partVar.ensure((size_t)cap * e->tppLay.npatch * 32 * sizeof(double)));
         CK(e->lossPart.ensure((size_t)cap * 4 * sizeof(double)));
         e->fused = true;
         return VN_OK;
@@ -1459,7 +1459,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         a.stash = e->stashVar.as<float>(); a.stashFloats = g.stashFloats;
         a.lossPart = e->lossPart.as<double>();
         const bool tc = e->useTc64, tpp = e->useTpp && needGrad;
-        if (tpp) { a.ntiles = (int)(((long long)e->P + 127) / 128); a.psz = e->tppLay.npatch * 64; }
+        if (tpp) { a.ntiles = (int)(((long long)e->P + 127) / 128); a.psz = e->tppLay.npatch * 32; }
         if (tc) {
             a.ntiles = (int)(((long long)e->P + 127) / 128);
             a.psz = e->tc64Geom.psz; a.stashFloats = e->tc64Geom.stashFloats;

@@ -6,7 +6,7 @@
 //               rowA[l] + s * w_l + k : a_{l,s}[k], later overwritten in place by zbar_{l,s}[k]
 //               rowX + c              : input x_c        rowU + s : adjoint seed ubar_s
 //               rowOne / rowZero      : constant rows (bias row of the weight-gradient patches, padding)
-//   gacc    : [npatch][64] FP64 weight-gradient patches of this CTA (all its tiles)
+//   gacc    : [npatch][32] FP64 weight-gradient patches (8 rows x 4 columns) of this CTA (all its tiles)
 // Per tile: thread-local forward sweep -> integrand -> R_i (warp segment sums) -> seeds -> for block = L, L-1, .., 0:
 //   [barrier] patches of block (cross-thread contraction over the 128 points) [barrier] zbar of the next layer down in place.
 #include <cuda_runtime.h>
@@ -20,9 +20,9 @@ constexpr int NW = T / 32;
 
 struct TppArgs { TileArgs t; TppLayout lay; };
 
-__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ u64 lds64(const float* p) { return *reinterpret_cast<const u64*>(p); }
 
-// transposing warp reduction of N per-lane values: N = 64 leaves elements 2*lane and 2*lane+1 in v[0], v[1];
+// transposing warp reduction of N per-lane values: N = 32 leaves element `lane` in v[0];
 // N = 8 leaves element lane >> 2 in v[0] (on all four lanes of the group)
 template <int N> __device__ __forceinline__ void bfly(float (&v)[N], int lane) {
     int n = N;
@@ -63,7 +63,8 @@ template <int S, int ACT> __device__ __forceinline__ void zbar_in_place(float* a
 }
 
 // Weight-gradient block `blk` (0..L-1: [a_{blk-1}; 1]^T zbar_blk, gW rows then the bias row; L: the output layer, one column):
-// warp `warp` takes 8x8 patches round-robin and contracts them over the T points of the tile.
+// warp `warp` takes 8x4 patches round-robin and contracts them over the T points of the tile.  A lane handles two adjacent points
+// per step: the 64-bit operand loads are the packed operands of fma.rn.f32x2 (one accumulator pair per patch entry).
 template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, const float* rows, double* gacc, int blk, int lane, int warp) {
     const int L = Y.L;
     const int win = blk == 0 ? Y.inpDim : Y.w[blk - 1];
@@ -73,15 +74,15 @@ template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, con
     const int ncb = Y.ncb[blk], nrb = (win + 8) >> 3;
     for (int pi = warp; pi < nrb * ncb; pi += NW) {
         const int rb = pi / ncb, cb = pi - rb * ncb;
-        double* g = gacc + (size_t)(Y.patch0[blk] + pi) * 64;
+        double* g = gacc + (size_t)(Y.patch0[blk] + pi) * 32;
         auto a_row = [&](int s, int r) -> int {           // shared-memory row of operand row r, stream s (warp-uniform)
             if (r < win) return blk == 0 ? (s == 0 ? arow0 + r : (r == s - 1 ? Y.rowOne : Y.rowZero)) : arow0 + s * win + r;
             return (r == win && s == 0) ? Y.rowOne : Y.rowZero;
         };
         if (ncols == 1) {
-            float acc[8];
+            u64 acc2[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            for (int i = 0; i < 8; ++i) acc2[i] = 0ull;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 int ao[8];
@@ -91,48 +92,46 @@ template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, con
 #pragma unroll
                 for (int it = 0; it < T / 64; ++it) {
                     const int p = 2 * lane + 64 * it;
-                    const float2 z = lds2(rows + zo + p);
+                    const u64 z = lds64(rows + zo + p);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 a = lds2(rows + ao[i] + p);
-                        acc[i] = fmaf(a.x, z.x, acc[i]);
-                        acc[i] = fmaf(a.y, z.y, acc[i]);
-                    }
+                    for (int i = 0; i < 8; ++i) ffma2(acc2[i], lds64(rows + ao[i] + p), z);
                 }
             }
-            bfly<8>(acc, lane);
-            if ((lane & 3) == 0) g[(lane >> 2) * 8] += (double)acc[0];
-        } else {
-            float acc[64];
+            float acc[8];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+            for (int i = 0; i < 8; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
+            bfly<8>(acc, lane);
+            if ((lane & 3) == 0) g[(lane >> 2) * 4] += (double)acc[0];
+        } else {
+            u64 acc2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc2[i] = 0ull;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                int ao[8], zo[8];
+                int ao[8], zo[4];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ao[i] = a_row(s, rb * 8 + i) * T;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const int c = cb * 8 + j; zo[j] = (c < ncols ? zrow0 + s * ncols + c : Y.rowZero) * T; }
+                for (int j = 0; j < 4; ++j) { const int c = cb * 4 + j; zo[j] = (c < ncols ? zrow0 + s * ncols + c : Y.rowZero) * T; }
 #pragma unroll
                 for (int it = 0; it < T / 64; ++it) {
                     const int p = 2 * lane + 64 * it;
-                    float2 a[8];
+                    u64 a[8], z[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = lds2(rows + ao[i] + p);
+                    for (int i = 0; i < 8; ++i) a[i] = lds64(rows + ao[i] + p);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 z = lds2(rows + zo[j] + p);
+                    for (int j = 0; j < 4; ++j) z[j] = lds64(rows + zo[j] + p);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            acc[i * 8 + j] = fmaf(a[i].x, z.x, acc[i * 8 + j]);
-                            acc[i * 8 + j] = fmaf(a[i].y, z.y, acc[i * 8 + j]);
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ffma2(acc2[i * 4 + j], a[i], z[j]);
                 }
             }
-            bfly<64>(acc, lane);
-            g[2 * lane] += (double)acc[0];
-            g[2 * lane + 1] += (double)acc[1];
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
+            bfly<32>(acc, lane);
+            g[lane] += (double)acc[0];
         }
     }
 }
@@ -148,10 +147,10 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
     float* wts = smem;
     float* rows = smem + Y.wfloats;
     double* gacc = reinterpret_cast<double*>(rows + (size_t)Y.nrows * T);
-    float* segW = reinterpret_cast<float*>(gacc + (size_t)Y.npatch * 64);
+    float* segW = reinterpret_cast<float*>(gacc + (size_t)Y.npatch * 32);
 
     for (int i = tid; i < Y.wfloats; i += T) wts[i] = 0.f;
-    for (int i = tid; i < Y.npatch * 64; i += T) gacc[i] = 0.0;
+    for (int i = tid; i < Y.npatch * 32; i += T) gacc[i] = 0.0;
     rows[Y.rowOne * T + tid] = 1.f;
     rows[Y.rowZero * T + tid] = 0.f;
     __syncthreads();
@@ -181,6 +180,26 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         const bool valid = gp < A.P;
         const size_t row = valid ? table_row(A, gp) : 0;
 
+        // ---- this point's integrand coefficients (in flight under the forward sweep) and the CTA's next tile -> L2
+        float gco[S - 1], dnt = 0.f, srcn = 0.f, wq = 1.f, dj = 0.f;
+        const unsigned int itf = gp / integNum, q = gp - itf * integNum;
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) gco[k] = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k) gco[k] = __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
+            if (A.timeDependent) dnt = __ldg(A.cols + (size_t)A.colT * A.pstride + row);
+            if (A.isSource) srcn = __ldg(A.cols + (size_t)A.colS * A.pstride + row);
+            if (A.integW) wq = __ldg(A.integW + q);
+            dj = A.detJvec ? __ldg(A.detJ + table_tf(A, itf)) : __ldg(A.detJ);
+        }
+        if (!A.tfIndex && lane == 0 && tile + (int)gridDim.x < A.ntiles) {
+            const size_t nrow = (size_t)(A.tile0 + tile + (int)gridDim.x) * T + tid;        // 32 points = one 128-byte line per column
+            for (int c = 0; c < A.nxTable; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cols + (size_t)(A.colX + c) * A.pstride + nrow));
+            for (int k = 0; k < S - 1; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cols + (size_t)(A.colG + k) * A.pstride + nrow));
+            if (A.timeDependent) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cols + (size_t)A.colT * A.pstride + nrow));
+            if (A.isSource) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cols + (size_t)A.colS * A.pstride + nrow));
+        }
         // ---- inputs
         float x[VN_KIN];
 #pragma unroll
@@ -234,25 +253,35 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
             const float* bl = wts + Y.offB[l];
             const float* ain = rows + Y.rowA[l - 1] * T + tid;
             float* aout = rows + Y.rowA[l] * T + tid;
+            const float* ps[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) ps[s] = ain + s * wi * T;
             for (int j0 = 0; j0 < wo; j0 += 8) {
-                float acc[S][8];
-                { const float4 ba = lds4(bl + j0), bb = lds4(bl + j0 + 4);
-                  acc[0][0] = ba.x; acc[0][1] = ba.y; acc[0][2] = ba.z; acc[0][3] = ba.w; acc[0][4] = bb.x; acc[0][5] = bb.y; acc[0][6] = bb.z; acc[0][7] = bb.w; }
+                // 8 outputs as 4 packed pairs per stream: fma.rn.f32x2 with the broadcast activation, weights straight from the 128-bit loads
+                u64 acc2[S][4];
+                { const ulonglong2 ba = lds2x64(bl + j0), bb = lds2x64(bl + j0 + 4);
+                  acc2[0][0] = ba.x; acc2[0][1] = ba.y; acc2[0][2] = bb.x; acc2[0][3] = bb.y; }
 #pragma unroll
                 for (int s = 1; s < S; ++s)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[s][i] = 0.f;
+                    for (int i = 0; i < 4; ++i) acc2[s][i] = 0ull;
+                const float* wr = Wl + j0;
 #pragma unroll 2
                 for (int k = 0; k < wi; ++k) {
-                    const float4 wa = lds4(Wl + k * wpo + j0), wb = lds4(Wl + k * wpo + j0 + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const ulonglong2 wa = lds2x64(wr + k * wpo), wb = lds2x64(wr + k * wpo + 4);
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        const float a = ain[(s * wi + k) * T];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[s][i] = fmaf(a, wv[i], acc[s][i]);
+                        const float a = ps[s][k * T];
+                        const u64 a2 = pack2(a, a);
+                        ffma2(acc2[s][0], a2, wa.x); ffma2(acc2[s][1], a2, wa.y);
+                        ffma2(acc2[s][2], a2, wb.x); ffma2(acc2[s][3], a2, wb.y);
                     }
                 }
+                float acc[S][8];
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) unpack2(acc2[s][i], acc[s][2 * i], acc[s][2 * i + 1]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (j0 + i < wo) {
@@ -281,20 +310,13 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
             u[0] += wts[Y.offB[L]];
         }
         // ---- integrand I = sum_k u_k gcoef_k - u dNt - source N, times integW_q (TFModel.py:653-660)
-        float gco[S - 1], dnt = 0.f, wq = 1.f;
-        const unsigned int itf = gp / integNum, q = gp - itf * integNum;
         float I = 0.f;
-#pragma unroll
-        for (int k = 0; k < S - 1; ++k) gco[k] = 0.f;
         if (valid) {
 #pragma unroll
-            for (int k = 0; k < S - 1; ++k) {
-                gco[k] = __ldg(A.cols + (size_t)(A.colG + k) * A.pstride + row);
-                I = fmaf(u[1 + k], gco[k], I);
-            }
-            if (A.timeDependent) { dnt = __ldg(A.cols + (size_t)A.colT * A.pstride + row); I -= u[0] * dnt; }
-            if (A.isSource) I -= __ldg(A.cols + (size_t)A.colS * A.pstride + row);
-            if (A.integW) { wq = __ldg(A.integW + q); I *= wq; }
+            for (int k = 0; k < S - 1; ++k) I = fmaf(u[1 + k], gco[k], I);
+            if (A.timeDependent) I -= u[0] * dnt;
+            if (A.isSource) I -= srcn;
+            if (A.integW) I *= wq;
         }
         // ---- R_i = sum_q I_iq: the integNum points of a test function are consecutive threads (integNum | T, a power of two)
         float r = I;
@@ -309,7 +331,6 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         }
         float lam = 0.f;
         if (valid) {
-            const float dj = A.detJvec ? __ldg(A.detJ + table_tf(A, itf)) : __ldg(A.detJ);
             if (q == 0) {
                 const float r2 = r * r;
                 A.R[itf] = r;
@@ -351,23 +372,32 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
             const float* WT = wts + Y.offWT[l];
             const float* zl = rows + Y.rowA[l] * T + tid;
             float* am = rows + Y.rowA[l - 1] * T + tid;
+            const float* pz[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) pz[s] = zl + s * wo * T;
             for (int k0 = 0; k0 < wi; k0 += 8) {
+                u64 acc2[S][4];
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc2[s][i] = 0ull;
+                const float* wr = WT + k0;
+#pragma unroll 2
+                for (int j = 0; j < wo; ++j) {
+                    const ulonglong2 wa = lds2x64(wr + j * wpi), wb = lds2x64(wr + j * wpi + 4);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const float z = pz[s][j * T];
+                        const u64 z2 = pack2(z, z);
+                        ffma2(acc2[s][0], z2, wa.x); ffma2(acc2[s][1], z2, wa.y);
+                        ffma2(acc2[s][2], z2, wb.x); ffma2(acc2[s][3], z2, wb.y);
+                    }
+                }
                 float acc[S][8];
 #pragma unroll
                 for (int s = 0; s < S; ++s)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[s][i] = 0.f;
-#pragma unroll 2
-                for (int j = 0; j < wo; ++j) {
-                    const float4 wa = lds4(WT + j * wpi + k0), wb = lds4(WT + j * wpi + k0 + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const float z = zl[(s * wo + j) * T];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[s][i] = fmaf(z, wv[i], acc[s][i]);
-                    }
-                }
+                    for (int i = 0; i < 4; ++i) unpack2(acc2[s][i], acc[s][2 * i], acc[s][2 * i + 1]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (k0 + i < wi) {
@@ -386,7 +416,7 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
     __syncthreads();
     {
         double* slab = A.part + (size_t)blockIdx.x * A.psz;
-        for (int i = tid; i < Y.npatch * 64; i += T) slab[i] = A.accumulate ? slab[i] + gacc[i] : gacc[i];
+        for (int i = tid; i < Y.npatch * 32; i += T) slab[i] = A.accumulate ? slab[i] + gacc[i] : gacc[i];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lossAcc += __shfl_xor_sync(0xffffffffu, lossAcc, o);
@@ -408,8 +438,8 @@ __global__ void tpp_reduce_kernel(NetDesc net, TppLayout Y, const double* __rest
         if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { row = (idx - net.woff[l]) / wo; col = (idx - net.woff[l]) - row * wo; break; }
         if (idx >= net.boff[l] && idx < net.boff[l] + wo) { row = wi; col = idx - net.boff[l]; break; }
     }
-    const int slot = (Y.patch0[l] + (row >> 3) * Y.ncb[l] + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7);
-    const int psz = Y.npatch * 64;
+    const int slot = (Y.patch0[l] + (row >> 3) * Y.ncb[l] + (col >> 2)) * 32 + (row & 7) * 4 + (col & 3);
+    const int psz = Y.npatch * 32;
     double s = 0.0;
     for (int c = lane; c < nCta; c += 32) s += __ldcg(slab + (size_t)c * psz + slot);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -457,13 +487,13 @@ void vn_tpp_layout(const NetDesc& net, int S, TppLayout* Y) {
     for (int b = 0; b <= net.L; ++b) {
         const int win = b == 0 ? net.inpDim : net.width[b - 1];
         const int ncols = b == net.L ? 1 : net.width[b];
-        Y->ncb[b] = (ncols + 7) >> 3;
+        Y->ncb[b] = (ncols + 3) >> 2;
         Y->patch0[b] = p;
         p += ((win + 8) >> 3) * Y->ncb[b];
     }
     Y->patch0[net.L + 1] = p;
     Y->npatch = p;
-    Y->smemBytes = ((size_t)Y->wfloats + (size_t)Y->nrows * T) * sizeof(float) + (size_t)p * 64 * sizeof(double) + 64;
+    Y->smemBytes = ((size_t)Y->wfloats + (size_t)Y->nrows * T) * sizeof(float) + (size_t)p * 32 * sizeof(double) + 64;
 }
 cudaError_t vn_tpp_prepare(int S, int act, size_t smem, int* ctas) {
     if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem, ctas) : prepare_t<2, VN_TANH>(smem, ctas);

@@ -6,8 +6,8 @@
 // utilisation.  Here one thread owns one quadrature point: the forward sweep (value + `dim` forward tangents), the integrand,
 // the adjoint sweep and z-bar live in that thread's column of a [row][128 points] shared-memory array, looped over the ACTUAL
 // widths in blocks of 8 neurons (weights are warp-uniform 128-bit broadcasts).  Only the weight gradients need the other
-// threads' points: per layer, warps take 8x8 patches of [a_{l-1}; 1]^T [zbar_l] and contract them over the tile's 128 points
-// (two points per lane and step, 64-bit loads), a transposing warp butterfly leaves two patch entries per lane, and those are
+// threads' points: per layer, warps take 8x4 patches of [a_{l-1}; 1]^T [zbar_l] and contract them over the tile's 128 points
+// (two points per lane and step: the 64-bit loads are the packed operands of fma.rn.f32x2), a transposing warp butterfly leaves one patch entry per lane, and those are
 // accumulated in FP64 in shared memory over all tiles of the CTA.  z-bar_l overwrites a_l in place once the patches that need
 // a_l are done, so a CTA needs (sum_l S w_l + inpDim + S + 2) * 512 B: 3-5 CTAs per SM instead of one.
 // Only the variational term (MODE_VAR_FUSED semantics, integNum | 128) runs here; boundary/initial rows and loss-only passes stay
@@ -25,7 +25,7 @@ struct TppLayout {
     int offWT[VN_MAX_LAYERS];      // W_l^T as [out][wpin] (l >= 1), wpin = wp[l-1]
     int offB[VN_MAX_LAYERS + 1];   // biases (l == L: b_out)
     int wfloats;                   // floats of the weight region (multiple of 4)
-    int patch0[VN_MAX_LAYERS + 2]; // first 8x8 patch of gradient block l = 0..L ([a_{l-1}; 1]^T zbar_l; block L: the output layer)
+    int patch0[VN_MAX_LAYERS + 2]; // first 8x4 patch of gradient block l = 0..L ([a_{l-1}; 1]^T zbar_l; block L: the output layer)
     int ncb[VN_MAX_LAYERS + 1];    // column blocks of block l
     int npatch;
     size_t smemBytes;
@@ -34,7 +34,7 @@ struct TppLayout {
 bool vn_tpp_supported(const NetDesc& net, int S);
 void vn_tpp_layout(const NetDesc& net, int S, TppLayout* lay);
 cudaError_t vn_tpp_prepare(int S, int act, size_t smemBytes, int* ctasPerSM);
-// a: as for vn_adj_kernel<MODE_VAR_FUSED>; a.part = [grid][npatch * 64] FP64 patch slabs, a.lossPart = [grid][4]
+// a: as for vn_adj_kernel<MODE_VAR_FUSED>; a.part = [grid][npatch * 32] FP64 patch slabs, a.lossPart = [grid][4]
 cudaError_t vn_tpp_launch(int S, int act, const TileArgs& a, const TppLayout& lay, int grid, cudaStream_t st);
 // fixed-order sum of the per-CTA patch slabs -> flat[nparam] in reference variable order
 cudaError_t vn_tpp_reduce(const NetDesc& net, const TppLayout& lay, const double* slab, int nCta, double* flat, cudaStream_t st);
