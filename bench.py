@@ -349,7 +349,8 @@ def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
         P = int(np.prod(tData.optimFeedicts[0][tw_loc.intShape])) * world
         out[name] = dict(steps_per_sec=steps / dt, quad_points_per_step=P, quad_pts_per_sec=steps * P / dt,
                          steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build, n_gpus=world,
-                         host_round_trips="one per 64 steps (vn_train_steps)" if chunked else "one per step")
+                         host_round_trips="one per 64 steps (vn_train_steps)" if chunked else
+                         ("one per %d mini-batch steps (vn_train_batches)" % tData.batchNum if tData.batchNum > 1 else "one per step"))
         if cpu_seconds > 0 and rank == 0:
             f0 = {k.name: (np.array(v) if type(v).__name__ == "TableView" else v) for k, v in tData.optimFeedicts[0].items()
                   if getattr(k, "tower", None) == tw_loc.index}

@@ -173,6 +173,10 @@ int vn_train_step(vn_engine* e, float lr, float* loss_out);
 /* k steps on the current batch back to back (the captured step graph replayed k times, the k losses returned together):
  * k x sess.run([optMinimize, loss]) on an unchanged feed with one host round trip.  k <= 4096. */
 int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses);
+/* One optimizer step per mini-batch for k mini-batches of the current table with one host round trip: row i of
+ * tf_index[k][nb] is the index list of step i, i.e. k x { vn_set_batch; vn_train_step } = one ManageTrainData.optimIter
+ * over its mini-batches (VarNetUtility.py:1021-1047).  losses[k]; the engine is left on the last batch.  k <= 4096. */
+int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k, float* losses);
 
 /* ---- multi-GPU (one handle per GPU, one process per GPU): the towers' gradients and losses are summed like
  *      TFNN.sum_grads / optimSetup do on the controller (TFModel.py:315-319,342-377), with one NCCL all-reduce of the

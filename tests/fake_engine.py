@@ -160,6 +160,13 @@ class FakeEngine:
         self.optimizer_step(lr)
         return np.float32(loss) if fetch_loss else None
 
+    def train_batches(self, lr, tf_index):
+        out = []
+        for row in np.asarray(tf_index):
+            self.set_batch(row)
+            out.append(self.train_step(lr))
+        return np.asarray(out, dtype=np.float32)
+
     def eval(self, X):
         self.calls["eval"] += 1
         X = np.asarray(X, dtype=np.float32).astype(np.float64).reshape(-1, self.inpDim)

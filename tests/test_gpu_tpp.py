@@ -122,3 +122,31 @@ def test_thread_per_point_training_minibatch_and_extra_inputs():
             assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
     finally:
         eng.close()
+
+
+def test_train_batches_equals_set_batch_plus_train_step():
+    """vn_train_batches (k mini-batches of the resident table, one host round trip) takes bit for bit the steps of
+    k x {vn_set_batch, vn_train_step}: same losses, same weights, the engine left on the last batch."""
+    rng = np.random.RandomState(21)
+    dim, inpDim, lw = 1, 3, [10, 20, 30]
+    nb, integNum, k, nbatch = 240, 16, 6, 40
+    feed = synth_feed(rng, dim, inpDim, nb, integNum, 120, 80)
+    theta = go.glorot_init(inpDim, lw, seed=11)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+    idx = np.stack([rng.permutation(nb)[:nbatch] for _ in range(k)]).astype(np.int32)
+    res = []
+    for batched in (False, True):
+        eng = make_engine(feed, theta=theta, **kw)
+        try:
+            if batched:
+                losses = eng.train_batches(1e-3, idx)
+            else:
+                losses = []
+                for row in idx:
+                    eng.set_batch(row)
+                    losses.append(eng.train_step(1e-3))
+            last = eng.loss_grad()                       # on the last batch, with the final weights
+            res.append((np.asarray(losses, dtype=np.float32), eng.get_params().copy(), float(last["loss"])))
+        finally:
+            eng.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]

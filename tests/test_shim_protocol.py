@@ -168,3 +168,32 @@ def test_device_resident_batches_equal_host_gathers(shim, monkeypatch, name, kw)
     (lv, tv, upv, sbv), (lm, tm, upm, sbm) = results
     assert np.allclose(lv, lm, rtol=1e-12) and np.allclose(tv, tm, rtol=1e-7, atol=1e-9)
     assert upv < upm and sbv > 0            # tables stay resident; batches are index lists
+
+
+def test_minibatch_epoch_as_one_engine_call_equals_per_batch_runs(shim):
+    """ManageTrainData.optimIter over several mini-batches: the batched path (Session.run_batches -> Engine.train_batches, one call
+    per epoch) takes exactly the steps of one sess.run per mini-batch — same losses, same weights, the engine left on the last batch."""
+    import varnet_b200
+
+    def run(batched):
+        FakeEngine.instances.clear()
+        vn = configs.operator_1dtmor(varnet_b200, 0.08, seed=5)
+        tf = vn.tfData
+        fd = vn.fixData; fd.setFEdata()
+        Input, _, biInput, _ = vn.trainingPoints()
+        disc = vn.PDE.MORvar.discretizeArg(vn.MORdiscScheme)
+        tData = varnet_b200.ManageTrainData(Input, biInput, 4, None, True, fd.MORbatchNum)
+        losses = []
+        tf.batch_steps = batched                         # False: the reference-style loop, one sess.run per mini-batch
+        for mb in range(2):
+            tData = vn.trainData(mb, disc, tData)
+            if mb == 0:
+                tData.updateDictFields('trainW', np.array([10., 10., 1.]), normalizeW=False)
+            losses.append(float(tData.optimIter(tf)))
+        eng = FakeEngine.instances[0]
+        return losses, tf.get_parameters().copy(), eng.calls.get("set_batch", 0), np.array(eng.batch)
+
+    l1, th1, nset1, last1 = run(True)
+    l0, th0, nset0, last0 = run(False)
+    assert np.allclose(l1, l0, rtol=1e-12) and np.array_equal(th1, th0)
+    assert np.array_equal(last1, last0) and nset1 >= 8

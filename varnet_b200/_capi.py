@@ -65,6 +65,7 @@ SIGNATURES = {
     "vn_optimizer_step": (C.c_int, [_vp, C.c_float]),
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
     "vn_train_steps": (C.c_int, [_vp, C.c_float, _i32, _f32p]),
+    "vn_train_batches": (C.c_int, [_vp, C.c_float, C.POINTER(_i32), _i64, _i32, _f32p]),
     "vn_comm_unique_id": (C.c_int, [C.c_char_p, _vp]),
     "vn_comm_init": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _i32]),
     "vn_comm_world": (C.c_int, [_vp]),
@@ -411,6 +412,16 @@ class Engine:
         """k optimizer steps on the current batch with one host round trip; returns the k losses."""
         out = np.empty(int(k), dtype=np.float32)
         self._check(self.lib.vn_train_steps(self._h, float(lr), int(k), _ptr(out, C.c_float)))
+        return out
+
+    def train_batches(self, lr, tf_index):
+        """One optimizer step per row of tf_index[k][nb] (mini-batches of the current table) with one host round trip;
+        returns the k losses.  The engine is left on the last batch."""
+        idx = np.ascontiguousarray(tf_index, dtype=np.int32)
+        k, nb = idx.shape
+        out = np.empty(k, dtype=np.float32)
+        self._check(self.lib.vn_train_batches(self._h, float(lr), idx.ctypes.data_as(C.POINTER(_i32)), nb, k, _ptr(out, C.c_float)))
+        self.nb = int(nb)
         return out
 
     # -- evaluation

@@ -391,6 +391,51 @@ class Session:
         o.step_count += len(out)
         return out
 
+    def run_batches(self, feeds):
+        """`run([optMinimize, loss], fd)` for every feed dict of `feeds` in order (ManageTrainData.optimIter, one step per
+        mini-batch): the list of the losses.  When the feeds are index lists of equal length into one device-resident table
+        (TableViews differing only in their test functions) and there is one tower per process, the whole sequence is one
+        engine call (vn_train_batches: the index lists go over once, the step graph is replayed per list); otherwise ordinary runs."""
+        o = self._o
+        towers = self._local_towers()
+        feeds = list(feeds)
+        fast = (len(feeds) > 1 and len(towers) == 1 and hasattr(towers[0].engine, "train_batches") and o.feed_cache and
+                (_dist() is None or o.native_comm))
+        fds = []
+        if fast:
+            tw = towers[0]
+            fds = [{k.name: v for k, v in fd.items() if isinstance(k, Node) and k.tower == tw.index} for fd in feeds]
+            def same_value(a, b):
+                if isinstance(a, TableView) or isinstance(b, TableView):
+                    return isinstance(a, TableView) and isinstance(b, TableView) and a.base is b.base
+                if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+                    return a is b
+                try:
+                    return bool(a == b)
+                except Exception:
+                    return False
+            f0 = fds[0]
+            fast = all(self._is_view_feed(f) for f in fds)
+            for f in fds[1:] if fast else []:
+                same = (set(f) == set(f0) and all(same_value(f[k], f0[k]) for k in f if k not in ("intShape", "w")) and
+                        len(f["Input"].tf) == len(f0["Input"].tf) and f["Input"].integNum == f0["Input"].integNum and
+                        (f["Input"].extra is f0["Input"].extra or np.array_equal(f["Input"].extra, f0["Input"].extra)) and
+                        list(np.ravel(f.get("intShape"))) == list(np.ravel(f0.get("intShape"))) and
+                        np.array_equal(np.asarray(f.get("w")), np.asarray(f0.get("w"))))
+                if not same:
+                    fast = False
+                    break
+        if not fast:
+            return [self.run([o.optMinimize, o.loss], fd)[1] for fd in feeds]
+        tw = towers[0]
+        self._sync_feeds(feeds[0])
+        idx = np.stack([np.asarray(f["Input"].tf, dtype=np.int32).ravel() for f in fds])
+        losses = tw.engine.train_batches(o.learning_rate, idx)
+        tw._tokens["view_batch"] = _token(fds[-1]["Input"].tf)       # the engine is left on the last mini-batch
+        self._last_sig = None
+        o.step_count += len(feeds)
+        return [np.float32(v) for v in losses]
+
     def _gradients(self):
         o = self._o
         towers = self._local_towers()
@@ -576,6 +621,7 @@ class TFNN:
         self.controller = self.processors[0] if controller is None else controller
         self.lossOpt, self.optimizer_name, self.learning_rate = lossOpt, optimizer_name, learning_rate
         self.uploads, self.step_count, self.generated = 0, 0, 0
+        self.batch_steps = True      # an epoch of index-list mini-batches goes to the engine in one call (Session.run_batches)
         # uniform-mesh / constant-coefficient tables are generated on the device instead of uploaded (vn_generate_table_f64)
         self.auto_generate = os.environ.get("VARNET_B200_AUTO_GENERATE", "1") != "0"
         # True: a feed array is uploaded only when it is replaced by a new object (in-place edits of a fed array are NOT

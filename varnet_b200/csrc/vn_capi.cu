@@ -230,6 +230,10 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             for (int p = 0; p < nslot; ++p) s += __ldcg(A.partVar + (size_t)c * pl.psz + slot[p]);
         for (int c = lane; c < A.nBic; c += 32)
             for (int p = 0; p < nslot; ++p) s += __ldcg(A.partBic + (size_t)c * pl.psz + slot[p]);
+        if (A.slab) {
+            const int sl = __ldg(A.slabSlot + idx);
+            for (int c = lane; c < A.nSlab; c += 32) s += __ldcg(A.slab + (size_t)c * A.slabStride + sl);
+        }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
             if (A.flat) s += A.flat[idx];
@@ -461,7 +465,7 @@ struct vn_engine {
     bool useTpp = false;         // ... and the current batch does (integNum | 128)
     TppLayout tppLay{};
     int tppCtas = 0;             // resident CTAs per SM
-    DevBuf tppFlat;
+    DevBuf tppSlot;              // [nparam] slot of each parameter in a CTA's patch slab
     // fed steps (vn_loss_grad_fed_*): copy stream + one event per uploaded chunk
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> fedEvents;
@@ -481,7 +485,7 @@ struct vn_engine {
     // current table through a device index list (vn_select_table / vn_set_batch)
     std::vector<PointSet*> slots;
     PointSet* t = nullptr;
-    DevBuf batchIdx, extraX;
+    DevBuf batchIdx, extraX, batchSeq;
     bool indexed = false;        // batch = index list into the table (else: the whole table in order)
     int nExtra = 0;              // trailing MLP inputs supplied as per-call constants (MOR parameters)
     // parameters + optimizer
@@ -665,7 +669,10 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
                 if (cet != cudaSuccess) { delete e; return fail(VN_E_CUDA, "thread-per-point kernel: %s", cudaGetErrorString(cet)); }
                 if (ctas >= 2) {
                     e->tpp = true; e->tppCtas = ctas;
-                    CK(e->tppFlat.ensure((size_t)e->net.nparam * sizeof(double)));
+                    std::vector<int> slots((size_t)e->net.nparam);
+                    vn_tpp_param_slots(e->net, e->tppLay, slots.data());
+                    CK(e->tppSlot.ensure(slots.size() * sizeof(int)));
+                    CK(cudaMemcpy(e->tppSlot.p, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
                 }
             }
         }
@@ -708,7 +715,7 @@ extern "C" int vn_destroy(vn_engine* e) {
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->tppFlat, &e->lossRing};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->tppSlot, &e->lossRing, &e->batchSeq};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -1495,10 +1502,6 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
             CK(vn_tc64_reduce(e->net, e->partVar.as<double>(), e->tc64Geom.psz, e->gridVar, e->tc64Flat.as<double>(), st));
             e->launches++;
         }
-        if (tpp) {
-            CK(vn_tpp_reduce(e->net, e->tppLay, e->partVar.as<double>(), e->gridVar, e->tppFlat.as<double>(), st));
-            e->launches++;
-        }
         nSeg = e->gridVar * (tc ? e->tc64Geom.lossSlots : (tpp ? 4 : g.NT / 32));
         segPtr = e->lossPart.as<double>();
     } else {
@@ -1542,7 +1545,10 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         f.net = e->net; f.pl = e->gVarAdj.pl;
         f.partVar = e->partVar.as<double>(); f.nVar = e->gridVar;
         if (needGrad && e->fused && e->useTc64) { f.nVar = 0; f.flat = e->tc64Flat.as<double>(); }
-        if (needGrad && e->fused && e->useTpp) { f.nVar = 0; f.flat = e->tppFlat.as<double>(); }
+        if (needGrad && e->fused && e->useTpp) {          // the reduction kernel sums the patch slabs itself (no separate launch)
+            f.nVar = 0; f.slab = e->partVar.as<double>(); f.slabSlot = e->tppSlot.as<int>();
+            f.slabStride = e->tppLay.npatch * 32; f.nSlab = e->gridVar;
+        }
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
         f.segSum = segPtr; f.nSeg = nSeg;
         f.detJ = e->t->detJ.as<float>(); f.detJvec = e->t->detJvec;
@@ -1818,6 +1824,39 @@ extern "C" int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses) 
     if (k > n1) CK(cudaMemcpyAsync(losses + n1, e->lossRing.as<float>(), (size_t)(k - n1) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     float sc[4];
     return read_scalars(e, sc);              // synchronises; reports an expired tensor-core barrier wait
+}
+
+// One optimizer step per mini-batch for k mini-batches of the current table, one host round trip: row i of `tf_index`
+// ([k][nb], host) is the index list of step i (what k x {vn_set_batch, vn_train_step} would do: ManageTrainData.optimIter,
+// VarNetUtility.py:1021-1047, one sess.run per mini-batch).  The k lists are uploaded once; between two replays of the captured
+// step graph only a device-to-device copy of the next list runs on the engine's stream.  The engine is left on the last batch.
+extern "C" int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k, float* losses) {
+    if (!e || !tf_index || !losses) return fail(VN_E_INVALID, "null argument");
+    if (k < 1 || k > kLossRing) return fail(VN_E_INVALID, "k must be in [1, %d]", kLossRing);
+    if (nb < 1) return fail(VN_E_INVALID, "a batch needs at least one test function");
+    if (!e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
+    if (e->t->integNum % 4 != 0) return fail(VN_E_UNSUPPORTED, "indexed batches need integNum to be a multiple of 4");
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t one = (size_t)nb * sizeof(int32_t);
+    CK(e->batchSeq.ensure(one * k));
+    CK(e->batchIdx.ensure(one));
+    CK(cudaMemcpyAsync(e->batchSeq.p, tf_index, one * k, cudaMemcpyHostToDevice, e->stream));
+    long long step0 = 0;
+    CK(cudaMemcpyAsync(&step0, e->stepbuf.p, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->indexed = true; e->nb = (unsigned int)nb;
+    int rc = ensure_work(e);
+    if (rc) return rc;
+    for (int i = 0; i < k; ++i) {
+        CK(cudaMemcpyAsync(e->batchIdx.p, e->batchSeq.as<char>() + one * i, one, cudaMemcpyDeviceToDevice, e->stream));
+        rc = train_step_enqueue(e, lr);
+        if (rc) return rc;
+    }
+    const int a = (int)(step0 % kLossRing), n1 = std::min((int)k, kLossRing - a);
+    CK(cudaMemcpyAsync(losses, e->lossRing.as<float>() + a, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (k > n1) CK(cudaMemcpyAsync(losses + n1, e->lossRing.as<float>(), (size_t)(k - n1) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    float sc[4];
+    return read_scalars(e, sc);
 }
 
 // ------------------------------------------------------------------ evaluation

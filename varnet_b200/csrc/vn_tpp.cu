@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         __syncthreads();           // block 0 has read the input rows and zbar_0 before the next tile overwrites them
     }
 
-    // ---- per-CTA results: FP64 patches (fixed-order sum over CTAs in tpp_reduce_kernel), loss partial per warp
+    // ---- per-CTA results: FP64 patches (summed over the CTAs in fixed order by vn_finalize_kernel), loss partial per warp
     __syncthreads();
     {
         double* slab = A.part + (size_t)blockIdx.x * A.psz;
@@ -424,26 +424,6 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         double* lp = A.lossPart + blockIdx.x * NW + warp;
         *lp = A.accumulate ? *lp + lossAcc : lossAcc;
     }
-}
-
-// flat[idx] = sum over CTAs of the patch entry of parameter idx (one warp per parameter, lanes take CTAs c, c+32, ... in order)
-__global__ void tpp_reduce_kernel(NetDesc net, TppLayout Y, const double* __restrict__ slab, int nCta, double* __restrict__ flat) {
-    const int lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (idx >= net.nparam) return;
-    int l = 0, row = 0, col = 0;
-    for (l = 0; l <= net.L; ++l) {
-        const int wi = l == 0 ? net.inpDim : net.width[l - 1];
-        const int wo = l == net.L ? 1 : net.width[l];
-        if (idx >= net.woff[l] && idx < net.woff[l] + wi * wo) { row = (idx - net.woff[l]) / wo; col = (idx - net.woff[l]) - row * wo; break; }
-        if (idx >= net.boff[l] && idx < net.boff[l] + wo) { row = wi; col = idx - net.boff[l]; break; }
-    }
-    const int slot = (Y.patch0[l] + (row >> 3) * Y.ncb[l] + (col >> 2)) * 32 + (row & 7) * 4 + (col & 3);
-    const int psz = Y.npatch * 32;
-    double s = 0.0;
-    for (int c = lane; c < nCta; c += 32) s += __ldcg(slab + (size_t)c * psz + slot);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) flat[idx] = s;
 }
 
 template <int S, int ACT> cudaError_t launch_t(const TppArgs& k, int grid, cudaStream_t st) {
@@ -505,7 +485,14 @@ cudaError_t vn_tpp_launch(int S, int act, const TileArgs& a, const TppLayout& la
     if (S == 2) return act == VN_SIGMOID ? launch_t<2, VN_SIGMOID>(k, grid, st) : launch_t<2, VN_TANH>(k, grid, st);
     return act == VN_SIGMOID ? launch_t<3, VN_SIGMOID>(k, grid, st) : launch_t<3, VN_TANH>(k, grid, st);
 }
-cudaError_t vn_tpp_reduce(const NetDesc& net, const TppLayout& lay, const double* slab, int nCta, double* flat, cudaStream_t st) {
-    tpp_reduce_kernel<<<(net.nparam + 3) / 4, 128, 0, st>>>(net, lay, slab, nCta, flat);
-    return cudaGetLastError();
+// slot of every flat parameter (reference variable order) in a CTA's patch slab: vn_finalize_kernel sums the slabs in fixed order
+void vn_tpp_param_slots(const NetDesc& net, const TppLayout& Y, int* slots) {
+    for (int l = 0; l <= net.L; ++l) {
+        const int wi = l == 0 ? net.inpDim : net.width[l - 1];
+        const int wo = l == net.L ? 1 : net.width[l];
+        auto slot = [&](int row, int col) { return (Y.patch0[l] + (row >> 3) * Y.ncb[l] + (col >> 2)) * 32 + (row & 7) * 4 + (col & 3); };
+        for (int i = 0; i < wi; ++i)
+            for (int j = 0; j < wo; ++j) slots[net.woff[l] + i * wo + j] = slot(i, j);
+        for (int j = 0; j < wo; ++j) slots[net.boff[l] + j] = slot(wi, j);      // the bias row of the patch block
+    }
 }

@@ -36,5 +36,6 @@ void vn_tpp_layout(const NetDesc& net, int S, TppLayout* lay);
 cudaError_t vn_tpp_prepare(int S, int act, size_t smemBytes, int* ctasPerSM);
 // a: as for vn_adj_kernel<MODE_VAR_FUSED>; a.part = [grid][npatch * 32] FP64 patch slabs, a.lossPart = [grid][4]
 cudaError_t vn_tpp_launch(int S, int act, const TileArgs& a, const TppLayout& lay, int grid, cudaStream_t st);
-// fixed-order sum of the per-CTA patch slabs -> flat[nparam] in reference variable order
-cudaError_t vn_tpp_reduce(const NetDesc& net, const TppLayout& lay, const double* slab, int nCta, double* flat, cudaStream_t st);
+// slots[nparam]: position of every flat parameter (reference variable order) in a CTA's patch slab; vn_finalize_kernel sums
+// the slabs of all CTAs in fixed order (bitwise reproducible)
+void vn_tpp_param_slots(const NetDesc& net, const TppLayout& lay, int* slots);

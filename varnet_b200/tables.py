@@ -410,6 +410,11 @@ class ManageTrainData:
         if not hasattr(self, 'optimFeedicts'):
             raise Exception('\'trainDicts\' must be called first to construct training dictionaries!')
         total = 0
+        if len(self.optimFeedicts) > 1 and hasattr(tfData.sess, "run_batches") and getattr(tfData, "batch_steps", True):
+            # same steps in the same order; index-list mini-batches of one resident table go to the engine in one call
+            for val in tfData.sess.run_batches(self.optimFeedicts):
+                total += val
+            return total
         for fd in self.optimFeedicts:
             _, val = tfData.sess.run([tfData.optMinimize, tfData.loss], feed_dict=fd)
             total += val
