@@ -6,7 +6,9 @@
 //               rowA[l] + s * w_l + k : a_{l,s}[k], later overwritten in place by zbar_{l,s}[k]
 //               rowX + c              : input x_c        rowU + s : adjoint seed ubar_s
 //               rowOne / rowZero      : constant rows (bias row of the weight-gradient patches, padding)
-//   gacc    : [npatch][32] FP64 weight-gradient patches (8 rows x 4 columns) of this CTA (all its tiles)
+//   otab    : operand-row offsets of the weight-gradient patches (tile invariant)
+// The FP64 weight-gradient patches [npatch][32] (8 rows x 4 columns) of a CTA live in its global slab (L2): one RED.ADD.F64 per
+// lane and patch, single writer per slot.
 // Per tile: thread-local forward sweep -> integrand -> R_i (warp segment sums) -> seeds -> for block = L, L-1, .., 0:
 //   [barrier] patches of block (cross-thread contraction over the 128 points) [barrier] zbar of the next layer down in place.
 #include <cuda_runtime.h>
@@ -64,31 +66,27 @@ template <int S, int ACT> __device__ __forceinline__ void zbar_in_place(float* a
 
 // Weight-gradient block `blk` (0..L-1: [a_{blk-1}; 1]^T zbar_blk, gW rows then the bias row; L: the output layer, one column):
 // warp `warp` takes 8x4 patches round-robin and contracts them over the T points of the tile.  A lane handles two adjacent points
-// per step: the 64-bit operand loads are the packed operands of fma.rn.f32x2 (one accumulator pair per patch entry).
-template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, const float* rows, double* gacc, int blk, int lane, int warp) {
-    const int L = Y.L;
-    const int win = blk == 0 ? Y.inpDim : Y.w[blk - 1];
-    const int ncols = blk == L ? 1 : Y.w[blk];
-    const int zrow0 = blk == L ? Y.rowU : Y.rowA[blk];
-    const int arow0 = blk == 0 ? Y.rowX : Y.rowA[blk - 1];
-    const int ncb = Y.ncb[blk], nrb = (win + 8) >> 3;
+// per step: the 64-bit operand loads are the packed operands of fma.rn.f32x2 (one accumulator pair per patch entry).  The
+// shared-memory rows of the operands come from the offset table built once per CTA (build_offsets); a patch entry is added to
+// the CTA's FP64 slab in global memory with a fire-and-forget reduction (one writer per slot and a fixed order of the tiles:
+// bitwise reproducible).
+template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, const float* rows, const int* otab, double* slab, int blk, int lane, int warp) {
+    const int ncols = blk == Y.L ? 1 : Y.w[blk];
+    const int ncb = Y.ncb[blk], nrb = Y.nrb[blk];
+    const int* ta = otab + Y.tabA[blk];               // [S][nrb * 8] operand rows (x T)
+    const int* tz = otab + Y.tabZ[blk];               // [S][ncb * 4] z-bar / seed rows (x T)
     for (int pi = warp; pi < nrb * ncb; pi += NW) {
         const int rb = pi / ncb, cb = pi - rb * ncb;
-        double* g = gacc + (size_t)(Y.patch0[blk] + pi) * 32;
-        auto a_row = [&](int s, int r) -> int {           // shared-memory row of operand row r, stream s (warp-uniform)
-            if (r < win) return blk == 0 ? (s == 0 ? arow0 + r : (r == s - 1 ? Y.rowOne : Y.rowZero)) : arow0 + s * win + r;
-            return (r == win && s == 0) ? Y.rowOne : Y.rowZero;
-        };
+        double* g = slab + (size_t)(Y.patch0[blk] + pi) * 32;
         if (ncols == 1) {
             u64 acc2[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc2[i] = 0ull;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                int ao[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ao[i] = a_row(s, rb * 8 + i) * T;
-                const int zo = (zrow0 + s) * T;
+                const int4 o0 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8), o1 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8 + 4);
+                const int ao[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                const int zo = tz[s * 4];
 #pragma unroll
                 for (int it = 0; it < T / 64; ++it) {
                     const int p = 2 * lane + 64 * it;
@@ -101,18 +99,17 @@ template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, con
 #pragma unroll
             for (int i = 0; i < 8; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
             bfly<8>(acc, lane);
-            if ((lane & 3) == 0) g[(lane >> 2) * 4] += (double)acc[0];
+            if ((lane & 3) == 0) atomicAdd(g + (lane >> 2) * 4, (double)acc[0]);
         } else {
             u64 acc2[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc2[i] = 0ull;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                int ao[8], zo[4];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ao[i] = a_row(s, rb * 8 + i) * T;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const int c = cb * 4 + j; zo[j] = (c < ncols ? zrow0 + s * ncols + c : Y.rowZero) * T; }
+                const int4 o0 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8), o1 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8 + 4);
+                const int4 oz = *reinterpret_cast<const int4*>(tz + s * ncb * 4 + cb * 4);
+                const int ao[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                const int zo[4] = {oz.x, oz.y, oz.z, oz.w};
 #pragma unroll
                 for (int it = 0; it < T / 64; ++it) {
                     const int p = 2 * lane + 64 * it;
@@ -131,7 +128,30 @@ template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, con
 #pragma unroll
             for (int i = 0; i < 32; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
             bfly<32>(acc, lane);
-            g[lane] += (double)acc[0];
+            atomicAdd(g + lane, (double)acc[0]);
+        }
+    }
+}
+
+// operand-row offsets of every weight-gradient block (tile invariant): row r of block blk, stream s -> shared-memory row * T
+__device__ __forceinline__ void build_offsets(const TppLayout& Y, int* otab, int tid) {
+    const int S = Y.S;
+    for (int blk = 0; blk <= Y.L; ++blk) {
+        const int win = blk == 0 ? Y.inpDim : Y.w[blk - 1];
+        const int ncols = blk == Y.L ? 1 : Y.w[blk];
+        const int zrow0 = blk == Y.L ? Y.rowU : Y.rowA[blk];
+        const int arow0 = blk == 0 ? Y.rowX : Y.rowA[blk - 1];
+        const int na = Y.nrb[blk] * 8, nz = Y.ncb[blk] * 4;
+        for (int idx = tid; idx < S * na; idx += T) {
+            const int s = idx / na, r = idx - s * na;
+            int row;
+            if (r < win) row = blk == 0 ? (s == 0 ? arow0 + r : (r == s - 1 ? Y.rowOne : Y.rowZero)) : arow0 + s * win + r;
+            else row = (r == win && s == 0) ? Y.rowOne : Y.rowZero;
+            otab[Y.tabA[blk] + idx] = row * T;
+        }
+        for (int idx = tid; idx < S * nz; idx += T) {
+            const int s = idx / nz, c = idx - s * nz;
+            otab[Y.tabZ[blk] + idx] = (c < ncols ? zrow0 + s * ncols + c : Y.rowZero) * T;
         }
     }
 }
@@ -146,11 +166,14 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* wts = smem;
     float* rows = smem + Y.wfloats;
-    double* gacc = reinterpret_cast<double*>(rows + (size_t)Y.nrows * T);
-    float* segW = reinterpret_cast<float*>(gacc + (size_t)Y.npatch * 32);
+    int* otab = reinterpret_cast<int*>(rows + (size_t)Y.nrows * T);
+    float* segW = reinterpret_cast<float*>(otab + Y.ntab);
+    double* slab = A.part + (size_t)blockIdx.x * A.psz;       // this CTA's FP64 patches (L2 resident)
 
     for (int i = tid; i < Y.wfloats; i += T) wts[i] = 0.f;
-    for (int i = tid; i < Y.npatch * 32; i += T) gacc[i] = 0.0;
+    if (!A.accumulate)
+        for (int i = tid; i < Y.npatch * 32; i += T) slab[i] = 0.0;
+    build_offsets(Y, otab, tid);
     rows[Y.rowOne * T + tid] = 1.f;
     rows[Y.rowZero * T + tid] = 0.f;
     __syncthreads();
@@ -348,7 +371,7 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
 
         // ---- output-layer gradients (block L) need a_{L-1} before it is overwritten
         __syncthreads();
-        phase_b<S>(Y, rows, gacc, L, lane, warp);
+        phase_b<S>(Y, rows, otab, slab, L, lane, warp);
         __syncthreads();
         {
             const int w = Y.w[L - 1];
@@ -364,7 +387,7 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         }
         for (int l = L - 1;; --l) {
             __syncthreads();
-            phase_b<S>(Y, rows, gacc, l, lane, warp);
+            phase_b<S>(Y, rows, otab, slab, l, lane, warp);
             if (l == 0) break;
             __syncthreads();
             // abar_{l-1,s} = zbar_{l,s} W_l^T, then zbar_{l-1} in place of a_{l-1}
@@ -412,12 +435,7 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
         __syncthreads();           // block 0 has read the input rows and zbar_0 before the next tile overwrites them
     }
 
-    // ---- per-CTA results: FP64 patches (summed over the CTAs in fixed order by vn_finalize_kernel), loss partial per warp
-    __syncthreads();
-    {
-        double* slab = A.part + (size_t)blockIdx.x * A.psz;
-        for (int i = tid; i < Y.npatch * 32; i += T) slab[i] = A.accumulate ? slab[i] + gacc[i] : gacc[i];
-    }
+    // ---- per-CTA results: the FP64 patch slab is complete (summed over the CTAs in fixed order by vn_finalize_kernel); loss partial per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lossAcc += __shfl_xor_sync(0xffffffffu, lossAcc, o);
     if (lane == 0) {
@@ -473,7 +491,15 @@ void vn_tpp_layout(const NetDesc& net, int S, TppLayout* Y) {
     }
     Y->patch0[net.L + 1] = p;
     Y->npatch = p;
-    Y->smemBytes = ((size_t)Y->wfloats + (size_t)Y->nrows * T) * sizeof(float) + (size_t)p * 32 * sizeof(double) + 64;
+    int tb = 0;
+    for (int b = 0; b <= net.L; ++b) {
+        const int win = b == 0 ? net.inpDim : net.width[b - 1];
+        Y->nrb[b] = (win + 8) >> 3;
+        Y->tabA[b] = tb; tb += S * Y->nrb[b] * 8;
+        Y->tabZ[b] = tb; tb += S * Y->ncb[b] * 4;
+    }
+    Y->ntab = tb;
+    Y->smemBytes = ((size_t)Y->wfloats + (size_t)Y->nrows * T + (size_t)tb) * sizeof(float) + 64;
 }
 cudaError_t vn_tpp_prepare(int S, int act, size_t smem, int* ctas) {
     if (S == 2) return act == VN_SIGMOID ? prepare_t<2, VN_SIGMOID>(smem, ctas) : prepare_t<2, VN_TANH>(smem, ctas);

@@ -8,7 +8,7 @@
 // widths in blocks of 8 neurons (weights are warp-uniform 128-bit broadcasts).  Only the weight gradients need the other
 // threads' points: per layer, warps take 8x4 patches of [a_{l-1}; 1]^T [zbar_l] and contract them over the tile's 128 points
 // (two points per lane and step: the 64-bit loads are the packed operands of fma.rn.f32x2), a transposing warp butterfly leaves one patch entry per lane, and those are
-// accumulated in FP64 in shared memory over all tiles of the CTA.  z-bar_l overwrites a_l in place once the patches that need
+// accumulated in FP64 in the CTA's own global slab (fire-and-forget reductions, one writer per slot).  z-bar_l overwrites a_l in place once the patches that need
 // a_l are done, so a CTA needs (sum_l S w_l + inpDim + S + 2) * 512 B: 3-5 CTAs per SM instead of one.
 // Only the variational term (MODE_VAR_FUSED semantics, integNum | 128) runs here; boundary/initial rows and loss-only passes stay
 // on the FMA tile class.
@@ -27,6 +27,8 @@ struct TppLayout {
     int wfloats;                   // floats of the weight region (multiple of 4)
     int patch0[VN_MAX_LAYERS + 2]; // first 8x4 patch of gradient block l = 0..L ([a_{l-1}; 1]^T zbar_l; block L: the output layer)
     int ncb[VN_MAX_LAYERS + 1];    // column blocks of block l
+    int nrb[VN_MAX_LAYERS + 1];    // row blocks of block l (rows: a_{l-1} then the bias row)
+    int tabA[VN_MAX_LAYERS + 1], tabZ[VN_MAX_LAYERS + 1], ntab;   // operand-row offset tables (ints, in shared memory)
     int npatch;
     size_t smemBytes;
 };
