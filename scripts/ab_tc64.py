@@ -47,6 +47,12 @@ def child(name):
     bfeed, meta = workloads.generate_on_device(eng, 100, 100, 100, 0, ntf)
     eng.upload_bic(bfeed["biInput"], bfeed["biLabel"], bfeed["bDof"], bfeed["biDimVal"])
     eng.set_weights(np.array([1.0, 1.0, 1.0]))
+    g0 = eng.loss_grad()["grad"].astype(np.float64)          # gradient of the large launch (window folds exercised)
+    np.save("/tmp/ab_grad_%s.npy" % name, g0)
+    gdiff = None
+    if os.environ.get("AB_REF") and os.path.exists("/tmp/ab_grad_%s.npy" % os.environ["AB_REF"]):
+        gr = np.load("/tmp/ab_grad_%s.npy" % os.environ["AB_REF"])
+        gdiff = max(float(rel_inf(g0[sl], gr[sl])) for _, sl in layer_slices(3, lw)[:-1])
     for _ in range(3):
         eng.train_step(1e-3)
     eng.profile_enable(True); eng.profile_read()
@@ -55,7 +61,7 @@ def child(name):
     pr = eng.profile_read()
     k = pr["var_adj"][0] / pr["var_adj"][1]
     eng.close()
-    print(json.dumps(dict(name=name, kernel_ms=round(k, 3), mpts=round(ntf * 64 / k / 1e3, 1), worst_err=worst, loss=float(loss),
+    print(json.dumps(dict(name=name, kernel_ms=round(k, 3), mpts=round(ntf * 64 / k / 1e3, 1), worst_err=worst, grad_vs_first_variant=gdiff, loss=float(loss),
                           errs={a: float("%.2e" % b) for a, b in errs.items()}, info=info.split("|")[0][:80])), flush=True)
 
 
@@ -68,7 +74,7 @@ def main():
         variants.append((name, dict(kv.split("=") for kv in rest.split(",") if kv)))
     for rep in range(2):
         for name, env in variants:
-            e = dict(os.environ, **env)
+            e = dict(os.environ, AB_REF=variants[0][0], **env)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name], env=e, capture_output=True, text=True, timeout=600)
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
             print(line[-1] if line else ("FAILED %s: %s" % (name, (r.stdout + r.stderr)[-1500:])), flush=True)

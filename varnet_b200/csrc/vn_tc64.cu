@@ -21,7 +21,7 @@ constexpr int W = 64;              // padded hidden width
 constexpr int NH = 4;              // neuron groups: warp w -> lane quarter w & 3, neuron group w >> 2
 constexpr int CPT = W / NH;        // neurons (columns) per thread
 constexpr int NT = 128 * NH;       // threads
-constexpr int FOLD = 128;          // tiles accumulated in the FP32 window slab before the FP64 fold (VARNET_B200_TC64_FOLD)
+constexpr int FOLD = 512;          // tiles accumulated in the FP32 window slab before the FP64 fold (VARNET_B200_TC64_FOLD)
 constexpr uint32_t SBO = 128;      // bytes between 8-row groups of a canonical K-major operand
 constexpr uint32_t W_LBO = 2048;   // weight images: 128 rows x 16 B per 4-wide K unit
 constexpr uint32_t G_LBO = 2064;   // weight-gradient operands (K = points): + 16 B pad, transposing stores hit 32 banks
