@@ -150,8 +150,10 @@ int vn_loss_grad(vn_engine* e, float out[4]);
  * every step like the reference does (sess.run(..., feed_dict), VarNetUtility.py:1044; float64 -> float32
  * cast + copy per step): the table is uploaded chunk by chunk on a copy stream and the adjoint kernel is
  * launched per chunk as soon as it has been packed, so the copies overlap the step's kernels.  Same results
- * as the two separate calls; the caller's arrays are no longer read when the call returns.  Falls back to the
- * sequential path for small tables, the two-pass (integNum does not divide the tile) and tensor-core classes. */
+ * as the two separate calls; the caller's arrays are no longer read when the call returns.  Every kernel family takes
+ * the chunks as they arrive (single-pass kernels per chunk; the two-pass class - integNum divides no tile - its forward
+ * pass per chunk; the tensor-core class its own point chunks once the uploads cover them); tables of at most one
+ * 4 Mi-row chunk are uploaded and then stepped. */
 int vn_loss_grad_fed_f32(vn_engine* e, const float* Input, const float* gcoef, const float* source, const float* N,
                          const float* dNt, int64_t nb, int32_t integNum, const float* integW, const float* detJ,
                          int32_t detJvec, float out[4]);

@@ -232,6 +232,46 @@ def test_deep_and_ragged_networks_match_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lw,nb,q", [([16, 16], 125000, 36), ([128, 128], 70000, 64)], ids=["two_pass_q36", "tensor_core_class_w128"])
+def test_fed_step_other_kernel_families(lw, nb, q):
+    """vn_loss_grad_fed on the kernel families that used to fall back to upload-then-step: the two-pass class (integNum = 36 divides
+    no tile: the forward pass now runs per uploaded chunk) and the tensor-core class (its point chunks wait for the uploads that
+    cover them).  Same loss / lossVec bits and gradient as vn_upload_points + vn_loss_grad on a table of more than one 4 Mi-row chunk."""
+    from varnet_b200._capi import Engine
+    import ctypes as C
+    rng = np.random.RandomState(13)
+    dim, inpDim = 2, 3
+    P = nb * q
+    X = rng.uniform(-1, 1, (P, inpDim)); G = rng.randn(P, dim); dNt = rng.randn(P, 1)
+    bX = rng.uniform(-1, 1, (500, inpDim)).astype(np.float32); bL = rng.randn(500, 1).astype(np.float32)
+    theta = go.glorot_init(inpDim, lw, seed=2)
+    outs = []
+    for fed in (False, True):
+        eng = Engine(dim, inpDim, lw, "tanh", True)
+        try:
+            eng.set_params(theta)
+            eng.upload_bic(bX, bL, 300, 2.0)
+            eng.set_weights([3.0, 5.0, 7.0])
+            if fed:
+                eng.loss_grad_fed(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+                g = np.empty(eng.nparam, dtype=np.float32); o = np.empty(4, dtype=np.float32)
+                eng._check(eng.lib.vn_get_grad(eng._h, g.ctypes.data_as(C.POINTER(C.c_float)), g.size, o.ctypes.data_as(C.POINTER(C.c_float))))
+                r = dict(loss=o[0], varLoss=o[3], grad=g)
+            else:
+                eng.upload_points(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+                r = eng.loss_grad()
+            outs.append((r, eng.get_lossvec().copy(), eng.kernel_info()))
+        finally:
+            eng.close()
+    a, b = outs
+    assert ("tcgen05" in a[2]) == (lw[0] > 64) and ("two-pass" in a[2]) == (q == 36), a[2]
+    for k in ("loss", "varLoss"):
+        assert abs(float(a[0][k]) - float(b[0][k])) <= 1e-6 * abs(float(a[0][k])), k
+    assert rel_inf(b[0]["grad"], a[0]["grad"]) <= 1e-6
+    assert np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("feed_dtype", [np.float32, np.float64])
 def test_fed_step_overlapping_copies_equals_upload_then_step(feed_dtype):
     """vn_loss_grad_fed (table uploaded chunk by chunk while the adjoint kernel already runs on the first chunks; pageable NumPy

@@ -873,6 +873,13 @@ static int ensure_work(vn_engine* e) {
 // per-call constants (vn_set_extra_inputs).  The batch is reset to "whole table, in order".
 // A fed step uploads the table chunk by chunk on the copy stream and launches the adjoint kernel once per chunk
 // on the engine stream as soon as that chunk is packed (cudaStreamWaitEvent): copies overlap the step's kernels.
+// tile size in which a fed step (vn_loss_grad_fed_*) hands uploaded chunks to the kernels of this engine
+static int fed_tile(const vn_engine* e, long long integNum) {
+    if (e->wclass == 256) return 128;                                                   // tensor-core class: 128-point tiles
+    if ((e->tc64 || e->tpp) && integNum > 0 && (128 % integNum) == 0) return 128;       // resident-tile tensor-core / thread-per-point kernels
+    if (integNum > 0 && (e->gVarAdj.TP % integNum) == 0) return e->gVarAdj.TP;          // fused FMA tiles
+    return e->gVarFwd.TP;                                                               // two-pass class: the forward pass runs per chunk
+}
 struct FedPlan {
     struct Sub { int tile0, ntiles; cudaEvent_t ev; };
     // chunk k of the table: staged, copied and packed on the copy stream when run_loss asks for it, so that the host-side staging
@@ -998,7 +1005,7 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
         if (t->pstride > P)
             for (int cc = 0; cc < t->ncols; ++cc)
                 CK(cudaMemsetAsync(t->cols.as<float>() + (size_t)cc * t->pstride + P, 0, (size_t)(t->pstride - P) * sizeof(float), us));
-        const int TP = ((e->tc64 || e->tpp) && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
+        const int TP = fed_tile(e, integNum);
         // pageable caller arrays (what NumPy hands over) are staged through pinned bounce buffers by a few host threads
         static const bool stagerOff = [] { const char* v = getenv("VARNET_B200_STAGE_THREADS"); return v && atoi(v) <= 0; }();
         const bool pageable = !stagerOff && is_pageable(X) && is_pageable(G);
@@ -1376,7 +1383,7 @@ static void bic_args(const vn_engine* e, TileArgs* a) {
 }
 
 // tensor-core class: chunked layer pipeline (vn_tc.cu), FP64 accumulation of the gradient across chunks
-static int run_loss_tc(vn_engine* e, bool needGrad) {
+static int run_loss_tc(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr) {
     const vn_config& c = e->cfg;
     cudaStream_t st = e->stream;
     const int np = e->net.nparam;
@@ -1390,8 +1397,24 @@ static int run_loss_tc(vn_engine* e, bool needGrad) {
     {
         j.S = e->S; j.mode = TC_VAR;
         var_args(e, &j.in);
+        size_t pk = 0; long long covered = 0; bool done = false; int prc = 0;
+        if (plan)
+            j.waitRows = [&](unsigned long long need) -> cudaError_t {      // uploads run ahead on the copy stream, chunk by chunk
+                while (!done && covered < (long long)need) {
+                    FedPlan::Sub sub;
+                    const int pr = plan->produce(pk, &sub);
+                    if (pr < 0) { prc = pr; return cudaErrorUnknown; }
+                    if (pr == 0) { done = true; break; }
+                    const cudaError_t we = cudaStreamWaitEvent(st, sub.ev, 0);
+                    if (we != cudaSuccess) return we;
+                    covered = ((long long)sub.tile0 + sub.ntiles) * 128; ++pk;
+                }
+                return cudaSuccess;
+            };
         ProfScope ps(e, PK_VAR_ADJ);
         cudaError_t ce = vn_tc_run(j);
+        j.waitRows = nullptr;
+        if (prc) return prc;
         if (ce != cudaSuccess) return fail(VN_E_CUDA, "tensor-core pipeline (variational term): %s", cudaGetErrorString(ce));
         e->launches += j.launches;
     }
@@ -1428,7 +1451,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
     const vn_config& c = e->cfg;
     CK(cudaSetDevice(c.device));
     cudaStream_t st = e->stream;
-    if (e->wclass == 256) return run_loss_tc(e, needGrad);
+    if (e->wclass == 256) return run_loss_tc(e, needGrad, plan);
     TileArgs a;
     // boundary / initial rows: independent of the variational kernels until the final reduction, so they run on the
     // auxiliary stream next to them (fork here, join before vn_finalize_kernel); sequential when profiling
@@ -1509,9 +1532,23 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         {
             const TileGeom& g = e->gVarFwd;
             a.ntiles = (int)(((long long)e->P + g.TP - 1) / g.TP);
-            const int grid = std::min(a.ntiles, 2 * e->numSMs);
             ProfScope ps(e, PK_VAR_FWD);
-            CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, grid, g.smemBytes, st));
+            if (plan) {
+                // fed step: the forward pass takes every uploaded chunk as soon as it has been packed
+                for (size_t k = 0;; ++k) {
+                    FedPlan::Sub sub;
+                    const int pr = plan->produce(k, &sub);
+                    if (pr < 0) return pr;
+                    if (pr == 0) break;
+                    CK(cudaStreamWaitEvent(st, sub.ev, 0));
+                    a.tile0 = sub.tile0; a.ntiles = sub.ntiles;
+                    CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, st));
+                    if (k) e->launches++;
+                }
+                a.tile0 = 0;
+            } else {
+                CK(vn_tile_launch(e->S, e->wclass, c.act, MODE_VAR_FWD, a, std::min(a.ntiles, 2 * e->numSMs), g.smemBytes, st));
+            }
         }
         // 2. per-test-function residuals R_i, lossVec, block partials of the variational loss
         {
@@ -1605,9 +1642,10 @@ static int loss_grad_fed(vn_engine* e, const T* X, const T* G, const T* src, con
     if (!e) return fail(VN_E_INVALID, "null engine");
     e->nExtra = 0;
     const long long P = (long long)nb * integNum;
-    const int fedTP = ((e->tc64 || e->tpp) && integNum > 0 && (128 % integNum) == 0) ? 128 : e->gVarAdj.TP;
-    const bool overlap = e->wclass != 256 && e->nbi > 0 && P > kChunk && integNum > 0 && (fedTP % integNum) == 0 &&
-                         kChunk % fedTP == 0 && kChunk / fedTP >= e->numSMs && !e->profOn;
+    // every kernel family takes the chunks as they arrive: the fused single-pass kernels per chunk, the two-pass class (integNum does
+    // not divide the tile) its forward pass per chunk, the tensor-core class its own point chunks once the uploads cover them
+    const int fedTP = fed_tile(e, integNum);
+    const bool overlap = e->nbi > 0 && P > kChunk && integNum > 0 && fedTP > 0 && kChunk % fedTP == 0 && kChunk / fedTP >= e->numSMs && !e->profOn;
     if (!overlap) {
         int rc = upload_table<T>(e, X, e->cfg.inpDim, G, src, N, dNt, nb, integNum, integW, detJ, detJvec);
         if (rc) return rc;

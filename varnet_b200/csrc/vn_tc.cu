@@ -1147,6 +1147,7 @@ cudaError_t vn_tc_run(TcJob& j) {
         const unsigned int valid = (unsigned int)std::min<unsigned long long>(chunk, A.P - c0);
         const unsigned int nPts = (valid + TM - 1) / TM * TM;
         const int mTiles = (int)(nPts / TM);
+        if (j.waitRows) TCK(j.waitRows(c0 + valid));
 
         // ---- layer 0
         {

@@ -14,6 +14,7 @@
 // Layer 0 (K = inpDim <= 8), the output layer, the integrand / per-test-function residual and the layer-0
 // gradients are plain FP32 kernels.  Math: SURVEY.md App. A (TFModel.py:515-714).
 #pragma once
+#include <functional>
 #include "vn_tile.cuh"
 
 enum { TC_VAR = 0, TC_BIC = 1, TC_EVAL = 2 };
@@ -41,6 +42,9 @@ struct TcJob {
     cudaStream_t st;
     int numSMs;
     long long launches;     // out: kernels launched
+    // optional (fed steps): called before a chunk is processed with the number of leading table rows it needs; makes the stream
+    // wait for the uploads that cover them (vn_loss_grad_fed on the tensor-core class)
+    std::function<cudaError_t(unsigned long long)> waitRows;
 };
 
 // theta -> zero-padded quad-major copies of the hidden kernels (both orientations) inside the workspace

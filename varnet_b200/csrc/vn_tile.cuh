@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(C::NT, 1) vn_fwd_kernel(const __grid_constant_
     stage_network<C>(A, m, smem, (int)tile_smem_floats<C>(L, false), RES ? A.dim + (A.timeDependent ? 1 : 0) : C::S - 1);
 
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
-        const unsigned int base = (unsigned int)tile * TP;
+        const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;      // tile0: forward launched per uploaded chunk (vn_loss_grad_fed, two-pass class)
         load_inputs<C>(A, m, base);
         __syncthreads();
         for (int l = 0; l < L; ++l) {
