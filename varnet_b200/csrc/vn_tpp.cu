@@ -24,8 +24,8 @@ struct TppArgs { TileArgs t; TppLayout lay; };
 
 __device__ __forceinline__ u64 lds64(const float* p) { return *reinterpret_cast<const u64*>(p); }
 
-// transposing warp reduction of N per-lane values: N = 32 leaves element `lane` in v[0];
-// N = 8 leaves element lane >> 2 in v[0] (on all four lanes of the group)
+// transposing warp reduction of N per-lane values: N = 32 leaves element `lane` in v[0]; N = 16 element lane >> 1 (on both
+// lanes of the pair); N = 8 element lane >> 2 (on all four lanes of the group)
 template <int N> __device__ __forceinline__ void bfly(float (&v)[N], int lane) {
     int n = N;
 #pragma unroll
@@ -64,6 +64,41 @@ template <int S, int ACT> __device__ __forceinline__ void zbar_in_place(float* a
     a[k * T] = fmaf(abar[0], d1, act_d2r<ACT>(a0) * cross);
 }
 
+// One NR x 4 patch of a weight-gradient block, contracted over the T points of the tile: ta / tz = offset-table rows of the
+// patch's operand rows / columns (stream s at + s * sa / + s * sz).  NR = 8, or 4 for a short last row block.
+template <int S, int NR> __device__ __forceinline__ void patch_full(const float* rows, const int* ta, int sa, const int* tz, int sz, double* g, int lane) {
+    u64 acc2[NR * 4];
+#pragma unroll
+    for (int i = 0; i < NR * 4; ++i) acc2[i] = 0ull;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        int ao[NR];
+        { const int4 o0 = *reinterpret_cast<const int4*>(ta + s * sa); ao[0] = o0.x; ao[1] = o0.y; ao[2] = o0.z; ao[3] = o0.w; }
+        if (NR == 8) { const int4 o1 = *reinterpret_cast<const int4*>(ta + s * sa + 4); ao[NR - 4] = o1.x; ao[NR - 3] = o1.y; ao[NR - 2] = o1.z; ao[NR - 1] = o1.w; }
+        const int4 oz = *reinterpret_cast<const int4*>(tz + s * sz);
+        const int zo[4] = {oz.x, oz.y, oz.z, oz.w};
+#pragma unroll
+        for (int it = 0; it < T / 64; ++it) {
+            const int p = 2 * lane + 64 * it;
+            u64 a[NR], z[4];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) a[i] = lds64(rows + ao[i] + p);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[j] = lds64(rows + zo[j] + p);
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ffma2(acc2[i * 4 + j], a[i], z[j]);
+        }
+    }
+    float acc[NR * 4];
+#pragma unroll
+    for (int i = 0; i < NR * 4; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
+    bfly<NR * 4>(acc, lane);
+    if (NR == 8) atomicAdd(g + lane, (double)acc[0]);
+    else if ((lane & 1) == 0) atomicAdd(g + (lane >> 1), (double)acc[0]);
+}
+
 // Weight-gradient block `blk` (0..L-1: [a_{blk-1}; 1]^T zbar_blk, gW rows then the bias row; L: the output layer, one column):
 // warp `warp` takes 8x4 patches round-robin and contracts them over the T points of the tile.  A lane handles two adjacent points
 // per step: the 64-bit operand loads are the packed operands of fma.rn.f32x2 (one accumulator pair per patch entry).  The
@@ -72,6 +107,7 @@ template <int S, int ACT> __device__ __forceinline__ void zbar_in_place(float* a
 // bitwise reproducible).
 template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, const float* rows, const int* otab, double* slab, int blk, int lane, int warp) {
     const int ncols = blk == Y.L ? 1 : Y.w[blk];
+    const int win = blk == 0 ? Y.inpDim : Y.w[blk - 1];      // operand rows: win activations (inputs) + the bias row
     const int ncb = Y.ncb[blk], nrb = Y.nrb[blk];
     const int* ta = otab + Y.tabA[blk];               // [S][nrb * 8] operand rows (x T)
     const int* tz = otab + Y.tabZ[blk];               // [S][ncb * 4] z-bar / seed rows (x T)
@@ -100,35 +136,10 @@ template <int S> __device__ __forceinline__ void phase_b(const TppLayout& Y, con
             for (int i = 0; i < 8; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
             bfly<8>(acc, lane);
             if ((lane & 3) == 0) atomicAdd(g + (lane >> 2) * 4, (double)acc[0]);
+        } else if (rb == nrb - 1 && win + 1 - rb * 8 <= 4) {
+            patch_full<S, 4>(rows, ta + rb * 8, nrb * 8, tz + cb * 4, ncb * 4, g, lane);     // short last row block: 4 x 4 patch
         } else {
-            u64 acc2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc2[i] = 0ull;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                const int4 o0 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8), o1 = *reinterpret_cast<const int4*>(ta + s * nrb * 8 + rb * 8 + 4);
-                const int4 oz = *reinterpret_cast<const int4*>(tz + s * ncb * 4 + cb * 4);
-                const int ao[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-                const int zo[4] = {oz.x, oz.y, oz.z, oz.w};
-#pragma unroll
-                for (int it = 0; it < T / 64; ++it) {
-                    const int p = 2 * lane + 64 * it;
-                    u64 a[8], z[4];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = lds64(rows + ao[i] + p);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) z[j] = lds64(rows + zo[j] + p);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ffma2(acc2[i * 4 + j], a[i], z[j]);
-                }
-            }
-            float acc[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { float lo, hi; unpack2(acc2[i], lo, hi); acc[i] = lo + hi; }
-            bfly<32>(acc, lane);
-            atomicAdd(g + lane, (double)acc[0]);
+            patch_full<S, 8>(rows, ta + rb * 8, nrb * 8, tz + cb * 4, ncb * 4, g, lane);
         }
     }
 }
