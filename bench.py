@@ -323,10 +323,12 @@ def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
                 return n
             steps = 0
             for _ in range(n):
+                total = 0
                 for b in range(fd.MORbatchNum):
                     tData = vn.trainData(b, disc, tData)
-                    tData.optimIter(tf)
+                    total += tData.optimIter(tf)        # may be a backend.Deferred: the steps are enqueued, not waited for
                     steps += tData.batchNum
+                float(total)                            # the epoch's loss, as VarNet.train reads it: every step has completed
             return steps
         epochs(1)                                      # warm-up (also caches the MOR batches on the host)
         # every rank runs the same number of epochs (the steps contain a collective): fixed count from a short calibration
@@ -350,7 +352,8 @@ def operator_config_steps(world=1, rank=0, budget_s=4.0, cpu_seconds=0.0):
         out[name] = dict(steps_per_sec=steps / dt, quad_points_per_step=P, quad_pts_per_sec=steps * P / dt,
                          steps_per_epoch=int(fd.MORbatchNum * tData.batchNum), table_build_s=t_build, n_gpus=world,
                          host_round_trips="one per 64 steps (vn_train_steps)" if chunked else
-                         ("one per %d mini-batch steps (vn_train_batches)" % tData.batchNum if tData.batchNum > 1 else "one per step"))
+                         ("one per %d mini-batch steps (vn_train_batches_begin/_end; the host prepares the next MOR batch meanwhile)" % tData.batchNum
+                          if tData.batchNum > 1 else "one per step"))
         if cpu_seconds > 0 and rank == 0:
             f0 = {k.name: (np.array(v) if type(v).__name__ == "TableView" else v) for k, v in tData.optimFeedicts[0].items()
                   if getattr(k, "tower", None) == tw_loc.index}

@@ -179,6 +179,14 @@ int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses);
  * tf_index[k][nb] is the index list of step i, i.e. k x { vn_set_batch; vn_train_step } = one ManageTrainData.optimIter
  * over its mini-batches (VarNetUtility.py:1021-1047).  losses[k]; the engine is left on the last batch.  k <= 4096. */
 int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k, float* losses);
+/* The same call in two halves: _begin copies the index lists into a pinned staging buffer and enqueues the copies, the k
+ * steps and the read-back of their losses without waiting; _end waits for them and returns losses[k] (and reports an
+ * expired tensor-core barrier wait).  Between the two the caller prepares the next feed dicts (the host work of the next
+ * MOR parameter batch, VarNet.py:843-851) while the GPU runs.  Up to two calls may be in flight per engine (the next one
+ * is enqueued, together with the vn_set_extra_inputs / vn_upload_bic_* that precede it, before the previous one is
+ * collected: those small uploads are staged in pinned memory and do not wait either); _end collects the older one. */
+int vn_train_batches_begin(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k);
+int vn_train_batches_end(vn_engine* e, float* losses, int32_t k);
 
 /* ---- multi-GPU (one handle per GPU, one process per GPU): the towers' gradients and losses are summed like
  *      TFNN.sum_grads / optimSetup do on the controller (TFModel.py:315-319,342-377), with one NCCL all-reduce of the

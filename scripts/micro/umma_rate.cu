@@ -15,6 +15,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
     d |= (uint64_t)1 << 46;
     return d;
 }
+// MN-major operand, LayoutType::SWIZZLE_128B_BASE32B: rows of 128 B (32 elements of M/N), k atoms of 4 rows, MN groups 16 KB apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((16384u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
 __device__ __forceinline__ uint32_t idesc(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t aT, uint64_t db, uint32_t id, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
@@ -49,6 +59,11 @@ template <int PAT> __device__ __forceinline__ void issue_one(int i, uint32_t tme
     if (PAT == 10) mma_ts(tmem + 256, tmem + kb * 8, db[kb], idesc(256), 1u);                             // TS N256
     if (PAT == 11) mma_ts(tmem + 256, tmem + kb * 8, db[kb], idesc(192), 1u);                             // TS N192
     if (PAT == 12) mma_ts(tmem + 384, tmem + kb * 8, db[kb], idesc(32), 1u);                              // TS N32
+    if (PAT == 13) mma_ss(tmem + 384, make_desc_mn((uint32_t)(da[0] & 0x3FFF) * 16 + kb * 1024), make_desc_mn((uint32_t)(db[0] & 0x3FFF) * 16 + kb * 1024), idesc(128) | (3u << 15), 1u);   // SS N128, A and B MN-major
+    if (PAT == 14) mma_ss(tmem + 384, make_desc_mn((uint32_t)(da[0] & 0x3FFF) * 16 + kb * 1024), db[kb], idesc(128) | (1u << 15), 1u);   // SS N128, A MN-major
+    if (PAT == 15) mma_ss(tmem + 384, da[kb], make_desc_mn((uint32_t)(db[0] & 0x3FFF) * 16 + kb * 1024), idesc(128) | (1u << 16), 1u);   // SS N128, B MN-major
+    if (PAT == 16) mma_ts(tmem + 384, tmem + kb * 8, make_desc_mn((uint32_t)(db[0] & 0x3FFF) * 16 + kb * 1024), idesc(128) | (1u << 16), 1u);   // TS N128, B MN-major
+    if (PAT == 17) mma_ts(tmem + 384, tmem + kb * 8, make_desc_mn((uint32_t)(db[0] & 0x3FFF) * 16 + kb * 1024), idesc(64) | (1u << 16), 1u);    // TS N64, B MN-major
 }
 template <int PAT> __device__ __forceinline__ void run_pat(long long* out, int n, uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t bar, uint32_t& phase) {
     for (int rep = 0; rep < 3; ++rep) {
@@ -94,13 +109,15 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int npat, 
     run_pat<6>(out, n, tmem, sa, sb, bar, phase); run_pat<7>(out, n, tmem, sa, sb, bar, phase); run_pat<8>(out, n, tmem, sa, sb, bar, phase);
     run_pat<9>(out, n, tmem, sa, sb, bar, phase); run_pat<10>(out, n, tmem, sa, sb, bar, phase); run_pat<11>(out, n, tmem, sa, sb, bar, phase);
     run_pat<12>(out, n, tmem, sa, sb, bar, phase);
+    run_pat<13>(out, n, tmem, sa, sb, bar, phase); run_pat<14>(out, n, tmem, sa, sb, bar, phase); run_pat<15>(out, n, tmem, sa, sb, bar, phase);
+    run_pat<16>(out, n, tmem, sa, sb, bar, phase); run_pat<17>(out, n, tmem, sa, sb, bar, phase);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 int main() {
-    const int npat = 13;
+    const int npat = 18;
     long long* d; cudaMalloc(&d, npat * 3 * 2 * sizeof(long long));
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536);
     long long h[2][npat * 3];
@@ -113,7 +130,8 @@ int main() {
     }
     const char* names[npat] = {"SS N128 one acc", "SS N128 two accs", "TS N128 one acc", "TS N128 two accs", "TS N64 one acc", "TS N64 two accs",
                                "TS N64 four accs", "fwd pattern (TS N128 + TS N64)", "adj pattern (main,small,small N64)", "SS N64 one acc",
-                               "TS N256", "TS N192", "TS N32"};
+                               "TS N256", "TS N192", "TS N32", "SS N128 A,B MN-major (BASE32B)", "SS N128 A MN-major", "SS N128 B MN-major",
+                               "TS N128 B MN-major", "TS N64 B MN-major"};
     for (int p = 0; p < npat; ++p) {
         const double per = (double)(h[1][p * 3 + 2] - h[0][p * 3 + 2]) / (ns[1] - ns[0]);
         printf("%-38s  n=48: %6lld cyc  n=240: %6lld cyc  -> %.1f cyc/MMA (148 CTAs, all SMs busy)\n", names[p], h[0][p * 3 + 2], h[1][p * 3 + 2], per);

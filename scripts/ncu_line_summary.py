@@ -39,7 +39,7 @@ for addr, src, n, ex, st in recs:
     for k, v in st.items():
         by_line[l][2][k] += v
 tot = sum(v[0] for v in by_line.values())
-src_lines = open("varnet_b200/csrc/vn_tc64.cu").read().split("\n")
+src_lines = open(sys.argv[5] if len(sys.argv) > 5 else "varnet_b200/csrc/vn_tc64.cu").read().split("\n")
 print("total samples", tot)
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 for l, (n, ex, st) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:

@@ -19,10 +19,17 @@ tData.updateDictFields('trainW', np.array([10., 10., 1.]))
 tf = vn.tfData
 def epoch():
     global tData
+    total = 0
     for b in range(fd.MORbatchNum):
         tData = vn.trainData(b, disc, tData)
-        tData.optimIter(tf)
+        total += tData.optimIter(tf)
+    return float(total)
 epoch(); epoch()
-t0 = time.perf_counter(); epoch(); print("epoch s", time.perf_counter() - t0, "uploads", tf.uploads)
+for rep in range(3):
+    t0 = time.perf_counter()
+    for _ in range(20):
+        loss = epoch()
+    dt = (time.perf_counter() - t0) / 20
+    print("epoch %.3f ms  %.0f steps/s  loss %.6g  uploads %d  defer %s" % (dt * 1e3, fd.MORbatchNum * tData.batchNum / dt, loss, tf.uploads, tf.defer_losses))
 cProfile.run("epoch()", "/tmp/prof.out")
 pstats.Stats("/tmp/prof.out").sort_stats("cumulative").print_stats(18)

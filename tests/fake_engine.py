@@ -167,6 +167,18 @@ class FakeEngine:
             out.append(self.train_step(lr))
         return np.asarray(out, dtype=np.float32)
 
+    def train_batches_begin(self, lr, tf_index):
+        pend = self.__dict__.setdefault("_pending", [])
+        if len(pend) >= 2:
+            raise RuntimeError("two vn_train_batches_begin calls are in flight")
+        pend.append(self.train_batches(lr, tf_index))
+
+    def train_batches_end(self):
+        pend = self.__dict__.setdefault("_pending", [])
+        if not pend:
+            raise RuntimeError("no train_batches_begin call is in flight")
+        return pend.pop(0)
+
     def eval(self, X):
         self.calls["eval"] += 1
         X = np.asarray(X, dtype=np.float32).astype(np.float64).reshape(-1, self.inpDim)

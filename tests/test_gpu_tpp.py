@@ -135,11 +135,24 @@ def test_train_batches_equals_set_batch_plus_train_step():
     kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="sigmoid", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
     idx = np.stack([rng.permutation(nb)[:nbatch] for _ in range(k)]).astype(np.int32)
     res = []
-    for batched in (False, True):
+    for batched in (0, 1, 2):
         eng = make_engine(feed, theta=theta, **kw)
         try:
-            if batched:
+            if batched == 1:
                 losses = eng.train_batches(1e-3, idx)
+            elif batched == 2:
+                # the two halves (vn_train_batches_begin / _end), two calls in flight
+                eng.train_batches_begin(1e-3, idx[:k // 3])
+                eng.train_batches_begin(1e-3, idx[k // 3:2 * (k // 3)])
+                with pytest.raises(Exception):
+                    eng.train_batches_begin(1e-3, idx[:1])               # a third call in flight is refused
+                with pytest.raises(Exception):
+                    eng.train_batches(1e-3, idx[:1])                     # and so is the waiting form
+                first = eng.train_batches_end()                          # the older one
+                eng.train_batches_begin(1e-3, idx[2 * (k // 3):])
+                losses = np.concatenate([first, eng.train_batches_end(), eng.train_batches_end()])
+                with pytest.raises(Exception):
+                    eng.train_batches_end()
             else:
                 losses = []
                 for row in idx:
@@ -149,4 +162,5 @@ def test_train_batches_equals_set_batch_plus_train_step():
             res.append((np.asarray(losses, dtype=np.float32), eng.get_params().copy(), float(last["loss"])))
         finally:
             eng.close()
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]) and np.array_equal(res[0][1], r[1]) and res[0][2] == r[2]

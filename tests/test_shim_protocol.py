@@ -197,3 +197,46 @@ def test_minibatch_epoch_as_one_engine_call_equals_per_batch_runs(shim):
     l0, th0, nset0, last0 = run(False)
     assert np.allclose(l1, l0, rtol=1e-12) and np.array_equal(th1, th0)
     assert np.array_equal(last1, last0) and nset1 >= 8
+
+
+def test_deferred_epoch_losses_equal_waited_ones(shim):
+    """Session.run_batches leaves the mini-batch steps running and returns backend.Deferred losses (vn_train_batches_begin / _end):
+    an epoch summed over the MOR batches before anything is waited for gives the very same number and weights as the waiting
+    path, a second call collects the first, and any other session call collects what is in flight."""
+    import varnet_b200
+    from varnet_b200.backend import Deferred
+
+    def run(defer):
+        FakeEngine.instances.clear()
+        vn = configs.operator_1dtmor(varnet_b200, 0.08, seed=5)
+        tf = vn.tfData
+        tf.defer_losses = defer
+        fd = vn.fixData; fd.setFEdata()
+        Input, _, biInput, _ = vn.trainingPoints()
+        disc = vn.PDE.MORvar.discretizeArg(vn.MORdiscScheme)
+        tData = varnet_b200.ManageTrainData(Input, biInput, 4, None, True, fd.MORbatchNum)
+        epochs, kinds = [], []
+        for ep in range(2):
+            total = 0
+            for mb in range(fd.MORbatchNum):
+                tData = vn.trainData(mb, disc, tData)
+                if ep == 0 and mb == 0:
+                    tData.updateDictFields('trainW', np.array([10., 10., 1.]), normalizeW=False)
+                v = tData.optimIter(tf)
+                kinds.append(isinstance(v, Deferred))
+                total += v
+            epochs.append(total)
+        pending_before = bool(getattr(tf.sess, "_pending", None))
+        theta = tf.get_parameters().copy()
+        lc = tData.splitLoss(tf, False)                               # another session call: collects what is in flight
+        pending_after = bool(getattr(tf.sess, "_pending", None))
+        vals = [e.value() if isinstance(e, Deferred) else e for e in epochs]
+        return vals, theta, kinds, pending_before, pending_after, lc[:3]
+
+    v1, th1, k1, pb1, pa1, lc1 = run(True)
+    v0, th0, k0, pb0, pa0, lc0 = run(False)
+    assert all(k1) and not any(k0)
+    assert pb1 and not pa1 and not pb0
+    assert [type(a) for a in v1] == [type(a) for a in v0]
+    assert v1 == v0 and np.array_equal(th1, th0) and lc1 == lc0
+    assert v1[1] < v1[0]                                              # and it trains

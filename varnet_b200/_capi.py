@@ -66,6 +66,8 @@ SIGNATURES = {
     "vn_train_step": (C.c_int, [_vp, C.c_float, _f32p]),
     "vn_train_steps": (C.c_int, [_vp, C.c_float, _i32, _f32p]),
     "vn_train_batches": (C.c_int, [_vp, C.c_float, C.POINTER(_i32), _i64, _i32, _f32p]),
+    "vn_train_batches_begin": (C.c_int, [_vp, C.c_float, C.POINTER(_i32), _i64, _i32]),
+    "vn_train_batches_end": (C.c_int, [_vp, _f32p, _i32]),
     "vn_comm_unique_id": (C.c_int, [C.c_char_p, _vp]),
     "vn_comm_init": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _i32]),
     "vn_comm_world": (C.c_int, [_vp]),
@@ -422,6 +424,25 @@ class Engine:
         out = np.empty(k, dtype=np.float32)
         self._check(self.lib.vn_train_batches(self._h, float(lr), idx.ctypes.data_as(C.POINTER(_i32)), nb, k, _ptr(out, C.c_float)))
         self.nb = int(nb)
+        return out
+
+    def train_batches_begin(self, lr, tf_index):
+        """First half of train_batches: enqueue the k steps and return at once (vn_train_batches_begin); the losses are
+        collected by train_batches_end().  Up to two calls in flight per engine."""
+        idx = np.ascontiguousarray(tf_index, dtype=np.int32)
+        k, nb = idx.shape
+        self._check(self.lib.vn_train_batches_begin(self._h, float(lr), idx.ctypes.data_as(C.POINTER(_i32)), nb, k))
+        self.nb = int(nb)
+        self.__dict__.setdefault("_pending_k", []).append(int(k))
+
+    def train_batches_end(self):
+        """Losses of the OLDER call in flight."""
+        pend = self.__dict__.setdefault("_pending_k", [])
+        if not pend:
+            raise RuntimeError("no train_batches_begin call is in flight")
+        k = pend.pop(0)
+        out = np.empty(k, dtype=np.float32)
+        self._check(self.lib.vn_train_batches_end(self._h, _ptr(out, C.c_float), k))
         return out
 
     # -- evaluation

@@ -123,6 +123,50 @@ def _token(v):
     return ("s", v)
 
 
+class Deferred:
+    """A loss value (or a sum of them) whose device work has been enqueued but not waited for: `Session.run_batches` returns
+    these when the mini-batch steps of a call are still running, so that the caller's host work for the next MOR batch
+    (VarNet.py:843-851) overlaps them.  It turns into the number on first use (float(), comparison, formatting, NumPy
+    conversion, `.value()`); `+` builds another Deferred that performs the very same additions later."""
+    __slots__ = ("_fn", "_val")
+
+    def __init__(self, fn):
+        self._fn, self._val = fn, None
+
+    def value(self):
+        if self._fn is not None:
+            self._val, self._fn = self._fn(), None
+        return self._val
+
+    @staticmethod
+    def _of(x):
+        return x.value() if isinstance(x, Deferred) else x
+
+    def __add__(self, other):
+        return Deferred(lambda: self.value() + Deferred._of(other))
+
+    def __radd__(self, other):
+        return Deferred(lambda: Deferred._of(other) + self.value())
+
+    def __float__(self):
+        return float(self.value())
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.value(), dtype=dtype)
+
+    def __lt__(self, o): return self.value() < Deferred._of(o)
+    def __le__(self, o): return self.value() <= Deferred._of(o)
+    def __gt__(self, o): return self.value() > Deferred._of(o)
+    def __ge__(self, o): return self.value() >= Deferred._of(o)
+    def __eq__(self, o): return self.value() == Deferred._of(o)
+    def __ne__(self, o): return self.value() != Deferred._of(o)
+    __hash__ = None
+
+    def __format__(self, spec): return format(self.value(), spec)
+    def __repr__(self): return repr(self.value())
+    def __str__(self): return str(self.value())
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -147,12 +191,16 @@ class Session:
         self._o = owner
 
     def close(self):
+        try:
+            self._collect()
+        except Exception:
+            pass
         for tw in self._o.compTowers:
             if tw.engine is not None:
                 tw.engine.close()
 
     # -- feed handling
-    def _sync_feeds(self, feed, need_points=True, need_bic=True, defer_points=False):
+    def _sync_feeds(self, feed, need_points=True, need_bic=True, defer_points=False, set_batch=True):
         # fast path for the launch-bound configs: the very same feed dict holding the very same objects as at
         # the previous call has nothing to upload (tokens below are only computed when something was replaced)
         if self._o.feed_cache and feed is not None:
@@ -172,7 +220,7 @@ class Session:
             fd, eng, tok = by_tower[tw.index], tw.engine, tw._tokens
             if need_points and "Input" in fd and "intShape" in fd:
                 if self._is_view_feed(fd):
-                    self._sync_view_feed(tw, fd)
+                    self._sync_view_feed(tw, fd, set_batch)
                 else:
                     names = ("Input", "gcoef", "source", "N", "dNt", "intShape", "integW", "detJ", "detJvec")
                     t = tuple(_token(fd.get(k)) for k in names)
@@ -224,7 +272,7 @@ class Session:
                 return False
         return isinstance(fd.get("gcoef"), TableView)
 
-    def _sync_view_feed(self, tw, fd):
+    def _sync_view_feed(self, tw, fd, set_batch=True):
         o, eng, tok = self._o, tw.engine, tw._tokens
         X = fd["Input"]
         base = lambda k: (fd[k].base if isinstance(fd.get(k), TableView) else fd.get(k))
@@ -266,7 +314,7 @@ class Session:
             eng.set_extra_inputs(extra)
             tok["view_extra"] = extra
         bt = _token(X.tf)
-        if tok.get("view_batch") != bt:
+        if set_batch and tok.get("view_batch") != bt:                 # run_batches hands all its index lists over itself
             eng.set_batch(X.tf)
             tok["view_batch"] = bt
         tok["view"] = True
@@ -380,6 +428,7 @@ class Session:
         k = int(k)
         fast = (k > 1 and len(towers) == 1 and hasattr(towers[0].engine, "train_steps") and o.feed_cache and
                 (_dist() is None or o.native_comm))
+        self._collect()
         if not fast:
             return [self.run([o.optMinimize, o.loss], feed_dict)[1] for _ in range(k)]
         self._sync_feeds(feed_dict)
@@ -406,35 +455,69 @@ class Session:
             tw = towers[0]
             fds = [{k.name: v for k, v in fd.items() if isinstance(k, Node) and k.tower == tw.index} for fd in feeds]
             def same_value(a, b):
+                if a is b:
+                    return True
                 if isinstance(a, TableView) or isinstance(b, TableView):
                     return isinstance(a, TableView) and isinstance(b, TableView) and a.base is b.base
                 if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
-                    return a is b
+                    return False
                 try:
                     return bool(a == b)
                 except Exception:
                     return False
             f0 = fds[0]
+            X0 = f0.get("Input")
             fast = all(self._is_view_feed(f) for f in fds)
             for f in fds[1:] if fast else []:
-                same = (set(f) == set(f0) and all(same_value(f[k], f0[k]) for k in f if k not in ("intShape", "w")) and
-                        len(f["Input"].tf) == len(f0["Input"].tf) and f["Input"].integNum == f0["Input"].integNum and
-                        (f["Input"].extra is f0["Input"].extra or np.array_equal(f["Input"].extra, f0["Input"].extra)) and
-                        list(np.ravel(f.get("intShape"))) == list(np.ravel(f0.get("intShape"))) and
-                        np.array_equal(np.asarray(f.get("w")), np.asarray(f0.get("w"))))
+                X, w, w0 = f["Input"], f.get("w"), f0.get("w")
+                same = (len(f) == len(f0) and len(X.tf) == len(X0.tf) and X.integNum == X0.integNum and
+                        (X.extra is X0.extra or np.array_equal(X.extra, X0.extra)) and
+                        (w is w0 or np.array_equal(np.asarray(w), np.asarray(w0))) and
+                        all(k in f0 and same_value(v, f0[k]) for k, v in f.items() if k != "w"))
                 if not same:
                     fast = False
                     break
         if not fast:
             return [self.run([o.optMinimize, o.loss], fd)[1] for fd in feeds]
         tw = towers[0]
-        self._sync_feeds(feeds[0])
         idx = np.stack([np.asarray(f["Input"].tf, dtype=np.int32).ravel() for f in fds])
-        losses = tw.engine.train_batches(o.learning_rate, idx)
+        defer = o.defer_losses and hasattr(tw.engine, "train_batches_begin")
+        if not defer:
+            self._collect()
+        # the uploads of this call (extra inputs, BC/IC rows of the MOR batch) and its steps are enqueued behind the steps of
+        # the previous call, which is only collected afterwards: the GPU does not idle across the host work in between
+        self._sync_feeds(feeds[0], set_batch=False)
         tw._tokens["view_batch"] = _token(fds[-1]["Input"].tf)       # the engine is left on the last mini-batch
         self._last_sig = None
         o.step_count += len(feeds)
-        return [np.float32(v) for v in losses]
+        if not defer:
+            return [np.float32(v) for v in tw.engine.train_batches(o.learning_rate, idx)]
+        tw.engine.train_batches_begin(o.learning_rate, idx)
+        box = {}
+        pend = self.__dict__.setdefault("_pending", [])
+        pend.append((tw.engine, box))
+        while len(pend) > 1:
+            self._collect_one()
+
+        def fetch(i, box=box):
+            while "v" not in box:
+                self._collect_one()
+            return np.float32(box["v"][i])
+        return [Deferred(lambda i=i: fetch(i)) for i in range(len(feeds))]
+
+    def _collect_one(self):
+        """Wait for the OLDER run_batches call in flight and hand its losses to its Deferreds."""
+        eng, box = self._pending.pop(0)
+        try:
+            box["v"] = eng.train_batches_end()
+        except Exception:
+            box["v"] = [np.float32(np.nan)] * 4096
+            raise
+
+    def _collect(self):
+        """Wait for every mini-batch step enqueued by run_batches (any other use of the session starts here)."""
+        while getattr(self, "_pending", None):
+            self._collect_one()
 
     def _gradients(self):
         o = self._o
@@ -467,6 +550,7 @@ class Session:
     # -- the protocol
     def run(self, fetches, feed_dict=None):
         o = self._o
+        self._collect()
         single = not isinstance(fetches, (list, tuple))
         flist = [fetches] if single else list(fetches)
         names = [f.name if isinstance(f, Node) else None for f in flist]
@@ -624,6 +708,8 @@ class TFNN:
         self.batch_steps = True      # an epoch of index-list mini-batches goes to the engine in one call (Session.run_batches)
         # uniform-mesh / constant-coefficient tables are generated on the device instead of uploaded (vn_generate_table_f64)
         self.auto_generate = os.environ.get("VARNET_B200_AUTO_GENERATE", "1") != "0"
+        # run_batches returns its losses as Deferred numbers and leaves the steps running (VARNET_B200_DEFER_LOSSES=0: wait)
+        self.defer_losses = os.environ.get("VARNET_B200_DEFER_LOSSES", "1") != "0"
         # True: a feed array is uploaded only when it is replaced by a new object (in-place edits of a fed array are NOT
         # seen: replace the dict entry, as updateDictFields / shuffleTrainData do); False: every
         # sess.run re-uploads its feeds, like the reference's per-step feed (VarNetUtility.py:1044)

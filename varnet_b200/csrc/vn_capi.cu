@@ -180,6 +180,11 @@ __device__ __forceinline__ void advance_step(long long* step, double* corr) {
     const double tn = (double)(t + 1);     // bias correction of the NEXT step
     corr[0] = sqrt(1.0 - pow(0.999, tn)) / (1.0 - pow(0.9, tn));
 }
+// the last k entries of the loss ring in step order (the step counter already counts them)
+__global__ void vn_ring_gather_kernel(const float* __restrict__ ring, int ringSize, const long long* __restrict__ step, int k, float* __restrict__ out) {
+    const long long s0 = step[0] - k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = ring[(unsigned long long)(s0 + i) % (unsigned long long)ringSize];
+}
 __global__ void vn_advance_kernel(long long* step, double* corr, const int* err, float* lossRing, int ringSize, const float* lossPtr) {
     if (lossRing) lossRing[(unsigned long long)step[0] % (unsigned long long)ringSize] = *lossPtr;       // loss of the step being applied
     if (!(err && *err)) advance_step(step, corr);
@@ -485,7 +490,14 @@ struct vn_engine {
     // current table through a device index list (vn_select_table / vn_set_batch)
     std::vector<PointSet*> slots;
     PointSet* t = nullptr;
-    DevBuf batchIdx, extraX, batchSeq;
+    DevBuf batchIdx, extraX, batchSeq, lossOut;
+    // vn_train_batches_begin / _end: up to two calls in flight, each with its own pinned staging (index lists, the small
+    // uploads that precede the call: extra inputs, BC/IC rows) and pinned result slots
+    struct Pend {
+        void* seq = nullptr; size_t seqBytes = 0; float* loss = nullptr; int* err = nullptr; cudaEvent_t ev = nullptr; int k = 0;
+        unsigned char* aux = nullptr; size_t auxOff = 0;
+    } pend[2];
+    int pendNext = 0;            // slot of the next vn_train_batches_begin
     bool indexed = false;        // batch = index list into the table (else: the whole table in order)
     int nExtra = 0;              // trailing MLP inputs supplied as per-call constants (MOR parameters)
     // parameters + optimizer
@@ -710,12 +722,19 @@ extern "C" int vn_destroy(vn_engine* e) {
     if (e->evJoin) cudaEventDestroy(e->evJoin);
     for (cudaEvent_t ev : e->fedEvents) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pinEv[i]) cudaEventDestroy(e->pinEv[i]); }
+    for (auto& p : e->pend) {
+        if (p.seq) cudaFreeHost(p.seq);
+        if (p.loss) cudaFreeHost(p.loss);
+        if (p.err) cudaFreeHost(p.err);
+        if (p.aux) cudaFreeHost(p.aux);
+        if (p.ev) cudaEventDestroy(p.ev);
+    }
     delete e->pool;
     for (PointSet* t : e->slots) { t->cols.release(); t->integW.release(); t->detJ.release(); t->genBuf.release(); delete t; }
     DevBuf* bufs[] = {&e->theta, &e->m, &e->v, &e->gbuf, &e->wts, &e->stepbuf, &e->corrbuf, &e->batchIdx, &e->extraX,
                       &e->Iw, &e->R, &e->lossVec, &e->segSum, &e->bcols, &e->blabel, &e->cj, &e->partVar,
                       &e->partBic, &e->part32Var, &e->part32Bic, &e->stashVar, &e->stashBic, &e->lossPart, &e->stage, &e->evalCols, &e->evalOut,
-                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->tppSlot, &e->lossRing, &e->batchSeq};
+                      &e->tcWork, &e->tcAcc, &e->tcErr, &e->ticket, &e->tc64Img, &e->tc64Flat, &e->tppSlot, &e->lossRing, &e->batchSeq, &e->lossOut};
     for (DevBuf* b : bufs) b->release();
     delete e;
     return VN_OK;
@@ -1226,6 +1245,29 @@ extern "C" int vn_generate_table_f64(vn_engine* e, const double* coord, int64_t 
     return ensure_work(e);
 }
 
+// Host-to-device copy of a caller's (pageable) array that does not wait for the stream: the bytes are staged in the pinned
+// arena of the next vn_train_batches_begin call, so the uploads that precede a call (extra inputs, BC/IC rows of the next
+// MOR batch) queue up behind the steps of the call still running.  *staged = false: plain copy, the caller synchronises.
+static const size_t kAuxBytes = 4u << 20;
+static cudaError_t h2d_staged(vn_engine* e, void* dst, const void* src, size_t bytes, bool* staged) {
+    vn_engine::Pend& p = e->pend[e->pendNext];
+    *staged = false;
+    if (p.k == 0 && bytes <= kAuxBytes) {
+        if (!p.aux) { cudaError_t ce = cudaHostAlloc(reinterpret_cast<void**>(&p.aux), kAuxBytes, cudaHostAllocDefault); if (ce != cudaSuccess) return ce; }
+        size_t off = (p.auxOff + 15) & ~(size_t)15;
+        if (off + bytes > kAuxBytes) {                  // arena used up without a call in between: everything staged so far must land first
+            cudaError_t ce = cudaStreamSynchronize(e->stream);
+            if (ce != cudaSuccess) return ce;
+            off = 0;
+        }
+        memcpy(p.aux + off, src, bytes);
+        p.auxOff = off + bytes;
+        *staged = true;
+        return cudaMemcpyAsync(dst, p.aux + off, bytes, cudaMemcpyHostToDevice, e->stream);
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream);
+}
+
 extern "C" int vn_select_table(vn_engine* e, int32_t slot) {
     if (!e) return fail(VN_E_INVALID, "null engine");
     if (slot < 0 || slot >= VN_MAX_TABLES) return fail(VN_E_INVALID, "table slot must be in [0,%d)", VN_MAX_TABLES);
@@ -1280,8 +1322,9 @@ extern "C" int vn_set_extra_inputs(vn_engine* e, const float* vals, int32_t n) {
     CK(e->extraX.ensure(VN_MAX_INPDIM * sizeof(float)));
     if (n > 0) {
         if (!vals) return fail(VN_E_INVALID, "null argument");
-        CK(cudaMemcpyAsync(e->extraX.p, vals, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
+        bool staged = false;
+        CK(h2d_staged(e, e->extraX.p, vals, n * sizeof(float), &staged));
+        if (!staged) CK(cudaStreamSynchronize(e->stream));
     }
     e->nExtra = n;
     return VN_OK;
@@ -1301,7 +1344,13 @@ template <typename T>
 static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64_t bDof, double biDimVal) {
     if (!e || !bX || !bL) return fail(VN_E_INVALID, "biInput and biLabel are required");
     if (nbi < 1 || bDof < 0 || bDof > nbi) return fail(VN_E_INVALID, "need 0 <= bDof <= nbi and nbi >= 1");
-    drop_graph(e);
+    // the captured step graphs carry the row counts and biDimVal as kernel arguments: only new CONTENT of the same shape (a
+    // MOR parameter batch re-uploads its BC/IC rows before every epoch of mini-batches, VarNet.py:843-851) keeps them valid;
+    // reallocated buffers are caught by the graphs' allocation epoch
+    if ((unsigned int)nbi != e->nbi || (unsigned int)bDof != e->bDof || (float)biDimVal != e->biDimVal) {
+        cudaStreamSynchronize(e->stream);               // a replay may still be running (vn_train_batches_begin)
+        drop_graph(e);
+    }
     const vn_config& c = e->cfg;
     CK(cudaSetDevice(c.device));
     e->bstride = (nbi + kPad - 1) / kPad * kPad;
@@ -1313,15 +1362,16 @@ static int upload_bic(vn_engine* e, const T* bX, const T* bL, int64_t nbi, int64
     CK(e->stage.ensure((size_t)nbi * (c.inpDim + 1) * sizeof(T)));
     T* sX = e->stage.as<T>();
     T* sL = sX + nbi * c.inpDim;
-    CK(cudaMemcpyAsync(sX, bX, nbi * c.inpDim * sizeof(T), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(sL, bL, nbi * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    bool stagedX = false, stagedL = false;
+    CK(h2d_staged(e, sX, bX, nbi * c.inpDim * sizeof(T), &stagedX));
+    CK(h2d_staged(e, sL, bL, nbi * sizeof(T), &stagedL));
     vn_pack_kernel<T><<<(unsigned)((nbi + 255) / 256), 256, 0, e->stream>>>(
         sX, c.inpDim, nullptr, 0, nullptr, nullptr, nullptr, e->bcols.as<float>(), e->bstride, 0, nbi, 0, 0, -1, -1);
     CK(cudaGetLastError());
     vn_cast_kernel<T><<<(unsigned)((nbi + 255) / 256), 256, 0, e->stream>>>(sL, e->blabel.as<float>(), nbi);
     CK(cudaGetLastError());
     e->launches += 2;
-    CK(cudaStreamSynchronize(e->stream));
+    if (!(stagedX && stagedL)) CK(cudaStreamSynchronize(e->stream));      // the caller's arrays are read until then
     if (e->wclass == 256) { e->gridBic = 0; return VN_OK; }
     const long long tiles = e->bstride / e->gBicAdj.TP;
     e->gridBic = (int)std::min<long long>(tiles, e->numSMs);
@@ -1868,20 +1918,29 @@ extern "C" int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses) 
 // ([k][nb], host) is the index list of step i (what k x {vn_set_batch, vn_train_step} would do: ManageTrainData.optimIter,
 // VarNetUtility.py:1021-1047, one sess.run per mini-batch).  The k lists are uploaded once; between two replays of the captured
 // step graph only a device-to-device copy of the next list runs on the engine's stream.  The engine is left on the last batch.
-extern "C" int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k, float* losses) {
-    if (!e || !tf_index || !losses) return fail(VN_E_INVALID, "null argument");
+extern "C" int vn_train_batches_begin(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k) {
+    if (!e || !tf_index) return fail(VN_E_INVALID, "null argument");
     if (k < 1 || k > kLossRing) return fail(VN_E_INVALID, "k must be in [1, %d]", kLossRing);
     if (nb < 1) return fail(VN_E_INVALID, "a batch needs at least one test function");
+    vn_engine::Pend& p = e->pend[e->pendNext];
+    if (p.k) return fail(VN_E_STATE, "two vn_train_batches_begin calls are in flight: vn_train_batches_end must collect the older one first");
     if (!e->t->loaded) return fail(VN_E_STATE, "vn_upload_points must be called first to construct training tables!");
     if (e->t->integNum % 4 != 0) return fail(VN_E_UNSUPPORTED, "indexed batches need integNum to be a multiple of 4");
     CK(cudaSetDevice(e->cfg.device));
     const size_t one = (size_t)nb * sizeof(int32_t);
+    if (one * k > p.seqBytes) {                          // this slot's previous call was collected: nothing reads the old buffer
+        if (p.seq) { cudaFreeHost(p.seq); p.seq = nullptr; p.seqBytes = 0; }
+        CK(cudaHostAlloc(&p.seq, one * k, cudaHostAllocDefault));
+        p.seqBytes = one * k;
+    }
+    if (!p.loss) CK(cudaHostAlloc(reinterpret_cast<void**>(&p.loss), kLossRing * sizeof(float), cudaHostAllocDefault));
+    if (!p.err) CK(cudaHostAlloc(reinterpret_cast<void**>(&p.err), sizeof(int), cudaHostAllocDefault));
+    if (!p.ev) CK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
     CK(e->batchSeq.ensure(one * k));
     CK(e->batchIdx.ensure(one));
-    CK(cudaMemcpyAsync(e->batchSeq.p, tf_index, one * k, cudaMemcpyHostToDevice, e->stream));
-    long long step0 = 0;
-    CK(cudaMemcpyAsync(&step0, e->stepbuf.p, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(e->lossOut.ensure(kLossRing * sizeof(float)));
+    memcpy(p.seq, tf_index, one * k);
+    CK(cudaMemcpyAsync(e->batchSeq.p, p.seq, one * k, cudaMemcpyHostToDevice, e->stream));
     e->indexed = true; e->nb = (unsigned int)nb;
     int rc = ensure_work(e);
     if (rc) return rc;
@@ -1890,11 +1949,40 @@ extern "C" int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index,
         rc = train_step_enqueue(e, lr);
         if (rc) return rc;
     }
-    const int a = (int)(step0 % kLossRing), n1 = std::min((int)k, kLossRing - a);
-    CK(cudaMemcpyAsync(losses, e->lossRing.as<float>() + a, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-    if (k > n1) CK(cudaMemcpyAsync(losses + n1, e->lossRing.as<float>(), (size_t)(k - n1) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-    float sc[4];
-    return read_scalars(e, sc);
+    vn_ring_gather_kernel<<<1, 256, 0, e->stream>>>(e->lossRing.as<float>(), kLossRing, e->stepbuf.as<long long>(), k, e->lossOut.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p.loss, e->lossOut.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    *p.err = 0;
+    if (e->wclass == 256 || e->tc64) CK(cudaMemcpyAsync(p.err, e->tcErr.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(p.ev, e->stream));
+    p.k = k;
+    e->pendNext ^= 1;
+    return VN_OK;
+}
+// collects the OLDER of the calls in flight
+extern "C" int vn_train_batches_end(vn_engine* e, float* losses, int32_t k) {
+    if (!e || !losses) return fail(VN_E_INVALID, "null argument");
+    const int slot = e->pend[e->pendNext].k ? e->pendNext : (e->pendNext ^ 1);
+    vn_engine::Pend& p = e->pend[slot];
+    if (!p.k) return fail(VN_E_STATE, "no vn_train_batches_begin call is in flight");
+    if (k != p.k) return fail(VN_E_INVALID, "the call in flight has %d mini-batches", p.k);
+    CK(cudaSetDevice(e->cfg.device));
+    p.k = 0;
+    CK(cudaEventSynchronize(p.ev));
+    p.auxOff = 0;                                        // everything staged for this call has landed
+    memcpy(losses, p.loss, (size_t)k * sizeof(float));
+    if (*p.err) {
+        cudaMemsetAsync(e->tcErr.p, 0, sizeof(int), e->stream);       // report once; the next call starts clean
+        return fail(VN_E_CUDA, "tensor-core pipeline: an mbarrier wait expired (results of this call are invalid)");
+    }
+    return VN_OK;
+}
+extern "C" int vn_train_batches(vn_engine* e, float lr, const int32_t* tf_index, int64_t nb, int32_t k, float* losses) {
+    if (!e || !losses) return fail(VN_E_INVALID, "null argument");
+    if (e->pend[0].k || e->pend[1].k) return fail(VN_E_STATE, "vn_train_batches_end must collect the calls in flight first");
+    int rc = vn_train_batches_begin(e, lr, tf_index, nb, k);
+    if (rc) return rc;
+    return vn_train_batches_end(e, losses, k);
 }
 
 // ------------------------------------------------------------------ evaluation

@@ -31,6 +31,14 @@ constexpr int OFF_WST = 0;                         // two weight stages
 constexpr int OFF_GA = 2 * WIMG_BYTES;             // [a_hi^T ; a_lo^T]     128 rows x 128 points
 constexpr int OFF_GB = OFF_GA + G_BYTES;           // [zbar_hi^T ; zbar_lo^T]
 constexpr int OFF_PAR = OFF_GB + G_BYTES;
+// MN-major weight-gradient operands (GWM > 0): row = point (128 B = 32 neurons), LayoutType::SWIZZLE_128B_BASE32B
+// (Swizzle<2,5,2>: the 32-byte chunk index of a row is XORed with point & 3; k atoms of 4 points = 512 B), four MN groups
+// of 32 rows of the 128-row operand (hi 0..31, hi 32..63, lo 0..31, lo 32..63), 16 KB each.  This is the only canonical
+// layout in which tcgen05.mma kind::tf32 accepts MN-major operands (scripts/micro/tc_probe3.cu; CUTLASS sm100_common.inl:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout").
+constexpr uint32_t MN_GROUP = 16384, MN_ATOM = 512, MN_KSTEP = 1024;
+constexpr int OFF_MGA = 2 * WIMG_BYTES;            // 64 KB
+constexpr int OFF_MGB = OFF_MGA + 4 * MN_GROUP;    // 64 KB
 constexpr int PAR_FLOATS = 1152 + NH * 384 + 640;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128]
 constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
@@ -64,6 +72,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
 }
 // D = F32, A = B = TF32, K-major, M = 128
 template <int N> struct IDesc { static constexpr uint32_t v = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((MN_GROUP >> 4) & 0x3FFF) << 16;        // leading byte offset: between MN groups of 32 elements
+    d |= (uint64_t)((MN_ATOM >> 4) & 0x3FFF) << 32;         // stride byte offset: between k atoms of 4 points
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
+    return d;
+}
+constexpr uint32_t IDESC_GW_MN = IDesc<128>::v | (1u << 15) | (1u << 16);     // A and B MN-major
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t aT, uint64_t db, uint32_t id, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
@@ -204,6 +222,35 @@ __device__ __forceinline__ void put_transposed(unsigned char* G, int p, int c0, 
         *reinterpret_cast<float*>(base + (8 + (jj >> 3)) * SBO + (jj & 7) * 16) = v[jj] - hi;
     }
 }
+// MN-major store of the same operand: the thread's 16 neurons of point p are 64 contiguous bytes of row p (two 32-byte
+// chunks, swizzled with p & 3); hi image in MN group h >> 1, lo image two groups further.  With 16-byte stores the lanes p
+// and p + 4 of a quarter warp would hit the same bank group (their rows are 512 B apart and carry the same swizzle), so
+// for GWM == 2 the lanes with p & 4 hold their register quads pairwise exchanged (`w` quad u = neuron quad u ^ 1: `v` is
+// exchanged in place by quad_swap, the stash rows are loaded that way) and store quad slot u to the other half of its
+// chunk: every store instruction then covers 8 different 16-byte bank groups per quarter warp.
+__device__ __forceinline__ void quad_swap(float (&v)[CPT], bool sw) {
+#pragma unroll
+    for (int cc = 0; cc < CPT / 8; ++cc)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = v[8 * cc + i], b = v[8 * cc + 4 + i];
+            v[8 * cc + i] = sw ? b : a;
+            v[8 * cc + 4 + i] = sw ? a : b;
+        }
+}
+__device__ __forceinline__ void put_mn(unsigned char* G, int p, int h, const float (&w)[CPT], bool sw) {
+    unsigned char* row = G + (h >> 1) * MN_GROUP + p * 128;
+    const uint32_t x = (uint32_t)(p & 3) << 5, o = 64u * (h & 1), f = sw ? 16u : 0u;
+#pragma unroll
+    for (int u = 0; u < CPT / 4; ++u) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hi[i] = tf32_rn(w[4 * u + i]); lo[i] = w[4 * u + i] - hi[i]; }
+        unsigned char* c = row + (((o + 32u * (u >> 1)) ^ x) + ((16u * (u & 1)) ^ f));
+        *reinterpret_cast<float4*>(c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(c + 2 * MN_GROUP) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
 // stash: [(l*S + s)][neuron/4][point][4].  The 148 per-CTA slabs (57 MB at 4x64) are rewritten by every tile: they are
 // written and read with an L2 evict_last policy (and the streamed point table with evict_first) so that they stay in the
 // 126 MB L2 instead of being written back to HBM tile after tile.
@@ -229,6 +276,15 @@ __device__ __forceinline__ void stash_get(const float* st, int slab, int p, int 
     for (int u = 0; u < CPT / 4; ++u)
         asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v[4 * u]), "=f"(v[4 * u + 1]), "=f"(v[4 * u + 2]),
                      "=f"(v[4 * u + 3]) : "l"(b + u * TP), "l"(pol) : "memory");
+}
+// the same rows with the quads pairwise exchanged (register quad u <- neuron quad u ^ 1) where `sw` (put_mn)
+__device__ __forceinline__ void stash_get_sw(const float* st, int slab, int p, int c0, float (&v)[CPT], uint64_t pol, bool sw) {
+    const float4* b = reinterpret_cast<const float4*>(st) + ((size_t)slab * 16 + (c0 >> 2)) * TP + p;
+    const int d = sw ? TP : 0;
+#pragma unroll
+    for (int u = 0; u < CPT / 4; ++u)
+        asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v[4 * u]), "=f"(v[4 * u + 1]), "=f"(v[4 * u + 2]),
+                     "=f"(v[4 * u + 3]) : "l"(b + u * TP + ((u & 1) ? -d : d)), "l"(pol) : "memory");
 }
 // sum over the 32 lanes of v[c], c < CPT: the lanes with index >> COLSUM_SHIFT == c return column c
 __device__ __forceinline__ float warp_colsum(float (&v)[CPT], int lane) {
@@ -265,7 +321,7 @@ constexpr uint32_t COL_PARK = 128;      //          + 64 s: abar_{l-1,s}
 constexpr uint32_t COL_SMALL = 320;     //          hi*lo + lo*hi of the running layer GEMM
 constexpr uint32_t COL_GW = 384;        //          weight-gradient accumulator (128 columns)
 
-template <int S, int ACT>
+template <int S, int ACT, int GWM>
 __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__ Tc64Args K) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TileArgs& A = K.t;
@@ -275,6 +331,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     const int q = warp & 3, h = warp >> 2;
     const int p = 32 * q + lane;                    // point of the tile == TMEM lane
     const int c0 = CPT * h;                         // first of this thread's CPT neurons
+    const bool sw = GWM == 2 && (p & 4);            // this lane keeps the weight-gradient operands quad-exchanged (put_mn)
 
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     float* W0s = par;                               // [8][64]
@@ -288,8 +345,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     const uint32_t bar = smem_u32(smem + OFF_BAR);            // forward GEMMs / adjoint layer GEMM
     const uint32_t barGw = bar + 8;                             // weight-gradient GEMM
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
-    unsigned char* GA = smem + OFF_GA;
-    unsigned char* GB = smem + OFF_GB;
+    unsigned char* GA = smem + (GWM ? OFF_MGA : OFF_GA);
+    unsigned char* GB = smem + (GWM ? OFF_MGB : OFF_GB);
 
     if (*reinterpret_cast<volatile int*>(K.err)) return;
     for (int i = tid; i < PAR_FLOATS; i += NT) par[i] = 0.f;
@@ -394,8 +451,10 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             tc_fence_after();
             const uint32_t ga = smem_u32(GA), gb = smem_u32(GB);
 #pragma unroll
-            for (int kb = 0; kb < 16; ++kb)
-                mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : gwAcc);
+            for (int kb = 0; kb < 16; ++kb) {
+                if (GWM) mma_ss(tmem + COL_GW, make_desc_mn(ga + kb * MN_KSTEP), make_desc_mn(gb + kb * MN_KSTEP), IDESC_GW_MN, kb ? 1u : gwAcc);
+                else mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : gwAcc);
+            }
             if (gwLast) mma_commit(barGw);              // drained after the last stream only; earlier streams are covered by `bar`
             const uint32_t aHi = tmem + COL_OP, aLo = aHi + 64, dMain = tmem + COL_PARK + 64 * s, dSmall = tmem + COL_SMALL;
 #pragma unroll
@@ -610,7 +669,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
             stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
             stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
-            stash_get(stash, (L - 2) * S + 1, p, c0, apre, polLast);
+            stash_get_sw(stash, (L - 2) * S + 1, p, c0, apre, polLast, sw);
             for (int l = L - 1; l >= 0; --l) {
                 uint32_t wst = 0;
 #pragma unroll
@@ -638,11 +697,20 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     if (l >= 1) {
                         if (si == 0) wst = acquire_image();
                         put_operand(tq + COL_OP, c0, v);
-                        put_transposed(GB, p, c0, v);
-                        put_transposed(GA, p, c0, apre);
+                        if (GWM) {
+                            put_mn(GA, p, h, apre, sw);
+                            if (GWM == 2) {
+                                quad_swap(v, sw);
+                                put_mn(GB, p, h, v, sw);
+                                if (s == 0) quad_swap(v, sw);
+                            } else {
+                                put_mn(GB, p, h, v, false);
+                            }
+                        } else { put_transposed(GB, p, c0, v); put_transposed(GA, p, c0, apre); }
                         if (s == 0) {
 #pragma unroll
                             for (int jj = 0; jj < CPT; ++jj) a0[jj] = apre[jj];                  // a_{l-1,0}: the value activations of the next layer down
+                            if (GWM == 2) quad_swap(a0, sw);                                     // apre holds it quad-exchanged
                             const float r = warp_colsum(v, lane);                                // g(b_l) = sum_p zbar_{l,0}
                             vec_add(l, r, first);
                         }
@@ -651,7 +719,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         // stash rows of the next step, in flight while the tensor core runs
                         if (ln >= 0) {
                             if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre, polLast);
-                            if (ln >= 1) stash_get(stash, (ln - 1) * S + sn, p, c0, apre, polLast);
+                            if (ln >= 1) stash_get_sw(stash, (ln - 1) * S + sn, p, c0, apre, polLast, sw);
                         }
                         if (si == S - 1) {
                             wait_gw();
@@ -1325,12 +1393,30 @@ __global__ void tc64_reduce_kernel(NetDesc net, const double* __restrict__ slab,
     if (lane == 0) flat[idx] = s;
 }
 
+// weight-gradient operand layout of the default schedule (VARNET_B200_TC64_GW): 0 (default) = K-major operands written by
+// transposing 4-byte stores; 1 = MN-major operands (SWIZZLE_128B_BASE32B), plain 16-byte stores; 2 = MN-major, quad-exchanged
+// lanes (bank-conflict-free 16-byte stores).  All three are bit-identical; measured on 1/4 of cfg 4 (same box, ABAB,
+// gpurun_out/r2be_ab.log): 38.4 / 42.2 / 40.4 ms.  The MN-major MMAs run at the full rate (scripts/micro/umma_rate.cu: 64.0 against
+// 63.5 cycles per 128x128x8), but a thread owns a (point, 16 neurons) strip, so its 16-byte stores of one instruction hit only 4
+// of the 8 bank groups (mode 1: 2-way conflicts, 2x the store wavefronts) unless half of the lanes exchange register quads first
+// (mode 2: +7 % instructions); the scalar transposing stores have neither problem and the same wavefront count.
+int gw_mode() {
+    static const int v = [] { const char* e = getenv("VARNET_B200_TC64_GW"); const int m = e ? atoi(e) : 0; return (m < 0 || m > 2) ? 0 : m; }();
+    return v;
+}
 template <int S, int ACT> cudaError_t launch_t(const Tc64Args& k, int grid, size_t smem, cudaStream_t st) {
-    tc64_var_kernel<S, ACT><<<grid, NT, smem, st>>>(k);
+    switch (gw_mode()) {
+        case 1: tc64_var_kernel<S, ACT, 1><<<grid, NT, smem, st>>>(k); break;
+        case 2: tc64_var_kernel<S, ACT, 2><<<grid, NT, smem, st>>>(k); break;
+        default: tc64_var_kernel<S, ACT, 0><<<grid, NT, smem, st>>>(k); break;
+    }
     return cudaGetLastError();
 }
 template <int S, int ACT> cudaError_t prepare_t(size_t smem) {
-    return cudaFuncSetAttribute(tc64_var_kernel<S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
 }
 
 }  // namespace

@@ -411,7 +411,9 @@ class ManageTrainData:
             raise Exception('\'trainDicts\' must be called first to construct training dictionaries!')
         total = 0
         if len(self.optimFeedicts) > 1 and hasattr(tfData.sess, "run_batches") and getattr(tfData, "batch_steps", True):
-            # same steps in the same order; index-list mini-batches of one resident table go to the engine in one call
+            # same steps in the same order; index-list mini-batches of one resident table go to the engine in one call.
+            # The losses may still be on their way (backend.Deferred): the sum is then a Deferred too, evaluated with
+            # the very same additions on first use, so the caller's next trainData() overlaps the running steps
             for val in tfData.sess.run_batches(self.optimFeedicts):
                 total += val
             return total

@@ -559,6 +559,8 @@ class VarNet:
                 for batch in range(fixData.MORbatchNum):
                     tData = self.trainData(batch, MORdiscArg, tData)
                     current_loss += tData.optimIter(tf)
+                if hasattr(current_loss, "value"):                      # backend.Deferred: the epoch's steps are all enqueued
+                    current_loss = current_loss.value()
                 losses = [current_loss]
             epoch_time += time.perf_counter() - t0
             for current_loss in losses:
