@@ -180,6 +180,33 @@ def test_shared_memory_operand_pipeline_matches_oracle(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_mn_major_weight_gradient_tiles_match_the_k_major_ones(monkeypatch):
+    """VARNET_B200_TC_GW=mn: tc_gw_kernel stores the quad-major 16-byte units as they are into MN-major tiles
+    (LayoutType::SWIZZLE_128B_BASE32B) instead of transposing them with scalar stores.  The MMAs contract the same numbers in
+    the same order: the result must meet the oracle bar and the weight gradients agree with the default tiles to 1e-6."""
+    rng = np.random.RandomState(8)
+    dim, inpDim, lw = 2, 3, [200, 256, 96]
+    feed = synth_feed(rng, dim, inpDim, 90, 64, 400, 250, True, True)
+    theta = go.glorot_init(inpDim, lw, seed=4)
+    kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=True, integWflag=False))
+    ref = go.loss_and_grad(theta, feed, **kw)
+    outs = {}
+    for mode in ("k", "mn"):
+        monkeypatch.setenv("VARNET_B200_TC_GW", mode)
+        eng = make_engine(feed, theta=theta, **kw)
+        try:
+            outs[mode] = eng.loss_grad()
+            check_against_oracle(eng, ref, feed, inpDim, lw, True)
+        finally:
+            eng.close()
+    assert float(outs["mn"]["loss"]) == float(outs["k"]["loss"])
+    for name, sl in layer_slices(inpDim, lw)[:-1]:
+        # the bias gradients ride on the loaders' FP32 partial sums, whose order follows the loader mapping: the oracle bar
+        bar = 1e-6 if name.startswith("kernel") else TOL
+        assert rel_inf(outs["mn"]["grad"][sl], outs["k"]["grad"][sl]) <= bar, name
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("scale,act", [(4.0, "tanh"), (6.0, "sigmoid"), (0.05, "tanh")])
 def test_split_product_is_robust_to_weight_scale(scale, act):
     """Saturated activations (large weights) and tiny pre-activations (small weights): the hi/lo split keeps FP32-level

@@ -133,3 +133,31 @@ def test_tile64_training_trajectory_and_minibatch_index_list():
             assert rel_inf(out["grad"][sl], ref["grad"][sl]) <= TOL, name
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_mn_major_weight_gradient_operands_are_bit_identical(monkeypatch):
+    """VARNET_B200_TC64_GW = 1 / 2: the weight-gradient GEMM reads MN-major operands (LayoutType::SWIZZLE_128B_BASE32B, the one
+    canonical layout in which kind::tf32 takes them: scripts/micro/tc_probe3.cu) written with 16-byte stores instead of the
+    transposing scalar stores.  Same MMAs in the same order on the same numbers: loss and gradient must not change by a bit
+    (several tiles per CTA, ragged last tile, S = 3 and S = 2)."""
+    for dim, inpDim, nb in ((2, 3, 148 * 2 * 3 + 5), (1, 2, 700)):
+        rng = np.random.RandomState(17 + dim)
+        lw = [64, 48, 64]
+        feed = synth_feed(rng, dim, inpDim, nb, 64, 200, 120)
+        theta = go.glorot_init(inpDim, lw, seed=3)
+        kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
+        ref = go.loss_and_grad(theta, feed, **kw)
+        outs = []
+        for mode in ("0", "1", "2"):
+            monkeypatch.setenv("VARNET_B200_TC64_GW", mode)
+            eng = make_engine(feed, theta=theta, **kw)
+            try:
+                assert "tile64" in eng.kernel_info()
+                outs.append(eng.loss_grad())
+                if mode == "2":
+                    check_against_oracle(eng, ref, feed, inpDim, lw, True)
+            finally:
+                eng.close()
+        for o in outs[1:]:
+            assert float(o["loss"]) == float(outs[0]["loss"]) and np.array_equal(o["grad"], outs[0]["grad"])

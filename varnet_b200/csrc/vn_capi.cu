@@ -1028,10 +1028,20 @@ static int upload_table(vn_engine* e, const T* X, int nx, const T* G, const T* s
         // pageable caller arrays (what NumPy hands over) are staged through pinned bounce buffers by a few host threads
         static const bool stagerOff = [] { const char* v = getenv("VARNET_B200_STAGE_THREADS"); return v && atoi(v) <= 0; }();
         const bool pageable = !stagerOff && is_pageable(X) && is_pageable(G);
+        // the first kernel launch of the step waits for the first chunk: chunks 0, 1, 2 are 1/4, 1/4 and 1/2 of the regular size
+        // (1 M, 1 M, 2 M rows, then 4 M each), so the kernels start after 24 MB instead of 96 MB have crossed the bus — what
+        // the end-to-end step loses against the resident one, and most of it when the ranks of a multi-GPU job feed 1/N each
+        const long long q = chunk / 4;
+        const bool ramp = chunk == kChunk && q % TP == 0 && q / TP >= e->numSMs;
         plan->produce = [=](size_t k, FedPlan::Sub* out) -> int {
-            const long long off = (long long)k * chunk;
+            long long off = (long long)k * chunk, len = chunk;
+            if (ramp) {
+                if (k < 2) { off = (long long)k * q; len = q; }
+                else if (k == 2) { off = 2 * q; len = 2 * q; }
+                else off = (long long)(k - 2) * chunk;
+            }
             if (off >= P) return 0;
-            const long long n = std::min(chunk, P - off);
+            const long long n = std::min(len, P - off);
             T* sX = e->stage.as<T>();
             T* sG = sX + n * nx;
             T* sT = sG + n * c.dim;

@@ -56,6 +56,28 @@ __device__ __forceinline__ void mma_tf32(uint32_t dTmem, uint64_t da, uint64_t d
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(dTmem), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
 }
+// MN-major operands of the weight-gradient GEMM (rows of the operand = points = K): LayoutType::SWIZZLE_128B_BASE32B, the only
+// canonical layout in which kind::tf32 takes MN-major shared-memory operands (scripts/micro/tc_probe3.cu).  One tile =
+// 128 operand rows (neurons) x KC points: four MN groups of 32 neurons, each KC rows of 128 B (one point, 32 neurons), the
+// 32-byte chunk index of a row XORed with point & 3; k atoms of 4 points (512 B).
+constexpr uint32_t MN_ROW = 128, MN_ATOM = 4 * MN_ROW, MN_GROUP = KC * MN_ROW, MN_TILE = 4 * MN_GROUP, MN_KSTEP = 8 * MN_ROW;
+constexpr int MN_STAGE_BYTES = 4 * MN_TILE;            // A hi, A lo, B hi, B lo
+constexpr int MN_BAR_OFF = NST * MN_STAGE_BYTES;
+constexpr int MN_SMEM_BYTES = MN_BAR_OFF + 128;
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((MN_GROUP >> 4) & 0x3FFF) << 16;        // leading byte offset: between MN groups
+    d |= (uint64_t)((MN_ATOM >> 4) & 0x3FFF) << 32;         // stride byte offset: between k atoms
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
+    return d;
+}
+__device__ __forceinline__ void mma_tf32_mn(uint32_t dTmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dTmem), "l"(da), "l"(db), "r"(IDESC | (1u << 15) | (1u << 16)), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -126,7 +148,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tmem) {
 //            each of the four neurons of a unit is written as a 4-byte scalar into its (neuron, 4 points) K unit —
 //            bank = lane thanks to the 16-byte pad on TILE_LBO, so these stores are conflict free too.
 // No second (neuron-major) copy of the activations exists.
-enum { LAY_QM = 0, LAY_QT = 1 };
+//   LAY_MN — weight-gradient GEMM with MN-major operands: the 16-byte quad-major units go to shared memory as they are (two
+//            16-byte stores per unit: hi and lo image) — no transposition.  A quarter warp covers 4 points x the 2 quads of
+//            one 32-byte chunk, i.e. 8 different 16-byte bank groups (the swizzle separates the 4 points), and its global
+//            request is two runs of 64 contiguous bytes.
+enum { LAY_QM = 0, LAY_QT = 1, LAY_MN = 2 };
 struct Opnd { const float* p; size_t ld; };     // p = array + (first row / 4 for QT, first row for QM) term, ld = points of the array
 struct TileRegs { float4 v[TM * (KC / 4) / NTHR]; };
 
@@ -139,7 +165,16 @@ __device__ __forceinline__ void tile_load(const Opnd& o, int k0, TileRegs& r, in
             const int u = i * NTHR + tid, row = u % TM, k4 = u / TM;
             r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)(k0 / 4 + k4) * o.ld + row) * 4));
         }
-    } else {
+    } else if (LAY == LAY_MN) {
+        static_assert(U == 4 && KC == 32, "warp = two neuron quads x 16 points per request");
+        const int warp = tid >> 5, lane = tid & 31;
+        const int pt = 4 * (lane >> 3) + (lane & 3), qb = (lane >> 2) & 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = 4 * warp + i, quad = 2 * (m >> 1) + qb, point = 16 * (m & 1) + pt;
+            r.v[i] = __ldg(reinterpret_cast<const float4*>(o.p + ((size_t)quad * o.ld + k0 + point) * 4));
+        }
+} else {
         static_assert(U == 4 && KC == 32, "warp = four neuron quads x 32 points");
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
@@ -164,7 +199,16 @@ __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned cha
             const int u = i * NTHR + tid, row = u % TM, k4 = u / TM;
             store_split(r.v[i], hiTile, loTile, k4 * TILE_LBO + row * 16);
         }
-    } else {
+    } else if (LAY == LAY_MN) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int pt = 4 * (lane >> 3) + (lane & 3), qb = (lane >> 2) & 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = 4 * warp + i, quad = 2 * (m >> 1) + qb, point = 16 * (m & 1) + pt;
+            const uint32_t off = (quad >> 3) * MN_GROUP + point * MN_ROW + (((uint32_t)((quad & 7) >> 1) ^ (uint32_t)(point & 3)) << 5) + (quad & 1) * 16;
+            store_split(r.v[i], hiTile, loTile, off);
+        }
+} else {
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -184,6 +228,20 @@ __device__ __forceinline__ void tile_store_split(const TileRegs& r, unsigned cha
 // the two small products lo*hi, hi*lo go to their own column set (magnitude 2^-11: their truncation is
 // harmless) and hi*hi of K block kb goes to the main set chosen by `mainSet(kb, fresh)`; the sets are summed
 // in FP32 (round to nearest) by the epilogue.
+template <class F>
+__device__ __forceinline__ void issue_chunk_mn(uint32_t tmem, uint32_t stageAddr, bool firstChunk, F&& mainSet) {
+    const uint32_t aHi = stageAddr, aLo = stageAddr + MN_TILE, bHi = stageAddr + 2 * MN_TILE, bLo = stageAddr + 3 * MN_TILE;
+#pragma unroll
+    for (int kb = 0; kb < KC / 8; ++kb) {
+        const uint64_t dAh = make_desc_mn(aHi + kb * MN_KSTEP), dAl = make_desc_mn(aLo + kb * MN_KSTEP);
+        const uint64_t dBh = make_desc_mn(bHi + kb * MN_KSTEP), dBl = make_desc_mn(bLo + kb * MN_KSTEP);
+        mma_tf32_mn(tmem + 3 * TN, dAl, dBh, (firstChunk && kb == 0) ? 0u : 1u);
+        mma_tf32_mn(tmem + 3 * TN, dAh, dBl, 1u);
+        bool fresh = false;
+        const int set = mainSet(kb, fresh);
+        mma_tf32_mn(tmem + set * TN, dAh, dBh, fresh ? 0u : 1u);
+    }
+}
 template <class F>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t stageAddr, bool firstChunk, F&& mainSet) {
     const uint32_t aHi = stageAddr, aLo = stageAddr + TILE_BYTES, bHi = stageAddr + 2 * TILE_BYTES, bLo = stageAddr + 3 * TILE_BYTES;
@@ -228,10 +286,11 @@ template <int LAY, class F>
 __device__ __forceinline__ void loader_step(unsigned char* smem, const Bars& bars, int it, int nIt, TileRegs& ra, TileRegs& rb,
                                             F&& src, int tid, bool& ok) {
     const int b = it % NST;
-    unsigned char* stage = smem + b * STAGE_BYTES;
+    constexpr int stageBytes = LAY == LAY_MN ? MN_STAGE_BYTES : STAGE_BYTES, tileBytes = LAY == LAY_MN ? (int)MN_TILE : TILE_BYTES;
+    unsigned char* stage = smem + b * stageBytes;
     if (it >= NST && ok) ok = mbar_wait(bars.empty + 8 * b, (uint32_t)((it / NST) - 1) & 1u);
-    tile_store_split<LAY>(ra, stage, stage + TILE_BYTES, tid);
-    tile_store_split<LAY>(rb, stage + 2 * TILE_BYTES, stage + 3 * TILE_BYTES, tid);
+    tile_store_split<LAY>(ra, stage, stage + tileBytes, tid);
+    tile_store_split<LAY>(rb, stage + 2 * tileBytes, stage + 3 * tileBytes, tid);
     if (it + 2 < nIt) {
         const ChunkSrc c = src(it + 2);
         tile_load<LAY>(c.a, c.k0, ra, tid);
@@ -241,14 +300,15 @@ __device__ __forceinline__ void loader_step(unsigned char* smem, const Bars& bar
     mbar_arrive(bars.full + 8 * b);
 }
 // MMA warp (one elected lane): consume the stages in order
-template <class F>
+template <bool MN = false, class F>
 __device__ __forceinline__ bool mma_warp_loop(unsigned char* smem, const Bars& bars, uint32_t tmem, int nIt, F&& mainSetOf) {
     bool ok = true;
     for (int it = 0; it < nIt; ++it) {
         const int b = it % NST;
         if (ok) ok = mbar_wait(bars.full + 8 * b, (uint32_t)(it / NST) & 1u);
         tc_fence_after();
-        issue_chunk(tmem, smem_u32(smem + b * STAGE_BYTES), it == 0, [&](int kb, bool& fresh) { return mainSetOf(it, kb, fresh); });
+        if (MN) issue_chunk_mn(tmem, smem_u32(smem + b * MN_STAGE_BYTES), it == 0, [&](int kb, bool& fresh) { return mainSetOf(it, kb, fresh); });
+        else issue_chunk(tmem, smem_u32(smem + b * STAGE_BYTES), it == 0, [&](int kb, bool& fresh) { return mainSetOf(it, kb, fresh); });
         mma_commit(bars.empty + 8 * b);
     }
     mma_commit(bars.done);
@@ -480,7 +540,9 @@ struct GwArgs {
 // long completed, so no truncating chain is longer than GW_EPOCH * KC / 8 MMAs and the pipeline never stalls.
 constexpr int GW_EPOCH = 4;
 
+template <bool MN>
 __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
+    constexpr int LAY = MN ? LAY_MN : LAY_QT;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (*reinterpret_cast<volatile int*>(a.err)) return;
@@ -492,11 +554,11 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
     const int chunks = (int)((pEnd - pBeg) / KC);
     const int nIt = a.S * chunks;
     Bars bars;
-    const uint32_t tmem = pipe_setup(smem, tid, warp, bars);
+    const uint32_t tmem = pipe_setup(smem, tid, warp, bars, MN ? MN_BAR_OFF : BAR_OFF);
 
     if (warp == NTHR / 32) {
         if (lane == 0) {
-            const bool ok = mma_warp_loop(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
+            const bool ok = mma_warp_loop<MN>(smem, bars, tmem, nIt, [&](int it, int kb, bool& fresh) {
                 fresh = (it % GW_EPOCH == 0) && kb == 0;
                 return (it / GW_EPOCH) % 3;
             });
@@ -522,7 +584,10 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
         auto biasAcc = [&](int it, const TileRegs& r) {
             if (doBias && it < chunks) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { bs[4 * i] += r.v[i].x; bs[4 * i + 1] += r.v[i].y; bs[4 * i + 2] += r.v[i].z; bs[4 * i + 3] += r.v[i].w; }
+                for (int i = 0; i < 4; ++i) {
+                    const int o = MN ? 4 * (i >> 1) : 4 * i;       // LAY_MN: units 0, 1 are one quad (4 warp + qb), units 2, 3 the quad two further
+                    bs[o] += r.v[i].x; bs[o + 1] += r.v[i].y; bs[o + 2] += r.v[i].z; bs[o + 3] += r.v[i].w;
+                }
             }
         };
         auto drain = [&](int set) {
@@ -536,8 +601,8 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
             }
         };
         TileRegs ra[2], rb[2];
-        { const ChunkSrc c = src(0); tile_load<LAY_QT>(c.a, c.k0, ra[0], tid); tile_load<LAY_QT>(c.b, c.k0, rb[0], tid); }
-        if (nIt > 1) { const ChunkSrc c = src(1); tile_load<LAY_QT>(c.a, c.k0, ra[1], tid); tile_load<LAY_QT>(c.b, c.k0, rb[1], tid); }
+        { const ChunkSrc c = src(0); tile_load<LAY>(c.a, c.k0, ra[0], tid); tile_load<LAY>(c.b, c.k0, rb[0], tid); }
+        if (nIt > 1) { const ChunkSrc c = src(1); tile_load<LAY>(c.a, c.k0, ra[1], tid); tile_load<LAY>(c.b, c.k0, rb[1], tid); }
         bool ok = true;
 #pragma unroll 1
         for (int it0 = 0; it0 < nIt; it0 += 2) {
@@ -553,7 +618,7 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
                         tc_fence_before();          // the set is overwritten by epoch e+1, whose first stage this thread publishes later
                     }
                     biasAcc(it, rb[h]);
-                    loader_step<LAY_QT>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
+                    loader_step<LAY>(smem, bars, it, nIt, ra[h], rb[h], src, tid, ok);
                 }
             }
         }
@@ -564,7 +629,20 @@ __global__ void __launch_bounds__(NTHR_ALL, 1) tc_gw_kernel(const GwArgs a) {
         for (int e = max(0, nEp - 2); e < nEp; ++e) drain(e % 3);           // the last two epochs were not drained in the loop
         drain(3);                                                            // small terms
 
-        if (doBias) {
+        if (doBias && MN) {
+            // LAY_MN loader mapping: lane bit 2 selects the quad of a pair (quads 4 warp + qb and 4 warp + 2 + qb); the other lane
+            // bits run over points
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t = bs[c];
+                t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+                const int qb = (lane >> 2) & 1;
+                const int j = jt * TN + 4 * (4 * warp + 2 * (c >> 2) + qb) + (c & 3);
+                if ((lane & 27) == 0 && j < a.wo) atomicAdd(a.gb + j, (double)t);
+            }
+        }
+        if (doBias && !MN) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 float t = bs[c];
@@ -1048,6 +1126,15 @@ template <int S> cudaError_t launch_top(int act, const TopArgs& a, dim3 grid, cu
 
 unsigned int gcd_u(unsigned int a, unsigned int b) { while (b) { const unsigned int t = a % b; a = b; b = t; } return a; }
 
+// weight-gradient GEMM operands: round 1's K-major tiles written by transposing 4-byte stores (default), or MN-major tiles
+// (VARNET_B200_TC_GW=mn: the quad-major 16-byte units stored as they are, a quarter of the store instructions, no bank
+// conflicts).  Same-box A/B (scripts/ab_wide.py, gpurun_out/r2bl_ab.log): 4x256 237.0 / 237.3 ms K-major against 238.5 / 239.0 ms
+// MN-major, 4x128 88.3 / 87.8 against 87.8 / 88.7 ms, identical loss: the kernel is bound by the delivery of its operands
+// from L2 (32 KB per 12 MMAs), not by the loader's stores.
+bool gw_mn() {
+    const char* e = getenv("VARNET_B200_TC_GW");           // read per launch: a test switches it inside one process
+    return e && e[0] == 'm';
+}
 }  // namespace
 
 #define TCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
@@ -1062,7 +1149,7 @@ bool vn_tc_geometry(const NetDesc& net, int S, int numSMs, TcGeom* g) {
     g->capPts = (unsigned int)numSMs * TM * waves;
     g->workBytes = carve(nullptr, net.L, S, g->WP, g->capPts).bytes;
     g->smemGemm = TS_SMEM_BYTES;         // layer GEMMs: A operand in tensor memory, weight tiles in shared memory (VARNET_B200_TC_TS=0: SMEM_BYTES)
-    g->smemGw = SMEM_BYTES;
+    g->smemGw = gw_mn() ? MN_SMEM_BYTES : SMEM_BYTES;
     return true;
 }
 
@@ -1070,7 +1157,8 @@ cudaError_t vn_tc_prepare(int S, int act) {
     (void)S; (void)act;
     if (const char* t = getenv("VARNET_B200_TC_TS")) g_ts = atoi(t) != 0;
 
-    cudaError_t e = cudaFuncSetAttribute(tc_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_gw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_FWD_VALUE>()) != cudaSuccess) return e;
     if ((e = prep_gemm<EPI_FWD_TANGENT>()) != cudaSuccess) return e;
@@ -1246,7 +1334,8 @@ cudaError_t vn_tc_run(TcJob& j) {
                 g.kPts = ((nPts + g.nsplit - 1) / g.nsplit + KC - 1) / KC * KC;
                 g.g = j.g64 + net.woff[l]; g.wi = net.width[l - 1]; g.wo = net.width[l]; g.gb = j.g64 + net.boff[l];
                 g.err = j.err;
-                tc_gw_kernel<<<tiles * g.nsplit, NTHR_ALL, SMEM_BYTES, st>>>(g);
+                if (gw_mn()) tc_gw_kernel<true><<<tiles * g.nsplit, NTHR_ALL, MN_SMEM_BYTES, st>>>(g);
+                else tc_gw_kernel<false><<<tiles * g.nsplit, NTHR_ALL, SMEM_BYTES, st>>>(g);
                 TCK(cudaGetLastError());
                 j.launches++;
             }

@@ -1401,8 +1401,9 @@ __global__ void tc64_reduce_kernel(NetDesc net, const double* __restrict__ slab,
 // of the 8 bank groups (mode 1: 2-way conflicts, 2x the store wavefronts) unless half of the lanes exchange register quads first
 // (mode 2: +7 % instructions); the scalar transposing stores have neither problem and the same wavefront count.
 int gw_mode() {
-    static const int v = [] { const char* e = getenv("VARNET_B200_TC64_GW"); const int m = e ? atoi(e) : 0; return (m < 0 || m > 2) ? 0 : m; }();
-    return v;
+    const char* e = getenv("VARNET_B200_TC64_GW");         // read per launch: a test switches it inside one process
+    const int m = e ? atoi(e) : 0;
+    return (m < 0 || m > 2) ? 0 : m;
 }
 template <int S, int ACT> cudaError_t launch_t(const Tc64Args& k, int grid, size_t smem, cudaStream_t st) {
     switch (gw_mode()) {
