@@ -137,7 +137,8 @@ def test_tile64_training_trajectory_and_minibatch_index_list():
 
 @pytest.mark.gpu
 def test_mn_major_weight_gradient_operands_are_bit_identical(monkeypatch):
-    """VARNET_B200_TC64_GW = 1 / 2: the weight-gradient GEMM reads MN-major operands (LayoutType::SWIZZLE_128B_BASE32B, the one
+    """VARNET_B200_TC64_GW = 0: every weight-gradient operand written in front of the issue (the default, 3, writes the next step's
+    a-operand under the running layer GEMM).  VARNET_B200_TC64_GW = 1 / 2: the weight-gradient GEMM reads MN-major operands (LayoutType::SWIZZLE_128B_BASE32B, the one
     canonical layout in which kind::tf32 takes them: scripts/micro/tc_probe3.cu) written with 16-byte stores instead of the
     transposing scalar stores.  Same MMAs in the same order on the same numbers: loss and gradient must not change by a bit
     (several tiles per CTA, ragged last tile, S = 3 and S = 2)."""
@@ -149,7 +150,7 @@ def test_mn_major_weight_gradient_operands_are_bit_identical(monkeypatch):
         kw = dict(dim=dim, inpDim=inpDim, layerWidth=lw, activation="tanh", timeDependent=True, lossOpt=dict(isSource=False, integWflag=False))
         ref = go.loss_and_grad(theta, feed, **kw)
         outs = []
-        for mode in ("0", "1", "2"):
+        for mode in ("3", "0", "1", "2"):
             monkeypatch.setenv("VARNET_B200_TC64_GW", mode)
             eng = make_engine(feed, theta=theta, **kw)
             try:

@@ -321,8 +321,10 @@ constexpr uint32_t COL_PARK = 128;      //          + 64 s: abar_{l-1,s}
 constexpr uint32_t COL_SMALL = 320;     //          hi*lo + lo*hi of the running layer GEMM
 constexpr uint32_t COL_GW = 384;        //          weight-gradient accumulator (128 columns)
 
-template <int S, int ACT, int GWM>
+template <int S, int ACT, int VAR>
 __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__ Tc64Args K) {
+    constexpr int GWM = VAR == 3 ? 0 : VAR;         // weight-gradient operand layout (gw_mode)
+    constexpr bool EARLY = VAR == 3;                // [a_hi ; a_lo] of the NEXT step is written under the running layer GEMM
     extern __shared__ __align__(1024) unsigned char smem[];
     const TileArgs& A = K.t;
     const NetDesc& net = A.net;
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 if (GWM) mma_ss(tmem + COL_GW, make_desc_mn(ga + kb * MN_KSTEP), make_desc_mn(gb + kb * MN_KSTEP), IDESC_GW_MN, kb ? 1u : gwAcc);
                 else mma_ss(tmem + COL_GW, make_desc(ga + kb * 2 * G_LBO, G_LBO), make_desc(gb + kb * 2 * G_LBO, G_LBO), IDesc<128>::v, kb ? 1u : gwAcc);
             }
-            if (gwLast) mma_commit(barGw);              // drained after the last stream only; earlier streams are covered by `bar`
+            if (gwLast || EARLY) mma_commit(barGw);     // drained after the last stream only; earlier streams are covered by `bar`
             const uint32_t aHi = tmem + COL_OP, aLo = aHi + 64, dMain = tmem + COL_PARK + 64 * s, dSmall = tmem + COL_SMALL;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
@@ -667,6 +669,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
         {
             float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
+            bool gaStored = false;
             stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
             stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
             stash_get_sw(stash, (L - 2) * S + 1, p, c0, apre, polLast, sw);
@@ -706,23 +709,39 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                             } else {
                                 put_mn(GB, p, h, v, false);
                             }
-                        } else { put_transposed(GB, p, c0, v); put_transposed(GA, p, c0, apre); }
+                        } else {
+                            put_transposed(GB, p, c0, v);
+                            if (!EARLY || !gaStored) put_transposed(GA, p, c0, apre);
+                        }
                         if (s == 0) {
 #pragma unroll
                             for (int jj = 0; jj < CPT; ++jj) a0[jj] = apre[jj];                  // a_{l-1,0}: the value activations of the next layer down
                             if (GWM == 2) quad_swap(a0, sw);                                     // apre holds it quad-exchanged
-                            const float r = warp_colsum(v, lane);                                // g(b_l) = sum_p zbar_{l,0}
-                            vec_add(l, r, first);
+                            if (!EARLY) {
+                                const float r = warp_colsum(v, lane);                            // g(b_l) = sum_p zbar_{l,0}
+                                vec_add(l, r, first);
+                            }
                         }
                         sync_for_issue();
                         issue_adj(s, wst, si > 0 ? 1u : 0u, si == S - 1);
+                        if (EARLY && s == 0) {                                                   // registers only: under the weight-gradient GEMM
+                            const float r = warp_colsum(v, lane);
+                            vec_add(l, r, first);
+                        }
                         // stash rows of the next step, in flight while the tensor core runs
                         if (ln >= 0) {
                             if (sn > 0) stash_get(stash, ln * S + sn, p, c0, dpre, polLast);
                             if (ln >= 1) stash_get_sw(stash, (ln - 1) * S + sn, p, c0, apre, polLast, sw);
                         }
-                        if (si == S - 1) {
+                        if (EARLY) {
+                            // the weight-gradient MMAs of this step have read both operands: the next step's a-operand (its rows are
+                            // in registers by now) goes to shared memory while the layer GEMM still runs
                             wait_gw();
+                            gaStored = ln >= 1;
+                            if (ln >= 1) put_transposed(GA, p, c0, apre);
+                        }
+                        if (si == S - 1) {
+                            if (!EARLY) wait_gw();
                             // the S streams of a layer are ONE K = S*128 contraction (a chain of 16 S <= 48 hi*hi MMAs), drained once:
                             // rows 0..63: a_hi (x) [zbar_hi | zbar_lo]; rows 64..127: a_lo (x) zbar_hi (lo x lo dropped)
                             float g[CPT];
@@ -1393,23 +1412,29 @@ __global__ void tc64_reduce_kernel(NetDesc net, const double* __restrict__ slab,
     if (lane == 0) flat[idx] = s;
 }
 
-// weight-gradient operand layout of the default schedule (VARNET_B200_TC64_GW): 0 (default) = K-major operands written by
-// transposing 4-byte stores; 1 = MN-major operands (SWIZZLE_128B_BASE32B), plain 16-byte stores; 2 = MN-major, quad-exchanged
-// lanes (bank-conflict-free 16-byte stores).  All three are bit-identical; measured on 1/4 of cfg 4 (same box, ABAB,
-// gpurun_out/r2be_ab.log): 38.4 / 42.2 / 40.4 ms.  The MN-major MMAs run at the full rate (scripts/micro/umma_rate.cu: 64.0 against
-// 63.5 cycles per 128x128x8), but a thread owns a (point, 16 neurons) strip, so its 16-byte stores of one instruction hit only 4
-// of the 8 bank groups (mode 1: 2-way conflicts, 2x the store wavefronts) unless half of the lanes exchange register quads first
-// (mode 2: +7 % instructions); the scalar transposing stores have neither problem and the same wavefront count.
+// weight-gradient operands of the default schedule (VARNET_B200_TC64_GW), all bit-identical in their results:
+//   3 (default) = K-major operands written by transposing 4-byte stores, with [a_hi ; a_lo] of the NEXT adjoint step (its stash rows
+//       are in registers by then) written as soon as the weight-gradient MMAs of the running step have completed (their own
+//       mbarrier on every step), i.e. under the layer GEMM instead of in front of the next issue; the bias column sums moved behind
+//       the issue as well.  Same-box A/B on 1/4 of cfg 4 (gpurun_out/r2bo_ab.log, r2bp_ab.log): 38.43 -> 37.56 ms (+2.3 %);
+//   0 = the same operands, all written in front of the issue (round 2's first schedule);
+//   1 = MN-major operands (SWIZZLE_128B_BASE32B), plain 16-byte stores; 2 = MN-major, quad-exchanged lanes (bank-conflict-free
+//       16-byte stores).  Measured (gpurun_out/r2be_ab.log): 38.4 (mode 0) / 42.2 / 40.4 ms.  The MN-major MMAs run at the full rate
+//       (scripts/micro/umma_rate.cu: 64.0 against 63.5 cycles per 128x128x8), but a thread owns a (point, 16 neurons) strip, so its
+//       16-byte stores of one instruction hit only 4 of the 8 bank groups (mode 1: 2-way conflicts, 2x the store wavefronts)
+//       unless half of the lanes exchange register quads first (mode 2: +7 % instructions); the scalar transposing stores have
+//       neither problem and the same wavefront count.
 int gw_mode() {
     const char* e = getenv("VARNET_B200_TC64_GW");         // read per launch: a test switches it inside one process
-    const int m = e ? atoi(e) : 0;
-    return (m < 0 || m > 2) ? 0 : m;
+    const int m = e ? atoi(e) : 3;
+    return (m < 0 || m > 3) ? 3 : m;
 }
 template <int S, int ACT> cudaError_t launch_t(const Tc64Args& k, int grid, size_t smem, cudaStream_t st) {
     switch (gw_mode()) {
+        case 0: tc64_var_kernel<S, ACT, 0><<<grid, NT, smem, st>>>(k); break;
         case 1: tc64_var_kernel<S, ACT, 1><<<grid, NT, smem, st>>>(k); break;
         case 2: tc64_var_kernel<S, ACT, 2><<<grid, NT, smem, st>>>(k); break;
-        default: tc64_var_kernel<S, ACT, 0><<<grid, NT, smem, st>>>(k); break;
+        default: tc64_var_kernel<S, ACT, 3><<<grid, NT, smem, st>>>(k); break;
     }
     return cudaGetLastError();
 }
@@ -1417,6 +1442,7 @@ template <int S, int ACT> cudaError_t prepare_t(size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc64_var_kernel<S, ACT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
 
