@@ -44,7 +44,11 @@ def child(name):
     ntf = int(os.environ.get("AB_NTF", "250000"))
     eng = Engine(2, 3, lw, "tanh", True, False, False, device=0)
     eng.set_params(theta)
-    bfeed, meta = workloads.generate_on_device(eng, 100, 100, 100, 0, ntf)
+    if os.environ.get("AB_UPLOAD"):             # streamed (uploaded) table instead of the in-kernel generated one
+        bfeed, meta = workloads.shard_feed(100, 100, 100, 0, ntf, dtype=np.float32)
+        eng.upload_points(bfeed["Input"], bfeed["gcoef"], bfeed["source"], bfeed["N"], bfeed["dNt"], bfeed["intShape"], bfeed["integW"], bfeed["detJ"], False)
+    else:
+        bfeed, meta = workloads.generate_on_device(eng, 100, 100, 100, 0, ntf)
     eng.upload_bic(bfeed["biInput"], bfeed["biLabel"], bfeed["bDof"], bfeed["biDimVal"])
     eng.set_weights(np.array([1.0, 1.0, 1.0]))
     g0 = eng.loss_grad()["grad"].astype(np.float64)          # gradient of the large launch (window folds exercised)

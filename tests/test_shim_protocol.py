@@ -240,3 +240,31 @@ def test_deferred_epoch_losses_equal_waited_ones(shim):
     assert [type(a) for a in v1] == [type(a) for a in v0]
     assert v1 == v0 and np.array_equal(th1, th0) and lc1 == lc0
     assert v1[1] < v1[0]                                              # and it trains
+
+
+def test_deferred_number_protocol():
+    """backend.Deferred: evaluated once, on first use; `+` defers and repeats the eager additions in the same order and types."""
+    from varnet_b200.backend import Deferred
+    calls = []
+
+    def mk(x):
+        def fn():
+            calls.append(x)
+            return np.float32(x)
+        return Deferred(fn)
+
+    a, b, c = mk(0.1), mk(0.2), mk(0.7)
+    total = 0
+    for d in (a, b, c):
+        total += d
+    assert isinstance(total, Deferred) and calls == []               # nothing evaluated yet
+    eager = 0
+    for x in (0.1, 0.2, 0.7):
+        eager += np.float32(x)
+    assert total.value() == eager and type(total.value()) is type(eager)
+    assert calls == [0.1, 0.2, 0.7]
+    assert float(total) == float(eager) and calls == [0.1, 0.2, 0.7]  # cached
+    assert total < 2 and total > 0.5 and not (total < 0.5) and total == eager and total != 0
+    assert "%.3f" % float(total) == "%.3f" % float(eager) and format(total, ".2e") == format(eager, ".2e") and str(total) == str(eager)
+    assert np.asarray(total).dtype == np.float32 and float(np.asarray([total], dtype=np.float64)[0]) == float(eager)
+    assert float(2.0 + mk(1.0) + 3) == 6.0 and float(mk(1.0) + mk(2.0)) == 3.0

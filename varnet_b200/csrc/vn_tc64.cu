@@ -39,12 +39,12 @@ constexpr int OFF_PAR = OFF_GB + G_BYTES;
 constexpr uint32_t MN_GROUP = 16384, MN_ATOM = 512, MN_KSTEP = 1024;
 constexpr int OFF_MGA = 2 * WIMG_BYTES;            // 64 KB
 constexpr int OFF_MGB = OFF_MGA + 4 * MN_GROUP;    // 64 KB
-constexpr int PAR_FLOATS = 1152 + NH * 384 + 640;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128]
+constexpr int PAR_FLOATS = 1152 + NH * 384 + 640 + 512;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128] | coef[4][128]
 constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
 
-struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; int fwdOnly; int fold; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING); fwdOnly: loss / lossVec / R only (v1 schedule)
+struct Tc64Args { TileArgs t; const float* wimg; int* err; long long* timing; int fwdOnly; int fold; int coefPre; };      // timing: optional [16] phase cycle counters of CTA 0 (VARNET_B200_TC64_TIMING); fwdOnly: loss / lossVec / R only (v1 schedule)
 
 struct SlabLayout { int vecOff, boutOff, psz, nkind; };
 __host__ __device__ inline SlabLayout slab_layout(int L, int inpDim) {
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     float* us = usP + NH * 384;                          // [3][128] u_s, then the adjoint seeds
     float* Ish = us + 384;                          // [128]
     float* Rsh = Ish + 128;                         // [128]
+    float* coefS = Rsh + 128;                       // [4][128] integrand coefficients of the tile's points (gcoef_0, gcoef_1, dNt, source*N)
     const uint32_t bar = smem_u32(smem + OFF_BAR);            // forward GEMMs / adjoint layer GEMM
     const uint32_t barGw = bar + 8;                             // weight-gradient GEMM
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
@@ -518,6 +519,11 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
         }
 
+        // integrand coefficient h of point p: requested now, parked in shared memory at the end of the forward sweep, so that the
+        // integrand / seed phases (128 threads, the tensor core idle) do not wait for global memory
+        float cfr = 0.f;
+        if (K.coefPre && (h < S - 1 || (h == 2 && A.timeDependent) || (h == 3 && A.isSource))) cfr = coefv(h);
+
         // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
         float d1[CPT];                                // act'(z_l) of the value stream, kept for the tangent streams
         {
@@ -582,6 +588,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 l = ln; s = sn;
             }
         }
+        if (K.coefPre) coefS[h * TP + p] = cfr;
         tmem_wait_st();
         __syncthreads();
 
@@ -598,9 +605,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             float I = 0.f;
             if (valid) {
 #pragma unroll
-                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], coefv(k), I);
-                if (A.timeDependent) I -= us[p] * coefv(2);
-                if (A.isSource) I -= coefv(3);
+                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], K.coefPre ? coefS[k * TP + p] : coefv(k), I);
+                if (A.timeDependent) I -= us[p] * (K.coefPre ? coefS[2 * TP + p] : coefv(2));
+                if (A.isSource) I -= (K.coefPre ? coefS[3 * TP + p] : coefv(3));
                 if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
             }
             Ish[p] = I;
@@ -636,9 +643,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 const float wq = A.integW ? __ldg(A.integW + qq) : 1.f;
                 lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
             }
-            us[p] = A.timeDependent ? -lam * coefv(2) : 0.f;
+            us[p] = A.timeDependent ? -lam * (K.coefPre ? coefS[2 * TP + p] : coefv(2)) : 0.f;
 #pragma unroll
-            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * coefv(k);
+            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * (K.coefPre ? coefS[k * TP + p] : coefv(k));
         }
         __syncthreads();
 
@@ -1495,6 +1502,7 @@ cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg,
     k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr; k.fwdOnly = fwdOnly;
     static const int fold = [] { const char* e = getenv("VARNET_B200_TC64_FOLD"); const int v = e ? atoi(e) : FOLD; return v > 0 ? v : FOLD; }();
     k.fold = fold;
+    { const char* ev = getenv("VARNET_B200_TC64_COEF"); k.coefPre = (ev && ev[0] == '0') ? 0 : 1; }
     if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
