@@ -39,7 +39,7 @@ constexpr int OFF_PAR = OFF_GB + G_BYTES;
 constexpr uint32_t MN_GROUP = 16384, MN_ATOM = 512, MN_KSTEP = 1024;
 constexpr int OFF_MGA = 2 * WIMG_BYTES;            // 64 KB
 constexpr int OFF_MGB = OFF_MGA + 4 * MN_GROUP;    // 64 KB
-constexpr int PAR_FLOATS = 1152 + NH * 384 + 640 + 512;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128] | coef[4][128]
+constexpr int PAR_FLOATS = 1152 + NH * 384 + 640 + 512 + 2 * VN_KIN * 128;  // W0[8][64] | bias[8][64] | wout[64] | bout.. | usP[NH][3][128] | us[3][128] | I[128] | R[128] | coef[4][128] | x[2][VN_KIN][128]
 constexpr int OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t COL_WORK = 384;
@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
     float* Ish = us + 384;                          // [128]
     float* Rsh = Ish + 128;                         // [128]
     float* coefS = Rsh + 128;                       // [4][128] integrand coefficients of the tile's points (gcoef_0, gcoef_1, dNt, source*N)
+    float* xS = coefS + 512;                        // [2][VN_KIN][128] MLP inputs of this tile's and of the CTA's next tile's points
+    const bool xPre = (K.coefPre & 2) != 0;
     const uint32_t bar = smem_u32(smem + OFF_BAR);            // forward GEMMs / adjoint layer GEMM
     const uint32_t barGw = bar + 8;                             // weight-gradient GEMM
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
@@ -480,7 +482,44 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
 
     prefetch_image(0, 0);
 
-    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    // MLP inputs of the 128 points of `tile` -> xS[buf]: streamed tables with 4-byte cp.async (no register, no wait), everything else
+    // (extra inputs, in-kernel generated coordinates, index-list batches) computed and stored; called one tile ahead
+    auto stage_inputs = [&](int tile, int buf) {
+        for (int idx = tid; idx < net.inpDim * TP; idx += NT) {
+            const int c = idx / TP, pp = idx - c * TP;
+            const unsigned int g = (unsigned int)(A.tile0 + tile) * TP + pp;
+            float* dst = xS + (buf * VN_KIN + c) * TP + pp;
+            if (c >= A.nxTable) { *dst = __ldg(A.extraX + (c - A.nxTable)); continue; }
+            if (A.useGen) {
+                float val = 0.f;
+                if (g < A.P) {
+                    const unsigned int bb = g / A.integNum;
+                    const int q2 = (int)(g - bb * A.integNum);
+                    const long long i2 = A.gen.tf0 + (long long)table_tf(A, bb);
+                    const long long s2 = i2 / A.gen.nTime, j2 = i2 - s2 * A.gen.nTime;
+                    const double ctr = c < A.gen.dim ? __ldg(A.gen.coord + s2 * A.gen.dim + c) : __ldg(A.gen.tcoord + j2);
+                    val = __double2float_rn(__dadd_rn(ctr, __ldg(A.gen.hd + (size_t)c * A.gen.q + q2)));
+                }
+                *dst = val;
+                continue;
+            }
+            const float* col = A.cols + (size_t)(A.colX + c) * A.pstride;
+            if (!A.tfIndex) {                           // zero padded table
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst)), "l"(col + g) : "memory");
+                continue;
+            }
+            *dst = g < A.P ? __ldg(col + table_row(A, g)) : 0.f;
+        }
+        cp_async_commit();                              // cp_async_wait_all() waits for committed groups only
+    };
+    int xbuf = 0;
+    if (xPre && (int)blockIdx.x < A.ntiles) stage_inputs(blockIdx.x, 0);
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, xbuf ^= 1) {
+        if (xPre) {                                     // this tile's inputs (staged one tile ago) have landed and are visible
+            cp_async_wait_all();
+            __syncthreads();
+        }
         const unsigned int base = (unsigned int)(A.tile0 + tile) * TP;
         const unsigned int gp = base + p;
         const bool valid = gp < A.P;
@@ -500,6 +539,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             return __ldg(A.cols + (size_t)col * A.pstride + row);
         };
         auto input = [&](int c) -> float {
+            if (xPre) return xS[(xbuf * VN_KIN + c) * TP + p];
             if (c >= A.nxTable) return __ldg(A.extraX + (c - A.nxTable));
             if (A.useGen) {
                 if (!valid) return 0.f;
@@ -522,7 +562,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // integrand coefficient h of point p: requested now, parked in shared memory at the end of the forward sweep, so that the
         // integrand / seed phases (128 threads, the tensor core idle) do not wait for global memory
         float cfr = 0.f;
-        if (K.coefPre && (h < S - 1 || (h == 2 && A.timeDependent) || (h == 3 && A.isSource))) cfr = coefv(h);
+        if ((K.coefPre & 1) && (h < S - 1 || (h == 2 && A.timeDependent) || (h == 3 && A.isSource))) cfr = coefv(h);
 
         // ---- inputs and layer 0 (K = inpDim: FP32 FMA).  Stream 1+k is seeded with the unit vector e_k.
         float d1[CPT];                                // act'(z_l) of the value stream, kept for the tangent streams
@@ -546,6 +586,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 if (!K.fwdOnly) stash_put(stash, 1 + k, p, c0, v, polLast);
             }
         }
+
+        if (xPre && tile + (int)gridDim.x < A.ntiles) stage_inputs(tile + (int)gridDim.x, xbuf ^ 1);
 
         // ---- hidden layers, forward: the GEMM of the next (layer, stream) step is issued before this step's epilogue
         // arithmetic, so the tensor core runs under the activation functions
@@ -588,7 +630,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 l = ln; s = sn;
             }
         }
-        if (K.coefPre) coefS[h * TP + p] = cfr;
+        if (K.coefPre & 1) coefS[h * TP + p] = cfr;
         tmem_wait_st();
         __syncthreads();
 
@@ -605,9 +647,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             float I = 0.f;
             if (valid) {
 #pragma unroll
-                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], K.coefPre ? coefS[k * TP + p] : coefv(k), I);
-                if (A.timeDependent) I -= us[p] * (K.coefPre ? coefS[2 * TP + p] : coefv(2));
-                if (A.isSource) I -= (K.coefPre ? coefS[3 * TP + p] : coefv(3));
+                for (int k = 0; k < S - 1; ++k) I = fmaf(us[(1 + k) * TP + p], (K.coefPre & 1) ? coefS[k * TP + p] : coefv(k), I);
+                if (A.timeDependent) I -= us[p] * ((K.coefPre & 1) ? coefS[2 * TP + p] : coefv(2));
+                if (A.isSource) I -= ((K.coefPre & 1) ? coefS[3 * TP + p] : coefv(3));
                 if (A.integW) I *= __ldg(A.integW + (gp % A.integNum));
             }
             Ish[p] = I;
@@ -643,9 +685,9 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                 const float wq = A.integW ? __ldg(A.integW + qq) : 1.f;
                 lam = 2.f * __ldg(A.wts + 2) * dj * wq * Rsh[p / A.integNum];
             }
-            us[p] = A.timeDependent ? -lam * (K.coefPre ? coefS[2 * TP + p] : coefv(2)) : 0.f;
+            us[p] = A.timeDependent ? -lam * ((K.coefPre & 1) ? coefS[2 * TP + p] : coefv(2)) : 0.f;
 #pragma unroll
-            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * (K.coefPre ? coefS[k * TP + p] : coefv(k));
+            for (int k = 0; k < S - 1; ++k) us[(1 + k) * TP + p] = lam * ((K.coefPre & 1) ? coefS[k * TP + p] : coefv(k));
         }
         __syncthreads();
 
@@ -1502,7 +1544,8 @@ cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg,
     k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr; k.fwdOnly = fwdOnly;
     static const int fold = [] { const char* e = getenv("VARNET_B200_TC64_FOLD"); const int v = e ? atoi(e) : FOLD; return v > 0 ? v : FOLD; }();
     k.fold = fold;
-    { const char* ev = getenv("VARNET_B200_TC64_COEF"); k.coefPre = (ev && ev[0] == '0') ? 0 : 1; }
+    // bit 0: integrand coefficients requested at tile start; bit 1: MLP inputs staged in shared memory one tile ahead
+    { const char* ev = getenv("VARNET_B200_TC64_COEF"); const int m = ev ? atoi(ev) : 3; k.coefPre = (m < 0 || m > 3) ? 3 : m; }
     if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
