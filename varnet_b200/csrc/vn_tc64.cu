@@ -631,13 +631,6 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
         }
         if (K.coefPre & 1) coefS[h * TP + p] = cfr;
-        // the first stash rows of the adjoint sweep (this thread wrote them itself) are requested before the integrand / seed / output-layer
-        // phases, so that the sweep does not start with an exposed L2 round trip
-        float a0[CPT], dpre[CPT], apre[CPT];
-        if (EARLY && (K.coefPre & 4) && !K.fwdOnly) {
-            stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
-            stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
-        }
         tmem_wait_st();
         __syncthreads();
 
@@ -724,12 +717,10 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // ---- adjoint sweep: step (l, s) turns abar_{l,s} into zbar_{l,s} (tangent streams first: the value stream needs
         // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
         {
-            float cross[CPT];
+            float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
             bool gaStored = false;
-            if (!(EARLY && (K.coefPre & 4))) {
-                stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
-                stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
-            }
+            stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
+            stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
             stash_get_sw(stash, (L - 2) * S + 1, p, c0, apre, polLast, sw);
             for (int l = L - 1; l >= 0; --l) {
                 uint32_t wst = 0;
@@ -1553,9 +1544,8 @@ cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg,
     k.t = a; k.wimg = wimg; k.err = err; k.timing = nullptr; k.fwdOnly = fwdOnly;
     static const int fold = [] { const char* e = getenv("VARNET_B200_TC64_FOLD"); const int v = e ? atoi(e) : FOLD; return v > 0 ? v : FOLD; }();
     k.fold = fold;
-    // bit 0: integrand coefficients requested at tile start; bit 1: MLP inputs staged in shared memory one tile ahead;
-    // bit 2: first stash rows of the adjoint sweep requested before the integrand / seed phases
-    { const char* ev = getenv("VARNET_B200_TC64_COEF"); const int m = ev ? atoi(ev) : 7; k.coefPre = (m < 0 || m > 7) ? 7 : m; }
+    // bit 0: integrand coefficients requested at tile start; bit 1: MLP inputs staged in shared memory one tile ahead
+    { const char* ev = getenv("VARNET_B200_TC64_COEF"); const int m = ev ? atoi(ev) : 3; k.coefPre = (m < 0 || m > 3) ? 3 : m; }
     if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
