@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
             const float* col = A.cols + (size_t)(A.colX + c) * A.pstride;
             if (!A.tfIndex) {                           // zero padded table
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst)), "l"(col + g) : "memory");
+                asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(smem_u32(dst)), "l"(col + g), "l"(polFirst) : "memory");   // streamed once: evict_first, the stash slabs keep the L2
                 continue;
             }
             *dst = g < A.P ? __ldg(col + table_row(A, g)) : 0.f;
@@ -536,6 +536,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         auto coefv = [&](int k) -> float {               // 0, 1: gcoef; 2: dNt; 3: source*N
             if (A.useGen) return __ldg(A.gen.coef + gq * 4 + k);
             const int col = k < 2 ? A.colG + k : (k == 2 ? A.colT : A.colS);
+            if (!A.tfIndex) return ldg_stream(A.cols + (size_t)col * A.pstride + row, polFirst);      // streamed once
             return __ldg(A.cols + (size_t)col * A.pstride + row);
         };
         auto input = [&](int c) -> float {
