@@ -530,8 +530,10 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         if (A.useGen && valid) {
             const unsigned int b = gp / A.integNum;
             gq = (int)(gp - b * A.integNum);
-            const long long i = A.gen.tf0 + (long long)table_tf(A, b);
-            gs = i / A.gen.nTime; gj = i - gs * A.gen.nTime;
+            if (!xPre) {                                 // with staged inputs only the Gauss index is needed here
+                const long long i = A.gen.tf0 + (long long)table_tf(A, b);
+                gs = i / A.gen.nTime; gj = i - gs * A.gen.nTime;
+            }
         }
         auto coefv = [&](int k) -> float {               // 0, 1: gcoef; 2: dNt; 3: source*N
             if (A.useGen) return __ldg(A.gen.coef + gq * 4 + k);
@@ -588,8 +590,6 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             }
         }
 
-        if (xPre && tile + (int)gridDim.x < A.ntiles) stage_inputs(tile + (int)gridDim.x, xbuf ^ 1);
-
         // ---- hidden layers, forward: the GEMM of the next (layer, stream) step is issued before this step's epilogue
         // arithmetic, so the tensor core runs under the activation functions
         {
@@ -597,6 +597,8 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
             uint32_t wst = acquire_image();
             sync_for_issue();
             issue_fwd(0, wst);
+            // inputs of the CTA's next tile -> the other shared-memory buffer, while the first GEMM of this tile runs
+            if (xPre && tile + (int)gridDim.x < A.ntiles) stage_inputs(tile + (int)gridDim.x, xbuf ^ 1);
             int l = 1, s = 0;
             for (int k = 0; k < nfs; ++k) {
                 wait_mma();
