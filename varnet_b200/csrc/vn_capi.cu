@@ -451,6 +451,9 @@ struct PointSet {
     bool inKernel = false; DevBuf genBuf; GenTab genTab{};
     cudaGraphExec_t graph = nullptr; float graphLr = -1.f; int graphLaunches = 0; unsigned int graphNb = 0; bool graphIndexed = false;
     long long graphEpoch = -1;   // g_reallocEpoch at capture time
+    // k consecutive steps as ONE graph (vn_train_steps / vn_train_batches): no graph launch between the steps
+    cudaGraphExec_t graphK = nullptr; int graphKn = 0; float graphKLr = -1.f; int graphKLaunches = 0; unsigned int graphKNb = 0;
+    bool graphKIndexed = false, graphKSeq = false; long long graphKEpoch = -1;
 };
 
 struct vn_engine {
@@ -546,7 +549,8 @@ static const int kLossRing = 4096;      // loss history kept on the device for b
 
 static void drop_graph(PointSet* t) {
     if (t && t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
-    if (t) t->graphLr = -1.f;
+    if (t && t->graphK) { cudaGraphExecDestroy(t->graphK); t->graphK = nullptr; }
+    if (t) { t->graphLr = -1.f; t->graphKLr = -1.f; t->graphKn = 0; }
 }
 static void drop_graph(vn_engine* e) {            // everything captured so far is stale (stream / BC-IC table changed)
     for (PointSet* t : e->slots) drop_graph(t);
@@ -1889,6 +1893,53 @@ static int train_step_enqueue(vn_engine* e, float lr) {
     }
     return VN_OK;
 }
+// k consecutive optimizer steps as ONE captured graph: for the launch-bound operator configurations a step is three kernels of a few
+// tens of microseconds, and a graph launch per step leaves the GPU idle for a few microseconds between them.  `seqBytes` > 0: step i
+// first copies index list i of e->batchSeq into e->batchIdx (vn_train_batches); 0: the same batch k times (vn_train_steps).
+// Returns 1 if the steps were enqueued this way, 0 if the caller has to enqueue them one by one, < 0 on error.
+static const int kStepsPerGraph = 16;
+static int train_steps_one_graph(vn_engine* e, float lr, int k, size_t seqBytes) {
+    static const bool off = [] { const char* v = getenv("VARNET_B200_MULTISTEP_GRAPH"); return v && v[0] == '0'; }();
+    if (off || k < 2 || !e->graphOK || e->profOn || e->stream == nullptr) return 0;
+    PointSet* t = e->t;
+    if (!e->P || !t->loaded || !e->nbi || t->nx + e->nExtra != e->cfg.inpDim) return 0;      // let the single-step path report it
+    // only small steps: a captured sequence of long steps gains nothing and the capture itself costs k steps of launch work
+    if ((double)e->P * e->net.nparam > 4.0e9) return 0;
+    const bool seq = seqBytes > 0;
+    if (!(t->graphK && t->graphKn == k && t->graphKLr == lr && t->graphKNb == e->nb && t->graphKIndexed == e->indexed &&
+          t->graphKSeq == seq && t->graphKEpoch == g_reallocEpoch)) {
+        if (t->graphK) { cudaGraphExecDestroy(t->graphK); t->graphK = nullptr; }
+        const bool fuse = e->wclass != 256 && !e->comm;
+        const int64_t l0 = e->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = VN_OK;
+        if (ce == cudaSuccess) {
+            for (int i = 0; i < k && !rc; ++i) {
+                if (seq && cudaMemcpyAsync(e->batchIdx.p, e->batchSeq.as<char>() + seqBytes * i, seqBytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) rc = VN_E_CUDA;
+                if (!rc) rc = run_loss(e, true, nullptr, fuse ? lr : -1.f);
+                if (!rc && e->comm) rc = vn_allreduce_grad(e);
+                if (!rc && !fuse) rc = vn_optimizer_step(e, lr);
+            }
+            ce = cudaStreamEndCapture(e->stream, &g);
+        }
+        const int64_t captured = e->launches - l0;
+        e->launches = l0;
+        if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&t->graphK, g, 0) != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            t->graphK = nullptr;
+            return 0;
+        }
+        cudaGraphDestroy(g);
+        t->graphKn = k; t->graphKLr = lr; t->graphKNb = e->nb; t->graphKIndexed = e->indexed; t->graphKSeq = seq;
+        t->graphKEpoch = g_reallocEpoch; t->graphKLaunches = (int)captured;
+    }
+    if (cudaGraphLaunch(t->graphK, e->stream) != cudaSuccess) { cudaGetLastError(); return 0; }
+    e->launches += t->graphKLaunches;
+    return 1;
+}
+
 extern "C" int vn_train_step(vn_engine* e, float lr, float* loss_out) {
     int rc = train_step_enqueue(e, lr);
     if (rc) return rc;
@@ -1913,7 +1964,16 @@ extern "C" int vn_train_steps(vn_engine* e, float lr, int32_t k, float* losses) 
     long long step0 = 0;
     CK(cudaMemcpyAsync(&step0, e->stepbuf.p, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < k; ++i) {
+    // chunks of kStepsPerGraph steps go out as one graph each (the caller's k varies from call to call: VarNet.train never crosses a
+    // saveFreq boundary), the remainder step by step
+    int done = 0;
+    while (k - done >= kStepsPerGraph) {
+        const int og = train_steps_one_graph(e, lr, kStepsPerGraph, 0);
+        if (og < 0) return og;
+        if (!og) break;
+        done += kStepsPerGraph;
+    }
+    for (int i = done; i < k; ++i) {
         int rc = train_step_enqueue(e, lr);
         if (rc) return rc;
     }
@@ -1954,7 +2014,9 @@ extern "C" int vn_train_batches_begin(vn_engine* e, float lr, const int32_t* tf_
     e->indexed = true; e->nb = (unsigned int)nb;
     int rc = ensure_work(e);
     if (rc) return rc;
-    for (int i = 0; i < k; ++i) {
+    const int og = train_steps_one_graph(e, lr, k, one);
+    if (og < 0) return og;
+    for (int i = 0; i < k && !og; ++i) {
         CK(cudaMemcpyAsync(e->batchIdx.p, e->batchSeq.as<char>() + one * i, one, cudaMemcpyDeviceToDevice, e->stream));
         rc = train_step_enqueue(e, lr);
         if (rc) return rc;
