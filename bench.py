@@ -637,7 +637,7 @@ def main():
         bytes_pt = 4 * (meta["inpDim"] + meta["dim"] + 1)
         roofline = dict(bound="fp32", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf if peak_tf else None,
                         traffic=measured_traffic(args.workload) if world == 1 else None, kernel="vn_adj_kernel<MODE_VAR_FUSED>", kernel_ms=kernel_ms,
-                        kernel_share_of_step=kernel_ms / ms_step if ms_step else None,
+                        kernel_share_of_step=kernel_ms / ms_prof if ms_prof else None,     # both from the profiled leg (plain launches, per-kernel events)
                         flop_per_point=flop_pt, points_per_launch=P_local,
                         peak_source="FFMA microbenchmark (vn_fp32_peak_tflops) measured in this run",
                         hbm=dict(bound="hbm", achieved=bytes_pt * P_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0,
