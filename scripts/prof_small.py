@@ -35,5 +35,5 @@ for name, dim, inpDim, lw, nb, q, nbi, bDof in SHAPES:
     pr = eng.profile_read()
     per = {a: round(1e3 * b[0] / max(b[1], 1), 2) for a, b in pr.items() if b[1]}
     print("%-24s %9.0f steps/s  %7.1f us/step  %8.1f M pts/s | profiled kernels (us): %s | %s" %
-          (name, n / dt, 1e6 * dt / n, nb * q * n / dt / 1e6, per, eng.kernel_info()[:150]), flush=True)
+          (name, n / dt, 1e6 * dt / n, nb * q * n / dt / 1e6, per, eng.kernel_info()[:150] + " ... " + eng.kernel_info()[-6:]), flush=True)
     eng.close()

@@ -21,6 +21,7 @@
 #include "vn_tc.h"
 #include "vn_tc64.h"
 #include "vn_tpp.h"
+#include "vn_pdl.cuh"
 #include <utility>
 
 // ------------------------------------------------------------------ errors
@@ -198,6 +199,10 @@ __global__ void vn_advance_kernel(long long* step, double* corr, const int* err,
 __global__ void vn_finalize_kernel(FinalArgs A) {
     const NetDesc& net = A.net;
     const PartLayout& pl = A.pl;
+    // k-steps-in-one-graph path: the next step's kernels may become resident now (they block in their own pdl_wait until this
+    // grid has completed); everything below reads what the step's point kernels wrote
+    pdl_launch_dependents();
+    pdl_wait();
     // a tensor-core kernel of this step gave up on an mbarrier wait: its partial slabs are stale.  Publish NaN and leave
     // the weights alone, so the caller sees the failure in the very step it happened (the host also reads the flag).
     const bool bad = A.err != nullptr && *reinterpret_cast<const volatile int*>(A.err) != 0;
@@ -253,11 +258,11 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
     } else {
     __shared__ double sh[32];
     double v = 0.0;
-    for (int k = threadIdx.x; k < A.nSeg; k += blockDim.x) v += A.segSum[k];
+    for (int k = threadIdx.x; k < A.nSeg; k += blockDim.x) v += __ldcg(A.segSum + k);
     const double segTot = block_sum(v, sh);
     double vb = 0.0, vi = 0.0;
     for (unsigned int k = threadIdx.x; k < A.nbi; k += blockDim.x) {
-        const double c = (double)A.cj[k];
+        const double c = (double)__ldcg(A.cj + k);
         if (k < A.bDof) vb += c; else vi += c;
     }
     const double sb = block_sum(vb, sh);
@@ -488,12 +493,14 @@ struct vn_engine {
     cudaStream_t stream = nullptr;      // engine-owned blocking stream (ordered w.r.t. the legacy default stream) or the caller's
     cudaStream_t ownStream = nullptr;
     int64_t launches = 0;
+    int pdlGraphs = 0;           // 1: the last k-step graph was instantiated with programmatic kernel -> kernel edges
     bool graphOK = true;         // CUDA-graph capture of vn_train_step available (one graph per table slot)
     // table slots: several uploaded point tables can be resident; mini-batches select test functions of the
     // current table through a device index list (vn_select_table / vn_set_batch)
     std::vector<PointSet*> slots;
     PointSet* t = nullptr;
     DevBuf batchIdx, extraX, batchSeq, lossOut;
+    const int* idxOverride = nullptr;   // capture of a mini-batch epoch: step i reads its index list in batchSeq directly
     // vn_train_batches_begin / _end: up to two calls in flight, each with its own pinned staging (index lists, the small
     // uploads that precede the call: extra inputs, BC/IC rows) and pinned result slots
     struct Pend {
@@ -1430,7 +1437,7 @@ static void var_args(const vn_engine* e, TileArgs* a) {
     a->colX = t->colX; a->colG = t->colG; a->colT = t->colT; a->colS = t->colS;
     a->useGen = t->inKernel ? 1 : 0; a->gen = t->genTab;
     a->nxTable = t->nx; a->extraX = e->extraX.as<float>();
-    a->tfIndex = e->indexed ? e->batchIdx.as<int>() : nullptr;
+    a->tfIndex = e->indexed ? (e->idxOverride ? e->idxOverride : e->batchIdx.as<int>()) : nullptr;
     a->P = e->P;
     a->integNum = t->integNum;
     a->integW = t->hasIntegW ? t->integW.as<float>() : nullptr;
@@ -1618,7 +1625,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         {
             SegArgs s;
             s.Iw = e->Iw.as<float>(); s.nb = e->nb; s.integNum = e->t->integNum; s.detJ = e->t->detJ.as<float>();
-            s.detJvec = e->t->detJvec; s.tfIndex = e->indexed ? e->batchIdx.as<int>() : nullptr; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
+            s.detJvec = e->t->detJvec; s.tfIndex = e->indexed ? (e->idxOverride ? e->idxOverride : e->batchIdx.as<int>()) : nullptr; s.R = e->R.as<float>(); s.lossVec = e->lossVec.as<float>();
             s.blockSum = e->segSum.as<double>();
             ProfScope ps(e, PK_SEG);
             vn_segreduce_kernel<<<nSeg, 256, 0, st>>>(s);
@@ -1893,6 +1900,36 @@ static int train_step_enqueue(vn_engine* e, float lr) {
     }
     return VN_OK;
 }
+// Kernel -> kernel edges of a captured step sequence become PROGRAMMATIC dependencies (vn_pdl.cuh): the downstream grid is scheduled
+// while the upstream one still runs and blocks in griddepcontrol.wait until it has completed, which takes the grid launch latency
+// (a few microseconds per dependency, two per step) off the critical path of the launch-bound operator configurations.  Only for
+// graphs whose kernel nodes are all {tpp_var_kernel, vn_adj_kernel (boundary/initial rows), vn_finalize_kernel}: these three carry
+// the wait.  Returns false (graph unchanged or partly converted: the caller discards it) when the runtime refuses.
+static bool pdl_edges(cudaGraph_t g) {
+    size_t n = 0;
+    if (cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (!n) return true;
+    std::vector<cudaGraphNode_t> from(n), to(n);
+    std::vector<cudaGraphEdgeData> ed(n);
+    if (cudaGraphGetEdges_v2(g, from.data(), to.data(), ed.data(), &n) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType tf, tt;
+        if (cudaGraphNodeGetType(from[i], &tf) != cudaSuccess || cudaGraphNodeGetType(to[i], &tt) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (tf != cudaGraphNodeTypeKernel || tt != cudaGraphNodeTypeKernel || ed[i].type != cudaGraphDependencyTypeDefault) continue;
+        if (cudaGraphRemoveDependencies_v2(g, &from[i], &to[i], &ed[i], 1) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaGraphEdgeData pe;
+        memset(&pe, 0, sizeof(pe));
+        pe.from_port = cudaGraphKernelNodePortProgrammatic;
+        pe.type = cudaGraphDependencyTypeProgrammatic;
+        if (cudaGraphAddDependencies_v2(g, &from[i], &to[i], &pe, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    }
+    return true;
+}
+static bool pdl_wanted(const vn_engine* e, bool fuse) {
+    static const bool off = [] { const char* v = getenv("VARNET_B200_PDL"); return v && v[0] == '0'; }();
+    return !off && fuse && e->useTpp && e->fused && !e->comm && e->auxStream != nullptr;
+}
+
 // k consecutive optimizer steps as ONE captured graph: for the launch-bound operator configurations a step is three kernels of a few
 // tens of microseconds, and a graph launch per step leaves the GPU idle for a few microseconds between them.  `seqBytes` > 0: step i
 // first copies index list i of e->batchSeq into e->batchIdx (vn_train_batches); 0: the same batch k times (vn_train_steps).
@@ -1915,18 +1952,36 @@ static int train_steps_one_graph(vn_engine* e, float lr, int k, size_t seqBytes)
         cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
         int rc = VN_OK;
         if (ce == cudaSuccess) {
+            // step i reads its index list where the upload put it (no copy between two steps: the step kernels stay adjacent
+            // kernel nodes); the engine is left on the last batch by one copy behind the last step
             for (int i = 0; i < k && !rc; ++i) {
-                if (seq && cudaMemcpyAsync(e->batchIdx.p, e->batchSeq.as<char>() + seqBytes * i, seqBytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) rc = VN_E_CUDA;
-                if (!rc) rc = run_loss(e, true, nullptr, fuse ? lr : -1.f);
+                if (seq) e->idxOverride = reinterpret_cast<const int*>(e->batchSeq.as<char>() + seqBytes * i);
+                rc = run_loss(e, true, nullptr, fuse ? lr : -1.f);
                 if (!rc && e->comm) rc = vn_allreduce_grad(e);
                 if (!rc && !fuse) rc = vn_optimizer_step(e, lr);
             }
+            e->idxOverride = nullptr;
+            if (seq && !rc && cudaMemcpyAsync(e->batchIdx.p, e->batchSeq.as<char>() + seqBytes * (k - 1), seqBytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) rc = VN_E_CUDA;
             ce = cudaStreamEndCapture(e->stream, &g);
         }
         const int64_t captured = e->launches - l0;
         e->launches = l0;
-        if (ce != cudaSuccess || rc || !g || cudaGraphInstantiate(&t->graphK, g, 0) != cudaSuccess) {
+        if (ce != cudaSuccess || rc || !g) {
             if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            t->graphK = nullptr;
+            return 0;
+        }
+        // programmatic kernel -> kernel edges on a clone, so that a refusal leaves the captured graph as it was
+        e->pdlGraphs = 0;
+        if (pdl_wanted(e, fuse)) {
+            cudaGraph_t gp = nullptr;
+            if (cudaGraphClone(&gp, g) == cudaSuccess && pdl_edges(gp) && cudaGraphInstantiate(&t->graphK, gp, 0) == cudaSuccess) e->pdlGraphs = 1;
+            else { cudaGetLastError(); t->graphK = nullptr; }
+            if (gp) cudaGraphDestroy(gp);
+        }
+        if (!t->graphK && cudaGraphInstantiate(&t->graphK, g, 0) != cudaSuccess) {
+            cudaGraphDestroy(g);
             cudaGetLastError();
             t->graphK = nullptr;
             return 0;
@@ -2193,9 +2248,9 @@ extern "C" int vn_kernel_info(const vn_engine* e, char* buf, size_t n) {
     }
     if (e->useTpp) {
         snprintf(buf, n, "family=fp32-thread-per-point class=%d S=%d L=%d var_adj(TP=128,NT=128,smem=%zu,grid=%d,%d CTAs/SM,fused-R single pass,"
-                 "%d gradient patches) var_fwd(fp32-fma-tile,TP=%d) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d",
+                 "%d gradient patches) var_fwd(fp32-fma-tile,TP=%d) bic_adj(fp32-fma-tile,TP=%d,smem=%zu,grid=%d) nparam=%d SMs=%d pdl=%d",
                  e->wclass, e->S, e->net.L, e->tppLay.smemBytes, e->gridVar, e->tppCtas, e->tppLay.npatch, e->gVarFwd.TP, e->gBicAdj.TP,
-                 e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs);
+                 e->gBicAdj.smemBytes, e->gridBic, e->net.nparam, e->numSMs, e->pdlGraphs);
         return VN_OK;
     }
     snprintf(buf, n,

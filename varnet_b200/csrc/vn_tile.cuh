@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "vn_pdl.cuh"
 
 #define VN_MAX_LAYERS 8
 #define VN_KIN 8          // padded MLP input rows (== VN_MAX_INPDIM)
@@ -409,24 +410,28 @@ __device__ __forceinline__ void stage_network(const TileArgs& A, const SmemMap<C
     const int tid = threadIdx.x, L = net.L;
     constexpr int NT = C::NT, WS = C::WS, WP = C::WP;
     for (int i = tid; i < total; i += NT) smem[i] = 0.f;
+    // k-steps-in-one-graph path (vn_pdl.cuh): the weights below were written by the previous step's reduction kernel
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
-    const float* __restrict__ th = A.theta;
+    const float* th = A.theta;
+    auto ld = [](const float* q) { return __ldcg(q); };                 // coherent loads: never ld.global.nc behind pdl_wait
     for (int idx = tid; idx < net.inpDim * net.width[0]; idx += NT) {
         int i = idx / net.width[0], j = idx - i * net.width[0];
-        m.W0[i * WS + j] = th[net.woff[0] + idx];
+        m.W0[i * WS + j] = ld(th + net.woff[0] + idx);
     }
     for (int l = 1; l < L; ++l) {
         const int wi = net.width[l - 1], wo = net.width[l];
         float* Wm = m.Wl + (l - 1) * WP * WS;
         for (int idx = tid; idx < wi * wo; idx += NT) {
             int i = idx / wo, j = idx - i * wo;
-            Wm[i * WS + j] = th[net.woff[l] + idx];
+            Wm[i * WS + j] = ld(th + net.woff[l] + idx);
         }
     }
     for (int l = 0; l < L; ++l)
-        for (int j = tid; j < net.width[l]; j += NT) m.bias[l * WP + j] = th[net.boff[l] + j];
-    for (int j = tid; j < net.width[L - 1]; j += NT) m.wout[j] = th[net.woff[L] + j];
-    if (tid == 0) m.wout[WP] = th[net.boff[L]];
+        for (int j = tid; j < net.width[l]; j += NT) m.bias[l * WP + j] = ld(th + net.boff[l] + j);
+    for (int j = tid; j < net.width[L - 1]; j += NT) m.wout[j] = ld(th + net.woff[L] + j);
+    if (tid == 0) m.wout[WP] = ld(th + net.boff[L]);
     // d x_c / d x_k = delta_ck  (stream 1+k seeds input column k)
     for (int idx = tid; idx < nunit * C::TP; idx += NT) {
         int k = idx / C::TP, p = idx - k * C::TP;

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "vn_tpp.h"
+#include "vn_pdl.cuh"
 
 namespace {
 
@@ -196,26 +197,30 @@ __global__ void __launch_bounds__(T, 4) tpp_var_kernel(const __grid_constant__ T
     double* slab = A.part + (size_t)blockIdx.x * A.psz;       // this CTA's FP64 patches (L2 resident)
 
     for (int i = tid; i < Y.wfloats; i += T) wts[i] = 0.f;
-    if (!A.accumulate)
-        for (int i = tid; i < Y.npatch * 32; i += T) slab[i] = 0.0;
     build_offsets(Y, otab, tid);
     rows[Y.rowOne * T + tid] = 1.f;
     rows[Y.rowZero * T + tid] = 0.f;
+    // k-steps-in-one-graph path (vn_pdl.cuh): the prologue above runs next to the previous step's reduction kernel, which reads
+    // this CTA's slab and writes the weights; nothing of either is touched before the wait
+    pdl_launch_dependents();
+    pdl_wait();
+    if (!A.accumulate)
+        for (int i = tid; i < Y.npatch * 32; i += T) slab[i] = 0.0;
     __syncthreads();
     {
-        const float* __restrict__ th = A.theta;
+        const float* th = A.theta;
         for (int l = 0; l < L; ++l) {
             const int wi = l == 0 ? Y.inpDim : Y.w[l - 1], wo = Y.w[l];
             for (int idx = tid; idx < wi * wo; idx += T) {
                 const int i = idx / wo, j = idx - i * wo;
-                const float v = th[net.woff[l] + idx];
+                const float v = __ldcg(th + net.woff[l] + idx);            // coherent loads: never ld.global.nc behind pdl_wait
                 wts[Y.offW[l] + i * Y.wp[l] + j] = v;
                 if (l >= 1) wts[Y.offWT[l] + j * Y.wp[l - 1] + i] = v;
             }
-            for (int j = tid; j < wo; j += T) wts[Y.offB[l] + j] = th[net.boff[l] + j];
+            for (int j = tid; j < wo; j += T) wts[Y.offB[l] + j] = __ldcg(th + net.boff[l] + j);
         }
-        for (int j = tid; j < Y.w[L - 1]; j += T) wts[Y.offW[L] + j] = th[net.woff[L] + j];
-        if (tid == 0) wts[Y.offB[L]] = th[net.boff[L]];
+        for (int j = tid; j < Y.w[L - 1]; j += T) wts[Y.offW[L] + j] = __ldcg(th + net.woff[L] + j);
+        if (tid == 0) wts[Y.offB[L]] = __ldcg(th + net.boff[L]);
     }
     __syncthreads();
 
