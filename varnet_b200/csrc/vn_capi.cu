@@ -206,10 +206,26 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
     // a tensor-core kernel of this step gave up on an mbarrier wait: its partial slabs are stale.  Publish NaN and leave
     // the weights alone, so the caller sees the failure in the very step it happened (the host also reads the flag).
     const bool bad = A.err != nullptr && *reinterpret_cast<const volatile int*>(A.err) != 0;
+    __shared__ double sh[32];
+    __shared__ double red[32][32];
     if (blockIdx.x + 1 < gridDim.x) {
         const int lane = threadIdx.x & 31;
-        const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (A.needGrad && idx < net.nparam) {
+        const bool patchMode = A.slotParam != nullptr;        // thread-per-point class: block = one 32-slot patch of the per-CTA slabs
+        const int wrp = threadIdx.x >> 5, nwrp = blockDim.x >> 5;
+        const int pslot = blockIdx.x * 32 + lane;
+        const int idx = patchMode ? __ldg(A.slotParam + pslot) : blockIdx.x * nwrp + wrp;
+        double s = 0.0;
+        // patch mode: warp w sums slabs w, w + nwrp, ... of the block's patch, one slot per lane: 256 contiguous bytes per load
+        // (one warp per parameter read 32 slabs per load, one 32-byte sector each)
+        if (patchMode && A.needGrad)
+            for (int c = wrp; c < A.nSlab; c += 8 * nwrp) {           // 8 loads in flight per lane, added in slab order
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = c + u * nwrp < A.nSlab ? __ldcg(A.slab + (size_t)(c + u * nwrp) * A.slabStride + pslot) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+        if (A.needGrad && idx >= 0 && idx < net.nparam) {
         // locate (layer, kind, i, j)
         int l = 0, isBias = 0, i = 0, j = 0;
         for (l = 0; l <= net.L; ++l) {
@@ -235,7 +251,10 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
                 slot[h] = pl.off_gw[l] + (r >> 1) * (2 * pl.NT) + 2 * tid + (r & 1);   // pair-interleaved slab
             }
         }
-        double s = 0.0;
+        if (patchMode) {
+            for (int c = wrp; c < A.nBic; c += nwrp)
+                for (int p = 0; p < nslot; ++p) s += __ldcg(A.partBic + (size_t)c * pl.psz + slot[p]);
+        } else {
         for (int c = lane; c < A.nVar; c += 32)
             for (int p = 0; p < nslot; ++p) s += __ldcg(A.partVar + (size_t)c * pl.psz + slot[p]);
         for (int c = lane; c < A.nBic; c += 32)
@@ -245,7 +264,17 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
             for (int c = lane; c < A.nSlab; c += 32) s += __ldcg(A.slab + (size_t)c * A.slabStride + sl);
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
+        }
+        }
+        if (patchMode) {                                       // warps of the block combined in fixed order by warp 0
+            red[wrp][lane] = s;
+            __syncthreads();
+            s = 0.0;
+            if (wrp == 0)
+                for (int k = 0; k < nwrp; ++k) s += red[k][lane];
+        }
+        if (A.needGrad && idx >= 0 && idx < net.nparam) {
+        if (patchMode ? wrp == 0 : lane == 0) {
             if (A.flat) s += A.flat[idx];
             const float g = bad ? __int_as_float(0x7fc00000) : (float)s;
             A.gbuf[idx] = g;
@@ -256,7 +285,6 @@ __global__ void vn_finalize_kernel(FinalArgs A) {
         }
         }
     } else {
-    __shared__ double sh[32];
     double v = 0.0;
     for (int k = threadIdx.x; k < A.nSeg; k += blockDim.x) v += __ldcg(A.segSum + k);
     const double segTot = block_sum(v, sh);
@@ -694,6 +722,10 @@ extern "C" int vn_create(const vn_config* cfg, vn_engine** out) {
                     e->tpp = true; e->tppCtas = ctas;
                     std::vector<int> slots((size_t)e->net.nparam);
                     vn_tpp_param_slots(e->net, e->tppLay, slots.data());
+                    // behind them the inverse map [npatch * 32]: parameter of a slab slot, -1 for padding (vn_finalize_kernel, patch mode)
+                    const size_t np0 = slots.size();
+                    slots.resize(np0 + (size_t)e->tppLay.npatch * 32, -1);
+                    for (size_t i = 0; i < np0; ++i) slots[np0 + slots[i]] = (int)i;
                     CK(e->tppSlot.ensure(slots.size() * sizeof(int)));
                     CK(cudaMemcpy(e->tppSlot.p, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
                 }
@@ -1656,6 +1688,7 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         if (needGrad && e->fused && e->useTpp) {          // the reduction kernel sums the patch slabs itself (no separate launch)
             f.nVar = 0; f.slab = e->partVar.as<double>(); f.slabSlot = e->tppSlot.as<int>();
             f.slabStride = e->tppLay.npatch * 32; f.nSlab = e->gridVar;
+            f.slotParam = e->tppSlot.as<int>() + e->net.nparam;             // inverse map behind the slots: block = patch
         }
         f.partBic = e->partBic.as<double>(); f.nBic = e->gridBic;
         f.segSum = segPtr; f.nSeg = nSeg;
@@ -1671,7 +1704,8 @@ static int run_loss(vn_engine* e, bool needGrad, const FedPlan* plan = nullptr, 
         }
         const int nb = needGrad ? (e->net.nparam + 3) / 4 : 0;          // one warp per parameter, 4 warps per block
         ProfScope ps(e, PK_FINAL);
-        vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
+        if (f.slotParam) vn_finalize_kernel<<<e->tppLay.npatch + 1, 1024, 0, st>>>(f);     // one 32-warp block per 32-slot patch
+        else vn_finalize_kernel<<<nb + 1, 128, 0, st>>>(f);
         CK(cudaGetLastError());
         e->launches++;
     }

@@ -883,6 +883,7 @@ struct FinalArgs {
     const double* partBic; int nBic;        // ... of the boundary/initial adjoint kernel
     const double* flat;                     // [nparam] already reduced variational gradient (vn_tc64 kernel), or nullptr
     const double* slab; const int* slabSlot; int slabStride, nSlab;   // or: per-CTA slabs [nSlab][slabStride] with parameter idx at slabSlot[idx] (vn_tpp kernel)
+    const int* slotParam;                   // slab mode, [nSlab slots]: parameter of a slot or -1 -> one block per 32-slot patch (coalesced slab reads)
     const double* segSum; int nSeg;         // partial sums of (detJ_i) R_i^2
     const float* detJ; int detJvec;
     const float* cj; unsigned int nbi, bDof; int timeDependent;
