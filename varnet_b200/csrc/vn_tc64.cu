@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
         // their second-order term), then abar_{l-1,s} = zbar_{l,s} W_l^T and gW_l += a_{l-1,s}^T zbar_{l,s}
         {
             float a0[CPT], dpre[CPT], apre[CPT], cross[CPT];
+            const bool L0MERGE = (K.coefPre & 4) != 0;
             bool gaStored = false;
             stash_get(stash, (L - 1) * S, p, c0, a0, polLast);
             stash_get(stash, (L - 1) * S + 1, p, c0, dpre, polLast);
@@ -817,7 +818,31 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                     } else {
                         // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
                         if (ln >= 0 && sn > 0) stash_get(stash, sn, p, c0, dpre, polLast);
-                        if (s > 0) {
+                        if (L0MERGE) {
+                            // zbar of tangent stream 1 + c waits in the (idle) operand columns of tensor memory and joins the column sum
+                            // of input row c: inpDim + 1 transposing warp reductions per tile instead of inpDim + S
+                            if (s > 0) {
+                                put_plain(tq + COL_OP + 64 * (s - 1) + c0, v);
+                                tmem_wait_st();
+                            } else {
+                                for (int c = 0; c < net.inpDim; ++c) {
+                                    const float xc = input(c);
+                                    float t[CPT];
+                                    if (c < S - 1) {
+                                        get_plain(tq + COL_OP + 64 * c + c0, t);
+#pragma unroll
+                                        for (int jj = 0; jj < CPT; ++jj) t[jj] = fmaf(xc, v[jj], t[jj]);
+                                    } else {
+#pragma unroll
+                                        for (int jj = 0; jj < CPT; ++jj) t[jj] = xc * v[jj];
+                                    }
+                                    const float r = warp_colsum(t, lane);
+                                    vec_add(L + 1 + c, r, first);
+                                }
+                                const float r = warp_colsum(v, lane);
+                                vec_add(0, r, first);
+                            }
+                        } else if (s > 0) {
                             const float r = warp_colsum(v, lane);
                             vec_add(L + 1 + (s - 1), r, first);
                         } else {
@@ -1548,7 +1573,7 @@ cudaError_t vn_tc64_launch(int S, int act, const TileArgs& a, const float* wimg,
     static const int fold = [] { const char* e = getenv("VARNET_B200_TC64_FOLD"); const int v = e ? atoi(e) : FOLD; return v > 0 ? v : FOLD; }();
     k.fold = fold;
     // bit 0: integrand coefficients requested at tile start; bit 1: MLP inputs staged in shared memory one tile ahead
-    { const char* ev = getenv("VARNET_B200_TC64_COEF"); const int m = ev ? atoi(ev) : 3; k.coefPre = (m < 0 || m > 3) ? 3 : m; }
+    { const char* ev = getenv("VARNET_B200_TC64_COEF"); const int m = ev ? atoi(ev) : 7; k.coefPre = (m < 0 || m > 7) ? 7 : m; }       // bit 0: coefficients, bit 1: inputs, bit 2: merged layer-0 column sums
     if (fwdOnly && !use_v1()) return cudaErrorNotSupported;
     static const bool timWanted = getenv("VARNET_B200_TC64_TIMING") != nullptr;
     if (timWanted && !use_v1()) {
