@@ -268,6 +268,10 @@ def test_train_steps_equals_single_steps():
     many = np.concatenate([b.train_steps(1e-3, 5), b.train_steps(1e-3, 32)])
     assert np.array_equal(one, many)
     assert np.array_equal(a.get_params(), b.get_params())
+    # the 32-step call went out as 16-step graphs whose kernel -> kernel edges are programmatic dependencies (griddepcontrol in the
+    # three kernels of the thread-per-point class): a runtime that refused them would fall back silently, so the flag is asserted
+    if os.environ.get("VARNET_B200_PDL", "1") != "0" and os.environ.get("VARNET_B200_MULTISTEP_GRAPH", "1") != "0":
+        assert "thread-per-point" in b.kernel_info() and b.kernel_info().rstrip().endswith("pdl=1"), b.kernel_info()
     a.close(); b.close()
     # the trainer's chunked epochs reproduce the per-epoch loop
     hist = {}
