@@ -817,7 +817,16 @@ __global__ void __launch_bounds__(NT, 1) tc64_var_kernel(const __grid_constant__
                         tmem_wait_st();
                     } else {
                         // layer 0: gb_0 = sum_p zbar_{0,0}; gW_0[c] = sum_p x_c zbar_{0,0} (+ sum_p zbar_{0,1+c} for the spatial inputs)
-                        if (ln >= 0 && sn > 0) stash_get(stash, sn, p, c0, dpre, polLast);
+                        // a_{0,sn} of the next tangent stream: recomputed from a_{0,0} (in a0) exactly as the forward sweep computed it
+                        // (act'(a_{0,0}) W_0[sn-1][:]: the same bits) instead of an exposed L2 round trip to the stash
+                        if (ln >= 0 && sn > 0) {
+                            if (L0MERGE) {
+#pragma unroll
+                                for (int jj = 0; jj < CPT; ++jj) dpre[jj] = act_d1<ACT>(a0[jj]) * W0s[(sn - 1) * W + c0 + jj];
+                            } else {
+                                stash_get(stash, sn, p, c0, dpre, polLast);
+                            }
+                        }
                         if (L0MERGE) {
                             // zbar of tangent stream 1 + c waits in the (idle) operand columns of tensor memory and joins the column sum
                             // of input row c: inpDim + 1 transposing warp reductions per tile instead of inpDim + S
