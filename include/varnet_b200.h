@@ -160,6 +160,14 @@ int vn_loss_grad_fed_f32(vn_engine* e, const float* Input, const float* gcoef, c
 int vn_loss_grad_fed_f64(vn_engine* e, const double* Input, const double* gcoef, const double* source, const double* N,
                          const double* dNt, int64_t nb, int32_t integNum, const double* integW, const double* detJ,
                          int32_t detJvec, float out[4]);
+/* Page-lock a caller-owned host array for direct DMA (cudaHostRegister, portable) / undo it.  The reference re-feeds the SAME NumPy
+ * arrays on every sess.run of an epoch loop (VarNetUtility.py:840-854 builds the dict once, :1044 runs it per step): once such an
+ * array is registered, vn_loss_grad_fed_* / vn_upload_* copy straight out of it (float64 over the bus, cast by the pack kernel)
+ * instead of casting it through pinned bounce buffers with host threads — which is what limits the fed step when several ranks
+ * share the host's cores.  The caller keeps the memory alive until vn_host_unregister.  Process-wide, no engine needed.
+ * vn_host_register returns 1 (not an error) when the range is already page-locked by its owner: do not unregister it. */
+int vn_host_register(const void* ptr, size_t bytes);
+int vn_host_unregister(const void* ptr);
 int vn_grad_buffer(vn_engine* e, void** device_ptr, int64_t* n_floats);
 int vn_get_grad(vn_engine* e, float* grad, int64_t n, float out[4]);
 int vn_get_scalars(vn_engine* e, float out[4]);     /* {loss, BCloss, ICloss, varLoss} of the gradient buffer; synchronises */

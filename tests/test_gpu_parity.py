@@ -315,6 +315,51 @@ def test_fed_step_overlapping_copies_equals_upload_then_step(feed_dtype):
 
 
 @pytest.mark.gpu
+def test_fed_step_from_registered_feed_arrays_is_bit_identical_to_the_staged_one():
+    """Feed arrays that show up a second time are page-locked in place (_capi.HostPins -> vn_host_register) and the fed step copies
+    them by DMA as float64, cast by the pack kernel, instead of casting them through bounce buffers with host threads: same
+    rounding (round-to-nearest-even on both sides), so loss, gradient and lossVec keep their bits; in-place edits of a registered
+    array are seen by the next step; release() unregisters."""
+    import ctypes as C
+    from varnet_b200._capi import Engine, HostPins
+    rng = np.random.RandomState(14)
+    dim, inpDim, lw, nb, q = 2, 3, [16, 16], 70000, 64                       # 4.48 M points = 2 chunks, 108 MB + 72 MB + 36 MB of float64
+    P = nb * q
+    X = rng.uniform(-1, 1, (P, inpDim)); G = rng.randn(P, dim); dNt = rng.randn(P, 1)
+    bX = rng.uniform(-1, 1, (500, inpDim)); bL = rng.randn(500, 1)
+    theta = go.glorot_init(inpDim, lw, seed=2)
+    eng = Engine(dim, inpDim, lw, "tanh", True)
+    eng.upload_bic(bX, bL, 300, 2.0)
+    eng.set_weights([3.0, 5.0, 7.0])
+
+    def step():
+        eng.set_params(theta)
+        eng.loss_grad_fed(X, G, None, None, dNt, [nb, q], None, 1.3e-6, False)
+        g = np.empty(eng.nparam, dtype=np.float32); o = np.empty(4, dtype=np.float32)
+        eng._check(eng.lib.vn_get_grad(eng._h, g.ctypes.data_as(C.POINTER(C.c_float)), g.size, o.ctypes.data_as(C.POINTER(C.c_float))))
+        return o.copy(), g, eng.get_lossvec()
+
+    pins = HostPins()
+    assert not pins.touch_group([X, G, dNt])                                 # first sighting: nothing is registered
+    staged = step()
+    assert pins.touch_group([X, G, dNt]) and pins.registered == 3            # second sighting: page-locked in place
+    assert pins.touch_group([X, G, dNt]) and pins.registered == 3
+    direct = step()
+    for a, b in zip(staged, direct):
+        assert np.array_equal(a, b)
+    X[:q] += 0.25                                                            # in-place edit of a registered array
+    edited = step()
+    assert not np.array_equal(edited[2][:1], direct[2][:1]) and np.array_equal(edited[2][1:], direct[2][1:])      # lossVec of test function 0 only
+    eng.synchronize()
+    pins.release()
+    assert pins.bytes == 0 and not pins.pins
+    again = step()                                                           # pageable again: the staged path, same bits
+    for a, b in zip(edited, again):
+        assert np.array_equal(a, b)
+    eng.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("integPnum,lw", [(2, [12, 20]), (3, [12, 20]), (2, [64, 64, 64, 64]), (2, [48, 64])])
 def test_device_generated_table_is_bit_identical_to_the_uploaded_one(integPnum, lw):
     """vn_generate_table_f64 (uniform mesh, constant coefficients, table built on the device from the mesh centres and

@@ -195,9 +195,28 @@ class Session:
             self._collect()
         except Exception:
             pass
+        pins = getattr(self, "_pins", None)
+        if pins:
+            for tw in self._o.compTowers:
+                if tw.engine is not None and hasattr(tw.engine, "synchronize"):
+                    tw.engine.synchronize()                         # no copy out of a registered array is in flight
+            pins.release()
         for tw in self._o.compTowers:
             if tw.engine is not None:
                 tw.engine.close()
+
+    def _host_pins(self):
+        """Registry of page-locked caller arrays (None when the engine is not the CUDA one, e.g. the test double)."""
+        if not hasattr(self, "_pins"):
+            self._pins = None
+            try:
+                from . import _capi
+                if any(isinstance(tw.engine, _capi.Engine) for tw in self._o.compTowers if tw.engine is not None):
+                    self._pins = _capi.HostPins()
+                    self._pins.sync = lambda: [tw.engine.synchronize() for tw in self._o.compTowers if tw.engine is not None]
+            except Exception:
+                self._pins = None
+        return self._pins
 
     # -- feed handling
     def _sync_feeds(self, feed, need_points=True, need_bic=True, defer_points=False, set_batch=True):
@@ -232,6 +251,12 @@ class Session:
                                 fd["intShape"], mat["integW"], mat["detJ"], bool(fd.get("detJvec", False)))
                         if defer_points and hasattr(eng, "loss_grad_fed"):
                             tw._pending_points = args               # uploaded by the step itself, copies overlapped (vn_loss_grad_fed)
+                            # arrays that are fed again and again (the reference's epoch loop) get page-locked in place on their
+                            # second step: direct DMA instead of the host-thread cast through bounce buffers (_capi.HostPins)
+                            pins = self._host_pins()
+                            if pins is not None:
+                                pins.touch_group([mat["Input"], mat["gcoef"], mat["dNt"]] +
+                                                 ([mat["source"], mat["N"]] if getattr(eng.cfg, "isSource", 0) else []))
                         else:
                             eng.upload_points(*args)
                         tok["points"] = t

@@ -1827,6 +1827,20 @@ extern "C" int vn_allreduce_grad(vn_engine* e) {
     e->launches++;
     return VN_OK;
 }
+extern "C" int vn_host_register(const void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(VN_E_INVALID, "null argument");
+    if (!is_pageable(ptr)) return 1;              // cudaHostAlloc / torch pinned memory / registered by someone else: usable as it is
+    const cudaError_t ce = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    if (ce == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 1; }       // page-locked by its owner: nothing to undo later
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(VN_E_CUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(ce)); }
+    return VN_OK;
+}
+extern "C" int vn_host_unregister(const void* ptr) {
+    if (!ptr) return fail(VN_E_INVALID, "null argument");
+    const cudaError_t ce = cudaHostUnregister(const_cast<void*>(ptr));
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(VN_E_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(ce)); }
+    return VN_OK;
+}
 extern "C" int vn_get_scalars(vn_engine* e, float out[4]) {
     if (!e || !out) return fail(VN_E_INVALID, "null argument");
     CK(cudaSetDevice(e->cfg.device));
