@@ -81,3 +81,19 @@ def test_a_refused_registration_switches_the_registry_off(monkeypatch):
     pins.touch_group([a])
     assert not pins.touch_group([a]) and pins.failed
     assert not pins.touch_group([a]) and len(lib.reg) == 1
+
+
+def test_a_recycled_address_is_not_a_second_sighting(monkeypatch):
+    """A feed that is rebuilt for every step (new arrays, the old ones freed) often lands on the same address: never registered."""
+    lib, pins = make(monkeypatch, cap_bytes=1 << 30, min_bytes=1000)
+    base = np.zeros(4000)
+
+    class View(np.ndarray):                           # distinct objects over the same memory = "a new array at the old address"
+        pass
+
+    for _ in range(4):
+        assert not pins.touch_group([base[:2000].view(View)])
+    assert lib.reg == []
+    keep = base[:2000].view(View)
+    assert not pins.touch_group([keep])
+    assert pins.touch_group([keep]) and len(lib.reg) == 1

@@ -5,6 +5,7 @@ missing or no CUDA device is visible the calls raise — they never fall back.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -175,12 +176,19 @@ class HostPins:
                 if k in self.pins:
                     self.pins[k][1] = self.clock
             return True
+        # "again" means the same array OBJECTS: a freed feed's address is often handed to the next one of the same size (large
+        # NumPy arrays are mmap'ed), which must not count as a second sighting of anything
         gkey = tuple(keys)
-        n = self.seen.get(gkey, 0) + 1
+        n, refs = self.seen.get(gkey, (0, ()))
+        if n and not (len(refs) == len(arrs) and all(r() is a for r, a in zip(refs, arrs))):
+            n = 0
         if len(self.seen) > 256:
             self.seen.clear()
-        self.seen[gkey] = n
-        if n < self.after:
+        try:
+            self.seen[gkey] = (n + 1, tuple(weakref.ref(a) for a in arrs))
+        except TypeError:
+            return False
+        if n + 1 < self.after:
             return False
         need = sum(a.nbytes for a, k in zip(arrs, keys) if k not in self.pins and k not in self.foreign)
         if need > self.cap:
