@@ -73,6 +73,23 @@ def test_feed_cache_semantics(shim):
     assert np.allclose(eng.feed["w"], [2., 3., 4.]) and eng.calls["upload_points"] == n_up
 
 
+def test_feed_token_sees_in_place_edits_on_its_sample():
+    """The cache key of a fed array: object identity + buffer + a strided sample of its values (bytes, so NaNs compare equal)."""
+    from varnet_b200.backend import _token
+    a = np.arange(10000, dtype=np.float64).reshape(2500, 4)
+    t0 = _token(a)
+    assert _token(a) == t0
+    a[0, 0] += 1.0
+    assert _token(a) != t0
+    t1 = _token(a)
+    a.reshape(-1)[(10000 // 63) * 17] = -5.0                     # an interior position of the sample
+    assert _token(a) != t1
+    t2 = _token(a)
+    a[-1, -1] = np.nan
+    assert _token(a) != t2 and _token(a) == _token(a)
+    assert _token(a.copy()) != _token(a)                          # another object is another feed
+
+
 def test_constructor_errors_match_reference_messages(shim):
     lossOpt = dict(isSource=False, integWflag=False)
     with pytest.raises(ValueError, match="unknown optimizer requested!"):
